@@ -1,0 +1,224 @@
+/*
+ * recombiner_b200.h -- C ABI of the B200-native RECOMBINER hot path.
+ *
+ * One shared object (recombiner_b200/librecombiner_b200.so, built for sm_100a).
+ * The reference (cambridge-mlg/RECOMBINER) has no FFI: its hot path is Python
+ * calling ATen.  Each entry point below therefore names the reference *Python*
+ * call site(s) it replaces (file:line relative to the reference checkout); the
+ * Python host mirror in recombiner_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; rcb_last_error() gives a
+ *    thread-local message.  Nothing here has a CPU fallback.
+ *  - all pointers are BORROWED DEVICE pointers (caller allocates outputs and
+ *    workspaces, the library never retains them past the call);
+ *  - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *    calls are asynchronous w.r.t. the host;
+ *  - float = f32, double = f64, int = int32; "rows" = datapoints or patches,
+ *    "item" = (row, MC sample) pair with index row*S + s.
+ */
+#ifndef RECOMBINER_B200_H
+#define RECOMBINER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rcb_stream_t;
+
+int rcb_version(void);
+const char* rcb_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * (a) fit path
+ * ------------------------------------------------------------------------- */
+
+/* Effective posterior -> reparameterised samples.
+ * Replaces test_model.py:286-303 (mask-mix, column un-permute, group->param
+ * gather, lpe draw) and utils.py:142-198 (hierarchical weight draw, one call per
+ * level).  For element (row n, MC sample s, parameter p):
+ *     q = g2p[p];  rr = row_map ? row_map[n] : n;  src row r = perm ? perm[rr*P + q] : rr
+ *     mu~ = loc*(1-m) + sample*m,  sigma~ = softplus(log_scale)/6*(1-m) + 1e-15*m
+ *     value = mu~ + sigma~ * eps
+ * p <  n_w : written (accumulate=0) or added (accumulate=1) to hw[(n*S+s)*ld_hw + p]
+ * p >= n_w : written to lpe[(n*S+s)*n_l + (p-n_w)]            (lpe may be NULL)
+ * eps: explicit tensors (eps_w (rows,S,n_w), eps_l (S,rows,n_l)) when non-NULL,
+ * else counter-based Philox4x32-10 keyed by (seed, step, tensor_id, element). */
+typedef struct {
+  const float* loc;        /* (src_rows, P) group order */
+  const float* log_scale;  /* (src_rows, P) */
+  const float* mask;       /* (src_rows, P) or NULL */
+  const float* sample;     /* (src_rows, P) or NULL */
+  const int* g2p;          /* (P) group_to_param, or NULL = identity */
+  const int* perm;         /* (src_rows, P) per-column row permutation, or NULL */
+  const int* row_map;      /* (rows) level-2/3 expansion: row -> src row, or NULL */
+  const float* eps_w;      /* (rows, S, n_w) or NULL */
+  const float* eps_l;      /* (S, rows, n_l) or NULL */
+  float* hw;               /* (rows*S, ld_hw) */
+  float* lpe;              /* (rows*S, n_l) or NULL */
+  int64_t seed;
+  int64_t row_offset;      /* global index of row 0 (multi-GPU shards) */
+  int rows, S, P, n_w, n_l, ld_hw;
+  int step, tensor_id, accumulate;
+} rcb_sample_args;
+int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
+
+/* C[M,N] = A[M,K] @ B[K,N] (+bias[n % bias_mod], LeakyReLU 0.01 if act=1).
+ * Replaces the shared-operand `mm` of the linear reparameterisation
+ * (test_model.py:348-349, prior_model.py:173-174) and its backward, and the
+ * first upsampler stage on small latent grids (prior_model.py:48-50) once the
+ * nearest-upsample + conv is folded into a dense map (rcb_fold_dense).
+ * lda/ldb/ldc in elements, all multiples of 4; trans_a: A given as [K,M]. */
+int rcb_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             int M, int N, int K, const float* bias, int bias_mod, int act,
+             int trans_a, int accumulate, rcb_stream_t stream);
+
+/* Geometry of one nearest-upsample + 'same' conv stage on a channel-last grid
+ * (1-D signals use h=1, fy=1, ky=1). prior_model.py:29-45. */
+typedef struct {
+  int h, w;        /* source grid */
+  int fy, fx;      /* nearest-upsample factors */
+  int ky, kx;      /* kernel extent (odd), padding (k-1)/2 */
+  int ic, oc;
+} rcb_upconv_geom;
+
+/* Fold nearest-upsample into the conv taps (polyphase form): for phase (ry,rx)
+ * and tap (ty,tx) in {0,1}^2,
+ *   w_eff[ry][rx][ty][tx][ic][oc] = sum of w[oc][ic][ky][kx] over the kernel taps
+ *   that land on source offset (by[ry]+ty, bx[rx]+tx).
+ * w: torch conv layout (oc, ic, ky, kx).  w_eff_t is the [..][oc][ic] transpose
+ * used by the data-gradient kernel. */
+int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_eff, float* w_eff_t,
+                  rcb_stream_t stream);
+/* Dense fold for tiny grids: m[(sy,sx,ic)][(oy,ox,oc)], and its transpose. */
+int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m, float* m_t,
+                   rcb_stream_t stream);
+
+/* out[item, y*fy+ry, x*fx+rx, :] = act(bias + sum_taps w_eff . src[item, y+.., x+.., :])
+ * Replaces prior_model.py:52-57 (up2/conv2/act2, up3/conv3) with the upsample
+ * never materialised. */
+int rcb_upconv_fwd(const float* src, const float* w_eff, const float* bias, float* out,
+                   const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
+/* d_src = (transpose of the above)(d_out) [* lrelu'(src_act) if src_act != NULL] */
+int rcb_upconv_bwd(const float* d_out, const float* w_eff_t, const float* src_act, float* d_src,
+                   const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+
+/* Fused per-item SIREN MLP (test_model.py:347-355 + loss :624-627 + their
+ * autograd backward).  mode 0: forward, writes y_pred.  mode 1: forward +
+ * squared-error + backward with dy = coef*(y_pred - y).  mode 2: forward +
+ * backward with dy read from `dy`.  Activations never leave shared memory. */
+typedef struct {
+  const float* wt;      /* (items, ld_w) per-item weights, layer-major, bias first */
+  const float* xt;      /* (x_rows, n_f, pix) Fourier features, transposed */
+  const float* pe;      /* (items, pix, 16) */
+  const float* y;       /* (rows, pix, out) targets (mode 1) */
+  const float* dy;      /* (items, pix, out) (mode 2) */
+  float* y_pred;        /* (items, pix, out) (mode 0) */
+  float* d_pe;          /* (items, pix, 16) (modes 1,2) */
+  float* d_wt;          /* (items, ld_w)    (modes 1,2) */
+  float* sqerr;         /* (items) sum of squared error (mode 1) */
+  int64_t x_row_stride; /* 0 if all rows share one x */
+  int items, S, pix, n_f, out, ld_w, mode;
+  float coef, w0;
+} rcb_mlp_args;
+int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
+
+/* Gradient reduction over MC samples + beta-weighted closed-form KL gradient
+ * (+ fused Adam).  Replaces the autograd backward of test_model.py:289-303,
+ * calculate_kl :357-377 and Adam.step (:635).  Group-order element (r,q):
+ *   g_mu  = (1-m) * sum_s d[n,s,p]        + beta*(mu-mu_p)/sig_p^2
+ *   g_rho = ((1-m) * sum_s d[n,s,p]*eps   + beta*(sig/sig_p^2 - 1/sig)) * sigmoid(rho)/6
+ * with p = p2g[q], n = inverse-permuted row.  adam=1 updates loc/log_scale in
+ * place (torch.optim.Adam arithmetic); adam=0 writes g_loc/g_log_scale.
+ * kl_out (double[1], optional) += sum beta*KL. */
+typedef struct {
+  float* loc; float* log_scale;          /* (src_rows, P) */
+  const float* mask;                     /* or NULL */
+  const float* p_loc; const float* p_log_scale;  /* (P) */
+  const float* beta;                     /* (src_rows, G) or NULL -> beta_scalar */
+  const int* group_idx;                  /* (P) */
+  const int* p2g;                        /* (P) param_to_group or NULL */
+  const int* perm_inv;                   /* (src_rows,P) or NULL */
+  const int* row_children;               /* level-2/3: (src_rows, n_children) rows fed by src row; NULL = self */
+  const float* d_hw;                     /* (rows*S, ld_hw) or NULL */
+  const float* d_lpe;                    /* (rows*S, n_l) or NULL */
+  const float* eps_w; const float* eps_l;
+  float* g_loc; float* g_log_scale;      /* adam=0 outputs */
+  float* m1_loc; float* v_loc; float* m1_ls; float* v_ls;  /* Adam state */
+  double* kl_out;
+  int64_t seed; int64_t row_offset;
+  int src_rows, rows, n_children, S, P, n_w, n_l, ld_hw, G;
+  int step, tensor_id, adam;
+  /* Adam: step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are computed by the
+   * host in f64 exactly as torch.optim.Adam does, then passed as f32. */
+  float adam_step_size, adam_bc2_sqrt, b1, b2, adam_eps, beta_scalar, grad_scale;
+} rcb_update_args;
+int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream);
+
+/* Per-(row, block) KL in nats, f64 accumulation (test_model.py:384-388). */
+int rcb_group_kl(const float* loc, const float* log_scale, const float* p_loc,
+                 const float* p_log_scale, const int* group_start, const int* group_end,
+                 double* kl, int rows, int P, int G, rcb_stream_t stream);
+/* Per-block beta annealing (test_model.py:404-413). coded: uint8 (rows,G). */
+int rcb_anneal_beta(float* beta, const double* kl, const uint8_t* coded, int rows, int G,
+                    double step, double upper, double lower, double bits, rcb_stream_t stream);
+/* Largest-KL not-yet-coded block per row (test_model.py:809-817). */
+int rcb_pick_block(const double* kl, const uint8_t* coded, int* block, int rows, int G,
+                   rcb_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (b) relative entropy coding
+ * ------------------------------------------------------------------------- */
+
+/* Standard-normal candidate table, dimension-major: table[(d)*n + k] =
+ * f32(ndtri(f64(sobol_k,d))) clamped to +-100, for n candidates (n <= 2^30).
+ * Replaces get_sobol_normal_sample (test_model.py:493-498): SobolEngine.draw
+ * by random access from the engine's scrambled state (shift (D), words (D,30),
+ * both int64 as torch stores them) + Cephes ndtri in f64. */
+int rcb_rec_table(const int64_t* shift, const int64_t* words, float* table, int D, int n,
+                  rcb_stream_t stream);
+
+/* Batched A* / Gumbel-max coding of n_pairs (row, block) pairs
+ * (sample_group + compress_group, test_model.py:501-533,586-595):
+ *   log_w_k = sum_d [log q(z_kd) - log p(z_kd)] + g_k,  z_kd = mu_p + sig_p * s_kd  (f64)
+ *   idx = first argmax_k.  If apply!=0: sample[row, start:end] = f32(z_idx),
+ *   mask[...] = 1, beta[row, block] = 0, coded[row, block] = 1, idx_out[row*G+block] = idx.
+ * tables: per-block pointer table (G entries) into dimension-major tables.
+ * q_scale/p_scale are standard deviations (already softplus/6). */
+typedef struct {
+  const int* pair_row; const int* pair_block;   /* (n_pairs) */
+  const float* q_loc; const float* q_scale;     /* (rows, P) group order */
+  const float* p_loc; const float* p_scale;     /* (P) */
+  const int* group_start; const int* group_end; /* (G) */
+  const float* const* tables;                   /* (G) device array of device pointers */
+  const double* gumbel;                         /* (n_cand) */
+  int* idx_out;                                 /* apply: (rows,G) else (n_pairs) */
+  float* z_out;                                 /* apply=0: (n_pairs, max_D) or NULL */
+  double* logw_out;                             /* (n_pairs, n_cand) or NULL */
+  float* sample; float* mask; float* beta; uint8_t* coded;   /* apply targets */
+  int n_pairs, P, G, n_cand, max_D, apply;
+} rcb_rec_args;
+int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream);
+
+/* Receiver side: regenerate z for (row, block, idx) -> sample[row, start:end]. */
+int rcb_rec_decode(const int* pair_row, const int* pair_block, const int* idx,
+                   const float* p_loc, const float* p_scale, const int* group_start,
+                   const int* group_end, const float* const* tables, float* sample,
+                   float* mask, int n_pairs, int P, int n_cand, rcb_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (c) prior EM statistics (main_prior_training.py:157-172)
+ * ------------------------------------------------------------------------- */
+/* stats[0:P] = sum_n mu, [P:2P] = sum_n mu^2, [2P:3P] = sum_n sigma^2 (f64). */
+int rcb_prior_suffstats(const float* loc, const float* log_scale, double* stats, int rows, int P,
+                        rcb_stream_t stream);
+/* mu_p = s0/N; sigma_p = sqrt(s2/N + (s1 - N mu_p^2)/(N-1)) from (all-reduced) stats. */
+int rcb_prior_from_stats(const double* stats, float* p_loc, float* p_scale, int64_t n_total, int P,
+                         rcb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECOMBINER_B200_H */

@@ -1,0 +1,127 @@
+"""ctypes binding of librecombiner_b200.so (the C ABI in include/recombiner_b200.h).
+
+There is no CPU fallback: importing the kernels without the built library, or
+calling them without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librecombiner_b200.so")
+
+P = C.c_void_p
+I32 = C.c_int
+I64 = C.c_int64
+F32 = C.c_float
+F64 = C.c_double
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("loc", "log_scale", "mask", "sample", "g2p", "perm", "row_map",
+                                 "eps_w", "eps_l", "hw", "lpe")] + \
+               [("seed", I64), ("row_offset", I64)] + \
+               [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate")]
+
+
+class UpconvGeom(C.Structure):
+    _fields_ = [(n, I32) for n in ("h", "w", "fy", "fx", "ky", "kx", "ic", "oc")]
+
+
+class MlpArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("wt", "xt", "pe", "y", "dy", "y_pred", "d_pe", "d_wt", "sqerr")] + \
+               [("x_row_stride", I64)] + \
+               [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode")] + \
+               [("coef", F32), ("w0", F32)]
+
+
+class UpdateArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("loc", "log_scale", "mask", "p_loc", "p_log_scale", "beta", "group_idx", "p2g",
+                                 "perm_inv", "row_children", "d_hw", "d_lpe", "eps_w", "eps_l", "g_loc",
+                                 "g_log_scale", "m1_loc", "v_loc", "m1_ls", "v_ls", "kl_out")] + \
+               [("seed", I64), ("row_offset", I64)] + \
+               [(n, I32) for n in ("src_rows", "rows", "n_children", "S", "P", "n_w", "n_l", "ld_hw", "G",
+                                   "step", "tensor_id", "adam")] + \
+               [(n, F32) for n in ("adam_step_size", "adam_bc2_sqrt", "b1", "b2", "adam_eps", "beta_scalar",
+                                   "grad_scale")]
+
+
+class RecArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("pair_row", "pair_block", "q_loc", "q_scale", "p_loc", "p_scale", "group_start",
+                                 "group_end", "tables", "gumbel", "idx_out", "z_out", "logw_out", "sample", "mask",
+                                 "beta", "coded")] + \
+               [(n, I32) for n in ("n_pairs", "P", "G", "n_cand", "max_D", "apply")]
+
+
+STRUCTS = {"rcb_sample_args": SampleArgs, "rcb_upconv_geom": UpconvGeom, "rcb_mlp_args": MlpArgs,
+           "rcb_update_args": UpdateArgs, "rcb_rec_args": RecArgs}
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "rcb_version": [],
+    "rcb_last_error": [],
+    "rcb_fit_sample": [C.POINTER(SampleArgs), P],
+    "rcb_gemm": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, I32, P],
+    "rcb_fold_poly": [P, C.POINTER(UpconvGeom), P, P, P],
+    "rcb_fold_dense": [P, C.POINTER(UpconvGeom), P, P, P],
+    "rcb_upconv_fwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
+    "rcb_upconv_bwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
+    "rcb_mlp": [C.POINTER(MlpArgs), P],
+    "rcb_fit_update": [C.POINTER(UpdateArgs), P],
+    "rcb_group_kl": [P, P, P, P, P, P, P, I32, I32, I32, P],
+    "rcb_anneal_beta": [P, P, P, I32, I32, F64, F64, F64, F64, P],
+    "rcb_pick_block": [P, P, P, I32, I32, P],
+    "rcb_rec_table": [P, P, P, I32, I32, P],
+    "rcb_rec_encode": [C.POINTER(RecArgs), P],
+    "rcb_rec_decode": [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, P],
+    "rcb_prior_suffstats": [P, P, P, I32, I32, P],
+    "rcb_prior_from_stats": [P, P, P, I64, I32, P],
+}
+_RESTYPES = {"rcb_last_error": C.c_char_p}
+
+_lib = None
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building nothing: see recombiner_b200._build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KernelError(
+            f"{LIB_PATH} is missing: build it with `python -m recombiner_b200._build` "
+            "(the sm_100a CUDA extension is the only implementation; there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().rcb_last_error().decode("utf-8", "replace")
+        raise KernelError(f"{what or 'librecombiner_b200'} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise KernelError("librecombiner_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise KernelError("non-contiguous tensor passed to a kernel")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

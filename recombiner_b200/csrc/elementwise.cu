@@ -1,0 +1,292 @@
+// HBM-bound kernels of the fit path: reparameterised sampling, sample-reduction +
+// KL gradient + Adam, per-block KL sums, beta annealing, block selection, and the
+// EM sufficient statistics of prior training.
+#include "common.cuh"
+
+namespace rcb {
+
+// ----------------------------------------------------------------- sampling --
+// grid: (ceil(P/256), rows).  One thread = one (row, parameter); loops over S.
+__global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (p >= a.P) return;
+  const int q = a.g2p ? a.g2p[p] : p;
+  int r = a.row_map ? a.row_map[n] : n;
+  if (a.perm) r = a.perm[(int64_t)r * a.P + q];
+  const int64_t e = (int64_t)r * a.P + q;
+  const float m = a.mask ? a.mask[e] : 0.f;
+  float mu = a.loc[e] * (1.f - m);
+  if (a.sample) mu += a.sample[e] * m;
+  const float sig = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
+  const int64_t gn = a.row_offset + n;
+  if (p < a.n_w) {
+    for (int s = 0; s < a.S; ++s) {
+      float eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
+                          : philox_normal(a.seed, a.step, a.tensor_id, (uint64_t)((gn * a.S + s) * a.n_w + p));
+      float v = fmaf(sig, eps, mu);
+      float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
+      *dst = a.accumulate ? *dst + v : v;
+    }
+  } else if (a.lpe) {
+    const int l = p - a.n_w;
+    for (int s = 0; s < a.S; ++s) {
+      float eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
+                          : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
+      a.lpe[((int64_t)n * a.S + s) * a.n_l + l] = fmaf(sig, eps, mu);
+    }
+  }
+}
+
+// ------------------------------------------- gradient reduction + KL + Adam --
+// grid: (ceil(P/256), src_rows).  One thread = one stored (row, group-order column).
+__global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  float kl_term = 0.f;
+  if (q < a.P) {
+    const int64_t e = (int64_t)r * a.P + q;
+    const int p = a.p2g ? a.p2g[q] : q;
+    const int rr = a.perm_inv ? a.perm_inv[e] : r;        // row of this level in parameter order
+    const float mu = a.loc[e], rho = a.log_scale[e];
+    const float m = a.mask ? a.mask[e] : 0.f;
+    const float sig = std_transform(rho);
+    // ---- reduce the per-sample gradients that this parameter produced
+    float d_mu = 0.f, d_sig = 0.f;
+    const bool is_w = p < a.n_w;
+    const float* src = is_w ? a.d_hw : a.d_lpe;
+    if (src && m != 1.f) {
+      const int nch = a.row_children ? a.n_children : 1;
+      for (int c = 0; c < nch; ++c) {
+        const int n = a.row_children ? a.row_children[(int64_t)rr * a.n_children + c] : rr;
+        const int64_t gn = a.row_offset + n;
+        for (int s = 0; s < a.S; ++s) {
+          float d, eps;
+          if (is_w) {
+            d = src[((int64_t)n * a.S + s) * a.ld_hw + p];
+            eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
+                          : philox_normal(a.seed, a.step, a.tensor_id, (uint64_t)((gn * a.S + s) * a.n_w + p));
+          } else {
+            const int l = p - a.n_w;
+            d = src[((int64_t)n * a.S + s) * a.n_l + l];
+            eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
+                          : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
+          }
+          d_mu += d;
+          d_sig = fmaf(d, eps, d_sig);
+        }
+      }
+      d_mu *= a.grad_scale * (1.f - m);
+      d_sig *= a.grad_scale * (1.f - m);
+    }
+    // ---- closed-form KL(q||p) and its gradient, weighted by the block's beta
+    const float beta = a.beta ? a.beta[(int64_t)r * a.G + a.group_idx[q]] : a.beta_scalar;
+    const float mu_p = a.p_loc[q], sig_p = std_transform(a.p_log_scale[q]);
+    const float inv_vp = 1.f / (sig_p * sig_p);
+    const float dm = mu - mu_p;
+    const float ratio = sig / sig_p;
+    const float vr = ratio * ratio;
+    const float t1 = (dm / sig_p) * (dm / sig_p);
+    kl_term = beta * 0.5f * (vr + t1 - 1.f - logf(vr));
+    float g_mu = d_mu + beta * dm * inv_vp;
+    float g_sig = d_sig + beta * (sig * inv_vp - 1.f / sig);
+    float g_rho = g_sig * std_transform_grad(rho);
+    if (a.adam) {
+      const float step_size = a.adam_step_size, bc2s = a.adam_bc2_sqrt;
+      float m1 = a.m1_loc[e], v = a.v_loc[e];
+      m1 = m1 + (g_mu - m1) * (1.f - a.b1);
+      v = v * a.b2 + (1.f - a.b2) * g_mu * g_mu;
+      a.m1_loc[e] = m1; a.v_loc[e] = v;
+      a.loc[e] = mu - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
+      m1 = a.m1_ls[e]; v = a.v_ls[e];
+      m1 = m1 + (g_rho - m1) * (1.f - a.b1);
+      v = v * a.b2 + (1.f - a.b2) * g_rho * g_rho;
+      a.m1_ls[e] = m1; a.v_ls[e] = v;
+      a.log_scale[e] = rho - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
+    } else {
+      a.g_loc[e] = g_mu;
+      a.g_log_scale[e] = g_rho;
+    }
+  }
+  if (a.kl_out) {
+    __shared__ float red[8];
+    float s = warp_sum(kl_term);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += (double)red[w];
+      atomicAdd(a.kl_out, t);
+    }
+  }
+}
+
+// ----------------------------------------------------------- per-block KL ----
+// grid: rows; one warp per block, lanes stride the block's contiguous columns.
+__global__ void __launch_bounds__(256) group_kl_kernel(const float* __restrict__ loc, const float* __restrict__ log_scale,
+                                                       const float* __restrict__ p_loc, const float* __restrict__ p_log_scale,
+                                                       const int* __restrict__ gs, const int* __restrict__ ge,
+                                                       double* __restrict__ kl, int P, int G) {
+  const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int g = warp; g < G; g += 8) {
+    double acc = 0.0;
+    for (int q = gs[g] + lane; q < ge[g]; q += 32) {
+      const int64_t e = (int64_t)r * P + q;
+      float sig = std_transform(log_scale[e]), sig_p = std_transform(p_log_scale[q]);
+      float ratio = sig / sig_p, vr = ratio * ratio;
+      float d = (loc[e] - p_loc[q]) / sig_p;
+      acc += (double)(0.5f * (vr + d * d - 1.f - logf(vr)));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) kl[(int64_t)r * G + g] = acc;
+  }
+}
+
+__global__ void anneal_kernel(float* __restrict__ beta, const double* __restrict__ kl, const uint8_t* __restrict__ coded,
+                              int64_t total, double step, double upper, double lower, double bits) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (coded && coded[i]) return;
+  const double b = kl[i] / 0.6931471805599453;
+  float v = beta[i];
+  const float factor = (float)(1.0 + step);   // f64 1+step, then .float() (test_model.py:407,409)
+  if (b > bits + upper) v = v * factor;
+  if (b <= bits - lower) v = v / factor;
+  beta[i] = fminf(fmaxf(v, 0.f), 10000.f);
+}
+
+// one warp per row: first index of the largest KL among not-yet-coded blocks
+__global__ void pick_block_kernel(const double* __restrict__ kl, const uint8_t* __restrict__ coded, int* __restrict__ block,
+                                  int rows, int G) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double best = -1e300;
+  int bi = 0x7fffffff;
+  for (int g = lane; g < G; g += 32) {
+    double v = coded[(int64_t)r * G + g] ? -1e10 : kl[(int64_t)r * G + g] / 0.6931471805599453;
+    if (v > best) { best = v; bi = g; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) block[r] = bi;
+}
+
+// ------------------------------------------------------ EM prior statistics --
+// grid: (ceil(P/128), row chunks); f64 partial sums added with atomics.
+__global__ void __launch_bounds__(128) suffstats_kernel(const float* __restrict__ loc, const float* __restrict__ log_scale,
+                                                        double* __restrict__ stats, int rows, int P, int rows_per_block) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int r = r0; r < r1; ++r) {
+    const int64_t e = (int64_t)r * P + p;
+    float mu = loc[e], sg = std_transform(log_scale[e]);
+    s0 += (double)mu;
+    s1 += (double)mu * (double)mu;
+    s2 += (double)(sg * sg);
+  }
+  atomicAdd(stats + p, s0);
+  atomicAdd(stats + P + p, s1);
+  atomicAdd(stats + 2 * (int64_t)P + p, s2);
+}
+
+__global__ void prior_from_stats_kernel(const double* __restrict__ stats, float* __restrict__ p_loc,
+                                        float* __restrict__ p_scale, double n, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double mean = stats[p] / n;
+  const double var_mu = (stats[P + p] - n * mean * mean) / (n - 1.0);   // unbiased, main_prior_training.py:158
+  const double v = stats[2 * (int64_t)P + p] / n + var_mu;
+  p_loc[p] = (float)mean;
+  p_scale[p] = (float)sqrt(v > 0.0 ? v : 0.0);
+}
+
+}  // namespace rcb
+
+using namespace rcb;
+
+extern "C" int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream) {
+  RCB_CHECK_ARG(a != nullptr, "rcb_fit_sample: null args");
+  RCB_CHECK_ARG(a->loc && a->log_scale && a->hw, "rcb_fit_sample: null tensor");
+  RCB_CHECK_ARG(a->rows > 0 && a->S > 0 && a->P > 0, "rcb_fit_sample: empty problem");
+  RCB_CHECK_ARG(a->n_w + a->n_l == a->P || (a->n_l == 0 && a->n_w == a->P), "rcb_fit_sample: n_w+n_l != P");
+  RCB_CHECK_ARG(a->ld_hw >= a->n_w, "rcb_fit_sample: ld_hw too small");
+  RCB_CHECK_ARG(a->rows <= 65535, "rcb_fit_sample: at most 65535 rows per call");
+  dim3 grid(ceil_div(a->P, 256), a->rows);
+  sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  RCB_CHECK_LAUNCH("rcb_fit_sample");
+  return 0;
+}
+
+extern "C" int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream) {
+  RCB_CHECK_ARG(a != nullptr, "rcb_fit_update: null args");
+  RCB_CHECK_ARG(a->loc && a->log_scale && a->p_loc && a->p_log_scale, "rcb_fit_update: null tensor");
+  RCB_CHECK_ARG(a->beta == nullptr || a->group_idx != nullptr, "rcb_fit_update: per-block beta needs group_idx");
+  RCB_CHECK_ARG(a->src_rows > 0 && a->src_rows <= 65535 && a->P > 0, "rcb_fit_update: bad shape");
+  if (a->adam) {
+    RCB_CHECK_ARG(a->m1_loc && a->v_loc && a->m1_ls && a->v_ls && a->adam_bc2_sqrt > 0.f, "rcb_fit_update: Adam state missing");
+  } else {
+    RCB_CHECK_ARG(a->g_loc && a->g_log_scale, "rcb_fit_update: gradient outputs missing");
+  }
+  dim3 grid(ceil_div(a->P, 256), a->src_rows);
+  update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  RCB_CHECK_LAUNCH("rcb_fit_update");
+  return 0;
+}
+
+extern "C" int rcb_group_kl(const float* loc, const float* log_scale, const float* p_loc, const float* p_log_scale,
+                            const int* group_start, const int* group_end, double* kl, int rows, int P, int G,
+                            rcb_stream_t stream) {
+  RCB_CHECK_ARG(loc && log_scale && p_loc && p_log_scale && group_start && group_end && kl, "rcb_group_kl: null tensor");
+  if (rows <= 0 || G <= 0) return 0;
+  group_kl_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(loc, log_scale, p_loc, p_log_scale, group_start, group_end, kl, P, G);
+  RCB_CHECK_LAUNCH("rcb_group_kl");
+  return 0;
+}
+
+extern "C" int rcb_anneal_beta(float* beta, const double* kl, const uint8_t* coded, int rows, int G, double step,
+                               double upper, double lower, double bits, rcb_stream_t stream) {
+  RCB_CHECK_ARG(beta && kl, "rcb_anneal_beta: null tensor");
+  int64_t total = (int64_t)rows * G;
+  if (total <= 0) return 0;
+  anneal_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(beta, kl, coded, total, step, upper, lower, bits);
+  RCB_CHECK_LAUNCH("rcb_anneal_beta");
+  return 0;
+}
+
+extern "C" int rcb_pick_block(const double* kl, const uint8_t* coded, int* block, int rows, int G, rcb_stream_t stream) {
+  RCB_CHECK_ARG(kl && coded && block, "rcb_pick_block: null tensor");
+  if (rows <= 0) return 0;
+  pick_block_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(kl, coded, block, rows, G);
+  RCB_CHECK_LAUNCH("rcb_pick_block");
+  return 0;
+}
+
+extern "C" int rcb_prior_suffstats(const float* loc, const float* log_scale, double* stats, int rows, int P,
+                                   rcb_stream_t stream) {
+  RCB_CHECK_ARG(loc && log_scale && stats, "rcb_prior_suffstats: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 3 * (size_t)P, st);
+  if (e != cudaSuccess) { set_error("rcb_prior_suffstats: memset failed: %s", cudaGetErrorString(e)); return -1; }
+  if (rows <= 0) return 0;
+  const int rpb = 64;
+  dim3 grid(ceil_div(P, 128), ceil_div(rows, rpb));
+  suffstats_kernel<<<grid, 128, 0, st>>>(loc, log_scale, stats, rows, P, rpb);
+  RCB_CHECK_LAUNCH("rcb_prior_suffstats");
+  return 0;
+}
+
+extern "C" int rcb_prior_from_stats(const double* stats, float* p_loc, float* p_scale, int64_t n_total, int P,
+                                    rcb_stream_t stream) {
+  RCB_CHECK_ARG(stats && p_loc && p_scale, "rcb_prior_from_stats: null tensor");
+  RCB_CHECK_ARG(n_total >= 2, "rcb_prior_from_stats: need at least 2 rows for the unbiased variance");
+  prior_from_stats_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(stats, p_loc, p_scale, (double)n_total, P);
+  RCB_CHECK_LAUNCH("rcb_prior_from_stats");
+  return 0;
+}

@@ -1,0 +1,150 @@
+// Plain GEMM, weight folding and polyphase up-convolution entry points.
+#include "gemm_engine.cuh"
+
+namespace rcb {
+
+static int make_geom(const rcb_upconv_geom* g, PolyGeom* out) {
+  RCB_CHECK_ARG(g != nullptr, "upconv: null geometry");
+  RCB_CHECK_ARG(g->h > 0 && g->w > 0 && g->fy > 0 && g->fx > 0, "upconv: bad grid/factors");
+  RCB_CHECK_ARG((g->ky & 1) && (g->kx & 1), "upconv: kernel extents must be odd");
+  RCB_CHECK_ARG(g->ic % 16 == 0 && g->oc % 16 == 0, "upconv: channels must be multiples of 16");
+  int py = (g->ky - 1) / 2, px = (g->kx - 1) / 2;
+  RCB_CHECK_ARG(py < g->fy || py == 0, "upconv: padding %d must be < factor %d", py, g->fy);
+  RCB_CHECK_ARG(px < g->fx || px == 0, "upconv: padding %d must be < factor %d", px, g->fx);
+  out->h = g->h; out->w = g->w; out->fy = g->fy; out->fx = g->fx; out->py = py; out->px = px;
+  out->Ty = (py == 0) ? 1 : 2;
+  out->Tx = (px == 0) ? 1 : 2;
+  out->ic = g->ic; out->oc = g->oc;
+  return 0;
+}
+
+// tap index in {0,1} of kernel position kk for phase r (or -1 if it falls off the
+// source grid never -- folding is border-agnostic; borders are handled by the
+// zero-padded gather).
+__device__ __forceinline__ int tap_of(int r, int kk, int p, int f) {
+  int num = r + kk - p;                       // offset on the upsampled grid
+  int off = (num >= 0) ? num / f : -((-num + f - 1) / f);   // floor division
+  int base = r < p ? -1 : 0;
+  return off - base;
+}
+
+__global__ void fold_poly_kernel(const float* __restrict__ w, PolyGeom g, int ky, int kx,
+                                 float* __restrict__ w_eff, float* __restrict__ w_eff_t) {
+  int64_t total = (int64_t)g.fy * g.fx * g.Ty * g.Tx * g.ic * g.oc;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int o = e % g.oc; int64_t r = e / g.oc;
+    int c = r % g.ic; r /= g.ic;
+    int tx = r % g.Tx; r /= g.Tx;
+    int ty = r % g.Ty; r /= g.Ty;
+    int rx = r % g.fx; int ry = r / g.fx;
+    float s = 0.f;
+    for (int a = 0; a < ky; ++a) {
+      if (tap_of(ry, a, g.py, g.fy) != ty) continue;
+      for (int b = 0; b < kx; ++b) {
+        if (tap_of(rx, b, g.px, g.fx) != tx) continue;
+        s += w[(((int64_t)o * g.ic + c) * ky + a) * kx + b];
+      }
+    }
+    w_eff[e] = s;
+    if (w_eff_t) {
+      int64_t seg = ((((int64_t)ry * g.fx + rx) * g.Ty + ty) * g.Tx + tx);
+      w_eff_t[(seg * g.oc + o) * g.ic + c] = s;
+    }
+  }
+}
+
+__global__ void fold_dense_kernel(const float* __restrict__ w, PolyGeom g, int ky, int kx,
+                                  float* __restrict__ m, float* __restrict__ m_t) {
+  int H = g.h * g.fy, W = g.w * g.fx;
+  int64_t rows = (int64_t)g.h * g.w * g.ic, cols = (int64_t)H * W * g.oc;
+  int64_t total = rows * cols;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t col = e % cols, row = e / cols;
+    int o = col % g.oc; int64_t t = col / g.oc;
+    int ox = t % W, oy = t / W;
+    int c = row % g.ic; t = row / g.ic;
+    int sx = t % g.w, sy = t / g.w;
+    float s = 0.f;
+    for (int a = 0; a < ky; ++a) {
+      int uy = oy + a - g.py;
+      if (uy < 0 || uy >= H || uy / g.fy != sy) continue;
+      for (int b = 0; b < kx; ++b) {
+        int ux = ox + b - g.px;
+        if (ux < 0 || ux >= W || ux / g.fx != sx) continue;
+        s += w[(((int64_t)o * g.ic + c) * ky + a) * kx + b];
+      }
+    }
+    m[e] = s;
+    if (m_t) m_t[col * rows + row] = s;
+  }
+}
+
+}  // namespace rcb
+
+using namespace rcb;
+
+extern "C" int rcb_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                        int M, int N, int K, const float* bias, int bias_mod, int act,
+                        int trans_a, int accumulate, rcb_stream_t stream) {
+  RCB_CHECK_ARG(A && B && C, "rcb_gemm: null operand");
+  RCB_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "rcb_gemm: lda/ldb must be multiples of 4 (got %d, %d)", lda, ldb);
+  RCB_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "rcb_gemm: A/B must be 16-byte aligned");
+  RCB_CHECK_ARG(ldb >= ((N + 3) / 4) * 4, "rcb_gemm: ldb %d too small for N %d (padded to 4)", ldb, N);
+  RCB_CHECK_ARG(!bias || bias_mod > 0, "rcb_gemm: bias_mod must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  PlainC ep{C, ldc, M, bias, bias_mod, act, accumulate};
+  if (trans_a) {
+    TransA al{A, lda, M};
+    return launch_engine("rcb_gemm(T)", al, B, ldb, 0, ep, M, N, K, 1, st);
+  }
+  PlainA al{A, lda, M};
+  return launch_engine("rcb_gemm", al, B, ldb, 0, ep, M, N, K, 1, st);
+}
+
+extern "C" int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_eff, float* w_eff_t,
+                             rcb_stream_t stream) {
+  PolyGeom pg;
+  if (int rc = make_geom(g, &pg)) return rc;
+  RCB_CHECK_ARG(w && w_eff, "rcb_fold_poly: null pointer");
+  int64_t total = (int64_t)pg.fy * pg.fx * pg.Ty * pg.Tx * pg.ic * pg.oc;
+  int blocks = (int)((total + 255) / 256); if (blocks > 4096) blocks = 4096;
+  fold_poly_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->ky, g->kx, w_eff, w_eff_t);
+  RCB_CHECK_LAUNCH("rcb_fold_poly");
+  return 0;
+}
+
+extern "C" int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m, float* m_t,
+                              rcb_stream_t stream) {
+  PolyGeom pg;
+  if (int rc = make_geom(g, &pg)) return rc;
+  RCB_CHECK_ARG(w && m, "rcb_fold_dense: null pointer");
+  int64_t total = (int64_t)pg.h * pg.w * pg.ic * pg.h * pg.fy * pg.w * pg.fx * pg.oc;
+  int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
+  fold_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->ky, g->kx, m, m_t);
+  RCB_CHECK_LAUNCH("rcb_fold_dense");
+  return 0;
+}
+
+extern "C" int rcb_upconv_fwd(const float* src, const float* w_eff, const float* bias, float* out,
+                              const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream) {
+  PolyGeom pg;
+  if (int rc = make_geom(g, &pg)) return rc;
+  RCB_CHECK_ARG(src && w_eff && bias && out, "rcb_upconv_fwd: null pointer");
+  int M = items * pg.h * pg.w, K = pg.Ty * pg.Tx * pg.ic, N = pg.oc, Z = pg.fy * pg.fx;
+  RCB_CHECK_ARG((int64_t)items * pg.h * pg.w < (1LL << 31), "rcb_upconv_fwd: too many rows");
+  ConvFwdA al{src, pg, M};
+  ConvFwdC ep{out, pg, M, bias, act};
+  return launch_engine("rcb_upconv_fwd", al, w_eff, N, (int64_t)K * N, ep, M, N, K, Z, (cudaStream_t)stream);
+}
+
+extern "C" int rcb_upconv_bwd(const float* d_out, const float* w_eff_t, const float* src_act, float* d_src,
+                              const rcb_upconv_geom* g, int items, rcb_stream_t stream) {
+  PolyGeom pg;
+  if (int rc = make_geom(g, &pg)) return rc;
+  RCB_CHECK_ARG(d_out && w_eff_t && d_src, "rcb_upconv_bwd: null pointer");
+  int M = items * pg.h * pg.w, K = pg.fy * pg.fx * pg.Ty * pg.Tx * pg.oc, N = pg.ic;
+  RCB_CHECK_ARG((int64_t)items * pg.h * pg.w < (1LL << 31), "rcb_upconv_bwd: too many rows");
+  ConvBwdA al{d_out, pg, M};
+  ConvBwdC ep{d_src, src_act, pg.ic, M};
+  return launch_engine("rcb_upconv_bwd", al, w_eff_t, N, 0, ep, M, N, K, 1, (cudaStream_t)stream);
+}

@@ -1,0 +1,289 @@
+// Relative entropy coding: candidate table generation (scrambled Sobol by random
+// access + Cephes inverse normal CDF in f64), batched A*/Gumbel-max scoring with a
+// block-level first-argmax, and the receiver-side regeneration.
+//
+// Reference: test_model.py:441-533 (get_sobol_normal_sample, sample_group),
+// :586-595 (compress_group).  All scoring is f64, as in the reference.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rcb {
+
+// ---- Cephes ndtri (the algorithm behind scipy.stats.norm.ppf) ----------------
+__device__ __forceinline__ double ndtri_p0(double x) {
+  double r = -5.99633501014107895267E1;
+  r = r * x + 9.80010754185999661536E1;
+  r = r * x + -5.66762857469070293439E1;
+  r = r * x + 1.39312609387279679503E1;
+  r = r * x + -1.23916583867381258016E0;
+  return r;
+}
+__device__ __forceinline__ double ndtri_q0(double x) {
+  double r = x + 1.95448858338141759834E0;
+  r = r * x + 4.67627912898881538453E0;
+  r = r * x + 8.63602421390890590575E1;
+  r = r * x + -2.25462687854119370527E2;
+  r = r * x + 2.00260212380060660359E2;
+  r = r * x + -8.20372256168333339912E1;
+  r = r * x + 1.59056225126211695515E1;
+  r = r * x + -1.18331621121330003142E0;
+  return r;
+}
+__device__ __forceinline__ double ndtri_p1(double x) {
+  double r = 4.05544892305962419923E0;
+  r = r * x + 3.15251094599893866154E1;
+  r = r * x + 5.71628192246421288162E1;
+  r = r * x + 4.40805073893200834700E1;
+  r = r * x + 1.46849561928858024014E1;
+  r = r * x + 2.18663306850790267539E0;
+  r = r * x + -1.40256079171354495875E-1;
+  r = r * x + -3.50424626827848203418E-2;
+  r = r * x + -8.57456785154685413611E-4;
+  return r;
+}
+__device__ __forceinline__ double ndtri_q1(double x) {
+  double r = x + 1.57799883256466749731E1;
+  r = r * x + 4.53907635128879210584E1;
+  r = r * x + 4.13172038254672030440E1;
+  r = r * x + 1.50425385692907503408E1;
+  r = r * x + 2.50464946208309415979E0;
+  r = r * x + -1.42182922854787788574E-1;
+  r = r * x + -3.80806407691578277194E-2;
+  r = r * x + -9.33259480895457427372E-4;
+  return r;
+}
+__device__ __forceinline__ double ndtri_p2(double x) {
+  double r = 3.23774891776946035970E0;
+  r = r * x + 6.91522889068984211695E0;
+  r = r * x + 3.93881025292474443415E0;
+  r = r * x + 1.33303460815807542389E0;
+  r = r * x + 2.01485389549179081538E-1;
+  r = r * x + 1.23716634817820021358E-2;
+  r = r * x + 3.01581553508235416007E-4;
+  r = r * x + 2.65806974686737550832E-6;
+  r = r * x + 6.23974539184983293730E-9;
+  return r;
+}
+__device__ __forceinline__ double ndtri_q2(double x) {
+  double r = x + 6.02427039364742014255E0;
+  r = r * x + 3.67983563856160859403E0;
+  r = r * x + 1.37702099489081330271E0;
+  r = r * x + 2.16236993594496635890E-1;
+  r = r * x + 1.34204006088543189037E-2;
+  r = r * x + 3.28014464682127739104E-4;
+  r = r * x + 2.89247864745380683936E-6;
+  r = r * x + 6.79019408009981274425E-9;
+  return r;
+}
+
+__device__ double ndtri(double y0) {
+  if (y0 <= 0.0) return -CUDART_INF;
+  if (y0 >= 1.0) return CUDART_INF;
+  bool negate = true;
+  double y = y0;
+  if (y > 1.0 - 0.13533528323661269189) { y = 1.0 - y; negate = false; }
+  if (y > 0.13533528323661269189) {
+    y = y - 0.5;
+    double y2 = y * y;
+    double x = y + y * (y2 * ndtri_p0(y2) / ndtri_q0(y2));
+    return x * 2.50662827463100050242E0;
+  }
+  double x = sqrt(-2.0 * log(y));
+  double x0 = x - log(x) / x;
+  double z = 1.0 / x;
+  double x1 = (x < 8.0) ? z * ndtri_p1(z) / ndtri_q1(z) : z * ndtri_p2(z) / ndtri_q2(z);
+  x = x0 - x1;
+  return negate ? -x : x;
+}
+
+// grid (ceil(n/256), D): table[d*n + k]
+__global__ void __launch_bounds__(256) rec_table_kernel(const int64_t* __restrict__ shift, const int64_t* __restrict__ words,
+                                                        float* __restrict__ table, int n, int nbits) {
+  __shared__ int64_t w[30];
+  const int d = blockIdx.y;
+  if (threadIdx.x < 30) w[threadIdx.x] = words[(int64_t)d * 30 + threadIdx.x];
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t gray = (uint32_t)k ^ ((uint32_t)k >> 1);
+  int64_t q = shift[d];
+  for (int j = 0; j < nbits; ++j) q ^= w[j] & -(int64_t)((gray >> j) & 1u);
+  const float u = __ll2float_rn(q) * 9.31322574615478515625e-10f;   // * 2^-30
+  float s = (float)ndtri((double)u);
+  s = fminf(fmaxf(s, -100.f), 100.f);
+  table[(int64_t)d * n + k] = s;
+}
+
+// ---- scoring -----------------------------------------------------------------
+constexpr int REC_THREADS = 512;
+constexpr int REC_ILP = 4;
+
+// One CTA per (row, block) pair.
+__global__ void __launch_bounds__(REC_THREADS) rec_encode_kernel(rcb_rec_args a) {
+  extern __shared__ __align__(16) double coef[];   // [2*D] (A_d, B_d) then reduction scratch
+  __shared__ double red_v[REC_THREADS / 32];
+  __shared__ int red_i[REC_THREADS / 32];
+  __shared__ double c0_s;
+  __shared__ int best_s;
+
+  const int pair = blockIdx.x;
+  const int row = a.pair_row[pair], blk = a.pair_block[pair];
+  const int start = a.group_start[blk], D = a.group_end[blk] - start;
+  const float* __restrict__ tab = a.tables[blk];
+  const int n = a.n_cand;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // per-dimension quadratic-form coefficients, reproducing the reference's mixed
+  // precision: var = scale*scale and log(scale) are f32, everything else f64
+  double c_part = 0.0;
+  for (int d = tid; d < D; d += REC_THREADS) {
+    const float mq = a.q_loc[(int64_t)row * a.P + start + d], sq = a.q_scale[(int64_t)row * a.P + start + d];
+    const float mp = a.p_loc[start + d], sp = a.p_scale[start + d];
+    const double kp = 1.0 / (2.0 * (double)__fmul_rn(sp, sp));
+    const double kq = 1.0 / (2.0 * (double)__fmul_rn(sq, sq));
+    const double delta = (double)mp - (double)mq;
+    const double spd = (double)sp;
+    coef[2 * d] = spd * spd * (kp - kq);
+    coef[2 * d + 1] = -2.0 * spd * delta * kq;
+    c_part += -delta * delta * kq + (double)logf(sp) - (double)logf(sq);
+  }
+  c_part = warp_sum(c_part);
+  if (lane == 0) red_v[warp] = c_part;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < REC_THREADS / 32; ++w) t += red_v[w];
+    c0_s = t;
+  }
+  __syncthreads();
+  const double c0 = c0_s;
+
+  double best = -CUDART_INF;
+  int best_k = 0x7fffffff;
+  for (int k0 = tid; k0 < n; k0 += REC_THREADS * REC_ILP) {
+    double acc[REC_ILP];
+#pragma unroll
+    for (int u = 0; u < REC_ILP; ++u) acc[u] = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double A = coef[2 * d], B = coef[2 * d + 1];
+      const float* col = tab + (int64_t)d * n + k0;
+#pragma unroll
+      for (int u = 0; u < REC_ILP; ++u) {
+        const int k = k0 + u * REC_THREADS;
+        const double s = (k < n) ? (double)__ldg(col + u * REC_THREADS) : 0.0;
+        acc[u] = fma(s, fma(A, s, B), acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < REC_ILP; ++u) {
+      const int k = k0 + u * REC_THREADS;
+      if (k < n) {
+        const double lw = acc[u] + c0 + a.gumbel[k];
+        if (a.logw_out) a.logw_out[(int64_t)pair * n + k] = lw;
+        if (lw > best) { best = lw; best_k = k; }     // k increases: keeps the first maximum
+      }
+    }
+  }
+  // block-level first-argmax
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ov > best || (ov == best && oi < best_k)) { best = ov; best_k = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { red_v[warp] = best; red_i[warp] = best_k; }
+  __syncthreads();
+  if (tid == 0) {
+    double bv = red_v[0]; int bi = red_i[0];
+    for (int w = 1; w < REC_THREADS / 32; ++w)
+      if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+    best_s = bi;
+    if (a.apply) {
+      a.idx_out[(int64_t)row * a.G + blk] = bi;
+      if (a.beta) a.beta[(int64_t)row * a.G + blk] = 0.f;
+      if (a.coded) a.coded[(int64_t)row * a.G + blk] = 1;
+    } else {
+      a.idx_out[pair] = bi;
+    }
+  }
+  __syncthreads();
+  const int kb = best_s;
+  if (kb >= n) return;   // n == 0
+  for (int d = tid; d < D; d += REC_THREADS) {
+    const double s = (double)tab[(int64_t)d * n + kb];
+    // z = mu_p + sigma_p * s in f64 with two roundings, then f32 on store (test_model.py:514,591)
+    const float z = (float)__dadd_rn((double)a.p_loc[start + d], __dmul_rn((double)a.p_scale[start + d], s));
+    if (a.apply) {
+      a.sample[(int64_t)row * a.P + start + d] = z;
+      a.mask[(int64_t)row * a.P + start + d] = 1.f;
+    } else if (a.z_out) {
+      a.z_out[(int64_t)pair * a.max_D + d] = z;
+    }
+  }
+}
+
+__global__ void rec_decode_kernel(const int* __restrict__ pair_row, const int* __restrict__ pair_block,
+                                  const int* __restrict__ idx, const float* __restrict__ p_loc,
+                                  const float* __restrict__ p_scale, const int* __restrict__ gs,
+                                  const int* __restrict__ ge, const float* const* __restrict__ tables,
+                                  float* __restrict__ sample, float* __restrict__ mask, int P, int n) {
+  const int pair = blockIdx.x;
+  const int row = pair_row[pair], blk = pair_block[pair];
+  const int start = gs[blk], D = ge[blk] - start;
+  const float* tab = tables[blk];
+  const int k = idx[pair];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double s = (double)tab[(int64_t)d * n + k];
+    const float z = (float)__dadd_rn((double)p_loc[start + d], __dmul_rn((double)p_scale[start + d], s));
+    sample[(int64_t)row * P + start + d] = z;
+    if (mask) mask[(int64_t)row * P + start + d] = 1.f;
+  }
+}
+
+}  // namespace rcb
+
+using namespace rcb;
+
+extern "C" int rcb_rec_table(const int64_t* shift, const int64_t* words, float* table, int D, int n, rcb_stream_t stream) {
+  RCB_CHECK_ARG(shift && words && table, "rcb_rec_table: null tensor");
+  RCB_CHECK_ARG(D > 0 && D <= 65535 && n > 0 && n <= (1 << 30), "rcb_rec_table: bad shape D=%d n=%d", D, n);
+  int nbits = 0;
+  while (nbits < 30 && ((int64_t)1 << nbits) < n) ++nbits;     // gray(k) < 2^nbits for k < n
+  dim3 grid(ceil_div(n, 256), D);
+  rec_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(shift, words, table, n, nbits);
+  RCB_CHECK_LAUNCH("rcb_rec_table");
+  return 0;
+}
+
+extern "C" int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream) {
+  RCB_CHECK_ARG(a != nullptr, "rcb_rec_encode: null args");
+  RCB_CHECK_ARG(a->pair_row && a->pair_block && a->q_loc && a->q_scale && a->p_loc && a->p_scale &&
+                a->group_start && a->group_end && a->tables && a->gumbel && a->idx_out, "rcb_rec_encode: null tensor");
+  RCB_CHECK_ARG(!a->apply || (a->sample && a->mask), "rcb_rec_encode: apply needs sample and mask");
+  RCB_CHECK_ARG(a->max_D > 0 && a->max_D <= 12000, "rcb_rec_encode: max_D %d out of range (1..12000)", a->max_D);
+  RCB_CHECK_ARG(a->n_cand > 0, "rcb_rec_encode: no candidates");
+  if (a->n_pairs <= 0) return 0;
+  size_t smem = sizeof(double) * 2 * (size_t)a->max_D;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rec_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rcb_rec_encode: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+  }
+  rec_encode_kernel<<<a->n_pairs, REC_THREADS, smem, (cudaStream_t)stream>>>(*a);
+  RCB_CHECK_LAUNCH("rcb_rec_encode");
+  return 0;
+}
+
+extern "C" int rcb_rec_decode(const int* pair_row, const int* pair_block, const int* idx, const float* p_loc,
+                              const float* p_scale, const int* group_start, const int* group_end,
+                              const float* const* tables, float* sample, float* mask, int n_pairs, int P, int n_cand,
+                              rcb_stream_t stream) {
+  RCB_CHECK_ARG(pair_row && pair_block && idx && p_loc && p_scale && group_start && group_end && tables && sample,
+                "rcb_rec_decode: null tensor");
+  if (n_pairs <= 0) return 0;
+  rec_decode_kernel<<<n_pairs, 128, 0, (cudaStream_t)stream>>>(pair_row, pair_block, idx, p_loc, p_scale, group_start,
+                                                               group_end, tables, sample, mask, P, n_cand);
+  RCB_CHECK_LAUNCH("rcb_rec_decode");
+  return 0;
+}

@@ -1,0 +1,312 @@
+"""Host-side composition of the sm_100a kernels for the fit path.
+
+`FitEngine` owns the device-side constants derived from the learned mappings
+(padded / transposed reparameterisation matrices, upsample-folded conv weights)
+and the per-(rows, S) workspaces, and sequences the C-ABI calls of one forward /
+backward / update.  All arithmetic happens in librecombiner_b200.so; torch is
+used for device memory and streams only.
+
+Reference call sites replaced: test_model.py:283-355 (predict), :357-377
+(calculate_kl), :621-635 (train step); prior_model.py:129-179 for the S=1 case.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (KernelError, MlpArgs, SampleArgs, UpconvGeom, UpdateArgs, check, ptr, stream)
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def layer_param_counts(dims: Sequence[int]) -> List[int]:
+    return [dims[i + 1] * (dims[i] + 1) for i in range(len(dims) - 1)]
+
+
+def _i32(a, device) -> torch.Tensor:
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a)).astype(np.int32), device=device)
+
+
+@dataclass
+class Noise:
+    """Either explicit eps tensors (parity tests) or a Philox key (production)."""
+    eps_w: Optional[torch.Tensor] = None      # (rows, S, W)
+    eps_l: Optional[torch.Tensor] = None      # (S, rows, L)
+    seed: int = 0
+    step: int = 0
+    row_offset: int = 0
+
+
+class LevelState:
+    """One level of posterior state in group order plus its block structure, on device.
+    Mirrors test_model.py:131-141,169,211-224 (level 1) / :144-166 (levels 2, 3)."""
+
+    def __init__(self, loc, log_scale, p_loc, p_log_scale, group_idx, group_start, group_end,
+                 group_to_param, param_to_group, beta, device):
+        self.device = device
+        self.loc = loc
+        self.log_scale = log_scale
+        self.p_loc = p_loc.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.p_log_scale = p_log_scale.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.rows, self.P = loc.shape
+        self.G = int(len(group_start))
+        self.group_idx = _i32(group_idx, device)
+        self.group_start = _i32(group_start, device)
+        self.group_end = _i32(group_end, device)
+        self.g2p = _i32(group_to_param, device)
+        self.p2g = _i32(param_to_group, device)
+        self.group_start_host = np.asarray(group_start).astype(np.int64)
+        self.group_end_host = np.asarray(group_end).astype(np.int64)
+        self.mask = torch.zeros(self.rows, self.P, device=device)
+        self.sample = torch.zeros(self.rows, self.P, device=device)
+        if torch.is_tensor(beta):
+            beta = beta.detach().to(device=device, dtype=torch.float32)
+            self.beta = (beta.expand(self.rows, self.G) if beta.ndim else beta.repeat(self.rows, self.G)).contiguous()
+        else:
+            self.beta = torch.full((self.rows, self.G), float(beta), device=device)
+        self.coded = torch.zeros(self.rows, self.G, dtype=torch.uint8, device=device)
+        self.idx = torch.zeros(self.rows, self.G, dtype=torch.int32, device=device)
+        self.group_kl = torch.zeros(self.rows, self.G, dtype=torch.float64, device=device)
+        self.adam = None
+
+    def reset_adam(self):
+        z = lambda: torch.zeros(self.rows, self.P, device=self.device)
+        self.adam = dict(m1_loc=z(), v_loc=z(), m1_ls=z(), v_ls=z(), t=0)
+
+
+class FitEngine:
+    """Kernel sequencing for one modality shape (non-patch modalities: cifar, protein)."""
+
+    def __init__(self, dims, data_dim, pixel_sizes, upsample_factors, latent_dim, layer_scales, paddings,
+                 w0, device):
+        if not torch.cuda.is_available():
+            raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.dims = list(dims)
+        self.counts = layer_param_counts(self.dims)
+        self.offsets = [0] + list(np.cumsum(self.counts))[:-1]
+        self.offsets = [int(o) for o in self.offsets]
+        self.W = int(sum(self.counts))
+        self.ldw = _round_up(self.W, 4)
+        if len(self.dims) != 5 or self.dims[1:4] != [32, 32, 32]:
+            raise KernelError(f"unsupported INR {self.dims}: kernels are built for 3 hidden layers of 32")
+        self.data_dim = data_dim
+        if data_dim not in (1, 2):
+            raise KernelError("this build covers 1-D and 2-D signals (3-D upsampler is not built yet)")
+        self.pixel_sizes = list(pixel_sizes)
+        self.pix = int(np.prod(pixel_sizes))
+        self.grid = [pixel_sizes[i] // upsample_factors[i] for i in range(data_dim)]
+        self.latent_dim = int(latent_dim)
+        self.L = int(np.prod(self.grid)) * self.latent_dim
+        self.n_f = self.dims[0] - 16
+        self.out = self.dims[-1]
+        self.w0 = float(w0)
+        if list(paddings) != [2, 1, 1]:
+            raise KernelError("upsampler kernels assume 'same' convolutions (paddings [2,1,1])")
+        # stage geometry: (h, w) grids for the three nearest-up + conv stages
+        h, w = (1, self.grid[0]) if data_dim == 1 else (self.grid[0], self.grid[1])
+        ks = [5, 3, 3]
+        chans = [(latent_dim, 64), (64, 64), (64, 16)]
+        self.geoms = []
+        for i in range(3):
+            f = layer_scales[i]
+            f = list(f) if isinstance(f, (tuple, list)) else [f] * data_dim
+            fy, fx = (1, int(f[0])) if data_dim == 1 else (int(f[0]), int(f[1]))
+            ky = 1 if data_dim == 1 else ks[i]
+            self.geoms.append(UpconvGeom(h, w, fy, fx, ky, ks[i], chans[i][0], chans[i][1]))
+            h, w = h * fy, w * fx
+        if h * w != self.pix:
+            raise KernelError("upsample factors do not reach the pixel grid")
+        self.dense1 = self.geoms[0].h * self.geoms[0].w <= 16
+        self._ws: Dict = {}
+        self._x_cache = None
+        self.A = None
+
+    # ---------------------------------------------------------------- mappings --
+    def set_mappings(self, A_list, up_state):
+        """Stage the frozen learned mappings on device: zero-padded A_l and A_l^T, and
+        the upsampler with its nearest-upsampling folded into the conv taps."""
+        dev = self.device
+        st = stream()
+        self.A, self.AT = [], []
+        for a, c in zip(A_list, self.counts):
+            a = a.detach().to(device=dev, dtype=torch.float32)
+            ld = _round_up(c, 4)
+            ap = torch.zeros(c, ld, device=dev); ap[:, :c] = a
+            at = torch.zeros(c, ld, device=dev); at[:, :c] = a.t()
+            self.A.append(ap); self.AT.append(at)
+        self.conv_b = [up_state[f"conv{i}.bias"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
+        conv_w = [up_state[f"conv{i}.weight"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
+        self.w_eff, self.w_eff_t = [None] * 3, [None] * 3
+        for i, g in enumerate(self.geoms):
+            if i == 0 and self.dense1:
+                rows = g.h * g.w * g.ic
+                cols = g.h * g.fy * g.w * g.fx * g.oc
+                self.M1 = torch.empty(rows, cols, device=dev)
+                self.M1T = torch.empty(cols, rows, device=dev)
+                check(self.lib.rcb_fold_dense(ptr(conv_w[0]), C.byref(g), ptr(self.M1), ptr(self.M1T), st), "rcb_fold_dense")
+                continue
+            ty = 1 if g.ky == 1 else 2
+            tx = 1 if g.kx == 1 else 2
+            n = g.fy * g.fx * ty * tx * g.ic * g.oc
+            self.w_eff[i] = torch.empty(n, device=dev)
+            self.w_eff_t[i] = torch.empty(n, device=dev)
+            check(self.lib.rcb_fold_poly(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff[i]), ptr(self.w_eff_t[i]), st), "rcb_fold_poly")
+
+    # -------------------------------------------------------------- workspaces --
+    def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
+        key = (rows, S)
+        ws = self._ws.get(key)
+        if ws is None:
+            items = rows * S
+            dev = self.device
+            g1, g2, g3 = self.geoms
+            n1 = g1.h * g1.fy * g1.w * g1.fx * g1.oc
+            n2 = g2.h * g2.fy * g2.w * g2.fx * g2.oc
+            e = lambda *s: torch.empty(*s, device=dev)
+            ws = dict(hw=torch.zeros(items, self.ldw, device=dev), wt=torch.zeros(items, self.ldw, device=dev),
+                      lpe=e(items, self.L), a1=e(items, n1), a2=e(items, n2), pe=e(items, self.pix, 16),
+                      d_pe=e(items, self.pix, 16), d_a2=e(items, n2), d_a1=e(items, n1), d_lpe=e(items, self.L),
+                      d_wt=torch.zeros(items, self.ldw, device=dev), d_hw=torch.zeros(items, self.ldw, device=dev),
+                      sqerr=torch.zeros(items, device=dev), y_pred=e(items, self.pix, self.out),
+                      kl=torch.zeros(1, dtype=torch.float64, device=dev))
+            self._ws[key] = ws
+        return ws
+
+    def prepare_x(self, x: torch.Tensor):
+        """(rows, pix, F) Fourier inputs -> transposed (F, pix) [shared] or (rows, F, pix)."""
+        key = (x.data_ptr(), tuple(x.shape), x._version)
+        if self._x_cache is not None and self._x_cache[0] == key:
+            return self._x_cache[1], self._x_cache[2]
+        if x.shape[1] != self.pix or x.shape[2] != self.n_f:
+            raise KernelError(f"x has shape {tuple(x.shape)}, expected (rows, {self.pix}, {self.n_f})")
+        x = x.to(device=self.device, dtype=torch.float32)
+        shared = bool((x == x[:1]).all().item()) if x.shape[0] > 1 else True
+        if shared:
+            xt, stride = x[0].t().contiguous(), 0
+        else:
+            xt, stride = x.transpose(1, 2).contiguous(), self.n_f * self.pix
+        self._x_cache = (key, xt, stride)
+        return xt, stride
+
+    # ------------------------------------------------------------------ forward --
+    def _sample(self, lv: LevelState, ws, S: int, noise: Noise):
+        a = SampleArgs()
+        a.loc, a.log_scale, a.mask, a.sample = ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.mask), ptr(lv.sample)
+        a.g2p, a.perm, a.row_map = ptr(lv.g2p), None, None
+        a.eps_w, a.eps_l = ptr(noise.eps_w), ptr(noise.eps_l)
+        a.hw, a.lpe = ptr(ws["hw"]), ptr(ws["lpe"])
+        a.seed, a.row_offset = noise.seed, noise.row_offset
+        a.rows, a.S, a.P, a.n_w, a.n_l, a.ld_hw = lv.rows, S, lv.P, self.W, self.L, self.ldw
+        a.step, a.tensor_id, a.accumulate = noise.step, 0, 0
+        check(self.lib.rcb_fit_sample(C.byref(a), stream()), "rcb_fit_sample")
+
+    def _gemm(self, A, a_off, lda, B, ldb, Cm, c_off, ldc, M, N, K, bias=None, bias_mod=1, act=0, trans_a=0, acc=0):
+        pa = A.data_ptr() + 4 * a_off
+        pc = Cm.data_ptr() + 4 * c_off
+        check(self.lib.rcb_gemm(pa, lda, ptr(B), ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
+              "rcb_gemm")
+
+    def forward_features(self, lv: LevelState, S: int, noise: Noise):
+        """sample -> per-item INR weights (wt) and positional encodings (pe)."""
+        if self.A is None:
+            raise KernelError("set_mappings() has not been called")
+        ws = self.workspace(lv.rows, S)
+        items = lv.rows * S
+        st = stream()
+        self._sample(lv, ws, S, noise)
+        for l, c in enumerate(self.counts):
+            self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
+                       ws["wt"], self.offsets[l], self.ldw, items, c, c)
+        g1, g2, g3 = self.geoms
+        if self.dense1:
+            self._gemm(ws["lpe"], 0, self.L, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
+                       items, self.M1.shape[1], self.L, bias=self.conv_b[0], bias_mod=g1.oc, act=1)
+        else:
+            check(self.lib.rcb_upconv_fwd(ptr(ws["lpe"]), ptr(self.w_eff[0]), ptr(self.conv_b[0]), ptr(ws["a1"]),
+                                          C.byref(g1), items, 1, st), "rcb_upconv_fwd[1]")
+        check(self.lib.rcb_upconv_fwd(ptr(ws["a1"]), ptr(self.w_eff[1]), ptr(self.conv_b[1]), ptr(ws["a2"]),
+                                      C.byref(g2), items, 1, st), "rcb_upconv_fwd[2]")
+        check(self.lib.rcb_upconv_fwd(ptr(ws["a2"]), ptr(self.w_eff[2]), ptr(self.conv_b[2]), ptr(ws["pe"]),
+                                      C.byref(g3), items, 0, st), "rcb_upconv_fwd[3]")
+        return ws
+
+    def mlp(self, ws, rows: int, S: int, x, mode: int, y=None, dy=None, coef: float = 0.0):
+        xt, stride = self.prepare_x(x)
+        a = MlpArgs()
+        a.wt, a.xt, a.pe = ptr(ws["wt"]), ptr(xt), ptr(ws["pe"])
+        a.y, a.dy, a.y_pred = ptr(y), ptr(dy), ptr(ws["y_pred"])
+        a.d_pe, a.d_wt, a.sqerr = ptr(ws["d_pe"]), ptr(ws["d_wt"]), ptr(ws["sqerr"])
+        a.x_row_stride = stride
+        a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
+        a.coef, a.w0 = coef, self.w0
+        check(self.lib.rcb_mlp(C.byref(a), stream()), "rcb_mlp")
+
+    # ----------------------------------------------------------------- backward --
+    def backward_features(self, ws, rows: int, S: int):
+        """d_pe, d_wt -> d_lpe, d_hw (data gradients only; the mappings are frozen)."""
+        items = rows * S
+        st = stream()
+        g1, g2, g3 = self.geoms
+        check(self.lib.rcb_upconv_bwd(ptr(ws["d_pe"]), ptr(self.w_eff_t[2]), ptr(ws["a2"]), ptr(ws["d_a2"]),
+                                      C.byref(g3), items, st), "rcb_upconv_bwd[3]")
+        check(self.lib.rcb_upconv_bwd(ptr(ws["d_a2"]), ptr(self.w_eff_t[1]), ptr(ws["a1"]), ptr(ws["d_a1"]),
+                                      C.byref(g2), items, st), "rcb_upconv_bwd[2]")
+        if self.dense1:
+            self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, self.L,
+                       items, self.L, self.M1T.shape[0])
+        else:
+            check(self.lib.rcb_upconv_bwd(ptr(ws["d_a1"]), ptr(self.w_eff_t[0]), None, ptr(ws["d_lpe"]),
+                                          C.byref(g1), items, st), "rcb_upconv_bwd[1]")
+        for l, c in enumerate(self.counts):
+            self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
+                       ws["d_hw"], self.offsets[l], self.ldw, items, c, c)
+
+    def update(self, lv: LevelState, ws, S: int, noise: Noise, *, with_data_grads: bool, adam: Optional[dict],
+               g_loc=None, g_log_scale=None, grad_scale: float = 1.0, kl_out: Optional[torch.Tensor] = None):
+        a = UpdateArgs()
+        a.loc, a.log_scale, a.mask = ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.mask)
+        a.p_loc, a.p_log_scale, a.beta, a.group_idx = ptr(lv.p_loc), ptr(lv.p_log_scale), ptr(lv.beta), ptr(lv.group_idx)
+        a.p2g, a.perm_inv, a.row_children = ptr(lv.p2g), None, None
+        a.d_hw = ptr(ws["d_hw"]) if with_data_grads else None
+        a.d_lpe = ptr(ws["d_lpe"]) if with_data_grads else None
+        a.eps_w, a.eps_l = ptr(noise.eps_w), ptr(noise.eps_l)
+        a.g_loc, a.g_log_scale = ptr(g_loc), ptr(g_log_scale)
+        a.kl_out = ptr(kl_out)
+        a.seed, a.row_offset = noise.seed, noise.row_offset
+        a.src_rows, a.rows, a.n_children, a.S, a.P = lv.rows, lv.rows, 1, S, lv.P
+        a.n_w, a.n_l, a.ld_hw, a.G = self.W, self.L, self.ldw, lv.G
+        a.step, a.tensor_id = noise.step, 0
+        a.beta_scalar, a.grad_scale = 0.0, grad_scale
+        if adam is not None:
+            st_ = lv.adam
+            st_["t"] += 1
+            t = st_["t"]
+            a.adam = 1
+            a.m1_loc, a.v_loc, a.m1_ls, a.v_ls = ptr(st_["m1_loc"]), ptr(st_["v_loc"]), ptr(st_["m1_ls"]), ptr(st_["v_ls"])
+            a.b1, a.b2, a.adam_eps = adam["b1"], adam["b2"], adam["eps"]
+            a.adam_step_size = adam["lr"] / (1.0 - adam["b1"] ** t)
+            a.adam_bc2_sqrt = math.sqrt(1.0 - adam["b2"] ** t)
+        else:
+            a.adam = 0
+        check(self.lib.rcb_fit_update(C.byref(a), stream()), "rcb_fit_update")
+
+    # --------------------------------------------------------------- block KL ----
+    def group_kl(self, lv: LevelState) -> torch.Tensor:
+        check(self.lib.rcb_group_kl(ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.p_loc), ptr(lv.p_log_scale),
+                                    ptr(lv.group_start), ptr(lv.group_end), ptr(lv.group_kl), lv.rows, lv.P, lv.G,
+                                    stream()), "rcb_group_kl")
+        return lv.group_kl
+
+    def anneal(self, lv: LevelState, step: float, upper: float, lower: float, bits: float):
+        check(self.lib.rcb_anneal_beta(ptr(lv.beta), ptr(lv.group_kl), ptr(lv.coded), lv.rows, lv.G,
+                                       step, upper, lower, bits, stream()), "rcb_anneal_beta")

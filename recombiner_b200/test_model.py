@@ -1,0 +1,421 @@
+"""Test-time (compression) model: per-datapoint variational INR fitting + REC.
+
+Drop-in host mirror of the reference `test_model.TestBNNmodel`
+(test_model.py:33-856): same constructor keywords, attributes and methods, but
+every tensor op of the hot path runs in the sm_100a kernels of
+librecombiner_b200.so (no CPU fallback, no torch autograd graph in the loop):
+
+  predict / train        -> FitEngine (sample, reparam GEMMs, folded upsampler,
+                            fused SIREN MLP fwd+loss+bwd, KL-gradient + Adam)
+  update_annealing_factors -> rcb_group_kl + rcb_anneal_beta (no host round trip)
+  sample_group / compress_group / compress_posteriors
+                         -> rcb_rec_table + batched rcb_rec_encode (one launch codes
+                            one block of *every* row; the reference loops rows in
+                            Python, test_model.py:806-818)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import rec as _rec
+from .engine import FitEngine, LevelState, Noise
+from ._lib import KernelError
+from .utils import count_net_params, metric
+
+
+class Sine(nn.Module):
+    """sin(w0 x) (kept for API compatibility; the kernels evaluate it in the MLP epilogue)."""
+
+    def __init__(self, w0=1.):
+        super().__init__()
+        self.w0 = w0
+
+    def forward(self, x):
+        return torch.sin(self.w0 * x)
+
+
+class _Predict(torch.autograd.Function):
+    """y_pred = INR(posterior sample); backward re-runs the fused MLP in gradient mode."""
+
+    @staticmethod
+    def forward(ctx, loc, log_scale, model, x, S, noise):
+        lv = model._lv
+        ws = model.engine.forward_features(lv, S, noise)
+        model.engine.mlp(ws, lv.rows, S, x, mode=0)
+        ctx.model, ctx.x, ctx.S, ctx.noise = model, x, S, noise
+        model._generation += 1
+        ctx.generation = model._generation
+        return ws["y_pred"].view(lv.rows, S, model.engine.pix, model.engine.out).clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        model, S, noise = ctx.model, ctx.S, ctx.noise
+        if ctx.generation != model._generation:
+            raise KernelError("predict() workspace was overwritten by a later forward before backward()")
+        lv = model._lv
+        ws = model.engine.workspace(lv.rows, S)
+        dy = dy.contiguous().view(lv.rows * S, model.engine.pix, model.engine.out)
+        model.engine.mlp(ws, lv.rows, S, ctx.x, mode=2, dy=dy)
+        model.engine.backward_features(ws, lv.rows, S)
+        g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
+        saved_beta = lv.beta
+        lv.beta = model._zero_beta          # data term only; KL has its own Function
+        try:
+            model.engine.update(lv, ws, S, noise, with_data_grads=True, adam=None, g_loc=g_loc, g_log_scale=g_ls)
+        finally:
+            lv.beta = saved_beta
+        return g_loc, g_ls, None, None, None, None
+
+
+class _WeightedKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, log_scale, model):
+        lv = model._lv
+        kl = torch.zeros(1, dtype=torch.float64, device=lv.device)
+        g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
+        model.engine.update(lv, None, 1, Noise(), with_data_grads=False, adam=None, g_loc=g_loc, g_log_scale=g_ls,
+                            kl_out=kl)
+        ctx.save_for_backward(g_loc, g_ls)
+        return kl.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        g_loc, g_ls = ctx.saved_tensors
+        return g * g_loc, g * g_ls, None
+
+
+class TestBNNmodel(nn.Module):
+    __test__ = False   # not a pytest class
+
+    def __init__(self,
+                 in_dim, hidden_dims, out_dim, number_of_datapoints, upsample_factors, latent_dim, data_dim,
+                 pixel_sizes, patch, patch_nums, hierarchical_patch_nums, dataset,
+                 linear_transform=None, upsample_net=None,
+                 p_loc=None, p_log_scale=None, init_log_scale=-4., param_to_group=None, group_to_param=None,
+                 n_groups=None, group_start_index=None, group_end_index=None, group_idx=None,
+                 h_p_loc=None, h_p_log_scale=None, h_init_log_scale=-4., h_param_to_group=None,
+                 h_group_to_param=None, h_n_groups=None, h_group_start_index=None, h_group_end_index=None,
+                 h_group_idx=None,
+                 hh_p_loc=None, hh_p_log_scale=None, hh_init_log_scale=-4., hh_param_to_group=None,
+                 hh_group_to_param=None, hh_n_groups=None, hh_group_start_index=None, hh_group_end_index=None,
+                 hh_group_idx=None,
+                 w0=30., c=6., random_seed=42, device='cuda', kl_upper_buffer=0., kl_lower_buffer=0.4,
+                 kl_adjust_gap=10, initial_beta=1e-8, beta_step_size=0.05, row_offset=0, layer_scales=None,
+                 paddings=None):
+        super().__init__()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise KernelError("recombiner_b200.TestBNNmodel runs on CUDA (sm_100a) only -- there is no CPU "
+                              "fallback; the CPU restatement used for parity lives in oracle/")
+        if patch:
+            raise NotImplementedError("patch modalities (kodak/audio/video) are not wired to the kernels yet")
+        self.bit_per_group = 16
+        self.n_layers = len(hidden_dims) + 1
+        self.dims = [in_dim] + list(hidden_dims) + [out_dim]
+        self.upsample_factors, self.latent_dim, self.data_dim = upsample_factors, latent_dim, data_dim
+        self.patch, self.patch_nums, self.pixel_sizes = patch, patch_nums, pixel_sizes
+        self.hierarchical_patch_nums = hierarchical_patch_nums
+        self.linear_transform, self.upsample_net = linear_transform, upsample_net
+        self.device, self.dataset, self.random_seed = dev, dataset, random_seed
+        self.row_offset = int(row_offset)
+        for m in (linear_transform, upsample_net):
+            if m is not None:
+                for p in m.parameters():
+                    p.requires_grad = False
+        _, self.cum_param_sizes = count_net_params(in_dim, hidden_dims, out_dim)
+
+        self.param_to_group, self.group_to_param, self.n_groups = param_to_group, group_to_param, n_groups
+        self.group_start_index, self.group_end_index, self.group_idx = group_start_index, group_end_index, group_idx
+        rows, P = number_of_datapoints, p_loc.shape[0]
+        init_ls = init_log_scale.to(dev) if torch.is_tensor(init_log_scale) else init_log_scale
+        self.loc = nn.Parameter(p_loc.detach().to(dev, torch.float32)[None, :].repeat(rows, 1).contiguous())
+        self.log_scale = nn.Parameter((torch.zeros(rows, P, device=dev) + init_ls).contiguous())
+        self.p_loc = p_loc.detach().clone().to(dev, torch.float32)
+        self.p_log_scale = p_log_scale.detach().clone().to(dev, torch.float32)
+
+        self.beta_step_size, self.kl_upper_buffer = beta_step_size, kl_upper_buffer
+        self.kl_lower_buffer, self.kl_adjust_gap = kl_lower_buffer, kl_adjust_gap
+
+        self._lv = LevelState(self.loc, self.log_scale, self.p_loc, self.p_log_scale, group_idx, group_start_index,
+                              group_end_index, group_to_param, param_to_group, initial_beta, dev)
+        self._zero_beta = torch.zeros_like(self._lv.beta)
+        self.compressed_sample_std = 1e-15 + torch.zeros(rows, P, device=dev)
+
+        cfg_scales = layer_scales if layer_scales is not None else [4, 2, 2]
+        self.engine = FitEngine(self.dims, data_dim, pixel_sizes, upsample_factors, latent_dim, cfg_scales,
+                                paddings if paddings is not None else [2, 1, 1], w0, dev)
+        if linear_transform is not None and upsample_net is not None:
+            self.engine.set_mappings(list(linear_transform.A), upsample_net.state_dict())
+        self.act = Sine(w0)
+        self.st = lambda v: torch.nn.functional.softplus(v, beta=1, threshold=20) / 6
+        self.bpp = (self.n_groups * self.bit_per_group) / np.prod(pixel_sizes)
+        if self.dataset == 'audio':
+            self.bpp = self.bpp / (3 / 48000) / 1000
+        print("Model Initialized. Expected bpp is %.2f" % self.bpp, flush=True)
+
+        self.g_samples = None
+        self._g_dev = None
+        self.group_samples = {}
+        self._tables = None
+        self._tables_ptr = None
+        self._generation = 0
+        self._adam_owner = None
+        self._global_step = 0
+
+    # ------------------------------------------------------- reference attributes --
+    @property
+    def kl_beta(self):
+        return self._lv.beta
+
+    @kl_beta.setter
+    def kl_beta(self, v):
+        self._lv.beta = torch.as_tensor(v, dtype=torch.float32).to(self.device).expand(self._lv.rows, self._lv.G).contiguous()
+
+    @property
+    def compressed_mask(self):
+        return self._lv.mask
+
+    @property
+    def compressed_sample(self):
+        return self._lv.sample
+
+    @property
+    def compressed_mask_groupwise(self):
+        return self._lv.coded.bool().cpu().numpy()
+
+    @property
+    def compressed_idx_groupwise(self):
+        """(rows, G) float64 numpy, as the reference stores and np.savetxt's it (test_model.py:221)."""
+        return self._lv.idx.cpu().numpy().astype(np.float64)
+
+    def group_to_layer(self, param, layer_idx):
+        lo = 0 if layer_idx == 0 else self.cum_param_sizes[layer_idx - 1]
+        return param[..., lo:self.cum_param_sizes[layer_idx]]
+
+    def layer_to_weight(self, in_dim, out_dim, layer_param):
+        lead = layer_param.shape[:-1]
+        bias = layer_param[..., :out_dim].unsqueeze(-2)
+        weights = layer_param[..., out_dim:].reshape(*lead, in_dim, out_dim)
+        return weights, bias
+
+    # -------------------------------------------------------------------- forward --
+    def _noise(self, random_seed, eps=None) -> Noise:
+        if eps is not None:
+            return Noise(eps_w=eps["w"].to(self.device).contiguous(), eps_l=eps["lpe"].to(self.device).contiguous())
+        if random_seed is None:
+            random_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())   # global torch RNG, like randn_like
+        seed = ((int(self.random_seed) & 0x7fffffff) << 32) | (int(random_seed) & 0xffffffff)
+        return Noise(seed=seed, step=0, row_offset=self.row_offset)
+
+    def predict(self, x, random_seed=None, sample_size=1, eps=None):
+        """MC forward (test_model.py:283-355).  `eps` (dict with 'lpe' (S,N,L) and 'w'
+        (N,S,W)) injects the noise for parity tests; otherwise it is Philox-generated
+        in-kernel from (model seed, random_seed)."""
+        noise = self._noise(random_seed, eps)
+        y = _Predict.apply(self.loc, self.log_scale, self, x, sample_size, noise)
+        return y[:, 0] if sample_size == 1 else y
+
+    def calculate_kl(self):
+        """sum_{n,p} beta[n, g(p)] KL(q_np || p_p)  (test_model.py:357-362)."""
+        return _WeightedKL.apply(self.loc, self.log_scale, self)
+
+    def update_annealing_factors(self, update=True):
+        """Per-(row, block) KL in nats; optionally anneal beta (test_model.py:379-439).
+        Returns a (rows, G) float64 numpy array like the reference."""
+        return self._annealing(update).cpu().numpy()
+
+    def _annealing(self, update: bool) -> torch.Tensor:
+        kl = self.engine.group_kl(self._lv)
+        if update:
+            self.engine.anneal(self._lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer,
+                               float(self.bit_per_group))
+        return kl
+
+    # ------------------------------------------------------------------------ REC --
+    def get_gumbel_sample(self):
+        n = int(np.ceil(2 ** self.bit_per_group))
+        g = _rec.gumbel_sequence(self.random_seed, n)
+        self.g_samples = torch.from_numpy(g)
+        self._g_dev = self.g_samples.to(self.device)
+
+    def _ensure_rec(self, n_cand: int):
+        if self.g_samples is None:
+            self.get_gumbel_sample()
+        if self._tables is None or self._tables.n != n_cand:
+            self._tables = _rec.CandidateTables(self.random_seed, n_cand, self.device)
+            sizes = self._lv.group_end_host - self._lv.group_start_host
+            self._tables_ptr = self._tables.pointer_array(sizes)
+            self._max_D = int(sizes.max())
+
+    def get_sobol_normal_sample(self, param_size, sample_size):
+        """(sample_size, param_size) float64 standard-normal candidates (test_model.py:493-498)."""
+        t = _rec.CandidateTables(self.random_seed, sample_size, self.device).table(int(param_size))
+        return t.t().to(torch.float64)
+
+    def get_sample(self, group_idx, group_sample_size):
+        key = (group_idx, group_sample_size)
+        if key not in self.group_samples:
+            D = int(self.group_end_index[group_idx] - self.group_start_index[group_idx])
+            self.group_samples[key] = self.get_sobol_normal_sample(D, group_sample_size)
+        return self.group_samples[key]
+
+    def _pairs(self, rows, blocks):
+        return (torch.as_tensor(rows, dtype=torch.int32, device=self.device).reshape(-1).contiguous(),
+                torch.as_tensor(blocks, dtype=torch.int32, device=self.device).reshape(-1).contiguous())
+
+    def _scales(self):
+        return self.st(self.log_scale.data).contiguous(), self.st(self.p_log_scale).contiguous()
+
+    def sample_group(self, row_idx, group_idx, group_sample_size):
+        """A*-code one block (test_model.py:501-533): returns (index, z_i, log_w)."""
+        self._ensure_rec(group_sample_size)
+        q_scale, p_scale = self._scales()
+        pr, pb = self._pairs([row_idx], [group_idx])
+        idx, z, logw = _rec.encode(self._lv, self._tables_ptr, self._g_dev, q_scale, p_scale, pr, pb,
+                                   group_sample_size, self._max_D, apply=False, want_logw=True)
+        D = int(self.group_end_index[group_idx] - self.group_start_index[group_idx])
+        return int(idx.item()), z[0, :D].to(torch.float64), logw[0]
+
+    def compress_group(self, row_idx, group_idx):
+        n = int(np.ceil(2 ** self.bit_per_group))
+        self._ensure_rec(n)
+        q_scale, p_scale = self._scales()
+        pr, pb = self._pairs([row_idx], [group_idx])
+        _rec.encode(self._lv, self._tables_ptr, self._g_dev, q_scale, p_scale, pr, pb, n, self._max_D, apply=True)
+        s, e = int(self.group_start_index[group_idx]), int(self.group_end_index[group_idx])
+        return int(self._lv.idx[row_idx, group_idx].item()), self._lv.sample[row_idx, s:e].clone()
+
+    def compress_round(self, blocks: Optional[torch.Tensor] = None):
+        """Code one block of every row in a single launch.  With blocks=None each row
+        codes its largest-KL not-yet-coded block (test_model.py:809-817)."""
+        from ._lib import check, ptr, stream
+        n = int(np.ceil(2 ** self.bit_per_group))
+        self._ensure_rec(n)
+        lv = self._lv
+        rows = torch.arange(lv.rows, dtype=torch.int32, device=self.device)
+        if blocks is None:
+            kl = self.engine.group_kl(lv)
+            blocks = torch.empty(lv.rows, dtype=torch.int32, device=self.device)
+            check(self.engine.lib.rcb_pick_block(ptr(kl), ptr(lv.coded), ptr(blocks), lv.rows, lv.G, stream()),
+                  "rcb_pick_block")
+        q_scale, p_scale = self._scales()
+        _rec.encode(lv, self._tables_ptr, self._g_dev, q_scale, p_scale, rows, blocks.contiguous(), n, self._max_D,
+                    apply=True)
+        return blocks
+
+    def decode_posteriors(self, indices: np.ndarray) -> torch.Tensor:
+        """Receiver side (the reference has none): rebuild every coded value from the
+        transmitted (rows, G) index table, prior and seed.  Returns (rows, P) in group order."""
+        n = int(np.ceil(2 ** self.bit_per_group))
+        self._ensure_rec(n)
+        lv = self._lv
+        rows = torch.arange(lv.rows, device=self.device, dtype=torch.int32).repeat_interleave(lv.G).contiguous()
+        blocks = torch.arange(lv.G, device=self.device, dtype=torch.int32).repeat(lv.rows).contiguous()
+        idx = torch.as_tensor(np.asarray(indices).astype(np.int32), device=self.device).reshape(-1).contiguous()
+        out = torch.zeros(lv.rows, lv.P, device=self.device)
+        _rec.decode(lv, self._tables_ptr, self.st(self.p_log_scale).contiguous(), rows, blocks, idx, n, out, None)
+        return out
+
+    # ------------------------------------------------------------------- training --
+    def _adam_config(self, optimizer):
+        if optimizer is not self._adam_owner:
+            self._adam_owner = optimizer
+            self._lv.reset_adam()
+        g = optimizer.param_groups[0] if optimizer is not None else {}
+        b1, b2 = g.get("betas", (0.9, 0.999))
+        return dict(lr=float(g.get("lr", 2e-4)), b1=float(b1), b2=float(b2), eps=float(g.get("eps", 1e-8)))
+
+    def fit_step(self, x, y, epoch, adam_cfg, sample_size=5, eps=None, anneal=None):
+        """One fused step: forward, loss, backward, (annealing), Adam (test_model.py:622-635)."""
+        lv, eng = self._lv, self.engine
+        S = sample_size
+        noise = self._noise(epoch, eps)
+        ws = eng.forward_features(lv, S, noise)
+        # d/dy of N * mean_{n,s,pix,c} (y_pred - y)^2
+        coef = 2.0 / (S * eng.pix * eng.out)
+        eng.mlp(ws, lv.rows, S, x, mode=1, y=y, coef=coef)
+        eng.backward_features(ws, lv.rows, S)
+        do_anneal = (epoch % self.kl_adjust_gap == 0) if anneal is None else anneal
+        if do_anneal:
+            eng.group_kl(lv)            # KL of the pre-step posterior ...
+        eng.update(lv, ws, S, noise, with_data_grads=True, adam=adam_cfg)
+        if do_anneal:                   # ... beta changes only after this step's gradient (test_model.py:629-634)
+            eng.anneal(lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer, float(self.bit_per_group))
+        return ws
+
+    def train(self, x=True, y=None, n_epochs=0, optimizer=None, verbose=False, sample_size=5):
+        if isinstance(x, bool):          # nn.Module.train(mode) / .eval() compatibility
+            return super().train(x)
+        cfg = self._adam_config(optimizer)
+        x = x.to(self.device)
+        y = y.to(self.device, torch.float32).contiguous()
+        it = range(n_epochs)
+        if verbose:
+            from tqdm import tqdm
+            it = tqdm(it)
+        for epoch in it:
+            self.fit_step(x, y, epoch, cfg, sample_size)
+
+    def _report(self, x, y, header):
+        with torch.no_grad():
+            y_pred = self.predict(x.to(self.device)).cpu()
+            distortion = np.mean(metric(y.cpu().numpy(), y_pred.numpy(), self.dataset))
+        kl_bits = self.update_annealing_factors(False) / np.log(2.)
+        print(header + " Average Distortion %.4f" % distortion, flush=True)
+        print("Bits per group: ave %.2f" % kl_bits.mean() + " max %.2f" % kl_bits.max(), flush=True)
+
+    def optimize_posteriors(self, x, y, n_epochs, lr, verbose):
+        if verbose:
+            self._report(x, y, "Initialization:")
+            print(' ')
+            print("Start to optimize posteriors...", flush=True)
+        optimizer = torch.optim.Adam(self.parameters(), lr=lr)
+        self.train(x=x, y=y, n_epochs=n_epochs, optimizer=optimizer, verbose=verbose)
+        if verbose:
+            self._report(x, y, "Optimization Finished.")
+
+    def compress_posteriors(self, x, y, n_epochs_finetune, h_n_epochs_finetune=None, hh_n_epochs_finetune=None,
+                            verbose=False, lr=2e-4, fine_tune_gap=1, compress_from_group_with_largest_kl=True):
+        """Progressive coding: each round codes one block per row, then re-fits the
+        remaining blocks (test_model.py:800-856)."""
+        if verbose:
+            print("Start to compress posteriors by A* coding...", flush=True)
+        if not hasattr(self, "compressed_num"):
+            self.compressed_num = 0
+        lv = self._lv
+        print_step = set(np.round(np.linspace(0, self.n_groups, 10)).astype(int).tolist())
+        it = range(self.compressed_num, self.n_groups)
+        if verbose:
+            from tqdm import tqdm
+            it = tqdm(it)
+        for _i in it:
+            if compress_from_group_with_largest_kl:
+                self.compress_round()
+            else:
+                self.compress_round(torch.full((lv.rows,), _i, dtype=torch.int32, device=self.device))
+            self.compressed_num += 1
+            if self.compressed_num % fine_tune_gap == 0:
+                optimizer = torch.optim.Adam(self.parameters(), lr=lr)   # fresh moments each round
+                self.train(x, y, n_epochs=n_epochs_finetune, optimizer=optimizer, verbose=False)
+            if verbose and _i in print_step:
+                with torch.no_grad():
+                    y_pred = self.predict(x.to(self.device)).cpu()
+                    distortion = np.mean(metric(y.cpu().numpy(), y_pred.numpy(), self.dataset))
+                kl_bits = self.update_annealing_factors(False) / np.log(2.)
+                open_ = ~self.compressed_mask_groupwise
+                if open_.any():
+                    print("Compress progress: %d; " % (100 * self.compressed_num / self.n_groups),
+                          "Average Distortion %.4f; " % distortion,
+                          "KL in uncompressed groups: MAX %.3f" % kl_bits[open_].max(),
+                          "AVE %.3f. " % kl_bits[open_].mean(), flush=True)
+        with torch.no_grad():
+            y_pred = self.predict(x.to(self.device)).cpu()
+            distortion = metric(y.cpu().numpy(), y_pred.numpy(), self.dataset)
+        if verbose:
+            print("Optimization Finished. Average Distortion %.4f" % np.mean(distortion), flush=True)
+        return distortion

@@ -1,0 +1,56 @@
+"""Build product-side (recombiner_b200) models from the shared synthetic cases."""
+import contextlib
+import io
+
+import numpy as np
+import torch
+
+from oracle import cases
+from oracle import recombiner_oracle as orc
+
+
+def product_mappings(case, device):
+    from recombiner_b200.prior_model import LinearTransform, Upsample
+    shape = case["shape"]
+    lt = LinearTransform(shape.dims)
+    with torch.no_grad():
+        for p, a in zip(lt.A, case["A"]):
+            p.copy_(a)
+    up = Upsample(shape.data_dim, shape.paddings, shape.layer_scales)
+    up.load_state_dict({k: v.clone() for k, v in case["w_up"].items()})
+    return lt.to(device), up.to(device)
+
+
+def product_test_model(case, dataset, device="cuda", quiet=True):
+    from recombiner_b200.test_model import TestBNNmodel
+    shape = case["shape"]
+    lt, up = product_mappings(case, device)
+    L = case["lvl1"]
+    ctx = contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()
+    with ctx:
+        m = TestBNNmodel(in_dim=shape.dims[0], hidden_dims=shape.dims[1:-1], out_dim=shape.dims[-1],
+                         number_of_datapoints=case["rows"], upsample_factors=shape.upsample_factors,
+                         latent_dim=shape.latent_dim, data_dim=shape.data_dim, pixel_sizes=shape.pixel_sizes,
+                         patch=shape.patch, patch_nums=shape.patch_nums, hierarchical_patch_nums=shape.hier,
+                         dataset=dataset, linear_transform=lt, upsample_net=up,
+                         p_loc=L["p_loc"], p_log_scale=L["p_log_scale"], init_log_scale=-4.0,
+                         param_to_group=L["param_to_group"], group_to_param=L["group_to_param"],
+                         n_groups=L["n_groups"], group_start_index=L["group_start"], group_end_index=L["group_end"],
+                         group_idx=L["group_idx"], device=device, random_seed=42,
+                         layer_scales=shape.layer_scales, paddings=shape.paddings)
+    with torch.no_grad():
+        m.loc.copy_(L["loc"])
+        m.log_scale.copy_(L["log_scale"])
+        m._lv.mask.copy_(L["mask"])
+        m._lv.sample.copy_(L["sample"])
+        m._lv.coded.copy_(torch.from_numpy(L["coded"].astype(np.uint8)))
+        m._lv.beta.copy_(L["beta"])
+    return m
+
+
+def oracle_level(L, requires_grad=True):
+    return orc.Level(loc=L["loc"].clone().requires_grad_(requires_grad),
+                     log_scale=L["log_scale"].clone().requires_grad_(requires_grad),
+                     p_loc=L["p_loc"], p_log_scale=L["p_log_scale"], group_to_param=L["group_to_param"],
+                     group_idx=L["group_idx"], group_start=L["group_start"], group_end=L["group_end"],
+                     mask=L["mask"].clone(), sample=L["sample"].clone())

@@ -1,0 +1,145 @@
+"""GPU parity of the fit path (north_star (a)): CUDA kernels through the C ABI and
+the drop-in TestBNNmodel API, against the reference goldens and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle import recombiner_oracle as orc
+
+pytestmark = pytest.mark.gpu
+# stated fp32 tolerances: forward 2e-4 rel, gradients 2e-3 rel (atol 1e-6 of the tensor's max)
+FWD = dict(rtol=2e-4, atol=2e-5)
+
+
+def _grad_close(a, ref, rtol=2e-3):
+    np.testing.assert_allclose(a, ref, rtol=rtol, atol=2e-6 * np.abs(ref).max() + 1e-9)
+
+
+def test_library_loads_on_gpu():
+    from recombiner_b200 import _lib
+    assert _lib.load().rcb_version() >= 100
+
+
+@pytest.mark.parametrize("M,N,K", [(70, 99, 99), (256, 1056, 1056), (33, 16, 256), (130, 4096, 512), (5, 33, 33)])
+def test_gemm_against_fp32_matmul(M, N, K):
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    lda, ldb = (K + 3) // 4 * 4, (N + 3) // 4 * 4
+    A = torch.zeros(M, lda); A[:, :K] = torch.randn(M, K, generator=g)
+    B = torch.zeros(K, ldb); B[:, :N] = torch.randn(K, N, generator=g)
+    bias = torch.randn(8, generator=g)
+    Ad, Bd, bd = A.cuda(), B.cuda(), bias.cuda()
+    Cd = torch.zeros(M, ldb, device="cuda")
+    check(lib.rcb_gemm(ptr(Ad), lda, ptr(Bd), ldb, ptr(Cd), ldb, M, N, K, None, 1, 0, 0, 0, stream()))
+    ref = A[:, :K].double() @ B[:, :N].double()
+    np.testing.assert_allclose(Cd[:, :N].cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    # bias + leaky-relu epilogue, accumulate, transposed-A
+    check(lib.rcb_gemm(ptr(Ad), lda, ptr(Bd), ldb, ptr(Cd), ldb, M, N, K, ptr(bd), 8, 1, 0, 0, stream()))
+    ref2 = torch.nn.functional.leaky_relu(ref + bias[torch.arange(N) % 8].double(), 0.01)
+    np.testing.assert_allclose(Cd[:, :N].cpu().numpy(), ref2.numpy(), rtol=1e-4, atol=1e-4)
+    ldm = (M + 3) // 4 * 4
+    At = torch.zeros(K, ldm); At[:, :M] = A[:, :K].t()
+    Atd = At.cuda()
+    Cd.fill_(1.0)
+    check(lib.rcb_gemm(ptr(Atd), ldm, ptr(Bd), ldb, ptr(Cd), ldb, M, N, K, None, 1, 0, 1, 1, stream()))
+    np.testing.assert_allclose(Cd[:, :N].cpu().numpy(), (ref + 1.0).numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name,n_data,S", [("cifar", 3, 2), ("protein", 4, 3)])
+def test_upsampler_matches_oracle(name, n_data, S):
+    """fold + (dense | polyphase) kernels == nearest-upsample + conv of the oracle."""
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case(name, n_data, S)
+    m = product_test_model(case, name)
+    lv, eng = m._lv, m.engine
+    noise = m._noise(None, case["eps"])
+    ws = eng.forward_features(lv, S, noise)
+    lpe = ws["lpe"].cpu().view(lv.rows, S, -1).permute(1, 0, 2).contiguous()        # (S, N, L)
+    pe_ref = orc.latent_to_pe(case["w_up"], lpe, case["shape"])                      # (N, S, pix, 16)
+    pe = ws["pe"].cpu().view(lv.rows, S, eng.pix, 16)
+    np.testing.assert_allclose(pe.numpy(), pe_ref.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,dataset,n_data,S", [("cifar", "cifar", 3, 2), ("protein", "protein", 4, 3)])
+def test_predict_loss_and_grads_match_reference(golden, name, dataset, n_data, S):
+    from tests.helpers import product_test_model
+    g = golden("fit_" + name)
+    case = cases.make_fit_case(name, n_data, S)
+    m = product_test_model(case, dataset)
+    y = case["y"].cuda()
+    y_pred = m.predict(case["x"].cuda(), None, S, eps=case["eps"])
+    np.testing.assert_allclose(y_pred.detach().cpu().numpy(), g["y_pred"] if S > 1 else g["y_pred"][:, 0], **FWD)
+    mse = torch.mean((y_pred - y[:, None]) ** 2) * y.shape[0]
+    kl = m.calculate_kl()
+    assert mse.item() == pytest.approx(float(g["mse"]), rel=1e-4)
+    assert kl.item() == pytest.approx(float(g["kl"]), rel=1e-4)
+    (mse + kl).backward()
+    _grad_close(m.loc.grad.cpu().numpy(), g["grad_loc"])
+    _grad_close(m.log_scale.grad.cpu().numpy(), g["grad_log_scale"])
+    # per-block KL and the annealing rule
+    kls = m.update_annealing_factors(True)
+    np.testing.assert_allclose(kls, g["group_kl"], rtol=2e-5)
+    np.testing.assert_allclose(m.kl_beta.cpu().numpy(), g["beta_after"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,n_data,S", [("cifar", 3, 2), ("protein", 4, 3)])
+def test_fused_step_matches_oracle_adam(name, n_data, S):
+    """fit_step (fused loss+backward+Adam, beta annealing) == oracle autograd + torch Adam."""
+    from tests.helpers import oracle_level, product_test_model
+    case = cases.make_fit_case(name, n_data, S)
+    m = product_test_model(case, name)
+    lv = oracle_level(case["lvl1"])
+    opt = torch.optim.Adam([lv.loc, lv.log_scale], lr=2e-4)
+    beta = case["lvl1"]["beta"].clone()
+    x, y = case["x"].cuda(), case["y"].cuda()
+    cfg = dict(lr=2e-4, b1=0.9, b2=0.999, eps=1e-8)
+    m._lv.reset_adam()
+    for step in range(3):
+        m.fit_step(x, y, step, cfg, sample_size=S, eps=case["eps"], anneal=(step == 0))
+        y_pred = orc.predict(case["x"], lv, case["A"], case["w_up"], case["shape"], case["eps"], S)
+        loss = orc.fit_loss(y_pred, case["y"]) + orc.weighted_kl(lv, beta)
+        if step == 0:
+            beta = orc.anneal_beta(beta, orc.group_kl_nats(lv), case["lvl1"]["coded"])
+        opt.zero_grad(); loss.backward(); opt.step()
+    # Adam's first steps are sign-like (|delta| ~ lr): compare the parameter *updates*
+    d_ref = (lv.loc.detach() - case["lvl1"]["loc"]).numpy()
+    d_gpu = (m.loc.detach().cpu() - case["lvl1"]["loc"]).numpy()
+    assert np.abs(d_gpu - d_ref).max() < 0.02 * 6e-4 + 1e-7
+    d_ref = (lv.log_scale.detach() - case["lvl1"]["log_scale"]).numpy()
+    d_gpu = (m.log_scale.detach().cpu() - case["lvl1"]["log_scale"]).numpy()
+    assert np.abs(d_gpu - d_ref).max() < 0.02 * 6e-4 + 1e-7
+    np.testing.assert_allclose(m.kl_beta.cpu().numpy(), beta.numpy(), rtol=1e-6)
+    # coded entries must not move
+    coded = case["lvl1"]["mask"].bool().numpy()
+    sq = float(m.engine.workspace(m._lv.rows, S)["sqerr"].sum().item())
+    assert np.isfinite(sq)
+
+
+def test_philox_noise_statistics_and_reproducibility():
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case("cifar", 8, 4, coded_frac=0.0)
+    m = product_test_model(case, "cifar")
+    with torch.no_grad():
+        m.loc.zero_(); m.log_scale.fill_(3.0)
+    sig = float(torch.nn.functional.softplus(torch.tensor(3.0)) / 6)
+    ws = m.engine.forward_features(m._lv, 4, m._noise(5))
+    hw = ws["hw"][:, :m.engine.W].clone() / sig
+    lpe = ws["lpe"].clone() / sig
+    for t in (hw, lpe):
+        assert abs(float(t.mean())) < 0.01 and abs(float(t.std()) - 1.0) < 0.01
+        assert abs(float((t ** 4).mean()) - 3.0) < 0.1
+    ws2 = m.engine.forward_features(m._lv, 4, m._noise(5))
+    assert torch.equal(ws2["hw"][:, :m.engine.W] / sig, hw)
+    ws3 = m.engine.forward_features(m._lv, 4, m._noise(6))
+    assert not torch.equal(ws3["hw"][:, :m.engine.W] / sig, hw)
+
+
+def test_cpu_device_is_refused():
+    from recombiner_b200._lib import KernelError
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case("cifar", 1, 1)
+    with pytest.raises(KernelError):
+        product_test_model(case, "cifar", device="cpu")
