@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the RECOMBINER hot path (BASELINE.json metric: datapoints compressed/s,
+CIFAR-10-shape 32x32; secondary: REC candidates/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU port of the reference (rank 0)
+
+Workload (configs[1] of BASELINE.json): 1024 synthetic CIFAR-shape images per GPU,
+S=5 MC samples, random-init prior (mu_p=0, sigma_p=softplus(-2)/6), synthetic
+grouping at 0.52 bpp (G blocks of 16 bits).  One *step* = one pass of the fit hot
+path over the batch (sample -> reparam GEMMs -> folded upsampler -> fused SIREN MLP
+fwd+loss+bwd -> conv/reparam data-gradients -> KL-gradient + Adam, beta annealing
+every 10th step), i.e. one iteration of test_model.py:622-635.  One *REC round* codes
+one block of every row (test_model.py:806-818).
+
+A full compression under the reference schedule (main_compression.py:148-162) is
+`steps_full = 30000 + G*max(30000//G, 50)` steps and G rounds, so
+
+    value = datapoints / (steps_full * t_step + G * t_round)      [datapoints compressed/s]
+
+with t_step and t_round both measured live (CUDA events, K timed iterations each,
+after W warm-ups).  The working set of a step (~2 GB) exceeds L2 (126 MB).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS_PER_GPU = 1024
+S = 5
+TOTAL_BITS = 532.0          # -> G = 33..34 blocks, 0.52 bpp on 1024 pixels
+N_CAND = 65536
+
+
+def schedule(G: int):
+    return 30000 + G * max(30000 // G, 50)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+def make_workload(rows: int, seed: int):
+    """Synthetic cifar-shape batch with a random-init prior, built
+    with the product's own host helpers (no oracle import on this arm)."""
+    from recombiner_b200.config import configs
+    from recombiner_b200.prior_model import LinearTransform, Upsample, get_grouping_by_kl
+    from recombiner_b200 import utils
+    cfg = configs["cifar"]
+    g = torch.Generator().manual_seed(seed)
+    coords, _ = utils.to_grid_coordinates_and_features(torch.zeros(1, *cfg["pixel_sizes"]))
+    x1 = utils.fourier_features(coords, cfg["fourier_dim"])
+    y = torch.rand(rows, x1.shape[0], cfg["output_dim"], generator=g)
+    dims = [cfg["input_dim"]] + cfg["hidden_dims"] + [cfg["output_dim"]]
+    W = sum(dims[i + 1] * (dims[i] + 1) for i in range(4))
+    L = int(np.prod([p // u for p, u in zip(cfg["pixel_sizes"], cfg["upsample_factors"])])) * cfg["latent_dim"]
+    P = W + L
+    bits = np.random.RandomState(0).gamma(2.0, 1.0, P)
+    bits *= TOTAL_BITS / bits.sum()
+    gi, gs, ge, g2p, p2g, G, _, _ = get_grouping_by_kl(bits)
+    torch.manual_seed(42)
+    lt = LinearTransform(dims)
+    up = Upsample(cfg["data_dim"], cfg["paddings"], cfg["layerwise_scale_factors"])
+    return dict(cfg=cfg, dims=dims, rows=rows, x=x1[None].expand(rows, -1, -1), y=y, lt=lt, up=up, P=P, W=W, L=L,
+                group_idx=gi, group_start=gs, group_end=ge, g2p=g2p, p2g=p2g, G=G,
+                p_loc=torch.zeros(P), p_log_scale=torch.full((P,), -2.0))
+
+
+def build_model(wl, device, row_offset=0):
+    from recombiner_b200.test_model import TestBNNmodel
+    cfg = wl["cfg"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        return TestBNNmodel(in_dim=cfg["input_dim"], hidden_dims=cfg["hidden_dims"], out_dim=cfg["output_dim"],
+                            number_of_datapoints=wl["rows"], upsample_factors=cfg["upsample_factors"],
+                            latent_dim=cfg["latent_dim"], data_dim=cfg["data_dim"], pixel_sizes=cfg["pixel_sizes"],
+                            patch=cfg["patch"], patch_nums=cfg["patch_nums"],
+                            hierarchical_patch_nums=cfg["hierarchical_patch_nums"], dataset="cifar",
+                            linear_transform=wl["lt"].to(device), upsample_net=wl["up"].to(device),
+                            p_loc=wl["p_loc"], p_log_scale=wl["p_log_scale"], init_log_scale=-4.0,
+                            param_to_group=wl["p2g"], group_to_param=wl["g2p"], n_groups=wl["G"],
+                            group_start_index=wl["group_start"], group_end_index=wl["group_end"],
+                            group_idx=wl["group_idx"], device=device, random_seed=42, initial_beta=1e-8,
+                            row_offset=row_offset, layer_scales=cfg["layerwise_scale_factors"], paddings=cfg["paddings"])
+
+
+def oracle_case(wl):
+    """The same workload in the oracle's input format (CPU baseline leg only)."""
+    from oracle import cases
+    rows, P, G = wl["rows"], wl["P"], wl["G"]
+    lvl = dict(loc=torch.zeros(rows, P), log_scale=torch.full((rows, P), -4.0), p_loc=wl["p_loc"],
+               p_log_scale=wl["p_log_scale"], group_idx=wl["group_idx"], group_start=wl["group_start"],
+               group_end=wl["group_end"], group_to_param=wl["g2p"], param_to_group=wl["p2g"], n_groups=G,
+               coded=np.zeros((rows, G), dtype=bool), mask=torch.zeros(rows, P), sample=torch.zeros(rows, P),
+               beta=torch.full((rows, G), 1e-8))
+    return dict(shape=cases.shape_of("cifar"), rows=rows, A=[a.detach().cpu() for a in wl["lt"].A],
+                w_up={k: v.detach().cpu() for k, v in wl["up"].state_dict().items()},
+                x=wl["x"].contiguous(), y=wl["y"], lvl1=lvl)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- #
+# algorithmic work per launch (DESIGN.md "Kernels"): MACs actually executed
+# ----------------------------------------------------------------------------- #
+def section_flops(items: int):
+    pix, hid, fin, out = 1024, 32, 32, 3
+    mlp_fwd = pix * (fin * hid + 2 * hid * hid + hid * out)
+    mlp_dx = pix * (hid * out + 2 * hid * hid + 16 * hid)          # dx0 only for the 16 pe inputs
+    conv2 = 256 * 64 * 256                                          # out px * oc * (4 taps * 64 ic)
+    conv3 = 1024 * 16 * 256
+    conv1 = 512 * 4096                                              # dense fold of up x4 + conv k5 on 2x2
+    rep = 3 * 1056 * 1056 + 99 * 99
+    macs = {"mlp_fwd_bwd": 2 * mlp_fwd + mlp_dx, "mlp_fwd": mlp_fwd, "conv1_fwd": conv1, "conv1_bwd": conv1,
+            "conv2_fwd": conv2, "conv2_bwd": conv2, "conv3_fwd": conv3, "conv3_bwd": conv3,
+            "reparam_fwd": rep, "reparam_bwd": rep}
+    return {k: 2.0 * v * items for k, v in macs.items()}
+
+
+# ----------------------------------------------------------------------------- #
+# CPU baseline: the oracle port of the reference loop on the host cores
+# ----------------------------------------------------------------------------- #
+def cpu_reference(steps: int, warmup: int, rows: int = 64, pairs: int = 8):
+    from oracle.ref_port import OracleCompressor
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    wl = make_workload(rows, seed=123)
+    G = wl["G"]
+    oc = OracleCompressor(oracle_case(wl))
+    for ep in range(warmup):
+        oc.fit_step(ep, S)
+    t0 = time.perf_counter()
+    for ep in range(steps):
+        oc.fit_step(warmup + ep, S)
+    t_step = (time.perf_counter() - t0) / max(steps, 1)
+    oc.gumbel()
+    blocks = list(range(min(pairs, G)))
+    t_tab0 = time.perf_counter()
+    for b in blocks:
+        oc.table(b)
+    t_table = (time.perf_counter() - t_tab0) / len(blocks)
+    t0 = time.perf_counter()
+    for i, b in enumerate(blocks):
+        oc.code_block(i % rows, b)
+    t_pair = (time.perf_counter() - t0) / len(blocks)
+    steps_full = schedule(G)
+    total = steps_full * t_step + G * rows * t_pair + G * t_table
+    return dict(value=rows / total, t_step=t_step, t_pair=t_pair, t_table=t_table, rows=rows, G=G, threads=threads,
+                cand_per_s=N_CAND / t_pair,
+                sample=f"{rows} cifar-shape rows, S=5: {steps} fit steps after {warmup} warm-ups + {len(blocks)} REC "
+                       f"(row,block) pairs on {threads} threads, extrapolated to the {steps_full}-step/{G}-round schedule")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(max(args.steps, 1), max(args.warmup, 1), rows=64)
+    steps_full = schedule(r["G"])
+    line = {"impl": "reference", "metric": "datapoints compressed/sec (CIFAR-10 32x32)", "value": r["value"],
+            "unit": "datapoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["t_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 fit / f64 REC", "data": "synthetic",
+            "config": {"workload": "cifar-shape 32x32, 64-row bounded sample of the 1024-row batch, S=5, G=%d (0.52 bpp)" % r["G"],
+                       "schedule_steps": steps_full, "rec_rounds": r["G"]},
+            "cpu_baseline": {"value": r["value"], "unit": "datapoints/s", "cores": r["threads"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "rec": {"candidates_per_s": r["cand_per_s"], "s_per_pair": r["t_pair"], "table_build_s_per_block": r["t_table"]},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- #
+# this repo's arm
+# ----------------------------------------------------------------------------- #
+def run_b200(args):
+    import torch.distributed as dist
+    from recombiner_b200 import _lib
+    from recombiner_b200.engine import SectionTimer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    wl = make_workload(ROWS_PER_GPU, seed=1000 + rank)
+    G = wl["G"]
+    m = build_model(wl, dev, row_offset=rank * ROWS_PER_GPU)
+    x_host = wl["x"][:1].clone().pin_memory()            # Fourier inputs are identical for every row
+    y_host = wl["y"].pin_memory()
+    x, y = x_host.to(dev).expand(ROWS_PER_GPU, -1, -1), wl["y"].to(dev)
+    cfg = dict(lr=2e-4, b1=0.9, b2=0.999, eps=1e-8)
+    m._lv.reset_adam()
+    m._ensure_rec(N_CAND)                                # candidate tables + Gumbel built once per prior
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm = max(args.steps, 1), max(args.warmup, 3)
+    step_no = [0]
+
+    def fit_steps(n):
+        for _ in range(n):
+            m.fit_step(x, y, step_no[0], cfg, S)
+            step_no[0] += 1
+
+    # ---- device-resident timing (value)
+    fit_steps(Wm)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    m.engine.timer = SectionTimer()
+    _lib.COUNTERS["launches"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fit_steps(K)
+    e1.record()
+    barrier()
+    t_fit = e0.elapsed_time(e1) / K                       # ms per step
+    launches = _lib.COUNTERS["launches"]
+    sections = m.engine.timer.summary()
+    m.engine.timer = None
+
+    # ---- REC rounds (each codes one block of every row)
+    n_rounds = min(max(2, min(K, 6)), G - 2)
+    m.compress_round()                                    # warm-up round
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.COUNTERS["launches"] = 0
+    r0.record()
+    for _ in range(n_rounds):
+        m.compress_round()
+    r1.record()
+    barrier()
+    t_round = r0.elapsed_time(r1) / n_rounds
+    launches += _lib.COUNTERS["launches"]
+    clk = clocks.stop() if clocks else None
+
+    # ---- end to end through the public call with HOST buffers: each step uploads that
+    # step's inputs from pinned memory and reads the step's loss terms back
+    ws = m.engine.workspace(ROWS_PER_GPU, S)
+    sq_host = torch.empty(ROWS_PER_GPU * S).pin_memory()
+    y_dev, x_dev = torch.empty_like(y), torch.empty(1, *x.shape[1:], device=dev)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        x_dev.copy_(x_host, non_blocking=True)
+        y_dev.copy_(y_host, non_blocking=True)
+        m.fit_step(x_dev.expand(ROWS_PER_GPU, -1, -1), y_dev, step_no[0], cfg, S)
+        step_no[0] += 1
+        sq_host.copy_(ws["sqerr"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    f1.record()
+    barrier()
+    t_e2e = f0.elapsed_time(f1) / K
+    h2d = x_host.numel() * 4 + y_host.numel() * 4
+    d2h = sq_host.numel() * 4
+
+    times = torch.tensor([t_fit, t_round, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_fit, t_round, t_e2e = (float(v) for v in times.cpu())
+
+    if rank == 0:
+        pk = peaks()
+        steps_full = schedule(G)
+        n_total = ROWS_PER_GPU * world
+        value = n_total / ((steps_full * t_fit + G * t_round) * 1e-3)
+        e2e = n_total / ((steps_full * t_e2e + G * t_round) * 1e-3)
+        flops = section_flops(ROWS_PER_GPU * S)
+        timed = {k: v[1] for k, v in sections.items()}
+        dom = max((k for k in timed if k in flops), key=lambda k: timed[k])
+        achieved = flops[dom] / (timed[dom] * 1e-3) / 1e12
+        step_flops = sum(flops[k] for k in timed if k in flops)
+        cand_per_s = ROWS_PER_GPU * world * N_CAND / (t_round * 1e-3)
+        cpu = cpu_reference(3, 1, rows=64) if not args.no_cpu_baseline else None
+        line = {
+            "metric": "datapoints compressed/sec (CIFAR-10 32x32)", "value": value, "unit": "datapoints/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": t_fit, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 fit (SIMT FFMA) / f64 REC", "data": "synthetic",
+            "config": {"workload": "cifar-shape 32x32, %d rows/GPU, S=5, G=%d blocks x 16 bit (0.52 bpp), "
+                                   "random-init prior" % (ROWS_PER_GPU, G),
+                       "schedule_steps": steps_full, "rec_rounds": G, "rec_ms_per_round": t_round,
+                       "timed": "K fit steps + %d REC rounds, CUDA events, max over ranks" % n_rounds,
+                       "l2": "per-step working set ~2 GB > 126 MB L2 (no flush needed)",
+                       "step_algorithmic_tflop": step_flops / 1e12,
+                       "step_tflops": step_flops / (t_fit * 1e-3) / 1e12},
+            "e2e": {"value": e2e, "unit": "datapoints/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tf"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                         "note": "fp32 SIMT parity path; executed (polyphase) FLOPs; per-launch ms: "
+                                 + ", ".join(f"{k}={v:.3f}" for k, v in sorted(timed.items(), key=lambda kv: -kv[1]))},
+            "rec": {"candidates_per_s": cand_per_s, "ms_per_round": t_round, "pairs_per_round": ROWS_PER_GPU * world},
+            "clocks": clk,
+        }
+        if cpu:
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": "datapoints/s", "cores": cpu["threads"], "kind": "port",
+                                    "sample": cpu["sample"], "rec_candidates_per_s": cpu["cand_per_s"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,4 @@
+"""Drop-in module name of the reference (`import config`): re-exports recombiner_b200.config.
+Prior checkpoints pickle `prior_model.LinearTransform` / `prior_model.Upsample` objects
+(main_prior_training.py:334-335), so these top-level names must stay importable."""
+from recombiner_b200.config import *  # noqa: F401,F403

@@ -105,7 +105,12 @@ def load() -> C.CDLL:
     return lib
 
 
+COUNTERS = {"launches": 0}
+
+
 def check(rc: int, what: str = "") -> None:
+    """Every C-ABI call launches exactly one kernel of ours and goes through here."""
+    COUNTERS["launches"] += 1
     if rc != 0:
         msg = load().rcb_last_error().decode("utf-8", "replace")
         raise KernelError(f"{what or 'librecombiner_b200'} failed (rc={rc}): {msg}")

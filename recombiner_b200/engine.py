@@ -82,8 +82,47 @@ class LevelState:
         self.adam = dict(m1_loc=z(), v_loc=z(), m1_ls=z(), v_ls=z(), t=0)
 
 
+class SectionTimer:
+    """CUDA-event brackets around named kernel launches on the launching stream
+    (bench.py uses this for the per-kernel roofline; disabled by default)."""
+
+    def __init__(self):
+        self.events = {}
+
+    def begin(self, name):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self.events.setdefault(name, []).append(ev)
+        ev[0].record()
+        return ev
+
+    @staticmethod
+    def end(ev):
+        ev[1].record()
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in self.events.items()}
+
+
+class _Section:
+    def __init__(self, timer, name):
+        self.timer, self.name = timer, name
+
+    def __enter__(self):
+        self.ev = self.timer.begin(self.name) if self.timer is not None else None
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            SectionTimer.end(self.ev)
+        return False
+
+
 class FitEngine:
     """Kernel sequencing for one modality shape (non-patch modalities: cifar, protein)."""
+    timer: Optional[SectionTimer] = None
+
+    def section(self, name):
+        return _Section(self.timer, name)
 
     def __init__(self, dims, data_dim, pixel_sizes, upsample_factors, latent_dim, layer_scales, paddings,
                  w0, device):
@@ -190,7 +229,10 @@ class FitEngine:
         if x.shape[1] != self.pix or x.shape[2] != self.n_f:
             raise KernelError(f"x has shape {tuple(x.shape)}, expected (rows, {self.pix}, {self.n_f})")
         x = x.to(device=self.device, dtype=torch.float32)
-        shared = bool((x == x[:1]).all().item()) if x.shape[0] > 1 else True
+        if x.shape[0] == 1 or x.stride(0) == 0:          # broadcast view: one x for every row
+            shared = True
+        else:
+            shared = bool((x == x[:1]).all().item())
         if shared:
             xt, stride = x[0].t().contiguous(), 0
         else:
@@ -223,21 +265,26 @@ class FitEngine:
         ws = self.workspace(lv.rows, S)
         items = lv.rows * S
         st = stream()
-        self._sample(lv, ws, S, noise)
-        for l, c in enumerate(self.counts):
-            self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
-                       ws["wt"], self.offsets[l], self.ldw, items, c, c)
+        with self.section("sample"):
+            self._sample(lv, ws, S, noise)
+        with self.section("reparam_fwd"):
+            for l, c in enumerate(self.counts):
+                self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
+                           ws["wt"], self.offsets[l], self.ldw, items, c, c)
         g1, g2, g3 = self.geoms
-        if self.dense1:
-            self._gemm(ws["lpe"], 0, self.L, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
-                       items, self.M1.shape[1], self.L, bias=self.conv_b[0], bias_mod=g1.oc, act=1)
-        else:
-            check(self.lib.rcb_upconv_fwd(ptr(ws["lpe"]), ptr(self.w_eff[0]), ptr(self.conv_b[0]), ptr(ws["a1"]),
-                                          C.byref(g1), items, 1, st), "rcb_upconv_fwd[1]")
-        check(self.lib.rcb_upconv_fwd(ptr(ws["a1"]), ptr(self.w_eff[1]), ptr(self.conv_b[1]), ptr(ws["a2"]),
-                                      C.byref(g2), items, 1, st), "rcb_upconv_fwd[2]")
-        check(self.lib.rcb_upconv_fwd(ptr(ws["a2"]), ptr(self.w_eff[2]), ptr(self.conv_b[2]), ptr(ws["pe"]),
-                                      C.byref(g3), items, 0, st), "rcb_upconv_fwd[3]")
+        with self.section("conv1_fwd"):
+            if self.dense1:
+                self._gemm(ws["lpe"], 0, self.L, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
+                           items, self.M1.shape[1], self.L, bias=self.conv_b[0], bias_mod=g1.oc, act=1)
+            else:
+                check(self.lib.rcb_upconv_fwd(ptr(ws["lpe"]), ptr(self.w_eff[0]), ptr(self.conv_b[0]), ptr(ws["a1"]),
+                                              C.byref(g1), items, 1, st), "rcb_upconv_fwd[1]")
+        with self.section("conv2_fwd"):
+            check(self.lib.rcb_upconv_fwd(ptr(ws["a1"]), ptr(self.w_eff[1]), ptr(self.conv_b[1]), ptr(ws["a2"]),
+                                          C.byref(g2), items, 1, st), "rcb_upconv_fwd[2]")
+        with self.section("conv3_fwd"):
+            check(self.lib.rcb_upconv_fwd(ptr(ws["a2"]), ptr(self.w_eff[2]), ptr(self.conv_b[2]), ptr(ws["pe"]),
+                                          C.byref(g3), items, 0, st), "rcb_upconv_fwd[3]")
         return ws
 
     def mlp(self, ws, rows: int, S: int, x, mode: int, y=None, dy=None, coef: float = 0.0):
@@ -249,7 +296,8 @@ class FitEngine:
         a.x_row_stride = stride
         a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
         a.coef, a.w0 = coef, self.w0
-        check(self.lib.rcb_mlp(C.byref(a), stream()), "rcb_mlp")
+        with self.section("mlp_fwd" if mode == 0 else "mlp_fwd_bwd"):
+            check(self.lib.rcb_mlp(C.byref(a), stream()), "rcb_mlp")
 
     # ----------------------------------------------------------------- backward --
     def backward_features(self, ws, rows: int, S: int):
@@ -257,19 +305,23 @@ class FitEngine:
         items = rows * S
         st = stream()
         g1, g2, g3 = self.geoms
-        check(self.lib.rcb_upconv_bwd(ptr(ws["d_pe"]), ptr(self.w_eff_t[2]), ptr(ws["a2"]), ptr(ws["d_a2"]),
-                                      C.byref(g3), items, st), "rcb_upconv_bwd[3]")
-        check(self.lib.rcb_upconv_bwd(ptr(ws["d_a2"]), ptr(self.w_eff_t[1]), ptr(ws["a1"]), ptr(ws["d_a1"]),
-                                      C.byref(g2), items, st), "rcb_upconv_bwd[2]")
-        if self.dense1:
-            self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, self.L,
-                       items, self.L, self.M1T.shape[0])
-        else:
-            check(self.lib.rcb_upconv_bwd(ptr(ws["d_a1"]), ptr(self.w_eff_t[0]), None, ptr(ws["d_lpe"]),
-                                          C.byref(g1), items, st), "rcb_upconv_bwd[1]")
-        for l, c in enumerate(self.counts):
-            self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
-                       ws["d_hw"], self.offsets[l], self.ldw, items, c, c)
+        with self.section("conv3_bwd"):
+            check(self.lib.rcb_upconv_bwd(ptr(ws["d_pe"]), ptr(self.w_eff_t[2]), ptr(ws["a2"]), ptr(ws["d_a2"]),
+                                          C.byref(g3), items, st), "rcb_upconv_bwd[3]")
+        with self.section("conv2_bwd"):
+            check(self.lib.rcb_upconv_bwd(ptr(ws["d_a2"]), ptr(self.w_eff_t[1]), ptr(ws["a1"]), ptr(ws["d_a1"]),
+                                          C.byref(g2), items, st), "rcb_upconv_bwd[2]")
+        with self.section("conv1_bwd"):
+            if self.dense1:
+                self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, self.L,
+                           items, self.L, self.M1T.shape[0])
+            else:
+                check(self.lib.rcb_upconv_bwd(ptr(ws["d_a1"]), ptr(self.w_eff_t[0]), None, ptr(ws["d_lpe"]),
+                                              C.byref(g1), items, st), "rcb_upconv_bwd[1]")
+        with self.section("reparam_bwd"):
+            for l, c in enumerate(self.counts):
+                self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
+                           ws["d_hw"], self.offsets[l], self.ldw, items, c, c)
 
     def update(self, lv: LevelState, ws, S: int, noise: Noise, *, with_data_grads: bool, adam: Optional[dict],
                g_loc=None, g_log_scale=None, grad_scale: float = 1.0, kl_out: Optional[torch.Tensor] = None):
@@ -298,7 +350,8 @@ class FitEngine:
             a.adam_bc2_sqrt = math.sqrt(1.0 - adam["b2"] ** t)
         else:
             a.adam = 0
-        check(self.lib.rcb_fit_update(C.byref(a), stream()), "rcb_fit_update")
+        with self.section("update"):
+            check(self.lib.rcb_fit_update(C.byref(a), stream()), "rcb_fit_update")
 
     # --------------------------------------------------------------- block KL ----
     def group_kl(self, lv: LevelState) -> torch.Tensor:
