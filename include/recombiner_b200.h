@@ -105,6 +105,18 @@ int rcb_upconv_fwd(const float* src, const float* w_eff, const float* bias, floa
 int rcb_upconv_bwd(const float* d_out, const float* w_eff_t, const float* src_act, float* d_src,
                    const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 
+/* Weight gradients of the learned mappings (prior training only; the mappings are
+ * frozen at compression time).  Autograd backward of prior_model.py:48-57,173-174.
+ *  rcb_upconv_wgrad: d_w_eff[z][tap][ic][oc] = sum_{item,y,x} src_gather * d_out (polyphase
+ *      form, split-K with f32 atomics; d_w_eff is zeroed by the call).
+ *  rcb_unfold_poly / rcb_unfold_dense: adjoint of the folds -> conv layout (oc, ic, ky, kx).
+ *  rcb_colsum: out[c % mod] = sum_r sum_{c' = c (mod mod)} X[r, c']   (bias gradients). */
+int rcb_upconv_wgrad(const float* src, const float* d_out, float* d_w_eff, const rcb_upconv_geom* g,
+                     int items, rcb_stream_t stream);
+int rcb_unfold_poly(const float* d_w_eff, const rcb_upconv_geom* g, float* d_w, rcb_stream_t stream);
+int rcb_unfold_dense(const float* d_m, const rcb_upconv_geom* g, float* d_w, rcb_stream_t stream);
+int rcb_colsum(const float* x, int64_t rows, int cols, int mod, float* out, rcb_stream_t stream);
+
 /* Fused per-item SIREN MLP (test_model.py:347-355 + loss :624-627 + their
  * autograd backward).  mode 0: forward, writes y_pred.  mode 1: forward +
  * squared-error + backward with dy = coef*(y_pred - y).  mode 2: forward +
@@ -151,6 +163,7 @@ typedef struct {
   int64_t seed; int64_t row_offset;
   int src_rows, rows, n_children, S, P, n_w, n_l, ld_hw, G;
   int step, tensor_id, adam;
+  int p_scale_direct;   /* 1: p_log_scale already holds sigma_p (prior training passes scales) */
   /* Adam: step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are computed by the
    * host in f64 exactly as torch.optim.Adam does, then passed as f32. */
   float adam_step_size, adam_bc2_sqrt, b1, b2, adam_eps, beta_scalar, grad_scale;

@@ -42,7 +42,7 @@ class UpdateArgs(C.Structure):
                                  "g_log_scale", "m1_loc", "v_loc", "m1_ls", "v_ls", "kl_out")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("src_rows", "rows", "n_children", "S", "P", "n_w", "n_l", "ld_hw", "G",
-                                   "step", "tensor_id", "adam")] + \
+                                   "step", "tensor_id", "adam", "p_scale_direct")] + \
                [(n, F32) for n in ("adam_step_size", "adam_bc2_sqrt", "b1", "b2", "adam_eps", "beta_scalar",
                                    "grad_scale")]
 
@@ -67,6 +67,10 @@ SIGNATURES = {
     "rcb_fold_dense": [P, C.POINTER(UpconvGeom), P, P, P],
     "rcb_upconv_fwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
+    "rcb_upconv_wgrad": [P, P, P, C.POINTER(UpconvGeom), I32, P],
+    "rcb_unfold_poly": [P, C.POINTER(UpconvGeom), P, P],
+    "rcb_unfold_dense": [P, C.POINTER(UpconvGeom), P, P],
+    "rcb_colsum": [P, I64, I32, I32, P, P],
     "rcb_mlp": [C.POINTER(MlpArgs), P],
     "rcb_fit_update": [C.POINTER(UpdateArgs), P],
     "rcb_group_kl": [P, P, P, P, P, P, P, I32, I32, I32, P],

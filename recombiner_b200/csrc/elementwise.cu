@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
     }
     // ---- closed-form KL(q||p) and its gradient, weighted by the block's beta
     const float beta = a.beta ? a.beta[(int64_t)r * a.G + a.group_idx[q]] : a.beta_scalar;
-    const float mu_p = a.p_loc[q], sig_p = std_transform(a.p_log_scale[q]);
+    const float mu_p = a.p_loc[q], sig_p = a.p_scale_direct ? a.p_log_scale[q] : std_transform(a.p_log_scale[q]);
     const float inv_vp = 1.f / (sig_p * sig_p);
     const float dm = mu - mu_p;
     const float ratio = sig / sig_p;

@@ -56,7 +56,15 @@ class LevelState:
         self.log_scale = log_scale
         self.p_loc = p_loc.detach().to(device=device, dtype=torch.float32).contiguous()
         self.p_log_scale = p_log_scale.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.p_scale_direct = False
+        self.beta_scalar = 0.0
         self.rows, self.P = loc.shape
+        self.adam = None
+        if group_start is None:          # parameter order, no blocks (prior training)
+            self.G = 0
+            self.group_idx = self.group_start = self.group_end = self.g2p = self.p2g = None
+            self.mask = self.sample = self.beta = self.coded = self.idx = self.group_kl = None
+            return
         self.G = int(len(group_start))
         self.group_idx = _i32(group_idx, device)
         self.group_start = _i32(group_start, device)
@@ -75,7 +83,6 @@ class LevelState:
         self.coded = torch.zeros(self.rows, self.G, dtype=torch.uint8, device=device)
         self.idx = torch.zeros(self.rows, self.G, dtype=torch.int32, device=device)
         self.group_kl = torch.zeros(self.rows, self.G, dtype=torch.float64, device=device)
-        self.adam = None
 
     def reset_adam(self):
         z = lambda: torch.zeros(self.rows, self.P, device=self.device)
@@ -252,10 +259,12 @@ class FitEngine:
         a.step, a.tensor_id, a.accumulate = noise.step, 0, 0
         check(self.lib.rcb_fit_sample(C.byref(a), stream()), "rcb_fit_sample")
 
-    def _gemm(self, A, a_off, lda, B, ldb, Cm, c_off, ldc, M, N, K, bias=None, bias_mod=1, act=0, trans_a=0, acc=0):
+    def _gemm(self, A, a_off, lda, B, ldb, Cm, c_off, ldc, M, N, K, bias=None, bias_mod=1, act=0, trans_a=0, acc=0,
+              b_tensor=None, b_off=0):
         pa = A.data_ptr() + 4 * a_off
         pc = Cm.data_ptr() + 4 * c_off
-        check(self.lib.rcb_gemm(pa, lda, ptr(B), ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
+        pb = ptr(B) if b_tensor is None else b_tensor.data_ptr() + 4 * b_off
+        check(self.lib.rcb_gemm(pa, lda, pb, ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
               "rcb_gemm")
 
     def forward_features(self, lv: LevelState, S: int, noise: Noise):
@@ -323,6 +332,47 @@ class FitEngine:
                 self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
                            ws["d_hw"], self.offsets[l], self.ldw, items, c, c)
 
+    def backward_mappings(self, ws, rows: int, S: int):
+        """Gradients of the learned mappings (prior training): dA_l = hw_l^T d_wt_l, and the
+        upsampler's conv weights/biases through the adjoints of the folds.  Call after
+        backward_features (it consumes d_pe, d_a2, d_a1, d_wt)."""
+        items = rows * S
+        st = stream()
+        dev = self.device
+        g = ws.setdefault("map_grads", {})
+        if not g:
+            g["A"] = [torch.zeros(c, _round_up(c, 4), device=dev) for c in self.counts]
+            for i, geo in enumerate(self.geoms):
+                kshape = (geo.oc, geo.ic, geo.ky, geo.kx) if self.data_dim == 2 else (geo.oc, geo.ic, geo.kx)
+                g[f"conv{i + 1}.weight"] = torch.zeros(*kshape, device=dev)
+                g[f"conv{i + 1}.bias"] = torch.zeros(geo.oc, device=dev)
+                ty, tx = (1 if geo.ky == 1 else 2), (1 if geo.kx == 1 else 2)
+                g[f"eff{i}"] = torch.zeros(geo.fy * geo.fx * ty * tx * geo.ic * geo.oc, device=dev)
+            if self.dense1:
+                g["dM1"] = torch.zeros_like(self.M1)
+        with self.section("reparam_wgrad"):
+            for l, c in enumerate(self.counts):
+                self._gemm(ws["hw"], self.offsets[l], self.ldw, None, self.ldw, g["A"][l], 0, g["A"][l].shape[1],
+                           c, c, items, trans_a=1, b_tensor=ws["d_wt"], b_off=self.offsets[l])
+        srcs = [ws["lpe"], ws["a1"], ws["a2"]]
+        douts = [ws["d_a1"], ws["d_a2"], ws["d_pe"]]
+        with self.section("conv_wgrad"):
+            for i, geo in enumerate(self.geoms):
+                out_px = geo.h * geo.fy * geo.w * geo.fx
+                check(self.lib.rcb_colsum(ptr(douts[i]), items * out_px, geo.oc, geo.oc, ptr(g[f"conv{i + 1}.bias"]), st),
+                      "rcb_colsum")
+                if i == 0 and self.dense1:
+                    self._gemm(ws["lpe"], 0, self.L, None, g["dM1"].shape[1], g["dM1"], 0, g["dM1"].shape[1],
+                               self.L, g["dM1"].shape[1], items, trans_a=1, b_tensor=ws["d_a1"], b_off=0)
+                    check(self.lib.rcb_unfold_dense(ptr(g["dM1"]), C.byref(geo), ptr(g["conv1.weight"]), st),
+                          "rcb_unfold_dense")
+                    continue
+                check(self.lib.rcb_upconv_wgrad(ptr(srcs[i]), ptr(douts[i]), ptr(g[f"eff{i}"]), C.byref(geo), items, st),
+                      "rcb_upconv_wgrad")
+                check(self.lib.rcb_unfold_poly(ptr(g[f"eff{i}"]), C.byref(geo), ptr(g[f"conv{i + 1}.weight"]), st),
+                      "rcb_unfold_poly")
+        return g
+
     def update(self, lv: LevelState, ws, S: int, noise: Noise, *, with_data_grads: bool, adam: Optional[dict],
                g_loc=None, g_log_scale=None, grad_scale: float = 1.0, kl_out: Optional[torch.Tensor] = None):
         a = UpdateArgs()
@@ -338,7 +388,8 @@ class FitEngine:
         a.src_rows, a.rows, a.n_children, a.S, a.P = lv.rows, lv.rows, 1, S, lv.P
         a.n_w, a.n_l, a.ld_hw, a.G = self.W, self.L, self.ldw, lv.G
         a.step, a.tensor_id = noise.step, 0
-        a.beta_scalar, a.grad_scale = 0.0, grad_scale
+        a.beta_scalar, a.grad_scale = float(lv.beta_scalar), grad_scale
+        a.p_scale_direct = int(lv.p_scale_direct)
         if adam is not None:
             st_ = lv.adam
             st_["t"] += 1

@@ -86,3 +86,244 @@ def get_grouping(q_loc, q_scale, prior_loc, prior_scale):
     kl = 0.5 * (ratio + ((q_loc - prior_loc) / prior_scale) ** 2 - 1 - ratio.log())
     weights = (kl / np.log(2.)).mean(0).cpu().detach().numpy()
     return get_grouping_by_kl(weights)
+
+
+# --------------------------------------------------------------------------- #
+# prior-training model (prior_model.py:62-262) on the sm_100a kernels
+# --------------------------------------------------------------------------- #
+import math as _math
+
+import torch.nn.functional as _F
+
+from . import _lib as _rcb_lib
+from ._lib import KernelError, check as _check, ptr as _ptr, stream as _stream
+from .utils import count_net_params
+
+
+class PriorBNNmodel(nn.Module):
+    """All training rows' factorised Gaussian posteriors, fitted jointly with the shared
+    mappings (LinearTransform, Upsample) against the current prior.
+
+    Same constructor, attributes (`loc`, `log_scale`, `lpe_loc`, `lpe_log_scale`, `st`,
+    `dims`) and methods (`forward`, `calculate_kl`, `train`) as the reference class.  The
+    weights and the latent grid of a row live in one (rows, W+L) tensor in parameter order
+    so one kernel pass covers both; `loc` / `lpe_loc` are views of it.  Rows may be a shard
+    of the training set: with torch.distributed initialised, `train` all-reduces the
+    shared-mapping gradients every step."""
+
+    def __init__(self, in_dim, hidden_dims, out_dim, train_size, data_dim, pixel_sizes, upsample_factors, latent_dim,
+                 patch, patch_nums, hierarchical_patch_nums, random_seed=42, device="cuda", init_log_scale=-4, c=6.,
+                 w0=30., layer_scales=None, paddings=None, row_offset=0, global_train_size=None):
+        super().__init__()
+        from .engine import FitEngine, LevelState
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise KernelError("recombiner_b200.PriorBNNmodel runs on CUDA (sm_100a) only -- no CPU fallback")
+        if patch:
+            raise NotImplementedError("patch modalities are not wired to the kernels yet")
+        self.random_seed, self.device = random_seed, dev
+        self.n_layers = len(hidden_dims) + 1
+        self.dims = [in_dim] + list(hidden_dims) + [out_dim]
+        self.patch = patch
+        self.act = lambda v: torch.sin(w0 * v)
+        self.st = lambda v: _F.softplus(v, beta=1, threshold=20) / 6
+        self.data_dim, self.train_size, self.latent_dim = data_dim, train_size, latent_dim
+        self.pixel_sizes, self.upsample_factors = pixel_sizes, upsample_factors
+        self.patch_nums, self.hierarchical_patch_nums = patch_nums, hierarchical_patch_nums
+        self.net_params_list, self.cum_param_sizes = count_net_params(in_dim, hidden_dims, out_dim)
+        self.row_offset = int(row_offset)
+        W = int(self.cum_param_sizes[-1])
+        self._lpe_shape = [pixel_sizes[i] // upsample_factors[i] for i in range(data_dim)] + [latent_dim]
+        L = int(np.prod(self._lpe_shape))
+        self._W, self._L = W, L
+        # reference init order under torch.manual_seed(seed): loc (rand), then lpe_loc (randn)
+        # (prior_model.py:100-110).  A shard draws the global tensors and keeps its rows.
+        n_glob = int(global_train_size) if global_train_size is not None else train_size
+        torch.manual_seed(random_seed)
+        w_std = np.sqrt(c / hidden_dims[-1]) / w0
+        loc = torch.rand(n_glob, W) * w_std * 2 - w_std
+        lpe = torch.randn(n_glob, *self._lpe_shape) * 0.1
+        rows = slice(self.row_offset, self.row_offset + train_size)
+        both = torch.cat([loc[rows], lpe[rows].reshape(train_size, L)], 1)
+        self._loc_all = nn.Parameter(both.to(dev).contiguous())
+        self._log_scale_all = nn.Parameter(torch.zeros(train_size, W + L, device=dev) + init_log_scale)
+        self.engine = FitEngine(self.dims, data_dim, pixel_sizes, upsample_factors, latent_dim,
+                                layer_scales if layer_scales is not None else [4, 2, 2],
+                                paddings if paddings is not None else [2, 1, 1], w0, dev)
+        zero = torch.zeros(W + L)
+        self._lv = LevelState(self._loc_all, self._log_scale_all, zero, zero, None, None, None, None, None, 0.0, dev)
+        self._lv.p_scale_direct = True
+        self._call = 0
+
+    # views with the reference's attribute names
+    @property
+    def loc(self):
+        return self._loc_all[:, :self._W]
+
+    @property
+    def log_scale(self):
+        return self._log_scale_all[:, :self._W]
+
+    @property
+    def lpe_loc(self):
+        return self._loc_all[:, self._W:].reshape(self.train_size, *self._lpe_shape)
+
+    @property
+    def lpe_log_scale(self):
+        return self._log_scale_all[:, self._W:].reshape(self.train_size, *self._lpe_shape)
+
+    def group_to_layer(self, params, layer_idx):
+        lo = 0 if layer_idx == 0 else self.cum_param_sizes[layer_idx - 1]
+        return params[..., lo:self.cum_param_sizes[layer_idx]]
+
+    def layer_to_weight(self, in_dim, out_dim, layer_param):
+        return layer_param[:, out_dim:].reshape(-1, in_dim, out_dim), layer_param[:, :out_dim]
+
+    # ------------------------------------------------------------------ pieces --
+    def _noise(self, eps=None, step=0):
+        from .engine import Noise
+        if eps is not None:
+            return Noise(eps_w=eps["w"].to(self.device).contiguous(),
+                         eps_l=eps["lpe"].to(self.device).reshape(1, self.train_size, self._L).contiguous())
+        base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        return Noise(seed=((int(self.random_seed) & 0x7fffffff) << 32) | base, step=step, row_offset=self.row_offset)
+
+    def _set_prior(self, prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale):
+        lv = self._lv
+        lv.p_loc = torch.cat([prior_loc.reshape(-1), prior_lpe_loc.reshape(-1)]).to(self.device, torch.float32).contiguous()
+        lv.p_log_scale = torch.cat([prior_scale.reshape(-1), prior_lpe_scale.reshape(-1)]).to(self.device, torch.float32).contiguous()
+
+    def forward(self, x, linear_transform, upsample_net, gradient_through_A=True, eps=None):
+        """Single-sample reconstruction (rows, pixels, out) (prior_model.py:129-179).  Evaluation
+        only: gradients are produced by `train` / `loss_and_grads`, not by autograd."""
+        assert x.shape[0] == self.train_size
+        eng = self.engine
+        eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
+        ws = eng.forward_features(self._lv, 1, self._noise(eps))
+        eng.mlp(ws, self.train_size, 1, x.to(self.device), mode=0)
+        return ws["y_pred"].view(self.train_size, eng.pix, eng.out).clone()
+
+    def _kl(self, beta: float):
+        """(sum of beta*KL as f64 device scalar, d/dloc, d/dlog_scale) of the current posterior."""
+        lv = self._lv
+        kl = torch.zeros(1, dtype=torch.float64, device=self.device)
+        g_loc, g_ls = torch.empty_like(self._loc_all.data), torch.empty_like(self._log_scale_all.data)
+        lv.beta_scalar = beta
+        from .engine import Noise
+        self.engine.update(lv, None, 1, Noise(), with_data_grads=False, adam=None, g_loc=g_loc, g_log_scale=g_ls, kl_out=kl)
+        return kl, g_loc, g_ls
+
+    def calculate_kl(self, prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc=None, prior_h_scale=None,
+                     prior_hh_loc=None, prior_hh_scale=None):
+        """sum KL(q || p) over weights and latent grid (prior_model.py:181-200)."""
+        self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale)
+        return self._kl(1.0)[0].to(torch.float32).reshape(())
+
+    def loss_and_grads(self, x, y, priors, linear_transform, upsample_net, kl_beta, eps=None, training_mappings=True):
+        """One forward/backward without an optimiser step (parity tests): returns
+        (mse*N, sum KL, gradient dict) of loss = N*mean((y_hat-y)^2) + kl_beta * sum KL."""
+        eng, lv, N = self.engine, self._lv, self.train_size
+        self._set_prior(*priors[:4])
+        eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
+        noise = self._noise(eps)
+        ws = eng.forward_features(lv, 1, noise)
+        eng.mlp(ws, N, 1, x.to(self.device), mode=1, y=y.to(self.device).contiguous(), coef=2.0 / (eng.pix * eng.out))
+        eng.backward_features(ws, N, 1)
+        grads = {}
+        if training_mappings:
+            g = eng.backward_mappings(ws, N, 1)
+            for l, c in enumerate(eng.counts):
+                grads[f"A{l}"] = g["A"][l][:, :c].clone()
+            for k in ("conv1", "conv2", "conv3"):
+                grads[k + ".weight"], grads[k + ".bias"] = g[k + ".weight"].clone(), g[k + ".bias"].clone()
+        kl = torch.zeros(1, dtype=torch.float64, device=self.device)
+        g_loc, g_ls = torch.empty_like(self._loc_all.data), torch.empty_like(self._log_scale_all.data)
+        lv.beta_scalar = float(kl_beta)
+        eng.update(lv, ws, 1, noise, with_data_grads=True, adam=None, g_loc=g_loc, g_log_scale=g_ls, kl_out=kl)
+        W = self._W
+        grads.update(loc=g_loc[:, :W], log_scale=g_ls[:, :W], lpe_loc=g_loc[:, W:].reshape(N, *self._lpe_shape),
+                     lpe_log_scale=g_ls[:, W:].reshape(N, *self._lpe_shape))
+        mse = ws["sqerr"].sum() / (eng.pix * eng.out)
+        return mse, kl / max(float(kl_beta), 1e-300), grads
+
+    def train(self, n_epoch=True, lr=2e-4, x=None, y=None, prior_loc=None, prior_scale=None, prior_lpe_loc=None,
+              prior_lpe_scale=None, prior_h_loc=None, prior_h_scale=None, prior_hh_loc=None, prior_hh_scale=None,
+              linear_transform=None, upsample_net=None, kl_beta=1e-8, training_mappings=True, verbose=False):
+        """n_epoch full-batch Adam steps on loss = N*mean((y_hat-y)^2) + kl_beta*sum KL over the
+        posteriors and (optionally) the mappings (prior_model.py:202-262).  Returns
+        (last mse / N, KL / N, list of per-step ELBOs)."""
+        if isinstance(n_epoch, bool):           # nn.Module.train(mode) / .eval()
+            return super().train(n_epoch)
+        import torch.distributed as dist
+        eng, lv, N = self.engine, self._lv, self.train_size
+        x = x.to(self.device)
+        y = y.to(self.device, torch.float32).contiguous()
+        self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale)
+        lv.beta_scalar = float(kl_beta)
+        lv.reset_adam()                          # the reference re-creates Adam on every call (:224-227)
+        shared = list(linear_transform.parameters()) + list(upsample_net.parameters())
+        for p in shared:
+            p.requires_grad_(True)
+        opt = torch.optim.Adam(shared, lr) if training_mappings else None
+        cfg = dict(lr=float(lr), b1=0.9, b2=0.999, eps=1e-8)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        n_total = N * world
+        coef = 2.0 / (eng.pix * eng.out)
+        stats = torch.zeros(n_epoch, 2, dtype=torch.float64, device=self.device)     # per step: (mse*N, beta*KL)
+        kl_step = torch.zeros(1, dtype=torch.float64, device=self.device)
+        base_noise = self._noise()
+        it = range(n_epoch)
+        if verbose:
+            from tqdm import tqdm
+            it = tqdm(it)
+        up_names = [k for k, _ in upsample_net.named_parameters()]
+        for i in it:
+            eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
+            noise = type(base_noise)(seed=base_noise.seed, step=i, row_offset=self.row_offset)
+            ws = eng.forward_features(lv, 1, noise)
+            eng.mlp(ws, N, 1, x, mode=1, y=y, coef=coef)
+            eng.backward_features(ws, N, 1)
+            if training_mappings:
+                g = eng.backward_mappings(ws, N, 1)
+                flat = [g["A"][l][:, :c].contiguous() for l, c in enumerate(eng.counts)] + [g[k] for k in up_names]
+                if world > 1:
+                    for t in flat:           # shared mappings: gradients are summed over all rows
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                for p, t in zip(shared, flat):
+                    p.grad = t.reshape(p.shape).clone()
+            kl_step.zero_()
+            eng.update(lv, ws, 1, noise, with_data_grads=True, adam=cfg, kl_out=kl_step)
+            if opt is not None:
+                opt.step()
+            stats[i, 0] = ws["sqerr"].sum().double() / (eng.pix * eng.out)
+            stats[i, 1] = kl_step[0]
+        if world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        kl_final = self._kl(1.0)[0]
+        if world > 1:
+            dist.all_reduce(kl_final, op=dist.ReduceOp.SUM)
+        stats = stats.cpu()
+        elbo = (-(stats[:, 0] + stats[:, 1])).tolist()
+        mse_last = float(stats[-1, 0]) if n_epoch > 0 else float("nan")
+        return mse_last / n_total, float(kl_final.item()) / n_total, elbo
+
+
+def em_prior_update(model: "PriorBNNmodel"):
+    """Closed-form prior update from all posteriors (main_prior_training.py:157-172):
+    mu_p = mean_n mu_q, sigma_p = sqrt(mean_n sigma_q^2 + var_n mu_q) (unbiased variance),
+    from f64 sufficient statistics that are all-reduced across shards.
+    Returns (prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale)."""
+    import torch.distributed as dist
+    lib = _rcb_lib.load()
+    N, P, dev = model.train_size, model._W + model._L, model.device
+    stats = torch.empty(3 * P, dtype=torch.float64, device=dev)
+    _check(lib.rcb_prior_suffstats(_ptr(model._loc_all.data), _ptr(model._log_scale_all.data), _ptr(stats), N, P, _stream()),
+           "rcb_prior_suffstats")
+    n_total = N
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        n_total = N * dist.get_world_size()
+    p_loc, p_scale = torch.empty(P, device=dev), torch.empty(P, device=dev)
+    _check(lib.rcb_prior_from_stats(_ptr(stats), _ptr(p_loc), _ptr(p_scale), n_total, P, _stream()), "rcb_prior_from_stats")
+    W = model._W
+    return (p_loc[:W], p_scale[:W], p_loc[W:].reshape(model._lpe_shape), p_scale[W:].reshape(model._lpe_shape))
