@@ -1,0 +1,93 @@
+"""End-to-end on the GPU through the reference-shaped drivers: train a small prior,
+write/read the reference's checkpoint stream, compress with a short schedule, decode."""
+import io
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _synthetic(n, seed=1):
+    from recombiner_b200 import utils
+    from recombiner_b200.config import configs
+    cfg = configs["cifar"]
+    coords, _ = utils.to_grid_coordinates_and_features(torch.zeros(1, *cfg["pixel_sizes"]))
+    x = utils.fourier_features(coords, cfg["fourier_dim"])[None].repeat(n, 1, 1)
+    g = torch.Generator().manual_seed(seed)
+    # smooth-ish targets so a few steps already reduce the error
+    base = torch.rand(n, 1, 3, generator=g)
+    y = (base + 0.1 * torch.rand(n, 1024, 3, generator=g)).clamp(0, 1)
+    return x, y
+
+
+def test_train_prior_then_compress_and_decode(tmp_path):
+    from recombiner_b200 import main_compression, main_prior_training
+    x, y = _synthetic(16)
+    objects, elbos, _ = main_prior_training.train_prior(x, y, "cifar", max_bitrate=0.5, n_em_iter=3, first_epochs=20,
+                                                        epochs=10, checkpoint_every=1, verbose=False)
+    assert len(elbos) == 40 and np.isfinite(elbos).all() and elbos[-1] > elbos[0]
+    path = str(tmp_path / "PRIOR_train_size_16_max_bitrate=0.500.pkl")
+    main_prior_training.save_checkpoint(path, objects)
+    loaded = main_compression.load_prior(path)
+    grouping, prior = loaded[0], loaded[1]
+    assert len(grouping) == 8 and grouping[5] == len(grouping[1]) and prior[0].shape == (3779,)
+    assert type(loaded[6]).__name__ == "LinearTransform" and type(loaded[7]).__name__ == "Upsample"
+    xt, yt = _synthetic(4, seed=9)
+    distortion, model = main_compression.compress(xt, yt, "cifar", loaded, "cuda", fit_epochs=60, finetune_epochs=2,
+                                                  verbose=0)
+    assert distortion.shape == (4,) and np.isfinite(distortion).all() and distortion.min() > 5.0   # PSNR in dB
+    idx = model.compressed_idx_groupwise
+    assert idx.shape == (4, model.n_groups) and idx.dtype == np.float64
+    assert bool(model._lv.coded.all()) and float(model._lv.beta.abs().max()) == 0.0
+    # receiver: indices + prior + seed reproduce every coded value bit-exactly, and the
+    # reconstruction from decoded values equals the encoder's final reconstruction
+    decoded = model.decode_posteriors(idx)
+    assert torch.equal(decoded, model._lv.sample)
+    buf = io.BytesIO()
+    np.savetxt(buf, idx, delimiter=",")
+    back = np.loadtxt(io.BytesIO(buf.getvalue()), delimiter=",")
+    np.testing.assert_array_equal(back, idx)
+    # fully coded posterior is deterministic (sigma = 1e-15): two predicts agree
+    with torch.no_grad():
+        a = model.predict(xt.cuda(), random_seed=1)
+        b = model.predict(xt.cuda(), random_seed=2)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-5)
+
+
+def test_short_schedule_matches_oracle_port_statistically():
+    """Trajectory-level parity: the same short schedule on the CUDA path (Philox noise) and on
+    the CPU oracle port (torch noise).  Distortion must agree within 0.5 dB and the coded
+    bits per block within 10 % (different noise streams, so no bit-level comparison here)."""
+    from oracle import cases
+    from oracle.ref_port import OracleCompressor
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case("cifar", 4, 5, coded_frac=0.0, total_bits=400.0)
+    L = case["lvl1"]
+    L["beta"] = torch.full_like(L["beta"], 1e-5)
+    L["loc"] = L["p_loc"][None].repeat(4, 1)
+    L["log_scale"] = torch.full_like(L["log_scale"], -4.0)
+    m = product_test_model(case, "cifar")
+    x, y = case["x"].cuda(), case["y"].cuda()
+    cfg = dict(lr=2e-4, b1=0.9, b2=0.999, eps=1e-8)
+    m._lv.reset_adam()
+    n_steps = 150
+    for ep in range(n_steps):
+        m.fit_step(x, y, ep, cfg, 5)
+    oc = OracleCompressor(case)
+    for ep in range(n_steps):
+        oc.fit_step(ep, 5)
+    from recombiner_b200.utils import batch_PSNR
+    with torch.no_grad():
+        yp = m.predict(x, random_seed=7).cpu().numpy()
+    yo = oc.reconstruct().numpy()[:, 0]
+    p_gpu = batch_PSNR(case["y"].numpy(), yp, True).mean()
+    p_cpu = batch_PSNR(case["y"].numpy(), yo, True).mean()
+    assert abs(p_gpu - p_cpu) < 0.5, (p_gpu, p_cpu)
+    from oracle import recombiner_oracle as orc
+    kl_gpu = m.update_annealing_factors(False).sum(1) / np.log(2)
+    kl_cpu = orc.group_kl_nats(oc.lv).sum(1) / np.log(2)
+    np.testing.assert_allclose(kl_gpu, kl_cpu, rtol=0.1)
