@@ -75,6 +75,14 @@ int rcb_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc
              int M, int N, int K, const float* bias, int bias_mod, int act,
              int trans_a, int accumulate, rcb_stream_t stream);
 
+/* Tensor-core variant of rcb_gemm: C[M,N] = A[M,K] @ Bt[N,K]^T with TF32 tcgen05.mma
+ * (fp32 accumulation in TMEM), TMA-fed, both operands K-major -- B is passed
+ * TRANSPOSED ([N,K] row-major, leading dimension ldbt).  Same epilogue as rcb_gemm.
+ * Tolerance vs fp32: ~1e-3 relative (10-bit mantissa operands), stated in the tests. */
+int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, int ldc,
+                int M, int N, int K, const float* bias, int bias_mod, int act,
+                int accumulate, rcb_stream_t stream);
+
 /* Geometry of one nearest-upsample + 'same' conv stage on a channel-last grid
  * (1-D signals use h=1, fy=1, ky=1). prior_model.py:29-45. */
 typedef struct {

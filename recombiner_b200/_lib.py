@@ -63,6 +63,7 @@ SIGNATURES = {
     "rcb_last_error": [],
     "rcb_fit_sample": [C.POINTER(SampleArgs), P],
     "rcb_gemm": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, I32, P],
+    "rcb_gemm_tc": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],
     "rcb_fold_poly": [P, C.POINTER(UpconvGeom), P, P, P],
     "rcb_fold_dense": [P, C.POINTER(UpconvGeom), P, P, P],
     "rcb_upconv_fwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],

@@ -132,7 +132,12 @@ class FitEngine:
         return _Section(self.timer, name)
 
     def __init__(self, dims, data_dim, pixel_sizes, upsample_factors, latent_dim, layer_scales, paddings,
-                 w0, device):
+                 w0, device, precision=None):
+        import os
+        self.precision = precision or os.environ.get("RECOMBINER_PRECISION", "tf32")
+        if self.precision not in ("fp32", "tf32"):
+            raise KernelError(f"unknown precision {self.precision!r}: 'fp32' (SIMT parity path) or 'tf32' (tcgen05)")
+        self.tc = self.precision == "tf32"
         if not torch.cuda.is_available():
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -260,9 +265,15 @@ class FitEngine:
         check(self.lib.rcb_fit_sample(C.byref(a), stream()), "rcb_fit_sample")
 
     def _gemm(self, A, a_off, lda, B, ldb, Cm, c_off, ldc, M, N, K, bias=None, bias_mod=1, act=0, trans_a=0, acc=0,
-              b_tensor=None, b_off=0):
+              b_tensor=None, b_off=0, Bt=None):
+        """C = A @ B.  With `Bt` (= B transposed, [N,K] row-major) and the tf32 mode the
+        tcgen05 kernel is used; otherwise the fp32 SIMT engine."""
         pa = A.data_ptr() + 4 * a_off
         pc = Cm.data_ptr() + 4 * c_off
+        if self.tc and Bt is not None and not trans_a:
+            check(self.lib.rcb_gemm_tc(pa, lda, ptr(Bt), Bt.shape[1], pc, ldc, M, N, K, ptr(bias), bias_mod, act, acc,
+                                       stream()), "rcb_gemm_tc")
+            return
         pb = ptr(B) if b_tensor is None else b_tensor.data_ptr() + 4 * b_off
         check(self.lib.rcb_gemm(pa, lda, pb, ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
               "rcb_gemm")
@@ -279,12 +290,12 @@ class FitEngine:
         with self.section("reparam_fwd"):
             for l, c in enumerate(self.counts):
                 self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
-                           ws["wt"], self.offsets[l], self.ldw, items, c, c)
+                           ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
         g1, g2, g3 = self.geoms
         with self.section("conv1_fwd"):
             if self.dense1:
                 self._gemm(ws["lpe"], 0, self.L, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
-                           items, self.M1.shape[1], self.L, bias=self.conv_b[0], bias_mod=g1.oc, act=1)
+                           items, self.M1.shape[1], self.L, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
             else:
                 check(self.lib.rcb_upconv_fwd(ptr(ws["lpe"]), ptr(self.w_eff[0]), ptr(self.conv_b[0]), ptr(ws["a1"]),
                                               C.byref(g1), items, 1, st), "rcb_upconv_fwd[1]")
@@ -323,14 +334,14 @@ class FitEngine:
         with self.section("conv1_bwd"):
             if self.dense1:
                 self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, self.L,
-                           items, self.L, self.M1T.shape[0])
+                           items, self.L, self.M1T.shape[0], Bt=self.M1)
             else:
                 check(self.lib.rcb_upconv_bwd(ptr(ws["d_a1"]), ptr(self.w_eff_t[0]), None, ptr(ws["d_lpe"]),
                                               C.byref(g1), items, st), "rcb_upconv_bwd[1]")
         with self.section("reparam_bwd"):
             for l, c in enumerate(self.counts):
                 self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
-                           ws["d_hw"], self.offsets[l], self.ldw, items, c, c)
+                           ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])
 
     def backward_mappings(self, ws, rows: int, S: int):
         """Gradients of the learned mappings (prior training): dA_l = hw_l^T d_wt_l, and the

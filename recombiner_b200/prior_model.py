@@ -113,7 +113,7 @@ class PriorBNNmodel(nn.Module):
 
     def __init__(self, in_dim, hidden_dims, out_dim, train_size, data_dim, pixel_sizes, upsample_factors, latent_dim,
                  patch, patch_nums, hierarchical_patch_nums, random_seed=42, device="cuda", init_log_scale=-4, c=6.,
-                 w0=30., layer_scales=None, paddings=None, row_offset=0, global_train_size=None):
+                 w0=30., layer_scales=None, paddings=None, row_offset=0, global_train_size=None, precision=None):
         super().__init__()
         from .engine import FitEngine, LevelState
         dev = torch.device(device)
@@ -149,7 +149,7 @@ class PriorBNNmodel(nn.Module):
         self._log_scale_all = nn.Parameter(torch.zeros(train_size, W + L, device=dev) + init_log_scale)
         self.engine = FitEngine(self.dims, data_dim, pixel_sizes, upsample_factors, latent_dim,
                                 layer_scales if layer_scales is not None else [4, 2, 2],
-                                paddings if paddings is not None else [2, 1, 1], w0, dev)
+                                paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision)
         zero = torch.zeros(W + L)
         self._lv = LevelState(self._loc_all, self._log_scale_all, zero, zero, None, None, None, None, None, 0.0, dev)
         self._lv.p_scale_direct = True

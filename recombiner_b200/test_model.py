@@ -106,7 +106,7 @@ class TestBNNmodel(nn.Module):
                  hh_group_idx=None,
                  w0=30., c=6., random_seed=42, device='cuda', kl_upper_buffer=0., kl_lower_buffer=0.4,
                  kl_adjust_gap=10, initial_beta=1e-8, beta_step_size=0.05, row_offset=0, layer_scales=None,
-                 paddings=None):
+                 paddings=None, precision=None):
         super().__init__()
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -148,7 +148,7 @@ class TestBNNmodel(nn.Module):
 
         cfg_scales = layer_scales if layer_scales is not None else [4, 2, 2]
         self.engine = FitEngine(self.dims, data_dim, pixel_sizes, upsample_factors, latent_dim, cfg_scales,
-                                paddings if paddings is not None else [2, 1, 1], w0, dev)
+                                paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision)
         if linear_transform is not None and upsample_net is not None:
             self.engine.set_mappings(list(linear_transform.A), upsample_net.state_dict())
         self.act = Sine(w0)

@@ -21,7 +21,7 @@ def product_mappings(case, device):
     return lt.to(device), up.to(device)
 
 
-def product_test_model(case, dataset, device="cuda", quiet=True):
+def product_test_model(case, dataset, device="cuda", quiet=True, precision="fp32"):
     from recombiner_b200.test_model import TestBNNmodel
     shape = case["shape"]
     lt, up = product_mappings(case, device)
@@ -37,7 +37,7 @@ def product_test_model(case, dataset, device="cuda", quiet=True):
                          param_to_group=L["param_to_group"], group_to_param=L["group_to_param"],
                          n_groups=L["n_groups"], group_start_index=L["group_start"], group_end_index=L["group_end"],
                          group_idx=L["group_idx"], device=device, random_seed=42,
-                         layer_scales=shape.layer_scales, paddings=shape.paddings)
+                         layer_scales=shape.layer_scales, paddings=shape.paddings, precision=precision)
     with torch.no_grad():
         m.loc.copy_(L["loc"])
         m.log_scale.copy_(L["log_scale"])

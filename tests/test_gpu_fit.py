@@ -143,3 +143,29 @@ def test_cpu_device_is_refused():
     case = cases.make_fit_case("cifar", 1, 1)
     with pytest.raises(KernelError):
         product_test_model(case, "cifar", device="cpu")
+
+
+@pytest.mark.parametrize("name,dataset,n_data,S", [("cifar", "cifar", 3, 2), ("protein", "protein", 4, 3)])
+def test_tf32_tensor_core_mode_within_stated_tolerance(golden, name, dataset, n_data, S):
+    """precision='tf32': reparam + dense conv1 GEMMs on tcgen05 (10-bit-mantissa operands).
+    Stated tolerance: forward <= 5e-3 absolute, loss 1e-3 relative, gradients <= 2 % relative
+    L2 error per tensor (fp32 mode: 2e-4 / 1e-4 / 2e-3 elementwise)."""
+    from tests.helpers import product_test_model
+    g = golden("fit_" + name)
+    case = cases.make_fit_case(name, n_data, S)
+    m = product_test_model(case, dataset, precision="tf32")
+    assert m.engine.tc
+    y = case["y"].cuda()
+    y_pred = m.predict(case["x"].cuda(), None, S, eps=case["eps"])
+    err = np.abs(y_pred.detach().cpu().numpy() - g["y_pred"]).max()
+    mse = torch.mean((y_pred - y[:, None]) ** 2) * y.shape[0]
+    (mse + m.calculate_kl()).backward()
+    rel = {}
+    for k, t in (("grad_loc", m.loc.grad), ("grad_log_scale", m.log_scale.grad)):
+        ref = g[k]
+        rel[k] = float(np.linalg.norm(t.cpu().numpy() - ref) / np.linalg.norm(ref))
+    print(f"[tf32 {name}] forward max abs err {err:.3e}; loss rel err {abs(mse.item() - float(g['mse'])) / float(g['mse']):.3e}; "
+          f"grad rel L2 {rel}")
+    assert err < 5e-3
+    assert mse.item() == pytest.approx(float(g["mse"]), rel=1e-3)
+    assert all(v < 2e-2 for v in rel.values())

@@ -22,7 +22,7 @@ def _model(case):
                       train_size=case["rows"], data_dim=shape.data_dim, pixel_sizes=shape.pixel_sizes,
                       upsample_factors=shape.upsample_factors, latent_dim=shape.latent_dim, patch=False,
                       patch_nums=None, hierarchical_patch_nums=None, device="cuda",
-                      layer_scales=shape.layer_scales, paddings=shape.paddings)
+                      layer_scales=shape.layer_scales, paddings=shape.paddings, precision="fp32")
     W = shape.n_weights
     with torch.no_grad():
         m._loc_all[:, :W] = case["loc"].cuda()
