@@ -57,11 +57,14 @@ typedef struct {
   const float* eps_w;      /* (rows, S, n_w) or NULL */
   const float* eps_l;      /* (S, rows, n_l) or NULL */
   float* hw;               /* (rows*S, ld_hw) */
-  float* lpe;              /* (rows*S, n_l) or NULL */
+  float* lpe;              /* (rows*S, n_l) or NULL; stitched (data*S, sp_total*lpe_c) when lpe_slot != NULL */
+  const int* lpe_slot;     /* patch modalities: (rows_per_datum, n_l/lpe_c) slot of each latent position in the
+                              datum's stitched grid (utils.py:71-90), or NULL */
   int64_t seed;
   int64_t row_offset;      /* global index of row 0 (multi-GPU shards) */
   int rows, S, P, n_w, n_l, ld_hw;
   int step, tensor_id, accumulate;
+  int rows_per_datum, sp_total, lpe_c;   /* used with lpe_slot */
 } rcb_sample_args;
 int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
 
@@ -139,8 +142,12 @@ typedef struct {
   float* d_pe;          /* (items, pix, 16) (modes 1,2) */
   float* d_wt;          /* (items, ld_w)    (modes 1,2) */
   float* sqerr;         /* (items) sum of squared error (mode 1) */
+  const int64_t* pe_base; /* patch modalities: per item, pixel offset of the patch origin inside the stitched
+                             pe / d_pe tensors (utils.py:104-116); NULL = item*pix */
   int64_t x_row_stride; /* 0 if all rows share one x */
+  int64_t pitch_z, pitch_y; /* pixel pitches of the stitched grid (with pe_base) */
   int items, S, pix, n_f, out, ld_w, mode;
+  int ph, pw;           /* patch extent along y and x (pixels); pix = pd*ph*pw (with pe_base) */
   float coef, w0;
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
@@ -165,6 +172,7 @@ typedef struct {
   const float* d_hw;                     /* (rows*S, ld_hw) or NULL */
   const float* d_lpe;                    /* (rows*S, n_l) or NULL */
   const float* eps_w; const float* eps_l;
+  const int* lpe_slot;                   /* as in rcb_sample_args, or NULL */
   float* g_loc; float* g_log_scale;      /* adam=0 outputs */
   float* m1_loc; float* v_loc; float* m1_ls; float* v_ls;  /* Adam state */
   double* kl_out;
@@ -172,6 +180,7 @@ typedef struct {
   int src_rows, rows, n_children, S, P, n_w, n_l, ld_hw, G;
   int step, tensor_id, adam;
   int p_scale_direct;   /* 1: p_log_scale already holds sigma_p (prior training passes scales) */
+  int rows_per_datum, sp_total, lpe_c;   /* used with lpe_slot */
   /* Adam: step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are computed by the
    * host in f64 exactly as torch.optim.Adam does, then passed as f32. */
   float adam_step_size, adam_bc2_sqrt, b1, b2, adam_eps, beta_scalar, grad_scale;

@@ -20,9 +20,10 @@ F64 = C.c_double
 
 class SampleArgs(C.Structure):
     _fields_ = [(n, P) for n in ("loc", "log_scale", "mask", "sample", "g2p", "perm", "row_map",
-                                 "eps_w", "eps_l", "hw", "lpe")] + \
+                                 "eps_w", "eps_l", "hw", "lpe", "lpe_slot")] + \
                [("seed", I64), ("row_offset", I64)] + \
-               [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate")]
+               [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate",
+                                   "rows_per_datum", "sp_total", "lpe_c")]
 
 
 class UpconvGeom(C.Structure):
@@ -30,19 +31,19 @@ class UpconvGeom(C.Structure):
 
 
 class MlpArgs(C.Structure):
-    _fields_ = [(n, P) for n in ("wt", "xt", "pe", "y", "dy", "y_pred", "d_pe", "d_wt", "sqerr")] + \
-               [("x_row_stride", I64)] + \
-               [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode")] + \
+    _fields_ = [(n, P) for n in ("wt", "xt", "pe", "y", "dy", "y_pred", "d_pe", "d_wt", "sqerr", "pe_base")] + \
+               [("x_row_stride", I64), ("pitch_z", I64), ("pitch_y", I64)] + \
+               [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode", "ph", "pw")] + \
                [("coef", F32), ("w0", F32)]
 
 
 class UpdateArgs(C.Structure):
     _fields_ = [(n, P) for n in ("loc", "log_scale", "mask", "p_loc", "p_log_scale", "beta", "group_idx", "p2g",
-                                 "perm_inv", "row_children", "d_hw", "d_lpe", "eps_w", "eps_l", "g_loc",
+                                 "perm_inv", "row_children", "d_hw", "d_lpe", "eps_w", "eps_l", "lpe_slot", "g_loc",
                                  "g_log_scale", "m1_loc", "v_loc", "m1_ls", "v_ls", "kl_out")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("src_rows", "rows", "n_children", "S", "P", "n_w", "n_l", "ld_hw", "G",
-                                   "step", "tensor_id", "adam", "p_scale_direct")] + \
+                                   "step", "tensor_id", "adam", "p_scale_direct", "rows_per_datum", "sp_total", "lpe_c")] + \
                [(n, F32) for n in ("adam_step_size", "adam_bc2_sqrt", "b1", "b2", "adam_eps", "beta_scalar",
                                    "grad_scale")]
 

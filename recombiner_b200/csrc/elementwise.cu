@@ -5,6 +5,16 @@
 
 namespace rcb {
 
+// element (row n, sample s, latent l) of the lpe / d_lpe tensors: plain (rows*S, n_l), or the
+// stitched per-datum grid of the patch modalities
+__device__ __forceinline__ int64_t lpe_index(const int* slot, int rows_per_datum, int sp_total, int C, int n_l, int S,
+                                             int n, int s, int l) {
+  if (!slot) return ((int64_t)n * S + s) * n_l + l;
+  const int d = n / rows_per_datum, r = n - d * rows_per_datum;
+  const int sp = l / C, c = l - sp * C;
+  return (((int64_t)d * S + s) * sp_total + slot[(int64_t)r * (n_l / C) + sp]) * C + c;
+}
+
 // ----------------------------------------------------------------- sampling --
 // grid: (ceil(P/256), rows).  One thread = one (row, parameter); loops over S.
 __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
@@ -33,7 +43,7 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
     for (int s = 0; s < a.S; ++s) {
       float eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
                           : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
-      a.lpe[((int64_t)n * a.S + s) * a.n_l + l] = fmaf(sig, eps, mu);
+      a.lpe[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)] = fmaf(sig, eps, mu);
     }
   }
 }
@@ -68,7 +78,7 @@ __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
                           : philox_normal(a.seed, a.step, a.tensor_id, (uint64_t)((gn * a.S + s) * a.n_w + p));
           } else {
             const int l = p - a.n_w;
-            d = src[((int64_t)n * a.S + s) * a.n_l + l];
+            d = src[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)];
             eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
                           : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
           }

@@ -112,7 +112,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(rcb_mlp_args a) {
   const float* B3 = Ws + L::off3;
 
   const float* xt = a.xt + (int64_t)row * a.x_row_stride;
-  const float* pe = a.pe + (int64_t)item * pix * NPE;
+  // positional encodings: (items, pix, 16), or a window of the stitched per-datum grid
+  const bool stitched = a.pe_base != nullptr;
+  const int64_t pe_origin = stitched ? a.pe_base[item] : (int64_t)item * pix;
+  const float* pe = a.pe + pe_origin * NPE;
+  const int php = a.ph * a.pw;
+  auto pe_off = [&](int gp) -> int64_t {      // pixel gp of this patch -> pixel offset from its origin
+    if (!stitched) return gp;
+    int z = gp / php, rem = gp - z * php;
+    int yy = rem / a.pw, xx = rem - yy * a.pw;
+    return (int64_t)z * a.pitch_z + (int64_t)yy * a.pitch_y + xx;
+  };
 
   // gradient accumulators (persist over tiles)
   float gW[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(rcb_mlp_args a) {
     for (int c = tid; c < TILE * (NPE / 4); c += MLP_THREADS) {
       int p = c / (NPE / 4), c4 = c % (NPE / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pix0 + p < pix) v = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)(pix0 + p) * NPE + c4 * 4));
+      if (pix0 + p < pix) v = __ldg(reinterpret_cast<const float4*>(pe + pe_off(pix0 + p) * NPE + c4 * 4));
       X0[(L::F + c4 * 4 + 0) * LDP + p] = v.x;
       X0[(L::F + c4 * 4 + 1) * LDP + p] = v.y;
       X0[(L::F + c4 * 4 + 2) * LDP + p] = v.z;
@@ -321,12 +331,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_kernel(rcb_mlp_args a) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[p][j] = 0.f;
         tile_gemm<HID>(DZ, WTl, NPE, px0, j0, acc);
-        float* dpe = a.d_pe + (int64_t)item * pix * NPE;
+        float* dpe = a.d_pe + pe_origin * NPE;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           int gp = pix0 + px0 + p;
           if (gp < pix)
-            *reinterpret_cast<float4*>(dpe + (int64_t)gp * NPE + j0) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+            *reinterpret_cast<float4*>(dpe + pe_off(gp) * NPE + j0) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
         }
       }
     };
@@ -408,6 +418,8 @@ extern "C" int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->mode != 1 || (a->y && a->sqerr), "rcb_mlp: mode 1 needs y and sqerr");
   RCB_CHECK_ARG(a->mode != 2 || a->dy, "rcb_mlp: mode 2 needs dy");
   RCB_CHECK_ARG(a->mode == 0 || (a->d_pe && a->d_wt), "rcb_mlp: backward needs d_pe and d_wt");
+  RCB_CHECK_ARG(!a->pe_base || (a->ph > 0 && a->pw > 0 && a->pix % (a->ph * a->pw) == 0),
+                "rcb_mlp: stitched addressing needs the patch extent (ph, pw) dividing pix");
   cudaStream_t st = (cudaStream_t)stream;
   const int in0 = a->n_f + NPE;
   if (in0 == 32 && a->out == 3) return launch_mlp<32, 3>(a, st);

@@ -38,11 +38,16 @@ def _i32(a, device) -> torch.Tensor:
 @dataclass
 class Noise:
     """Either explicit eps tensors (parity tests) or a Philox key (production)."""
-    eps_w: Optional[torch.Tensor] = None      # (rows, S, W)
-    eps_l: Optional[torch.Tensor] = None      # (S, rows, L)
+    eps_w: Optional[torch.Tensor] = None      # (rows, S, W)   level-1 weights
+    eps_l: Optional[torch.Tensor] = None      # (S, rows, L)   latent grid
     seed: int = 0
     step: int = 0
     row_offset: int = 0
+    eps_h: Optional[torch.Tensor] = None      # (rows, S, W)   level 2 (patch modalities)
+    eps_hh: Optional[torch.Tensor] = None     # (rows, S, W)   level 3
+
+    def eps_for(self, level: int):
+        return (self.eps_w, self.eps_h, self.eps_hh)[level]
 
 
 class LevelState:
@@ -60,6 +65,11 @@ class LevelState:
         self.beta_scalar = 0.0
         self.rows, self.P = loc.shape
         self.adam = None
+        # hierarchy (patch modalities): which level this is, per-column row permutation and
+        # the expansion of level rows over patch rows
+        self.level = 0
+        self.perm = self.perm_inv = self.row_map = self.row_children = None
+        self.n_children = 1
         if group_start is None:          # parameter order, no blocks (prior training)
             self.G = 0
             self.group_idx = self.group_start = self.group_end = self.g2p = self.p2g = None
@@ -83,6 +93,22 @@ class LevelState:
         self.coded = torch.zeros(self.rows, self.G, dtype=torch.uint8, device=device)
         self.idx = torch.zeros(self.rows, self.G, dtype=torch.int32, device=device)
         self.group_kl = torch.zeros(self.rows, self.G, dtype=torch.float64, device=device)
+
+    def set_permutation(self, perm_g2p: np.ndarray):
+        """perm_g2p[r, c] = stored row read by parameter-order row r in column c
+        (test_model.py:185-194); the inverse serves the gradient scatter."""
+        self.perm = _i32(perm_g2p, self.device)
+        self.perm_inv = _i32(np.argsort(perm_g2p, axis=0), self.device)
+
+    def set_expansion(self, row_map: np.ndarray):
+        """row_map[n] = row of this level feeding patch row n (utils.py:151-189)."""
+        row_map = np.asarray(row_map).astype(np.int64)
+        self.row_map = _i32(row_map, self.device)
+        order = np.argsort(row_map, kind="stable")
+        counts = np.bincount(row_map, minlength=self.rows)
+        assert counts.min() == counts.max(), "every level row must feed the same number of patches"
+        self.n_children = int(counts[0])
+        self.row_children = _i32(order.reshape(self.rows, self.n_children), self.device)
 
     def reset_adam(self):
         z = lambda: torch.zeros(self.rows, self.P, device=self.device)
@@ -132,7 +158,7 @@ class FitEngine:
         return _Section(self.timer, name)
 
     def __init__(self, dims, data_dim, pixel_sizes, upsample_factors, latent_dim, layer_scales, paddings,
-                 w0, device, precision=None):
+                 w0, device, precision=None, patch_nums=None, force_poly=False):
         import os
         self.precision = precision or os.environ.get("RECOMBINER_PRECISION", "tf32")
         if self.precision not in ("fp32", "tf32"):
@@ -155,16 +181,38 @@ class FitEngine:
             raise KernelError("this build covers 1-D and 2-D signals (3-D upsampler is not built yet)")
         self.pixel_sizes = list(pixel_sizes)
         self.pix = int(np.prod(pixel_sizes))
-        self.grid = [pixel_sizes[i] // upsample_factors[i] for i in range(data_dim)]
+        self.grid = [pixel_sizes[i] // upsample_factors[i] for i in range(data_dim)]       # per-row latent grid
         self.latent_dim = int(latent_dim)
         self.L = int(np.prod(self.grid)) * self.latent_dim
+        # patch modalities: the rows of one datum are stitched into one grid before the upsampler
+        self.patch_nums = list(patch_nums) if patch_nums is not None else None
+        pn = self.patch_nums or [1] * data_dim
+        self.R = int(np.prod(pn))                                    # rows per datum
+        self.full_grid = [pn[i] * self.grid[i] for i in range(data_dim)]
+        self.full_pixels = [pn[i] * pixel_sizes[i] for i in range(data_dim)]
+        self.sp = int(np.prod(self.grid))
+        self.sp_total = int(np.prod(self.full_grid))
+        self.pix_total = int(np.prod(self.full_pixels))
+        self.lpe_slot = None
+        self._patch_origin = None
+        if self.patch_nums is not None:
+            slot = np.empty((self.R, self.sp), dtype=np.int64)
+            origin = np.empty(self.R, dtype=np.int64)
+            for r in range(self.R):
+                pc = np.unravel_index(r, pn)
+                for sp_i in range(self.sp):
+                    gc = np.unravel_index(sp_i, self.grid)
+                    slot[r, sp_i] = np.ravel_multi_index([pc[i] * self.grid[i] + gc[i] for i in range(data_dim)], self.full_grid)
+                origin[r] = np.ravel_multi_index([pc[i] * pixel_sizes[i] for i in range(data_dim)], self.full_pixels)
+            self.lpe_slot = _i32(slot, torch.device(device))
+            self._patch_origin = origin
         self.n_f = self.dims[0] - 16
         self.out = self.dims[-1]
         self.w0 = float(w0)
         if list(paddings) != [2, 1, 1]:
             raise KernelError("upsampler kernels assume 'same' convolutions (paddings [2,1,1])")
         # stage geometry: (h, w) grids for the three nearest-up + conv stages
-        h, w = (1, self.grid[0]) if data_dim == 1 else (self.grid[0], self.grid[1])
+        h, w = (1, self.full_grid[0]) if data_dim == 1 else (self.full_grid[0], self.full_grid[1])
         ks = [5, 3, 3]
         chans = [(latent_dim, 64), (64, 64), (64, 16)]
         self.geoms = []
@@ -175,9 +223,13 @@ class FitEngine:
             ky = 1 if data_dim == 1 else ks[i]
             self.geoms.append(UpconvGeom(h, w, fy, fx, ky, ks[i], chans[i][0], chans[i][1]))
             h, w = h * fy, w * fx
-        if h * w != self.pix:
+        if h * w != self.pix_total:
             raise KernelError("upsample factors do not reach the pixel grid")
-        self.dense1 = self.geoms[0].h * self.geoms[0].w <= 16
+        self.dense1 = self.geoms[0].h * self.geoms[0].w <= 16 and not force_poly
+        if data_dim == 1:
+            self.ph, self.pw, self.pitch_y = 1, self.pixel_sizes[0], 0
+        else:
+            self.ph, self.pw, self.pitch_y = self.pixel_sizes[0], self.pixel_sizes[1], self.full_pixels[1]
         self._ws: Dict = {}
         self._x_cache = None
         self.A = None
@@ -218,18 +270,26 @@ class FitEngine:
         key = (rows, S)
         ws = self._ws.get(key)
         if ws is None:
-            items = rows * S
+            if rows % self.R:
+                raise KernelError(f"{rows} rows is not a multiple of the {self.R} patches per datum")
+            items = rows * S                      # (row, sample) items: INR weights, MLP
+            citems = (rows // self.R) * S         # (datum, sample) items: the stitched upsampler
+            Lt = self.sp_total * self.latent_dim
             dev = self.device
             g1, g2, g3 = self.geoms
             n1 = g1.h * g1.fy * g1.w * g1.fx * g1.oc
             n2 = g2.h * g2.fy * g2.w * g2.fx * g2.oc
             e = lambda *s: torch.empty(*s, device=dev)
             ws = dict(hw=torch.zeros(items, self.ldw, device=dev), wt=torch.zeros(items, self.ldw, device=dev),
-                      lpe=e(items, self.L), a1=e(items, n1), a2=e(items, n2), pe=e(items, self.pix, 16),
-                      d_pe=e(items, self.pix, 16), d_a2=e(items, n2), d_a1=e(items, n1), d_lpe=e(items, self.L),
+                      lpe=e(citems, Lt), a1=e(citems, n1), a2=e(citems, n2), pe=e(citems, self.pix_total, 16),
+                      d_pe=e(citems, self.pix_total, 16), d_a2=e(citems, n2), d_a1=e(citems, n1), d_lpe=e(citems, Lt),
                       d_wt=torch.zeros(items, self.ldw, device=dev), d_hw=torch.zeros(items, self.ldw, device=dev),
                       sqerr=torch.zeros(items, device=dev), y_pred=e(items, self.pix, self.out),
-                      kl=torch.zeros(1, dtype=torch.float64, device=dev))
+                      kl=torch.zeros(1, dtype=torch.float64, device=dev), citems=citems, pe_base=None)
+            if self.patch_nums is not None:
+                n = np.arange(rows)
+                base = ((n // self.R)[:, None] * S + np.arange(S)[None, :]) * self.pix_total + self._patch_origin[n % self.R][:, None]
+                ws["pe_base"] = torch.as_tensor(base.reshape(-1).astype(np.int64), device=dev)
             self._ws[key] = ws
         return ws
 
@@ -253,15 +313,22 @@ class FitEngine:
         return xt, stride
 
     # ------------------------------------------------------------------ forward --
-    def _sample(self, lv: LevelState, ws, S: int, noise: Noise):
+    def _sample(self, lv: LevelState, ws, S: int, noise: Noise, rows: int):
+        """Level 0 writes hw and the (stitched) latent grid; levels 1, 2 add their weight
+        samples to hw through the row expansion (utils.py:142-191)."""
         a = SampleArgs()
         a.loc, a.log_scale, a.mask, a.sample = ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.mask), ptr(lv.sample)
-        a.g2p, a.perm, a.row_map = ptr(lv.g2p), None, None
-        a.eps_w, a.eps_l = ptr(noise.eps_w), ptr(noise.eps_l)
-        a.hw, a.lpe = ptr(ws["hw"]), ptr(ws["lpe"])
+        a.g2p, a.perm, a.row_map = ptr(lv.g2p), ptr(lv.perm), ptr(lv.row_map)
+        a.eps_w = ptr(noise.eps_for(lv.level))
+        a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
+        a.hw = ptr(ws["hw"])
+        a.lpe = ptr(ws["lpe"]) if lv.level == 0 else None
+        a.lpe_slot = ptr(self.lpe_slot)
+        a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
         a.seed, a.row_offset = noise.seed, noise.row_offset
-        a.rows, a.S, a.P, a.n_w, a.n_l, a.ld_hw = lv.rows, S, lv.P, self.W, self.L, self.ldw
-        a.step, a.tensor_id, a.accumulate = noise.step, 0, 0
+        a.rows, a.S, a.P, a.n_w, a.ld_hw = rows, S, lv.P, self.W, self.ldw
+        a.n_l = self.L if lv.level == 0 else 0
+        a.step, a.tensor_id, a.accumulate = noise.step, lv.level, int(lv.level > 0)
         check(self.lib.rcb_fit_sample(C.byref(a), stream()), "rcb_fit_sample")
 
     def _gemm(self, A, a_off, lda, B, ldb, Cm, c_off, ldc, M, N, K, bias=None, bias_mod=1, act=0, trans_a=0, acc=0,
@@ -278,15 +345,20 @@ class FitEngine:
         check(self.lib.rcb_gemm(pa, lda, pb, ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
               "rcb_gemm")
 
-    def forward_features(self, lv: LevelState, S: int, noise: Noise):
-        """sample -> per-item INR weights (wt) and positional encodings (pe)."""
+    def forward_features(self, lv, S: int, noise: Noise):
+        """sample -> per-item INR weights (wt) and positional encodings (pe).  `lv` is the
+        level-1 state, or [level1, level2, level3] for the patch modalities."""
         if self.A is None:
             raise KernelError("set_mappings() has not been called")
-        ws = self.workspace(lv.rows, S)
-        items = lv.rows * S
+        levels = lv if isinstance(lv, (list, tuple)) else [lv]
+        rows = levels[0].rows
+        ws = self.workspace(rows, S)
+        items = rows * S
+        citems = ws["citems"]
         st = stream()
         with self.section("sample"):
-            self._sample(lv, ws, S, noise)
+            for l in levels:
+                self._sample(l, ws, S, noise, rows)
         with self.section("reparam_fwd"):
             for l, c in enumerate(self.counts):
                 self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
@@ -294,17 +366,18 @@ class FitEngine:
         g1, g2, g3 = self.geoms
         with self.section("conv1_fwd"):
             if self.dense1:
-                self._gemm(ws["lpe"], 0, self.L, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
-                           items, self.M1.shape[1], self.L, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
+                Lt = self.M1.shape[0]
+                self._gemm(ws["lpe"], 0, Lt, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
+                           citems, self.M1.shape[1], Lt, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
             else:
                 check(self.lib.rcb_upconv_fwd(ptr(ws["lpe"]), ptr(self.w_eff[0]), ptr(self.conv_b[0]), ptr(ws["a1"]),
-                                              C.byref(g1), items, 1, st), "rcb_upconv_fwd[1]")
+                                              C.byref(g1), citems, 1, st), "rcb_upconv_fwd[1]")
         with self.section("conv2_fwd"):
             check(self.lib.rcb_upconv_fwd(ptr(ws["a1"]), ptr(self.w_eff[1]), ptr(self.conv_b[1]), ptr(ws["a2"]),
-                                          C.byref(g2), items, 1, st), "rcb_upconv_fwd[2]")
+                                          C.byref(g2), citems, 1, st), "rcb_upconv_fwd[2]")
         with self.section("conv3_fwd"):
             check(self.lib.rcb_upconv_fwd(ptr(ws["a2"]), ptr(self.w_eff[2]), ptr(self.conv_b[2]), ptr(ws["pe"]),
-                                          C.byref(g3), items, 0, st), "rcb_upconv_fwd[3]")
+                                          C.byref(g3), citems, 0, st), "rcb_upconv_fwd[3]")
         return ws
 
     def mlp(self, ws, rows: int, S: int, x, mode: int, y=None, dy=None, coef: float = 0.0):
@@ -314,6 +387,8 @@ class FitEngine:
         a.y, a.dy, a.y_pred = ptr(y), ptr(dy), ptr(ws["y_pred"])
         a.d_pe, a.d_wt, a.sqerr = ptr(ws["d_pe"]), ptr(ws["d_wt"]), ptr(ws["sqerr"])
         a.x_row_stride = stride
+        a.pe_base = ptr(ws["pe_base"])
+        a.pitch_z, a.pitch_y, a.ph, a.pw = 0, self.pitch_y, self.ph, self.pw
         a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
         a.coef, a.w0 = coef, self.w0
         with self.section("mlp_fwd" if mode == 0 else "mlp_fwd_bwd"):
@@ -323,21 +398,23 @@ class FitEngine:
     def backward_features(self, ws, rows: int, S: int):
         """d_pe, d_wt -> d_lpe, d_hw (data gradients only; the mappings are frozen)."""
         items = rows * S
+        citems = ws["citems"]
         st = stream()
         g1, g2, g3 = self.geoms
         with self.section("conv3_bwd"):
             check(self.lib.rcb_upconv_bwd(ptr(ws["d_pe"]), ptr(self.w_eff_t[2]), ptr(ws["a2"]), ptr(ws["d_a2"]),
-                                          C.byref(g3), items, st), "rcb_upconv_bwd[3]")
+                                          C.byref(g3), citems, st), "rcb_upconv_bwd[3]")
         with self.section("conv2_bwd"):
             check(self.lib.rcb_upconv_bwd(ptr(ws["d_a2"]), ptr(self.w_eff_t[1]), ptr(ws["a1"]), ptr(ws["d_a1"]),
-                                          C.byref(g2), items, st), "rcb_upconv_bwd[2]")
+                                          C.byref(g2), citems, st), "rcb_upconv_bwd[2]")
         with self.section("conv1_bwd"):
             if self.dense1:
-                self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, self.L,
-                           items, self.L, self.M1T.shape[0], Bt=self.M1)
+                Lt = self.M1.shape[0]
+                self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, Lt,
+                           citems, Lt, self.M1T.shape[0], Bt=self.M1)
             else:
                 check(self.lib.rcb_upconv_bwd(ptr(ws["d_a1"]), ptr(self.w_eff_t[0]), None, ptr(ws["d_lpe"]),
-                                              C.byref(g1), items, st), "rcb_upconv_bwd[1]")
+                                              C.byref(g1), citems, st), "rcb_upconv_bwd[1]")
         with self.section("reparam_bwd"):
             for l, c in enumerate(self.counts):
                 self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
@@ -348,6 +425,7 @@ class FitEngine:
         upsampler's conv weights/biases through the adjoints of the folds.  Call after
         backward_features (it consumes d_pe, d_a2, d_a1, d_wt)."""
         items = rows * S
+        citems = ws["citems"]
         st = stream()
         dev = self.device
         g = ws.setdefault("map_grads", {})
@@ -370,35 +448,40 @@ class FitEngine:
         with self.section("conv_wgrad"):
             for i, geo in enumerate(self.geoms):
                 out_px = geo.h * geo.fy * geo.w * geo.fx
-                check(self.lib.rcb_colsum(ptr(douts[i]), items * out_px, geo.oc, geo.oc, ptr(g[f"conv{i + 1}.bias"]), st),
+                check(self.lib.rcb_colsum(ptr(douts[i]), citems * out_px, geo.oc, geo.oc, ptr(g[f"conv{i + 1}.bias"]), st),
                       "rcb_colsum")
                 if i == 0 and self.dense1:
-                    self._gemm(ws["lpe"], 0, self.L, None, g["dM1"].shape[1], g["dM1"], 0, g["dM1"].shape[1],
-                               self.L, g["dM1"].shape[1], items, trans_a=1, b_tensor=ws["d_a1"], b_off=0)
+                    Lt = self.M1.shape[0]
+                    self._gemm(ws["lpe"], 0, Lt, None, g["dM1"].shape[1], g["dM1"], 0, g["dM1"].shape[1],
+                               Lt, g["dM1"].shape[1], citems, trans_a=1, b_tensor=ws["d_a1"], b_off=0)
                     check(self.lib.rcb_unfold_dense(ptr(g["dM1"]), C.byref(geo), ptr(g["conv1.weight"]), st),
                           "rcb_unfold_dense")
                     continue
-                check(self.lib.rcb_upconv_wgrad(ptr(srcs[i]), ptr(douts[i]), ptr(g[f"eff{i}"]), C.byref(geo), items, st),
+                check(self.lib.rcb_upconv_wgrad(ptr(srcs[i]), ptr(douts[i]), ptr(g[f"eff{i}"]), C.byref(geo), citems, st),
                       "rcb_upconv_wgrad")
                 check(self.lib.rcb_unfold_poly(ptr(g[f"eff{i}"]), C.byref(geo), ptr(g[f"conv{i + 1}.weight"]), st),
                       "rcb_unfold_poly")
         return g
 
     def update(self, lv: LevelState, ws, S: int, noise: Noise, *, with_data_grads: bool, adam: Optional[dict],
-               g_loc=None, g_log_scale=None, grad_scale: float = 1.0, kl_out: Optional[torch.Tensor] = None):
+               g_loc=None, g_log_scale=None, grad_scale: float = 1.0, kl_out: Optional[torch.Tensor] = None,
+               rows: Optional[int] = None):
         a = UpdateArgs()
         a.loc, a.log_scale, a.mask = ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.mask)
         a.p_loc, a.p_log_scale, a.beta, a.group_idx = ptr(lv.p_loc), ptr(lv.p_log_scale), ptr(lv.beta), ptr(lv.group_idx)
-        a.p2g, a.perm_inv, a.row_children = ptr(lv.p2g), None, None
+        a.p2g, a.perm_inv, a.row_children = ptr(lv.p2g), ptr(lv.perm_inv), ptr(lv.row_children)
         a.d_hw = ptr(ws["d_hw"]) if with_data_grads else None
-        a.d_lpe = ptr(ws["d_lpe"]) if with_data_grads else None
-        a.eps_w, a.eps_l = ptr(noise.eps_w), ptr(noise.eps_l)
+        a.d_lpe = ptr(ws["d_lpe"]) if (with_data_grads and lv.level == 0) else None
+        a.eps_w = ptr(noise.eps_for(lv.level))
+        a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
+        a.lpe_slot = ptr(self.lpe_slot)
+        a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
         a.g_loc, a.g_log_scale = ptr(g_loc), ptr(g_log_scale)
         a.kl_out = ptr(kl_out)
         a.seed, a.row_offset = noise.seed, noise.row_offset
-        a.src_rows, a.rows, a.n_children, a.S, a.P = lv.rows, lv.rows, 1, S, lv.P
-        a.n_w, a.n_l, a.ld_hw, a.G = self.W, self.L, self.ldw, lv.G
-        a.step, a.tensor_id = noise.step, 0
+        a.src_rows, a.rows, a.n_children, a.S, a.P = lv.rows, (rows if rows is not None else lv.rows), lv.n_children, S, lv.P
+        a.n_w, a.n_l, a.ld_hw, a.G = self.W, (self.L if lv.level == 0 else 0), self.ldw, lv.G
+        a.step, a.tensor_id = noise.step, lv.level
         a.beta_scalar, a.grad_scale = float(lv.beta_scalar), grad_scale
         a.p_scale_direct = int(lv.p_scale_direct)
         if adam is not None:

@@ -40,57 +40,82 @@ class Sine(nn.Module):
 
 
 class _Predict(torch.autograd.Function):
-    """y_pred = INR(posterior sample); backward re-runs the fused MLP in gradient mode."""
+    """y_pred = INR(posterior sample); backward re-runs the fused MLP in gradient mode.
+    Tensor inputs: (loc, log_scale) of every level, in level order."""
 
     @staticmethod
-    def forward(ctx, loc, log_scale, model, x, S, noise):
-        lv = model._lv
-        ws = model.engine.forward_features(lv, S, noise)
-        model.engine.mlp(ws, lv.rows, S, x, mode=0)
+    def forward(ctx, model, x, S, noise, *params):
+        levels = model._levels
+        rows = levels[0].rows
+        ws = model.engine.forward_features(levels, S, noise)
+        model.engine.mlp(ws, rows, S, x, mode=0)
         ctx.model, ctx.x, ctx.S, ctx.noise = model, x, S, noise
         model._generation += 1
         ctx.generation = model._generation
-        return ws["y_pred"].view(lv.rows, S, model.engine.pix, model.engine.out).clone()
+        return ws["y_pred"].view(rows, S, model.engine.pix, model.engine.out).clone()
 
     @staticmethod
     def backward(ctx, dy):
         model, S, noise = ctx.model, ctx.S, ctx.noise
         if ctx.generation != model._generation:
             raise KernelError("predict() workspace was overwritten by a later forward before backward()")
-        lv = model._lv
-        ws = model.engine.workspace(lv.rows, S)
-        dy = dy.contiguous().view(lv.rows * S, model.engine.pix, model.engine.out)
-        model.engine.mlp(ws, lv.rows, S, ctx.x, mode=2, dy=dy)
-        model.engine.backward_features(ws, lv.rows, S)
-        g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
-        saved_beta = lv.beta
-        lv.beta = model._zero_beta          # data term only; KL has its own Function
-        try:
-            model.engine.update(lv, ws, S, noise, with_data_grads=True, adam=None, g_loc=g_loc, g_log_scale=g_ls)
-        finally:
-            lv.beta = saved_beta
-        return g_loc, g_ls, None, None, None, None
+        levels = model._levels
+        rows = levels[0].rows
+        ws = model.engine.workspace(rows, S)
+        dy = dy.contiguous().view(rows * S, model.engine.pix, model.engine.out)
+        model.engine.mlp(ws, rows, S, ctx.x, mode=2, dy=dy)
+        model.engine.backward_features(ws, rows, S)
+        grads = []
+        for lv in levels:
+            g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
+            saved_beta = lv.beta
+            lv.beta = torch.zeros_like(saved_beta)      # data term only; KL has its own Function
+            try:
+                model.engine.update(lv, ws, S, noise, with_data_grads=True, adam=None, g_loc=g_loc, g_log_scale=g_ls,
+                                    rows=rows)
+            finally:
+                lv.beta = saved_beta
+            grads += [g_loc, g_ls]
+        return (None, None, None, None, *grads)
 
 
 class _WeightedKL(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, loc, log_scale, model):
-        lv = model._lv
-        kl = torch.zeros(1, dtype=torch.float64, device=lv.device)
-        g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
-        model.engine.update(lv, None, 1, Noise(), with_data_grads=False, adam=None, g_loc=g_loc, g_log_scale=g_ls,
-                            kl_out=kl)
-        ctx.save_for_backward(g_loc, g_ls)
+    def forward(ctx, model, *params):
+        kl = torch.zeros(1, dtype=torch.float64, device=model.device)
+        grads = []
+        for lv in model._levels:
+            g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
+            model.engine.update(lv, None, 1, Noise(), with_data_grads=False, adam=None, g_loc=g_loc, g_log_scale=g_ls,
+                                kl_out=kl, rows=model._levels[0].rows)
+            grads += [g_loc, g_ls]
+        ctx.save_for_backward(*grads)
         return kl.to(torch.float32).reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        g_loc, g_ls = ctx.saved_tensors
-        return g * g_loc, g * g_ls, None
+        return (None, *[g * t for t in ctx.saved_tensors])
+
+
+def _level_prop(li, attr, post=None):
+    """Read-only view of one level's device state under the reference's attribute name."""
+    def get(self):
+        v = getattr(self._levels[li], attr)
+        return post(v) if post else v
+    return property(get)
+
+
+def _as_bool(t):
+    return t.bool().cpu().numpy()
+
+
+def _as_f64(t):
+    return t.cpu().numpy().astype(np.float64)
 
 
 class TestBNNmodel(nn.Module):
     __test__ = False   # not a pytest class
+    _PREFIX = ("", "h_", "hh_")
 
     def __init__(self,
                  in_dim, hidden_dims, out_dim, number_of_datapoints, upsample_factors, latent_dim, data_dim,
@@ -112,8 +137,8 @@ class TestBNNmodel(nn.Module):
         if dev.type != "cuda":
             raise KernelError("recombiner_b200.TestBNNmodel runs on CUDA (sm_100a) only -- there is no CPU "
                               "fallback; the CPU restatement used for parity lives in oracle/")
-        if patch:
-            raise NotImplementedError("patch modalities (kodak/audio/video) are not wired to the kernels yet")
+        if patch and data_dim == 3:
+            raise NotImplementedError("the 3-D (video) upsampler is not wired to the kernels yet")
         self.bit_per_group = 16
         self.n_layers = len(hidden_dims) + 1
         self.dims = [in_dim] + list(hidden_dims) + [out_dim]
@@ -128,32 +153,74 @@ class TestBNNmodel(nn.Module):
                 for p in m.parameters():
                     p.requires_grad = False
         _, self.cum_param_sizes = count_net_params(in_dim, hidden_dims, out_dim)
-
-        self.param_to_group, self.group_to_param, self.n_groups = param_to_group, group_to_param, n_groups
-        self.group_start_index, self.group_end_index, self.group_idx = group_start_index, group_end_index, group_idx
-        rows, P = number_of_datapoints, p_loc.shape[0]
-        init_ls = init_log_scale.to(dev) if torch.is_tensor(init_log_scale) else init_log_scale
-        self.loc = nn.Parameter(p_loc.detach().to(dev, torch.float32)[None, :].repeat(rows, 1).contiguous())
-        self.log_scale = nn.Parameter((torch.zeros(rows, P, device=dev) + init_ls).contiguous())
-        self.p_loc = p_loc.detach().clone().to(dev, torch.float32)
-        self.p_log_scale = p_log_scale.detach().clone().to(dev, torch.float32)
-
         self.beta_step_size, self.kl_upper_buffer = beta_step_size, kl_upper_buffer
         self.kl_lower_buffer, self.kl_adjust_gap = kl_lower_buffer, kl_adjust_gap
 
-        self._lv = LevelState(self.loc, self.log_scale, self.p_loc, self.p_log_scale, group_idx, group_start_index,
-                              group_end_index, group_to_param, param_to_group, initial_beta, dev)
-        self._zero_beta = torch.zeros_like(self._lv.beta)
-        self.compressed_sample_std = 1e-15 + torch.zeros(rows, P, device=dev)
+        rows = number_of_datapoints
+        R = int(np.prod(patch_nums)) if patch else 1
+        level_rows = [rows]
+        if patch:
+            level_rows += [rows // int(np.prod(hierarchical_patch_nums['level2'])),
+                           rows // int(np.prod(hierarchical_patch_nums['level3']))]
+        given = [
+            (p_loc, p_log_scale, init_log_scale, param_to_group, group_to_param, n_groups, group_start_index,
+             group_end_index, group_idx),
+            (h_p_loc, h_p_log_scale, h_init_log_scale, h_param_to_group, h_group_to_param, h_n_groups,
+             h_group_start_index, h_group_end_index, h_group_idx),
+            (hh_p_loc, hh_p_log_scale, hh_init_log_scale, hh_param_to_group, hh_group_to_param, hh_n_groups,
+             hh_group_start_index, hh_group_end_index, hh_group_idx)]
+        self._levels = []
+        for li, n_rows in enumerate(level_rows):
+            pre = self._PREFIX[li]
+            pl, pls, ils, p2g, g2p, ng, gs, ge, gi = given[li]
+            P = pl.shape[0]
+            ils = ils.to(dev) if torch.is_tensor(ils) else ils
+            loc = nn.Parameter(pl.detach().to(dev, torch.float32)[None, :].repeat(n_rows, 1).contiguous())
+            log_scale = nn.Parameter((torch.zeros(n_rows, P, device=dev) + ils).contiguous())
+            setattr(self, pre + "loc", loc)
+            setattr(self, pre + "log_scale", log_scale)
+            setattr(self, pre + "p_loc", pl.detach().clone().to(dev, torch.float32))
+            setattr(self, pre + "p_log_scale", pls.detach().clone().to(dev, torch.float32))
+            for nm, v in (("param_to_group", p2g), ("group_to_param", g2p), ("n_groups", ng),
+                          ("group_start_index", gs), ("group_end_index", ge), ("group_idx", gi)):
+                setattr(self, pre + nm, v)
+            lv = LevelState(loc, log_scale, getattr(self, pre + "p_loc"), getattr(self, pre + "p_log_scale"), gi, gs, ge,
+                            g2p, p2g, initial_beta, dev)
+            lv.level = li
+            setattr(self, pre + "compressed_sample_std", 1e-15 + torch.zeros(n_rows, P, device=dev))
+            self._levels.append(lv)
+        self._lv = self._levels[0]
+        if patch:
+            # per-column row permutations of levels 1 and 2 (test_model.py:182-208)
+            for li in (0, 1):
+                lv = self._levels[li]
+                perm = np.stack([np.random.RandomState(c).choice(lv.rows, lv.rows, False) for c in range(lv.P)], 1)
+                np.random.seed(None)
+                lv.set_permutation(perm)
+                setattr(self, self._PREFIX[li] + "permute_patch_x_g2p", perm)
+                setattr(self, self._PREFIX[li] + "permute_patch_x_p2g", np.argsort(perm, axis=0))
+            # expansion of level-2 / level-3 rows over the patches (utils.py:151-189)
+            l2 = hierarchical_patch_nums['level2']
+            ng = [patch_nums[i] // l2[i] for i in range(data_dim)]
+            n = np.arange(rows)
+            pc = np.unravel_index(n % R, patch_nums)
+            grp = np.ravel_multi_index([pc[i] // l2[i] for i in range(data_dim)], ng)
+            self._levels[1].set_expansion((n // R) * int(np.prod(ng)) + grp)
+            self._levels[2].set_expansion(n // R)
 
         cfg_scales = layer_scales if layer_scales is not None else [4, 2, 2]
         self.engine = FitEngine(self.dims, data_dim, pixel_sizes, upsample_factors, latent_dim, cfg_scales,
-                                paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision)
+                                paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision,
+                                patch_nums=patch_nums if patch else None)
         if linear_transform is not None and upsample_net is not None:
             self.engine.set_mappings(list(linear_transform.A), upsample_net.state_dict())
         self.act = Sine(w0)
         self.st = lambda v: torch.nn.functional.softplus(v, beta=1, threshold=20) / 6
-        self.bpp = (self.n_groups * self.bit_per_group) / np.prod(pixel_sizes)
+        pixels = np.prod(pixel_sizes)
+        self.bpp = (self.n_groups * self.bit_per_group) / pixels
+        if patch:
+            self.bpp += (self.h_n_groups * self.bit_per_group) / pixels / np.prod(hierarchical_patch_nums['level2'])
+            self.bpp += (self.hh_n_groups * self.bit_per_group) / pixels / np.prod(hierarchical_patch_nums['level3'])
         if self.dataset == 'audio':
             self.bpp = self.bpp / (3 / 48000) / 1000
         print("Model Initialized. Expected bpp is %.2f" % self.bpp, flush=True)
@@ -161,37 +228,32 @@ class TestBNNmodel(nn.Module):
         self.g_samples = None
         self._g_dev = None
         self.group_samples = {}
+        self.h_group_samples, self.hh_group_samples = {}, {}
         self._tables = None
-        self._tables_ptr = None
         self._generation = 0
         self._adam_owner = None
-        self._global_step = 0
 
     # ------------------------------------------------------- reference attributes --
-    @property
-    def kl_beta(self):
-        return self._lv.beta
+    kl_beta = property(lambda self: self._levels[0].beta, lambda self, v: self._set_beta(0, v))
+    h_kl_beta = property(lambda self: self._levels[1].beta, lambda self, v: self._set_beta(1, v))
+    hh_kl_beta = property(lambda self: self._levels[2].beta, lambda self, v: self._set_beta(2, v))
+    compressed_mask = _level_prop(0, "mask")
+    h_compressed_mask = _level_prop(1, "mask")
+    hh_compressed_mask = _level_prop(2, "mask")
+    compressed_sample = _level_prop(0, "sample")
+    h_compressed_sample = _level_prop(1, "sample")
+    hh_compressed_sample = _level_prop(2, "sample")
+    compressed_mask_groupwise = _level_prop(0, "coded", _as_bool)
+    h_compressed_mask_groupwise = _level_prop(1, "coded", _as_bool)
+    hh_compressed_mask_groupwise = _level_prop(2, "coded", _as_bool)
+    # (rows, G) float64 numpy, as the reference stores and np.savetxt's them (test_model.py:221)
+    compressed_idx_groupwise = _level_prop(0, "idx", _as_f64)
+    h_compressed_idx_groupwise = _level_prop(1, "idx", _as_f64)
+    hh_compressed_idx_groupwise = _level_prop(2, "idx", _as_f64)
 
-    @kl_beta.setter
-    def kl_beta(self, v):
-        self._lv.beta = torch.as_tensor(v, dtype=torch.float32).to(self.device).expand(self._lv.rows, self._lv.G).contiguous()
-
-    @property
-    def compressed_mask(self):
-        return self._lv.mask
-
-    @property
-    def compressed_sample(self):
-        return self._lv.sample
-
-    @property
-    def compressed_mask_groupwise(self):
-        return self._lv.coded.bool().cpu().numpy()
-
-    @property
-    def compressed_idx_groupwise(self):
-        """(rows, G) float64 numpy, as the reference stores and np.savetxt's it (test_model.py:221)."""
-        return self._lv.idx.cpu().numpy().astype(np.float64)
+    def _set_beta(self, li, v):
+        lv = self._levels[li]
+        lv.beta = torch.as_tensor(v, dtype=torch.float32).to(self.device).expand(lv.rows, lv.G).contiguous()
 
     def group_to_layer(self, param, layer_idx):
         lo = 0 if layer_idx == 0 else self.cum_param_sizes[layer_idx - 1]
@@ -203,38 +265,50 @@ class TestBNNmodel(nn.Module):
         weights = layer_param[..., out_dim:].reshape(*lead, in_dim, out_dim)
         return weights, bias
 
+    def _params(self):
+        out = []
+        for lv in self._levels:
+            out += [lv.loc, lv.log_scale]
+        return out
+
     # -------------------------------------------------------------------- forward --
     def _noise(self, random_seed, eps=None) -> Noise:
         if eps is not None:
-            return Noise(eps_w=eps["w"].to(self.device).contiguous(), eps_l=eps["lpe"].to(self.device).contiguous())
+            dev = self.device
+            return Noise(eps_w=eps["w"].to(dev).contiguous(), eps_l=eps["lpe"].to(dev).contiguous(),
+                         eps_h=eps["h"].to(dev).contiguous() if "h" in eps else None,
+                         eps_hh=eps["hh"].to(dev).contiguous() if "hh" in eps else None)
         if random_seed is None:
             random_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())   # global torch RNG, like randn_like
         seed = ((int(self.random_seed) & 0x7fffffff) << 32) | (int(random_seed) & 0xffffffff)
         return Noise(seed=seed, step=0, row_offset=self.row_offset)
 
     def predict(self, x, random_seed=None, sample_size=1, eps=None):
-        """MC forward (test_model.py:283-355).  `eps` (dict with 'lpe' (S,N,L) and 'w'
-        (N,S,W)) injects the noise for parity tests; otherwise it is Philox-generated
-        in-kernel from (model seed, random_seed)."""
+        """MC forward (test_model.py:283-355).  `eps` (dict with 'lpe' (S,N,L), 'w' (N,S,W) and,
+        for patch modalities, 'h' / 'hh' (N,S,W)) injects the noise for parity tests;
+        otherwise it is Philox-generated in-kernel from (model seed, random_seed)."""
         noise = self._noise(random_seed, eps)
-        y = _Predict.apply(self.loc, self.log_scale, self, x, sample_size, noise)
+        y = _Predict.apply(self, x, sample_size, noise, *self._params())
         return y[:, 0] if sample_size == 1 else y
 
     def calculate_kl(self):
-        """sum_{n,p} beta[n, g(p)] KL(q_np || p_p)  (test_model.py:357-362)."""
-        return _WeightedKL.apply(self.loc, self.log_scale, self)
+        """sum over levels of sum_{n,p} beta[n, g(p)] KL(q_np || p_p)  (test_model.py:357-377)."""
+        return _WeightedKL.apply(self, *self._params())
 
     def update_annealing_factors(self, update=True):
         """Per-(row, block) KL in nats; optionally anneal beta (test_model.py:379-439).
-        Returns a (rows, G) float64 numpy array like the reference."""
-        return self._annealing(update).cpu().numpy()
+        Returns (rows, G) float64 numpy -- one array per level for patch modalities."""
+        out = [k.cpu().numpy() for k in self._annealing(update)]
+        return tuple(out) if self.patch else out[0]
 
-    def _annealing(self, update: bool) -> torch.Tensor:
-        kl = self.engine.group_kl(self._lv)
-        if update:
-            self.engine.anneal(self._lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer,
-                               float(self.bit_per_group))
-        return kl
+    def _annealing(self, update: bool):
+        kls = []
+        for lv in self._levels:
+            kls.append(self.engine.group_kl(lv))
+            if update:
+                self.engine.anneal(lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer,
+                                   float(self.bit_per_group))
+        return kls
 
     # ------------------------------------------------------------------------ REC --
     def get_gumbel_sample(self):
@@ -244,108 +318,146 @@ class TestBNNmodel(nn.Module):
         self._g_dev = self.g_samples.to(self.device)
 
     def _ensure_rec(self, n_cand: int):
-        if self.g_samples is None:
+        if self.g_samples is None or self._g_dev is None or self._g_dev.numel() < n_cand:
             self.get_gumbel_sample()
         if self._tables is None or self._tables.n != n_cand:
             self._tables = _rec.CandidateTables(self.random_seed, n_cand, self.device)
-            sizes = self._lv.group_end_host - self._lv.group_start_host
-            self._tables_ptr = self._tables.pointer_array(sizes)
-            self._max_D = int(sizes.max())
+            for lv in self._levels:       # all levels share tables of equal block size and the Gumbel noise
+                sizes = lv.group_end_host - lv.group_start_host
+                lv.tables_ptr = self._tables.pointer_array(sizes)
+                lv.max_D = int(sizes.max())
 
     def get_sobol_normal_sample(self, param_size, sample_size):
         """(sample_size, param_size) float64 standard-normal candidates (test_model.py:493-498)."""
         t = _rec.CandidateTables(self.random_seed, sample_size, self.device).table(int(param_size))
         return t.t().to(torch.float64)
 
+    def _get_sample(self, li, cache, group_idx, n):
+        key = (group_idx, n)
+        if key not in cache:
+            lv = self._levels[li]
+            D = int(lv.group_end_host[group_idx] - lv.group_start_host[group_idx])
+            cache[key] = self.get_sobol_normal_sample(D, n)
+        return cache[key]
+
     def get_sample(self, group_idx, group_sample_size):
-        key = (group_idx, group_sample_size)
-        if key not in self.group_samples:
-            D = int(self.group_end_index[group_idx] - self.group_start_index[group_idx])
-            self.group_samples[key] = self.get_sobol_normal_sample(D, group_sample_size)
-        return self.group_samples[key]
+        return self._get_sample(0, self.group_samples, group_idx, group_sample_size)
+
+    def h_get_sample(self, group_idx, group_sample_size):
+        return self._get_sample(1, self.h_group_samples, group_idx, group_sample_size)
+
+    def hh_get_sample(self, group_idx, group_sample_size):
+        return self._get_sample(2, self.hh_group_samples, group_idx, group_sample_size)
 
     def _pairs(self, rows, blocks):
         return (torch.as_tensor(rows, dtype=torch.int32, device=self.device).reshape(-1).contiguous(),
                 torch.as_tensor(blocks, dtype=torch.int32, device=self.device).reshape(-1).contiguous())
 
-    def _scales(self):
-        return self.st(self.log_scale.data).contiguous(), self.st(self.p_log_scale).contiguous()
+    def _scales(self, li=0):
+        lv = self._levels[li]
+        return self.st(lv.log_scale.data).contiguous(), self.st(lv.p_log_scale).contiguous()
+
+    def _sample_group(self, li, row_idx, group_idx, n):
+        self._ensure_rec(n)
+        lv = self._levels[li]
+        q_scale, p_scale = self._scales(li)
+        pr, pb = self._pairs([row_idx], [group_idx])
+        idx, z, logw = _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, pr, pb, n, lv.max_D,
+                                   apply=False, want_logw=True)
+        D = int(lv.group_end_host[group_idx] - lv.group_start_host[group_idx])
+        return int(idx.item()), z[0, :D].to(torch.float64), logw[0]
 
     def sample_group(self, row_idx, group_idx, group_sample_size):
         """A*-code one block (test_model.py:501-533): returns (index, z_i, log_w)."""
-        self._ensure_rec(group_sample_size)
-        q_scale, p_scale = self._scales()
-        pr, pb = self._pairs([row_idx], [group_idx])
-        idx, z, logw = _rec.encode(self._lv, self._tables_ptr, self._g_dev, q_scale, p_scale, pr, pb,
-                                   group_sample_size, self._max_D, apply=False, want_logw=True)
-        D = int(self.group_end_index[group_idx] - self.group_start_index[group_idx])
-        return int(idx.item()), z[0, :D].to(torch.float64), logw[0]
+        return self._sample_group(0, row_idx, group_idx, group_sample_size)
 
-    def compress_group(self, row_idx, group_idx):
+    def h_sample_group(self, row_idx, group_idx, group_sample_size):
+        return self._sample_group(1, row_idx, group_idx, group_sample_size)
+
+    def hh_sample_group(self, row_idx, group_idx, group_sample_size):
+        return self._sample_group(2, row_idx, group_idx, group_sample_size)
+
+    def _compress_group(self, li, row_idx, group_idx):
         n = int(np.ceil(2 ** self.bit_per_group))
         self._ensure_rec(n)
-        q_scale, p_scale = self._scales()
+        lv = self._levels[li]
+        q_scale, p_scale = self._scales(li)
         pr, pb = self._pairs([row_idx], [group_idx])
-        _rec.encode(self._lv, self._tables_ptr, self._g_dev, q_scale, p_scale, pr, pb, n, self._max_D, apply=True)
-        s, e = int(self.group_start_index[group_idx]), int(self.group_end_index[group_idx])
-        return int(self._lv.idx[row_idx, group_idx].item()), self._lv.sample[row_idx, s:e].clone()
+        _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, pr, pb, n, lv.max_D, apply=True)
+        s, e = int(lv.group_start_host[group_idx]), int(lv.group_end_host[group_idx])
+        return int(lv.idx[row_idx, group_idx].item()), lv.sample[row_idx, s:e].clone()
 
-    def compress_round(self, blocks: Optional[torch.Tensor] = None):
-        """Code one block of every row in a single launch.  With blocks=None each row
-        codes its largest-KL not-yet-coded block (test_model.py:809-817)."""
+    def compress_group(self, row_idx, group_idx):
+        return self._compress_group(0, row_idx, group_idx)
+
+    def h_compress_group(self, row_idx, group_idx):
+        return self._compress_group(1, row_idx, group_idx)
+
+    def hh_compress_group(self, row_idx, group_idx):
+        return self._compress_group(2, row_idx, group_idx)
+
+    def compress_round(self, blocks: Optional[torch.Tensor] = None, level: int = 0):
+        """Code one block of every row of a level in a single launch.  With blocks=None each
+        row codes its largest-KL not-yet-coded block (test_model.py:809-817)."""
         from ._lib import check, ptr, stream
         n = int(np.ceil(2 ** self.bit_per_group))
         self._ensure_rec(n)
-        lv = self._lv
+        lv = self._levels[level]
         rows = torch.arange(lv.rows, dtype=torch.int32, device=self.device)
         if blocks is None:
             kl = self.engine.group_kl(lv)
             blocks = torch.empty(lv.rows, dtype=torch.int32, device=self.device)
             check(self.engine.lib.rcb_pick_block(ptr(kl), ptr(lv.coded), ptr(blocks), lv.rows, lv.G, stream()),
                   "rcb_pick_block")
-        q_scale, p_scale = self._scales()
-        _rec.encode(lv, self._tables_ptr, self._g_dev, q_scale, p_scale, rows, blocks.contiguous(), n, self._max_D,
+        q_scale, p_scale = self._scales(level)
+        _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, rows, blocks.contiguous(), n, lv.max_D,
                     apply=True)
         return blocks
 
-    def decode_posteriors(self, indices: np.ndarray) -> torch.Tensor:
-        """Receiver side (the reference has none): rebuild every coded value from the
-        transmitted (rows, G) index table, prior and seed.  Returns (rows, P) in group order."""
+    def decode_posteriors(self, indices: np.ndarray, level: int = 0) -> torch.Tensor:
+        """Receiver side (the reference has none): rebuild every coded value of a level from
+        its transmitted (rows, G) index table, the prior and the seed.  (rows, P), group order."""
         n = int(np.ceil(2 ** self.bit_per_group))
         self._ensure_rec(n)
-        lv = self._lv
+        lv = self._levels[level]
         rows = torch.arange(lv.rows, device=self.device, dtype=torch.int32).repeat_interleave(lv.G).contiguous()
         blocks = torch.arange(lv.G, device=self.device, dtype=torch.int32).repeat(lv.rows).contiguous()
         idx = torch.as_tensor(np.asarray(indices).astype(np.int32), device=self.device).reshape(-1).contiguous()
         out = torch.zeros(lv.rows, lv.P, device=self.device)
-        _rec.decode(lv, self._tables_ptr, self.st(self.p_log_scale).contiguous(), rows, blocks, idx, n, out, None)
+        _rec.decode(lv, lv.tables_ptr, self.st(lv.p_log_scale).contiguous(), rows, blocks, idx, n, out, None)
         return out
 
     # ------------------------------------------------------------------- training --
     def _adam_config(self, optimizer):
-        if optimizer is not self._adam_owner:
+        if optimizer is not self._adam_owner or self._levels[0].adam is None:
             self._adam_owner = optimizer
-            self._lv.reset_adam()
+            for lv in self._levels:
+                lv.reset_adam()
         g = optimizer.param_groups[0] if optimizer is not None else {}
         b1, b2 = g.get("betas", (0.9, 0.999))
         return dict(lr=float(g.get("lr", 2e-4)), b1=float(b1), b2=float(b2), eps=float(g.get("eps", 1e-8)))
 
     def fit_step(self, x, y, epoch, adam_cfg, sample_size=5, eps=None, anneal=None):
         """One fused step: forward, loss, backward, (annealing), Adam (test_model.py:622-635)."""
-        lv, eng = self._lv, self.engine
+        levels, eng = self._levels, self.engine
+        rows = levels[0].rows
         S = sample_size
         noise = self._noise(epoch, eps)
-        ws = eng.forward_features(lv, S, noise)
+        ws = eng.forward_features(levels, S, noise)
         # d/dy of N * mean_{n,s,pix,c} (y_pred - y)^2
         coef = 2.0 / (S * eng.pix * eng.out)
-        eng.mlp(ws, lv.rows, S, x, mode=1, y=y, coef=coef)
-        eng.backward_features(ws, lv.rows, S)
+        eng.mlp(ws, rows, S, x, mode=1, y=y, coef=coef)
+        eng.backward_features(ws, rows, S)
         do_anneal = (epoch % self.kl_adjust_gap == 0) if anneal is None else anneal
-        if do_anneal:
-            eng.group_kl(lv)            # KL of the pre-step posterior ...
-        eng.update(lv, ws, S, noise, with_data_grads=True, adam=adam_cfg)
-        if do_anneal:                   # ... beta changes only after this step's gradient (test_model.py:629-634)
-            eng.anneal(lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer, float(self.bit_per_group))
+        for lv in levels:
+            if lv.adam is None:
+                lv.reset_adam()
+            if do_anneal:
+                eng.group_kl(lv)            # KL of the pre-step posterior ...
+            eng.update(lv, ws, S, noise, with_data_grads=True, adam=adam_cfg, rows=rows)
+            if do_anneal:                   # ... beta changes only after this step's gradient (test_model.py:629-634)
+                eng.anneal(lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer,
+                           float(self.bit_per_group))
         return ws
 
     def train(self, x=True, y=None, n_epochs=0, optimizer=None, verbose=False, sample_size=5):
@@ -361,12 +473,19 @@ class TestBNNmodel(nn.Module):
         for epoch in it:
             self.fit_step(x, y, epoch, cfg, sample_size)
 
-    def _report(self, x, y, header):
+    def _distortion(self, x, y):
         with torch.no_grad():
             y_pred = self.predict(x.to(self.device)).cpu()
-            distortion = np.mean(metric(y.cpu().numpy(), y_pred.numpy(), self.dataset))
-        kl_bits = self.update_annealing_factors(False) / np.log(2.)
-        print(header + " Average Distortion %.4f" % distortion, flush=True)
+        return metric(y.cpu().numpy(), y_pred.numpy(), self.dataset)
+
+    def _all_kl_bits(self):
+        kls = self.update_annealing_factors(False)
+        kls = kls if self.patch else (kls,)
+        return [k / np.log(2.) for k in kls]
+
+    def _report(self, x, y, header):
+        print(header + " Average Distortion %.4f" % np.mean(self._distortion(x, y)), flush=True)
+        kl_bits = np.concatenate([k.reshape(-1) for k in self._all_kl_bits()])
         print("Bits per group: ave %.2f" % kl_bits.mean() + " max %.2f" % kl_bits.max(), flush=True)
 
     def optimize_posteriors(self, x, y, n_epochs, lr, verbose):
@@ -379,43 +498,51 @@ class TestBNNmodel(nn.Module):
         if verbose:
             self._report(x, y, "Optimization Finished.")
 
-    def compress_posteriors(self, x, y, n_epochs_finetune, h_n_epochs_finetune=None, hh_n_epochs_finetune=None,
-                            verbose=False, lr=2e-4, fine_tune_gap=1, compress_from_group_with_largest_kl=True):
-        """Progressive coding: each round codes one block per row, then re-fits the
-        remaining blocks (test_model.py:800-856)."""
-        if verbose:
-            print("Start to compress posteriors by A* coding...", flush=True)
-        if not hasattr(self, "compressed_num"):
-            self.compressed_num = 0
-        lv = self._lv
-        print_step = set(np.round(np.linspace(0, self.n_groups, 10)).astype(int).tolist())
-        it = range(self.compressed_num, self.n_groups)
+    def _compress_level(self, li, x, y, n_epochs_finetune, verbose, lr, fine_tune_gap, largest_kl):
+        """Code every block of one level: per round, one block of each row, then a re-fit of
+        everything not yet coded with fresh Adam moments (test_model.py:709-728,806-827)."""
+        lv = self._levels[li]
+        counter = self._PREFIX[li] + "compressed_num"
+        if not hasattr(self, counter):
+            setattr(self, counter, 0)
+        print_step = set(np.round(np.linspace(0, lv.G, 10)).astype(int).tolist())
+        it = range(getattr(self, counter), lv.G)
         if verbose:
             from tqdm import tqdm
             it = tqdm(it)
         for _i in it:
-            if compress_from_group_with_largest_kl:
-                self.compress_round()
+            if largest_kl:
+                self.compress_round(level=li)
             else:
-                self.compress_round(torch.full((lv.rows,), _i, dtype=torch.int32, device=self.device))
-            self.compressed_num += 1
-            if self.compressed_num % fine_tune_gap == 0:
+                self.compress_round(torch.full((lv.rows,), _i, dtype=torch.int32, device=self.device), level=li)
+            setattr(self, counter, getattr(self, counter) + 1)
+            if getattr(self, counter) % fine_tune_gap == 0:
                 optimizer = torch.optim.Adam(self.parameters(), lr=lr)   # fresh moments each round
                 self.train(x, y, n_epochs=n_epochs_finetune, optimizer=optimizer, verbose=False)
             if verbose and _i in print_step:
-                with torch.no_grad():
-                    y_pred = self.predict(x.to(self.device)).cpu()
-                    distortion = np.mean(metric(y.cpu().numpy(), y_pred.numpy(), self.dataset))
-                kl_bits = self.update_annealing_factors(False) / np.log(2.)
-                open_ = ~self.compressed_mask_groupwise
+                kl_bits = self._all_kl_bits()[li]
+                open_ = ~lv.coded.bool().cpu().numpy()
                 if open_.any():
-                    print("Compress progress: %d; " % (100 * self.compressed_num / self.n_groups),
-                          "Average Distortion %.4f; " % distortion,
+                    print("Compress progress: %d; " % (100 * getattr(self, counter) / lv.G),
+                          "Average Distortion %.4f; " % np.mean(self._distortion(x, y)),
                           "KL in uncompressed groups: MAX %.3f" % kl_bits[open_].max(),
                           "AVE %.3f. " % kl_bits[open_].mean(), flush=True)
-        with torch.no_grad():
-            y_pred = self.predict(x.to(self.device)).cpu()
-            distortion = metric(y.cpu().numpy(), y_pred.numpy(), self.dataset)
+        if verbose:
+            print(' ')
+
+    def compress_posteriors(self, x, y, n_epochs_finetune, h_n_epochs_finetune=None, hh_n_epochs_finetune=None,
+                            verbose=False, lr=2e-4, fine_tune_gap=1, compress_from_group_with_largest_kl=True):
+        """Progressive coding, coarsest level first: level 3, level 2, then the per-row level
+        (test_model.py:687-856).  Returns the distortion of the fully coded posterior."""
+        if verbose:
+            print("Start to compress posteriors by A* coding...", flush=True)
+        if self.patch:
+            self._compress_level(2, x, y, hh_n_epochs_finetune, verbose, lr, fine_tune_gap,
+                                 compress_from_group_with_largest_kl)
+            self._compress_level(1, x, y, h_n_epochs_finetune, verbose, lr, fine_tune_gap,
+                                 compress_from_group_with_largest_kl)
+        self._compress_level(0, x, y, n_epochs_finetune, verbose, lr, fine_tune_gap, compress_from_group_with_largest_kl)
+        distortion = self._distortion(x, y)
         if verbose:
             print("Optimization Finished. Average Distortion %.4f" % np.mean(distortion), flush=True)
         return distortion

@@ -25,26 +25,32 @@ def product_test_model(case, dataset, device="cuda", quiet=True, precision="fp32
     from recombiner_b200.test_model import TestBNNmodel
     shape = case["shape"]
     lt, up = product_mappings(case, device)
-    L = case["lvl1"]
+    kw = {}
+    for pre, key in (("", "lvl1"), ("h_", "lvl2"), ("hh_", "lvl3")):
+        if key not in case:
+            continue
+        L = case[key]
+        kw.update({pre + "p_loc": L["p_loc"], pre + "p_log_scale": L["p_log_scale"], pre + "init_log_scale": -4.0,
+                   pre + "param_to_group": L["param_to_group"], pre + "group_to_param": L["group_to_param"],
+                   pre + "n_groups": L["n_groups"], pre + "group_start_index": L["group_start"],
+                   pre + "group_end_index": L["group_end"], pre + "group_idx": L["group_idx"]})
     ctx = contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()
     with ctx:
         m = TestBNNmodel(in_dim=shape.dims[0], hidden_dims=shape.dims[1:-1], out_dim=shape.dims[-1],
                          number_of_datapoints=case["rows"], upsample_factors=shape.upsample_factors,
                          latent_dim=shape.latent_dim, data_dim=shape.data_dim, pixel_sizes=shape.pixel_sizes,
                          patch=shape.patch, patch_nums=shape.patch_nums, hierarchical_patch_nums=shape.hier,
-                         dataset=dataset, linear_transform=lt, upsample_net=up,
-                         p_loc=L["p_loc"], p_log_scale=L["p_log_scale"], init_log_scale=-4.0,
-                         param_to_group=L["param_to_group"], group_to_param=L["group_to_param"],
-                         n_groups=L["n_groups"], group_start_index=L["group_start"], group_end_index=L["group_end"],
-                         group_idx=L["group_idx"], device=device, random_seed=42,
-                         layer_scales=shape.layer_scales, paddings=shape.paddings, precision=precision)
+                         dataset=dataset, linear_transform=lt, upsample_net=up, device=device, random_seed=42,
+                         layer_scales=shape.layer_scales, paddings=shape.paddings, precision=precision, **kw)
     with torch.no_grad():
-        m.loc.copy_(L["loc"])
-        m.log_scale.copy_(L["log_scale"])
-        m._lv.mask.copy_(L["mask"])
-        m._lv.sample.copy_(L["sample"])
-        m._lv.coded.copy_(torch.from_numpy(L["coded"].astype(np.uint8)))
-        m._lv.beta.copy_(L["beta"])
+        for lv, key in zip(m._levels, ("lvl1", "lvl2", "lvl3")):
+            L = case[key]
+            lv.loc.copy_(L["loc"])
+            lv.log_scale.copy_(L["log_scale"])
+            lv.mask.copy_(L["mask"])
+            lv.sample.copy_(L["sample"])
+            lv.coded.copy_(torch.from_numpy(L["coded"].astype(np.uint8)))
+            lv.beta.copy_(L["beta"])
     return m
 
 

@@ -169,3 +169,51 @@ def test_tf32_tensor_core_mode_within_stated_tolerance(golden, name, dataset, n_
     assert err < 5e-3
     assert mse.item() == pytest.approx(float(g["mse"]), rel=1e-3)
     assert all(v < 2e-2 for v in rel.values())
+
+
+@pytest.mark.parametrize("name,dataset,n_data,S", [("patch2d", "kodak", 1, 2), ("patch1d", "audio", 2, 2)])
+def test_patch_modalities_match_reference(golden, name, dataset, n_data, S):
+    """Patch modalities: stitched latent grid through the upsampler, three-level hierarchical
+    weights with per-patch noise, per-column row permutations (utils.py:60-116,142-191;
+    test_model.py:182-208,292-330) -- forward, loss, KL, gradients of all six tensors,
+    per-block KL and annealing of every level."""
+    from tests.helpers import product_test_model
+    g = golden("fit_" + name)
+    case = cases.make_fit_case(name, n_data, S)
+    m = product_test_model(case, dataset)
+    np.testing.assert_array_equal(m.permute_patch_x_g2p, g["perm_g2p"])
+    np.testing.assert_array_equal(m.h_permute_patch_x_g2p, g["h_perm_g2p"])
+    assert m.bpp == pytest.approx(float(g["bpp"]), rel=1e-12)
+    y = case["y"].cuda()
+    y_pred = m.predict(case["x"].cuda(), None, S, eps=case["eps"])
+    np.testing.assert_allclose(y_pred.detach().cpu().numpy(), g["y_pred"], **FWD)
+    mse = torch.mean((y_pred - y[:, None]) ** 2) * y.shape[0]
+    kl = m.calculate_kl()
+    assert mse.item() == pytest.approx(float(g["mse"]), rel=1e-4)
+    assert kl.item() == pytest.approx(float(g["kl"]), rel=1e-4)
+    (mse + kl).backward()
+    for pre in ("", "h_", "hh_"):
+        _grad_close(getattr(m, pre + "loc").grad.cpu().numpy(), g[pre + "grad_loc"])
+        _grad_close(getattr(m, pre + "log_scale").grad.cpu().numpy(), g[pre + "grad_log_scale"])
+    kls = m.update_annealing_factors(True)
+    for k, pre in zip(kls, ("", "h_", "hh_")):
+        np.testing.assert_allclose(k, g[pre + "group_kl"], rtol=2e-5)
+        np.testing.assert_allclose(getattr(m, pre + "kl_beta").cpu().numpy(), g[pre + "beta_after"], rtol=1e-6)
+
+
+def test_patch_fused_step_and_progressive_coding():
+    """Patch modality through the fused step and the level-3 -> level-2 -> level-1 coding
+    order; every level decodes bit-exactly from its index table."""
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case("patch2d", 1, 2, coded_frac=0.0, total_bits=64.0)
+    m = product_test_model(case, "kodak")
+    x, y = case["x"].cuda(), case["y"].cuda()
+    before = [lv.loc.detach().clone() for lv in m._levels]
+    d = m.compress_posteriors(x, y, n_epochs_finetune=2, h_n_epochs_finetune=2, hh_n_epochs_finetune=2,
+                              verbose=False, lr=2e-4)
+    assert np.isfinite(d)
+    for li, lv in enumerate(m._levels):
+        assert bool(lv.coded.all()) and not torch.equal(lv.loc.detach(), before[li])
+        idx = (m.compressed_idx_groupwise, m.h_compressed_idx_groupwise, m.hh_compressed_idx_groupwise)[li]
+        assert idx.shape == (lv.rows, lv.G)
+        assert torch.equal(m.decode_posteriors(idx, level=li), lv.sample)
