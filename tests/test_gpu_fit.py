@@ -217,3 +217,32 @@ def test_patch_fused_step_and_progressive_coding():
         idx = (m.compressed_idx_groupwise, m.h_compressed_idx_groupwise, m.hh_compressed_idx_groupwise)[li]
         assert idx.shape == (lv.rows, lv.G)
         assert torch.equal(m.decode_posteriors(idx, level=li), lv.sample)
+
+
+@pytest.mark.parametrize("name,dataset,S", [("kodak", "kodak", 1), ("audio", "audio", 2)])
+def test_full_size_patch_modalities_match_oracle(name, dataset, S):
+    """BASELINE configs 3 and 4 at their real shapes (kodak: 96 patches of 64x64 stitched to a
+    32x48 latent grid -> polyphase first stage; audio: 60 patches of 800 samples): forward,
+    loss and all gradients against the (golden-pinned) oracle on the same inputs and noise."""
+    from tests.helpers import oracle_level, product_test_model
+    case = cases.make_fit_case(name, 1, S, total_bits=800.0)
+    m = product_test_model(case, dataset)
+    assert not m.engine.dense1
+    lv = {}
+    for key in ("lvl1", "lvl2", "lvl3"):
+        lv[key] = oracle_level(case[key])
+        if key != "lvl3":
+            lv[key].perm_g2p = orc.column_row_permutations(*case[key]["loc"].shape)
+    ref = orc.predict(case["x"], lv["lvl1"], case["A"], case["w_up"], case["shape"], case["eps"], S, lv["lvl2"], lv["lvl3"])
+    loss_ref = orc.fit_loss(ref, case["y"]) + sum(orc.weighted_kl(lv[k], case[k]["beta"]) for k in lv)
+    loss_ref.backward()
+    y = case["y"].cuda()
+    y_pred = m.predict(case["x"].cuda(), None, S, eps=case["eps"])
+    yp = y_pred if S > 1 else y_pred[:, None]
+    np.testing.assert_allclose(yp.detach().cpu().numpy(), ref.detach().numpy(), **FWD)
+    loss = torch.mean((yp - y[:, None]) ** 2) * y.shape[0] + m.calculate_kl()
+    assert loss.item() == pytest.approx(loss_ref.item(), rel=1e-4)
+    loss.backward()
+    for pre, key in (("", "lvl1"), ("h_", "lvl2"), ("hh_", "lvl3")):
+        _grad_close(getattr(m, pre + "loc").grad.cpu().numpy(), lv[key].loc.grad.numpy())
+        _grad_close(getattr(m, pre + "log_scale").grad.cpu().numpy(), lv[key].log_scale.grad.numpy())
