@@ -71,6 +71,7 @@ def compress(x, y, dataset, prior_objects, device, seed=42, fit_epochs=None, fin
                          layer_scales=config['layerwise_scale_factors'], paddings=config['paddings'], **kw).to(device)
     n_groups = kw["n_groups"]
     h_n, hh_n = kw.get("h_n_groups"), kw.get("hh_n_groups")
+    short = finetune_epochs            # an explicit fine-tune length also shortens the level-2/3 rounds
     fit_epochs = int(os.environ.get("RECOMBINER_FIT_EPOCHS", 30000)) if fit_epochs is None else fit_epochs
     if finetune_epochs is None:
         finetune_epochs = int(os.environ.get("RECOMBINER_FINETUNE_EPOCHS", max(30000 // n_groups, 50)))
@@ -78,8 +79,8 @@ def compress(x, y, dataset, prior_objects, device, seed=42, fit_epochs=None, fin
     model.optimize_posteriors(x, y, n_epochs=fit_epochs, lr=2e-4, verbose=verbose)
     distortion = model.compress_posteriors(
         x, y, n_epochs_finetune=finetune_epochs,
-        h_n_epochs_finetune=None if h_n is None else max(15000 // h_n, 20),
-        hh_n_epochs_finetune=None if hh_n is None else max(15000 // hh_n, 20),
+        h_n_epochs_finetune=None if h_n is None else (max(15000 // h_n, 20) if short is None else short),
+        hh_n_epochs_finetune=None if hh_n is None else (max(15000 // hh_n, 20) if short is None else short),
         verbose=verbose, lr=2e-4, fine_tune_gap=1, compress_from_group_with_largest_kl=True)
     return distortion, model
 

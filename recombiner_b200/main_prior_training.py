@@ -55,7 +55,7 @@ def step_beta(kl_beta, kl_bits, lo, hi):
 
 def checkpoint_objects(model, priors, kl_beta, linear_transform, upsample_net):
     """The 8 pickled objects of a prior checkpoint (main_prior_training.py:284-335)."""
-    prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale = priors
+    prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale = priors[:4]
     with torch.no_grad():
         q_loc = torch.cat([model.loc.flatten(1), model.lpe_loc.flatten(1)], -1)
         q_scale = torch.cat([model.st(model.log_scale).flatten(1), model.st(model.lpe_log_scale).flatten(1)], -1)
@@ -64,9 +64,15 @@ def checkpoint_objects(model, priors, kl_beta, linear_transform, upsample_net):
         grouping = get_grouping(q_loc, q_scale, p_loc, p_scale)
         avg_ls = torch.cat([model.log_scale.detach().mean(0).cpu(), model.lpe_log_scale.detach().mean(0).flatten().cpu()])
     none8 = (None,) * 8
-    return [grouping, (p_loc.cpu(), p_scale.cpu(), kl_beta, avg_ls),
-            none8, (None, None, kl_beta, None), none8, (None, None, kl_beta, None),
-            linear_transform, upsample_net]
+    extra = [none8, (None, None, kl_beta, None), none8, (None, None, kl_beta, None)]
+    if model.patch:
+        extra = []
+        for li, (q_l, q_ls) in enumerate(((model.h_loc, model.h_log_scale), (model.hh_loc, model.hh_log_scale))):
+            pl, ps = priors[4 + 2 * li], priors[5 + 2 * li]
+            with torch.no_grad():
+                extra.append(get_grouping(q_l, model.st(q_ls), pl, ps))
+                extra.append((pl.cpu(), ps.cpu(), kl_beta, q_ls.detach().mean(0).flatten().cpu()))
+    return [grouping, (p_loc.cpu(), p_scale.cpu(), kl_beta, avg_ls)] + extra + [linear_transform, upsample_net]
 
 
 def save_checkpoint(path, objects):
@@ -84,8 +90,6 @@ def train_prior(X, Y, dataset, max_bitrate, device="cuda", seed=42, n_em_iter=55
                 lr=2e-4, checkpoint_every=10, on_checkpoint=None, verbose=True, row_offset=0, global_train_size=None):
     """Returns (checkpoint objects, list of ELBOs).  X, Y: this rank's rows."""
     config = configs[dataset]
-    if config['patch']:
-        raise NotImplementedError("patch modalities are not wired to the kernels yet")
     train_size = X.shape[0]
     model = PriorBNNmodel(in_dim=config['input_dim'], hidden_dims=config['hidden_dims'], out_dim=config['output_dim'],
                           train_size=train_size, data_dim=config['data_dim'], pixel_sizes=config['pixel_sizes'],
@@ -104,11 +108,14 @@ def train_prior(X, Y, dataset, max_bitrate, device="cuda", seed=42, n_em_iter=55
     W, lpe_shape = model._W, model._lpe_shape
     priors = (torch.zeros(W, device=device), torch.full((W,), s0, device=device),
               torch.zeros(lpe_shape, device=device), torch.full(lpe_shape, s0, device=device))
+    if config['patch']:
+        priors += (torch.zeros(W, device=device), torch.full((W,), s0, device=device)) * 2
     X, Y = X.to(device), Y.to(device)
     elbos, objects, n_epoch = [], None, first_epochs
     for it in range(n_em_iter):
-        _, kl_per_row, e = model.train(n_epoch, lr, X, Y, *priors, None, None, None, None, linear_transform,
-                                       upsample_net, kl_beta, training_mappings=True, verbose=False)
+        p8 = tuple(priors) + (None,) * (8 - len(priors))
+        _, kl_per_row, e = model.train(n_epoch, lr, X, Y, *p8, linear_transform, upsample_net, kl_beta,
+                                       training_mappings=True, verbose=False)
         elbos += e
         n_epoch = epochs
         kl_bits = kl_per_row / np.log(2.)                 # average KL per row in bits (already all-reduced)

@@ -119,8 +119,8 @@ class PriorBNNmodel(nn.Module):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise KernelError("recombiner_b200.PriorBNNmodel runs on CUDA (sm_100a) only -- no CPU fallback")
-        if patch:
-            raise NotImplementedError("patch modalities are not wired to the kernels yet")
+        if patch and data_dim == 3:
+            raise NotImplementedError("the 3-D (video) upsampler is not wired to the kernels yet")
         self.random_seed, self.device = random_seed, dev
         self.n_layers = len(hidden_dims) + 1
         self.dims = [in_dim] + list(hidden_dims) + [out_dim]
@@ -136,12 +136,21 @@ class PriorBNNmodel(nn.Module):
         self._lpe_shape = [pixel_sizes[i] // upsample_factors[i] for i in range(data_dim)] + [latent_dim]
         L = int(np.prod(self._lpe_shape))
         self._W, self._L = W, L
-        # reference init order under torch.manual_seed(seed): loc (rand), then lpe_loc (randn)
-        # (prior_model.py:100-110).  A shard draws the global tensors and keeps its rows.
+        # reference init order under torch.manual_seed(seed): loc (rand), [h_loc, hh_loc (rand)],
+        # then lpe_loc (randn) (prior_model.py:100-110).  A shard draws the global tensors and
+        # keeps its rows.
         n_glob = int(global_train_size) if global_train_size is not None else train_size
+        R = int(np.prod(patch_nums)) if patch else 1
+        n2 = int(np.prod(hierarchical_patch_nums['level2'])) if patch else 1
+        n3 = int(np.prod(hierarchical_patch_nums['level3'])) if patch else 1
+        if train_size % R or self.row_offset % R or (patch and (train_size % n2 or train_size % n3)):
+            raise KernelError("patch modalities shard by whole datum: rows must be a multiple of the patch count")
         torch.manual_seed(random_seed)
         w_std = np.sqrt(c / hidden_dims[-1]) / w0
         loc = torch.rand(n_glob, W) * w_std * 2 - w_std
+        if patch:
+            h_loc = torch.rand(n_glob // n2, W) * w_std * 2 - w_std
+            hh_loc = torch.rand(n_glob // n3, W) * w_std * 2 - w_std
         lpe = torch.randn(n_glob, *self._lpe_shape) * 0.1
         rows = slice(self.row_offset, self.row_offset + train_size)
         both = torch.cat([loc[rows], lpe[rows].reshape(train_size, L)], 1)
@@ -149,10 +158,31 @@ class PriorBNNmodel(nn.Module):
         self._log_scale_all = nn.Parameter(torch.zeros(train_size, W + L, device=dev) + init_log_scale)
         self.engine = FitEngine(self.dims, data_dim, pixel_sizes, upsample_factors, latent_dim,
                                 layer_scales if layer_scales is not None else [4, 2, 2],
-                                paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision)
+                                paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision,
+                                patch_nums=patch_nums if patch else None)
         zero = torch.zeros(W + L)
         self._lv = LevelState(self._loc_all, self._log_scale_all, zero, zero, None, None, None, None, None, 0.0, dev)
         self._lv.p_scale_direct = True
+        self._levels = [self._lv]
+        if patch:
+            def shard(t, div):
+                return t[self.row_offset // div:(self.row_offset + train_size) // div]
+            self.h_loc = nn.Parameter(shard(h_loc, n2).to(dev).contiguous())
+            self.h_log_scale = nn.Parameter(torch.zeros(train_size // n2, W, device=dev) + init_log_scale)
+            self.hh_loc = nn.Parameter(shard(hh_loc, n3).to(dev).contiguous())
+            self.hh_log_scale = nn.Parameter(torch.zeros(train_size // n3, W, device=dev) + init_log_scale)
+            l2 = hierarchical_patch_nums['level2']
+            ng = [patch_nums[i] // l2[i] for i in range(data_dim)]
+            n = np.arange(train_size)
+            pc = np.unravel_index(n % R, patch_nums)
+            grp = np.ravel_multi_index([pc[i] // l2[i] for i in range(data_dim)], ng)
+            maps = [(n // R) * int(np.prod(ng)) + grp, n // R]
+            zw = torch.zeros(W)
+            for li, (lo, ls) in enumerate(((self.h_loc, self.h_log_scale), (self.hh_loc, self.hh_log_scale)), start=1):
+                lv = LevelState(lo, ls, zw, zw, None, None, None, None, None, 0.0, dev)
+                lv.p_scale_direct, lv.level = True, li
+                lv.set_expansion(maps[li - 1])
+                self._levels.append(lv)
         self._call = 0
 
     # views with the reference's attribute names
@@ -183,15 +213,23 @@ class PriorBNNmodel(nn.Module):
     def _noise(self, eps=None, step=0):
         from .engine import Noise
         if eps is not None:
-            return Noise(eps_w=eps["w"].to(self.device).contiguous(),
-                         eps_l=eps["lpe"].to(self.device).reshape(1, self.train_size, self._L).contiguous())
+            dev = self.device
+            return Noise(eps_w=eps["w"].to(dev).contiguous(),
+                         eps_l=eps["lpe"].to(dev).reshape(1, self.train_size, self._L).contiguous(),
+                         eps_h=eps["h"].to(dev).contiguous() if "h" in eps else None,
+                         eps_hh=eps["hh"].to(dev).contiguous() if "hh" in eps else None)
         base = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         return Noise(seed=((int(self.random_seed) & 0x7fffffff) << 32) | base, step=step, row_offset=self.row_offset)
 
-    def _set_prior(self, prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale):
+    def _set_prior(self, prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc=None, prior_h_scale=None,
+                   prior_hh_loc=None, prior_hh_scale=None):
+        f = lambda t: t.reshape(-1).to(self.device, torch.float32).contiguous()
         lv = self._lv
-        lv.p_loc = torch.cat([prior_loc.reshape(-1), prior_lpe_loc.reshape(-1)]).to(self.device, torch.float32).contiguous()
-        lv.p_log_scale = torch.cat([prior_scale.reshape(-1), prior_lpe_scale.reshape(-1)]).to(self.device, torch.float32).contiguous()
+        lv.p_loc = torch.cat([f(prior_loc), f(prior_lpe_loc)]).contiguous()
+        lv.p_log_scale = torch.cat([f(prior_scale), f(prior_lpe_scale)]).contiguous()
+        if self.patch:
+            self._levels[1].p_loc, self._levels[1].p_log_scale = f(prior_h_loc), f(prior_h_scale)
+            self._levels[2].p_loc, self._levels[2].p_log_scale = f(prior_hh_loc), f(prior_hh_scale)
 
     def forward(self, x, linear_transform, upsample_net, gradient_through_A=True, eps=None):
         """Single-sample reconstruction (rows, pixels, out) (prior_model.py:129-179).  Evaluation
@@ -199,34 +237,38 @@ class PriorBNNmodel(nn.Module):
         assert x.shape[0] == self.train_size
         eng = self.engine
         eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
-        ws = eng.forward_features(self._lv, 1, self._noise(eps))
+        ws = eng.forward_features(self._levels, 1, self._noise(eps))
         eng.mlp(ws, self.train_size, 1, x.to(self.device), mode=0)
         return ws["y_pred"].view(self.train_size, eng.pix, eng.out).clone()
 
     def _kl(self, beta: float):
         """(sum of beta*KL as f64 device scalar, d/dloc, d/dlog_scale) of the current posterior."""
-        lv = self._lv
-        kl = torch.zeros(1, dtype=torch.float64, device=self.device)
-        g_loc, g_ls = torch.empty_like(self._loc_all.data), torch.empty_like(self._log_scale_all.data)
-        lv.beta_scalar = beta
         from .engine import Noise
-        self.engine.update(lv, None, 1, Noise(), with_data_grads=False, adam=None, g_loc=g_loc, g_log_scale=g_ls, kl_out=kl)
-        return kl, g_loc, g_ls
+        kl = torch.zeros(1, dtype=torch.float64, device=self.device)
+        grads = []
+        for lv in self._levels:
+            g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
+            lv.beta_scalar = beta
+            self.engine.update(lv, None, 1, Noise(), with_data_grads=False, adam=None, g_loc=g_loc, g_log_scale=g_ls,
+                               kl_out=kl, rows=self.train_size)
+            grads.append((g_loc, g_ls))
+        return kl, grads
 
     def calculate_kl(self, prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc=None, prior_h_scale=None,
                      prior_hh_loc=None, prior_hh_scale=None):
         """sum KL(q || p) over weights and latent grid (prior_model.py:181-200)."""
-        self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale)
+        self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc, prior_h_scale,
+                        prior_hh_loc, prior_hh_scale)
         return self._kl(1.0)[0].to(torch.float32).reshape(())
 
     def loss_and_grads(self, x, y, priors, linear_transform, upsample_net, kl_beta, eps=None, training_mappings=True):
         """One forward/backward without an optimiser step (parity tests): returns
         (mse*N, sum KL, gradient dict) of loss = N*mean((y_hat-y)^2) + kl_beta * sum KL."""
         eng, lv, N = self.engine, self._lv, self.train_size
-        self._set_prior(*priors[:4])
+        self._set_prior(*priors)
         eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
         noise = self._noise(eps)
-        ws = eng.forward_features(lv, 1, noise)
+        ws = eng.forward_features(self._levels, 1, noise)
         eng.mlp(ws, N, 1, x.to(self.device), mode=1, y=y.to(self.device).contiguous(), coef=2.0 / (eng.pix * eng.out))
         eng.backward_features(ws, N, 1)
         grads = {}
@@ -237,12 +279,19 @@ class PriorBNNmodel(nn.Module):
             for k in ("conv1", "conv2", "conv3"):
                 grads[k + ".weight"], grads[k + ".bias"] = g[k + ".weight"].clone(), g[k + ".bias"].clone()
         kl = torch.zeros(1, dtype=torch.float64, device=self.device)
-        g_loc, g_ls = torch.empty_like(self._loc_all.data), torch.empty_like(self._log_scale_all.data)
-        lv.beta_scalar = float(kl_beta)
-        eng.update(lv, ws, 1, noise, with_data_grads=True, adam=None, g_loc=g_loc, g_log_scale=g_ls, kl_out=kl)
+        per_level = []
+        for l in self._levels:
+            g_loc, g_ls = torch.empty_like(l.loc.data), torch.empty_like(l.log_scale.data)
+            l.beta_scalar = float(kl_beta)
+            eng.update(l, ws, 1, noise, with_data_grads=True, adam=None, g_loc=g_loc, g_log_scale=g_ls, kl_out=kl, rows=N)
+            per_level.append((g_loc, g_ls))
         W = self._W
+        g_loc, g_ls = per_level[0]
         grads.update(loc=g_loc[:, :W], log_scale=g_ls[:, :W], lpe_loc=g_loc[:, W:].reshape(N, *self._lpe_shape),
                      lpe_log_scale=g_ls[:, W:].reshape(N, *self._lpe_shape))
+        if self.patch:
+            grads.update(h_loc=per_level[1][0], h_log_scale=per_level[1][1], hh_loc=per_level[2][0],
+                         hh_log_scale=per_level[2][1])
         mse = ws["sqerr"].sum() / (eng.pix * eng.out)
         return mse, kl / max(float(kl_beta), 1e-300), grads
 
@@ -258,9 +307,11 @@ class PriorBNNmodel(nn.Module):
         eng, lv, N = self.engine, self._lv, self.train_size
         x = x.to(self.device)
         y = y.to(self.device, torch.float32).contiguous()
-        self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale)
-        lv.beta_scalar = float(kl_beta)
-        lv.reset_adam()                          # the reference re-creates Adam on every call (:224-227)
+        self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc, prior_h_scale,
+                        prior_hh_loc, prior_hh_scale)
+        for l in self._levels:
+            l.beta_scalar = float(kl_beta)
+            l.reset_adam()                       # the reference re-creates Adam on every call (:224-227)
         shared = list(linear_transform.parameters()) + list(upsample_net.parameters())
         for p in shared:
             p.requires_grad_(True)
@@ -280,7 +331,7 @@ class PriorBNNmodel(nn.Module):
         for i in it:
             eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
             noise = type(base_noise)(seed=base_noise.seed, step=i, row_offset=self.row_offset)
-            ws = eng.forward_features(lv, 1, noise)
+            ws = eng.forward_features(self._levels, 1, noise)
             eng.mlp(ws, N, 1, x, mode=1, y=y, coef=coef)
             eng.backward_features(ws, N, 1)
             if training_mappings:
@@ -292,7 +343,8 @@ class PriorBNNmodel(nn.Module):
                 for p, t in zip(shared, flat):
                     p.grad = t.reshape(p.shape).clone()
             kl_step.zero_()
-            eng.update(lv, ws, 1, noise, with_data_grads=True, adam=cfg, kl_out=kl_step)
+            for l in self._levels:
+                eng.update(l, ws, 1, noise, with_data_grads=True, adam=cfg, kl_out=kl_step, rows=N)
             if opt is not None:
                 opt.step()
             stats[i, 0] = ws["sqerr"].sum().double() / (eng.pix * eng.out)
@@ -308,22 +360,33 @@ class PriorBNNmodel(nn.Module):
         return mse_last / n_total, float(kl_final.item()) / n_total, elbo
 
 
+def _level_prior(lib, loc, log_scale, n_rows, n_total):
+    import torch.distributed as dist
+    P, dev = loc.shape[1], loc.device
+    stats = torch.empty(3 * P, dtype=torch.float64, device=dev)
+    _check(lib.rcb_prior_suffstats(_ptr(loc), _ptr(log_scale), _ptr(stats), n_rows, P, _stream()), "rcb_prior_suffstats")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    p_loc, p_scale = torch.empty(P, device=dev), torch.empty(P, device=dev)
+    _check(lib.rcb_prior_from_stats(_ptr(stats), _ptr(p_loc), _ptr(p_scale), n_total, P, _stream()), "rcb_prior_from_stats")
+    return p_loc, p_scale
+
+
 def em_prior_update(model: "PriorBNNmodel"):
     """Closed-form prior update from all posteriors (main_prior_training.py:157-172):
     mu_p = mean_n mu_q, sigma_p = sqrt(mean_n sigma_q^2 + var_n mu_q) (unbiased variance),
     from f64 sufficient statistics that are all-reduced across shards.
-    Returns (prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale)."""
+    Returns (prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale[, prior_h_loc, prior_h_scale,
+    prior_hh_loc, prior_hh_scale])."""
     import torch.distributed as dist
     lib = _rcb_lib.load()
-    N, P, dev = model.train_size, model._W + model._L, model.device
-    stats = torch.empty(3 * P, dtype=torch.float64, device=dev)
-    _check(lib.rcb_prior_suffstats(_ptr(model._loc_all.data), _ptr(model._log_scale_all.data), _ptr(stats), N, P, _stream()),
-           "rcb_prior_suffstats")
-    n_total = N
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        n_total = N * dist.get_world_size()
-    p_loc, p_scale = torch.empty(P, device=dev), torch.empty(P, device=dev)
-    _check(lib.rcb_prior_from_stats(_ptr(stats), _ptr(p_loc), _ptr(p_scale), n_total, P, _stream()), "rcb_prior_from_stats")
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     W = model._W
-    return (p_loc[:W], p_scale[:W], p_loc[W:].reshape(model._lpe_shape), p_scale[W:].reshape(model._lpe_shape))
+    out = []
+    for li, lv in enumerate(model._levels):
+        p_loc, p_scale = _level_prior(lib, lv.loc.data, lv.log_scale.data, lv.rows, lv.rows * world)
+        if li == 0:
+            out += [p_loc[:W], p_scale[:W], p_loc[W:].reshape(model._lpe_shape), p_scale[W:].reshape(model._lpe_shape)]
+        else:
+            out += [p_loc, p_scale]
+    return tuple(out)

@@ -91,3 +91,29 @@ def test_short_schedule_matches_oracle_port_statistically():
     kl_gpu = m.update_annealing_factors(False).sum(1) / np.log(2)
     kl_cpu = orc.group_kl_nats(oc.lv).sum(1) / np.log(2)
     np.testing.assert_allclose(kl_gpu, kl_cpu, rtol=0.1)
+
+
+def test_patch_prior_training_and_compression_roundtrip(tmp_path):
+    """Patch modality (audio shape, 2 clips = 120 rows) through prior training, the checkpoint
+    stream with its level-2/3 groupings, and a short compression: plumbing + decode."""
+    from recombiner_b200 import main_compression, main_prior_training, utils
+    from recombiner_b200.config import configs
+    cfg = configs["audio"]
+    coords, _ = utils.to_grid_coordinates_and_features(torch.zeros(1, *cfg["pixel_sizes"]))
+    x1 = utils.fourier_features(coords, cfg["fourier_dim"])
+    g = torch.Generator().manual_seed(4)
+    rows = 120
+    x = x1[None].repeat(rows, 1, 1)
+    y = 0.5 + 0.2 * torch.sin(torch.linspace(0, 40, 800))[None, :, None] * torch.rand(rows, 1, 1, generator=g)
+    objects, elbos, model = main_prior_training.train_prior(x, y, "audio", max_bitrate=10.0, n_em_iter=2,
+                                                            first_epochs=6, epochs=4, checkpoint_every=1, verbose=False)
+    assert np.isfinite(elbos).all() and len(elbos) == 10
+    assert model.h_loc.shape == (30, 3201) and model.hh_loc.shape == (2, 3201)
+    path = str(tmp_path / "prior_audio.pkl")
+    main_prior_training.save_checkpoint(path, objects)
+    loaded = main_compression.load_prior(path)
+    assert loaded[2][5] >= 1 and loaded[4][5] >= 1 and loaded[3][0].shape == (3201,)
+    d, m = main_compression.compress(x[:60], y[:60], "audio", loaded, "cuda", fit_epochs=5, finetune_epochs=1, verbose=0)
+    assert np.isfinite(d)
+    for li, idx in enumerate((m.compressed_idx_groupwise, m.h_compressed_idx_groupwise, m.hh_compressed_idx_groupwise)):
+        assert torch.equal(m.decode_posteriors(idx, level=li), m._levels[li].sample)

@@ -20,8 +20,8 @@ def _model(case):
     lt, up = product_mappings(case, "cuda")
     m = PriorBNNmodel(in_dim=shape.dims[0], hidden_dims=shape.dims[1:-1], out_dim=shape.dims[-1],
                       train_size=case["rows"], data_dim=shape.data_dim, pixel_sizes=shape.pixel_sizes,
-                      upsample_factors=shape.upsample_factors, latent_dim=shape.latent_dim, patch=False,
-                      patch_nums=None, hierarchical_patch_nums=None, device="cuda",
+                      upsample_factors=shape.upsample_factors, latent_dim=shape.latent_dim, patch=shape.patch,
+                      patch_nums=shape.patch_nums, hierarchical_patch_nums=shape.hier, device="cuda",
                       layer_scales=shape.layer_scales, paddings=shape.paddings, precision="fp32")
     W = shape.n_weights
     with torch.no_grad():
@@ -29,6 +29,9 @@ def _model(case):
         m._loc_all[:, W:] = case["lpe_loc"].reshape(case["rows"], -1).cuda()
         m._log_scale_all[:, :W] = case["log_scale"].cuda()
         m._log_scale_all[:, W:] = case["lpe_log_scale"].reshape(case["rows"], -1).cuda()
+        for k in ("h_loc", "h_log_scale", "hh_loc", "hh_log_scale"):
+            if k in case:
+                getattr(m, k).copy_(case[k].cuda())
     return m, lt, up
 
 
@@ -36,21 +39,24 @@ def _close(a, ref, rtol=2e-3):
     np.testing.assert_allclose(a, ref, rtol=rtol, atol=3e-6 * np.abs(ref).max() + 1e-9)
 
 
-@pytest.mark.parametrize("name,n_data", [("cifar", 3), ("protein", 4)])
+@pytest.mark.parametrize("name,n_data", [("cifar", 3), ("protein", 4), ("patch2d", 1)])
 def test_prior_step_matches_reference(golden, name, n_data):
     g = golden("prior_" + name)
     case = cases.make_prior_case(name, n_data)
     m, lt, up = _model(case)
     P = case["prior"]
     pri = (P["loc"], P["scale"], P["lpe_loc"], P["lpe_scale"])
+    if case["shape"].patch:
+        pri += (P["loc"], P["scale"], P["loc"], P["scale"])
     y_hat = m.forward(case["x"].cuda(), lt, up, True, eps=case["eps"])
     np.testing.assert_allclose(y_hat.cpu().numpy(), g["y_hat"], rtol=2e-4, atol=2e-5)
     mse, kl, grads = m.loss_and_grads(case["x"], case["y"], pri, lt, up, case["kl_beta"], eps=case["eps"])
     assert float(mse) == pytest.approx(float(g["mse"]), rel=1e-4)
     assert float(kl) == pytest.approx(float(g["kl"]), rel=1e-4)
     assert float(m.calculate_kl(*pri)) == pytest.approx(float(g["kl"]), rel=1e-4)
-    for k in ("loc", "log_scale", "lpe_loc", "lpe_log_scale"):
-        _close(grads[k].cpu().numpy(), g["grad_" + k])
+    for k in ("loc", "log_scale", "lpe_loc", "lpe_log_scale", "h_loc", "h_log_scale", "hh_loc", "hh_log_scale"):
+        if k in grads:
+            _close(grads[k].cpu().numpy(), g["grad_" + k])
     for i in range(4):
         gf = grads[f"A{i}"].flatten().cpu()
         assert float(gf.double().norm()) == pytest.approx(float(g[f"grad_A{i}_norm"]), rel=1e-3)
