@@ -87,19 +87,20 @@ int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, in
                 int accumulate, rcb_stream_t stream);
 
 /* Geometry of one nearest-upsample + 'same' conv stage on a channel-last grid
- * (1-D signals use h=1, fy=1, ky=1). prior_model.py:29-45. */
+ * (item, d, h, w, c).  2-D signals use d=1, fz=1, kz=1; 1-D also h=1, fy=1, ky=1.
+ * prior_model.py:29-45. */
 typedef struct {
-  int h, w;        /* source grid */
-  int fy, fx;      /* nearest-upsample factors */
-  int ky, kx;      /* kernel extent (odd), padding (k-1)/2 */
+  int d, h, w;     /* source grid */
+  int fz, fy, fx;  /* nearest-upsample factors */
+  int kz, ky, kx;  /* kernel extent (odd), padding (k-1)/2 */
   int ic, oc;
 } rcb_upconv_geom;
 
 /* Fold nearest-upsample into the conv taps (polyphase form): for phase (ry,rx)
  * and tap (ty,tx) in {0,1}^2,
- *   w_eff[ry][rx][ty][tx][ic][oc] = sum of w[oc][ic][ky][kx] over the kernel taps
- *   that land on source offset (by[ry]+ty, bx[rx]+tx).
- * w: torch conv layout (oc, ic, ky, kx).  w_eff_t is the [..][oc][ic] transpose
+ *   w_eff[rz][ry][rx][tz][ty][tx][ic][oc] = sum of w[oc][ic][kz][ky][kx] over the kernel taps
+ *   that land on source offset (bz[rz]+tz, by[ry]+ty, bx[rx]+tx).
+ * w: torch conv layout (oc, ic, kz, ky, kx).  w_eff_t is the [..][oc][ic] transpose
  * used by the data-gradient kernel. */
 int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_eff, float* w_eff_t,
                   rcb_stream_t stream);

@@ -27,7 +27,7 @@ class SampleArgs(C.Structure):
 
 
 class UpconvGeom(C.Structure):
-    _fields_ = [(n, I32) for n in ("h", "w", "fy", "fx", "ky", "kx", "ic", "oc")]
+    _fields_ = [(n, I32) for n in ("d", "h", "w", "fz", "fy", "fx", "kz", "ky", "kx", "ic", "oc")]
 
 
 class MlpArgs(C.Structure):

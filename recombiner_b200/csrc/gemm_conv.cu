@@ -5,22 +5,25 @@ namespace rcb {
 
 static int make_geom(const rcb_upconv_geom* g, PolyGeom* out) {
   RCB_CHECK_ARG(g != nullptr, "upconv: null geometry");
-  RCB_CHECK_ARG(g->h > 0 && g->w > 0 && g->fy > 0 && g->fx > 0, "upconv: bad grid/factors");
-  RCB_CHECK_ARG((g->ky & 1) && (g->kx & 1), "upconv: kernel extents must be odd");
+  RCB_CHECK_ARG(g->d > 0 && g->h > 0 && g->w > 0 && g->fz > 0 && g->fy > 0 && g->fx > 0, "upconv: bad grid/factors");
+  RCB_CHECK_ARG((g->kz & 1) && (g->ky & 1) && (g->kx & 1), "upconv: kernel extents must be odd");
   RCB_CHECK_ARG(g->ic % 16 == 0 && g->oc % 16 == 0, "upconv: channels must be multiples of 16");
-  int py = (g->ky - 1) / 2, px = (g->kx - 1) / 2;
+  int pz = (g->kz - 1) / 2, py = (g->ky - 1) / 2, px = (g->kx - 1) / 2;
+  RCB_CHECK_ARG(pz < g->fz || pz == 0, "upconv: padding %d must be < factor %d", pz, g->fz);
   RCB_CHECK_ARG(py < g->fy || py == 0, "upconv: padding %d must be < factor %d", py, g->fy);
   RCB_CHECK_ARG(px < g->fx || px == 0, "upconv: padding %d must be < factor %d", px, g->fx);
-  out->h = g->h; out->w = g->w; out->fy = g->fy; out->fx = g->fx; out->py = py; out->px = px;
+  out->d = g->d; out->h = g->h; out->w = g->w;
+  out->fz = g->fz; out->fy = g->fy; out->fx = g->fx;
+  out->pz = pz; out->py = py; out->px = px;
+  out->Tz = (pz == 0) ? 1 : 2;
   out->Ty = (py == 0) ? 1 : 2;
   out->Tx = (px == 0) ? 1 : 2;
   out->ic = g->ic; out->oc = g->oc;
   return 0;
 }
 
-// tap index in {0,1} of kernel position kk for phase r (or -1 if it falls off the
-// source grid never -- folding is border-agnostic; borders are handled by the
-// zero-padded gather).
+// tap index in {0,1} of kernel position kk for phase r (folding is border-agnostic;
+// borders are handled by the zero-padded gather)
 __device__ __forceinline__ int tap_of(int r, int kk, int p, int f) {
   int num = r + kk - p;                       // offset on the upsampled grid
   int off = (num >= 0) ? num / f : -((-num + f - 1) / f);   // floor division
@@ -28,31 +31,37 @@ __device__ __forceinline__ int tap_of(int r, int kk, int p, int f) {
   return off - base;
 }
 
-__global__ void fold_poly_kernel(const float* __restrict__ w, PolyGeom g, int ky, int kx,
+// w_eff[phase][tap][ic][oc] (and the [..][oc][ic] transpose)
+__global__ void fold_poly_kernel(const float* __restrict__ w, PolyGeom g, int kz, int ky, int kx,
                                  float* __restrict__ w_eff, float* __restrict__ w_eff_t) {
-  int64_t total = (int64_t)g.fy * g.fx * g.Ty * g.Tx * g.ic * g.oc;
+  int64_t total = (int64_t)g.phases() * g.taps() * g.ic * g.oc;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int o = e % g.oc; int64_t r = e / g.oc;
     int c = r % g.ic; r /= g.ic;
-    int tx = r % g.Tx; r /= g.Tx;
-    int ty = r % g.Ty; r /= g.Ty;
-    int rx = r % g.fx; int ry = r / g.fx;
+    int tap = r % g.taps(); int ph = r / g.taps();
+    int tz, ty, tx, rz, ry, rx;
+    g.split_tap(tap, tz, ty, tx);
+    g.split_phase(ph, rz, ry, rx);
     float s = 0.f;
-    for (int a = 0; a < ky; ++a) {
-      if (tap_of(ry, a, g.py, g.fy) != ty) continue;
-      for (int b = 0; b < kx; ++b) {
-        if (tap_of(rx, b, g.px, g.fx) != tx) continue;
-        s += w[(((int64_t)o * g.ic + c) * ky + a) * kx + b];
+    for (int a0 = 0; a0 < kz; ++a0) {
+      if (tap_of(rz, a0, g.pz, g.fz) != tz) continue;
+      for (int a = 0; a < ky; ++a) {
+        if (tap_of(ry, a, g.py, g.fy) != ty) continue;
+        for (int b = 0; b < kx; ++b) {
+          if (tap_of(rx, b, g.px, g.fx) != tx) continue;
+          s += w[((((int64_t)o * g.ic + c) * kz + a0) * ky + a) * kx + b];
+        }
       }
     }
     w_eff[e] = s;
     if (w_eff_t) {
-      int64_t seg = ((((int64_t)ry * g.fx + rx) * g.Ty + ty) * g.Tx + tx);
+      int64_t seg = (int64_t)ph * g.taps() + tap;
       w_eff_t[(seg * g.oc + o) * g.ic + c] = s;
     }
   }
 }
 
+// dense fold (2-D / 1-D grids only): m[(sy,sx,ic)][(oy,ox,oc)]
 __global__ void fold_dense_kernel(const float* __restrict__ w, PolyGeom g, int ky, int kx,
                                   float* __restrict__ m, float* __restrict__ m_t) {
   int H = g.h * g.fy, W = g.w * g.fx;
@@ -106,9 +115,9 @@ extern "C" int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_
   PolyGeom pg;
   if (int rc = make_geom(g, &pg)) return rc;
   RCB_CHECK_ARG(w && w_eff, "rcb_fold_poly: null pointer");
-  int64_t total = (int64_t)pg.fy * pg.fx * pg.Ty * pg.Tx * pg.ic * pg.oc;
-  int blocks = (int)((total + 255) / 256); if (blocks > 4096) blocks = 4096;
-  fold_poly_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->ky, g->kx, w_eff, w_eff_t);
+  int64_t total = (int64_t)pg.phases() * pg.taps() * pg.ic * pg.oc;
+  int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
+  fold_poly_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->kz, g->ky, g->kx, w_eff, w_eff_t);
   RCB_CHECK_LAUNCH("rcb_fold_poly");
   return 0;
 }
@@ -118,6 +127,7 @@ extern "C" int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m
   PolyGeom pg;
   if (int rc = make_geom(g, &pg)) return rc;
   RCB_CHECK_ARG(w && m, "rcb_fold_dense: null pointer");
+  RCB_CHECK_ARG(pg.d == 1 && pg.fz == 1 && g->kz == 1, "rcb_fold_dense: 1-D / 2-D grids only");
   int64_t total = (int64_t)pg.h * pg.w * pg.ic * pg.h * pg.fy * pg.w * pg.fx * pg.oc;
   int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
   fold_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->ky, g->kx, m, m_t);
@@ -130,8 +140,9 @@ extern "C" int rcb_upconv_fwd(const float* src, const float* w_eff, const float*
   PolyGeom pg;
   if (int rc = make_geom(g, &pg)) return rc;
   RCB_CHECK_ARG(src && w_eff && bias && out, "rcb_upconv_fwd: null pointer");
-  int M = items * pg.h * pg.w, K = pg.Ty * pg.Tx * pg.ic, N = pg.oc, Z = pg.fy * pg.fx;
-  RCB_CHECK_ARG((int64_t)items * pg.h * pg.w < (1LL << 31), "rcb_upconv_fwd: too many rows");
+  int M = items * pg.vol(), K = pg.taps() * pg.ic, N = pg.oc, Z = pg.phases();
+  RCB_CHECK_ARG((int64_t)items * pg.vol() < (1LL << 31), "rcb_upconv_fwd: too many rows");
+  RCB_CHECK_ARG(Z <= 65535, "rcb_upconv_fwd: too many phases");
   ConvFwdA al{src, pg, M};
   ConvFwdC ep{out, pg, M, bias, act};
   return launch_engine("rcb_upconv_fwd", al, w_eff, N, (int64_t)K * N, ep, M, N, K, Z, (cudaStream_t)stream);
@@ -142,8 +153,8 @@ extern "C" int rcb_upconv_bwd(const float* d_out, const float* w_eff_t, const fl
   PolyGeom pg;
   if (int rc = make_geom(g, &pg)) return rc;
   RCB_CHECK_ARG(d_out && w_eff_t && d_src, "rcb_upconv_bwd: null pointer");
-  int M = items * pg.h * pg.w, K = pg.fy * pg.fx * pg.Ty * pg.Tx * pg.oc, N = pg.ic;
-  RCB_CHECK_ARG((int64_t)items * pg.h * pg.w < (1LL << 31), "rcb_upconv_bwd: too many rows");
+  int M = items * pg.vol(), K = pg.phases() * pg.taps() * pg.oc, N = pg.ic;
+  RCB_CHECK_ARG((int64_t)items * pg.vol() < (1LL << 31), "rcb_upconv_bwd: too many rows");
   ConvBwdA al{d_out, pg, M};
   ConvBwdC ep{d_src, src_act, pg.ic, M};
   return launch_engine("rcb_upconv_bwd", al, w_eff_t, N, 0, ep, M, N, K, 1, (cudaStream_t)stream);

@@ -33,70 +33,88 @@ struct TransA {  // A given as [K][M]
   int M;
 };
 
-// polyphase geometry shared by the conv loaders / epilogues
+// polyphase geometry shared by the conv loaders / epilogues (3-D; 2-D uses d=fz=Tz=1)
 struct PolyGeom {
-  int h, w, fy, fx, py, px, Ty, Tx, ic, oc;
+  int d, h, w, fz, fy, fx, pz, py, px, Tz, Ty, Tx, ic, oc;
+  __device__ __forceinline__ int base_z(int rz) const { return rz < pz ? -1 : 0; }
   __device__ __forceinline__ int base_y(int ry) const { return ry < py ? -1 : 0; }
   __device__ __forceinline__ int base_x(int rx) const { return rx < px ? -1 : 0; }
+  __host__ __device__ __forceinline__ int vol() const { return d * h * w; }
+  __host__ __device__ __forceinline__ int phases() const { return fz * fy * fx; }
+  __host__ __device__ __forceinline__ int taps() const { return Tz * Ty * Tx; }
+  __device__ __forceinline__ void split_row(int rem, int& z, int& y, int& x) const {
+    z = rem / (h * w); rem -= z * h * w;
+    y = rem / w; x = rem - y * w;
+  }
+  __device__ __forceinline__ void split_phase(int p, int& rz, int& ry, int& rx) const {
+    rz = p / (fy * fx); p -= rz * fy * fx;
+    ry = p / fx; rx = p - ry * fx;
+  }
+  __device__ __forceinline__ void split_tap(int t, int& tz, int& ty, int& tx) const {
+    tz = t / (Ty * Tx); t -= tz * Ty * Tx;
+    ty = t / Tx; tx = t - ty * Tx;
+  }
 };
 
-// forward: row m = (item, sy, sx); k = ((ty*Tx)+tx)*ic + c; z = ry*fx + rx
+// forward: row m = (item, sz, sy, sx); k = tap*ic + c; z = phase
 struct ConvFwdA {
   static constexpr bool kTrans = false;
   const float* src;
   PolyGeom g;
   int M;
-  struct Row { const float* base; int sy, sx; };
+  struct Row { const float* base; int sz, sy, sx; };
   __device__ __forceinline__ Row row(int m, int z) const {
     Row r;
-    if (m >= M) { r.base = nullptr; r.sy = r.sx = 0; return r; }
-    int hw = g.h * g.w;
-    int item = m / hw, rem = m - item * hw;
-    int sy = rem / g.w, sx = rem - sy * g.w;
-    int ry = z / g.fx, rx = z - ry * g.fx;
+    if (m >= M) { r.base = nullptr; r.sz = r.sy = r.sx = 0; return r; }
+    int vol = g.vol();
+    int item = m / vol, rem = m - item * vol;
+    int sz, sy, sx, rz, ry, rx;
+    g.split_row(rem, sz, sy, sx);
+    g.split_phase(z, rz, ry, rx);
+    r.sz = sz + g.base_z(rz);
     r.sy = sy + g.base_y(ry);
     r.sx = sx + g.base_x(rx);
-    r.base = src + (int64_t)item * hw * g.ic;
+    r.base = src + (int64_t)item * vol * g.ic;
     return r;
   }
   __device__ __forceinline__ const float* chunk(const Row& r, int k, int) const {
     if (!r.base) return nullptr;
     int tap = k / g.ic, c = k - tap * g.ic;
-    int ty = tap / g.Tx, tx = tap - ty * g.Tx;
-    int yy = r.sy + ty, xx = r.sx + tx;
-    if (yy < 0 || yy >= g.h || xx < 0 || xx >= g.w) return nullptr;
-    return r.base + ((int64_t)yy * g.w + xx) * g.ic + c;
+    int tz, ty, tx;
+    g.split_tap(tap, tz, ty, tx);
+    int zz = r.sz + tz, yy = r.sy + ty, xx = r.sx + tx;
+    if (zz < 0 || zz >= g.d || yy < 0 || yy >= g.h || xx < 0 || xx >= g.w) return nullptr;
+    return r.base + (((int64_t)zz * g.h + yy) * g.w + xx) * g.ic + c;
   }
 };
 
-// data gradient: row m = (item, y, x) source pixel;
-// k = ((((ry*fx)+rx)*Ty+ty)*Tx+tx)*oc + o
+// data gradient: row m = (item, z, y, x) source pixel; k = (phase*taps + tap)*oc + o
 struct ConvBwdA {
   static constexpr bool kTrans = false;
   const float* d_out;
   PolyGeom g;
   int M;
-  struct Row { const float* base; int y, x; };
+  struct Row { const float* base; int z, y, x; };
   __device__ __forceinline__ Row row(int m, int) const {
     Row r;
-    if (m >= M) { r.base = nullptr; r.y = r.x = 0; return r; }
-    int hw = g.h * g.w;
-    int item = m / hw, rem = m - item * hw;
-    r.y = rem / g.w;
-    r.x = rem - r.y * g.w;
-    r.base = d_out + (int64_t)item * hw * g.fy * g.fx * g.oc;
+    if (m >= M) { r.base = nullptr; r.z = r.y = r.x = 0; return r; }
+    int vol = g.vol();
+    int item = m / vol, rem = m - item * vol;
+    g.split_row(rem, r.z, r.y, r.x);
+    r.base = d_out + (int64_t)item * vol * g.phases() * g.oc;
     return r;
   }
   __device__ __forceinline__ const float* chunk(const Row& r, int k, int) const {
     if (!r.base) return nullptr;
     int seg = k / g.oc, o = k - seg * g.oc;
-    int tx = seg % g.Tx; seg /= g.Tx;
-    int ty = seg % g.Ty; seg /= g.Ty;
-    int rx = seg % g.fx; int ry = seg / g.fx;
-    int sy = r.y - g.base_y(ry) - ty, sx = r.x - g.base_x(rx) - tx;
-    if (sy < 0 || sy >= g.h || sx < 0 || sx >= g.w) return nullptr;
-    int oy = sy * g.fy + ry, ox = sx * g.fx + rx;
-    return r.base + ((int64_t)oy * (g.w * g.fx) + ox) * g.oc + o;
+    int tap = seg % g.taps(), ph = seg / g.taps();
+    int tz, ty, tx, rz, ry, rx;
+    g.split_tap(tap, tz, ty, tx);
+    g.split_phase(ph, rz, ry, rx);
+    int sz = r.z - g.base_z(rz) - tz, sy = r.y - g.base_y(ry) - ty, sx = r.x - g.base_x(rx) - tx;
+    if (sz < 0 || sz >= g.d || sy < 0 || sy >= g.h || sx < 0 || sx >= g.w) return nullptr;
+    int oz = sz * g.fz + rz, oy = sy * g.fy + ry, ox = sx * g.fx + rx;
+    return r.base + (((int64_t)oz * (g.h * g.fy) + oy) * (g.w * g.fx) + ox) * g.oc + o;
   }
 };
 
@@ -125,12 +143,13 @@ struct ConvFwdC {
   int act;
   __device__ __forceinline__ float* row_ptr(int m, int z) const {
     if (m >= M) return nullptr;
-    int hw = g.h * g.w;
-    int item = m / hw, rem = m - item * hw;
-    int sy = rem / g.w, sx = rem - sy * g.w;
-    int ry = z / g.fx, rx = z - ry * g.fx;
-    int oy = sy * g.fy + ry, ox = sx * g.fx + rx;
-    return out + (((int64_t)item * g.h * g.fy + oy) * (g.w * g.fx) + ox) * g.oc;
+    int vol = g.vol();
+    int item = m / vol, rem = m - item * vol;
+    int sz, sy, sx, rz, ry, rx;
+    g.split_row(rem, sz, sy, sx);
+    g.split_phase(z, rz, ry, rx);
+    int oz = sz * g.fz + rz, oy = sy * g.fy + ry, ox = sx * g.fx + rx;
+    return out + ((((int64_t)item * g.d * g.fz + oz) * (g.h * g.fy) + oy) * (g.w * g.fx) + ox) * g.oc;
   }
   __device__ __forceinline__ float xform(float v, float*, int n) const {
     v += bias[n];

@@ -20,12 +20,11 @@ __global__ void __launch_bounds__(256) upconv_wgrad_kernel(const float* __restri
   const int tid = threadIdx.x;
   const int ic0 = blockIdx.x * BM;
   const int seg = blockIdx.z;
-  int t = seg;
-  const int tx = t % g.Tx; t /= g.Tx;
-  const int ty = t % g.Ty; t /= g.Ty;
-  const int rx = t % g.fx; const int ry = t / g.fx;
-  const int dy = g.base_y(ry) + ty, dx = g.base_x(rx) + tx;
-  const int hw = g.h * g.w, Wout = g.w * g.fx;
+  int tz, ty, tx, rz, ry, rx;
+  g.split_tap(seg % g.taps(), tz, ty, tx);
+  g.split_phase(seg / g.taps(), rz, ry, rx);
+  const int dz = g.base_z(rz) + tz, dy = g.base_y(ry) + ty, dx = g.base_x(rx) + tx;
+  const int vol = g.vol(), Hout = g.h * g.fy, Wout = g.w * g.fx;
   const int m_begin = blockIdx.y * WG_ROWS_PER_CHUNK;
   const int m_end = min(M, m_begin + WG_ROWS_PER_CHUNK);
 
@@ -43,11 +42,12 @@ __global__ void __launch_bounds__(256) upconv_wgrad_kernel(const float* __restri
       const int m = m0 + kk;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < m_end) {
-        int item = m / hw, rem = m - item * hw;
-        int sy = rem / g.w, sx = rem - sy * g.w;
-        int yy = sy + dy, xx = sx + dx;
-        if (yy >= 0 && yy < g.h && xx >= 0 && xx < g.w)
-          v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)item * hw + (int64_t)yy * g.w + xx) * g.ic + ic0 + c4 * 4));
+        int item = m / vol, rem = m - item * vol;
+        int sz, sy, sx;
+        g.split_row(rem, sz, sy, sx);
+        int zz = sz + dz, yy = sy + dy, xx = sx + dx;
+        if (zz >= 0 && zz < g.d && yy >= 0 && yy < g.h && xx >= 0 && xx < g.w)
+          v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)item * vol + ((int64_t)zz * g.h + yy) * g.w + xx) * g.ic + ic0 + c4 * 4));
       }
       *reinterpret_cast<float4*>(&As[kk][c4 * 4]) = v;
     }
@@ -57,10 +57,11 @@ __global__ void __launch_bounds__(256) upconv_wgrad_kernel(const float* __restri
       const int m = m0 + kk;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < m_end) {
-        int item = m / hw, rem = m - item * hw;
-        int sy = rem / g.w, sx = rem - sy * g.w;
-        int oy = sy * g.fy + ry, ox = sx * g.fx + rx;
-        v = __ldg(reinterpret_cast<const float4*>(d_out + (((int64_t)item * g.h * g.fy + oy) * Wout + ox) * g.oc + c4 * 4));
+        int item = m / vol, rem = m - item * vol;
+        int sz, sy, sx;
+        g.split_row(rem, sz, sy, sx);
+        int oz = sz * g.fz + rz, oy = sy * g.fy + ry, ox = sx * g.fx + rx;
+        v = __ldg(reinterpret_cast<const float4*>(d_out + ((((int64_t)item * g.d * g.fz + oz) * Hout + oy) * Wout + ox) * g.oc + c4 * 4));
       }
       *reinterpret_cast<float4*>(&Bs[kk][c4 * 4]) = v;
     }
@@ -93,20 +94,24 @@ __device__ __forceinline__ int tap_index(int r, int kk, int p, int f) {
   return off - (r < p ? -1 : 0);
 }
 
-// d_w[o][c][a][b] = sum over phases of d_w_eff[ry][rx][tap_y(ry,a)][tap_x(rx,b)][c][o]
-__global__ void unfold_poly_kernel(const float* __restrict__ d_w_eff, PolyGeom g, int ky, int kx, float* __restrict__ d_w) {
-  int64_t total = (int64_t)g.oc * g.ic * ky * kx;
+// d_w[o][c][a0][a][b] = sum over phases of d_w_eff[phase][tap(phase, a0, a, b)][c][o]
+__global__ void unfold_poly_kernel(const float* __restrict__ d_w_eff, PolyGeom g, int kz, int ky, int kx, float* __restrict__ d_w) {
+  int64_t total = (int64_t)g.oc * g.ic * kz * ky * kx;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int b = e % kx; int64_t r = e / kx;
     int a = r % ky; r /= ky;
+    int a0 = r % kz; r /= kz;
     int c = r % g.ic; int o = r / g.ic;
     float s = 0.f;
-    for (int ry = 0; ry < g.fy; ++ry) {
-      int ty = tap_index(ry, a, g.py, g.fy);
-      for (int rx = 0; rx < g.fx; ++rx) {
-        int tx = tap_index(rx, b, g.px, g.fx);
-        int64_t seg = (((int64_t)ry * g.fx + rx) * g.Ty + ty) * g.Tx + tx;
-        s += d_w_eff[(seg * g.ic + c) * g.oc + o];
+    for (int rz = 0; rz < g.fz; ++rz) {
+      int tz = tap_index(rz, a0, g.pz, g.fz);
+      for (int ry = 0; ry < g.fy; ++ry) {
+        int ty = tap_index(ry, a, g.py, g.fy);
+        for (int rx = 0; rx < g.fx; ++rx) {
+          int tx = tap_index(rx, b, g.px, g.fx);
+          int64_t seg = (((int64_t)rz * g.fy + ry) * g.fx + rx) * g.taps() + ((tz * g.Ty + ty) * g.Tx + tx);
+          s += d_w_eff[(seg * g.ic + c) * g.oc + o];
+        }
       }
     }
     d_w[e] = s;
@@ -170,9 +175,9 @@ __global__ void colsum_flat_kernel(const float* __restrict__ x, int64_t total, i
 
 static int geom_of(const rcb_upconv_geom* g, PolyGeom* pg) {
   RCB_CHECK_ARG(g != nullptr, "null geometry");
-  pg->h = g->h; pg->w = g->w; pg->fy = g->fy; pg->fx = g->fx;
-  pg->py = (g->ky - 1) / 2; pg->px = (g->kx - 1) / 2;
-  pg->Ty = pg->py == 0 ? 1 : 2; pg->Tx = pg->px == 0 ? 1 : 2;
+  pg->d = g->d; pg->h = g->h; pg->w = g->w; pg->fz = g->fz; pg->fy = g->fy; pg->fx = g->fx;
+  pg->pz = (g->kz - 1) / 2; pg->py = (g->ky - 1) / 2; pg->px = (g->kx - 1) / 2;
+  pg->Tz = pg->pz == 0 ? 1 : 2; pg->Ty = pg->py == 0 ? 1 : 2; pg->Tx = pg->px == 0 ? 1 : 2;
   pg->ic = g->ic; pg->oc = g->oc;
   return 0;
 }
@@ -188,10 +193,11 @@ extern "C" int rcb_upconv_wgrad(const float* src, const float* d_out, float* d_w
   RCB_CHECK_ARG(src && d_out && d_w_eff, "rcb_upconv_wgrad: null pointer");
   RCB_CHECK_ARG(pg.ic % 64 == 0 && (pg.oc == 16 || pg.oc == 64), "rcb_upconv_wgrad: unsupported channels %d -> %d", pg.ic, pg.oc);
   cudaStream_t st = (cudaStream_t)stream;
-  const int nseg = pg.fy * pg.fx * pg.Ty * pg.Tx;
+  const int nseg = pg.phases() * pg.taps();
+  RCB_CHECK_ARG(nseg <= 65535, "rcb_upconv_wgrad: too many (phase, tap) segments");
   cudaError_t e = cudaMemsetAsync(d_w_eff, 0, sizeof(float) * (size_t)nseg * pg.ic * pg.oc, st);
   if (e != cudaSuccess) { set_error("rcb_upconv_wgrad: memset failed: %s", cudaGetErrorString(e)); return -1; }
-  const int M = items * pg.h * pg.w;
+  const int M = items * pg.vol();
   if (M <= 0) return 0;
   dim3 grid(pg.ic / 64, ceil_div(M, WG_ROWS_PER_CHUNK), nseg);
   RCB_CHECK_ARG(grid.y <= 65535, "rcb_upconv_wgrad: too many rows");
@@ -205,8 +211,8 @@ extern "C" int rcb_unfold_poly(const float* d_w_eff, const rcb_upconv_geom* g, f
   PolyGeom pg;
   if (int rc = geom_of(g, &pg)) return rc;
   RCB_CHECK_ARG(d_w_eff && d_w, "rcb_unfold_poly: null pointer");
-  int64_t total = (int64_t)pg.oc * pg.ic * g->ky * g->kx;
-  unfold_poly_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_w_eff, pg, g->ky, g->kx, d_w);
+  int64_t total = (int64_t)pg.oc * pg.ic * g->kz * g->ky * g->kx;
+  unfold_poly_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_w_eff, pg, g->kz, g->ky, g->kx, d_w);
   RCB_CHECK_LAUNCH("rcb_unfold_poly");
   return 0;
 }
@@ -215,6 +221,7 @@ extern "C" int rcb_unfold_dense(const float* d_m, const rcb_upconv_geom* g, floa
   PolyGeom pg;
   if (int rc = geom_of(g, &pg)) return rc;
   RCB_CHECK_ARG(d_m && d_w, "rcb_unfold_dense: null pointer");
+  RCB_CHECK_ARG(pg.d == 1 && pg.fz == 1 && g->kz == 1, "rcb_unfold_dense: 1-D / 2-D grids only");
   int64_t total = (int64_t)pg.oc * pg.ic * g->ky * g->kx;
   unfold_dense_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_m, pg, g->ky, g->kx, d_w);
   RCB_CHECK_LAUNCH("rcb_unfold_dense");

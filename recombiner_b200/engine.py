@@ -177,8 +177,8 @@ class FitEngine:
         if len(self.dims) != 5 or self.dims[1:4] != [32, 32, 32]:
             raise KernelError(f"unsupported INR {self.dims}: kernels are built for 3 hidden layers of 32")
         self.data_dim = data_dim
-        if data_dim not in (1, 2):
-            raise KernelError("this build covers 1-D and 2-D signals (3-D upsampler is not built yet)")
+        if data_dim not in (1, 2, 3):
+            raise KernelError("signals must be 1-D, 2-D or 3-D")
         self.pixel_sizes = list(pixel_sizes)
         self.pix = int(np.prod(pixel_sizes))
         self.grid = [pixel_sizes[i] // upsample_factors[i] for i in range(data_dim)]       # per-row latent grid
@@ -211,25 +211,28 @@ class FitEngine:
         self.w0 = float(w0)
         if list(paddings) != [2, 1, 1]:
             raise KernelError("upsampler kernels assume 'same' convolutions (paddings [2,1,1])")
-        # stage geometry: (h, w) grids for the three nearest-up + conv stages
-        h, w = (1, self.full_grid[0]) if data_dim == 1 else (self.full_grid[0], self.full_grid[1])
+        # stage geometry: (d, h, w) grids of the three nearest-up + conv stages (leading axes
+        # of lower-dimensional signals are singleton with factor 1 and kernel extent 1)
+        pad = 3 - data_dim
+        grid3 = [1] * pad + list(self.full_grid)
         ks = [5, 3, 3]
         chans = [(latent_dim, 64), (64, 64), (64, 16)]
         self.geoms = []
         for i in range(3):
             f = layer_scales[i]
-            f = list(f) if isinstance(f, (tuple, list)) else [f] * data_dim
-            fy, fx = (1, int(f[0])) if data_dim == 1 else (int(f[0]), int(f[1]))
-            ky = 1 if data_dim == 1 else ks[i]
-            self.geoms.append(UpconvGeom(h, w, fy, fx, ky, ks[i], chans[i][0], chans[i][1]))
-            h, w = h * fy, w * fx
-        if h * w != self.pix_total:
+            f = [int(v) for v in f] if isinstance(f, (tuple, list)) else [int(f)] * data_dim
+            f3 = [1] * pad + f
+            k3 = [1] * pad + [ks[i]] * data_dim
+            self.geoms.append(UpconvGeom(*grid3, *f3, *k3, chans[i][0], chans[i][1]))
+            grid3 = [grid3[j] * f3[j] for j in range(3)]
+        if int(np.prod(grid3)) != self.pix_total or grid3[pad:] != self.full_pixels:
             raise KernelError("upsample factors do not reach the pixel grid")
-        self.dense1 = self.geoms[0].h * self.geoms[0].w <= 16 and not force_poly
-        if data_dim == 1:
-            self.ph, self.pw, self.pitch_y = 1, self.pixel_sizes[0], 0
-        else:
-            self.ph, self.pw, self.pitch_y = self.pixel_sizes[0], self.pixel_sizes[1], self.full_pixels[1]
+        g0 = self.geoms[0]
+        self.dense1 = data_dim < 3 and g0.h * g0.w <= 16 and not force_poly
+        fp = [1] * pad + list(self.full_pixels)
+        pp = [1] * pad + list(self.pixel_sizes)
+        self.ph, self.pw = pp[1], pp[2]
+        self.pitch_y, self.pitch_z = fp[2], fp[1] * fp[2]
         self._ws: Dict = {}
         self._x_cache = None
         self.A = None
@@ -253,14 +256,13 @@ class FitEngine:
         for i, g in enumerate(self.geoms):
             if i == 0 and self.dense1:
                 rows = g.h * g.w * g.ic
-                cols = g.h * g.fy * g.w * g.fx * g.oc
+                cols = g.h * g.fy * g.w * g.fx * g.oc          # dense fold: 1-D / 2-D grids only
                 self.M1 = torch.empty(rows, cols, device=dev)
                 self.M1T = torch.empty(cols, rows, device=dev)
                 check(self.lib.rcb_fold_dense(ptr(conv_w[0]), C.byref(g), ptr(self.M1), ptr(self.M1T), st), "rcb_fold_dense")
                 continue
-            ty = 1 if g.ky == 1 else 2
-            tx = 1 if g.kx == 1 else 2
-            n = g.fy * g.fx * ty * tx * g.ic * g.oc
+            taps = (1 if g.kz == 1 else 2) * (1 if g.ky == 1 else 2) * (1 if g.kx == 1 else 2)
+            n = g.fz * g.fy * g.fx * taps * g.ic * g.oc
             self.w_eff[i] = torch.empty(n, device=dev)
             self.w_eff_t[i] = torch.empty(n, device=dev)
             check(self.lib.rcb_fold_poly(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff[i]), ptr(self.w_eff_t[i]), st), "rcb_fold_poly")
@@ -277,8 +279,8 @@ class FitEngine:
             Lt = self.sp_total * self.latent_dim
             dev = self.device
             g1, g2, g3 = self.geoms
-            n1 = g1.h * g1.fy * g1.w * g1.fx * g1.oc
-            n2 = g2.h * g2.fy * g2.w * g2.fx * g2.oc
+            n1 = g1.d * g1.fz * g1.h * g1.fy * g1.w * g1.fx * g1.oc
+            n2 = g2.d * g2.fz * g2.h * g2.fy * g2.w * g2.fx * g2.oc
             e = lambda *s: torch.empty(*s, device=dev)
             ws = dict(hw=torch.zeros(items, self.ldw, device=dev), wt=torch.zeros(items, self.ldw, device=dev),
                       lpe=e(citems, Lt), a1=e(citems, n1), a2=e(citems, n2), pe=e(citems, self.pix_total, 16),
@@ -388,7 +390,7 @@ class FitEngine:
         a.d_pe, a.d_wt, a.sqerr = ptr(ws["d_pe"]), ptr(ws["d_wt"]), ptr(ws["sqerr"])
         a.x_row_stride = stride
         a.pe_base = ptr(ws["pe_base"])
-        a.pitch_z, a.pitch_y, a.ph, a.pw = 0, self.pitch_y, self.ph, self.pw
+        a.pitch_z, a.pitch_y, a.ph, a.pw = self.pitch_z, self.pitch_y, self.ph, self.pw
         a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
         a.coef, a.w0 = coef, self.w0
         with self.section("mlp_fwd" if mode == 0 else "mlp_fwd_bwd"):
@@ -432,11 +434,11 @@ class FitEngine:
         if not g:
             g["A"] = [torch.zeros(c, _round_up(c, 4), device=dev) for c in self.counts]
             for i, geo in enumerate(self.geoms):
-                kshape = (geo.oc, geo.ic, geo.ky, geo.kx) if self.data_dim == 2 else (geo.oc, geo.ic, geo.kx)
+                kshape = (geo.oc, geo.ic) + (geo.kz, geo.ky, geo.kx)[3 - self.data_dim:]
                 g[f"conv{i + 1}.weight"] = torch.zeros(*kshape, device=dev)
                 g[f"conv{i + 1}.bias"] = torch.zeros(geo.oc, device=dev)
-                ty, tx = (1 if geo.ky == 1 else 2), (1 if geo.kx == 1 else 2)
-                g[f"eff{i}"] = torch.zeros(geo.fy * geo.fx * ty * tx * geo.ic * geo.oc, device=dev)
+                taps = (1 if geo.kz == 1 else 2) * (1 if geo.ky == 1 else 2) * (1 if geo.kx == 1 else 2)
+                g[f"eff{i}"] = torch.zeros(geo.fz * geo.fy * geo.fx * taps * geo.ic * geo.oc, device=dev)
             if self.dense1:
                 g["dM1"] = torch.zeros_like(self.M1)
         with self.section("reparam_wgrad"):
@@ -447,7 +449,7 @@ class FitEngine:
         douts = [ws["d_a1"], ws["d_a2"], ws["d_pe"]]
         with self.section("conv_wgrad"):
             for i, geo in enumerate(self.geoms):
-                out_px = geo.h * geo.fy * geo.w * geo.fx
+                out_px = geo.d * geo.fz * geo.h * geo.fy * geo.w * geo.fx
                 check(self.lib.rcb_colsum(ptr(douts[i]), citems * out_px, geo.oc, geo.oc, ptr(g[f"conv{i + 1}.bias"]), st),
                       "rcb_colsum")
                 if i == 0 and self.dense1:

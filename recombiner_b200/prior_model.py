@@ -119,8 +119,6 @@ class PriorBNNmodel(nn.Module):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise KernelError("recombiner_b200.PriorBNNmodel runs on CUDA (sm_100a) only -- no CPU fallback")
-        if patch and data_dim == 3:
-            raise NotImplementedError("the 3-D (video) upsampler is not wired to the kernels yet")
         self.random_seed, self.device = random_seed, dev
         self.n_layers = len(hidden_dims) + 1
         self.dims = [in_dim] + list(hidden_dims) + [out_dim]

@@ -137,8 +137,6 @@ class TestBNNmodel(nn.Module):
         if dev.type != "cuda":
             raise KernelError("recombiner_b200.TestBNNmodel runs on CUDA (sm_100a) only -- there is no CPU "
                               "fallback; the CPU restatement used for parity lives in oracle/")
-        if patch and data_dim == 3:
-            raise NotImplementedError("the 3-D (video) upsampler is not wired to the kernels yet")
         self.bit_per_group = 16
         self.n_layers = len(hidden_dims) + 1
         self.dims = [in_dim] + list(hidden_dims) + [out_dim]

@@ -171,7 +171,8 @@ def test_tf32_tensor_core_mode_within_stated_tolerance(golden, name, dataset, n_
     assert all(v < 2e-2 for v in rel.values())
 
 
-@pytest.mark.parametrize("name,dataset,n_data,S", [("patch2d", "kodak", 1, 2), ("patch1d", "audio", 2, 2)])
+@pytest.mark.parametrize("name,dataset,n_data,S", [("patch2d", "kodak", 1, 2), ("patch1d", "audio", 2, 2),
+                                                   ("patch3d", "video", 1, 2)])
 def test_patch_modalities_match_reference(golden, name, dataset, n_data, S):
     """Patch modalities: stitched latent grid through the upsampler, three-level hierarchical
     weights with per-patch noise, per-column row permutations (utils.py:60-116,142-191;
@@ -219,7 +220,7 @@ def test_patch_fused_step_and_progressive_coding():
         assert torch.equal(m.decode_posteriors(idx, level=li), lv.sample)
 
 
-@pytest.mark.parametrize("name,dataset,S", [("kodak", "kodak", 1), ("audio", "audio", 2)])
+@pytest.mark.parametrize("name,dataset,S", [("kodak", "kodak", 1), ("audio", "audio", 2), ("video", "video", 1)])
 def test_full_size_patch_modalities_match_oracle(name, dataset, S):
     """BASELINE configs 3 and 4 at their real shapes (kodak: 96 patches of 64x64 stitched to a
     32x48 latent grid -> polyphase first stage; audio: 60 patches of 800 samples): forward,
