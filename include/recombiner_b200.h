@@ -104,6 +104,9 @@ typedef struct {
  * used by the data-gradient kernel. */
 int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_eff, float* w_eff_t,
                   rcb_stream_t stream);
+/* Forward weights in K-major form for the tensor-core path:
+ * w_eff_k[phase][oc][tap*ic + c] (same values as w_eff). */
+int rcb_fold_poly_k(const float* w, const rcb_upconv_geom* g, float* w_eff_k, rcb_stream_t stream);
 /* Dense fold for tiny grids: m[(sy,sx,ic)][(oy,ox,oc)], and its transpose. */
 int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m, float* m_t,
                    rcb_stream_t stream);
@@ -116,6 +119,15 @@ int rcb_upconv_fwd(const float* src, const float* w_eff, const float* bias, floa
 /* d_src = (transpose of the above)(d_out) [* lrelu'(src_act) if src_act != NULL] */
 int rcb_upconv_bwd(const float* d_out, const float* w_eff_t, const float* src_act, float* d_src,
                    const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+
+/* Tensor-core (tcgen05, TF32) variants of rcb_upconv_fwd / rcb_upconv_bwd: implicit GEMM whose
+ * A operand is gathered by 5-D TMA boxes of the channel-last activation tensor (tap shift in
+ * the forward, stride-f traversal in the data gradient; borders = TMA out-of-bounds zero fill).
+ * fwd takes w_eff_k (rcb_fold_poly_k); bwd takes w_eff (rcb_fold_poly).  ic % 32 == 0. */
+int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const float* bias, float* out,
+                      const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
+int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
+                      const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 
 /* Weight gradients of the learned mappings (prior training only; the mappings are
  * frozen at compression time).  Autograd backward of prior_model.py:48-57,173-174.

@@ -67,6 +67,9 @@ SIGNATURES = {
     "rcb_gemm_tc": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],
     "rcb_fold_poly": [P, C.POINTER(UpconvGeom), P, P, P],
     "rcb_fold_dense": [P, C.POINTER(UpconvGeom), P, P, P],
+    "rcb_fold_poly_k": [P, C.POINTER(UpconvGeom), P, P],
+    "rcb_upconv_fwd_tc": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
+    "rcb_upconv_bwd_tc": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_fwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_wgrad": [P, P, P, C.POINTER(UpconvGeom), I32, P],

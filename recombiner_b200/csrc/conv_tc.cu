@@ -1,0 +1,410 @@
+// Tensor-core polyphase up-convolution: TMA-gathered implicit GEMM on tcgen05 (TF32, fp32
+// accumulation in TMEM).  No im2col and no materialised upsampling: each k-block of the
+// A operand is ONE 5-D TMA box of the channel-last activation tensor, shifted by the tap
+// offset (forward) or strided by the upsampling factor (data gradient); image borders are
+// the TMA unit's out-of-bounds zero fill.
+//
+//   forward : out[item, s*f + r, :] = act(bias + sum_{tap,ic} src[item, s + b_r + tap, ic] * w_eff[r][tap][ic][:])
+//             one CTA = 128 source pixels x a group of phases r, one TMEM accumulator per phase
+//   backward: d_src[item, s, :] = lrelu'(.) * sum_{r,tap,oc} d_out[item, (s - b_r - tap)*f + r, oc] * w_eff[r][tap][:][oc]
+//             one CTA = 128 source pixels, K = phases*taps*oc
+// Warp roles as in gemm_tc.cu.  Reference semantics: prior_model.py:47-59.
+#include "gemm_engine.cuh"
+#include "tc_common.cuh"
+
+namespace rcb {
+
+struct ConvTile {
+  int tx, ty, tz, ni;            // box extent in source pixels / items (tx*ty*tz*ni <= 128)
+  int ntx, nty, ntz;             // tiles per axis
+};
+
+struct ConvTcArgs {
+  PolyGeom g;
+  ConvTile t;
+  int items;
+  int phases_per_cta;            // forward: TMEM accumulators per CTA
+  int kblocks;                   // k-blocks per (phase[,tap]) unit
+  int bk;                        // 32 (128B swizzle) or 16 (64B swizzle)
+  int act;
+  const float* bias;             // forward
+  const float* src_act;          // backward (post-activation of the producing stage) or NULL
+  float* out;
+};
+
+constexpr int CT_MAX_PHASES = 16;
+
+struct ConvSmem {
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int B_BYTES = 128 * 128;          // up to 128 rows of 128 B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = TC_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+};
+
+__device__ __forceinline__ void tile_origin(const ConvTcArgs& a, int tile, int& item0, int& z0, int& y0, int& x0) {
+  int t = tile;
+  x0 = (t % a.t.ntx) * a.t.tx; t /= a.t.ntx;
+  y0 = (t % a.t.nty) * a.t.ty; t /= a.t.nty;
+  z0 = (t % a.t.ntz) * a.t.tz; t /= a.t.ntz;
+  item0 = t * a.t.ni;
+}
+// tile row -> (item, z, y, x) of the source pixel; false if outside the tensor
+__device__ __forceinline__ bool tile_row(const ConvTcArgs& a, int r, int item0, int z0, int y0, int x0,
+                                         int& item, int& z, int& y, int& x) {
+  int t = r;
+  x = x0 + t % a.t.tx; t /= a.t.tx;
+  y = y0 + t % a.t.ty; t /= a.t.ty;
+  z = z0 + t % a.t.tz; t /= a.t.tz;
+  item = item0 + t;
+  return t < a.t.ni && item < a.items && z < a.g.d && y < a.g.h && x < a.g.w;
+}
+
+// ------------------------------------------------------------------------------ forward --
+__global__ void __launch_bounds__(TC_THREADS, 1)
+upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcArgs a) {
+  using S = ConvSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* acc_full = empty + TC_STAGES;                 // one per phase handled by this CTA
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + CT_MAX_PHASES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PolyGeom& g = a.g;
+  const int OC = g.oc;
+  int item0, z0, y0, x0;
+  tile_origin(a, blockIdx.x, item0, z0, y0, x0);
+  const int ph0 = blockIdx.y * a.phases_per_cta;
+  const int nph = min(a.phases_per_cta, g.phases() - ph0);
+  const int kb_per_phase = g.taps() * a.kblocks;          // kblocks = ic / 32
+  const uint32_t a_bytes = (uint32_t)(a.t.tx * a.t.ty * a.t.tz * a.t.ni) * 128u;
+  const uint32_t b_bytes = (uint32_t)OC * 128u;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < a.phases_per_cta * OC) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int p = 0; p < CT_MAX_PHASES; ++p) mbar_init(&acc_full[p], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int p = 0; p < nph; ++p) {
+        int rz, ry, rx;
+        g.split_phase(ph0 + p, rz, ry, rx);
+        const int bz = g.base_z(rz), by = g.base_y(ry), bx = g.base_x(rx);
+        for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+          const int tap = kb / a.kblocks, c0 = (kb - tap * a.kblocks) * 32;
+          int tz, ty, tx;
+          g.split_tap(tap, tz, ty, tx);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          mbar_expect_tx(&full[s], a_bytes + b_bytes);
+          tma_load_5d(&tmA, &full[s], a_dst, c0, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
+          tma_load_2d(&tmB, &full[s], a_dst + S::A_BYTES, kb * 32, (ph0 + p) * OC);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(OC);
+      int it = 0;
+      for (int p = 0; p < nph; ++p) {
+        for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait(&full[s], (it / TC_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(a_addr + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[p]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int item, z, y, x;
+    const bool valid = tile_row(a, r, item0, z0, y0, x0, item, z, y, x);
+    const int Ho = g.h * g.fy, Wo = g.w * g.fx, Do = g.d * g.fz;
+    for (int p = 0; p < nph; ++p) {
+      mbar_wait(&acc_full[p], 0);
+      tc_fence_after();
+      int rz, ry, rx;
+      g.split_phase(ph0 + p, rz, ry, rx);
+      float* orow = nullptr;
+      if (valid) {
+        const int oz = z * g.fz + rz, oy = y * g.fy + ry, ox = x * g.fx + rx;
+        orow = a.out + ((((int64_t)item * Do + oz) * Ho + oy) * Wo + ox) * OC;
+      }
+      for (int c0 = 0; c0 < OC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * OC + c0), v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float f = __uint_as_float(v[j + t]) + a.bias[c0 + j + t];
+              o[t] = a.act ? (f > 0.f ? f : 0.01f * f) : f;
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ----------------------------------------------------------------------------- backward --
+template <int BK>   // 32: 128-byte rows / swizzle; 16: 64-byte rows / swizzle (oc = 16)
+__global__ void __launch_bounds__(TC_THREADS, 1)
+upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcArgs a) {
+  using S = ConvSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* acc_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + CT_MAX_PHASES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PolyGeom& g = a.g;
+  const int IC = g.ic;                                     // N of this GEMM
+  int item0, z0, y0, x0;
+  tile_origin(a, blockIdx.x, item0, z0, y0, x0);
+  const int nseg = g.phases() * g.taps();
+  const int nkb = nseg * a.kblocks;                        // kblocks = oc / BK
+  constexpr uint32_t ROW_BYTES = BK * 4;
+  const uint32_t a_bytes = (uint32_t)(a.t.tx * a.t.ty * a.t.tz * a.t.ni) * ROW_BYTES;
+  const uint32_t b_bytes = (uint32_t)IC * ROW_BYTES;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < IC) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&acc_full[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+        const int seg = it / a.kblocks, c0 = (it - seg * a.kblocks) * BK;
+        int tz, ty, tx, rz, ry, rx;
+        g.split_tap(seg % g.taps(), tz, ty, tx);
+        g.split_phase(seg / g.taps(), rz, ry, rx);
+        // output pixel feeding source pixel s through (phase, tap): (s - b - t) * f + r, stride f per source step
+        const int cx = (x0 - g.base_x(rx) - tx) * g.fx + rx;
+        const int cy = (y0 - g.base_y(ry) - ty) * g.fy + ry;
+        const int cz = (z0 - g.base_z(rz) - tz) * g.fz + rz;
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], a_bytes + b_bytes);
+        tma_load_5d(&tmA, &full[s], a_dst, c0, cx, cy, cz, item0);
+        tma_load_2d(&tmB, &full[s], a_dst + S::A_BYTES, c0, seg * IC);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(IC);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait(&full[s], (it / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t da = BK == 32 ? smem_desc_sw128(a_addr) : smem_desc_sw64(a_addr);
+        const uint64_t db = BK == 32 ? smem_desc_sw128(a_addr + S::A_BYTES) : smem_desc_sw64(a_addr + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)
+          umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(&acc_full[0]);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int item, z, y, x;
+    const bool valid = tile_row(a, r, item0, z0, y0, x0, item, z, y, x);
+    mbar_wait(&acc_full[0], 0);
+    tc_fence_after();
+    const int64_t m = valid ? (((int64_t)item * g.d + z) * g.h + y) * g.w + x : 0;
+    float* orow = a.out + m * IC;
+    const float* arow = a.src_act ? a.src_act + m * IC : nullptr;
+    for (int c0 = 0; c0 < IC; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float f = __uint_as_float(v[j + t]);
+            if (arow) f *= (arow[c0 + j + t] > 0.f ? 1.f : 0.01f);
+            o[t] = f;
+          }
+          *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------- host --
+static int make_geom_tc(const rcb_upconv_geom* g, PolyGeom* out) {
+  RCB_CHECK_ARG(g != nullptr, "upconv_tc: null geometry");
+  int pz = (g->kz - 1) / 2, py = (g->ky - 1) / 2, px = (g->kx - 1) / 2;
+  out->d = g->d; out->h = g->h; out->w = g->w; out->fz = g->fz; out->fy = g->fy; out->fx = g->fx;
+  out->pz = pz; out->py = py; out->px = px;
+  out->Tz = pz == 0 ? 1 : 2; out->Ty = py == 0 ? 1 : 2; out->Tx = px == 0 ? 1 : 2;
+  out->ic = g->ic; out->oc = g->oc;
+  return 0;
+}
+
+// 128 source pixels per tile, widest along x; `limit` caps the box extent per axis
+// (strided data-gradient boxes must stay <= 256 elements: extent * factor <= 256)
+static ConvTile choose_tile(const PolyGeom& g, int items, int lim_x, int lim_y, int lim_z) {
+  ConvTile t;
+  auto mn = [](int a, int b) { return a < b ? a : b; };
+  t.tx = mn(mn(g.w, 128), lim_x);
+  t.ty = mn(mn(g.h, 128 / t.tx), lim_y);
+  t.tz = mn(mn(g.d, 128 / (t.tx * t.ty)), lim_z);
+  t.ni = mn(items, 128 / (t.tx * t.ty * t.tz));
+  if (t.ni < 1) t.ni = 1;
+  t.ntx = ceil_div(g.w, t.tx); t.nty = ceil_div(g.h, t.ty); t.ntz = ceil_div(g.d, t.tz);
+  return t;
+}
+
+// 5-D map over a channel-last activation tensor (items, D, H, W, C), optional traversal strides
+static int make_map_5d(CUtensorMap* map, const float* base, int items, int D, int H, int W, int C, const ConvTile& t,
+                       int box_c, int sz, int sy, int sx, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)items};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(t.tx * sx), (cuuint32_t)(t.ty * sy), (cuuint32_t)(t.tz * sz), (cuuint32_t)t.ni};
+  cuuint32_t estr[5] = {1, (cuuint32_t)sx, (cuuint32_t)sy, (cuuint32_t)sz, 1};
+  // a strided box of extent n*s covers exactly n elements only if it does not run past the last one
+  for (int i = 1; i < 4; ++i) box[i] = box[i] - (estr[i] - 1);
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(5d) failed with CUresult %d", (int)r); return -1; }
+  return 0;
+}
+
+static int make_map_b(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, int box_cols,
+                      CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return -1; }
+  return 0;
+}
+
+template <class K>
+static int opt_in_smem(K kernel, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem::TOTAL);
+  if (e != cudaSuccess) { set_error("%s: smem opt-in failed: %s", name, cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+}  // namespace rcb
+
+using namespace rcb;
+
+// w_eff_k: forward weights in K-major form [phase][oc][tap*ic] (rcb_fold_poly_k).
+extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const float* bias, float* out,
+                                 const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(src && w_eff_k && bias && out, "rcb_upconv_fwd_tc: null pointer");
+  RCB_CHECK_ARG(g.ic % 32 == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
+  if (items <= 0) return 0;
+  ConvTcArgs a;
+  a.g = g;
+  a.t = choose_tile(g, items, 128, 128, 128);
+  a.items = items;
+  int ppc = 512 / g.oc;
+  if (ppc > CT_MAX_PHASES) ppc = CT_MAX_PHASES;
+  if (ppc > g.phases()) ppc = g.phases();
+  a.phases_per_cta = ppc;
+  a.kblocks = g.ic / 32;
+  a.bk = 32;
+  a.act = act; a.bias = bias; a.src_act = nullptr; a.out = out;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, a.t, 32, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, 32,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = opt_in_smem(upconv_fwd_tc_kernel, "rcb_upconv_fwd_tc")) return rc;
+  dim3 grid(a.t.ntx * a.t.nty * a.t.ntz * ceil_div(items, a.t.ni), ceil_div(g.phases(), ppc));
+  upconv_fwd_tc_kernel<<<grid, TC_THREADS, ConvSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, a);
+  RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc");
+  return 0;
+}
+
+// w_eff: [phase][tap][ic][oc] as produced by rcb_fold_poly (already K-major for this GEMM).
+extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
+                                 const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(d_out && w_eff && d_src, "rcb_upconv_bwd_tc: null pointer");
+  RCB_CHECK_ARG(g.ic % 16 == 0 && g.ic <= 128 && (g.oc == 16 || g.oc % 32 == 0),
+                "rcb_upconv_bwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
+  if (items <= 0) return 0;
+  ConvTcArgs a;
+  a.g = g;
+  a.t = choose_tile(g, items, 256 / g.fx, 256 / g.fy, 256 / g.fz);
+  a.items = items;
+  a.phases_per_cta = 1;
+  const int bk = (g.oc == 16) ? 16 : 32;
+  a.bk = bk;
+  a.kblocks = g.oc / bk;
+  a.act = 0; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
+  const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_5d(&tmA, d_out, items, g.d * g.fz, g.h * g.fy, g.w * g.fx, g.oc, a.t, bk, g.fz, g.fy, g.fx, swz)) return rc;
+  if (int rc = make_map_b(&tmB, w_eff, (int64_t)g.phases() * g.taps() * g.ic, g.oc, g.ic, bk, swz)) return rc;
+  dim3 grid(a.t.ntx * a.t.nty * a.t.ntz * ceil_div(items, a.t.ni));
+  if (bk == 32) {
+    if (int rc = opt_in_smem(upconv_bwd_tc_kernel<32>, "rcb_upconv_bwd_tc")) return rc;
+    upconv_bwd_tc_kernel<32><<<grid, TC_THREADS, ConvSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, a);
+  } else {
+    if (int rc = opt_in_smem(upconv_bwd_tc_kernel<16>, "rcb_upconv_bwd_tc")) return rc;
+    upconv_bwd_tc_kernel<16><<<grid, TC_THREADS, ConvSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, a);
+  }
+  RCB_CHECK_LAUNCH("rcb_upconv_bwd_tc");
+  return 0;
+}

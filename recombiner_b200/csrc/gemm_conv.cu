@@ -33,7 +33,7 @@ __device__ __forceinline__ int tap_of(int r, int kk, int p, int f) {
 
 // w_eff[phase][tap][ic][oc] (and the [..][oc][ic] transpose)
 __global__ void fold_poly_kernel(const float* __restrict__ w, PolyGeom g, int kz, int ky, int kx,
-                                 float* __restrict__ w_eff, float* __restrict__ w_eff_t) {
+                                 float* __restrict__ w_eff, float* __restrict__ w_eff_t, float* __restrict__ w_eff_k) {
   int64_t total = (int64_t)g.phases() * g.taps() * g.ic * g.oc;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int o = e % g.oc; int64_t r = e / g.oc;
@@ -53,11 +53,12 @@ __global__ void fold_poly_kernel(const float* __restrict__ w, PolyGeom g, int kz
         }
       }
     }
-    w_eff[e] = s;
+    if (w_eff) w_eff[e] = s;
     if (w_eff_t) {
       int64_t seg = (int64_t)ph * g.taps() + tap;
       w_eff_t[(seg * g.oc + o) * g.ic + c] = s;
     }
+    if (w_eff_k) w_eff_k[((int64_t)ph * g.oc + o) * ((int64_t)g.taps() * g.ic) + (int64_t)tap * g.ic + c] = s;
   }
 }
 
@@ -117,8 +118,19 @@ extern "C" int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_
   RCB_CHECK_ARG(w && w_eff, "rcb_fold_poly: null pointer");
   int64_t total = (int64_t)pg.phases() * pg.taps() * pg.ic * pg.oc;
   int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
-  fold_poly_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->kz, g->ky, g->kx, w_eff, w_eff_t);
+  fold_poly_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->kz, g->ky, g->kx, w_eff, w_eff_t, nullptr);
   RCB_CHECK_LAUNCH("rcb_fold_poly");
+  return 0;
+}
+
+extern "C" int rcb_fold_poly_k(const float* w, const rcb_upconv_geom* g, float* w_eff_k, rcb_stream_t stream) {
+  PolyGeom pg;
+  if (int rc = make_geom(g, &pg)) return rc;
+  RCB_CHECK_ARG(w && w_eff_k, "rcb_fold_poly_k: null pointer");
+  int64_t total = (int64_t)pg.phases() * pg.taps() * pg.ic * pg.oc;
+  int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
+  fold_poly_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, pg, g->kz, g->ky, g->kx, nullptr, nullptr, w_eff_k);
+  RCB_CHECK_LAUNCH("rcb_fold_poly_k");
   return 0;
 }
 

@@ -164,6 +164,7 @@ class FitEngine:
         if self.precision not in ("fp32", "tf32"):
             raise KernelError(f"unknown precision {self.precision!r}: 'fp32' (SIMT parity path) or 'tf32' (tcgen05)")
         self.tc = self.precision == "tf32"
+        self.tc_conv = self.tc and os.environ.get("RECOMBINER_TC_CONV", "1") != "0"
         if not torch.cuda.is_available():
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -252,7 +253,7 @@ class FitEngine:
             self.A.append(ap); self.AT.append(at)
         self.conv_b = [up_state[f"conv{i}.bias"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
         conv_w = [up_state[f"conv{i}.weight"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
-        self.w_eff, self.w_eff_t = [None] * 3, [None] * 3
+        self.w_eff, self.w_eff_t, self.w_eff_k = [None] * 3, [None] * 3, [None] * 3
         for i, g in enumerate(self.geoms):
             if i == 0 and self.dense1:
                 rows = g.h * g.w * g.ic
@@ -266,6 +267,9 @@ class FitEngine:
             self.w_eff[i] = torch.empty(n, device=dev)
             self.w_eff_t[i] = torch.empty(n, device=dev)
             check(self.lib.rcb_fold_poly(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff[i]), ptr(self.w_eff_t[i]), st), "rcb_fold_poly")
+            if self.tc_conv:
+                self.w_eff_k[i] = torch.empty(n, device=dev)
+                check(self.lib.rcb_fold_poly_k(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff_k[i]), st), "rcb_fold_poly_k")
 
     # -------------------------------------------------------------- workspaces --
     def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
@@ -347,6 +351,24 @@ class FitEngine:
         check(self.lib.rcb_gemm(pa, lda, pb, ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
               "rcb_gemm")
 
+    def _upconv_fwd(self, i, src, out, citems, act):
+        g = self.geoms[i]
+        if self.tc_conv:
+            check(self.lib.rcb_upconv_fwd_tc(ptr(src), ptr(self.w_eff_k[i]), ptr(self.conv_b[i]), ptr(out), C.byref(g),
+                                             citems, act, stream()), f"rcb_upconv_fwd_tc[{i + 1}]")
+        else:
+            check(self.lib.rcb_upconv_fwd(ptr(src), ptr(self.w_eff[i]), ptr(self.conv_b[i]), ptr(out), C.byref(g),
+                                          citems, act, stream()), f"rcb_upconv_fwd[{i + 1}]")
+
+    def _upconv_bwd(self, i, d_out, src_act, d_src, citems):
+        g = self.geoms[i]
+        if self.tc_conv:
+            check(self.lib.rcb_upconv_bwd_tc(ptr(d_out), ptr(self.w_eff[i]), ptr(src_act), ptr(d_src), C.byref(g), citems,
+                                             stream()), f"rcb_upconv_bwd_tc[{i + 1}]")
+        else:
+            check(self.lib.rcb_upconv_bwd(ptr(d_out), ptr(self.w_eff_t[i]), ptr(src_act), ptr(d_src), C.byref(g), citems,
+                                          stream()), f"rcb_upconv_bwd[{i + 1}]")
+
     def forward_features(self, lv, S: int, noise: Noise):
         """sample -> per-item INR weights (wt) and positional encodings (pe).  `lv` is the
         level-1 state, or [level1, level2, level3] for the patch modalities."""
@@ -372,14 +394,11 @@ class FitEngine:
                 self._gemm(ws["lpe"], 0, Lt, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
                            citems, self.M1.shape[1], Lt, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
             else:
-                check(self.lib.rcb_upconv_fwd(ptr(ws["lpe"]), ptr(self.w_eff[0]), ptr(self.conv_b[0]), ptr(ws["a1"]),
-                                              C.byref(g1), citems, 1, st), "rcb_upconv_fwd[1]")
+                self._upconv_fwd(0, ws["lpe"], ws["a1"], citems, 1)
         with self.section("conv2_fwd"):
-            check(self.lib.rcb_upconv_fwd(ptr(ws["a1"]), ptr(self.w_eff[1]), ptr(self.conv_b[1]), ptr(ws["a2"]),
-                                          C.byref(g2), citems, 1, st), "rcb_upconv_fwd[2]")
+            self._upconv_fwd(1, ws["a1"], ws["a2"], citems, 1)
         with self.section("conv3_fwd"):
-            check(self.lib.rcb_upconv_fwd(ptr(ws["a2"]), ptr(self.w_eff[2]), ptr(self.conv_b[2]), ptr(ws["pe"]),
-                                          C.byref(g3), citems, 0, st), "rcb_upconv_fwd[3]")
+            self._upconv_fwd(2, ws["a2"], ws["pe"], citems, 0)
         return ws
 
     def mlp(self, ws, rows: int, S: int, x, mode: int, y=None, dy=None, coef: float = 0.0):
@@ -404,19 +423,16 @@ class FitEngine:
         st = stream()
         g1, g2, g3 = self.geoms
         with self.section("conv3_bwd"):
-            check(self.lib.rcb_upconv_bwd(ptr(ws["d_pe"]), ptr(self.w_eff_t[2]), ptr(ws["a2"]), ptr(ws["d_a2"]),
-                                          C.byref(g3), citems, st), "rcb_upconv_bwd[3]")
+            self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
         with self.section("conv2_bwd"):
-            check(self.lib.rcb_upconv_bwd(ptr(ws["d_a2"]), ptr(self.w_eff_t[1]), ptr(ws["a1"]), ptr(ws["d_a1"]),
-                                          C.byref(g2), citems, st), "rcb_upconv_bwd[2]")
+            self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
         with self.section("conv1_bwd"):
             if self.dense1:
                 Lt = self.M1.shape[0]
                 self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, Lt,
                            citems, Lt, self.M1T.shape[0], Bt=self.M1)
             else:
-                check(self.lib.rcb_upconv_bwd(ptr(ws["d_a1"]), ptr(self.w_eff_t[0]), None, ptr(ws["d_lpe"]),
-                                              C.byref(g1), citems, st), "rcb_upconv_bwd[1]")
+                self._upconv_bwd(0, ws["d_a1"], None, ws["d_lpe"], citems)
         with self.section("reparam_bwd"):
             for l, c in enumerate(self.counts):
                 self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],

@@ -1,0 +1,62 @@
+"""Tensor-core (tcgen05 + 5-D TMA gather) polyphase up-convolutions against the fp32 SIMT
+engine on the same inputs and folded weights.  TF32 operands: stated tolerance 2e-3 of
+|a|.|b| per output (10-bit mantissas), forward and data gradient; 1-D, 2-D and 3-D grids,
+ragged tiles, the 64-byte-swizzle path (oc = 16) and the multi-CTA phase split (16 phases)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = {
+    # name: (d, h, w, fz, fy, fx, kz, ky, kx, ic, oc, items)
+    "cifar_conv2": (1, 8, 8, 1, 2, 2, 1, 3, 3, 64, 64, 7),
+    "cifar_conv3": (1, 16, 16, 1, 2, 2, 1, 3, 3, 64, 16, 5),
+    "conv1_poly_2d": (1, 6, 10, 1, 4, 4, 1, 5, 5, 128, 64, 3),
+    "protein_conv2": (1, 1, 24, 1, 1, 2, 1, 1, 3, 64, 64, 11),
+    "audio_conv3_ragged": (1, 1, 300, 1, 1, 2, 1, 1, 3, 64, 16, 2),
+    "wide_2d_ragged": (1, 5, 200, 1, 2, 2, 1, 3, 3, 64, 64, 1),
+    "video_conv2_3d": (3, 4, 4, 2, 2, 2, 3, 3, 3, 64, 64, 4),
+    "video_conv1_3d": (1, 2, 2, 6, 4, 4, 5, 5, 5, 128, 64, 2),
+}
+
+
+@pytest.mark.parametrize("name", list(GEOMS))
+def test_upconv_tc_matches_simt(name):
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    d, h, w, fz, fy, fx, kz, ky, kx, ic, oc, items = GEOMS[name]
+    geo = UpconvGeom(d, h, w, fz, fy, fx, kz, ky, kx, ic, oc)
+    gen = torch.Generator().manual_seed(len(name))
+    wt = (torch.randn(oc, ic, kz, ky, kx, generator=gen) / np.sqrt(ic * kz * ky * kx)).cuda()
+    bias = torch.randn(oc, generator=gen).cuda()
+    src = torch.randn(items, d, h, w, ic, generator=gen).cuda()
+    taps = (1 if kz == 1 else 2) * (1 if ky == 1 else 2) * (1 if kx == 1 else 2)
+    n = fz * fy * fx * taps * ic * oc
+    w_eff, w_eff_t, w_eff_k = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_k(ptr(wt), C.byref(geo), ptr(w_eff_k), stream()))
+    out_shape = (items, d * fz, h * fy, w * fx, oc)
+    ref = torch.zeros(out_shape, device="cuda")
+    got = torch.full(out_shape, 3.0, device="cuda")
+    check(lib.rcb_upconv_fwd(ptr(src), ptr(w_eff), ptr(bias), ptr(ref), C.byref(geo), items, 1, stream()))
+    check(lib.rcb_upconv_fwd_tc(ptr(src), ptr(w_eff_k), ptr(bias), ptr(got), C.byref(geo), items, 1, stream()))
+    torch.cuda.synchronize()
+    scale = float(src.norm(dim=-1).max()) * float(wt.flatten(1).norm(dim=1).max())
+    err = float((got - ref).abs().max())
+    assert err < 2e-3 * scale, (err, scale)
+    # data gradient (with the LeakyReLU mask of the producing stage)
+    d_out = torch.randn(out_shape, generator=gen).cuda()
+    act = torch.randn(items, d, h, w, ic, generator=gen).cuda()
+    ref_b = torch.zeros_like(src)
+    got_b = torch.full_like(src, 3.0)
+    check(lib.rcb_upconv_bwd(ptr(d_out), ptr(w_eff_t), ptr(act), ptr(ref_b), C.byref(geo), items, stream()))
+    check(lib.rcb_upconv_bwd_tc(ptr(d_out), ptr(w_eff), ptr(act), ptr(got_b), C.byref(geo), items, stream()))
+    torch.cuda.synchronize()
+    scale_b = float(d_out.norm(dim=-1).max()) * float(wt.norm()) / np.sqrt(ic) * 4
+    err_b = float((got_b - ref_b).abs().max())
+    assert err_b < 2e-3 * scale_b, (err_b, scale_b)
+    print(f"[conv_tc {name}] fwd err {err:.2e} (scale {scale:.2f}); bwd err {err_b:.2e} (scale {scale_b:.2f})")
