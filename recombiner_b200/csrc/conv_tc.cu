@@ -27,6 +27,7 @@ struct ConvTcArgs {
   int kblocks;                   // k-blocks per (phase[,tap]) unit
   int bk;                        // 32 (128B swizzle) or 16 (64B swizzle)
   int act;
+  int b_off, stage_bytes, bar_off;   // shared-memory layout (bytes): B tile offset in a stage, stage size, barriers
   const float* bias;             // forward
   const float* src_act;          // backward (post-activation of the producing stage) or NULL
   float* out;
@@ -34,13 +35,16 @@ struct ConvTcArgs {
 
 constexpr int CT_MAX_PHASES = 16;
 
-struct ConvSmem {
-  static constexpr int A_BYTES = TC_BM * 128;
-  static constexpr int B_BYTES = 128 * 128;          // up to 128 rows of 128 B
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = TC_STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
-};
+// stage = [A tile: 128 rows x row_bytes][B tile: n rows x row_bytes], both 1024-B aligned; sized per
+// problem so that several CTAs fit on an SM (their prologues/epilogues overlap the others' main loops)
+static void smem_layout(ConvTcArgs* a, int row_bytes, int b_rows, int* total) {
+  int a_bytes = (TC_BM * row_bytes + 1023) / 1024 * 1024;
+  int b_bytes = (b_rows * row_bytes + 1023) / 1024 * 1024;
+  a->b_off = a_bytes;
+  a->stage_bytes = a_bytes + b_bytes;
+  a->bar_off = TC_STAGES * a->stage_bytes;
+  *total = a->bar_off + 512 + 1024;
+}
 
 __device__ __forceinline__ void tile_origin(const ConvTcArgs& a, int tile, int& item0, int& z0, int& y0, int& x0) {
   int t = tile;
@@ -61,12 +65,11 @@ __device__ __forceinline__ bool tile_row(const ConvTcArgs& a, int r, int item0, 
 }
 
 // ------------------------------------------------------------------------------ forward --
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS)
 upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcArgs a) {
-  using S = ConvSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* full = (uint64_t*)(smem + a.bar_off);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* acc_full = empty + TC_STAGES;                 // one per phase handled by this CTA
   uint32_t* tmem_slot = (uint32_t*)(acc_full + CT_MAX_PHASES);
@@ -108,10 +111,10 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int tap = kb / a.kblocks, c0 = (kb - tap * a.kblocks) * 32;
           int tz, ty, tx;
           g.split_tap(tap, tz, ty, tx);
-          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* a_dst = smem + s * a.stage_bytes;
           mbar_expect_tx(&full[s], a_bytes + b_bytes);
           tma_load_5d(&tmA, &full[s], a_dst, c0, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
-          tma_load_2d(&tmB, &full[s], a_dst + S::A_BYTES, kb * 32, (ph0 + p) * OC);
+          tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * 32, (ph0 + p) * OC);
         }
       }
     }
@@ -124,8 +127,8 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int s = it % TC_STAGES;
           mbar_wait(&full[s], (it / TC_STAGES) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(a_addr + S::A_BYTES);
+          const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
+          const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(a_addr + a.b_off);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_tf32(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
@@ -175,12 +178,11 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 // ----------------------------------------------------------------------------- backward --
 template <int BK>   // 32: 128-byte rows / swizzle; 16: 64-byte rows / swizzle (oc = 16)
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS)
 upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcArgs a) {
-  using S = ConvSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* full = (uint64_t*)(smem + a.bar_off);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* acc_full = empty + TC_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(acc_full + CT_MAX_PHASES);
@@ -222,10 +224,10 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int cx = (x0 - g.base_x(rx) - tx) * g.fx + rx;
         const int cy = (y0 - g.base_y(ry) - ty) * g.fy + ry;
         const int cz = (z0 - g.base_z(rz) - tz) * g.fz + rz;
-        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        uint8_t* a_dst = smem + s * a.stage_bytes;
         mbar_expect_tx(&full[s], a_bytes + b_bytes);
         tma_load_5d(&tmA, &full[s], a_dst, c0, cx, cy, cz, item0);
-        tma_load_2d(&tmB, &full[s], a_dst + S::A_BYTES, c0, seg * IC);
+        tma_load_2d(&tmB, &full[s], a_dst + a.b_off, c0, seg * IC);
       }
     }
   } else if (warp == 1) {
@@ -235,9 +237,9 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int s = it % TC_STAGES;
         mbar_wait(&full[s], (it / TC_STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
         const uint64_t da = BK == 32 ? smem_desc_sw128(a_addr) : smem_desc_sw64(a_addr);
-        const uint64_t db = BK == 32 ? smem_desc_sw128(a_addr + S::A_BYTES) : smem_desc_sw64(a_addr + S::A_BYTES);
+        const uint64_t db = BK == 32 ? smem_desc_sw128(a_addr + a.b_off) : smem_desc_sw64(a_addr + a.b_off);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k)
           umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
@@ -336,7 +338,7 @@ static int make_map_b(CUtensorMap* map, const float* base, int64_t rows, int64_t
 
 template <class K>
 static int opt_in_smem(K kernel, const char* name) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem::TOTAL);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) { set_error("%s: smem opt-in failed: %s", name, cudaGetErrorString(e)); return -1; }
   return 0;
 }
@@ -364,13 +366,15 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   a.kblocks = g.ic / 32;
   a.bk = 32;
   a.act = act; a.bias = bias; a.src_act = nullptr; a.out = out;
+  int smem_total;
+  smem_layout(&a, 128, g.oc, &smem_total);
   CUtensorMap tmA, tmB;
   if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, a.t, 32, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = opt_in_smem(upconv_fwd_tc_kernel, "rcb_upconv_fwd_tc")) return rc;
   dim3 grid(a.t.ntx * a.t.nty * a.t.ntz * ceil_div(items, a.t.ni), ceil_div(g.phases(), ppc));
-  upconv_fwd_tc_kernel<<<grid, TC_THREADS, ConvSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, a);
+  upconv_fwd_tc_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, a);
   RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc");
   return 0;
 }
@@ -393,6 +397,8 @@ extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const f
   a.bk = bk;
   a.kblocks = g.oc / bk;
   a.act = 0; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
+  int smem_total;
+  smem_layout(&a, bk * 4, g.ic, &smem_total);
   const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmA, tmB;
   if (int rc = make_map_5d(&tmA, d_out, items, g.d * g.fz, g.h * g.fy, g.w * g.fx, g.oc, a.t, bk, g.fz, g.fy, g.fx, swz)) return rc;
@@ -400,10 +406,10 @@ extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const f
   dim3 grid(a.t.ntx * a.t.nty * a.t.ntz * ceil_div(items, a.t.ni));
   if (bk == 32) {
     if (int rc = opt_in_smem(upconv_bwd_tc_kernel<32>, "rcb_upconv_bwd_tc")) return rc;
-    upconv_bwd_tc_kernel<32><<<grid, TC_THREADS, ConvSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, a);
+    upconv_bwd_tc_kernel<32><<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, a);
   } else {
     if (int rc = opt_in_smem(upconv_bwd_tc_kernel<16>, "rcb_upconv_bwd_tc")) return rc;
-    upconv_bwd_tc_kernel<16><<<grid, TC_THREADS, ConvSmem::TOTAL, (cudaStream_t)stream>>>(tmA, tmB, a);
+    upconv_bwd_tc_kernel<16><<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, a);
   }
   RCB_CHECK_LAUNCH("rcb_upconv_bwd_tc");
   return 0;
