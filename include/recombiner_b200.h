@@ -164,6 +164,11 @@ typedef struct {
   float coef, w0;
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
+/* Same contract on tcgen05: every 128-pixel contraction (three sine layers, their data
+ * gradients, and all four weight gradients as one MN-major 128x128 GEMM kept in TMEM over
+ * the item's tiles) is a TF32 tensor-core MMA; activations are chained TMEM -> registers
+ * (sin/cos) -> swizzled shared memory -> next MMA.  32 input features only (n_f = 16). */
+int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream);
 
 /* Gradient reduction over MC samples + beta-weighted closed-form KL gradient
  * (+ fused Adam).  Replaces the autograd backward of test_model.py:289-303,

@@ -165,6 +165,7 @@ class FitEngine:
             raise KernelError(f"unknown precision {self.precision!r}: 'fp32' (SIMT parity path) or 'tf32' (tcgen05)")
         self.tc = self.precision == "tf32"
         self.tc_conv = self.tc and os.environ.get("RECOMBINER_TC_CONV", "1") != "0"
+        self.tc_mlp = self.tc and os.environ.get("RECOMBINER_TC_MLP", "1") != "0"
         if not torch.cuda.is_available():
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -413,7 +414,10 @@ class FitEngine:
         a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
         a.coef, a.w0 = coef, self.w0
         with self.section("mlp_fwd" if mode == 0 else "mlp_fwd_bwd"):
-            check(self.lib.rcb_mlp(C.byref(a), stream()), "rcb_mlp")
+            if self.tc_mlp and self.n_f == 16:
+                check(self.lib.rcb_mlp_tc(C.byref(a), stream()), "rcb_mlp_tc")
+            else:
+                check(self.lib.rcb_mlp(C.byref(a), stream()), "rcb_mlp")
 
     # ----------------------------------------------------------------- backward --
     def backward_features(self, ws, rows: int, S: int):

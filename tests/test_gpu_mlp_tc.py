@@ -1,0 +1,65 @@
+"""Tensor-core fused SIREN MLP (rcb_mlp_tc) against the fp32 SIMT kernel (rcb_mlp) on the same
+inputs: prediction, squared error, d pe and all weight/bias gradients.  TF32 operands
+(round-to-nearest on store) through sin(30 z): stated tolerance 3e-2 * max|reference| per
+tensor, 1e-3 relative on the summed squared error."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(lib_args, items, S, pix, out, ld_w, mode, t, coef=0.0):
+    from recombiner_b200._lib import ptr
+    a = lib_args()
+    a.wt, a.xt, a.pe = ptr(t["wt"]), ptr(t["xt"]), ptr(t["pe"])
+    a.y, a.dy, a.y_pred = ptr(t["y"]), ptr(t["dy"]), ptr(t["y_pred"])
+    a.d_pe, a.d_wt, a.sqerr = ptr(t["d_pe"]), ptr(t["d_wt"]), ptr(t["sqerr"])
+    a.pe_base = None
+    a.x_row_stride, a.pitch_z, a.pitch_y = 0, 0, 0
+    a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = items, S, pix, 16, out, ld_w, mode
+    a.ph, a.pw = 1, pix
+    a.coef, a.w0 = coef, 30.0
+    return a
+
+
+@pytest.mark.parametrize("pix,out,rows,S,wscale", [(1024, 3, 3, 2, 0.05), (96, 3, 5, 1, 0.1), (800, 1, 2, 3, 0.05),
+                                                   (128, 3, 1, 1, 0.02)])
+def test_mlp_tc_matches_simt(pix, out, rows, S, wscale):
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import MlpArgs, check, stream
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(pix + out)
+    items = rows * S
+    n_w = 3 * 1056 + out * 33
+    ld_w = (n_w + 3) // 4 * 4
+    base = dict(wt=torch.zeros(items, ld_w), xt=torch.rand(16, pix, generator=g) * 2 - 1,
+                pe=torch.randn(items, pix, 16, generator=g) * 0.5, y=torch.rand(rows, pix, out, generator=g),
+                dy=torch.randn(items, pix, out, generator=g) * 1e-3)
+    base["wt"][:, :n_w] = torch.randn(items, n_w, generator=g) * wscale
+    res = {}
+    for name, fn in (("simt", lib.rcb_mlp), ("tc", lib.rcb_mlp_tc)):
+        for mode in (0, 1, 2):
+            t = {k: v.cuda().contiguous() for k, v in base.items()}
+            t.update(y_pred=torch.zeros(items, pix, out, device="cuda"), d_pe=torch.zeros(items, pix, 16, device="cuda"),
+                     d_wt=torch.zeros(items, ld_w, device="cuda"), sqerr=torch.zeros(items, device="cuda"))
+            a = _args(MlpArgs, items, S, pix, out, ld_w, mode, t, coef=2.0 / (S * pix * out))
+            check(fn(C.byref(a), stream()), name)
+            torch.cuda.synchronize()
+            res[(name, mode)] = {k: t[k].cpu().numpy() for k in ("y_pred", "d_pe", "d_wt", "sqerr")}
+
+    def close(key, mode, tol=3e-2):
+        ref, got = res[("simt", mode)][key], res[("tc", mode)][key]
+        err = np.abs(got - ref).max()
+        scale = np.abs(ref).max()
+        print(f"[mlp_tc pix={pix} out={out} mode={mode}] {key}: max err {err:.3e} (max |ref| {scale:.3e})")
+        assert err <= tol * scale + 1e-12, (key, mode, err, scale)
+
+    close("y_pred", 0)
+    for mode in (1, 2):
+        close("d_pe", mode)
+        close("d_wt", mode)
+    ref, got = res[("simt", 1)]["sqerr"], res[("tc", 1)]["sqerr"]
+    np.testing.assert_allclose(got, ref, rtol=2e-3)
