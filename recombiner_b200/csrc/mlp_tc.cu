@@ -8,9 +8,11 @@
 //   X0 -> [X0 W0] -> sin -> X1 -> [X1 W1] -> sin -> X2 -> [X2 W2] -> sin -> X3 -> y (CUDA cores, 32->out)
 //   dy -> dZ2 -> [dZ2 W2^T] -> dZ1 -> [dZ1 W1^T] -> dZ0 -> [dZ0 W0pe^T] -> d pe
 //   [X0|X1|X2|X3]^T [dZ0|dZ1|dZ2|dy]  -> all four weight gradients in ONE 128x128 accumulator that
-//   stays in TMEM over the item's tiles (the px-major tiles are read as MN-major operands).
-// Activation tiles are [128 px][32 features] fp32, 128-byte rows, 128B-swizzled exactly as
-// a TMA box would write them (written here from registers; fence.proxy.async before the MMA).
+//   stays in TMEM over the item's tiles.  (TF32 MN-major operands would need the 32B-base
+//   swizzle, incompatible with the K-major tiles of the chain, so the epilogues also write a
+//   feature-major copy [feature][pixel] of every activation / gradient tile for this GEMM.)
+// Chain tiles are [128 px][32 features] fp32, 128-byte rows, 128B-swizzled exactly as a TMA
+// box would write them (written here from registers; fence.proxy.async before the MMA).
 // Reference semantics: test_model.py:347-355, 624-627; weight layout :269-280.
 #include <type_traits>
 
@@ -38,26 +40,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// MN-major operand: rows = K (pixels), 128-byte rows hold 32 consecutive M/N values; atoms of 32
-// values are `lbo_bytes` apart, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 struct MtSmem {
-  // tiles (1024-B aligned): X0..X3 contiguous, then DZ0, DZ1, DZ2, DY contiguous
-  static constexpr int X = 0;
-  static constexpr int DZ = 4 * TILE_BYTES;
-  static constexpr int WF = 8 * TILE_BYTES;                 // 3 forward weight tiles  [j][i]
+  // all tiles 1024-B aligned
+  static constexpr int XA = 0;                              // px-major activation tile (A of the layer GEMMs)
+  static constexpr int DZA = TILE_BYTES;                    // px-major gradient tile (A of the data-gradient GEMMs)
+  static constexpr int TA = 2 * TILE_BYTES;                 // feature-major [4 px-blocks][128 = 4 layers x 32][32 px]
+  static constexpr int TB = 6 * TILE_BYTES;                 // same for [dZ0 | dZ1 | dZ2 | dy]
+  static constexpr int WF = 10 * TILE_BYTES;                // 3 forward weight tiles  [j][i]
   static constexpr int WB = WF + 3 * WTILE_BYTES;           // 3 backward weight tiles [i][j] (layer 0: 16 pe rows)
-  static constexpr int PLAIN = WB + 3 * WTILE_BYTES;        // biases (3*32 + 4) and W3 (32*4) as plain floats
-  static constexpr int BAR = PLAIN + 1024;
+  static constexpr int PLAIN = WB + 3 * WTILE_BYTES;        // biases (3*32 + 4), W3 (32*4), dy exchange (128*4)
+  static constexpr int BAR = PLAIN + 1024 + 2048;
   static constexpr int TOTAL = BAR + 128 + 1024;
 };
 
@@ -102,8 +94,11 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
     for (int e = t; e < 3 * HID; e += MT_EPI) plain[e] = wt_g[(e / HID == 0 ? off0 : (e / HID == 1 ? off1 : off2)) + e % HID];
     if (t < OUT) plain[96 + t] = wt_g[off3 + t];
     for (int e = t; e < HID * 4; e += MT_EPI) plain[128 + e] = (e % 4 < OUT) ? wt_g[off3 + OUT + (e / 4) * OUT + e % 4] : 0.f;
-    // DY tile: columns >= OUT stay zero for the whole kernel
-    for (int e = t; e < TILE_BYTES / 16; e += MT_EPI) ((float4*)(smem + MtSmem::DZ + 3 * TILE_BYTES))[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // rows 96..127 of the feature-major gradient tiles hold dy (OUT rows) and zeros
+    for (int e = t; e < 4 * 32 * 32; e += MT_EPI) {
+      const int kb = e / 1024, rr = 96 + (e / 32) % 32, c = e % 32;
+      *(float*)(smem + MtSmem::TB + kb * TILE_BYTES + swz(rr, c)) = 0.f;
+    }
   }
   fence_async_smem();
   tc_fence_before();
@@ -117,8 +112,9 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
       const uint32_t id32 = idesc_tf32(32), id16 = idesc_tf32(16);
-      const uint32_t id_dw = idesc_tf32(128) | (1u << 15) | (1u << 16);        // both operands MN-major
-      const uint32_t sX = smem_u32(smem + MtSmem::X), sDZ = smem_u32(smem + MtSmem::DZ);
+      const uint32_t id_dw = idesc_tf32(128);
+      const uint32_t sX = smem_u32(smem + MtSmem::XA), sDZ = smem_u32(smem + MtSmem::DZA);
+      const uint32_t sTA = smem_u32(smem + MtSmem::TA), sTB = smem_u32(smem + MtSmem::TB);
       const uint32_t sWF = smem_u32(smem + MtSmem::WF), sWB = smem_u32(smem + MtSmem::WB);
       uint32_t ph = 0;
       auto gemm = [&](uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
@@ -130,21 +126,24 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
       };
       for (int tile = 0; tile < ntiles; ++tile) {
         for (int l = 0; l < 3; ++l) {
-          gemm(sX + l * TILE_BYTES, sWF + l * WTILE_BYTES, id32);
+          gemm(sX, sWF + l * WTILE_BYTES, id32);
           umma_commit(bar_mma);
         }
         if (MODE != 0) {
-          gemm(sDZ + 2 * TILE_BYTES, sWB + 2 * WTILE_BYTES, id32);   // dX2 = dZ2 W2^T
+          gemm(sDZ, sWB + 2 * WTILE_BYTES, id32);                    // dX2 = dZ2 W2^T
           umma_commit(bar_mma);
-          gemm(sDZ + 1 * TILE_BYTES, sWB + 1 * WTILE_BYTES, id32);   // dX1 = dZ1 W1^T
+          gemm(sDZ, sWB + 1 * WTILE_BYTES, id32);                    // dX1 = dZ1 W1^T
           umma_commit(bar_mma);
           gemm(sDZ, sWB, id16);                                      // d pe = dZ0 W0[pe rows]^T
           umma_commit(bar_mma);
-          // weight gradients of all layers: K = 128 pixels, 8 per instruction (one 1024-B row group)
-          const uint64_t da = smem_desc_mn_sw128(sX, TILE_BYTES), db = smem_desc_mn_sw128(sDZ, TILE_BYTES);
+          // weight gradients of all layers: [4 x 32 features] x [128 gradient columns], K = 128 pixels
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_tf32(tm_dw, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), id_dw, (tile | k) ? 1u : 0u);
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t da = smem_desc_sw128(sTA + kb * TILE_BYTES), db = smem_desc_sw128(sTB + kb * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tm_dw, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), id_dw, (tile | kb | k) ? 1u : 0u);
+          }
           umma_commit(bar_dw);
         }
       }
@@ -178,11 +177,22 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
     for (int k = 0; k < OUT; ++k) gb3[k] = 0.f;
     float sq = 0.f;
 
-    // write this thread's 16 values of row r into a px-major swizzled tile
-    auto store16 = [&](uint8_t* tile, const float (&v)[16]) {
+    float* dy_x = plain + 256;              // [128 rows][4]: dy exchange between the two halves of a row
+    // this thread's 16 values of pixel row r: px-major chain tile (optional) + feature-major copy
+    auto store16 = [&](uint8_t* chain_tile, uint8_t* t_tiles, int feat_base, const float (&v)[16]) {
+      float w[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *(float4*)(tile + swz(r, j0 + c * 4)) = make_float4(to_tf32(v[c * 4]), to_tf32(v[c * 4 + 1]), to_tf32(v[c * 4 + 2]), to_tf32(v[c * 4 + 3]));
+      for (int j = 0; j < 16; ++j) w[j] = to_tf32(v[j]);
+      if (chain_tile) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *(float4*)(chain_tile + swz(r, j0 + c * 4)) = make_float4(w[c * 4], w[c * 4 + 1], w[c * 4 + 2], w[c * 4 + 3]);
+      }
+      if (MODE != 0) {
+        uint8_t* blk = t_tiles + (r >> 5) * TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) *(float*)(blk + swz(feat_base + j0 + j, r & 31)) = w[j];
+      }
     };
 
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
             v[c * 4] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
           }
         }
-        store16(smem + MtSmem::X, v);
+        store16(smem + MtSmem::XA, smem + MtSmem::TA, 0, v);
       }
       fence_async_smem();
       mbar_arrive(bar_ready);
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
           x[j] = s;
           cs[l][j] = w0 * c;
         }
-        store16(smem + MtSmem::X + (l + 1) * TILE_BYTES, x);
+        store16(smem + MtSmem::XA, smem + MtSmem::TA, (l + 1) * 32, x);
         tc_fence_before();
         if (l < 2) { fence_async_smem(); mbar_arrive(bar_ready); }
       }
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
         for (int k = 0; k < OUT; ++k) o[k] = plain[96 + k];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4 xv = *(const float4*)(smem + MtSmem::X + 3 * TILE_BYTES + swz(r, c * 4));
+          float4 xv = *(const float4*)(smem + MtSmem::XA + swz(r, c * 4));
           const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t)
@@ -261,15 +271,17 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
             }
             gb3[k] += dyv[k];
           }
-          *(float4*)(smem + MtSmem::DZ + 3 * TILE_BYTES + swz(r, 0)) =
-              make_float4(to_tf32(dyv[0]), to_tf32(dyv[1]), to_tf32(dyv[2]), to_tf32(dyv[3]));
+          *(float4*)(dy_x + r * 4) = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
+#pragma unroll
+          for (int k = 0; k < OUT; ++k)
+            *(float*)(smem + MtSmem::TB + (r >> 5) * TILE_BYTES + swz(96 + k, r & 31)) = to_tf32(dyv[k]);
         }
       }
+      epi_sync();                            // dy visible to the partner half; X3 reads done before XA is reused
       if (MODE == 0) continue;
-      epi_sync();                            // dy visible to the partner half
       // ---- dZ2 = (dy W3^T) * 30 cos
       {
-        float4 d4 = *(const float4*)(smem + MtSmem::DZ + 3 * TILE_BYTES + swz(r, 0));
+        float4 d4 = *(const float4*)(dy_x + r * 4);
         const float dyv[4] = {d4.x, d4.y, d4.z, d4.w};
         float dz[16];
 #pragma unroll
@@ -280,7 +292,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
           dz[j] = v * cs[2][j];
           gb[2][j] += dz[j];
         }
-        store16(smem + MtSmem::DZ + 2 * TILE_BYTES, dz);
+        store16(smem + MtSmem::DZA, smem + MtSmem::TB, 2 * 32, dz);
       }
       fence_async_smem();
       mbar_arrive(bar_ready);
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
           dz[j] = __uint_as_float(acc[j]) * cs[l][j];
           gb[l][j] += dz[j];
         }
-        store16(smem + MtSmem::DZ + l * TILE_BYTES, dz);
+        store16(smem + MtSmem::DZA, smem + MtSmem::TB, l * 32, dz);
         tc_fence_before();
         fence_async_smem();
         mbar_arrive(bar_ready);
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mlp_tc_kernel(rcb_mlp_args a) {
         }
       }
       // ---- bias gradients: reduce the per-row partial sums over the 128 rows (4 warps per half)
-      float* scratch = (float*)(smem + MtSmem::X);       // tiles are dead now: [8 warps][64]
+      float* scratch = (float*)(smem + MtSmem::XA);      // tiles are dead now: [8 warps][64]
       epi_sync();
 #pragma unroll
       for (int l = 0; l < 3; ++l)

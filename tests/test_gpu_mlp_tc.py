@@ -25,8 +25,10 @@ def _args(lib_args, items, S, pix, out, ld_w, mode, t, coef=0.0):
     return a
 
 
-@pytest.mark.parametrize("pix,out,rows,S,wscale", [(1024, 3, 3, 2, 0.05), (96, 3, 5, 1, 0.1), (800, 1, 2, 3, 0.05),
-                                                   (128, 3, 1, 1, 0.02)])
+# weight scale: SIREN initialisation sqrt(6/32)/30 = 0.0144 (prior_model.py:101), i.e. 30*W keeps
+# unit gain per layer; larger weights make the network chaotic and amplify ANY rounding
+@pytest.mark.parametrize("pix,out,rows,S,wscale", [(1024, 3, 3, 2, 0.015), (96, 3, 5, 1, 0.02), (800, 1, 2, 3, 0.015),
+                                                   (128, 3, 1, 1, 0.01)])
 def test_mlp_tc_matches_simt(pix, out, rows, S, wscale):
     from recombiner_b200 import _lib
     from recombiner_b200._lib import MlpArgs, check, stream
