@@ -46,6 +46,11 @@ TOTAL_BITS = 532.0          # -> G = 33..34 blocks, 0.52 bpp on 1024 pixels
 N_CAND = 65536
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+# captures (profiles/README.md); None where no capture exists yet
+TRAFFIC = {}
+
+
 def schedule(G: int):
     return 30000 + G * max(30000 // G, 50)
 
@@ -338,10 +343,13 @@ def run_b200(args):
         line = {
             "metric": "datapoints compressed/sec (CIFAR-10 32x32)", "value": value, "unit": "datapoints/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": t_fit, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 fit (SIMT FFMA) / f64 REC", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("tf32 (tcgen05, fp32 accumulate) fit / f64 REC" if m.engine.tc else "f32 fit (SIMT FFMA) / f64 REC"),
+            "data": "synthetic",
             "config": {"workload": "cifar-shape 32x32, %d rows/GPU, S=5, G=%d blocks x 16 bit (0.52 bpp), "
                                    "random-init prior" % (ROWS_PER_GPU, G),
                        "schedule_steps": steps_full, "rec_rounds": G, "rec_ms_per_round": t_round,
+                       "precision": m.engine.precision,
                        "timed": "K fit steps + %d REC rounds, CUDA events, max over ranks" % n_rounds,
                        "l2": "per-step working set ~2 GB > 126 MB L2 (no flush needed)",
                        "step_algorithmic_tflop": step_flops / 1e12,
@@ -350,8 +358,10 @@ def run_b200(args):
                     "ms_per_step": t_e2e},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tf"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
-                         "note": "fp32 SIMT parity path; executed (polyphase) FLOPs; per-launch ms: "
+                         "frac": achieved / pk["tf"], "traffic": TRAFFIC.get(dom), "peak_source": pk["src"] + " bf16 sustained",
+                         "frac_of_tf32_peak": achieved / (pk["tf"] / 2),
+                         "note": "operands are TF32 (half the bf16 rate): frac_of_tf32_peak uses peak/2; executed "
+                                 "(polyphase) FLOPs; per-launch ms: "
                                  + ", ".join(f"{k}={v:.3f}" for k, v in sorted(timed.items(), key=lambda kv: -kv[1]))},
             "rec": {"candidates_per_s": cand_per_s, "ms_per_round": t_round, "pairs_per_round": ROWS_PER_GPU * world},
             "clocks": clk,
