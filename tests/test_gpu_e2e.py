@@ -56,6 +56,17 @@ def test_train_prior_then_compress_and_decode(tmp_path):
         a = model.predict(xt.cuda(), random_seed=1)
         b = model.predict(xt.cuda(), random_seed=2)
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-5)
+    # standalone receiver: packed 16-bit bitstream + prior + seed -> the same reconstruction
+    from recombiner_b200 import decode
+    blob = decode.bitstream_of(model)
+    assert len(blob) == 12 + 8 + 2 * idx.size                       # 16 bits per block, nothing else
+    rows, tabs = decode.unpack_bitstream(blob)
+    assert rows == 4 and np.array_equal(tabs[0], idx.astype(np.int64))
+    y_dec, m_dec = decode.decode("cifar", main_compression.load_prior(path), blob, "cuda", seed=42)
+    assert torch.equal(m_dec._lv.sample, model._lv.sample)          # bit-exact posterior samples
+    with torch.no_grad():
+        y_enc = model.predict(xt.cuda(), random_seed=0)
+    np.testing.assert_allclose(y_dec.cpu().numpy(), y_enc.cpu().numpy(), atol=1e-5)
 
 
 def test_short_schedule_matches_oracle_port_statistically():

@@ -126,3 +126,17 @@ def test_checkpoint_classes_have_reference_layout():
     assert tuple(up.conv1.weight.shape) == (64, 128, 5, 5) and tuple(up.conv3.weight.shape) == (16, 64, 3, 3)
     assert sum(p.numel() for p in up.parameters()) == 251024
     assert sum(p.numel() for p in Upsample(1, [2, 1, 1], [4, 2, 2]).parameters()) == 56464
+
+
+def test_bitstream_pack_roundtrip():
+    from recombiner_b200 import decode
+    rs = np.random.RandomState(1)
+    tabs = [rs.randint(0, 65536, (8, 33)), rs.randint(0, 65536, (2, 5)), rs.randint(0, 65536, (1, 7))]
+    blob = decode.pack_bitstream(tabs)
+    assert len(blob) == 12 + 3 * 8 + 2 * sum(t.size for t in tabs)
+    rows, back = decode.unpack_bitstream(blob)
+    assert rows == 8 and all(np.array_equal(a, b) for a, b in zip(tabs, back))
+    with pytest.raises(ValueError):
+        decode.pack_bitstream([np.array([[70000]])])
+    with pytest.raises(ValueError):
+        decode.unpack_bitstream(b"nope" + blob[4:])
