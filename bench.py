@@ -48,7 +48,7 @@ N_CAND = 65536
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/README.md); None where no capture exists yet
-TRAFFIC = {}
+TRAFFIC = {"mlp_fwd_bwd": 820.3e6}      # profiles/r1_ncu_full_mlp_tc.csv (1024 rows x S=5)
 
 
 def schedule(G: int):

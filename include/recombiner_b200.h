@@ -60,6 +60,8 @@ typedef struct {
   float* lpe;              /* (rows*S, n_l) or NULL; stitched (data*S, sp_total*lpe_c) when lpe_slot != NULL */
   const int* lpe_slot;     /* patch modalities: (rows_per_datum, n_l/lpe_c) slot of each latent position in the
                               datum's stitched grid (utils.py:71-90), or NULL */
+  float* eps_w_store;      /* optional (rows, S, n_w): keep the generated noise for rcb_fit_update */
+  float* eps_l_store;      /* optional (S, rows, n_l) */
   int64_t seed;
   int64_t row_offset;      /* global index of row 0 (multi-GPU shards) */
   int rows, S, P, n_w, n_l, ld_hw;

@@ -20,7 +20,7 @@ F64 = C.c_double
 
 class SampleArgs(C.Structure):
     _fields_ = [(n, P) for n in ("loc", "log_scale", "mask", "sample", "g2p", "perm", "row_map",
-                                 "eps_w", "eps_l", "hw", "lpe", "lpe_slot")] + \
+                                 "eps_w", "eps_l", "hw", "lpe", "lpe_slot", "eps_w_store", "eps_l_store")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate",
                                    "rows_per_datum", "sp_total", "lpe_c")]

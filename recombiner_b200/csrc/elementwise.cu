@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
     for (int s = 0; s < a.S; ++s) {
       float eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
                           : philox_normal(a.seed, a.step, a.tensor_id, (uint64_t)((gn * a.S + s) * a.n_w + p));
+      if (a.eps_w_store) a.eps_w_store[((int64_t)n * a.S + s) * a.n_w + p] = eps;
       float v = fmaf(sig, eps, mu);
       float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
       *dst = a.accumulate ? *dst + v : v;
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
     for (int s = 0; s < a.S; ++s) {
       float eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
                           : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
+      if (a.eps_l_store) a.eps_l_store[((int64_t)s * a.rows + n) * a.n_l + l] = eps;
       a.lpe[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)] = fmaf(sig, eps, mu);
     }
   }

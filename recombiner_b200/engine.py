@@ -332,6 +332,11 @@ class FitEngine:
         a.lpe = ptr(ws["lpe"]) if lv.level == 0 else None
         a.lpe_slot = ptr(self.lpe_slot)
         a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
+        # generated noise is kept for the gradient kernel: 4 B/element of HBM traffic is far
+        # cheaper than a second Philox + Box-Muller per element
+        store = self._eps_store(ws, rows, S)
+        a.eps_w_store = ptr(store[lv.level]) if a.eps_w is None else None
+        a.eps_l_store = ptr(store[3]) if (lv.level == 0 and a.eps_l is None) else None
         a.seed, a.row_offset = noise.seed, noise.row_offset
         a.rows, a.S, a.P, a.n_w, a.ld_hw = rows, S, lv.P, self.W, self.ldw
         a.n_l = self.L if lv.level == 0 else 0
@@ -351,6 +356,16 @@ class FitEngine:
         pb = ptr(B) if b_tensor is None else b_tensor.data_ptr() + 4 * b_off
         check(self.lib.rcb_gemm(pa, lda, pb, ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
               "rcb_gemm")
+
+    def _eps_store(self, ws, rows, S):
+        st = ws.get("eps_store")
+        if st is None:
+            dev = self.device
+            n_levels = 3 if self.patch_nums is not None else 1
+            st = [torch.empty(rows, S, self.W, device=dev) if l < n_levels else None for l in range(3)]
+            st.append(torch.empty(S, rows, self.L, device=dev))
+            ws["eps_store"] = st
+        return st
 
     def _upconv_fwd(self, i, src, out, citems, act):
         g = self.geoms[i]
@@ -496,6 +511,11 @@ class FitEngine:
         a.d_lpe = ptr(ws["d_lpe"]) if (with_data_grads and lv.level == 0) else None
         a.eps_w = ptr(noise.eps_for(lv.level))
         a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
+        if with_data_grads and ws is not None and "eps_store" in ws:      # noise kept by the sampling kernel
+            if a.eps_w is None:
+                a.eps_w = ptr(ws["eps_store"][lv.level])
+            if a.eps_l is None and lv.level == 0:
+                a.eps_l = ptr(ws["eps_store"][3])
         a.lpe_slot = ptr(self.lpe_slot)
         a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
         a.g_loc, a.g_log_scale = ptr(g_loc), ptr(g_log_scale)
