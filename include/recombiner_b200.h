@@ -166,10 +166,10 @@ typedef struct {
   float coef, w0;
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
-/* Same contract on tcgen05: every 128-pixel contraction (three sine layers, their data
- * gradients, and all four weight gradients as one MN-major 128x128 GEMM kept in TMEM over
- * the item's tiles) is a TF32 tensor-core MMA; activations are chained TMEM -> registers
- * (sin/cos) -> swizzled shared memory -> next MMA.  32 input features only (n_f = 16). */
+/* Same contract on tcgen05 (TF32 operands, fp32 accumulation in TMEM): two CTAs per SM, one
+ * item each; the chain products read their A operand straight from TMEM (the epilogue
+ * writes sin(.) and dZ back with tcgen05.st), the weight/bias gradients accumulate in TMEM
+ * over the tiles of the item from feature-major shared-memory copies.  n_f = 16 only. */
 int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream);
 
 /* Gradient reduction over MC samples + beta-weighted closed-form KL gradient
