@@ -65,19 +65,33 @@ struct Philox {
   }
 };
 
-// One standard normal per (seed, step, tensor_id, element): Philox block on the
-// element counter, Box-Muller on the first two words.  The same function is
-// called by the sampling kernel and by the gradient kernel, so eps is never stored.
-__device__ __forceinline__ float philox_normal(int64_t seed, int step, int tensor_id, uint64_t elem) {
-  uint32_t c[4] = {(uint32_t)elem, (uint32_t)(elem >> 32), (uint32_t)tensor_id, (uint32_t)step};
+// Standard normals keyed by (seed, step, tensor_id, item, index), item = global row * S + sample.
+// One Philox block yields two Box-Muller pairs = the normals of indices {c + t, c + 256 + t,
+// c + 512 + t, c + 768 + t} of a 1024-index chunk c (block number "quad" = chunk * 256 + t), so a
+// 256-thread CTA that owns a chunk reads and writes it fully coalesced.  philox_normal4 and
+// philox_normal return the same values: the sampling kernel and the gradient kernel agree
+// whether or not the noise is kept in memory.
+__device__ __forceinline__ void philox_normal4(int64_t seed, int step, int tensor_id, int64_t item, uint32_t quad,
+                                               float (&z)[4]) {
+  uint32_t c[4] = {quad, (uint32_t)item, (uint32_t)tensor_id ^ ((uint32_t)((uint64_t)item >> 32) << 8), (uint32_t)step};
   Philox::block(c, (uint32_t)seed, (uint32_t)((uint64_t)seed >> 32));
-  // u1 in (0,1], u2 in [0,1)
-  float u1 = ((float)(c[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);
-  float u2 = (float)(c[1] >> 8) * (1.0f / 16777216.0f);
-  float r = sqrtf(-2.0f * logf(u1));
-  float sn, cs;
-  sincospif(2.0f * u2, &sn, &cs);
-  return r * cs;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // u1 in (0,1], u2 in [0,1)
+    const float u1 = ((float)(c[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.2831853071795865f * u2, &sn, &cs);
+    z[2 * h] = r * cs;
+    z[2 * h + 1] = r * sn;
+  }
+}
+__device__ __forceinline__ float philox_normal(int64_t seed, int step, int tensor_id, int64_t item, uint32_t idx) {
+  float z[4];
+  philox_normal4(seed, step, tensor_id, item, ((idx >> 10) << 8) | (idx & 255u), z);
+  const uint32_t k = (idx >> 8) & 3u;
+  return k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3]));
 }
 
 template <typename T>

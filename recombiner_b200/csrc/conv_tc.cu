@@ -254,24 +254,36 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool valid = tile_row(a, r, item0, z0, y0, x0, item, z, y, x);
     mbar_wait(&acc_full[0], 0);
     tc_fence_after();
-    const int64_t m = valid ? (((int64_t)item * g.d + z) * g.h + y) * g.w + x : 0;
-    float* orow = a.out + m * IC;
-    const float* arow = a.src_act ? a.src_act + m * IC : nullptr;
+    // All MMAs (and therefore all TMA fills) are done: the pipeline stages are free.  Each warp
+    // stages its 32 x IC accumulator rows there (row-per-lane out of TMEM, padded rows), then
+    // walks them again with consecutive lanes on consecutive 16-B chunks of a row, so the
+    // activation-mask loads and the gradient stores are coalesced.
+    const int64_t m = valid ? (((int64_t)item * g.d + z) * g.h + y) * g.w + x : -1;
+    const int ldw = IC + 4;                                 // floats per staged row (bank-conflict-free float4 rows)
+    float* wbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * ldw;
     for (int c0 = 0; c0 < IC; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float f = __uint_as_float(v[j + t]);
-            if (arow) f *= (arow[c0 + j + t] > 0.f ? 1.f : 0.01f);
-            o[t] = f;
-          }
-          *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(wbuf + lane * ldw + c0 + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    __syncwarp();
+    const int lanes_per_row = IC / 4;                        // 16-B chunks per row: 4, 16 or 32
+    const int rows_per_iter = 32 / lanes_per_row;
+    const int sub = lane / lanes_per_row, ch = (lane % lanes_per_row) * 4;
+    for (int r0 = 0; r0 < 32; r0 += rows_per_iter) {
+      const int rr = r0 + sub;
+      const int64_t mm = __shfl_sync(0xffffffffu, m, rr & 31);
+      if (sub < rows_per_iter && mm >= 0) {
+        float4 f = *reinterpret_cast<const float4*>(wbuf + rr * ldw + ch);
+        if (a.src_act) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch));
+          f.x *= (s4.x > 0.f ? 1.f : 0.01f); f.y *= (s4.y > 0.f ? 1.f : 0.01f);
+          f.z *= (s4.z > 0.f ? 1.f : 0.01f); f.w *= (s4.w > 0.f ? 1.f : 0.01f);
         }
+        *reinterpret_cast<float4*>(a.out + mm * IC + ch) = f;
       }
     }
   }
@@ -399,6 +411,7 @@ extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const f
   a.act = 0; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
   int smem_total;
   smem_layout(&a, bk * 4, g.ic, &smem_total);
+  RCB_CHECK_ARG(4 * 32 * (g.ic + 4) * 4 <= a.bar_off, "rcb_upconv_bwd_tc: epilogue staging does not fit the pipeline stages");
   const CUtensorMapSwizzle swz = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmA, tmB;
   if (int rc = make_map_5d(&tmA, d_out, items, g.d * g.fz, g.h * g.fy, g.w * g.fx, g.oc, a.t, bk, g.fz, g.fy, g.fx, swz)) return rc;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
   if (p < a.n_w) {
     for (int s = 0; s < a.S; ++s) {
       float eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
-                          : philox_normal(a.seed, a.step, a.tensor_id, (uint64_t)((gn * a.S + s) * a.n_w + p));
+                          : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
       if (a.eps_w_store) a.eps_w_store[((int64_t)n * a.S + s) * a.n_w + p] = eps;
       float v = fmaf(sig, eps, mu);
       float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
@@ -43,9 +43,185 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
     const int l = p - a.n_w;
     for (int s = 0; s < a.S; ++s) {
       float eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
-                          : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
+                          : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
       if (a.eps_l_store) a.eps_l_store[((int64_t)s * a.rows + n) * a.n_l + l] = eps;
       a.lpe[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)] = fmaf(sig, eps, mu);
+    }
+  }
+}
+
+
+// Row-per-CTA variant for the non-patch modalities (no row permutation / expansion / stitching):
+// the row's posterior (group order) is staged once in shared memory, then every (sample,
+// parameter) output is written coalesced, four Philox normals per block.
+// dynamic smem: 4 * P floats.
+__global__ void __launch_bounds__(256) sample_rows_kernel(rcb_sample_args a) {
+  extern __shared__ float sm[];
+  float* s_mu = sm;                 // parameter order
+  float* s_sig = sm + a.P;
+  float* g_mu = sm + 2 * a.P;       // group order (as stored)
+  float* g_sig = sm + 3 * a.P;
+  const int n = blockIdx.x;
+  for (int q = threadIdx.x; q < a.P; q += blockDim.x) {
+    const int64_t e = (int64_t)n * a.P + q;
+    const float m = a.mask ? a.mask[e] : 0.f;
+    float mu = a.loc[e] * (1.f - m);
+    if (a.sample) mu += a.sample[e] * m;
+    g_mu[q] = mu;
+    g_sig[q] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
+    const int q = a.g2p ? a.g2p[p] : p;
+    s_mu[p] = g_mu[q];
+    s_sig[p] = g_sig[q];
+  }
+  __syncthreads();
+  const int64_t gn = a.row_offset + n;
+  const int t = threadIdx.x;                     // blockDim.x == 256: slot of the Philox chunk
+  for (int s = 0; s < a.S; ++s) {
+    const int64_t item = (int64_t)n * a.S + s;
+    float* hw = a.hw + item * a.ld_hw;
+    const float* ein = a.eps_w ? a.eps_w + item * a.n_w : nullptr;
+    float* eout = a.eps_w_store ? a.eps_w_store + item * a.n_w : nullptr;
+    for (int c0 = 0; c0 < a.n_w; c0 += 1024) {
+      float z[4];
+      if (!ein) philox_normal4(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)((c0 >> 2) + t), z);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int p = c0 + k * 256 + t;
+        if (p < a.n_w) {
+          const float eps = ein ? ein[p] : z[k];
+          if (eout) eout[p] = eps;
+          hw[p] = fmaf(s_sig[p], eps, s_mu[p]);
+        }
+      }
+    }
+    if (a.lpe) {
+      float* lpe = a.lpe + item * a.n_l;
+      const float* lin = a.eps_l ? a.eps_l + ((int64_t)s * a.rows + n) * a.n_l : nullptr;
+      float* lout = a.eps_l_store ? a.eps_l_store + ((int64_t)s * a.rows + n) * a.n_l : nullptr;
+      for (int c0 = 0; c0 < a.n_l; c0 += 1024) {
+        float z[4];
+        if (!lin) philox_normal4(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)((c0 >> 2) + t), z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int l = c0 + k * 256 + t;
+          if (l < a.n_l) {
+            const float eps = lin ? lin[l] : z[k];
+            if (lout) lout[l] = eps;
+            lpe[l] = fmaf(s_sig[a.n_w + l], eps, s_mu[a.n_w + l]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Row-per-CTA variant of update_kernel for the same case: the per-sample gradients are reduced
+// in parameter order (coalesced) into shared memory, then the KL gradient + Adam runs in group
+// order (coalesced on the stored state).  Same arithmetic order as update_kernel.
+// dynamic smem: 2 * P floats.
+__global__ void __launch_bounds__(256) update_rows_kernel(rcb_update_args a) {
+  extern __shared__ float sm[];
+  float* s_dmu = sm;
+  float* s_dsig = sm + a.P;
+  const int r = blockIdx.x;
+  const int64_t gn = a.row_offset + r;
+  // loads of 2 parameters x up to 4 samples are issued together (memory-level parallelism);
+  // the sums still run over s in ascending order
+  for (int p0 = threadIdx.x; p0 < a.P; p0 += 2 * blockDim.x) {
+    float d_mu[2] = {0.f, 0.f}, d_sig[2] = {0.f, 0.f};
+    for (int s0 = 0; s0 < a.S; s0 += 4) {
+      float d[2][4], eps[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int p = p0 + u * blockDim.x;
+        const bool is_w = p < a.n_w;
+        const int l = p - a.n_w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int s = s0 + k;
+          d[u][k] = 0.f; eps[u][k] = 0.f;
+          if (p < a.P && s < a.S) {
+            const int64_t item = (int64_t)r * a.S + s;
+            if (is_w) {
+              d[u][k] = a.d_hw[item * a.ld_hw + p];
+              eps[u][k] = a.eps_w ? a.eps_w[item * a.n_w + p]
+                                  : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
+            } else {
+              d[u][k] = a.d_lpe[item * a.n_l + l];
+              eps[u][k] = a.eps_l ? a.eps_l[((int64_t)s * a.rows + r) * a.n_l + l]
+                                  : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (s0 + k < a.S) {
+            d_mu[u] += d[u][k];
+            d_sig[u] = fmaf(d[u][k], eps[u][k], d_sig[u]);
+          }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int p = p0 + u * blockDim.x;
+      if (p < a.P) { s_dmu[p] = d_mu[u]; s_dsig[p] = d_sig[u]; }
+    }
+  }
+  __syncthreads();
+  float kl_term = 0.f;
+  for (int q = threadIdx.x; q < a.P; q += blockDim.x) {
+    const int64_t e = (int64_t)r * a.P + q;
+    const int p = a.p2g ? a.p2g[q] : q;
+    const float mu = a.loc[e], rho = a.log_scale[e];
+    const float m = a.mask ? a.mask[e] : 0.f;
+    const float sig = std_transform(rho);
+    float d_mu = 0.f, d_sig = 0.f;
+    if (m != 1.f) {
+      d_mu = s_dmu[p] * (a.grad_scale * (1.f - m));
+      d_sig = s_dsig[p] * (a.grad_scale * (1.f - m));
+    }
+    const float beta = a.beta ? a.beta[(int64_t)r * a.G + a.group_idx[q]] : a.beta_scalar;
+    const float mu_p = a.p_loc[q], sig_p = a.p_scale_direct ? a.p_log_scale[q] : std_transform(a.p_log_scale[q]);
+    const float inv_vp = 1.f / (sig_p * sig_p);
+    const float dm = mu - mu_p;
+    const float ratio = sig / sig_p;
+    const float vr = ratio * ratio;
+    const float t1 = (dm / sig_p) * (dm / sig_p);
+    kl_term += beta * 0.5f * (vr + t1 - 1.f - logf(vr));
+    const float g_mu = d_mu + beta * dm * inv_vp;
+    const float g_sig = d_sig + beta * (sig * inv_vp - 1.f / sig);
+    const float g_rho = g_sig * std_transform_grad(rho);
+    if (a.adam) {
+      const float step_size = a.adam_step_size, bc2s = a.adam_bc2_sqrt;
+      float m1 = a.m1_loc[e], v = a.v_loc[e];
+      m1 = m1 + (g_mu - m1) * (1.f - a.b1);
+      v = v * a.b2 + (1.f - a.b2) * g_mu * g_mu;
+      a.m1_loc[e] = m1; a.v_loc[e] = v;
+      a.loc[e] = mu - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
+      m1 = a.m1_ls[e]; v = a.v_ls[e];
+      m1 = m1 + (g_rho - m1) * (1.f - a.b1);
+      v = v * a.b2 + (1.f - a.b2) * g_rho * g_rho;
+      a.m1_ls[e] = m1; a.v_ls[e] = v;
+      a.log_scale[e] = rho - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
+    } else {
+      a.g_loc[e] = g_mu;
+      a.g_log_scale[e] = g_rho;
+    }
+  }
+  if (a.kl_out) {
+    __shared__ float red[8];
+    const float s = warp_sum(kl_term);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += (double)red[w];
+      atomicAdd(a.kl_out, t);
     }
   }
 }
@@ -77,12 +253,12 @@ __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
           if (is_w) {
             d = src[((int64_t)n * a.S + s) * a.ld_hw + p];
             eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
-                          : philox_normal(a.seed, a.step, a.tensor_id, (uint64_t)((gn * a.S + s) * a.n_w + p));
+                          : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
           } else {
             const int l = p - a.n_w;
             d = src[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)];
             eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
-                          : philox_normal(a.seed, a.step, a.tensor_id + 16, (uint64_t)((gn * a.S + s) * a.n_l + l));
+                          : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
           }
           d_mu += d;
           d_sig = fmaf(d, eps, d_sig);
@@ -230,6 +406,16 @@ extern "C" int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->n_w + a->n_l == a->P || (a->n_l == 0 && a->n_w == a->P), "rcb_fit_sample: n_w+n_l != P");
   RCB_CHECK_ARG(a->ld_hw >= a->n_w, "rcb_fit_sample: ld_hw too small");
   RCB_CHECK_ARG(a->rows <= 65535, "rcb_fit_sample: at most 65535 rows per call");
+  const size_t row_smem = 4 * sizeof(float) * (size_t)a->P;
+  if (!a->perm && !a->row_map && !a->lpe_slot && !a->accumulate && row_smem <= 200 * 1024) {
+    if (row_smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
+      if (e != cudaSuccess) { set_error("rcb_fit_sample: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+    }
+    sample_rows_kernel<<<a->rows, 256, row_smem, (cudaStream_t)stream>>>(*a);
+    RCB_CHECK_LAUNCH("rcb_fit_sample");
+    return 0;
+  }
   dim3 grid(ceil_div(a->P, 256), a->rows);
   sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
   RCB_CHECK_LAUNCH("rcb_fit_sample");
@@ -245,6 +431,17 @@ extern "C" int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream) {
     RCB_CHECK_ARG(a->m1_loc && a->v_loc && a->m1_ls && a->v_ls && a->adam_bc2_sqrt > 0.f, "rcb_fit_update: Adam state missing");
   } else {
     RCB_CHECK_ARG(a->g_loc && a->g_log_scale, "rcb_fit_update: gradient outputs missing");
+  }
+  const size_t row_smem = 2 * sizeof(float) * (size_t)a->P;
+  if (!a->perm_inv && !a->row_children && !a->lpe_slot && a->d_hw && (a->n_l == 0 || a->d_lpe) && a->n_w + a->n_l == a->P &&
+      row_smem <= 200 * 1024) {
+    if (row_smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(update_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
+      if (e != cudaSuccess) { set_error("rcb_fit_update: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+    }
+    update_rows_kernel<<<a->src_rows, 256, row_smem, (cudaStream_t)stream>>>(*a);
+    RCB_CHECK_LAUNCH("rcb_fit_update");
+    return 0;
   }
   dim3 grid(ceil_div(a->P, 256), a->src_rows);
   update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);

@@ -86,8 +86,27 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+#ifdef RCB_MLP_PROFILE
+__device__ long long rcb_prof_buf[4 * 512];
+#define PROF(id)                                                                         \
+  do {                                                                                   \
+    if (prof_slot >= 0 && prof_n < 255) {                                                \
+      rcb_prof_buf[prof_slot * 512 + 2 * prof_n] = (id);                                 \
+      rcb_prof_buf[prof_slot * 512 + 2 * prof_n + 1] = clock64();                        \
+      ++prof_n;                                                                          \
+    }                                                                                    \
+  } while (0)
+#else
+#define PROF(id) do {} while (0)
+#endif
+
 template <int OUT, int MODE>
 __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
+#ifdef RCB_MLP_PROFILE
+  int prof_n = 0;
+  const int prof_slot = (blockIdx.x == 3000 && (threadIdx.x == 0 || threadIdx.x == 64)) ? (threadIdx.x == 0 ? 0 : 1)
+                        : ((blockIdx.x == 3001 && (threadIdx.x == 0 || threadIdx.x == 64)) ? (threadIdx.x == 0 ? 2 : 3) : -1);
+#endif
   constexpr int F = 16, HID = 32, NPE = 16;
   constexpr int off0 = 0, off1 = HID * (32 + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
   extern __shared__ uint8_t smem_raw[];
@@ -171,6 +190,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const uint32_t id32 = idesc_tf32(32), id16 = idesc_tf32(16);
       mbar_wait(bar_ready, ph_ready);
       tc_fence_after();
+      PROF(100 + stage);
       switch (stage) {
         case 0: chain(TM_ACC, TM_S0, MtSmem::WF, id32); break;
         case 1: chain(TM_ACC, TM_S1, MtSmem::WF + 4096, id32); break;
@@ -191,6 +211,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           break;
       }
       umma_commit(bar_mma);
+      PROF(110 + stage);
     }
     ph_ready ^= 1;
     __syncwarp();
@@ -220,19 +241,19 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) sts32(base + swz(j0 + j, lane), v[j]);
   };
-  // this thread's 16 input features of pixel gp: Fourier features (half 0) or positional encodings (half 1)
+  // this thread's 16 input features of pixel gp: Fourier features (half 0) or positional encodings (half 1);
+  // raw fp32 patterns (TF32 rounding happens when they are consumed, so the loads stay in flight)
   auto load_x0 = [&](int gp, uint32_t (&v)[16]) {
     const bool ok = gp < pix;
     if (hh == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = ok ? rnd_tf32(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
+      for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
     } else {
-      const float4* p = reinterpret_cast<const float4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
+      const uint4* p = reinterpret_cast<const uint4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float4 t4 = ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[c * 4] = ok ? rnd_tf32(t4.x) : 0u; v[c * 4 + 1] = ok ? rnd_tf32(t4.y) : 0u;
-        v[c * 4 + 2] = ok ? rnd_tf32(t4.z) : 0u; v[c * 4 + 3] = ok ? rnd_tf32(t4.w) : 0u;
+        const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
+        v[c * 4] = t4.x; v[c * 4 + 1] = t4.y; v[c * 4 + 2] = t4.z; v[c * 4 + 3] = t4.w;
       }
     }
   };
@@ -257,17 +278,23 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     const bool valid = gp < pix;
     const bool first = tile == 0;
     // ---- X0 -> TMEM
+    PROF(0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xin[i] += 0x1000u;                // TF32 round-to-nearest of the inputs
     tmem_st16(tm + TM_S0 + j0, xin);
     publish(false);
+    PROF(1);
     issue(0, first);
     // ---- three sine layers: X_{l+1} = sin(acc + b'), cs_l = cos(acc + b')
     float cs[3][16];
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
       wait_mma();
+      PROF(10 + l);
       uint32_t acc[16];
       tmem_ld16_issue(tm + TM_ACC + j0, acc);
       tmem_ld_wait();
+      PROF(20 + l);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float z = __uint_as_float(acc[j]) + plain[l * 32 + j0 + j];
@@ -275,11 +302,14 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         acc[j] = rnd_tf32(__sinf(z));
       }
       tmem_st16(tm + (l == 0 ? TM_S1 : (l == 1 ? TM_S2 : TM_ACC)) + j0, acc);
+      PROF(30 + l);
       publish(false);
+      PROF(40 + l);
       issue(l + 1, first);
     }
     // ---- output layer (on the tensor core), loss and dy; both halves of a row read the same columns
     wait_mma();
+    PROF(50);
     float dy[OUT];
     {
       uint32_t yv[16];
@@ -330,13 +360,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       }
       store_t(dzt_addr, dz);
       tmem_st16(tm + TM_S2 + j0, dz);
+      PROF(51);
       publish(true);
+      PROF(52);
       issue(4, first);
     }
     // ---- dZ1, dZ0: data gradient from the tensor core times cos; X1^T, X0^T
 #pragma unroll
     for (int l = 1; l >= 0; --l) {
       wait_mma();
+      PROF(60 + l);
       uint32_t acc[16], xv[16];
       tmem_ld16_issue(tm + TM_ACC + j0, acc);
       tmem_ld16_issue(tm + (l == 1 ? TM_S1 : TM_S0) + j0, xv);
@@ -346,13 +379,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       for (int j = 0; j < 16; ++j) acc[j] = rnd_tf32(__uint_as_float(acc[j]) * cs[l][j]);
       store_t(dzt_addr, acc);
       tmem_st16(tm + (l == 1 ? TM_S1 : TM_S0) + j0, acc);
+      PROF(62 + l);
       publish(true);
+      PROF(64 + l);
       issue(l == 1 ? 5 : 6, first);
     }
     // ---- next tile's inputs travel while the last MMAs of this tile run
     if (tile + 1 < ntiles) load_x0(gp + 128, xin);
     // ---- d pe (16 columns: 8 per half); the chain carries dZ / w0
+    PROF(70);
     wait_mma();
+    PROF(71);
     {
       uint32_t acc[16];
       tmem_ld16_issue(tm + TM_ACC, acc);
@@ -427,6 +464,12 @@ static int launch_mlp_tc(const rcb_mlp_args* a, cudaStream_t st) {
 }  // namespace rcb
 
 using namespace rcb;
+
+#ifdef RCB_MLP_PROFILE
+extern "C" int rcb_mlp_prof_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rcb_prof_buf, sizeof(long long) * 4 * 512);
+}
+#endif
 
 extern "C" int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a != nullptr, "rcb_mlp_tc: null args");
