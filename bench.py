@@ -48,7 +48,8 @@ N_CAND = 65536
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/README.md); None where no capture exists yet
-TRAFFIC = {"mlp_fwd_bwd": 820.3e6}      # profiles/r1_ncu_full_mlp_tc.csv (1024 rows x S=5)
+TRAFFIC = {"mlp_fwd_bwd": 777.8e6,       # profiles/r1_ncu_full_mlp_tc_v2_sample_update.csv (1024 rows x S=5)
+           "update": 310.9e6, "sample": 157.7e6}
 
 
 def schedule(G: int):
