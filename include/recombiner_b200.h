@@ -166,10 +166,13 @@ typedef struct {
   float coef, w0;
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
-/* Same contract on tcgen05 (TF32 operands, fp32 accumulation in TMEM): two CTAs per SM, one
- * item each; the chain products read their A operand straight from TMEM (the epilogue
- * writes sin(.) and dZ back with tcgen05.st), the weight/bias gradients accumulate in TMEM
- * over the tiles of the item from feature-major shared-memory copies.  n_f = 16 only. */
+/* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA, two CTAs per SM.
+ * Chain products (TF32 operands, fp32 accumulation in TMEM) read their A operand straight from
+ * TMEM and are updated in place by the epilogue (tcgen05.ld -> sin / *cos -> tcgen05.st); the
+ * weight/bias gradients accumulate in TMEM over the item's tiles from feature-major fp16 copies
+ * in shared memory (X in [-1,1]; gradients carried in units of coef).  n_f = 16 only.
+ * mode 1 needs coef > 0; in mode 2 `coef` (if > 0) is a scale applied to dy inside the kernel and
+ * removed from the outputs (pick ~1/max|dy| so that fp16 keeps its 10-bit mantissa). */
 int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream);
 
 /* Gradient reduction over MC samples + beta-weighted closed-form KL gradient

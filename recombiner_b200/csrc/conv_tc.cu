@@ -98,16 +98,17 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // warps 0 and 1 stay converged; one elected lane issues the TMA loads / MMAs (see elect_one)
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      for (int p = 0; p < nph; ++p) {
-        int rz, ry, rx;
-        g.split_phase(ph0 + p, rz, ry, rx);
-        const int bz = g.base_z(rz), by = g.base_y(ry), bx = g.base_x(rx);
-        for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+    int it = 0;
+    for (int p = 0; p < nph; ++p) {
+      int rz, ry, rx;
+      g.split_phase(ph0 + p, rz, ry, rx);
+      const int bz = g.base_z(rz), by = g.base_y(ry), bx = g.base_x(rx);
+      for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+        if (elect_one()) {
           const int tap = kb / a.kblocks, c0 = (kb - tap * a.kblocks) * 32;
           int tz, ty, tx;
           g.split_tap(tap, tz, ty, tx);
@@ -116,25 +117,27 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_load_5d(&tmA, &full[s], a_dst, c0, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
           tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * 32, (ph0 + p) * OC);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(OC);
-      int it = 0;
-      for (int p = 0; p < nph; ++p) {
-        for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          mbar_wait(&full[s], (it / TC_STAGES) & 1);
-          tc_fence_after();
+    const uint32_t idesc = idesc_tf32(OC);
+    int it = 0;
+    for (int p = 0; p < nph; ++p) {
+      for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait(&full[s], (it / TC_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
           const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(a_addr + a.b_off);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_tf32(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           umma_commit(&empty[s]);
+          if (kb == kb_per_phase - 1) umma_commit(&acc_full[p]);
         }
-        umma_commit(&acc_full[p]);
+        __syncwarp();
       }
     }
   } else {
@@ -212,10 +215,10 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % TC_STAGES;
-        mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % TC_STAGES;
+      mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         const int seg = it / a.kblocks, c0 = (it - seg * a.kblocks) * BK;
         int tz, ty, tx, rz, ry, rx;
         g.split_tap(seg % g.taps(), tz, ty, tx);
@@ -229,14 +232,15 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tma_load_5d(&tmA, &full[s], a_dst, c0, cx, cy, cz, item0);
         tma_load_2d(&tmB, &full[s], a_dst + a.b_off, c0, seg * IC);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(IC);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % TC_STAGES;
-        mbar_wait(&full[s], (it / TC_STAGES) & 1);
-        tc_fence_after();
+    const uint32_t idesc = idesc_tf32(IC);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % TC_STAGES;
+      mbar_wait(&full[s], (it / TC_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
         const uint64_t da = BK == 32 ? smem_desc_sw128(a_addr) : smem_desc_sw64(a_addr);
         const uint64_t db = BK == 32 ? smem_desc_sw128(a_addr + a.b_off) : smem_desc_sw64(a_addr + a.b_off);
@@ -244,8 +248,9 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int k = 0; k < BK / 8; ++k)
           umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
         umma_commit(&empty[s]);
+        if (it == nkb - 1) umma_commit(&acc_full[0]);
       }
-      umma_commit(&acc_full[0]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -57,28 +57,30 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+    // whole warp converged, one elected lane issues (see elect_one)
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
         mbar_expect_tx(&full[s], S::STAGE_BYTES);
         tma_load_2d(&tmA, &full[s], a_dst, kb * TC_BK, m0);
         tma_load_2d(&tmB, &full[s], b_dst, kb * TC_BK, n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ===== MMA issuer (whole warp converged, one elected lane issues) =====
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b_addr = a_addr + S::A_BYTES;
         const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(b_addr);
@@ -88,8 +90,9 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
         }
         umma_commit(&empty[s]);          // frees the smem stage once these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full);   // accumulator complete
       }
-      umma_commit(tmem_full);            // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====

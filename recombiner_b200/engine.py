@@ -427,9 +427,15 @@ class FitEngine:
         a.pe_base = ptr(ws["pe_base"])
         a.pitch_z, a.pitch_y, a.ph, a.pw = self.pitch_z, self.pitch_y, self.ph, self.pw
         a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
+        use_tc = self.tc_mlp and self.n_f == 16
+        if use_tc and mode == 2 and coef == 0.0:
+            # the tensor-core kernel keeps its weight-gradient operands in fp16: hand it a power-of-two
+            # scale that brings the caller's dy to O(1) (host sync; this is the autograd path, not the fit loop)
+            amax = float(dy.abs().max())
+            coef = 2.0 ** round(-math.log2(amax)) if amax > 0.0 and math.isfinite(amax) else 1.0
         a.coef, a.w0 = coef, self.w0
         with self.section("mlp_fwd" if mode == 0 else "mlp_fwd_bwd"):
-            if self.tc_mlp and self.n_f == 16:
+            if use_tc:
                 check(self.lib.rcb_mlp_tc(C.byref(a), stream()), "rcb_mlp_tc")
             else:
                 check(self.lib.rcb_mlp(C.byref(a), stream()), "rcb_mlp")

@@ -1,7 +1,8 @@
 """Tensor-core fused SIREN MLP (rcb_mlp_tc) against the fp32 SIMT kernel (rcb_mlp) on the same
-inputs: prediction, squared error, d pe and all weight/bias gradients.  TF32 operands
-(round-to-nearest on store) through sin(30 z): stated tolerance 3e-2 * max|reference| per
-tensor, 1e-3 relative on the summed squared error."""
+inputs: prediction, squared error, d pe and all weight/bias gradients.  TF32 chain operands,
+fp16 weight-gradient operands (10-bit mantissas, round-to-nearest) through sin(30 z): stated
+tolerance 3e-2 * max|reference| per tensor, 2e-3 relative on the summed squared error.  In mode 2
+`coef` is the dy scale of the tensor-core kernel (ignored by the SIMT kernel)."""
 import ctypes as C
 
 import numpy as np
@@ -47,7 +48,7 @@ def test_mlp_tc_matches_simt(pix, out, rows, S, wscale):
             t = {k: v.cuda().contiguous() for k, v in base.items()}
             t.update(y_pred=torch.zeros(items, pix, out, device="cuda"), d_pe=torch.zeros(items, pix, 16, device="cuda"),
                      d_wt=torch.zeros(items, ld_w, device="cuda"), sqerr=torch.zeros(items, device="cuda"))
-            a = _args(MlpArgs, items, S, pix, out, ld_w, mode, t, coef=2.0 / (S * pix * out))
+            a = _args(MlpArgs, items, S, pix, out, ld_w, mode, t, coef=2.0 / (S * pix * out) if mode != 2 else 256.0)
             check(fn(C.byref(a), stream()), name)
             torch.cuda.synchronize()
             res[(name, mode)] = {k: t[k].cpu().numpy() for k in ("y_pred", "d_pe", "d_wt", "sqerr")}
