@@ -166,7 +166,8 @@ typedef struct {
   float coef, w0;
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
-/* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA, two CTAs per SM.
+/* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA (one 128-thread group
+ * each, a thread per pixel row), two CTAs per SM.
  * Chain products (TF32 operands, fp32 accumulation in TMEM) read their A operand straight from
  * TMEM and are updated in place by the epilogue (tcgen05.ld -> sin / *cos -> tcgen05.st); the
  * weight/bias gradients accumulate in TMEM over the item's tiles from feature-major fp16 copies

@@ -1,6 +1,7 @@
-// Tensor-core fused per-item SIREN MLP (forward + squared error + backward): TWO 128-pixel tiles of the item in flight
-// per CTA (software-pipelined by the same 256 threads: while tile A's MMAs run, the threads do
-// tile B's epilogue) and two CTAs per SM, i.e. four tiles in flight per SM.
+// Tensor-core fused per-item SIREN MLP (forward + squared error + backward): TWO 128-pixel tiles of
+// the item in flight per CTA -- warps 0-3 own the even tiles, warps 4-7 the odd ones, one thread per
+// pixel row with all 32 features, so one group's epilogue overlaps the other group's MMA round
+// trip -- and two CTAs per SM, i.e. four tiles in flight per SM.
 //
 // What makes four tiles fit:
 //  * the chain  Z_l = X_l W_l,  y = X_3 W_3,  dX_l = dZ_l W_l^T  (tcgen05 kind::tf32, A operand in
@@ -23,10 +24,10 @@
 #include "tc_common.cuh"
 
 namespace rcb {
-namespace v3 {
+namespace mlp {
 
-constexpr int MT_EPI = 256;
-constexpr int MT_THREADS = 256;        // two threads per pixel row, 16 features each; the warps take turns issuing the MMAs
+constexpr int MT_THREADS = 256;        // 2 groups x 128 threads: one thread per pixel row of the group's tile
+constexpr int MT_GROUP = 128;
 
 // TMEM columns: tile slot s owns [64 s, 64 s + 64) = regions R0, R1; weight-gradient accumulators after
 constexpr uint32_t TM_DW = 128, TM_COLS = 256;
@@ -114,33 +115,37 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 
-#ifdef RCB_MLP_PROFILE
-__device__ long long rcb_prof_buf[4 * 1024];
-#define PROF(id)                                                                         \
-  do {                                                                                   \
-    if (prof_slot >= 0 && prof_n < 511) {                                                \
-      rcb_prof_buf[prof_slot * 1024 + 2 * prof_n] = (id);                               \
-      rcb_prof_buf[prof_slot * 1024 + 2 * prof_n + 1] = clock64();                      \
-      ++prof_n;                                                                          \
-    }                                                                                    \
-  } while (0)
-#else
-#define PROF(id) do {} while (0)
-#endif
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 
 template <int OUT, int MODE>
 __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
-#ifdef RCB_MLP_PROFILE
-  int prof_n = 0;
-  const int prof_slot = (blockIdx.x == 3000 && (threadIdx.x == 0 || threadIdx.x == 64)) ? (threadIdx.x == 0 ? 0 : 1)
-                        : ((blockIdx.x == 3001 && (threadIdx.x == 0 || threadIdx.x == 64)) ? (threadIdx.x == 0 ? 2 : 3) : -1);
-#endif
   constexpr int F = 16, HID = 32, NPE = 16;
   constexpr int off0 = 0, off1 = HID * (32 + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   float* plain = (float*)(smem + Sm::PLAIN);
-  uint64_t* bar_ready = (uint64_t*)(smem + Sm::BAR);       // [2] epilogue -> MMA (256 arrivals), one per tile slot
+  uint64_t* bar_ready = (uint64_t*)(smem + Sm::BAR);       // [2] epilogue -> MMA (128 arrivals), one per group
   uint64_t* bar_mma = bar_ready + 2;                       // [2] MMA -> epilogue (commit of the stage's MMAs)
   uint32_t* tmem_slot = (uint32_t*)(bar_ready + 4);
 
@@ -157,8 +162,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 
   if ((sbase & 1023u) != 0u) __trap();                     // the swizzled tiles assume a 1024-B aligned window
   if (threadIdx.x == 0) {
-    mbar_init(&bar_ready[0], MT_EPI);
-    mbar_init(&bar_ready[1], MT_EPI);
+    mbar_init(&bar_ready[0], MT_GROUP);
+    mbar_init(&bar_ready[1], MT_GROUP);
     mbar_init(&bar_mma[0], 1);
     mbar_init(&bar_mma[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // ---- stage the item's weights (w0 folded in), the constant rows of the A tiles, zero padding of dy^T
   {
     const int t = threadIdx.x;
-    for (int e = t; e < 3 * HID * HID; e += MT_EPI) {
+    for (int e = t; e < 3 * HID * HID; e += MT_THREADS) {
       const int l = e / (HID * HID), r = (e / HID) % HID, c = e % HID;          // W_l[i = r][j = c]
       const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
       const uint32_t w = rnd_tf32(w0 * wt_g[off + HID + r * HID + c]);
@@ -175,20 +180,20 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       if (l > 0) sts32(sbase + Sm::WB + l * 4096 + swz4(r, c), w);              // backward B: rows i, K = j
       else if (r >= F) sts32(sbase + Sm::WB + swz4(r - F, c), w);               // layer 0: pe inputs only
     }
-    for (int e = t; e < 16 * HID; e += MT_EPI) {
+    for (int e = t; e < 16 * HID; e += MT_THREADS) {
       const int k = e / HID, j = e % HID;                                       // W_3[j][k] -> rows k, K = j
       sts32(sbase + Sm::W3 + swz4(k, j), k < OUT ? rnd_tf32(wt_g[off3 + OUT + j * OUT + k]) : 0u);
     }
-    for (int e = t; e < 3 * HID; e += MT_EPI) plain[e] = w0 * wt_g[(e / HID == 0 ? off0 : (e / HID == 1 ? off1 : off2)) + e % HID];
+    for (int e = t; e < 3 * HID; e += MT_THREADS) plain[e] = w0 * wt_g[(e / HID == 0 ? off0 : (e / HID == 1 ? off1 : off2)) + e % HID];
     if (t < 4) plain[96 + t] = t < OUT ? wt_g[off3 + t] : 0.f;
-    for (int e = t; e < HID * 4; e += MT_EPI) plain[128 + e] = (e % 4 < OUT) ? wt_g[off3 + OUT + (e / 4) * OUT + e % 4] : 0.f;
+    for (int e = t; e < HID * 4; e += MT_THREADS) plain[128 + e] = (e % 4 < OUT) ? wt_g[off3 + OUT + (e / 4) * OUT + e % 4] : 0.f;
     if (MODE != 0) {
       // rows 32..39 of every K block of every A tile: ones row + zeros (32-bit words = fp16 pairs)
-      for (int e = t; e < 2 * 3 * 2 * 8 * 32; e += MT_EPI) {
+      for (int e = t; e < 2 * 3 * 2 * 8 * 32; e += MT_THREADS) {
         const int s = e / 1536, b = (e / 512) % 3, kb = (e / 256) % 2, rr = 32 + (e / 32) % 8, c = e % 32;
         sts32(sbase + s * Sm::SLOT + b * Sm::XT_BYTES + kb * Sm::XT_KB + rr * 128 + c * 4, rr == 32 ? 0x3c003c00u : 0u);
       }
-      for (int e = t; e < 2 * 1024; e += MT_EPI) sts32(sbase + (e / 1024) * Sm::SLOT + Sm::DZ3 + (e % 1024) * 4, 0u);
+      for (int e = t; e < 2 * 1024; e += MT_THREADS) sts32(sbase + (e / 1024) * Sm::SLOT + Sm::DZ3 + (e % 1024) * 4, 0u);
     }
   }
   fence_async_smem();
@@ -197,42 +202,60 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- MMA issue.  The stage's MMAs are issued by ONE warp, right after it has published its own
-  // share: the whole warp waits for the 256 arrivals (converged), one elected lane issues and
-  // commits.  Issue blocks while the tensor pipe is busy, so the warps take turns (stage, slot) ->
-  // warp: no single warp carries all of it.  MMAs of consecutive stages of a slot are ordered by
-  // completion (commit -> wait -> publish); the slots only share the weight-gradient accumulators,
-  // where the in-order pipe makes every D += A B atomic.
-  uint32_t ph_ready[2] = {0u, 0u};
-  // 128 x n x 32 chain product (TF32), A in TMEM columns [a_col, a_col + 32)
+  const int g = warp >> 2;                // group = tile slot: tiles g, g + 2, g + 4, ...
+  const int q = warp & 3;                 // TMEM lane quarter
+  const int r = q * 32 + lane;            // pixel row inside the tile
+  const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t R0 = (uint32_t)(64 * g), R1 = R0 + 32;
+  const int so = g * Sm::SLOT;
+
+  if (MODE != 0) {
+    // the weight-gradient accumulators are shared by both groups: start them at zero, always accumulate
+    if (g == 0) {
+      uint32_t z[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) z[i] = 0u;
+      tmem_st32(tm + TM_DW, z);
+      tmem_st32(tm + TM_DW + 32, z);
+      tmem_st32(tm + TM_DW + 64, z);
+      tmem_st32(tm + TM_DW + 80, z);      // columns [208, 240): overlaps the previous store, covers DW3
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  // ---- MMA issue.  The stage's MMAs are issued by ONE warp of the group, right after it has published
+  // its own share: the whole warp waits for the group's 128 arrivals (converged), one elected lane
+  // issues and commits.  Issue blocks while the tensor pipe is busy, so the group's warps take turns.
+  // Consecutive stages of a tile are ordered by completion (commit -> wait -> publish); the groups
+  // only share the weight-gradient accumulators, where the in-order pipe makes every D += A B atomic.
+  uint32_t ph_ready = 0u;
   auto chain = [&](uint32_t d_col, uint32_t a_col, int b_off, uint32_t idesc) {
     const uint64_t db = smem_desc_sw128(sbase + b_off);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
   };
-  // d[feature i (+ ones row)][j] += sum over the tile's 128 pixels of X^T[i][px] dZ^T[j][px]   (fp16 operands)
-  auto wgrad = [&](uint32_t d_col, int xt_off, int dz_off, int dz_kb, uint32_t idesc, bool first) {
+  auto wgrad = [&](uint32_t d_col, int xt_off, int dz_off, int dz_kb, uint32_t idesc) {
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb) {
       const uint64_t da = smem_desc_sw128(sbase + xt_off + kb * Sm::XT_KB);
       const uint64_t db = smem_desc_sw128(sbase + dz_off + kb * dz_kb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(tmem_base + d_col, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first && kb == 0 && k == 0) ? 0u : 1u);
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_base + d_col, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
     }
   };
-  // stages of one tile: 0-2 sine layers, 3 output layer, 4-6 backward.  R0 = 64 s, R1 = 64 s + 32.
-  auto issue = [&](int s, int stage, bool first) {
-    const bool mine = warp == ((2 * stage + s) & 7);
+  // stages of one tile: 0-2 sine layers, 3 output layer, 4-6 backward
+  auto issue = [&](int stage) {
+    const bool mine = q == (stage & 3);
     if (mine) {
-      mbar_wait(&bar_ready[s], ph_ready[s]);
+      mbar_wait(&bar_ready[g], ph_ready);
       tc_fence_after();
     }
     if (mine && elect_one()) {
       const uint32_t t32 = idesc_tf32(32), t16 = idesc_tf32(16), h32 = idesc_f16(32), h16 = idesc_f16(16);
-      const uint32_t R0 = (uint32_t)(64 * s), R1 = R0 + 32;
-      const int so = s * Sm::SLOT;
       switch (stage) {
         case 0: chain(R1, R0, Sm::WF, t32); break;                              // Z0 = X0 W0
         case 1: chain(R0, R1, Sm::WF + 4096, t32); break;                       // Z1 = X1 W1
@@ -240,29 +263,24 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         case 3: chain(R0, R1, Sm::W3, t16); break;                              // y  = X3 W3
         case 4:
           chain(R0, R1, Sm::WB + 8192, t32);                                    // dX2 = dZ2 W2^T
-          wgrad(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, 2048, h16, first);      // dW3 = X3^T dy
-          wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, 4096, h32, first);      // dW2 = X2^T dZ2
+          wgrad(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, 2048, h16);             // dW3 = X3^T dy
+          wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, 4096, h32);             // dW2 = X2^T dZ2
           break;
         case 5:
           chain(R1, R0, Sm::WB + 4096, t32);                                    // dX1 = dZ1 W1^T
-          wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, 4096, h32, first);      // dW1 = X1^T dZ1
+          wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, 4096, h32);             // dW1 = X1^T dZ1
           break;
         default:
           chain(R0, R1, Sm::WB, t16);                                           // d pe = dZ0 W0[pe rows]^T
-          wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, 4096, h32, first);           // dW0 = X0^T dZ0
+          wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, 4096, h32);                  // dW0 = X0^T dZ0
           break;
       }
-      umma_commit(&bar_mma[s]);
+      umma_commit(&bar_mma[g]);
     }
-    ph_ready[s] ^= 1;
+    ph_ready ^= 1;
     __syncwarp();
   };
 
-  const int q = warp & 3;                 // TMEM lane quarter
-  const int hh = warp >> 2;               // which 16 of the 32 features
-  const int r = q * 32 + lane;            // pixel row inside the tile
-  const int j0 = hh * 16;
-  const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16);
   const float* xt = a.xt + (int64_t)row_item * a.x_row_stride;
   const bool stitched = a.pe_base != nullptr;
   const int64_t pe_origin = stitched ? a.pe_base[item] : (int64_t)item * pix;
@@ -276,218 +294,188 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // feature-major fp16 element of this thread's pixel: K block r / 64, column r % 64
   const uint32_t t_kb = (uint32_t)(q >> 1);
   const int t_col = (q & 1) * 32 + lane;
-  auto store_t = [&](uint32_t tile, int kb_bytes, const float (&v)[16]) {     // tile = address of K block 0
+  // rows f0 .. f0+15 of a feature-major tile <- v[0..15] (fp16, round to nearest)
+  auto store_t16 = [&](uint32_t tile, int kb_bytes, int f0, const float* v) {
     const uint32_t base = tile + t_kb * (uint32_t)kb_bytes;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sts16(base + swz2(j0 + j, t_col), __float2half_rn(v[j]));
-  };
-  // this thread's 16 input features of pixel gp: Fourier features (half 0) or positional encodings (half 1)
-  auto load_x0 = [&](int gp, uint32_t (&v)[16]) {
-    const bool ok = gp < pix;
-    if (hh == 0) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
-    } else {
-      const uint4* p = reinterpret_cast<const uint4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
-        v[c * 4] = t4.x; v[c * 4 + 1] = t4.y; v[c * 4 + 2] = t4.z; v[c * 4 + 3] = t4.w;
-      }
+    for (int j = 0; j < 16; j += 2) {
+      const uint32_t h2 = pack_h2(v[j], v[j + 1]);
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + swz2(f0 + j, t_col)), "h"((unsigned short)(h2 & 0xffffu)) : "memory");
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + swz2(f0 + j + 1, t_col)), "h"((unsigned short)(h2 >> 16)) : "memory");
     }
   };
-  auto publish = [&](int s, bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
-    tmem_st_wait();
-    PROF(310 + s);
-    if (smem_written) fence_async_smem();
-    PROF(320 + s);
-    tc_fence_before();
-    mbar_arrive(&bar_ready[s]);
-    PROF(300 + s);
+  // the 32 input features of pixel gp: 16 Fourier features, 16 positional encodings (raw fp32 patterns)
+  auto load_x0 = [&](int gp, uint32_t (&v)[32]) {
+    const bool ok = gp < pix;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
+    const uint4* p = reinterpret_cast<const uint4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
+      v[16 + c * 4] = t4.x; v[17 + c * 4] = t4.y; v[18 + c * 4] = t4.z; v[19 + c * 4] = t4.w;
+    }
   };
-  uint32_t ph_mma[2] = {0u, 0u};
-  int prof_stage[2] = {0, 0};
-  auto wait_mma = [&](int s) {
-    PROF(100 + prof_stage[s] * 10 + s);
-    mbar_wait(&bar_mma[s], ph_mma[s]);
-    ph_mma[s] ^= 1;
+  auto publish = [&](bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
+    tmem_st_wait();
+    if (smem_written) fence_async_smem();
+    tc_fence_before();
+    mbar_arrive(&bar_ready[g]);
+  };
+  uint32_t ph_mma = 0u;
+  auto wait_mma = [&]() {
+    mbar_wait(&bar_mma[g], ph_mma);
+    ph_mma ^= 1;
     tc_fence_after();
-    PROF(200 + prof_stage[s] * 10 + s);
-    prof_stage[s] = (prof_stage[s] + 1) % 7;
   };
   float sq = 0.f;
-  uint32_t xin[2][16];
-  load_x0(r, xin[0]);
-  if (ntiles > 1) load_x0(128 + r, xin[1]);
+  uint32_t xin[32];
+  if (g < ntiles) load_x0(g * 128 + r, xin);
 
-  for (int t0 = 0; t0 < ntiles; t0 += 2) {
-    const bool act1 = t0 + 1 < ntiles;
-    const bool first = t0 == 0;
-    uint32_t cs[2][3][8];                         // cos(.) of the three sine layers, packed half2
-    float dy[2][OUT];
+  for (int tile = g; tile < ntiles; tile += 2) {
+    const int gp = tile * 128 + r;
+    const bool valid = gp < pix;
+    uint32_t cs[3][16];                           // cos(.) of the three sine layers, packed half2
     // ---- X0 -> TMEM (R0)
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (s == 1 && !act1) continue;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) xin[s][i] += 0x1000u;                 // TF32 round-to-nearest of the inputs
-      tmem_st16(tm + (uint32_t)(64 * s) + j0, xin[s]);
-      publish(s, false);
-      issue(s, 0, first && s == 0);
-    }
+    for (int i = 0; i < 32; ++i) xin[i] += 0x1000u;                      // TF32 round-to-nearest of the inputs
+    tmem_st32(tm + R0, xin);
+    publish(false);
+    issue(0);
     // ---- three sine layers: X_{l+1} = sin(acc + b') back into the accumulator's columns, fp16 copy of X_{l+1}^T
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
+      const uint32_t reg = tm + ((l & 1) ? R0 : R1);                     // Z0 -> R1, Z1 -> R0, Z2 -> R1
+      wait_mma();
+      uint32_t acc[32];
+      tmem_ld32_issue(reg, acc);
+      tmem_ld_wait();
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (s == 1 && !act1) continue;
-        const uint32_t reg = tm + (uint32_t)(64 * s + ((l & 1) ? 0 : 32)) + j0;   // Z0 -> R1, Z1 -> R0, Z2 -> R1
-        wait_mma(s);
-        uint32_t acc[16];
-        tmem_ld16_issue(reg, acc);
-        tmem_ld_wait();
-        PROF(400 + s);
+      for (int h = 0; h < 2; ++h) {
         float x[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float z0 = __uint_as_float(acc[j]) + plain[l * 32 + j0 + j];
-          const float z1 = __uint_as_float(acc[j + 1]) + plain[l * 32 + j0 + j + 1];
+          const float z0 = __uint_as_float(acc[16 * h + j]) + plain[l * 32 + 16 * h + j];
+          const float z1 = __uint_as_float(acc[16 * h + j + 1]) + plain[l * 32 + 16 * h + j + 1];
           x[j] = __sinf(z0); x[j + 1] = __sinf(z1);
-          cs[s][l][j >> 1] = pack_h2(__cosf(z0), __cosf(z1));
-          acc[j] = rnd_tf32(x[j]); acc[j + 1] = rnd_tf32(x[j + 1]);
+          cs[l][(16 * h + j) >> 1] = pack_h2(__cosf(z0), __cosf(z1));
+          acc[16 * h + j] = rnd_tf32(x[j]); acc[16 * h + j + 1] = rnd_tf32(x[j + 1]);
         }
-        PROF(410 + s);
-        tmem_st16(reg, acc);
-        PROF(420 + s);
-        if (MODE != 0) store_t(sbase + s * Sm::SLOT + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), Sm::XT_KB, x);
-        PROF(430 + s);
-        publish(s, MODE != 0);
-        issue(s, l + 1, first && s == 0);
+        if (MODE != 0) store_t16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), Sm::XT_KB, 16 * h, x);
       }
+      tmem_st32(reg, acc);
+      publish(MODE != 0);
+      issue(l + 1);
     }
     // ---- output layer (on the tensor core), loss and dy; dZ2 = (dy W3^T) * cos in place of X3; dy^T, dZ2^T
+    wait_mma();
+    float dy[OUT];
+    {
+      uint32_t yv[16];
+      tmem_ld16_issue(tm + R0, yv);
+      tmem_ld_wait();
+      if (MODE == 0) {
+        if (valid)
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (s == 1 && !act1) continue;
-      const int gp = (t0 + s) * 128 + r;
-      const bool valid = gp < pix;
-      wait_mma(s);
-      {
-        uint32_t yv[16];
-        tmem_ld16_issue(tm + (uint32_t)(64 * s), yv);       // both halves of a row read the same columns
-        tmem_ld_wait();
-        if (MODE == 0) {
-          if (hh == 0 && valid)
+          for (int k = 0; k < OUT; ++k) a.y_pred[((int64_t)item * pix + gp) * OUT + k] = __uint_as_float(yv[k]) + plain[96 + k];
+      } else {
 #pragma unroll
-            for (int k = 0; k < OUT; ++k) a.y_pred[((int64_t)item * pix + gp) * OUT + k] = __uint_as_float(yv[k]) + plain[96 + k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < OUT; ++k) {
-            if (MODE == 1) {
-              const float rr = valid ? __uint_as_float(yv[k]) + plain[96 + k] - __ldg(a.y + ((int64_t)row_item * pix + gp) * OUT + k) : 0.f;
-              if (hh == 0) sq = fmaf(rr, rr, sq);
-              dy[s][k] = rr;
-            } else {
-              dy[s][k] = valid ? gscale * __ldg(a.dy + ((int64_t)item * pix + gp) * OUT + k) : 0.f;
-            }
+        for (int k = 0; k < OUT; ++k) {
+          if (MODE == 1) {
+            const float rr = valid ? __uint_as_float(yv[k]) + plain[96 + k] - __ldg(a.y + ((int64_t)row_item * pix + gp) * OUT + k) : 0.f;
+            sq = fmaf(rr, rr, sq);
+            dy[k] = rr;
+          } else {
+            dy[k] = valid ? gscale * __ldg(a.dy + ((int64_t)item * pix + gp) * OUT + k) : 0.f;
           }
         }
       }
-      if (MODE == 0) continue;
-      const int so = s * Sm::SLOT;
-      if (hh == 0) {
-#pragma unroll
-        for (int k = 0; k < OUT; ++k) sts16(sbase + so + Sm::DZ3 + t_kb * 2048 + swz2(k, t_col), __float2half_rn(dy[s][k]));
-      }
-      float dz[16];
-      uint32_t dzr[16];
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float2 c2 = unpack_h2(cs[s][2][j >> 1]);
-        const float4 wa = *(const float4*)(plain + 128 + (j0 + j) * 4);
-        const float4 wb = *(const float4*)(plain + 128 + (j0 + j + 1) * 4);
-        float va = dy[s][0] * wa.x, vb = dy[s][0] * wb.x;
-        if (OUT > 1) { va = fmaf(dy[s][1], wa.y, va); vb = fmaf(dy[s][1], wb.y, vb); }
-        if (OUT > 2) { va = fmaf(dy[s][2], wa.z, va); vb = fmaf(dy[s][2], wb.z, vb); }
-        dz[j] = va * c2.x; dz[j + 1] = vb * c2.y;
-        dzr[j] = rnd_tf32(dz[j]); dzr[j + 1] = rnd_tf32(dz[j + 1]);
-      }
-      tmem_st16(tm + (uint32_t)(64 * s + 32) + j0, dzr);    // R1: A operand of dX2
-      store_t(sbase + so + Sm::DZT, 4096, dz);
-      publish(s, true);
-      issue(s, 4, first && s == 0);
     }
-    if (MODE != 0) {
-      // ---- dZ1 (from R0, in place), dZ0 (from R1, in place) = data gradient * cos; X0^T reloaded for dW0
+    if (MODE == 0) {
+      if (tile + 2 < ntiles) load_x0(gp + 256, xin);
+      continue;
+    }
 #pragma unroll
-      for (int l = 1; l >= 0; --l) {
+    for (int k = 0; k < OUT; ++k) sts16(sbase + so + Sm::DZ3 + t_kb * 2048 + swz2(k, t_col), __float2half_rn(dy[k]));
+    {
+      uint32_t dzr[32];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (s == 1 && !act1) continue;
-          const int so = s * Sm::SLOT;
-          const uint32_t reg = tm + (uint32_t)(64 * s + (l == 1 ? 0 : 32)) + j0;
-          uint32_t x0[16];
-          if (l == 0) load_x0((t0 + s) * 128 + r, x0);        // in flight while the MMAs finish
-          wait_mma(s);
-          uint32_t acc[16];
-          tmem_ld16_issue(reg, acc);
-          tmem_ld_wait();
-          float dz[16];
+      for (int h = 0; h < 2; ++h) {
+        float dz[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float2 c2 = unpack_h2(cs[s][l][j >> 1]);
-            dz[j] = __uint_as_float(acc[j]) * c2.x; dz[j + 1] = __uint_as_float(acc[j + 1]) * c2.y;
-            acc[j] = rnd_tf32(dz[j]); acc[j + 1] = rnd_tf32(dz[j + 1]);
-          }
-          tmem_st16(reg, acc);
-          store_t(sbase + so + Sm::DZT, 4096, dz);
-          if (l == 0) {
-            float xf[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) xf[j] = __uint_as_float(x0[j]);
-            store_t(sbase + so + Sm::XT3, Sm::XT_KB, xf);
-          }
-          publish(s, true);
-          issue(s, l == 1 ? 5 : 6, first && s == 0);
+        for (int j = 0; j < 16; j += 2) {
+          const float2 c2 = unpack_h2(cs[2][(16 * h + j) >> 1]);
+          const float4 wa = *(const float4*)(plain + 128 + (16 * h + j) * 4);
+          const float4 wb = *(const float4*)(plain + 128 + (16 * h + j + 1) * 4);
+          float va = dy[0] * wa.x, vb = dy[0] * wb.x;
+          if (OUT > 1) { va = fmaf(dy[1], wa.y, va); vb = fmaf(dy[1], wb.y, vb); }
+          if (OUT > 2) { va = fmaf(dy[2], wa.z, va); vb = fmaf(dy[2], wb.z, vb); }
+          dz[j] = va * c2.x; dz[j + 1] = vb * c2.y;
+          dzr[16 * h + j] = rnd_tf32(dz[j]); dzr[16 * h + j + 1] = rnd_tf32(dz[j + 1]);
         }
+        store_t16(sbase + so + Sm::DZT, 4096, 16 * h, dz);
       }
+      tmem_st32(tm + R1, dzr);                                           // A operand of dX2
     }
-    // ---- the next pair's inputs travel while the last MMAs of this pair run
-    if (t0 + 2 < ntiles) load_x0((t0 + 2) * 128 + r, xin[0]);
-    if (t0 + 3 < ntiles) load_x0((t0 + 3) * 128 + r, xin[1]);
-    if (MODE == 0) continue;
-    // ---- d pe (16 columns of R0: 8 per half), back in true units
-    float dpe[2][8];
+    publish(true);
+    issue(4);
+    // ---- dZ1 (from R0, in place), dZ0 (from R1, in place) = data gradient * cos; X0^T reloaded for dW0
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (s == 1 && !act1) continue;
-      wait_mma(s);
-      uint32_t acc[16];
-      tmem_ld16_issue(tm + (uint32_t)(64 * s), acc);
+    for (int l = 1; l >= 0; --l) {
+      const uint32_t reg = tm + (l == 1 ? R0 : R1);
+      if (l == 0) load_x0(gp, xin);                                      // in flight while the MMAs finish
+      wait_mma();
+      uint32_t acc[32];
+      tmem_ld32_issue(reg, acc);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dpe[s][c] = unscale * __uint_as_float(hh ? acc[8 + c] : acc[c]);
-    }
-    // both halves of a pixel row read the same 16 columns, and the next pair's X0 goes into them:
-    // nobody may run ahead into the next pair before every thread has its d pe
-    tc_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    tc_fence_after();
+      for (int h = 0; h < 2; ++h) {
+        float dz[16];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (s == 1 && !act1) continue;
-      const int gp = (t0 + s) * 128 + r;
-      if (gp < pix) {
-        float* dst = a.d_pe + (pe_origin + pe_off(gp)) * NPE + hh * 8;
-        *(float4*)(dst) = make_float4(dpe[s][0], dpe[s][1], dpe[s][2], dpe[s][3]);
-        *(float4*)(dst + 4) = make_float4(dpe[s][4], dpe[s][5], dpe[s][6], dpe[s][7]);
+        for (int j = 0; j < 16; j += 2) {
+          const float2 c2 = unpack_h2(cs[l][(16 * h + j) >> 1]);
+          dz[j] = __uint_as_float(acc[16 * h + j]) * c2.x; dz[j + 1] = __uint_as_float(acc[16 * h + j + 1]) * c2.y;
+          acc[16 * h + j] = rnd_tf32(dz[j]); acc[16 * h + j + 1] = rnd_tf32(dz[j + 1]);
+        }
+        store_t16(sbase + so + Sm::DZT, 4096, 16 * h, dz);
+        if (l == 0) {
+          float xf[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xf[j] = __uint_as_float(xin[16 * h + j]);
+          store_t16(sbase + so + Sm::XT3, Sm::XT_KB, 16 * h, xf);
+        }
+      }
+      tmem_st32(reg, acc);
+      publish(true);
+      issue(l == 1 ? 5 : 6);
+    }
+    // ---- the group's next tile's inputs travel while the last MMAs of this tile run
+    if (tile + 2 < ntiles) load_x0(gp + 256, xin);
+    // ---- d pe (16 columns of R0), back in true units
+    wait_mma();
+    {
+      uint32_t acc[16];
+      tmem_ld16_issue(tm + R0, acc);
+      tmem_ld_wait();
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(a.d_pe + (pe_origin + pe_off(gp)) * NPE);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_float4(unscale * __uint_as_float(acc[4 * c]), unscale * __uint_as_float(acc[4 * c + 1]),
+                               unscale * __uint_as_float(acc[4 * c + 2]), unscale * __uint_as_float(acc[4 * c + 3]));
       }
     }
   }
 
   if (MODE != 0) {
-    // ---- weight gradients: TMEM lane i < 32 = input feature i, lane 32 = the ones row (bias)
-    float* g = a.d_wt + (int64_t)item * a.ld_w;
+    // both groups' MMAs have retired once every thread is here
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // ---- weight gradients: TMEM lane i < 32 = input feature i, lane 32 = the ones row (bias);
+    //      group 0's warps take columns 0-15, group 1's 16-31
+    float* gw = a.d_wt + (int64_t)item * a.ld_w;
+    const int j0 = g * 16;
     if (q == 0 || q == 1) {
       uint32_t acc[16];
       const float sc = w0 * unscale;
@@ -496,7 +484,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         tmem_ld16_issue(tm + TM_DW + (uint32_t)(l * 32 + j0), acc);
         tmem_ld_wait();
         const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
-        float* dst = q == 0 ? g + off + HID + lane * HID + j0 : g + off + j0;
+        float* dst = q == 0 ? gw + off + HID + lane * HID + j0 : gw + off + j0;
         if (q == 0 || lane == 0) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -504,26 +492,27 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
                                                   sc * __uint_as_float(acc[c * 4 + 2]), sc * __uint_as_float(acc[c * 4 + 3]));
         }
       }
-      if (hh == 0) {
+      if (g == 0) {
         tmem_ld16_issue(tm + TM_DW + 96, acc);
         tmem_ld_wait();
         if (q == 0) {
 #pragma unroll
-          for (int k = 0; k < OUT; ++k) g[off3 + OUT + lane * OUT + k] = unscale * __uint_as_float(acc[k]);
+          for (int k = 0; k < OUT; ++k) gw[off3 + OUT + lane * OUT + k] = unscale * __uint_as_float(acc[k]);
         } else if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < OUT; ++k) g[off3 + k] = unscale * __uint_as_float(acc[k]);
+          for (int k = 0; k < OUT; ++k) gw[off3 + k] = unscale * __uint_as_float(acc[k]);
         }
       }
     }
     if (MODE == 1) {
       sq = warp_sum(sq);
-      if (hh == 0 && lane == 0) plain[104 + q] = sq;
+      if (lane == 0) plain[104 + warp] = sq;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (MODE == 1 && threadIdx.x == 0) a.sqerr[item] = (plain[104] + plain[105]) + (plain[106] + plain[107]);
+  if (MODE == 1 && threadIdx.x == 0)
+    a.sqerr[item] = ((plain[104] + plain[105]) + (plain[106] + plain[107])) + ((plain[108] + plain[109]) + (plain[110] + plain[111]));
   if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
 }
 
@@ -544,16 +533,10 @@ static int launch(const rcb_mlp_args* a, cudaStream_t st) {
   return 0;
 }
 
-}  // namespace v3
+}  // namespace mlp
 }  // namespace rcb
 
 using namespace rcb;
-
-#ifdef RCB_MLP_PROFILE
-extern "C" int rcb_mlp_prof_read(long long* host) {
-  return (int)cudaMemcpyFromSymbol(host, rcb::v3::rcb_prof_buf, sizeof(long long) * 4 * 1024);
-}
-#endif
 
 extern "C" int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a != nullptr, "rcb_mlp_tc: null args");
@@ -568,8 +551,8 @@ extern "C" int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->ld_w % 4 == 0, "rcb_mlp_tc: ld_w must be a multiple of 4");
   RCB_CHECK_ARG(!a->pe_base || (a->ph > 0 && a->pw > 0), "rcb_mlp_tc: stitched addressing needs the patch extent");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->out == 3) return v3::launch<3>(a, st);
-  if (a->out == 1) return v3::launch<1>(a, st);
+  if (a->out == 3) return mlp::launch<3>(a, st);
+  if (a->out == 1) return mlp::launch<1>(a, st);
   set_error("rcb_mlp_tc: unsupported output width %d", a->out);
   return -2;
 }
