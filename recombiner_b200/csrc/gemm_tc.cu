@@ -4,9 +4,10 @@
 // fp32 in HBM, TF32 tensor-core math (kind::tf32), fp32 accumulation in TMEM.
 //
 // One CTA per 128 x BN output tile, warp-specialised:
-//   warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
+//   warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 3-stage mbarrier ring)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5: epilogue (tcgen05.ld 32x32b -> bias/activation -> global)
+//   warps 2-5: epilogue (tcgen05.ld 32x32b -> staged through the idle pipeline stages -> bias/activation ->
+//              coalesced global stores); two CTAs per SM
 // Both operands are K-major (A row-major [M,K]; B passed transposed as [N,K]); ragged M/N/K
 // edges are handled by TMA out-of-bounds zero fill plus guarded stores.
 #include "tc_common.cuh"
@@ -15,17 +16,21 @@ namespace rcb {
 
 constexpr int TC_BK = 32;            // 32 tf32 = 128 bytes = one swizzle row
 
+constexpr int GEMM_STAGES = 3;       // 3 x 32 KB: two CTAs per SM, one's epilogue under the other's main loop
+
 template <int BN>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 4;
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = TC_STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = GEMM_STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;   // barriers + slack for 1024-B alignment
+  static constexpr int EPI_LD = BN + 4;                // floats per staged accumulator row (conflict-free float4 rows)
+  static_assert(4 * 32 * EPI_LD * 4 <= BAR_OFF, "epilogue staging must fit the pipeline stages");
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     float* __restrict__ C, int ldc, int M, int N, int K,
                     const float* __restrict__ bias, int bias_mod, int act, int accumulate) {
@@ -33,8 +38,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* tmem_full = empty + TC_STAGES;
+  uint64_t* empty = full + GEMM_STAGES;
+  uint64_t* tmem_full = empty + GEMM_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -42,7 +47,7 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int nkb = (K + TC_BK - 1) / TC_BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -59,8 +64,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== TMA producer =====
     // whole warp converged, one elected lane issues (see elect_one)
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % TC_STAGES;
-      const uint32_t ph = (kb / TC_STAGES) & 1;
+      const int s = kb % GEMM_STAGES;
+      const uint32_t ph = (kb / GEMM_STAGES) & 1;
       mbar_wait(&empty[s], ph ^ 1);
       if (elect_one()) {
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
@@ -76,8 +81,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % TC_STAGES;
-      const uint32_t ph = (kb / TC_STAGES) & 1;
+      const int s = kb % GEMM_STAGES;
+      const uint32_t ph = (kb / GEMM_STAGES) & 1;
       mbar_wait(&full[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
@@ -95,12 +100,12 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> shared (row per lane) -> global (row per instruction) =====
+    // All MMAs and therefore all TMA fills are done when tmem_full fires: the pipeline stages are free.
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    float* crow = C + (int64_t)row * ldc;
+    float* wbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * S::EPI_LD;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -115,27 +120,36 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n >= N) break;
-          float o[4];
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(wbuf + lane * S::EPI_LD + c0 + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    __syncwarp();
+    // lanes walk a row: BN / 4 float4 chunks per row, 32 / (BN / 4) rows per instruction
+    constexpr int LPR = BN / 4;
+    constexpr int RPI = 32 / LPR;
+    const int sub = lane / LPR, n = n0 + (lane % LPR) * 4;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += RPI) {
+      const int rr = r0 + sub;
+      const int row = m0 + q * 32 + rr;
+      if (row < M && n < N) {
+        const float4 f4 = *reinterpret_cast<const float4*>(wbuf + rr * S::EPI_LD + (lane % LPR) * 4);
+        float o[4] = {f4.x, f4.y, f4.z, f4.w};
+        float* crow = C + (int64_t)row * ldc;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float x = __uint_as_float(v[j + t]);
-            if (n + t < N) {
-              if (accumulate) x += crow[n + t];
-              if (bias) x += bias[(n + t) % bias_mod];
-              if (act) x = x > 0.f ? x : 0.01f * x;
-            }
-            o[t] = x;
+        for (int t = 0; t < 4; ++t) {
+          if (n + t < N) {
+            if (accumulate) o[t] += crow[n + t];
+            if (bias) o[t] += bias[(n + t) % bias_mod];
+            if (act) o[t] = o[t] > 0.f ? o[t] : 0.01f * o[t];
           }
-          if (n + 4 <= N) {
-            *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int t = 0; t < 4 && n + t < N; ++t) crow[n + t] = o[t];
-          }
+        }
+        if (n + 4 <= N) {
+          *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int t = 0; t < 4 && n + t < N; ++t) crow[n + t] = o[t];
         }
       }
     }
