@@ -49,7 +49,8 @@ N_CAND = 65536
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/README.md); None where no capture exists yet
 TRAFFIC = {"mlp_fwd_bwd": 777.8e6,       # profiles/r1_ncu_full_mlp_tc_v2_sample_update.csv (1024 rows x S=5)
-           "update": 310.9e6, "sample": 157.7e6}
+           "update": 310.9e6, "sample": 157.7e6,
+           "conv3_fwd": 625.4e6, "conv2_fwd": 372.0e6}   # profiles/r1_ncu_full_v4.csv
 
 
 def schedule(G: int):
@@ -364,7 +365,15 @@ def run_b200(args):
                          "note": "operands are TF32 (half the bf16 rate): frac_of_tf32_peak uses peak/2; executed "
                                  "(polyphase) FLOPs; per-launch ms: "
                                  + ", ".join(f"{k}={v:.3f}" for k, v in sorted(timed.items(), key=lambda kv: -kv[1]))},
-            "rec": {"candidates_per_s": cand_per_s, "ms_per_round": t_round, "pairs_per_round": ROWS_PER_GPU * world},
+            # REC round: every (row, block) pair streams its D x 65536 f32 candidate table once
+            # (no reuse assumed) -> algorithmic bytes = rows * mean(D) * 65536 * 4
+            "rec": {"candidates_per_s": cand_per_s, "ms_per_round": t_round, "pairs_per_round": ROWS_PER_GPU * world,
+                    "roofline": {"bound": "hbm", "kernel": "rec_encode_kernel",
+                                 "achieved": ROWS_PER_GPU * (wl["P"] / G) * N_CAND * 4 / (t_round * 1e-3) / 1e9,
+                                 "peak": pk["hbm"], "unit": "GB/s",
+                                 "frac": ROWS_PER_GPU * (wl["P"] / G) * N_CAND * 4 / (t_round * 1e-3) / 1e9 / pk["hbm"],
+                                 "traffic": None, "peak_source": pk["src"] + " copy bandwidth",
+                                 "note": "table bytes of the mean block size; blocks picked per row by largest KL"}},
             "clocks": clk,
         }
         if cpu:
