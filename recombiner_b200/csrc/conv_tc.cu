@@ -9,6 +9,7 @@
 //   backward: d_src[item, s, :] = lrelu'(.) * sum_{r,tap,oc} d_out[item, (s - b_r - tap)*f + r, oc] * w_eff[r][tap][:][oc]
 //             one CTA = 128 source pixels, K = phases*taps*oc
 // Warp roles as in gemm_tc.cu.  Reference semantics: prior_model.py:47-59.
+#include <cstdlib>
 #include "gemm_engine.cuh"
 #include "tc_common.cuh"
 
@@ -178,6 +179,231 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
+
+// ------------------------------------------------------------------- forward, halo tile --
+// 2-D grids: one CTA = 8 x 16 source pixels of one item.  Per 32-channel k-block the (8+2) x (16+2)
+// neighbourhood is fetched ONCE (one 5-D TMA box of 18 lines x 10 pixels, image borders zero-filled) and
+// every (phase, tap) MMA reads its shifted 128 rows out of that tile through the shared-memory
+// descriptor alone: start address + (line, pixel) shift, 8-row groups 1280 B (= one line) apart.  The
+// 128-byte swizzle is a function of the absolute shared-memory address on both the TMA and the MMA
+// side, so a row-shifted start needs no base offset (checked on hardware).  A traffic drops from
+// (phases x taps) tiles per k-block to 2.25 tiles.  The weight tiles of all taps of one
+// (k-block, phase) travel as one ring stage (one barrier wait per 4 * taps MMAs), and the
+// single-thread loops carry no integer division.
+struct ConvHaloArgs {
+  PolyGeom g;
+  int items, tiles_x, tiles_y;
+  int phases_per_cta, kblocks;         // kblocks = ic / 32
+  int act;
+  int b_bytes, nbs;                    // weight ring: nbs stages of taps x (oc x 128 B)
+  int a_off, bar_off;                  // shared-memory layout
+  const float* bias;
+  float* out;
+};
+constexpr int HALO_LINES = 18, HALO_PITCH = 10;                 // (16 + 2) lines of (8 + 2) pixel rows
+constexpr int HALO_BYTES = HALO_LINES * HALO_PITCH * 128;       // 23040 per k-block
+constexpr int HALO_BUF = (HALO_BYTES + 1023) / 1024 * 1024;     // double-buffered, 1024-B aligned
+constexpr int HALO_NBS_MAX = 4;
+
+#ifdef RCB_CONV_PROFILE
+__device__ long long rcb_conv_prof[256];
+#define CPROF(i) do { if (blockIdx.x == 5000 && blockIdx.y == 0 && lane == 0) rcb_conv_prof[i] = clock64(); } while (0)
+#else
+#define CPROF(i) do {} while (0)
+#endif
+
+__global__ void __launch_bounds__(TC_THREADS)
+upconv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvHaloArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + a.bar_off);       // [2] halo tile landed
+  uint64_t* a_empty = a_full + 2;                          // [2] halo tile consumed
+  uint64_t* b_full = a_empty + 2;                          // [nbs]
+  uint64_t* b_empty = b_full + HALO_NBS_MAX;               // [nbs]
+  uint64_t* acc_full = b_empty + HALO_NBS_MAX;             // [1]
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1) CPROF(0);
+  const PolyGeom& g = a.g;
+  const int OC = g.oc;
+  int t = blockIdx.x;
+  const int x0 = (t % a.tiles_x) * 8; t /= a.tiles_x;
+  const int y0 = (t % a.tiles_y) * 16; t /= a.tiles_y;
+  const int item = t;
+  const int ph0 = blockIdx.y * a.phases_per_cta;
+  const int nph = min(a.phases_per_cta, g.phases() - ph0);
+  const int stage_bytes = 4 * a.b_bytes;                   // Ty * Tx = 4 taps
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < a.phases_per_cta * OC) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < a.nbs; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: halo tile per k-block, then the weight tiles of its phases (all taps per stage)
+    int s = 0;
+    uint32_t par = 1;                               // parity to wait on b_empty[s]: first lap passes
+    auto load_halo = [&](int kb) {
+      const int ab = kb & 1;
+      mbar_wait(&a_empty[ab], ((kb >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&a_full[ab], HALO_BYTES);
+        tma_load_5d(&tmA, &a_full[ab], smem + a.a_off + ab * HALO_BUF, kb * 32, x0 - 1, y0 - 1, 0, item);
+      }
+      __syncwarp();
+    };
+    load_halo(0);
+    for (int kb = 0; kb < a.kblocks; ++kb) {
+      if (kb + 1 < a.kblocks) load_halo(kb + 1);    // the next tile travels under this k-block's MMAs
+      for (int p = 0; p < nph; ++p) {
+        mbar_wait(&b_empty[s], par);
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[s], (uint32_t)stage_bytes);
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap)
+            tma_load_2d(&tmB, &b_full[s], smem + s * stage_bytes + tap * a.b_bytes, tap * g.ic + kb * 32, (ph0 + p) * OC);
+        }
+        __syncwarp();
+        if (++s == a.nbs) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    CPROF(1);
+    const uint32_t idesc = idesc_tf32(OC);
+    // descriptor template: K-major, 128-byte swizzle, 8-row groups one line (2048 B) apart
+    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    int s = 0;
+    uint32_t par = 0;
+    for (int kb = 0; kb < a.kblocks; ++kb) {
+      const int ab = kb & 1;
+      const uint32_t a_addr = smem_u32(smem + a.a_off + ab * HALO_BUF);
+      mbar_wait(&a_full[ab], (kb >> 1) & 1);
+      tc_fence_after();
+      CPROF(2 + kb * 40);
+      int ry = ph0 / g.fx, rx = ph0 - ry * g.fx;    // 2-D: phase = ry * fx + rx
+      for (int p = 0; p < nph; ++p) {
+        const int by = g.base_y(ry), bx = g.base_x(rx);
+        mbar_wait(&b_full[s], par);
+        tc_fence_after();
+        CPROF(3 + kb * 40 + p);
+        if (elect_one()) {
+          const uint32_t b_addr = smem_u32(smem + s * stage_bytes);
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap) {
+            const uint32_t shift_rows = (uint32_t)((1 + by + (tap >> 1)) * HALO_PITCH + (1 + bx + (tap & 1)));
+            const uint64_t da = da_hi | (uint64_t)(((a_addr + shift_rows * 128u) & 0x3FFFF) >> 4);
+            const uint64_t db = smem_desc_sw128(b_addr + tap * a.b_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | tap | k) ? 1u : 0u);
+          }
+          umma_commit(&b_empty[s]);
+          if (p == nph - 1) {
+            umma_commit(&a_empty[ab]);
+            if (kb == a.kblocks - 1) umma_commit(acc_full);
+          }
+        }
+        __syncwarp();
+        if (++s == a.nbs) { s = 0; par ^= 1; }
+        if (++rx == g.fx) { rx = 0; ++ry; }
+      }
+    }
+  } else {
+    // ===== epilogue: row m = (line m / 8, pixel m % 8) of the tile
+    const int q = warp & 3;
+    const int Wo = g.w * g.fx;
+    const int64_t row_pitch = (int64_t)Wo * OC;
+    if (warp == 2) CPROF(100);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (warp == 2) CPROF(101);
+    const int W = g.fx * OC;                               // floats one source pixel contributes to an output line
+    if (a.phases_per_cta % g.fx == 0 && W <= 128 && 128 % W == 0 && 4 * 32 * (W + 4) * 4 <= 2 * HALO_BUF) {
+      // All MMAs are done, so the halo buffers are free: each warp stages its 32 rows x (fx phases x OC) there and
+      // writes them back with consecutive lanes on consecutive 16-B chunks.  The fx phases of one output line are
+      // adjacent in memory (pixel 2x, 2x+1, ...), so a store instruction covers whole 128-byte lines.
+      const int ldw = W + 4;
+      float* wbuf = reinterpret_cast<float*>(smem + a.a_off) + (size_t)q * 32 * ldw;
+      const int lanes_per_row = W / 4, rows_per_iter = 32 / lanes_per_row;
+      const int sub = lane / lanes_per_row, ch = (lane % lanes_per_row) * 4;
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ch % OC));
+      int ry = ph0 / g.fx;
+      for (int p = 0; p < nph; p += g.fx, ++ry) {
+        for (int c0 = 0; c0 < W; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * OC + c0), v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(wbuf + lane * ldw + c0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+        __syncwarp();
+        for (int r0 = 0; r0 < 32; r0 += rows_per_iter) {
+          const int rr = r0 + sub, m = q * 32 + rr;
+          const int y = y0 + (m >> 3), x = x0 + (m & 7);
+          if (y < g.h && x < g.w) {
+            float4 f = *reinterpret_cast<const float4*>(wbuf + rr * ldw + ch);
+            f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+            if (a.act) {
+              f.x = f.x > 0.f ? f.x : 0.01f * f.x; f.y = f.y > 0.f ? f.y : 0.01f * f.y;
+              f.z = f.z > 0.f ? f.z : 0.01f * f.z; f.w = f.w > 0.f ? f.w : 0.01f * f.w;
+            }
+            float* dst = a.out + (((int64_t)item * g.h * g.fy + (int64_t)y * g.fy + ry) * Wo + (int64_t)x * g.fx) * OC + ch;
+            *reinterpret_cast<float4*>(dst) = f;
+          }
+        }
+        __syncwarp();
+      }
+    } else {
+      const int m = q * 32 + lane;
+      const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      const bool valid = y < g.h && x < g.w;
+      float* obase = a.out + (((int64_t)item * g.h * g.fy + (int64_t)y * g.fy) * Wo + (int64_t)x * g.fx) * OC;
+      int ry = ph0 / g.fx, rx = ph0 - ry * g.fx;
+      for (int p = 0; p < nph; ++p) {
+        float* orow = obase + ry * row_pitch + rx * OC;
+        for (int c0 = 0; c0 < OC; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * OC + c0), v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
+              float o[4] = {__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y,
+                            __uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w};
+              if (a.act) {
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) o[tt] = o[tt] > 0.f ? o[tt] : 0.01f * o[tt];
+              }
+              *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+        if (++rx == g.fx) { rx = 0; ++ry; }
+      }
+    }
+    if (warp == 2) CPROF(102);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) CPROF(103);
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+#ifdef RCB_CONV_PROFILE
+extern "C" int rcb_conv_prof_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, rcb::rcb_conv_prof, sizeof(long long) * 256); }
+#endif
 
 // ----------------------------------------------------------------------------- backward --
 template <int BK>   // 32: 128-byte rows / swizzle; 16: 64-byte rows / swizzle (oc = 16)
@@ -372,6 +598,36 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   RCB_CHECK_ARG(src && w_eff_k && bias && out, "rcb_upconv_fwd_tc: null pointer");
   RCB_CHECK_ARG(g.ic % 32 == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
   if (items <= 0) return 0;
+  if (g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
+    // 2-D grid with full 8 x 16 tiles: halo-tile kernel
+    ConvHaloArgs h;
+    h.g = g; h.items = items;
+    h.tiles_x = ceil_div(g.w, 8); h.tiles_y = ceil_div(g.h, 16);
+    int ppc = 256 / g.oc;                       // <= 256 TMEM columns: two CTAs per SM
+    if (ppc < 1) ppc = 1;
+    if (ppc > g.phases()) ppc = g.phases();
+    h.phases_per_cta = ppc;
+    h.kblocks = g.ic / 32;
+    h.act = act; h.bias = bias; h.out = out;
+    h.b_bytes = (g.oc * 128 + 1023) / 1024 * 1024;
+    h.nbs = 24576 / (4 * h.b_bytes);            // about 24 KB of weight ring, at least double-buffered
+    if (h.nbs > HALO_NBS_MAX) h.nbs = HALO_NBS_MAX;
+    if (h.nbs < 2) h.nbs = 2;
+    h.a_off = h.nbs * 4 * h.b_bytes;
+    h.bar_off = h.a_off + 2 * HALO_BUF;
+    const int smem_total = h.bar_off + 512 + 1024;
+    ConvTile box;                               // 16 x 18 pixels of one item
+    box.tx = HALO_PITCH; box.ty = HALO_LINES; box.tz = 1; box.ni = 1; box.ntx = box.nty = box.ntz = 1;
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, box, 32, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, 32,
+                            CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = opt_in_smem(upconv_fwd_halo_kernel, "rcb_upconv_fwd_tc")) return rc;
+    dim3 grid(h.tiles_x * h.tiles_y * items, ceil_div(g.phases(), ppc));
+    upconv_fwd_halo_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, h);
+    RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc");
+    return 0;
+  }
   ConvTcArgs a;
   a.g = g;
   a.t = choose_tile(g, items, 128, 128, 128);
