@@ -106,20 +106,21 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int rz, ry, rx;
       g.split_phase(ph0 + p, rz, ry, rx);
       const int bz = g.base_z(rz), by = g.base_y(ry), bx = g.base_x(rx);
-      for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
-        const int s = it % TC_STAGES;
-        mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
-        if (elect_one()) {
-          const int tap = kb / a.kblocks, c0 = (kb - tap * a.kblocks) * 32;
-          int tz, ty, tx;
-          g.split_tap(tap, tz, ty, tx);
-          uint8_t* a_dst = smem + s * a.stage_bytes;
-          mbar_expect_tx(&full[s], a_bytes + b_bytes);
-          tma_load_5d(&tmA, &full[s], a_dst, c0, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
-          tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * 32, (ph0 + p) * OC);
-        }
-        __syncwarp();
-      }
+      int kb = 0;
+      for (int tz = 0; tz < g.Tz; ++tz)
+        for (int ty = 0; ty < g.Ty; ++ty)
+          for (int tx = 0; tx < g.Tx; ++tx)
+            for (int cb = 0; cb < a.kblocks; ++cb, ++kb, ++it) {
+              const int s = it % TC_STAGES;
+              mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+              if (elect_one()) {
+                uint8_t* a_dst = smem + s * a.stage_bytes;
+                mbar_expect_tx(&full[s], a_bytes + b_bytes);
+                tma_load_5d(&tmA, &full[s], a_dst, cb * 32, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
+                tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * 32, (ph0 + p) * OC);
+              }
+              __syncwarp();
+            }
     }
   } else if (warp == 1) {
     const uint32_t idesc = idesc_tf32(OC);
@@ -441,25 +442,30 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % TC_STAGES;
-      mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
-      if (elect_one()) {
-        const int seg = it / a.kblocks, c0 = (it - seg * a.kblocks) * BK;
-        int tz, ty, tx, rz, ry, rx;
-        g.split_tap(seg % g.taps(), tz, ty, tx);
-        g.split_phase(seg / g.taps(), rz, ry, rx);
-        // output pixel feeding source pixel s through (phase, tap): (s - b - t) * f + r, stride f per source step
-        const int cx = (x0 - g.base_x(rx) - tx) * g.fx + rx;
-        const int cy = (y0 - g.base_y(ry) - ty) * g.fy + ry;
-        const int cz = (z0 - g.base_z(rz) - tz) * g.fz + rz;
-        uint8_t* a_dst = smem + s * a.stage_bytes;
-        mbar_expect_tx(&full[s], a_bytes + b_bytes);
-        tma_load_5d(&tmA, &full[s], a_dst, c0, cx, cy, cz, item0);
-        tma_load_2d(&tmB, &full[s], a_dst + a.b_off, c0, seg * IC);
-      }
-      __syncwarp();
-    }
+    // nested (phase, tap, k-block) counters: the single-thread loop carries no integer division
+    int it = 0, seg = 0;
+    for (int rz = 0; rz < g.fz; ++rz)
+      for (int ry = 0; ry < g.fy; ++ry)
+        for (int rx = 0; rx < g.fx; ++rx)
+          for (int tz = 0; tz < g.Tz; ++tz)
+            for (int ty = 0; ty < g.Ty; ++ty)
+              for (int tx = 0; tx < g.Tx; ++tx, ++seg) {
+                // output pixel feeding source pixel s through (phase, tap): (s - b - t) * f + r, stride f per source step
+                const int cx = (x0 - g.base_x(rx) - tx) * g.fx + rx;
+                const int cy = (y0 - g.base_y(ry) - ty) * g.fy + ry;
+                const int cz = (z0 - g.base_z(rz) - tz) * g.fz + rz;
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                  const int s = it % TC_STAGES;
+                  mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+                  if (elect_one()) {
+                    uint8_t* a_dst = smem + s * a.stage_bytes;
+                    mbar_expect_tx(&full[s], a_bytes + b_bytes);
+                    tma_load_5d(&tmA, &full[s], a_dst, kb * BK, cx, cy, cz, item0);
+                    tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * BK, seg * IC);
+                  }
+                  __syncwarp();
+                }
+              }
   } else if (warp == 1) {
     const uint32_t idesc = idesc_tf32(IC);
     for (int it = 0; it < nkb; ++it) {
