@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
 // the row's posterior (group order) is staged once in shared memory, then every (sample,
 // parameter) output is written coalesced, four Philox normals per block.
 // dynamic smem: 4 * P floats.
-__global__ void __launch_bounds__(256) sample_rows_kernel(rcb_sample_args a) {
+__global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) {
   extern __shared__ float sm[];
   float* s_mu = sm;                 // parameter order
   float* s_sig = sm + a.P;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(rcb_sample_args a) {
 // in parameter order (coalesced) into shared memory, then the KL gradient + Adam runs in group
 // order (coalesced on the stored state).  Same arithmetic order as update_kernel.
 // dynamic smem: 2 * P floats.
-__global__ void __launch_bounds__(256) update_rows_kernel(rcb_update_args a) {
+__global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) {
   extern __shared__ float sm[];
   float* s_dmu = sm;
   float* s_dsig = sm + a.P;

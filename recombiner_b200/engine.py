@@ -166,6 +166,10 @@ class FitEngine:
         self.tc = self.precision == "tf32"
         self.tc_conv = self.tc and os.environ.get("RECOMBINER_TC_CONV", "1") != "0"
         self.tc_mlp = self.tc and os.environ.get("RECOMBINER_TC_MLP", "1") != "0"
+        # the reparameterisation GEMMs (hw <-> wt) and the upsampler chain (lpe <-> pe) are independent
+        # between the sampling kernel and the MLP: run them on two streams
+        self.overlap = os.environ.get("RECOMBINER_OVERLAP", "1") != "0"
+        self._side = None
         if not torch.cuda.is_available():
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -399,10 +403,13 @@ class FitEngine:
         with self.section("sample"):
             for l in levels:
                 self._sample(l, ws, S, noise, rows)
-        with self.section("reparam_fwd"):
-            for l, c in enumerate(self.counts):
-                self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
-                           ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
+
+        def reparam():
+            with self.section("reparam_fwd"):
+                for l, c in enumerate(self.counts):
+                    self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
+                               ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
+        join = self._fork(reparam)
         g1, g2, g3 = self.geoms
         with self.section("conv1_fwd"):
             if self.dense1:
@@ -415,7 +422,25 @@ class FitEngine:
             self._upconv_fwd(1, ws["a1"], ws["a2"], citems, 1)
         with self.section("conv3_fwd"):
             self._upconv_fwd(2, ws["a2"], ws["pe"], citems, 0)
+        join()
         return ws
+
+    def _fork(self, fn):
+        """Run fn on the side stream, ordered after everything queued so far on the current stream;
+        returns the join that makes the current stream wait for it."""
+        if not self.overlap:
+            fn()
+            return lambda: None
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_fork)
+            fn()
+            self._ev_join.record(self._side)
+        return lambda: main.wait_event(self._ev_join)
 
     def mlp(self, ws, rows: int, S: int, x, mode: int, y=None, dy=None, coef: float = 0.0):
         xt, stride = self.prepare_x(x)
@@ -447,6 +472,13 @@ class FitEngine:
         citems = ws["citems"]
         st = stream()
         g1, g2, g3 = self.geoms
+
+        def reparam():
+            with self.section("reparam_bwd"):
+                for l, c in enumerate(self.counts):
+                    self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
+                               ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])
+        join = self._fork(reparam)
         with self.section("conv3_bwd"):
             self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
         with self.section("conv2_bwd"):
@@ -458,10 +490,7 @@ class FitEngine:
                            citems, Lt, self.M1T.shape[0], Bt=self.M1)
             else:
                 self._upconv_bwd(0, ws["d_a1"], None, ws["d_lpe"], citems)
-        with self.section("reparam_bwd"):
-            for l, c in enumerate(self.counts):
-                self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
-                           ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])
+        join()
 
     def backward_mappings(self, ws, rows: int, S: int):
         """Gradients of the learned mappings (prior training): dA_l = hw_l^T d_wt_l, and the
