@@ -132,7 +132,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -301,28 +301,60 @@ def run_b200(args):
     barrier()
     t_round = r0.elapsed_time(r1) / n_rounds
     launches += _lib.COUNTERS["launches"]
-    clk = clocks.stop() if clocks else None
 
-    # ---- end to end through the public call with HOST buffers: each step uploads that
-    # step's inputs from pinned memory and reads the step's loss terms back
+    # ---- end to end through the public call with HOST buffers.  Every step uploads that step's
+    # inputs from pinned memory and brings the step's loss terms back to the host; the transfers
+    # run on a copy stream, double-buffered, so step k+1's upload and step k-1's read-back travel
+    # under step k's kernels (the host reads each step's result one step late).
     ws = m.engine.workspace(ROWS_PER_GPU, S)
-    sq_host = torch.empty(ROWS_PER_GPU * S).pin_memory()
-    y_dev, x_dev = torch.empty_like(y), torch.empty(1, *x.shape[1:], device=dev)
+    sq_host = [torch.empty(ROWS_PER_GPU * S).pin_memory() for _ in range(2)]
+    sq_stage = [torch.empty(ROWS_PER_GPU * S, device=dev) for _ in range(2)]
+    y_dev = [torch.empty_like(y) for _ in range(2)]
+    x_dev = [torch.empty(1, *x.shape[1:], device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    step_done = [torch.cuda.Event() for _ in range(2)]
+    back_done = [torch.cuda.Event() for _ in range(2)]
+    loss_sum = 0.0
+
+    def upload(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(step_done[b])          # the step that last read these buffers is over
+            x_dev[b].copy_(x_host, non_blocking=True)
+            y_dev[b].copy_(y_host, non_blocking=True)
+            up_done[b].record(copy_stream)
+
     barrier()
+    for ev in step_done:
+        ev.record(main_stream)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(K):
-        x_dev.copy_(x_host, non_blocking=True)
-        y_dev.copy_(y_host, non_blocking=True)
-        m.fit_step(x_dev.expand(ROWS_PER_GPU, -1, -1), y_dev, step_no[0], cfg, S)
+    upload(0)
+    for k in range(K):
+        b = k & 1
+        if k + 1 < K:
+            upload(b ^ 1)
+        main_stream.wait_event(up_done[b])
+        m.fit_step(x_dev[b].expand(ROWS_PER_GPU, -1, -1), y_dev[b], step_no[0], cfg, S)
         step_no[0] += 1
-        sq_host.copy_(ws["sqerr"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        sq_stage[b].copy_(ws["sqerr"], non_blocking=True)
+        step_done[b].record(main_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(step_done[b])
+            sq_host[b].copy_(sq_stage[b], non_blocking=True)
+            back_done[b].record(copy_stream)
+        if k > 0:                                         # the previous step's loss terms, on the host
+            back_done[b ^ 1].synchronize()
+            loss_sum += float(sq_host[b ^ 1][0])
+    back_done[(K - 1) & 1].synchronize()
+    loss_sum += float(sq_host[(K - 1) & 1][0])
     f1.record()
     barrier()
+    clk = clocks.stop() if clocks else None            # sampled over the fit, REC and end-to-end regions
     t_e2e = f0.elapsed_time(f1) / K
     h2d = x_host.numel() * 4 + y_host.numel() * 4
-    d2h = sq_host.numel() * 4
+    d2h = sq_host[0].numel() * 4
 
     times = torch.tensor([t_fit, t_round, t_e2e], device=dev, dtype=torch.float64)
     if world > 1:
