@@ -418,6 +418,7 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = (uint32_t*)(acc_full + CT_MAX_PHASES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1) CPROF(0);
   const PolyGeom& g = a.g;
   const int IC = g.ic;                                     // N of this GEMM
   int item0, z0, y0, x0;
@@ -467,11 +468,13 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
               }
   } else if (warp == 1) {
+    CPROF(1);
     const uint32_t idesc = idesc_tf32(IC);
     for (int it = 0; it < nkb; ++it) {
       const int s = it % TC_STAGES;
       mbar_wait(&full[s], (it / TC_STAGES) & 1);
       tc_fence_after();
+      if (it < 90) CPROF(2 + it);
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
         const uint64_t da = BK == 32 ? smem_desc_sw128(a_addr) : smem_desc_sw64(a_addr);
@@ -489,13 +492,32 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int r = q * 32 + lane;
     int item, z, y, x;
     const bool valid = tile_row(a, r, item0, z0, y0, x0, item, z, y, x);
+    // Walk order of the coalesced write-back: consecutive lanes on consecutive 16-B chunks of a row.
+    const int64_t m = valid ? (((int64_t)item * g.d + z) * g.h + y) * g.w + x : -1;
+    const int lanes_per_row = IC / 4;                        // 16-B chunks per row: 4, 16 or 32
+    const int rows_per_iter = 32 / lanes_per_row;
+    const int sub = lane / lanes_per_row, ch = (lane % lanes_per_row) * 4;
+    // The LeakyReLU mask of the producing stage does not depend on the MMAs: fetch it while they run and
+    // keep one bit per element (4 bits per walk step).
+    uint64_t lrelu_bits[2] = {0ull, 0ull};
+    if (a.src_act) {
+      int step = 0;
+      for (int r0 = 0; r0 < 32; r0 += rows_per_iter, ++step) {
+        const int64_t mm = __shfl_sync(0xffffffffu, m, (r0 + sub) & 31);
+        if (sub < rows_per_iter && mm >= 0) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch));
+          const uint64_t b = (uint64_t)((s4.x > 0.f ? 1u : 0u) | (s4.y > 0.f ? 2u : 0u) | (s4.z > 0.f ? 4u : 0u) | (s4.w > 0.f ? 8u : 0u));
+          lrelu_bits[step >> 4] |= b << ((step & 15) * 4);
+        }
+      }
+    }
+    if (warp == 2) CPROF(100);
     mbar_wait(&acc_full[0], 0);
     tc_fence_after();
+    if (warp == 2) CPROF(101);
     // All MMAs (and therefore all TMA fills) are done: the pipeline stages are free.  Each warp
     // stages its 32 x IC accumulator rows there (row-per-lane out of TMEM, padded rows), then
-    // walks them again with consecutive lanes on consecutive 16-B chunks of a row, so the
-    // activation-mask loads and the gradient stores are coalesced.
-    const int64_t m = valid ? (((int64_t)item * g.d + z) * g.h + y) * g.w + x : -1;
+    // walks them again so that the gradient stores are coalesced.
     const int ldw = IC + 4;                                 // floats per staged row (bank-conflict-free float4 rows)
     float* wbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * ldw;
     for (int c0 = 0; c0 < IC; c0 += 16) {
@@ -507,22 +529,21 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
     }
     __syncwarp();
-    const int lanes_per_row = IC / 4;                        // 16-B chunks per row: 4, 16 or 32
-    const int rows_per_iter = 32 / lanes_per_row;
-    const int sub = lane / lanes_per_row, ch = (lane % lanes_per_row) * 4;
-    for (int r0 = 0; r0 < 32; r0 += rows_per_iter) {
+    int step = 0;
+    for (int r0 = 0; r0 < 32; r0 += rows_per_iter, ++step) {
       const int rr = r0 + sub;
       const int64_t mm = __shfl_sync(0xffffffffu, m, rr & 31);
       if (sub < rows_per_iter && mm >= 0) {
         float4 f = *reinterpret_cast<const float4*>(wbuf + rr * ldw + ch);
         if (a.src_act) {
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch));
-          f.x *= (s4.x > 0.f ? 1.f : 0.01f); f.y *= (s4.y > 0.f ? 1.f : 0.01f);
-          f.z *= (s4.z > 0.f ? 1.f : 0.01f); f.w *= (s4.w > 0.f ? 1.f : 0.01f);
+          const uint32_t b = (uint32_t)(lrelu_bits[step >> 4] >> ((step & 15) * 4));
+          f.x *= (b & 1u) ? 1.f : 0.01f; f.y *= (b & 2u) ? 1.f : 0.01f;
+          f.z *= (b & 4u) ? 1.f : 0.01f; f.w *= (b & 8u) ? 1.f : 0.01f;
         }
         *reinterpret_cast<float4*>(a.out + mm * IC + ch) = f;
       }
     }
+    if (warp == 2) CPROF(102);
   }
   tc_fence_before();
   __syncthreads();
