@@ -501,13 +501,22 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // keep one bit per element (4 bits per walk step).
     uint64_t lrelu_bits[2] = {0ull, 0ull};
     if (a.src_act) {
-      int step = 0;
-      for (int r0 = 0; r0 < 32; r0 += rows_per_iter, ++step) {
-        const int64_t mm = __shfl_sync(0xffffffffu, m, (r0 + sub) & 31);
-        if (sub < rows_per_iter && mm >= 0) {
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch));
-          const uint64_t b = (uint64_t)((s4.x > 0.f ? 1u : 0u) | (s4.y > 0.f ? 2u : 0u) | (s4.z > 0.f ? 4u : 0u) | (s4.w > 0.f ? 8u : 0u));
-          lrelu_bits[step >> 4] |= b << ((step & 15) * 4);
+      const int nsteps = 32 / rows_per_iter;
+      for (int s0 = 0; s0 < nsteps; s0 += 8) {            // eight loads in flight per lane
+        float4 s4[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = (s0 + u) * rows_per_iter + sub;
+          const int64_t mm = __shfl_sync(0xffffffffu, m, rr & 31);
+          s4[u] = (s0 + u < nsteps && sub < rows_per_iter && mm >= 0)
+                      ? __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int step = s0 + u;
+          const uint64_t b = (uint64_t)((s4[u].x > 0.f ? 1u : 0u) | (s4[u].y > 0.f ? 2u : 0u) | (s4[u].z > 0.f ? 4u : 0u) | (s4[u].w > 0.f ? 8u : 0u));
+          if (step < 16) lrelu_bits[0] |= b << ((step & 15) * 4);
+          else lrelu_bits[1] |= b << ((step & 15) * 4);
         }
       }
     }
@@ -536,7 +545,7 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (sub < rows_per_iter && mm >= 0) {
         float4 f = *reinterpret_cast<const float4*>(wbuf + rr * ldw + ch);
         if (a.src_act) {
-          const uint32_t b = (uint32_t)(lrelu_bits[step >> 4] >> ((step & 15) * 4));
+          const uint32_t b = (uint32_t)((step < 16 ? lrelu_bits[0] : lrelu_bits[1]) >> ((step & 15) * 4));
           f.x *= (b & 1u) ? 1.f : 0.01f; f.y *= (b & 2u) ? 1.f : 0.01f;
           f.z *= (b & 4u) ? 1.f : 0.01f; f.w *= (b & 8u) ? 1.f : 0.01f;
         }
