@@ -29,6 +29,7 @@ struct ConvTcArgs {
   int bk;                        // 32 (128B swizzle) or 16 (64B swizzle)
   int act;
   int b_off, stage_bytes, bar_off;   // shared-memory layout (bytes): B tile offset in a stage, stage size, barriers
+  int nstages, epi_off;              // forward: ring depth and the epilogue staging area (4 warps x 32 x (oc + 4) floats)
   const float* bias;             // forward
   const float* src_act;          // backward (post-activation of the producing stage) or NULL
   float* out;
@@ -38,12 +39,14 @@ constexpr int CT_MAX_PHASES = 16;
 
 // stage = [A tile: 128 rows x row_bytes][B tile: n rows x row_bytes], both 1024-B aligned; sized per
 // problem so that several CTAs fit on an SM (their prologues/epilogues overlap the others' main loops)
-static void smem_layout(ConvTcArgs* a, int row_bytes, int b_rows, int* total) {
+static void smem_layout(ConvTcArgs* a, int row_bytes, int b_rows, int* total, int nstages = TC_STAGES, int epi_bytes = 0) {
   int a_bytes = (TC_BM * row_bytes + 1023) / 1024 * 1024;
   int b_bytes = (b_rows * row_bytes + 1023) / 1024 * 1024;
   a->b_off = a_bytes;
   a->stage_bytes = a_bytes + b_bytes;
-  a->bar_off = TC_STAGES * a->stage_bytes;
+  a->nstages = nstages;
+  a->epi_off = nstages * a->stage_bytes;
+  a->bar_off = a->epi_off + (epi_bytes + 1023) / 1024 * 1024;
   *total = a->bar_off + 512 + 1024;
 }
 
@@ -89,7 +92,7 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   while ((int)tmem_cols < a.phases_per_cta * OC) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < a.nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }   // nstages <= TC_STAGES
     for (int p = 0; p < CT_MAX_PHASES; ++p) mbar_init(&acc_full[p], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -101,7 +104,8 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   // warps 0 and 1 stay converged; one elected lane issues the TMA loads / MMAs (see elect_one)
   if (warp == 0) {
-    int it = 0;
+    int s = 0;
+    uint32_t par = 1;
     for (int p = 0; p < nph; ++p) {
       int rz, ry, rx;
       g.split_phase(ph0 + p, rz, ry, rx);
@@ -110,9 +114,8 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tz = 0; tz < g.Tz; ++tz)
         for (int ty = 0; ty < g.Ty; ++ty)
           for (int tx = 0; tx < g.Tx; ++tx)
-            for (int cb = 0; cb < a.kblocks; ++cb, ++kb, ++it) {
-              const int s = it % TC_STAGES;
-              mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+            for (int cb = 0; cb < a.kblocks; ++cb, ++kb) {
+              mbar_wait(&empty[s], par);
               if (elect_one()) {
                 uint8_t* a_dst = smem + s * a.stage_bytes;
                 mbar_expect_tx(&full[s], a_bytes + b_bytes);
@@ -120,15 +123,16 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * 32, (ph0 + p) * OC);
               }
               __syncwarp();
+              if (++s == a.nstages) { s = 0; par ^= 1; }
             }
     }
   } else if (warp == 1) {
     const uint32_t idesc = idesc_tf32(OC);
-    int it = 0;
+    int s = 0;
+    uint32_t par = 0;
     for (int p = 0; p < nph; ++p) {
-      for (int kb = 0; kb < kb_per_phase; ++kb, ++it) {
-        const int s = it % TC_STAGES;
-        mbar_wait(&full[s], (it / TC_STAGES) & 1);
+      for (int kb = 0; kb < kb_per_phase; ++kb) {
+        mbar_wait(&full[s], par);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
@@ -140,6 +144,7 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (kb == kb_per_phase - 1) umma_commit(&acc_full[p]);
         }
         __syncwarp();
+        if (++s == a.nstages) { s = 0; par ^= 1; }
       }
     }
   } else {
@@ -148,32 +153,56 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int item, z, y, x;
     const bool valid = tile_row(a, r, item0, z0, y0, x0, item, z, y, x);
     const int Ho = g.h * g.fy, Wo = g.w * g.fx, Do = g.d * g.fz;
+    // element offset of this row's phase-(0,0,0) output pixel, or -1
+    const int64_t base0 = valid ? ((((int64_t)item * Do + (int64_t)z * g.fz) * Ho + (int64_t)y * g.fy) * Wo + (int64_t)x * g.fx) * OC : -1;
+    // Each warp stages its 32 x OC accumulator rows of a phase in its own shared-memory area (row per lane out of
+    // TMEM), then writes them back with consecutive lanes on consecutive 16-B chunks of a row: whole 128-byte
+    // lines per store instruction instead of 32 scattered ones.
+    const int ldw = OC + 4;
+    float* wbuf = reinterpret_cast<float*>(smem + a.epi_off) + (size_t)q * 32 * ldw;
+    const int lanes_per_row = OC / 4, rows_per_iter = 32 / lanes_per_row;
+    const int sub = lane / lanes_per_row, ch = (lane % lanes_per_row) * 4;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ch));
     for (int p = 0; p < nph; ++p) {
-      mbar_wait(&acc_full[p], 0);
-      tc_fence_after();
       int rz, ry, rx;
       g.split_phase(ph0 + p, rz, ry, rx);
-      float* orow = nullptr;
-      if (valid) {
-        const int oz = z * g.fz + rz, oy = y * g.fy + ry, ox = x * g.fx + rx;
-        orow = a.out + ((((int64_t)item * Do + oz) * Ho + oy) * Wo + ox) * OC;
-      }
+      const int64_t ph_off = (((int64_t)rz * Ho + ry) * Wo + rx) * OC;
+      mbar_wait(&acc_full[p], 0);
+      tc_fence_after();
       for (int c0 = 0; c0 < OC; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * OC + c0), v);
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float o[4];
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(wbuf + lane * ldw + c0 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+      __syncwarp();
+      // four walk steps per trip: the shuffles and shared-memory loads of all four are issued before the stores
+      for (int r0 = 0; r0 < 32; r0 += 4 * rows_per_iter) {
+        float4 f[4];
+        int64_t bb[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float f = __uint_as_float(v[j + t]) + a.bias[c0 + j + t];
-              o[t] = a.act ? (f > 0.f ? f : 0.01f * f) : f;
+        for (int u = 0; u < 4; ++u) {
+          const int rr = r0 + u * rows_per_iter + sub;
+          bb[u] = __shfl_sync(0xffffffffu, base0, rr & 31);
+          if (sub >= rows_per_iter || rr >= 32) bb[u] = -1;
+          f[u] = *reinterpret_cast<const float4*>(wbuf + (rr & 31) * ldw + ch);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (bb[u] >= 0) {
+            float4 o = f[u];
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (a.act) {
+              o.x = o.x > 0.f ? o.x : 0.01f * o.x; o.y = o.y > 0.f ? o.y : 0.01f * o.y;
+              o.z = o.z > 0.f ? o.z : 0.01f * o.z; o.w = o.w > 0.f ? o.w : 0.01f * o.w;
             }
-            *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(a.out + bb[u] + ph_off + ch) = o;
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -538,21 +567,30 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
     }
     __syncwarp();
-    int step = 0;
-    for (int r0 = 0; r0 < 32; r0 += rows_per_iter, ++step) {
-      const int rr = r0 + sub;
-      const int64_t mm = __shfl_sync(0xffffffffu, m, rr & 31);
-      if (sub < rows_per_iter && mm >= 0) {
-        float4 f = *reinterpret_cast<const float4*>(wbuf + rr * ldw + ch);
-        if (a.src_act) {
-          const uint32_t b = (uint32_t)((step < 16 ? lrelu_bits[0] : lrelu_bits[1]) >> ((step & 15) * 4));
-          f.x *= (b & 1u) ? 1.f : 0.01f; f.y *= (b & 2u) ? 1.f : 0.01f;
-          f.z *= (b & 4u) ? 1.f : 0.01f; f.w *= (b & 8u) ? 1.f : 0.01f;
+    for (int s0 = 0; s0 * rows_per_iter < 32; s0 += 4) {
+      float4 f[4];
+      int64_t mm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = (s0 + u) * rows_per_iter + sub;
+        mm[u] = __shfl_sync(0xffffffffu, m, rr & 31);
+        if (sub >= rows_per_iter || rr >= 32) mm[u] = -1;
+        f[u] = *reinterpret_cast<const float4*>(wbuf + (rr & 31) * ldw + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (mm[u] >= 0) {
+          float4 o = f[u];
+          if (a.src_act) {
+            const int step = s0 + u;
+            const uint32_t b = (uint32_t)((step < 16 ? lrelu_bits[0] : lrelu_bits[1]) >> ((step & 15) * 4));
+            o.x *= (b & 1u) ? 1.f : 0.01f; o.y *= (b & 2u) ? 1.f : 0.01f;
+            o.z *= (b & 4u) ? 1.f : 0.01f; o.w *= (b & 8u) ? 1.f : 0.01f;
+          }
+          *reinterpret_cast<float4*>(a.out + mm[u] * IC + ch) = o;
         }
-        *reinterpret_cast<float4*>(a.out + mm * IC + ch) = f;
       }
     }
-    if (warp == 2) CPROF(102);
   }
   tc_fence_before();
   __syncthreads();
@@ -676,7 +714,7 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   a.bk = 32;
   a.act = act; a.bias = bias; a.src_act = nullptr; a.out = out;
   int smem_total;
-  smem_layout(&a, 128, g.oc, &smem_total);
+  smem_layout(&a, 128, g.oc, &smem_total, 3, 4 * 32 * (g.oc + 4) * 4);
   CUtensorMap tmA, tmB;
   if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, a.t, 32, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, 32,
