@@ -49,7 +49,7 @@ struct Sm {
   static constexpr int TOTAL = BAR + 64;
 };
 static_assert(Sm::SLOT % 1024 == 0 && Sm::WF % 1024 == 0 && Sm::W3 % 1024 == 0, "swizzled tiles need 1024-B alignment");
-static_assert(Sm::SLOT + Sm::XT3 + Sm::XT_KB + 128 * 128 <= Sm::BAR, "M=128 reads past the last A tile must stay in the allocation");
+static_assert(Sm::SLOT + Sm::XT3 + Sm::XT_KB + 64 * 128 <= Sm::BAR, "M=64 reads past the last A tile must stay in the allocation");
 
 // byte offset of element (row, col) in a tile of 128-byte rows with the 128-byte swizzle; 4- and 2-byte elements
 __device__ __forceinline__ uint32_t swz4(int row, int col) {
@@ -105,9 +105,10 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 64 (the weight-gradient tiles have 33 useful
+// rows: half the shared-memory reads of M = 128).  Accumulator row i lives in TMEM lane (i % 16) + 32 * (i / 16).
 __device__ __forceinline__ uint32_t idesc_f16(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
@@ -138,8 +139,26 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       : "memory");
 }
 
+#ifdef RCB_MLP_PROFILE
+__device__ long long rcb_prof_buf[4 * 1024];
+#define PROF(id)                                                                         \
+  do {                                                                                   \
+    if (prof_slot >= 0 && prof_n < 511) {                                                \
+      rcb_prof_buf[prof_slot * 1024 + 2 * prof_n] = (id);                                \
+      rcb_prof_buf[prof_slot * 1024 + 2 * prof_n + 1] = clock64();                       \
+      ++prof_n;                                                                          \
+    }                                                                                    \
+  } while (0)
+#else
+#define PROF(id) do {} while (0)
+#endif
+
 template <int OUT, int MODE>
 __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
+#ifdef RCB_MLP_PROFILE
+  int prof_n = 0;
+  const int prof_slot = (blockIdx.x == 3000 && (threadIdx.x == 32 || threadIdx.x == 160)) ? (threadIdx.x == 32 ? 0 : 1) : -1;
+#endif
   constexpr int F = 16, HID = 32, NPE = 16;
   constexpr int off0 = 0, off1 = HID * (32 + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -160,6 +179,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   const float gscale = MODE == 2 ? (a.coef > 0.f ? a.coef : 1.f) : 1.f;
   const float unscale = MODE == 1 ? a.coef : 1.f / gscale;
 
+  PROF(1);
   if ((sbase & 1023u) != 0u) __trap();                     // the swizzled tiles assume a 1024-B aligned window
   if (threadIdx.x == 0) {
     mbar_init(&bar_ready[0], MT_GROUP);
@@ -172,21 +192,41 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // ---- stage the item's weights (w0 folded in), the constant rows of the A tiles, zero padding of dy^T
   {
     const int t = threadIdx.x;
-    for (int e = t; e < 3 * HID * HID; e += MT_THREADS) {
-      const int l = e / (HID * HID), r = (e / HID) % HID, c = e % HID;          // W_l[i = r][j = c]
-      const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
-      const uint32_t w = rnd_tf32(w0 * wt_g[off + HID + r * HID + c]);
+    // all global loads first (they are independent), then the swizzled stores: the st.shared asm
+    // statements are ordering points for the compiler, and a load-store-load-store chain would pay
+    // the full memory latency twelve times per thread
+    float wv[12], w3v[2], bv = 0.f, b3v = 0.f, w3p = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int e = t + i * MT_THREADS;                                         // W_l[i = r][j = c]
+      const int l = e / (HID * HID), r = (e / HID) % HID, c = e % HID;
+      wv[i] = wt_g[(l == 0 ? off0 : (l == 1 ? off1 : off2)) + HID + r * HID + c];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = t + i * MT_THREADS, k = e / HID, j = e % HID;               // W_3[j][k] -> rows k, K = j
+      w3v[i] = k < OUT ? wt_g[off3 + OUT + j * OUT + k] : 0.f;
+    }
+    if (t < 3 * HID) bv = wt_g[(t / HID == 0 ? off0 : (t / HID == 1 ? off1 : off2)) + t % HID];
+    if (t < OUT) b3v = wt_g[off3 + t];
+    if (t < HID * 4 && t % 4 < OUT) w3p = wt_g[off3 + OUT + (t / 4) * OUT + t % 4];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int e = t + i * MT_THREADS;
+      const int l = e / (HID * HID), r = (e / HID) % HID, c = e % HID;
+      const uint32_t w = rnd_tf32(w0 * wv[i]);
       sts32(sbase + Sm::WF + l * 4096 + swz4(c, r), w);                         // forward B: rows j, K = i
       if (l > 0) sts32(sbase + Sm::WB + l * 4096 + swz4(r, c), w);              // backward B: rows i, K = j
       else if (r >= F) sts32(sbase + Sm::WB + swz4(r - F, c), w);               // layer 0: pe inputs only
     }
-    for (int e = t; e < 16 * HID; e += MT_THREADS) {
-      const int k = e / HID, j = e % HID;                                       // W_3[j][k] -> rows k, K = j
-      sts32(sbase + Sm::W3 + swz4(k, j), k < OUT ? rnd_tf32(wt_g[off3 + OUT + j * OUT + k]) : 0u);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = t + i * MT_THREADS, k = e / HID, j = e % HID;
+      sts32(sbase + Sm::W3 + swz4(k, j), k < OUT ? rnd_tf32(w3v[i]) : 0u);
     }
-    for (int e = t; e < 3 * HID; e += MT_THREADS) plain[e] = w0 * wt_g[(e / HID == 0 ? off0 : (e / HID == 1 ? off1 : off2)) + e % HID];
-    if (t < 4) plain[96 + t] = t < OUT ? wt_g[off3 + t] : 0.f;
-    for (int e = t; e < HID * 4; e += MT_THREADS) plain[128 + e] = (e % 4 < OUT) ? wt_g[off3 + OUT + (e / 4) * OUT + e % 4] : 0.f;
+    if (t < 3 * HID) plain[t] = w0 * bv;
+    if (t < 4) plain[96 + t] = b3v;
+    if (t < HID * 4) plain[128 + t] = w3p;
     if (MODE != 0) {
       // rows 32..39 of every K block of every A tile: ones row + zeros (32-bit words = fp16 pairs)
       for (int e = t; e < 2 * 3 * 2 * 8 * 32; e += MT_THREADS) {
@@ -196,10 +236,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       for (int e = t; e < 2 * 1024; e += MT_THREADS) sts32(sbase + (e / 1024) * Sm::SLOT + Sm::DZ3 + (e % 1024) * 4, 0u);
     }
   }
+  PROF(2);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  PROF(3);
   const uint32_t tmem_base = *tmem_slot;
 
   const int g = warp >> 2;                // group = tile slot: tiles g, g + 2, g + 4, ...
@@ -317,17 +359,22 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     }
   };
   auto publish = [&](bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
+    PROF(300);
     tmem_st_wait();
     if (smem_written) fence_async_smem();
     tc_fence_before();
     mbar_arrive(&bar_ready[g]);
+    PROF(301);
   };
   uint32_t ph_mma = 0u;
   auto wait_mma = [&]() {
+    PROF(100);
     mbar_wait(&bar_mma[g], ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
+    PROF(200);
   };
+  PROF(4);
   float sq = 0.f;
   uint32_t xin[32];
   if (g < ntiles) load_x0(g * 128 + r, xin);
@@ -467,25 +514,29 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     }
   }
 
+  PROF(5);
   if (MODE != 0) {
     // both groups' MMAs have retired once every thread is here
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // ---- weight gradients: TMEM lane i < 32 = input feature i, lane 32 = the ones row (bias);
-    //      group 0's warps take columns 0-15, group 1's 16-31
+    PROF(6);
+    // ---- weight gradients (M = 64 accumulators): input feature i < 16 in TMEM lane i, 16 <= i < 32 in lane
+    //      32 + (i - 16), the ones row (bias) in lane 64; group 0's warps take columns 0-15, group 1's 16-31
     float* gw = a.d_wt + (int64_t)item * a.ld_w;
     const int j0 = g * 16;
-    if (q == 0 || q == 1) {
+    if (q <= 2) {
       uint32_t acc[16];
       const float sc = w0 * unscale;
+      const bool wrow = q < 2 && lane < 16, brow = q == 2 && lane == 0;
+      const int irow = q * 16 + lane;
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
         tmem_ld16_issue(tm + TM_DW + (uint32_t)(l * 32 + j0), acc);
         tmem_ld_wait();
         const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
-        float* dst = q == 0 ? gw + off + HID + lane * HID + j0 : gw + off + j0;
-        if (q == 0 || lane == 0) {
+        float* dst = wrow ? gw + off + HID + irow * HID + j0 : gw + off + j0;
+        if (wrow || brow) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *(float4*)(dst + c * 4) = make_float4(sc * __uint_as_float(acc[c * 4]), sc * __uint_as_float(acc[c * 4 + 1]),
@@ -495,10 +546,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       if (g == 0) {
         tmem_ld16_issue(tm + TM_DW + 96, acc);
         tmem_ld_wait();
-        if (q == 0) {
+        if (wrow) {
 #pragma unroll
-          for (int k = 0; k < OUT; ++k) gw[off3 + OUT + lane * OUT + k] = unscale * __uint_as_float(acc[k]);
-        } else if (lane == 0) {
+          for (int k = 0; k < OUT; ++k) gw[off3 + OUT + irow * OUT + k] = unscale * __uint_as_float(acc[k]);
+        } else if (brow) {
 #pragma unroll
           for (int k = 0; k < OUT; ++k) gw[off3 + k] = unscale * __uint_as_float(acc[k]);
         }
@@ -509,8 +560,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       if (lane == 0) plain[104 + warp] = sq;
     }
   }
+  PROF(7);
   tc_fence_before();
   __syncthreads();
+  PROF(8);
   if (MODE == 1 && threadIdx.x == 0)
     a.sqerr[item] = ((plain[104] + plain[105]) + (plain[106] + plain[107])) + ((plain[108] + plain[109]) + (plain[110] + plain[111]));
   if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
@@ -537,6 +590,12 @@ static int launch(const rcb_mlp_args* a, cudaStream_t st) {
 }  // namespace rcb
 
 using namespace rcb;
+
+#ifdef RCB_MLP_PROFILE
+extern "C" int rcb_mlp_prof_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, rcb::mlp::rcb_prof_buf, sizeof(long long) * 4 * 1024);
+}
+#endif
 
 extern "C" int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a != nullptr, "rcb_mlp_tc: null args");
