@@ -179,6 +179,34 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   const float gscale = MODE == 2 ? (a.coef > 0.f ? a.coef : 1.f) : 1.f;
   const float unscale = MODE == 1 ? a.coef : 1.f / gscale;
 
+  const int g = warp >> 2;                // group = tile slot: tiles g, g + 2, g + 4, ...
+  const int q = warp & 3;                 // TMEM lane quarter
+  const int r = q * 32 + lane;            // pixel row inside the tile
+  const float* xt = a.xt + (int64_t)row_item * a.x_row_stride;
+  const bool stitched = a.pe_base != nullptr;
+  const int64_t pe_origin = stitched ? a.pe_base[item] : (int64_t)item * pix;
+  const int php = a.ph * a.pw;
+  auto pe_off = [&](int gp) -> int64_t {
+    if (!stitched) return gp;
+    int z = gp / php, rem = gp - z * php;
+    int yy = rem / a.pw, xx = rem - yy * a.pw;
+    return (int64_t)z * a.pitch_z + (int64_t)yy * a.pitch_y + xx;
+  };
+  // the 32 input features of pixel gp: 16 Fourier features, 16 positional encodings (raw fp32 patterns)
+  auto load_x0 = [&](int gp, uint32_t (&v)[32]) {
+    const bool ok = gp < pix;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
+    const uint4* p = reinterpret_cast<const uint4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
+      v[16 + c * 4] = t4.x; v[17 + c * 4] = t4.y; v[18 + c * 4] = t4.z; v[19 + c * 4] = t4.w;
+    }
+  };
+  uint32_t xin[32];
+  if (g < ntiles) load_x0(g * 128 + r, xin);    // first tile's inputs travel under the weight staging
+
   PROF(1);
   if ((sbase & 1023u) != 0u) __trap();                     // the swizzled tiles assume a 1024-B aligned window
   if (threadIdx.x == 0) {
@@ -244,9 +272,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   PROF(3);
   const uint32_t tmem_base = *tmem_slot;
 
-  const int g = warp >> 2;                // group = tile slot: tiles g, g + 2, g + 4, ...
-  const int q = warp & 3;                 // TMEM lane quarter
-  const int r = q * 32 + lane;            // pixel row inside the tile
   const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t R0 = (uint32_t)(64 * g), R1 = R0 + 32;
   const int so = g * Sm::SLOT;
@@ -323,16 +348,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     __syncwarp();
   };
 
-  const float* xt = a.xt + (int64_t)row_item * a.x_row_stride;
-  const bool stitched = a.pe_base != nullptr;
-  const int64_t pe_origin = stitched ? a.pe_base[item] : (int64_t)item * pix;
-  const int php = a.ph * a.pw;
-  auto pe_off = [&](int gp) -> int64_t {
-    if (!stitched) return gp;
-    int z = gp / php, rem = gp - z * php;
-    int yy = rem / a.pw, xx = rem - yy * a.pw;
-    return (int64_t)z * a.pitch_z + (int64_t)yy * a.pitch_y + xx;
-  };
   // feature-major fp16 element of this thread's pixel: K block r / 64, column r % 64
   const uint32_t t_kb = (uint32_t)(q >> 1);
   const int t_col = (q & 1) * 32 + lane;
@@ -344,18 +359,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const uint32_t h2 = pack_h2(v[j], v[j + 1]);
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + swz2(f0 + j, t_col)), "h"((unsigned short)(h2 & 0xffffu)) : "memory");
       asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + swz2(f0 + j + 1, t_col)), "h"((unsigned short)(h2 >> 16)) : "memory");
-    }
-  };
-  // the 32 input features of pixel gp: 16 Fourier features, 16 positional encodings (raw fp32 patterns)
-  auto load_x0 = [&](int gp, uint32_t (&v)[32]) {
-    const bool ok = gp < pix;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
-    const uint4* p = reinterpret_cast<const uint4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
-      v[16 + c * 4] = t4.x; v[17 + c * 4] = t4.y; v[18 + c * 4] = t4.z; v[19 + c * 4] = t4.w;
     }
   };
   auto publish = [&](bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
@@ -376,8 +379,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   };
   PROF(4);
   float sq = 0.f;
-  uint32_t xin[32];
-  if (g < ntiles) load_x0(g * 128 + r, xin);
 
   for (int tile = g; tile < ntiles; tile += 2) {
     const int gp = tile * 128 + r;
