@@ -176,6 +176,12 @@ int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
  * removed from the outputs (pick ~1/max|dy| so that fp16 keeps its 10-bit mantissa). */
 int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream);
 
+/* out[c][r] = in[r][c] (row strides ld_in, ld_out in elements).  Puts the (items, W) tensors of the
+ * reparameterisation weight gradient dA_l = hw_l^T d_wt_l (prior_model.py:170-174 under autograd)
+ * into the K-major form rcb_gemm_tc takes. */
+int rcb_transpose(const float* in, int64_t ld_in, float* out, int64_t ld_out, int rows, int cols,
+                  rcb_stream_t stream);
+
 /* Gradient reduction over MC samples + beta-weighted closed-form KL gradient
  * (+ fused Adam).  Replaces the autograd backward of test_model.py:289-303,
  * calculate_kl :357-377 and Adam.step (:635).  Group-order element (r,q):

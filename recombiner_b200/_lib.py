@@ -78,6 +78,7 @@ SIGNATURES = {
     "rcb_colsum": [P, I64, I32, I32, P, P],
     "rcb_mlp": [C.POINTER(MlpArgs), P],
     "rcb_mlp_tc": [C.POINTER(MlpArgs), P],
+    "rcb_transpose": [P, I64, P, I64, I32, I32, P],
     "rcb_fit_update": [C.POINTER(UpdateArgs), P],
     "rcb_group_kl": [P, P, P, P, P, P, P, I32, I32, I32, P],
     "rcb_anneal_beta": [P, P, P, I32, I32, F64, F64, F64, F64, P],

@@ -363,6 +363,26 @@ __global__ void pick_block_kernel(const double* __restrict__ kl, const uint8_t* 
   if (lane == 0) block[r] = bi;
 }
 
+// ------------------------------------------------------------------ transpose --
+// out[c][r] = in[r][c] through a padded 32 x 32 shared-memory tile (coalesced on both sides).
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in, float* __restrict__ out,
+                                                        int64_t ld_out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[(int64_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = tile[tx][i];
+  }
+}
+
 // ------------------------------------------------------ EM prior statistics --
 // grid: (ceil(P/128), row chunks); f64 partial sums added with atomics.
 __global__ void __launch_bounds__(128) suffstats_kernel(const float* __restrict__ loc, const float* __restrict__ log_scale,
@@ -474,6 +494,17 @@ extern "C" int rcb_pick_block(const double* kl, const uint8_t* coded, int* block
   if (rows <= 0) return 0;
   pick_block_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(kl, coded, block, rows, G);
   RCB_CHECK_LAUNCH("rcb_pick_block");
+  return 0;
+}
+
+extern "C" int rcb_transpose(const float* in, int64_t ld_in, float* out, int64_t ld_out, int rows, int cols,
+                             rcb_stream_t stream) {
+  RCB_CHECK_ARG(in && out, "rcb_transpose: null tensor");
+  RCB_CHECK_ARG(rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "rcb_transpose: bad shape");
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  RCB_CHECK_ARG(grid.y <= 65535, "rcb_transpose: too many rows");
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, cols);
+  RCB_CHECK_LAUNCH("rcb_transpose");
   return 0;
 }
 

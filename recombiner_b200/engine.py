@@ -512,9 +512,23 @@ class FitEngine:
             if self.dense1:
                 g["dM1"] = torch.zeros_like(self.M1)
         with self.section("reparam_wgrad"):
-            for l, c in enumerate(self.counts):
-                self._gemm(ws["hw"], self.offsets[l], self.ldw, None, self.ldw, g["A"][l], 0, g["A"][l].shape[1],
-                           c, c, items, trans_a=1, b_tensor=ws["d_wt"], b_off=self.offsets[l])
+            if self.tc:
+                # dA_l = hw_l^T d_wt_l with K = items: transpose both once (K-major), then the tcgen05 GEMM
+                ldt = _round_up(items, 4)
+                if "hwT" not in ws or ws["hwT"].shape[1] != ldt:
+                    ws["hwT"] = torch.zeros(self.ldw, ldt, device=dev)
+                    ws["dwtT"] = torch.zeros(self.ldw, ldt, device=dev)
+                check(self.lib.rcb_transpose(ptr(ws["hw"]), self.ldw, ptr(ws["hwT"]), ldt, items, self.W, st), "rcb_transpose")
+                check(self.lib.rcb_transpose(ptr(ws["d_wt"]), self.ldw, ptr(ws["dwtT"]), ldt, items, self.W, st), "rcb_transpose")
+                for l, c in enumerate(self.counts):
+                    pa = ws["hwT"].data_ptr() + 4 * self.offsets[l] * ldt
+                    pb = ws["dwtT"].data_ptr() + 4 * self.offsets[l] * ldt
+                    check(self.lib.rcb_gemm_tc(pa, ldt, pb, ldt, ptr(g["A"][l]), g["A"][l].shape[1], c, c, items,
+                                               None, 1, 0, 0, st), "rcb_gemm_tc")
+            else:
+                for l, c in enumerate(self.counts):
+                    self._gemm(ws["hw"], self.offsets[l], self.ldw, None, self.ldw, g["A"][l], 0, g["A"][l].shape[1],
+                               c, c, items, trans_a=1, b_tensor=ws["d_wt"], b_off=self.offsets[l])
         srcs = [ws["lpe"], ws["a1"], ws["a2"]]
         douts = [ws["d_a1"], ws["d_a2"], ws["d_pe"]]
         with self.section("conv_wgrad"):
@@ -524,8 +538,20 @@ class FitEngine:
                       "rcb_colsum")
                 if i == 0 and self.dense1:
                     Lt = self.M1.shape[0]
-                    self._gemm(ws["lpe"], 0, Lt, None, g["dM1"].shape[1], g["dM1"], 0, g["dM1"].shape[1],
-                               Lt, g["dM1"].shape[1], citems, trans_a=1, b_tensor=ws["d_a1"], b_off=0)
+                    n1 = g["dM1"].shape[1]
+                    if self.tc and n1 % 4 == 0:
+                        # dM1 = lpe^T d_a1 with K = items: K-major copies, then the tcgen05 GEMM
+                        ldt = _round_up(citems, 4)
+                        if "lpeT" not in ws or ws["lpeT"].shape[1] != ldt:
+                            ws["lpeT"] = torch.zeros(Lt, ldt, device=dev)
+                            ws["da1T"] = torch.zeros(n1, ldt, device=dev)
+                        check(self.lib.rcb_transpose(ptr(ws["lpe"]), Lt, ptr(ws["lpeT"]), ldt, citems, Lt, st), "rcb_transpose")
+                        check(self.lib.rcb_transpose(ptr(ws["d_a1"]), n1, ptr(ws["da1T"]), ldt, citems, n1, st), "rcb_transpose")
+                        check(self.lib.rcb_gemm_tc(ptr(ws["lpeT"]), ldt, ptr(ws["da1T"]), ldt, ptr(g["dM1"]), n1, Lt, n1, citems,
+                                                   None, 1, 0, 0, st), "rcb_gemm_tc")
+                    else:
+                        self._gemm(ws["lpe"], 0, Lt, None, n1, g["dM1"], 0, n1,
+                                   Lt, n1, citems, trans_a=1, b_tensor=ws["d_a1"], b_off=0)
                     check(self.lib.rcb_unfold_dense(ptr(g["dM1"]), C.byref(geo), ptr(g["conv1.weight"]), st),
                           "rcb_unfold_dense")
                     continue
