@@ -48,9 +48,8 @@ N_CAND = 65536
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/README.md); None where no capture exists yet
-TRAFFIC = {"mlp_fwd_bwd": 777.8e6,       # profiles/r1_ncu_full_mlp_tc_v2_sample_update.csv (1024 rows x S=5)
-           "update": 310.9e6, "sample": 157.7e6,
-           "conv3_fwd": 625.4e6, "conv2_fwd": 372.0e6}   # profiles/r1_ncu_full_v4.csv
+TRAFFIC = {"mlp_fwd_bwd": 775.5e6, "conv3_fwd": 625.6e6, "conv2_fwd": 365.5e6, "conv3_bwd": 979.1e6,
+           "conv2_bwd": 490.6e6, "update": 320.6e6, "sample": 158.1e6}   # profiles/r1_ncu_full_final.csv
 
 
 def schedule(G: int):
