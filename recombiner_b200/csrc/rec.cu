@@ -116,111 +116,160 @@ __global__ void __launch_bounds__(256) rec_table_kernel(const int64_t* __restric
 }
 
 // ---- scoring -----------------------------------------------------------------
-constexpr int REC_THREADS = 512;
+constexpr int REC_THREADS = 256;
 constexpr int REC_ILP = 4;
+constexpr int REC_RPC = 4;        // pairs per CTA; consecutive pairs that share a block share the table loads
 
-// One CTA per (row, block) pair.
-__global__ void __launch_bounds__(REC_THREADS) rec_encode_kernel(rcb_rec_args a) {
-  extern __shared__ __align__(16) double coef[];   // [2*D] (A_d, B_d) then reduction scratch
-  __shared__ double red_v[REC_THREADS / 32];
-  __shared__ int red_i[REC_THREADS / 32];
-  __shared__ double c0_s;
-  __shared__ int best_s;
-
-  const int pair = blockIdx.x;
-  const int row = a.pair_row[pair], blk = a.pair_block[pair];
-  const int start = a.group_start[blk], D = a.group_end[blk] - start;
-  const float* __restrict__ tab = a.tables[blk];
-  const int n = a.n_cand;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // per-dimension quadratic-form coefficients, reproducing the reference's mixed
-  // precision: var = scale*scale and log(scale) are f32, everything else f64
-  double c_part = 0.0;
-  for (int d = tid; d < D; d += REC_THREADS) {
-    const float mq = a.q_loc[(int64_t)row * a.P + start + d], sq = a.q_scale[(int64_t)row * a.P + start + d];
-    const float mp = a.p_loc[start + d], sp = a.p_scale[start + d];
-    const double kp = 1.0 / (2.0 * (double)__fmul_rn(sp, sp));
-    const double kq = 1.0 / (2.0 * (double)__fmul_rn(sq, sq));
-    const double delta = (double)mp - (double)mq;
-    const double spd = (double)sp;
-    coef[2 * d] = spd * spd * (kp - kq);
-    coef[2 * d + 1] = -2.0 * spd * delta * kq;
-    c_part += -delta * delta * kq + (double)logf(sp) - (double)logf(sq);
-  }
-  c_part = warp_sum(c_part);
-  if (lane == 0) red_v[warp] = c_part;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    for (int w = 0; w < REC_THREADS / 32; ++w) t += red_v[w];
-    c0_s = t;
-  }
-  __syncthreads();
-  const double c0 = c0_s;
-
-  double best = -CUDART_INF;
-  int best_k = 0x7fffffff;
+// Score R rows that code the SAME block against the block's candidate table: every table value is loaded
+// once and used for R quadratic forms.  Per row the arithmetic (order of d, mixed f32/f64 roundings) is
+// exactly that of a single-row pass, so indices and log-weights do not depend on the grouping.
+// coef: [R][2*D] (A_d, B_d); c0[r]; best[r] / best_k[r]: per-thread running first-argmax.
+template <int R>
+__device__ __forceinline__ void rec_score_run(const rcb_rec_args& a, const float* __restrict__ tab, const double* coef,
+                                              const double* c0, int D, int n, int pair0, double (&best)[REC_RPC],
+                                              int (&best_k)[REC_RPC]) {
+  const int tid = threadIdx.x;
   for (int k0 = tid; k0 < n; k0 += REC_THREADS * REC_ILP) {
-    double acc[REC_ILP];
+    double acc[R][REC_ILP];
 #pragma unroll
-    for (int u = 0; u < REC_ILP; ++u) acc[u] = 0.0;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int u = 0; u < REC_ILP; ++u) acc[r][u] = 0.0;
     for (int d = 0; d < D; ++d) {
-      const double A = coef[2 * d], B = coef[2 * d + 1];
       const float* col = tab + (int64_t)d * n + k0;
+      double sv[REC_ILP];
 #pragma unroll
-      for (int u = 0; u < REC_ILP; ++u) {
-        const int k = k0 + u * REC_THREADS;
-        const double s = (k < n) ? (double)__ldg(col + u * REC_THREADS) : 0.0;
-        acc[u] = fma(s, fma(A, s, B), acc[u]);
+      for (int u = 0; u < REC_ILP; ++u) sv[u] = (k0 + u * REC_THREADS < n) ? (double)__ldg(col + u * REC_THREADS) : 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double A = coef[(r * D + d) * 2], B = coef[(r * D + d) * 2 + 1];
+#pragma unroll
+        for (int u = 0; u < REC_ILP; ++u) acc[r][u] = fma(sv[u], fma(A, sv[u], B), acc[r][u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < REC_ILP; ++u) {
       const int k = k0 + u * REC_THREADS;
       if (k < n) {
-        const double lw = acc[u] + c0 + a.gumbel[k];
-        if (a.logw_out) a.logw_out[(int64_t)pair * n + k] = lw;
-        if (lw > best) { best = lw; best_k = k; }     // k increases: keeps the first maximum
+        const double gk = a.gumbel[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double lw = acc[r][u] + c0[r] + gk;
+          if (a.logw_out) a.logw_out[(int64_t)(pair0 + r) * n + k] = lw;
+          if (lw > best[r]) { best[r] = lw; best_k[r] = k; }     // k increases: keeps the first maximum
+        }
       }
     }
   }
-  // block-level first-argmax
+}
+
+// One CTA per REC_RPC consecutive (row, block) pairs.  Runs of equal blocks inside the CTA are scored together;
+// callers that sort their pairs by block (TestBNNmodel.compress_round does) get the table reuse.
+__global__ void __launch_bounds__(REC_THREADS) rec_encode_kernel(rcb_rec_args a, int rpc) {
+  extern __shared__ __align__(16) double coef[];   // [rpc][2*max_D] (A_d, B_d)
+  __shared__ double red_v[REC_THREADS / 32];
+  __shared__ int red_i[REC_THREADS / 32];
+  __shared__ double c0_s[REC_RPC];
+  __shared__ int best_s[REC_RPC];
+
+  const int n = a.n_cand;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p_begin = blockIdx.x * rpc, p_end = min(a.n_pairs, p_begin + rpc);
+
+  for (int pair0 = p_begin; pair0 < p_end;) {
+    const int blk = a.pair_block[pair0];
+    int R = 1;
+    while (pair0 + R < p_end && a.pair_block[pair0 + R] == blk) ++R;
+    const int start = a.group_start[blk], D = a.group_end[blk] - start;
+    const float* __restrict__ tab = a.tables[blk];
+
+    // per-dimension quadratic-form coefficients, reproducing the reference's mixed
+    // precision: var = scale*scale and log(scale) are f32, everything else f64
+    for (int r = 0; r < R; ++r) {
+      const int row = a.pair_row[pair0 + r];
+      double c_part = 0.0;
+      for (int d = tid; d < D; d += REC_THREADS) {
+        const float mq = a.q_loc[(int64_t)row * a.P + start + d], sq = a.q_scale[(int64_t)row * a.P + start + d];
+        const float mp = a.p_loc[start + d], sp = a.p_scale[start + d];
+        const double kp = 1.0 / (2.0 * (double)__fmul_rn(sp, sp));
+        const double kq = 1.0 / (2.0 * (double)__fmul_rn(sq, sq));
+        const double delta = (double)mp - (double)mq;
+        const double spd = (double)sp;
+        coef[(r * D + d) * 2] = spd * spd * (kp - kq);
+        coef[(r * D + d) * 2 + 1] = -2.0 * spd * delta * kq;
+        c_part += -delta * delta * kq + (double)logf(sp) - (double)logf(sq);
+      }
+      c_part = warp_sum(c_part);
+      __syncthreads();
+      if (lane == 0) red_v[warp] = c_part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < REC_THREADS / 32; ++w) t += red_v[w];
+        c0_s[r] = t;
+      }
+    }
+    __syncthreads();
+    double c0[REC_RPC], best[REC_RPC];
+    int best_k[REC_RPC];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, best, o);
-    int oi = __shfl_xor_sync(0xffffffffu, best_k, o);
-    if (ov > best || (ov == best && oi < best_k)) { best = ov; best_k = oi; }
-  }
-  __syncthreads();
-  if (lane == 0) { red_v[warp] = best; red_i[warp] = best_k; }
-  __syncthreads();
-  if (tid == 0) {
-    double bv = red_v[0]; int bi = red_i[0];
-    for (int w = 1; w < REC_THREADS / 32; ++w)
-      if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
-    best_s = bi;
-    if (a.apply) {
-      a.idx_out[(int64_t)row * a.G + blk] = bi;
-      if (a.beta) a.beta[(int64_t)row * a.G + blk] = 0.f;
-      if (a.coded) a.coded[(int64_t)row * a.G + blk] = 1;
-    } else {
-      a.idx_out[pair] = bi;
+    for (int r = 0; r < REC_RPC; ++r) { c0[r] = r < R ? c0_s[r] : 0.0; best[r] = -CUDART_INF; best_k[r] = 0x7fffffff; }
+
+    if (R == 1) rec_score_run<1>(a, tab, coef, c0, D, n, pair0, best, best_k);
+    else if (R == 2) rec_score_run<2>(a, tab, coef, c0, D, n, pair0, best, best_k);
+    else if (R == 3) rec_score_run<3>(a, tab, coef, c0, D, n, pair0, best, best_k);
+    else rec_score_run<4>(a, tab, coef, c0, D, n, pair0, best, best_k);
+
+    // block-level first-argmax, one row at a time
+#pragma unroll
+    for (int r = 0; r < REC_RPC; ++r) {
+      if (r < R) {
+        double bv = best[r];
+        int bi = best_k[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+          double v = red_v[0]; int i = red_i[0];
+          for (int w = 1; w < REC_THREADS / 32; ++w)
+            if (red_v[w] > v || (red_v[w] == v && red_i[w] < i)) { v = red_v[w]; i = red_i[w]; }
+          best_s[r] = i;
+          const int row = a.pair_row[pair0 + r];
+          if (a.apply) {
+            a.idx_out[(int64_t)row * a.G + blk] = i;
+            if (a.beta) a.beta[(int64_t)row * a.G + blk] = 0.f;
+            if (a.coded) a.coded[(int64_t)row * a.G + blk] = 1;
+          } else {
+            a.idx_out[pair0 + r] = i;
+          }
+        }
+      }
     }
-  }
-  __syncthreads();
-  const int kb = best_s;
-  if (kb >= n) return;   // n == 0
-  for (int d = tid; d < D; d += REC_THREADS) {
-    const double s = (double)tab[(int64_t)d * n + kb];
-    // z = mu_p + sigma_p * s in f64 with two roundings, then f32 on store (test_model.py:514,591)
-    const float z = (float)__dadd_rn((double)a.p_loc[start + d], __dmul_rn((double)a.p_scale[start + d], s));
-    if (a.apply) {
-      a.sample[(int64_t)row * a.P + start + d] = z;
-      a.mask[(int64_t)row * a.P + start + d] = 1.f;
-    } else if (a.z_out) {
-      a.z_out[(int64_t)pair * a.max_D + d] = z;
+    __syncthreads();
+    for (int r = 0; r < R; ++r) {
+      const int kb = best_s[r];
+      if (kb >= n) continue;   // n == 0
+      const int row = a.pair_row[pair0 + r];
+      for (int d = tid; d < D; d += REC_THREADS) {
+        const double sd = (double)tab[(int64_t)d * n + kb];
+        // z = mu_p + sigma_p * s in f64 with two roundings, then f32 on store (test_model.py:514,591)
+        const float z = (float)__dadd_rn((double)a.p_loc[start + d], __dmul_rn((double)a.p_scale[start + d], sd));
+        if (a.apply) {
+          a.sample[(int64_t)row * a.P + start + d] = z;
+          a.mask[(int64_t)row * a.P + start + d] = 1.f;
+        } else if (a.z_out) {
+          a.z_out[(int64_t)(pair0 + r) * a.max_D + d] = z;
+        }
+      }
     }
+    __syncthreads();           // coef / best_s are rewritten by the next run
+    pair0 += R;
   }
 }
 
@@ -265,12 +314,14 @@ extern "C" int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->max_D > 0 && a->max_D <= 12000, "rcb_rec_encode: max_D %d out of range (1..12000)", a->max_D);
   RCB_CHECK_ARG(a->n_cand > 0, "rcb_rec_encode: no candidates");
   if (a->n_pairs <= 0) return 0;
-  size_t smem = sizeof(double) * 2 * (size_t)a->max_D;
+  int rpc = REC_RPC;
+  while (rpc > 1 && sizeof(double) * 2 * (size_t)a->max_D * rpc > 96 * 1024) --rpc;
+  size_t smem = sizeof(double) * 2 * (size_t)a->max_D * rpc;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(rec_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("rcb_rec_encode: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
   }
-  rec_encode_kernel<<<a->n_pairs, REC_THREADS, smem, (cudaStream_t)stream>>>(*a);
+  rec_encode_kernel<<<ceil_div(a->n_pairs, rpc), REC_THREADS, smem, (cudaStream_t)stream>>>(*a, rpc);
   RCB_CHECK_LAUNCH("rcb_rec_encode");
   return 0;
 }

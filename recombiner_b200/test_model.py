@@ -408,8 +408,10 @@ class TestBNNmodel(nn.Module):
             check(self.engine.lib.rcb_pick_block(ptr(kl), ptr(lv.coded), ptr(blocks), lv.rows, lv.G, stream()),
                   "rcb_pick_block")
         q_scale, p_scale = self._scales(level)
-        _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, rows, blocks.contiguous(), n, lv.max_D,
-                    apply=True)
+        # pairs sorted by block: the kernel scores runs of equal blocks against one pass over the candidate table
+        order = torch.argsort(blocks, stable=True)
+        _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, rows[order].contiguous(),
+                    blocks[order].contiguous(), n, lv.max_D, apply=True)
         return blocks
 
     def decode_posteriors(self, indices: np.ndarray, level: int = 0) -> torch.Tensor:
