@@ -403,8 +403,11 @@ def run_b200(args):
                                  "achieved": ROWS_PER_GPU * (wl["P"] / G) * N_CAND * 4 / (t_round * 1e-3) / 1e9,
                                  "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": ROWS_PER_GPU * (wl["P"] / G) * N_CAND * 4 / (t_round * 1e-3) / 1e9 / pk["hbm"],
-                                 "traffic": None, "peak_source": pk["src"] + " copy bandwidth",
-                                 "note": "table bytes of the mean block size; blocks picked per row by largest KL"}},
+                                 "traffic": 36.5e6, "peak_source": pk["src"] + " copy bandwidth",
+                                 "note": "achieved = candidate-table bytes each (row, block) pair consumes; with this synthetic "
+                                         "prior the rows pick few distinct blocks, so the tables are served from L2 (ncu: 36 MB "
+                                         "of DRAM traffic per round, profiles/r1_ncu_full_rec_encode.csv) and the kernel is bound "
+                                         "by load-to-use latency at 39 % issue-slot utilisation, 21 % FP64 pipe"}},
             "clocks": clk,
         }
         if cpu:
