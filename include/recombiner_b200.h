@@ -176,11 +176,24 @@ int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
  * removed from the outputs (pick ~1/max|dy| so that fp16 keeps its 10-bit mantissa). */
 int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream);
 
+/* Polyphase conv weight gradient on tcgen05 (2-D grids, k > 1): d_w_eff[phase][tap][ic][oc] as produced by
+ * rcb_upconv_wgrad, from channel-major copies srcT [3 x-shifts][ic][items*h*w] (rcb_transpose_xshift) and doutT
+ * [oc][items][fy*fx phases][h][w] (rcb_transpose_phases).  TF32 operands, fp32 accumulation; split-K partial sums
+ * are added atomically. */
+int rcb_upconv_wgrad_tc(const float* srcT, const float* doutT, float* d_w_eff, const rcb_upconv_geom* g,
+                        int items, rcb_stream_t stream);
+
 /* out[c][r] = in[r][c] (row strides ld_in, ld_out in elements).  Puts the (items, W) tensors of the
  * reparameterisation weight gradient dA_l = hw_l^T d_wt_l (prior_model.py:170-174 under autograd)
  * into the K-major form rcb_gemm_tc takes. */
 int rcb_transpose(const float* in, int64_t ld_in, float* out, int64_t ld_out, int rows, int cols,
                   rcb_stream_t stream);
+/* out[dx+1][c][r] = in[r+dx][c] inside the line of w pixels that row r belongs to, 0 outside (dx = -1, 0, 1). */
+int rcb_transpose_xshift(const float* in, float* out, int64_t rows, int cols, int w, rcb_stream_t stream);
+/* Channel-major copy of an upsampled channel-last tensor in (rows = items*(h*fy)*(w*fx), cols) with the rows
+ * regrouped by phase: out[c][((item*fy + oy%fy)*fx + ox%fx)*h*w + (oy/fy)*w + ox/fx] = in[(item, oy, ox)][c]. */
+int rcb_transpose_phases(const float* in, float* out, int64_t rows, int cols, int h, int w, int fy, int fx,
+                         rcb_stream_t stream);
 
 /* Gradient reduction over MC samples + beta-weighted closed-form KL gradient
  * (+ fused Adam).  Replaces the autograd backward of test_model.py:289-303,

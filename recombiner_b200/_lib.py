@@ -73,12 +73,15 @@ SIGNATURES = {
     "rcb_upconv_fwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_wgrad": [P, P, P, C.POINTER(UpconvGeom), I32, P],
+    "rcb_upconv_wgrad_tc": [P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_unfold_poly": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_unfold_dense": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_colsum": [P, I64, I32, I32, P, P],
     "rcb_mlp": [C.POINTER(MlpArgs), P],
     "rcb_mlp_tc": [C.POINTER(MlpArgs), P],
     "rcb_transpose": [P, I64, P, I64, I32, I32, P],
+    "rcb_transpose_phases": [P, P, I64, I32, I32, I32, I32, I32, P],
+    "rcb_transpose_xshift": [P, P, I64, I32, I32, P],
     "rcb_fit_update": [C.POINTER(UpdateArgs), P],
     "rcb_group_kl": [P, P, P, P, P, P, P, I32, I32, I32, P],
     "rcb_anneal_beta": [P, P, P, I32, I32, F64, F64, F64, F64, P],

@@ -762,3 +762,208 @@ extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const f
   RCB_CHECK_LAUNCH("rcb_upconv_bwd_tc");
   return 0;
 }
+
+// ===================================================================== weight gradient ====
+// Polyphase conv weight gradient of the upsampler (prior training) on tcgen05:
+//   d_w_eff[phase][tap][ic][oc] = sum over (item, source pixel s) of src[s + shift(phase, tap)][ic] * d_out[s*f + r][oc]
+// One TMEM accumulator (ic x oc) per (phase, tap) segment; K = pixels.  Both operands are read from
+// channel-major copies (srcT [ic][items*h*w], doutT [oc][items*Ho*Wo], made by rcb_transpose), so a K block of
+// 32 consecutive source pixels (of the flattened (y, x) grid of an item) is a 128-byte K-major row per channel: A tiles
+// are 3-D TMA boxes, shifted by whole lines through the pixel coordinate (outside the item = zero fill) and along x by
+// picking one of three pre-shifted copies (a TMA box start must be 16-byte aligned); doutT is regrouped by phase (rcb_transpose_phases), so B tiles are dense boxes of one phase plane.  The distinct shifts of a CTA's segments are
+// loaded once per K block (9 tiles for 16 (phase, tap) pairs at factor 2).  Split-K over CTAs, partial sums
+// are added atomically (like the SIMT kernel they replace).
+namespace rcb {
+
+constexpr int WG_MAX_SEG = 16, WG_MAX_SHIFT = 9;
+
+struct WgTcArgs {
+  int h, w, fy, fx, ic, oc, items;
+  int kb_per_item;                    // K block = 32 consecutive source pixels of the flattened (y, x) grid of one item
+  int kb_total, kb_per_cta;
+  int phases_per_cta, nshift, phase0; // segments per CTA = 4 * phases_per_cta, first phase of this launch
+  int shift_dy[WG_MAX_SHIFT], shift_dx[WG_MAX_SHIFT];
+  int seg_shift[WG_MAX_SEG];          // per CTA-local segment: index of its shift
+  int a_bytes, b_bytes, stage_bytes, bar_off;
+  float* d_w_eff;
+};
+
+__global__ void __launch_bounds__(TC_THREADS)
+upconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, WgTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + a.bar_off);          // [2]
+  uint64_t* empty = full + 2;                               // [2]
+  uint64_t* acc_full = empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nseg = 4 * a.phases_per_cta;
+  const int ph0 = a.phase0;
+  const int kb0 = blockIdx.x * a.kb_per_cta;
+  const int nkb = min(a.kb_per_cta, a.kb_total - kb0);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < nseg * a.oc) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (nkb <= 0) {                       // uniform per CTA
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer: K block -> (item, first pixel) by counters
+    int item = kb0 / a.kb_per_item, kbi = kb0 - item * a.kb_per_item;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb & 1;
+      mbar_wait(&empty[s], ((kb >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        uint8_t* st = smem + s * a.stage_bytes;
+        mbar_expect_tx(&full[s], (uint32_t)(a.nshift * a.a_bytes + a.phases_per_cta * a.b_bytes));
+        const int p0 = kbi * 32;
+        // a line shift is +-w pixels of the flattened grid; pixels before the first / after the last line of the item
+        // are outside the tensor dimension and come back as zeros
+        for (int i = 0; i < a.nshift; ++i)
+          tma_load_3d(&tmA, &full[s], st + i * a.a_bytes, p0 + a.shift_dy[i] * a.w, item, (a.shift_dx[i] + 1) * a.ic);
+        for (int p = 0; p < a.phases_per_cta; ++p)
+          tma_load_3d(&tmB, &full[s], st + a.nshift * a.a_bytes + p * a.b_bytes, p0, item * (a.fy * a.fx) + ph0 + p, 0);
+      }
+      __syncwarp();
+      if (++kbi == a.kb_per_item) { kbi = 0; ++item; }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: per K block, 4 k-steps for every (phase, tap) segment
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.oc >> 3) << 17) | ((uint32_t)(a.ic >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb & 1;
+      mbar_wait(&full[s], (kb >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = smem_u32(smem + s * a.stage_bytes);
+        for (int sg = 0; sg < nseg; ++sg) {
+          const uint64_t da = smem_desc_sw128(st + a.seg_shift[sg] * a.a_bytes);
+          const uint64_t db = smem_desc_sw128(st + a.nshift * a.a_bytes + (sg >> 2) * a.b_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + (uint32_t)(sg * a.oc), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (kb == nkb - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: accumulator row = input channel.  M = 128: TMEM lane = row; M = 64: row i in lane (i % 16) + 32 (i / 16)
+    const int q = warp & 3;
+    const int row = a.ic == 128 ? q * 32 + lane : q * 16 + lane;
+    const bool has_row = a.ic == 128 || lane < 16;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int seg_global = (ph0 + (sg >> 2)) * 4 + (sg & 3);
+      float* dst = a.d_w_eff + ((int64_t)seg_global * a.ic + row) * a.oc;
+      for (int c0 = 0; c0 < a.oc; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sg * a.oc + c0), v);
+        if (has_row) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// 3-D map over a channel-major tensor [channels][planes][pixels] (fp32), box = 32 consecutive pixels of one plane x box_ch channels
+static int make_map_cm(CUtensorMap* map, const float* base, int channels, int planes, int pixels, int box_ch) {
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint64_t dims[3] = {(cuuint64_t)pixels, (cuuint64_t)planes, (cuuint64_t)channels};
+  cuuint64_t strides[2] = {(cuuint64_t)pixels * 4, (cuuint64_t)planes * pixels * 4};
+  cuuint32_t box[3] = {32, 1, (cuuint32_t)box_ch};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(channel-major) failed with CUresult %d", (int)r); return -1; }
+  return 0;
+}
+
+}  // namespace rcb
+
+// srcT: [3 x-shifts][ic][items*h*w] (rcb_transpose_xshift), doutT: [oc][items][fy*fx phases][h][w] (rcb_transpose_phases).
+// d_w_eff: [phases][taps][ic][oc], overwritten.
+extern "C" int rcb_upconv_wgrad_tc(const float* srcT, const float* doutT, float* d_w_eff, const rcb_upconv_geom* geo,
+                                   int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(srcT && doutT && d_w_eff, "rcb_upconv_wgrad_tc: null pointer");
+  RCB_CHECK_ARG(g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2, "rcb_upconv_wgrad_tc: 2-D grids with k > 1 only");
+  RCB_CHECK_ARG((g.ic == 64 || g.ic == 128) && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_wgrad_tc: unsupported channels %d -> %d", g.ic, g.oc);
+  WgTcArgs a;
+  a.h = g.h; a.w = g.w; a.fy = g.fy; a.fx = g.fx; a.ic = g.ic; a.oc = g.oc; a.items = items;
+  RCB_CHECK_ARG((g.h * g.w) % 32 == 0 && g.w % 4 == 0, "rcb_upconv_wgrad_tc: %d x %d grid does not tile into 32-pixel K blocks", g.h, g.w);
+  a.kb_per_item = g.h * g.w / 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nphase = g.fy * g.fx;
+  cudaError_t e = cudaMemsetAsync(d_w_eff, 0, sizeof(float) * (size_t)nphase * 4 * g.ic * g.oc, st);
+  if (e != cudaSuccess) { set_error("rcb_upconv_wgrad_tc: memset failed: %s", cudaGetErrorString(e)); return -1; }
+  if (items <= 0) return 0;
+  a.kb_total = items * a.kb_per_item;
+  int ppc = 256 / (4 * g.oc);                    // <= 256 TMEM columns per CTA
+  if (ppc < 1) ppc = 1;
+  if (ppc > nphase) ppc = nphase;
+  while (nphase % ppc) --ppc;
+  a.phases_per_cta = ppc;
+  a.a_bytes = g.ic * 128;
+  a.b_bytes = (g.oc * 128 + 1023) / 1024 * 1024;
+  a.d_w_eff = d_w_eff;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_cm(&tmA, srcT, 3 * g.ic, items, g.h * g.w, g.ic)) return rc;
+  if (int rc = make_map_cm(&tmB, doutT, g.oc, items * nphase, g.h * g.w, g.oc)) return rc;
+  if (int rc = opt_in_smem(upconv_wgrad_tc_kernel, "rcb_upconv_wgrad_tc")) return rc;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int ngroups = nphase / ppc;
+  for (int grp = 0; grp < ngroups; ++grp) {     // one launch per phase group: each has its own set of distinct shifts
+    WgTcArgs b = a;
+    b.phase0 = grp * ppc;
+    b.nshift = 0;
+    for (int lp = 0; lp < ppc; ++lp)
+      for (int t = 0; t < 4; ++t) {
+        const int ph = b.phase0 + lp, ry = ph / g.fx, rx = ph % g.fx;
+        const int dy = (ry < g.py ? -1 : 0) + (t >> 1), dx = (rx < g.px ? -1 : 0) + (t & 1);
+        int idx = -1;
+        for (int i = 0; i < b.nshift; ++i) if (b.shift_dy[i] == dy && b.shift_dx[i] == dx) idx = i;
+        if (idx < 0) {
+          RCB_CHECK_ARG(b.nshift < WG_MAX_SHIFT, "rcb_upconv_wgrad_tc: too many shifts");
+          idx = b.nshift; b.shift_dy[idx] = dy; b.shift_dx[idx] = dx; ++b.nshift;
+        }
+        b.seg_shift[lp * 4 + t] = idx;
+      }
+    b.stage_bytes = b.nshift * b.a_bytes + ppc * b.b_bytes;
+    b.bar_off = 2 * b.stage_bytes;
+    const int smem_total = b.bar_off + 256 + 1024;
+    RCB_CHECK_ARG(smem_total <= 200 * 1024, "rcb_upconv_wgrad_tc: stage does not fit shared memory");
+    int ksplit = (sms + ngroups - 1) / ngroups;  // the phase groups run concurrently: share the SMs
+    if (ksplit > b.kb_total) ksplit = b.kb_total;
+    b.kb_per_cta = (b.kb_total + ksplit - 1) / ksplit;
+    const int nct = (b.kb_total + b.kb_per_cta - 1) / b.kb_per_cta;
+    upconv_wgrad_tc_kernel<<<nct, TC_THREADS, smem_total, st>>>(tmA, tmB, b);
+    RCB_CHECK_LAUNCH("rcb_upconv_wgrad_tc");
+  }
+  return 0;
+}

@@ -383,6 +383,71 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// Three channel-major copies of a channel-last tensor whose rows are (item, y, x) pixels, shifted by dx = -1, 0, +1
+// along x with zeros outside the line: out[dx + 1][c][r] = (0 <= r % w + dx < w) ? in[r + dx][c] : 0.
+// (TMA needs 16-byte aligned box starts, so a one-pixel shift along a tensor's innermost dimension cannot be a box
+// coordinate; the tensor-core weight gradient picks the copy instead.)
+__global__ void __launch_bounds__(256) transpose_xshift_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                                               int cols, int w) {
+  __shared__ float tile[34][33];                    // rows r0 - 1 .. r0 + 32
+  const int c0 = blockIdx.x * 32;
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 34; i += 8) {
+    const int64_t r = r0 - 1 + i;
+    const int c = c0 + tx;
+    tile[i][tx] = (r >= 0 && r < rows && c < cols) ? in[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t r = r0 + tx;
+  if (r < rows) {
+    const int x = (int)(r % w);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int dx = k - 1;
+      const bool inside = x + dx >= 0 && x + dx < w;
+#pragma unroll
+      for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i;
+        if (c < cols) out[((int64_t)k * cols + c) * rows + r] = inside ? tile[tx + 1 + dx][i] : 0.f;
+      }
+    }
+  }
+}
+
+// Same, with the rows (item, oy, ox) of an upsampled channel-last tensor regrouped by phase on the way out:
+// out[c][((item * fy + oy % fy) * fx + ox % fx) * h * w + (oy / fy) * w + ox / fx] = in[(item, oy, ox)][c],
+// i.e. every phase of the output grid becomes a dense (h, w) plane per channel (TMA cannot stride its innermost
+// dimension; the tensor-core weight gradient reads one phase at a time).
+__global__ void __launch_bounds__(256) transpose_phases_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                                               int cols, int h, int w, int fy, int fx) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32;
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  const int Wo = w * fx, Ho = h * fy;
+  const int64_t r = r0 + tx;
+  if (r < rows) {
+    const int ox = (int)(r % Wo);
+    const int64_t t = r / Wo;
+    const int oy = (int)(t % Ho);
+    const int64_t item = t / Ho;
+    const int64_t ro = ((item * fy + oy % fy) * fx + ox % fx) * (int64_t)(h * w) + (int64_t)(oy / fy) * w + ox / fx;
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i;
+      if (c < cols) out[(int64_t)c * rows + ro] = tile[tx][i];
+    }
+  }
+}
+
 // ------------------------------------------------------ EM prior statistics --
 // grid: (ceil(P/128), row chunks); f64 partial sums added with atomics.
 __global__ void __launch_bounds__(128) suffstats_kernel(const float* __restrict__ loc, const float* __restrict__ log_scale,
@@ -505,6 +570,28 @@ extern "C" int rcb_transpose(const float* in, int64_t ld_in, float* out, int64_t
   RCB_CHECK_ARG(grid.y <= 65535, "rcb_transpose: too many rows");
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, cols);
   RCB_CHECK_LAUNCH("rcb_transpose");
+  return 0;
+}
+
+extern "C" int rcb_transpose_xshift(const float* in, float* out, int64_t rows, int cols, int w, rcb_stream_t stream) {
+  RCB_CHECK_ARG(in && out, "rcb_transpose_xshift: null tensor");
+  RCB_CHECK_ARG(rows > 0 && cols > 0 && w > 0 && rows % w == 0, "rcb_transpose_xshift: rows must be whole lines of w pixels");
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  RCB_CHECK_ARG(grid.y <= 65535 * 32, "rcb_transpose_xshift: too many rows");
+  transpose_xshift_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, w);
+  RCB_CHECK_LAUNCH("rcb_transpose_xshift");
+  return 0;
+}
+
+extern "C" int rcb_transpose_phases(const float* in, float* out, int64_t rows, int cols, int h, int w, int fy, int fx,
+                                    rcb_stream_t stream) {
+  RCB_CHECK_ARG(in && out, "rcb_transpose_phases: null tensor");
+  RCB_CHECK_ARG(rows > 0 && cols > 0 && h > 0 && w > 0 && fy > 0 && fx > 0 && rows % ((int64_t)h * fy * w * fx) == 0,
+                "rcb_transpose_phases: rows must be whole (h*fy, w*fx) grids");
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  RCB_CHECK_ARG(grid.y <= 65535 * 32, "rcb_transpose_phases: too many rows");
+  transpose_phases_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, h, w, fy, fx);
+  RCB_CHECK_LAUNCH("rcb_transpose_phases");
   return 0;
 }
 

@@ -555,8 +555,23 @@ class FitEngine:
                     check(self.lib.rcb_unfold_dense(ptr(g["dM1"]), C.byref(geo), ptr(g["conv1.weight"]), st),
                           "rcb_unfold_dense")
                     continue
-                check(self.lib.rcb_upconv_wgrad(ptr(srcs[i]), ptr(douts[i]), ptr(g[f"eff{i}"]), C.byref(geo), citems, st),
-                      "rcb_upconv_wgrad")
+                in_px = geo.d * geo.h * geo.w
+                if (self.tc_conv and self.data_dim == 2 and geo.ic in (64, 128) and geo.oc % 16 == 0
+                        and (geo.h * geo.w) % 32 == 0 and geo.w % 4 == 0):
+                    # tcgen05 weight gradient on channel-major (K-major) copies of the activations
+                    kt = f"wgT{i}"
+                    if kt not in ws or ws[kt][0].shape[1] != citems * in_px:
+                        ws[kt] = (torch.empty(3 * geo.ic, citems * in_px, device=dev), torch.empty(geo.oc, citems * out_px, device=dev))
+                    srcT, doutT = ws[kt]
+                    check(self.lib.rcb_transpose_xshift(ptr(srcs[i]), ptr(srcT), citems * in_px, geo.ic, geo.w, st),
+                          "rcb_transpose_xshift")
+                    check(self.lib.rcb_transpose_phases(ptr(douts[i]), ptr(doutT), citems * out_px, geo.oc, geo.h, geo.w,
+                                                        geo.fy, geo.fx, st), "rcb_transpose_phases")
+                    check(self.lib.rcb_upconv_wgrad_tc(ptr(srcT), ptr(doutT), ptr(g[f"eff{i}"]), C.byref(geo), citems, st),
+                          "rcb_upconv_wgrad_tc")
+                else:
+                    check(self.lib.rcb_upconv_wgrad(ptr(srcs[i]), ptr(douts[i]), ptr(g[f"eff{i}"]), C.byref(geo), citems, st),
+                          "rcb_upconv_wgrad")
                 check(self.lib.rcb_unfold_poly(ptr(g[f"eff{i}"]), C.byref(geo), ptr(g[f"conv{i + 1}.weight"]), st),
                       "rcb_unfold_poly")
         return g

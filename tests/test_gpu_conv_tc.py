@@ -60,3 +60,36 @@ def test_upconv_tc_matches_simt(name):
     err_b = float((got_b - ref_b).abs().max())
     assert err_b < 2e-3 * scale_b, (err_b, scale_b)
     print(f"[conv_tc {name}] fwd err {err:.2e} (scale {scale:.2f}); bwd err {err_b:.2e} (scale {scale_b:.2f})")
+
+
+@pytest.mark.parametrize("name", ["cifar_conv2", "cifar_conv3", "conv1_poly_2d_wg"])
+def test_upconv_wgrad_tc_matches_simt(name):
+    """Weight gradient of the polyphase conv on tcgen05 (channel-major copies through rcb_transpose) against the
+    SIMT split-K kernel: TF32 operands, stated tolerance 2e-3 of |src|.|d_out| summed over the K extent."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    geoms = dict(GEOMS, conv1_poly_2d_wg=(1, 8, 16, 1, 4, 4, 1, 5, 5, 128, 64, 3))
+    d, h, w, fz, fy, fx, kz, ky, kx, ic, oc, items = geoms[name]
+    geo = UpconvGeom(d, h, w, fz, fy, fx, kz, ky, kx, ic, oc)
+    gen = torch.Generator().manual_seed(7 + len(name))
+    src = torch.randn(items, d, h, w, ic, generator=gen).cuda()
+    d_out = torch.randn(items, d * fz, h * fy, w * fx, oc, generator=gen).cuda()
+    n = fy * fx * 4 * ic * oc
+    ref, got = torch.zeros(n, device="cuda"), torch.full((n,), 3.0, device="cuda")
+    check(lib.rcb_upconv_wgrad(ptr(src), ptr(d_out), ptr(ref), C.byref(geo), items, stream()))
+    rows_in, rows_out = items * h * w, items * h * fy * w * fx
+    srcT, doutT = torch.empty(3, ic, rows_in, device="cuda"), torch.empty(oc, rows_out, device="cuda")
+    check(lib.rcb_transpose_xshift(ptr(src), ptr(srcT), rows_in, ic, w, stream()))
+    check(lib.rcb_transpose_phases(ptr(d_out), ptr(doutT), rows_out, oc, h, w, fy, fx, stream()))
+    padded = torch.nn.functional.pad(src, (0, 0, 1, 1))                      # zeros left and right of every line
+    for k in range(3):
+        assert torch.equal(srcT[k], padded[:, :, :, k:k + w].reshape(rows_in, ic).t())
+    planes = d_out.reshape(items, h, fy, w, fx, oc).permute(5, 0, 2, 4, 1, 3).reshape(oc, rows_out)
+    assert torch.equal(doutT, planes)
+    check(lib.rcb_upconv_wgrad_tc(ptr(srcT), ptr(doutT), ptr(got), C.byref(geo), items, stream()))
+    torch.cuda.synchronize()
+    scale = float(np.sqrt(rows_in)) * 3.0
+    err = float((got - ref).abs().max())
+    print(f"[wgrad_tc {name}] err {err:.2e} (max |ref| {float(ref.abs().max()):.2f}, scale {scale:.1f})")
+    assert err < 2e-3 * scale * 4, (err, scale)
