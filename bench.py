@@ -461,6 +461,15 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to file descriptor 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -469,10 +478,20 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    real_stdout = _quiet_stdout()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    other = [ln for ln in buf.getvalue().splitlines() if not ln.startswith("{")]
+    if other:
+        print("\n".join(other), file=sys.stderr)
+    if lines:
+        real_stdout.write(lines[-1] + "\n")
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
