@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   uint64_t* bar_ready = (uint64_t*)(smem + Sm::BAR);       // [2] epilogue -> MMA (128 arrivals), one per group
   uint64_t* bar_mma = bar_ready + 2;                       // [2] MMA -> epilogue (commit of the stage's MMAs)
   uint32_t* tmem_slot = (uint32_t*)(bar_ready + 4);
+  volatile int* wg_turn = (volatile int*)(tmem_slot + 1);    // [3] next tile allowed to issue its weight-gradient MMAs, per backward stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     mbar_init(&bar_ready[1], MT_GROUP);
     mbar_init(&bar_mma[0], 1);
     mbar_init(&bar_mma[1], 1);
+    wg_turn[0] = wg_turn[1] = wg_turn[2] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     }
   };
   // stages of one tile: 0-2 sine layers, 3 output layer, 4-6 backward
-  auto issue = [&](int stage) {
+  auto issue = [&](int stage, int tile = 0) {
     const bool mine = q == (stage & 3);
     if (mine) {
       mbar_wait(&bar_ready[g], ph_ready);
@@ -328,18 +330,27 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         case 1: chain(R0, R1, Sm::WF + 4096, t32); break;                       // Z1 = X1 W1
         case 2: chain(R1, R0, Sm::WF + 8192, t32); break;                       // Z2 = X2 W2
         case 3: chain(R0, R1, Sm::W3, t16); break;                              // y  = X3 W3
+        // The two groups add into the same weight-gradient accumulators.  The tensor pipe runs MMAs in the order
+        // they are issued, so the tiles take turns (tile t after tile t - 1, per stage): the fp32 summation order,
+        // and with it every bit of the gradients, does not depend on how the groups happen to interleave.
         case 4:
           chain(R0, R1, Sm::WB + 8192, t32);                                    // dX2 = dZ2 W2^T
+          while (wg_turn[0] != tile) {}
           wgrad(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, 2048, h16);             // dW3 = X3^T dy
           wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, 4096, h32);             // dW2 = X2^T dZ2
+          wg_turn[0] = tile + 1;
           break;
         case 5:
           chain(R1, R0, Sm::WB + 4096, t32);                                    // dX1 = dZ1 W1^T
+          while (wg_turn[1] != tile) {}
           wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, 4096, h32);             // dW1 = X1^T dZ1
+          wg_turn[1] = tile + 1;
           break;
         default:
           chain(R0, R1, Sm::WB, t16);                                           // d pe = dZ0 W0[pe rows]^T
+          while (wg_turn[2] != tile) {}
           wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, 4096, h32);                  // dW0 = X0^T dZ0
+          wg_turn[2] = tile + 1;
           break;
       }
       umma_commit(&bar_mma[g]);
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       tmem_st32(tm + R1, dzr);                                           // A operand of dX2
     }
     publish(true);
-    issue(4);
+    issue(4, tile);
     // ---- dZ1 (from R0, in place), dZ0 (from R1, in place) = data gradient * cos; X0^T reloaded for dW0
 #pragma unroll
     for (int l = 1; l >= 0; --l) {
@@ -495,7 +506,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       }
       tmem_st32(reg, acc);
       publish(true);
-      issue(l == 1 ? 5 : 6);
+      issue(l == 1 ? 5 : 6, tile);
     }
     // ---- the group's next tile's inputs travel while the last MMAs of this tile run
     if (tile + 2 < ntiles) load_x0(gp + 256, xin);

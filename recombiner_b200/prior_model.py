@@ -335,10 +335,9 @@ class PriorBNNmodel(nn.Module):
             if training_mappings:
                 g = eng.backward_mappings(ws, N, 1)
                 flat = [g["A"][l][:, :c].contiguous() for l, c in enumerate(eng.counts)] + [g[k] for k in up_names]
-                if world > 1:                # shared mappings: gradients are summed over all rows, ONE all-reduce
-                    bucket = torch.cat([t.reshape(-1) for t in flat])
-                    dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
-                    flat = [c.reshape(t.shape) for c, t in zip(bucket.split([t.numel() for t in flat]), flat)]
+                if world > 1:
+                    for t in flat:           # shared mappings: gradients are summed over all rows
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 for p, t in zip(shared, flat):
                     p.grad = t.reshape(p.shape).clone()
             kl_step.zero_()

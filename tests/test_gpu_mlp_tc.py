@@ -66,3 +66,33 @@ def test_mlp_tc_matches_simt(pix, out, rows, S, wscale):
         close("d_wt", mode)
     ref, got = res[("simt", 1)]["sqerr"], res[("tc", 1)]["sqerr"]
     np.testing.assert_allclose(got, ref, rtol=2e-3)
+
+
+def test_mlp_tc_is_run_to_run_deterministic():
+    """Two groups of a CTA add into the same TMEM weight-gradient accumulators; their MMAs take turns in tile
+    order, so repeated launches on the same inputs must agree bit for bit (sharded and unsharded compression are
+    compared bit for bit in test_gpu_multi.py)."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import MlpArgs, check, stream
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    rows, S, pix, out = 150, 4, 1024, 3
+    items = rows * S
+    n_w = 3 * 1056 + out * 33
+    ld_w = (n_w + 3) // 4 * 4
+    base = dict(wt=torch.zeros(items, ld_w), xt=torch.rand(16, pix, generator=g) * 2 - 1,
+                pe=torch.randn(items, pix, 16, generator=g) * 0.5, y=torch.rand(rows, pix, out, generator=g),
+                dy=torch.zeros(1))
+    base["wt"][:, :n_w] = torch.randn(items, n_w, generator=g) * 0.015
+    outs = []
+    for _ in range(3):
+        t = {k: v.cuda().contiguous() for k, v in base.items()}
+        t.update(y_pred=torch.zeros(1, device="cuda"), d_pe=torch.zeros(items, pix, 16, device="cuda"),
+                 d_wt=torch.zeros(items, ld_w, device="cuda"), sqerr=torch.zeros(items, device="cuda"))
+        a = _args(MlpArgs, items, S, pix, out, ld_w, 1, t, coef=2.0 / (S * pix * out))
+        check(lib.rcb_mlp_tc(C.byref(a), stream()), "rcb_mlp_tc")
+        torch.cuda.synchronize()
+        outs.append((t["d_wt"].clone(), t["d_pe"].clone(), t["sqerr"].clone()))
+    for o in outs[1:]:
+        for a_, b_ in zip(outs[0], o):
+            assert torch.equal(a_, b_)
