@@ -253,6 +253,7 @@ def prior_training_ms(wl, dev, steps=10, warmup=3):
     def run(n):
         m.train(n, 2e-4, x, y, *pri, None, None, None, None, lt, up, 1e-8, True, False)
     run(warmup)
+    run(steps)              # a full-length untimed call: per-call setup (Adam state, allocator growth) is paid here
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
