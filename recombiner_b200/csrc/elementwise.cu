@@ -245,23 +245,37 @@ __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
     const float* src = is_w ? a.d_hw : a.d_lpe;
     if (src && m != 1.f) {
       const int nch = a.row_children ? a.n_children : 1;
-      for (int c = 0; c < nch; ++c) {
-        const int n = a.row_children ? a.row_children[(int64_t)rr * a.n_children + c] : rr;
-        const int64_t gn = a.row_offset + n;
-        for (int s = 0; s < a.S; ++s) {
-          float d, eps;
-          if (is_w) {
-            d = src[((int64_t)n * a.S + s) * a.ld_hw + p];
-            eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
-                          : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
-          } else {
-            const int l = p - a.n_w;
-            d = src[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)];
-            eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
-                          : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
+      // (child row, sample) pairs in the reference's order; eight gradient / noise loads are issued together
+      // (a level-3 row of a patch modality sums over every patch of the datum: hundreds of terms per thread)
+      const int total = nch * a.S;
+      for (int t0 = 0; t0 < total; t0 += 8) {
+        float dv[8], ev[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + u;
+          dv[u] = 0.f; ev[u] = 0.f;
+          if (t < total) {
+            const int c = t / a.S, s = t - c * a.S;
+            const int n = a.row_children ? a.row_children[(int64_t)rr * a.n_children + c] : rr;
+            const int64_t gn = a.row_offset + n;
+            if (is_w) {
+              dv[u] = src[((int64_t)n * a.S + s) * a.ld_hw + p];
+              ev[u] = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
+                              : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
+            } else {
+              const int l = p - a.n_w;
+              dv[u] = src[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)];
+              ev[u] = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
+                              : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
+            }
           }
-          d_mu += d;
-          d_sig = fmaf(d, eps, d_sig);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (t0 + u < total) {
+            d_mu += dv[u];
+            d_sig = fmaf(dv[u], ev[u], d_sig);
+          }
         }
       }
       d_mu *= a.grad_scale * (1.f - m);
