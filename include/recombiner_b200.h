@@ -46,6 +46,20 @@ const char* rcb_last_error(void);
  * p >= n_w : written to lpe[(n*S+s)*n_l + (p-n_w)]            (lpe may be NULL)
  * eps: explicit tensors (eps_w (rows,S,n_w), eps_l (S,rows,n_l)) when non-NULL,
  * else counter-based Philox4x32-10 keyed by (seed, step, tensor_id, element). */
+
+/* Per-step scalars kept in device memory, so that a captured CUDA graph of one fit step can be replayed with a new
+ * noise key and new Adam bias corrections: rcb_set_step_state writes them (arguments by value, stream-ordered),
+ * and kernels given a non-NULL `dyn` read them instead of the by-value fields of their argument block. */
+typedef struct {
+  int64_t seed;            /* Philox key (the fit loop folds the epoch into its low word) */
+  int step;
+  float adam_step_size;    /* lr / (1 - b1^t) */
+  float adam_bc2_sqrt;     /* sqrt(1 - b2^t) */
+  int reserved;
+} rcb_step_state;
+int rcb_set_step_state(rcb_step_state* dev, int64_t seed, int step, float adam_step_size, float adam_bc2_sqrt,
+                       rcb_stream_t stream);
+
 typedef struct {
   const float* loc;        /* (src_rows, P) group order */
   const float* log_scale;  /* (src_rows, P) */
@@ -67,6 +81,7 @@ typedef struct {
   int rows, S, P, n_w, n_l, ld_hw;
   int step, tensor_id, accumulate;
   int rows_per_datum, sp_total, lpe_c;   /* used with lpe_slot */
+  const rcb_step_state* dyn;             /* optional: seed and step read from device memory */
 } rcb_sample_args;
 int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
 
@@ -227,6 +242,7 @@ typedef struct {
   /* Adam: step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are computed by the
    * host in f64 exactly as torch.optim.Adam does, then passed as f32. */
   float adam_step_size, adam_bc2_sqrt, b1, b2, adam_eps, beta_scalar, grad_scale;
+  const rcb_step_state* dyn;             /* optional: seed, step and the Adam scalars read from device memory */
 } rcb_update_args;
 int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream);
 

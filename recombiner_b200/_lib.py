@@ -23,7 +23,7 @@ class SampleArgs(C.Structure):
                                  "eps_w", "eps_l", "hw", "lpe", "lpe_slot", "eps_w_store", "eps_l_store")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate",
-                                   "rows_per_datum", "sp_total", "lpe_c")]
+                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P)]
 
 
 class UpconvGeom(C.Structure):
@@ -45,7 +45,7 @@ class UpdateArgs(C.Structure):
                [(n, I32) for n in ("src_rows", "rows", "n_children", "S", "P", "n_w", "n_l", "ld_hw", "G",
                                    "step", "tensor_id", "adam", "p_scale_direct", "rows_per_datum", "sp_total", "lpe_c")] + \
                [(n, F32) for n in ("adam_step_size", "adam_bc2_sqrt", "b1", "b2", "adam_eps", "beta_scalar",
-                                   "grad_scale")]
+                                   "grad_scale")] + [("dyn", P)]
 
 
 class RecArgs(C.Structure):
@@ -55,13 +55,18 @@ class RecArgs(C.Structure):
                [(n, I32) for n in ("n_pairs", "P", "G", "n_cand", "max_D", "apply")]
 
 
-STRUCTS = {"rcb_sample_args": SampleArgs, "rcb_upconv_geom": UpconvGeom, "rcb_mlp_args": MlpArgs,
+class StepState(C.Structure):
+    _fields_ = [("seed", I64), ("step", I32), ("adam_step_size", F32), ("adam_bc2_sqrt", F32), ("reserved", I32)]
+
+
+STRUCTS = {"rcb_step_state": StepState, "rcb_sample_args": SampleArgs, "rcb_upconv_geom": UpconvGeom, "rcb_mlp_args": MlpArgs,
            "rcb_update_args": UpdateArgs, "rcb_rec_args": RecArgs}
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
     "rcb_version": [],
     "rcb_last_error": [],
+    "rcb_set_step_state": [P, I64, I32, F32, F32, P],
     "rcb_fit_sample": [C.POINTER(SampleArgs), P],
     "rcb_gemm": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, I32, P],
     "rcb_gemm_tc": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],

@@ -18,6 +18,7 @@ __device__ __forceinline__ int64_t lpe_index(const int* slot, int rows_per_datum
 // ----------------------------------------------------------------- sampling --
 // grid: (ceil(P/256), rows).  One thread = one (row, parameter); loops over S.
 __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
+  if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; }
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (p >= a.P) return;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
 // parameter) output is written coalesced, four Philox normals per block.
 // dynamic smem: 4 * P floats.
 __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) {
+  if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; }
   extern __shared__ float sm[];
   float* s_mu = sm;                 // parameter order
   float* s_sig = sm + a.P;
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
 // order (coalesced on the stored state).  Same arithmetic order as update_kernel.
 // dynamic smem: 2 * P floats.
 __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) {
+  if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt; }
   extern __shared__ float sm[];
   float* s_dmu = sm;
   float* s_dsig = sm + a.P;
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) 
 // ------------------------------------------- gradient reduction + KL + Adam --
 // grid: (ceil(P/256), src_rows).  One thread = one stored (row, group-order column).
 __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
+  if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt; }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   float kl_term = 0.f;
@@ -377,6 +381,10 @@ __global__ void pick_block_kernel(const double* __restrict__ kl, const uint8_t* 
   if (lane == 0) block[r] = bi;
 }
 
+__global__ void set_step_state_kernel(rcb_step_state* dev, long long seed, int step, float ss, float bc) {
+  dev->seed = seed; dev->step = step; dev->adam_step_size = ss; dev->adam_bc2_sqrt = bc; dev->reserved = 0;
+}
+
 // ------------------------------------------------------------------ transpose --
 // out[c][r] = in[r][c] through a padded 32 x 32 shared-memory tile (coalesced on both sides).
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in, float* __restrict__ out,
@@ -498,6 +506,14 @@ __global__ void prior_from_stats_kernel(const double* __restrict__ stats, float*
 
 using namespace rcb;
 
+extern "C" int rcb_set_step_state(rcb_step_state* dev, int64_t seed, int step, float adam_step_size,
+                                  float adam_bc2_sqrt, rcb_stream_t stream) {
+  RCB_CHECK_ARG(dev != nullptr, "rcb_set_step_state: null pointer");
+  set_step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev, (long long)seed, step, adam_step_size, adam_bc2_sqrt);
+  RCB_CHECK_LAUNCH("rcb_set_step_state");
+  return 0;
+}
+
 extern "C" int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a != nullptr, "rcb_fit_sample: null args");
   RCB_CHECK_ARG(a->loc && a->log_scale && a->hw, "rcb_fit_sample: null tensor");
@@ -527,7 +543,7 @@ extern "C" int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->beta == nullptr || a->group_idx != nullptr, "rcb_fit_update: per-block beta needs group_idx");
   RCB_CHECK_ARG(a->src_rows > 0 && a->src_rows <= 65535 && a->P > 0, "rcb_fit_update: bad shape");
   if (a->adam) {
-    RCB_CHECK_ARG(a->m1_loc && a->v_loc && a->m1_ls && a->v_ls && a->adam_bc2_sqrt > 0.f, "rcb_fit_update: Adam state missing");
+    RCB_CHECK_ARG(a->m1_loc && a->v_loc && a->m1_ls && a->v_ls && (a->dyn || a->adam_bc2_sqrt > 0.f), "rcb_fit_update: Adam state missing");
   } else {
     RCB_CHECK_ARG(a->g_loc && a->g_log_scale, "rcb_fit_update: gradient outputs missing");
   }

@@ -111,6 +111,11 @@ class LevelState:
         self.row_children = _i32(order.reshape(self.rows, self.n_children), self.device)
 
     def reset_adam(self):
+        if getattr(self, "adam", None) is not None:      # in place: captured fit-step graphs keep these pointers
+            for k in ("m1_loc", "v_loc", "m1_ls", "v_ls"):
+                self.adam[k].zero_()
+            self.adam["t"] = 0
+            return
         z = lambda: torch.zeros(self.rows, self.P, device=self.device)
         self.adam = dict(m1_loc=z(), v_loc=z(), m1_ls=z(), v_ls=z(), t=0)
 
@@ -153,6 +158,8 @@ class _Section:
 class FitEngine:
     """Kernel sequencing for one modality shape (non-patch modalities: cifar, protein)."""
     timer: Optional[SectionTimer] = None
+    map_generation = 0                            # bumped by set_mappings(): invalidates captured steps
+    step_state: Optional[torch.Tensor] = None     # set while a fit step is being captured into a CUDA graph
 
     def section(self, name):
         return _Section(self.timer, name)
@@ -241,12 +248,14 @@ class FitEngine:
         self.pitch_y, self.pitch_z = fp[2], fp[1] * fp[2]
         self._ws: Dict = {}
         self._x_cache = None
+        self._xt_bufs = {}
         self.A = None
 
     # ---------------------------------------------------------------- mappings --
     def set_mappings(self, A_list, up_state):
         """Stage the frozen learned mappings on device: zero-padded A_l and A_l^T, and
         the upsampler with its nearest-upsampling folded into the conv taps."""
+        self.map_generation += 1
         dev = self.device
         st = stream()
         self.A, self.AT = [], []
@@ -316,10 +325,19 @@ class FitEngine:
             shared = True
         else:
             shared = bool((x == x[:1]).all().item())
+        # the transposed copy lives in one buffer per layout, so that captured fit steps (which hold its
+        # address) keep seeing the current x
+        bkey = (shared, tuple(x.shape[1:]) if shared else tuple(x.shape))
+        xt = self._xt_bufs.get(bkey)
+        if xt is None:
+            shape = (self.n_f, self.pix) if shared else (x.shape[0], self.n_f, self.pix)
+            xt = self._xt_bufs[bkey] = torch.empty(shape, device=self.device)
         if shared:
-            xt, stride = x[0].t().contiguous(), 0
+            xt.copy_(x[0].t())
+            stride = 0
         else:
-            xt, stride = x.transpose(1, 2).contiguous(), self.n_f * self.pix
+            xt.copy_(x.transpose(1, 2))
+            stride = self.n_f * self.pix
         self._x_cache = (key, xt, stride)
         return xt, stride
 
@@ -345,6 +363,7 @@ class FitEngine:
         a.rows, a.S, a.P, a.n_w, a.ld_hw = rows, S, lv.P, self.W, self.ldw
         a.n_l = self.L if lv.level == 0 else 0
         a.step, a.tensor_id, a.accumulate = noise.step, lv.level, int(lv.level > 0)
+        a.dyn = ptr(self.step_state)
         check(self.lib.rcb_fit_sample(C.byref(a), stream()), "rcb_fit_sample")
 
     def _gemm(self, A, a_off, lda, B, ldb, Cm, c_off, ldc, M, N, K, bias=None, bias_mod=1, act=0, trans_a=0, acc=0,
@@ -424,6 +443,11 @@ class FitEngine:
             self._upconv_fwd(2, ws["a2"], ws["pe"], citems, 0)
         join()
         return ws
+
+    def set_step_state(self, buf: torch.Tensor, seed: int, step: int, adam: dict, t: int):
+        """Write the per-step scalars a captured fit step reads from device memory (rcb_step_state)."""
+        check(self.lib.rcb_set_step_state(ptr(buf), seed, step, adam["lr"] / (1.0 - adam["b1"] ** t),
+                                          math.sqrt(1.0 - adam["b2"] ** t), stream()), "rcb_set_step_state")
 
     def _fork(self, fn):
         """Run fn on the side stream, ordered after everything queued so far on the current stream;
@@ -602,10 +626,12 @@ class FitEngine:
         a.step, a.tensor_id = noise.step, lv.level
         a.beta_scalar, a.grad_scale = float(lv.beta_scalar), grad_scale
         a.p_scale_direct = int(lv.p_scale_direct)
+        a.dyn = ptr(self.step_state)
         if adam is not None:
             st_ = lv.adam
-            st_["t"] += 1
-            t = st_["t"]
+            if self.step_state is None:      # a captured step gets t from set_step_state(); its caller counts
+                st_["t"] += 1
+            t = max(st_["t"], 1)
             a.adam = 1
             a.m1_loc, a.v_loc, a.m1_ls, a.v_ls = ptr(st_["m1_loc"]), ptr(st_["v_loc"]), ptr(st_["m1_ls"]), ptr(st_["v_ls"])
             a.b1, a.b2, a.adam_eps = adam["b1"], adam["b2"], adam["eps"]

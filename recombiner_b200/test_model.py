@@ -15,7 +15,9 @@ librecombiner_b200.so (no CPU fallback, no torch autograd graph in the loop):
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -24,7 +26,7 @@ from torch import nn
 
 from . import rec as _rec
 from .engine import FitEngine, LevelState, Noise
-from ._lib import KernelError
+from ._lib import COUNTERS, KernelError, StepState
 from .utils import count_net_params, metric
 
 
@@ -230,6 +232,8 @@ class TestBNNmodel(nn.Module):
         self._tables = None
         self._generation = 0
         self._adam_owner = None
+        self._graphs = {}
+        self.use_graph = os.environ.get("RECOMBINER_GRAPH", "1") != "0"
 
     # ------------------------------------------------------- reference attributes --
     kl_beta = property(lambda self: self._levels[0].beta, lambda self, v: self._set_beta(0, v))
@@ -438,26 +442,80 @@ class TestBNNmodel(nn.Module):
         return dict(lr=float(g.get("lr", 2e-4)), b1=float(b1), b2=float(b2), eps=float(g.get("eps", 1e-8)))
 
     def fit_step(self, x, y, epoch, adam_cfg, sample_size=5, eps=None, anneal=None):
-        """One fused step: forward, loss, backward, (annealing), Adam (test_model.py:622-635)."""
+        """One fused step: forward, loss, backward, (annealing), Adam (test_model.py:622-635).
+
+        With Philox noise the kernel sequence of a step depends on the epoch only through the noise key and the
+        Adam bias corrections, so from the second step of a configuration on it is replayed from a captured CUDA
+        graph with those scalars in device memory (rcb_step_state); RECOMBINER_GRAPH=0 keeps every step eager."""
+        levels, eng = self._levels, self.engine
+        do_anneal = bool((epoch % self.kl_adjust_gap == 0) if anneal is None else anneal)
+        for lv in levels:
+            if lv.adam is None:
+                lv.reset_adam()
+        if self.use_graph and eps is None and eng.timer is None and not torch.cuda.is_current_stream_capturing():
+            ws = self._fit_step_graph(x, y, epoch, adam_cfg, sample_size, do_anneal)
+            if ws is not None:
+                return ws
+        return self._fit_step_eager(x, y, self._noise(epoch, eps), adam_cfg, sample_size, do_anneal)
+
+    def _fit_step_eager(self, x, y, noise, adam_cfg, S, do_anneal):
         levels, eng = self._levels, self.engine
         rows = levels[0].rows
-        S = sample_size
-        noise = self._noise(epoch, eps)
         ws = eng.forward_features(levels, S, noise)
         # d/dy of N * mean_{n,s,pix,c} (y_pred - y)^2
         coef = 2.0 / (S * eng.pix * eng.out)
         eng.mlp(ws, rows, S, x, mode=1, y=y, coef=coef)
         eng.backward_features(ws, rows, S)
-        do_anneal = (epoch % self.kl_adjust_gap == 0) if anneal is None else anneal
         for lv in levels:
-            if lv.adam is None:
-                lv.reset_adam()
             if do_anneal:
                 eng.group_kl(lv)            # KL of the pre-step posterior ...
             eng.update(lv, ws, S, noise, with_data_grads=True, adam=adam_cfg, rows=rows)
             if do_anneal:                   # ... beta changes only after this step's gradient (test_model.py:629-634)
                 eng.anneal(lv, self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer,
                            float(self.bit_per_group))
+        return ws
+
+    _GRAPH_CACHE = 8
+
+    def _fit_step_graph(self, x, y, epoch, adam_cfg, S, do_anneal):
+        levels, eng = self._levels, self.engine
+        t = levels[0].adam["t"]
+        if any(lv.adam["t"] != t for lv in levels):
+            return None
+        # everything a captured step holds by value or by pointer
+        xt, x_stride = eng.prepare_x(x)
+        key = (S, do_anneal, xt.data_ptr(), x_stride, y.data_ptr(), tuple(y.shape),
+               adam_cfg["b1"], adam_cfg["b2"], adam_cfg["eps"], self.row_offset, eng.map_generation,
+               self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer, float(self.bit_per_group)) + \
+            tuple(v for lv in levels for v in (
+                lv.loc.data_ptr(), lv.log_scale.data_ptr(), lv.mask.data_ptr(), lv.sample.data_ptr(),
+                lv.p_loc.data_ptr(), lv.p_log_scale.data_ptr(), lv.beta.data_ptr(), lv.coded.data_ptr(),
+                lv.adam["m1_loc"].data_ptr(), float(lv.beta_scalar), lv.rows))
+        noise = self._noise(epoch)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if key not in self._graphs:          # first sight: run eagerly (sizes workspaces, x cache, TMA maps)
+                if len(self._graphs) >= self._GRAPH_CACHE:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = None
+                return None
+            state = torch.zeros(C.sizeof(StepState), dtype=torch.uint8, device=self.device)      # rcb_step_state
+            graph = torch.cuda.CUDAGraph()
+            eng.step_state = state
+            n0 = COUNTERS["launches"]
+            try:
+                with torch.cuda.graph(graph):
+                    ws = self._fit_step_eager(x, y, noise, adam_cfg, S, do_anneal)
+            finally:
+                eng.step_state = None
+            entry = self._graphs[key] = (graph, state, ws, COUNTERS["launches"] - n0)
+            COUNTERS["launches"] = n0
+        graph, state, ws, n_kernels = entry
+        eng.set_step_state(state, noise.seed, noise.step, adam_cfg, t + 1)
+        graph.replay()
+        COUNTERS["launches"] += n_kernels
+        for lv in levels:
+            lv.adam["t"] = t + 1
         return ws
 
     def train(self, x=True, y=None, n_epochs=0, optimizer=None, verbose=False, sample_size=5):

@@ -247,3 +247,35 @@ def test_full_size_patch_modalities_match_oracle(name, dataset, S):
     for pre, key in (("", "lvl1"), ("h_", "lvl2"), ("hh_", "lvl3")):
         _grad_close(getattr(m, pre + "loc").grad.cpu().numpy(), lv[key].loc.grad.numpy())
         _grad_close(getattr(m, pre + "log_scale").grad.cpu().numpy(), lv[key].log_scale.grad.numpy())
+
+
+@pytest.mark.parametrize("name,dataset,n_data,S,precision", [("cifar", "cifar", 6, 3, "fp32"),
+                                                           ("cifar", "cifar", 6, 3, "tf32"),
+                                                           ("patch2d", "kodak", 1, 2, "fp32")])
+def test_graph_replayed_steps_equal_eager_steps(name, dataset, n_data, S, precision):
+    """train() replays captured fit steps (noise key and Adam bias corrections from rcb_step_state); the
+    posteriors, Adam moments and betas must be bit-identical to launching every step eagerly, across
+    annealing steps, an optimizer reset and a change of the coded mask."""
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case(name, n_data, S, coded_frac=0.0)
+    x, y = case["x"].cuda(), case["y"].cuda()
+    models = []
+    for use_graph in (False, True):
+        m = product_test_model(case, dataset, precision=precision)
+        m.use_graph = use_graph
+        m.kl_adjust_gap = 4
+        for rnd in range(2):
+            opt = torch.optim.Adam(m.parameters(), lr=2e-4 * (rnd + 1))
+            m.train(x=x, y=y, n_epochs=11, optimizer=opt, sample_size=S)
+            if rnd == 0:                        # code one block of every row, in place, as compress_round does
+                for lv in m._levels:
+                    lv.mask[:, : lv.P // 3] = 1
+        models.append(m)
+    eager, graphed = models
+    assert any(v is not None for v in graphed._graphs.values()) and not eager._graphs
+    for le, lg in zip(eager._levels, graphed._levels):
+        assert le.adam["t"] == lg.adam["t"] == 11
+        assert torch.equal(le.loc.data, lg.loc.data) and torch.equal(le.log_scale.data, lg.log_scale.data)
+        assert torch.equal(le.beta, lg.beta)
+        for k in ("m1_loc", "v_loc", "m1_ls", "v_ls"):
+            assert torch.equal(le.adam[k], lg.adam[k])

@@ -120,7 +120,7 @@ def test_checkpoint_classes_have_reference_layout():
     from recombiner_b200.prior_model import LinearTransform, Upsample
     lt = LinearTransform([32, 32, 32, 32, 3])
     assert [tuple(a.shape) for a in lt.A] == [(1056, 1056)] * 3 + [(99, 99)]
-    assert all(float(a.abs().max()) <= 1.0 / a.shape[0] for a in lt.A)
+    assert all(float(a.detach().abs().max()) <= (1.0 + 1e-6) / a.shape[0] for a in lt.A)    # fp32 rounding of 1/n
     up = Upsample(2, [2, 1, 1], [4, 2, 2])
     assert sorted(up.state_dict()) == sorted(f"conv{i}.{k}" for i in (1, 2, 3) for k in ("weight", "bias"))
     assert tuple(up.conv1.weight.shape) == (64, 128, 5, 5) and tuple(up.conv3.weight.shape) == (16, 64, 3, 3)
