@@ -145,6 +145,13 @@ int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const float* bias,
                       const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
 int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
                       const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+/* The x2 / 3-tap / 64 -> 16 channel stage (the last one of the 2-D upsamplers, prior_model.py:47-59) with fp16
+ * source activations and fp16 weights (rcb_to_half of w_eff_k): fp16 keeps the same 10 mantissa bits the TF32
+ * MMAs read of an fp32 operand, at half the bytes.  fp32 accumulation, bias, activation and output. */
+int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, const float* bias, float* out,
+                        const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
+/* dst[i] = (fp16, round to nearest) src[i] */
+int rcb_to_half(const float* src, void* dst, int64_t n, rcb_stream_t stream);
 
 /* Weight gradients of the learned mappings (prior training only; the mappings are
  * frozen at compression time).  Autograd backward of prior_model.py:48-57,173-174.

@@ -431,6 +431,232 @@ upconv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------- forward, factor 2, resident weights --
+// The last upsampler stage (x2, 3-tap) is where the forward pass moves most of its bytes.  A tile's 16
+// (phase, tap) products read only 9 distinct shifts of the halo tile, and products that share a shift differ only
+// in the weight rows.  With the four phase accumulators laid side by side in TMEM in the order
+// (0,0) (0,1) (1,1) (1,0), phases that share a shift are neighbours, so one MMA of N = members * oc serves them
+// all: 10 MMAs per k-step instead of 16 (the tensor core's shared-memory operand read, ~128 B/clk, is what
+// bounds these thin-N MMAs).  The weights (16 oc-row blocks per k-block, 64 KB for 64 -> 16 channels) are loaded
+// once per CTA; the CTAs are persistent (one per SM), walk the tiles round-robin, and keep two accumulator sets
+// so that the epilogue of a tile runs under the MMAs of the next.
+constexpr int F2_GROUPS = 10, F2_STAGES = 4;
+struct ConvF2Args {
+  PolyGeom g;
+  int items, tiles_x, tiles_y, n_tiles;
+  int kblocks, act;
+  int w_bytes_kb;                       // bytes of resident weights per k-block: 16 blocks of oc rows x 128 B
+  int a_off, epi_off, bar_off;          // shared-memory layout
+  int grp_shift[F2_GROUPS];             // halo row shift of the group's A operand
+  int grp_col[F2_GROUPS];               // first accumulator column (within one accumulator set)
+  int grp_n[F2_GROUPS];                 // MMA N
+  int grp_row[F2_GROUPS];               // first weight row of the group within a k-block
+  int mem_phase[16], mem_tap[16];       // weight block b (oc rows) = w_eff_k[mem_phase[b]][:, mem_tap[b]]
+  int phase_col[4];                     // accumulator column of phase ry * 2 + rx
+  const float* bias;
+  float* out;
+};
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_f16_m128(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// HALF: the source activations and the weights are fp16 (the 10-bit mantissa TF32 keeps of an fp32 operand anyway):
+// 64 channels per 128-byte row, kind::f16 MMAs, half the shared-memory operand bytes per MMA.
+template <bool HALF>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+upconv_fwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvF2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + a.bar_off);        // [F2_STAGES]
+  uint64_t* a_empty = a_full + F2_STAGES;                   // [F2_STAGES]
+  uint64_t* acc_full = a_empty + F2_STAGES;                 // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2], one arrival per epilogue warp
+  uint64_t* w_full = acc_empty + 2;                         // [1]
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PolyGeom& g = a.g;
+  const int OC = g.oc;
+  const int acc_cols = 4 * OC;
+  constexpr int KC = HALF ? 64 : 32;                        // channels per 128-byte operand row
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < F2_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int t, int& item, int& y0, int& x0) {
+    x0 = (t % a.tiles_x) * 8; t /= a.tiles_x;
+    y0 = (t % a.tiles_y) * 16; t /= a.tiles_y;
+    item = t;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: the resident weights, then one halo tile per (tile, k-block)
+    if (elect_one()) {
+      mbar_expect_tx(w_full, (uint32_t)(a.kblocks * a.w_bytes_kb));
+      for (int kb = 0; kb < a.kblocks; ++kb)
+        for (int b = 0; b < 16; ++b)
+          tma_load_2d(&tmB, w_full, smem + kb * a.w_bytes_kb + b * OC * 128, a.mem_tap[b] * g.ic + kb * KC, a.mem_phase[b] * OC);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t par = 1;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        mbar_wait(&a_empty[s], par);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[s], HALO_BYTES);
+          tma_load_5d(&tmA, &a_full[s], smem + a.a_off + s * HALO_BUF, kb * KC, x0 - 1, y0 - 1, 0, item);
+        }
+        __syncwarp();
+        if (++s == F2_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    uint32_t idesc[F2_GROUPS];
+#pragma unroll
+    for (int j = 0; j < F2_GROUPS; ++j) idesc[j] = HALF ? idesc_f16_m128(a.grp_n[j]) : idesc_tf32(a.grp_n[j]);
+    mbar_wait(w_full, 0);
+    int s = 0;
+    uint32_t par = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols);
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        mbar_wait(&a_full[s], par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + a.a_off + s * HALO_BUF);
+          const uint32_t w_addr = smem_u32(smem + kb * a.w_bytes_kb);
+#pragma unroll
+          for (int j = 0; j < F2_GROUPS; ++j) {
+            const uint64_t da = da_hi | (uint64_t)(((a_addr + (uint32_t)a.grp_shift[j] * 128u) & 0x3FFFF) >> 4);
+            const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)a.grp_row[j] * 128u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { // group 0 covers every column, so it alone starts the accumulation
+              if (HALF) umma_f16_ss(acc + (uint32_t)a.grp_col[j], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc[j], (kb | j | k) ? 1u : 0u);
+              else umma_tf32(acc + (uint32_t)a.grp_col[j], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc[j], (kb | j | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[s]);
+          if (kb == a.kblocks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == F2_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: row m = (line m / 8, pixel m % 8) of the tile.  The two phases of an output line are
+    // adjacent in memory (2 * oc = 32 floats = 128 B per source pixel), so each warp stages its 32 rows as
+    // 128-byte swizzled rows -- bias and LeakyReLU applied in registers -- and one TMA store per output line
+    // parity writes them out (the store clips ragged tiles); two staging buffers per warp.
+    const int q = warp & 3;
+    uint8_t* stage = smem + a.epi_off + q * 2 * 4096;
+    float bias[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + j));
+      bias[j] = b4.x; bias[j + 1] = b4.y; bias[j + 2] = b4.z; bias[j + 3] = b4.w;
+    }
+    const float slope = a.act ? 0.01f : 1.0f;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols);
+#pragma unroll
+      for (int ry = 0; ry < 2; ++ry) {
+        uint32_t v[2][16];
+        tmem_ld16_nowait(acc + (uint32_t)a.phase_col[ry * 2], v[0]);
+        tmem_ld16_nowait(acc + (uint32_t)a.phase_col[ry * 2 + 1], v[1]);
+        if (lane == 0) bulk_wait_read<1>();                // this buffer's previous store has left shared memory
+        __syncwarp();
+        tmem_wait_ld();
+        if (ry == 1) {                                     // accumulators drained: the next tile but one may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+        }
+        uint8_t* row = stage + ry * 4096 + lane * 128;
+#pragma unroll
+        for (int rx = 0; rx < 2; ++rx)
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float f = __uint_as_float(v[rx][j + e]) + bias[j + e];
+              o[e] = f > 0.f ? f : slope * f;
+            }
+            const int chunk = (rx * 4 + (j >> 2)) ^ (lane & 7);
+            *reinterpret_cast<float4*>(row + chunk * 16) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_5d(&tmO, stage + ry * 4096, 0, x0, ry, y0 + q * 4, item);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 #ifdef RCB_CONV_PROFILE
 extern "C" int rcb_conv_prof_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, rcb::rcb_conv_prof, sizeof(long long) * 256); }
 #endif
@@ -623,31 +849,32 @@ static ConvTile choose_tile(const PolyGeom& g, int items, int lim_x, int lim_y, 
 }
 
 // 5-D map over a channel-last activation tensor (items, D, H, W, C), optional traversal strides
-static int make_map_5d(CUtensorMap* map, const float* base, int items, int D, int H, int W, int C, const ConvTile& t,
-                       int box_c, int sz, int sy, int sx, CUtensorMapSwizzle swz) {
+static int make_map_5d(CUtensorMap* map, const void* base, int items, int D, int H, int W, int C, const ConvTile& t,
+                       int box_c, int sz, int sy, int sx, CUtensorMapSwizzle swz, int esize = 4) {
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)items};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)D * H * W * C * 4};
+  const cuuint64_t es = (cuuint64_t)esize;
+  cuuint64_t strides[4] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es, (cuuint64_t)D * H * W * C * es};
   cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(t.tx * sx), (cuuint32_t)(t.ty * sy), (cuuint32_t)(t.tz * sz), (cuuint32_t)t.ni};
   cuuint32_t estr[5] = {1, (cuuint32_t)sx, (cuuint32_t)sy, (cuuint32_t)sz, 1};
   // a strided box of extent n*s covers exactly n elements only if it does not run past the last one
   for (int i = 1; i < 4; ++i) box[i] = box[i] - (estr[i] - 1);
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(5d) failed with CUresult %d", (int)r); return -1; }
   return 0;
 }
 
-static int make_map_b(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, int box_cols,
-                      CUtensorMapSwizzle swz) {
+static int make_map_b(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int box_cols,
+                      CUtensorMapSwizzle swz, int esize = 4) {
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (cuuint64_t)esize};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return -1; }
   return 0;
@@ -657,6 +884,75 @@ template <class K>
 static int opt_in_smem(K kernel, const char* name) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) { set_error("%s: smem opt-in failed: %s", name, cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+// x2 stage with 16 output channels: persistent CTAs, resident weights, phases that share a shift in one MMA
+static bool f2_eligible(const PolyGeom& g, bool half) {
+  return g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16 && g.fy == 2 && g.fx == 2 && g.py == 1 && g.px == 1 &&
+         g.oc == 16 && g.ic <= 64 && g.ic % (half ? 64 : 32) == 0;
+}
+static int launch_f2(const void* src, const void* w_eff_k, const float* bias, float* out, const PolyGeom& g, int items,
+                     int act, rcb_stream_t stream, bool half) {
+  ConvF2Args f;
+  f.g = g; f.items = items;
+  f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
+  f.n_tiles = f.tiles_x * f.tiles_y * items;
+  const int KC = half ? 64 : 32, es = half ? 2 : 4;
+  f.kblocks = g.ic / KC; f.act = act; f.bias = bias; f.out = out;
+  f.w_bytes_kb = 16 * g.oc * 128;
+  // accumulator order (ry, rx) = (0,0) (0,1) (1,1) (1,0); a phase's tap for the shift (dy, dx) is
+  // (dy - base_y(ry), dx - base_x(rx)) with base(0) = -1, base(1) = 0
+  const int order[4] = {0, 1, 3, 2};
+  for (int i = 0; i < 4; ++i) f.phase_col[order[i]] = i * g.oc;
+  // groups: {dy, dx, first slot, members}
+  const int groups[F2_GROUPS][4] = {{0, 0, 0, 4}, {-1, 0, 0, 2}, {0, 1, 1, 2}, {1, 0, 2, 2}, {0, -1, 0, 1},
+                                    {0, -1, 3, 1}, {-1, -1, 0, 1}, {-1, 1, 1, 1}, {1, 1, 2, 1}, {1, -1, 3, 1}};
+  int nb = 0;
+  for (int j = 0; j < F2_GROUPS; ++j) {
+    const int dy = groups[j][0], dx = groups[j][1], slot = groups[j][2], mem = groups[j][3];
+    f.grp_shift[j] = (1 + dy) * HALO_PITCH + (1 + dx);
+    f.grp_col[j] = slot * g.oc;
+    f.grp_n[j] = mem * g.oc;
+    f.grp_row[j] = nb * g.oc;
+    for (int i = 0; i < mem; ++i, ++nb) {
+      const int ph = order[slot + i], ry = ph >> 1, rx = ph & 1;
+      const int ty = dy - (ry == 0 ? -1 : 0), tx = dx - (rx == 0 ? -1 : 0);
+      RCB_CHECK_ARG(nb < 16 && ty >= 0 && ty < 2 && tx >= 0 && tx < 2, "rcb_upconv_fwd_tc: bad shift table");
+      f.mem_phase[nb] = ph; f.mem_tap[nb] = ty * 2 + tx;
+    }
+  }
+  RCB_CHECK_ARG(nb == 16, "rcb_upconv_fwd_tc: bad shift table");
+  f.a_off = f.kblocks * f.w_bytes_kb;
+  f.epi_off = f.a_off + F2_STAGES * HALO_BUF;
+  f.bar_off = f.epi_off + 4 * 2 * 4096;            // per epilogue warp: two buffers of 32 rows x 128 B
+  const int smem_total = f.bar_off + 512 + 1024;
+  ConvTile box;
+  box.tx = HALO_PITCH; box.ty = HALO_LINES; box.tz = 1; box.ni = 1; box.ntx = box.nty = box.ntz = 1;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, box, KC, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B, es)) return rc;
+  if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, KC,
+                          CU_TENSOR_MAP_SWIZZLE_128B, es)) return rc;
+  CUtensorMap tmO;                            // out as (item, y, line parity, x, 2 * oc): one 128-byte row per source pixel
+  {
+    EncodeTiledFn enc = tc_get_encode();
+    const cuuint64_t W2 = 2 * (cuuint64_t)g.oc, line = (cuuint64_t)g.w * W2 * 4;
+    cuuint64_t dims[5] = {W2, (cuuint64_t)g.w, 2, (cuuint64_t)g.h, (cuuint64_t)items};
+    cuuint64_t strides[4] = {W2 * 4, line, 2 * line, (cuuint64_t)g.h * 2 * line};
+    cuuint32_t obox[5] = {(cuuint32_t)W2, 8, 1, 4, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims, strides, obox, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed with CUresult %d", (int)r); return -1; }
+  }
+  if (int rc = half ? opt_in_smem(upconv_fwd_f2_kernel<true>, "rcb_upconv_fwd_tc") : opt_in_smem(upconv_fwd_f2_kernel<false>, "rcb_upconv_fwd_tc")) return rc;
+  static int n_sm = 0;
+  if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
+  if (half) upconv_fwd_f2_kernel<true><<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  else upconv_fwd_f2_kernel<false><<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc");
   return 0;
 }
 
@@ -672,6 +968,7 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   RCB_CHECK_ARG(src && w_eff_k && bias && out, "rcb_upconv_fwd_tc: null pointer");
   RCB_CHECK_ARG(g.ic % 32 == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
   if (items <= 0) return 0;
+  if (f2_eligible(g, false) && !getenv("RCB_NO_F2")) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, false);
   if (g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
     // 2-D grid with full 8 x 16 tiles: halo-tile kernel
     ConvHaloArgs h;
@@ -724,6 +1021,18 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   upconv_fwd_tc_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, a);
   RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc");
   return 0;
+}
+
+// fp16 source activations and fp16 K-major weights (rcb_to_half of the rcb_fold_poly_k output); only the x2 / 16-channel
+// stage that launch_f2 covers.
+extern "C" int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, const float* bias, float* out,
+                                   const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(src_h && w_eff_k_h && bias && out, "rcb_upconv_fwd_tc_h: null pointer");
+  RCB_CHECK_ARG(f2_eligible(g, true), "rcb_upconv_fwd_tc_h: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
+  if (items <= 0) return 0;
+  return launch_f2(src_h, w_eff_k_h, bias, out, g, items, act, stream, true);
 }
 
 // w_eff: [phase][tap][ic][oc] as produced by rcb_fold_poly (already K-major for this GEMM).

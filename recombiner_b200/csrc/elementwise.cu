@@ -1,6 +1,7 @@
 // HBM-bound kernels of the fit path: reparameterised sampling, sample-reduction +
 // KL gradient + Adam, per-block KL sums, beta annealing, block selection, and the
 // EM sufficient statistics of prior training.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace rcb {
@@ -381,6 +382,13 @@ __global__ void pick_block_kernel(const double* __restrict__ kl, const uint8_t* 
   if (lane == 0) block[r] = bi;
 }
 
+__global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (i0 + e < n) dst[i0 + e] = __float2half_rn(src[i0 + e]);
+}
+
 __global__ void set_step_state_kernel(rcb_step_state* dev, long long seed, int step, float ss, float bc) {
   dev->seed = seed; dev->step = step; dev->adam_step_size = ss; dev->adam_bc2_sqrt = bc; dev->reserved = 0;
 }
@@ -589,6 +597,15 @@ extern "C" int rcb_pick_block(const double* kl, const uint8_t* coded, int* block
   if (rows <= 0) return 0;
   pick_block_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(kl, coded, block, rows, G);
   RCB_CHECK_LAUNCH("rcb_pick_block");
+  return 0;
+}
+
+extern "C" int rcb_to_half(const float* src, void* dst, int64_t n, rcb_stream_t stream) {
+  RCB_CHECK_ARG(src && dst && n > 0, "rcb_to_half: bad arguments");
+  const int64_t blocks = (n + 1023) / 1024;
+  RCB_CHECK_ARG(blocks < (1ll << 31), "rcb_to_half: tensor too large");
+  to_half_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n);
+  RCB_CHECK_LAUNCH("rcb_to_half");
   return 0;
 }
 

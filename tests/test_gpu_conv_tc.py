@@ -20,6 +20,9 @@ GEOMS = {
     "wide_2d_ragged": (1, 5, 200, 1, 2, 2, 1, 3, 3, 64, 64, 1),
     "video_conv2_3d": (3, 4, 4, 2, 2, 2, 3, 3, 3, 64, 64, 4),
     "video_conv1_3d": (1, 2, 2, 6, 4, 4, 5, 5, 5, 128, 64, 2),
+    # persistent x2 kernel: ragged tiles, more than two tiles per CTA (both accumulator sets re-used)
+    "f2_many_tiles": (1, 40, 44, 1, 2, 2, 1, 3, 3, 64, 16, 20),
+    "f2_oc32": (1, 16, 24, 1, 2, 2, 1, 3, 3, 32, 32, 3),
 }
 
 
@@ -93,3 +96,37 @@ def test_upconv_wgrad_tc_matches_simt(name):
     err = float((got - ref).abs().max())
     print(f"[wgrad_tc {name}] err {err:.2e} (max |ref| {float(ref.abs().max()):.2f}, scale {scale:.1f})")
     assert err < 2e-3 * scale * 4, (err, scale)
+
+
+@pytest.mark.parametrize("h,w,items", [(16, 16, 5), (40, 44, 20)])
+def test_upconv_fwd_fp16_operands_match_simt_on_rounded_inputs(h, w, items):
+    """rcb_upconv_fwd_tc_h (fp16 activations and weights, fp32 accumulation) against the fp32 SIMT engine run on
+    the same fp16-rounded activations: what is left is the fp16 rounding of the weights and the summation order."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    ic, oc = 64, 16
+    geo = UpconvGeom(1, h, w, 1, 2, 2, 1, 3, 3, ic, oc)
+    gen = torch.Generator().manual_seed(h * w)
+    wt = (torch.randn(oc, ic, 1, 3, 3, generator=gen) / np.sqrt(ic * 9)).cuda()
+    bias = torch.randn(oc, generator=gen).cuda()
+    src = torch.randn(items, 1, h, w, ic, generator=gen).cuda()
+    n = 4 * 4 * ic * oc
+    w_eff, w_eff_t, w_eff_k = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_k(ptr(wt), C.byref(geo), ptr(w_eff_k), stream()))
+    src_h = torch.empty(src.shape, dtype=torch.float16, device="cuda")
+    w_h = torch.empty(n, dtype=torch.float16, device="cuda")
+    check(lib.rcb_to_half(ptr(src), ptr(src_h), src.numel(), stream()))
+    check(lib.rcb_to_half(ptr(w_eff_k), ptr(w_h), n, stream()))
+    assert torch.equal(src_h, src.half()) and torch.equal(w_h, w_eff_k.half())
+    out_shape = (items, 1, 2 * h, 2 * w, oc)
+    ref = torch.zeros(out_shape, device="cuda")
+    got = torch.full(out_shape, 3.0, device="cuda")
+    src_r = src_h.float().contiguous()
+    check(lib.rcb_upconv_fwd(ptr(src_r), ptr(w_eff), ptr(bias), ptr(ref), C.byref(geo), items, 1, stream()))
+    check(lib.rcb_upconv_fwd_tc_h(ptr(src_h), ptr(w_h), ptr(bias), ptr(got), C.byref(geo), items, 1, stream()))
+    torch.cuda.synchronize()
+    scale = float(src.norm(dim=-1).max()) * float(wt.flatten(1).norm(dim=1).max())
+    err = float((got - ref).abs().max())
+    assert err < 1e-3 * scale, (err, scale)
