@@ -150,6 +150,12 @@ int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_a
  * MMAs read of an fp32 operand, at half the bytes.  fp32 accumulation, bias, activation and output. */
 int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, const float* bias, float* out,
                         const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
+/* rcb_upconv_fwd_tc writing its activations as fp16 (for a following rcb_upconv_fwd_tc_h stage), and
+ * rcb_upconv_bwd_tc reading the LeakyReLU mask from such fp16 activations (only the signs are used). */
+int rcb_upconv_fwd_tc_oh(const float* src, const float* w_eff_k, const float* bias, void* out_h,
+                         const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
+int rcb_upconv_bwd_tc_ah(const float* d_out, const float* w_eff, const void* src_act_h, float* d_src,
+                         const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 /* dst[i] = (fp16, round to nearest) src[i] */
 int rcb_to_half(const float* src, void* dst, int64_t n, rcb_stream_t stream);
 

@@ -10,10 +10,16 @@
 //             one CTA = 128 source pixels, K = phases*taps*oc
 // Warp roles as in gemm_tc.cu.  Reference semantics: prior_model.py:47-59.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "gemm_engine.cuh"
 #include "tc_common.cuh"
 
 namespace rcb {
+
+__device__ __forceinline__ uint2 pack_h4(const float4& o) {
+  const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
 
 struct ConvTile {
   int tx, ty, tz, ni;            // box extent in source pixels / items (tx*ty*tz*ni <= 128)
@@ -28,6 +34,8 @@ struct ConvTcArgs {
   int kblocks;                   // k-blocks per (phase[,tap]) unit
   int bk;                        // 32 (128B swizzle) or 16 (64B swizzle)
   int act;
+  int out_half;                  // forward: out is fp16 (the next stage reads it as an fp16 MMA operand)
+  int act_half;                  // backward: src_act is fp16
   int b_off, stage_bytes, bar_off;   // shared-memory layout (bytes): B tile offset in a stage, stage size, barriers
   int nstages, epi_off;              // forward: ring depth and the epilogue staging area (4 warps x 32 x (oc + 4) floats)
   const float* bias;             // forward
@@ -198,7 +206,8 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               o.x = o.x > 0.f ? o.x : 0.01f * o.x; o.y = o.y > 0.f ? o.y : 0.01f * o.y;
               o.z = o.z > 0.f ? o.z : 0.01f * o.z; o.w = o.w > 0.f ? o.w : 0.01f * o.w;
             }
-            *reinterpret_cast<float4*>(a.out + bb[u] + ph_off + ch) = o;
+            if (a.out_half) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + bb[u] + ph_off + ch) = pack_h4(o);
+            else *reinterpret_cast<float4*>(a.out + bb[u] + ph_off + ch) = o;
           }
         }
       }
@@ -224,7 +233,7 @@ struct ConvHaloArgs {
   PolyGeom g;
   int items, tiles_x, tiles_y;
   int phases_per_cta, kblocks;         // kblocks = ic / 32
-  int act;
+  int act, out_half;
   int b_bytes, nbs;                    // weight ring: nbs stages of taps x (oc x 128 B)
   int a_off, bar_off;                  // shared-memory layout
   const float* bias;
@@ -389,8 +398,9 @@ upconv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               f.x = f.x > 0.f ? f.x : 0.01f * f.x; f.y = f.y > 0.f ? f.y : 0.01f * f.y;
               f.z = f.z > 0.f ? f.z : 0.01f * f.z; f.w = f.w > 0.f ? f.w : 0.01f * f.w;
             }
-            float* dst = a.out + (((int64_t)item * g.h * g.fy + (int64_t)y * g.fy + ry) * Wo + (int64_t)x * g.fx) * OC + ch;
-            *reinterpret_cast<float4*>(dst) = f;
+            const int64_t off = (((int64_t)item * g.h * g.fy + (int64_t)y * g.fy + ry) * Wo + (int64_t)x * g.fx) * OC + ch;
+            if (a.out_half) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + off) = pack_h4(f);
+            else *reinterpret_cast<float4*>(a.out + off) = f;
           }
         }
         __syncwarp();
@@ -399,10 +409,10 @@ upconv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int m = q * 32 + lane;
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
       const bool valid = y < g.h && x < g.w;
-      float* obase = a.out + (((int64_t)item * g.h * g.fy + (int64_t)y * g.fy) * Wo + (int64_t)x * g.fx) * OC;
+      const int64_t obase = (((int64_t)item * g.h * g.fy + (int64_t)y * g.fy) * Wo + (int64_t)x * g.fx) * OC;
       int ry = ph0 / g.fx, rx = ph0 - ry * g.fx;
       for (int p = 0; p < nph; ++p) {
-        float* orow = obase + ry * row_pitch + rx * OC;
+        const int64_t orow = obase + ry * row_pitch + rx * OC;
         for (int c0 = 0; c0 < OC; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * OC + c0), v);
@@ -416,7 +426,9 @@ upconv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
                 for (int tt = 0; tt < 4; ++tt) o[tt] = o[tt] > 0.f ? o[tt] : 0.01f * o[tt];
               }
-              *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+              const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+              if (a.out_half) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + orow + c0 + j) = pack_h4(o4);
+              else *reinterpret_cast<float4*>(a.out + orow + c0 + j) = o4;
             }
           }
         }
@@ -759,17 +771,26 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int nsteps = 32 / rows_per_iter;
       for (int s0 = 0; s0 < nsteps; s0 += 8) {            // eight loads in flight per lane
         float4 s4[8];
+        uint2 h2[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int rr = (s0 + u) * rows_per_iter + sub;
           const int64_t mm = __shfl_sync(0xffffffffu, m, rr & 31);
-          s4[u] = (s0 + u < nsteps && sub < rows_per_iter && mm >= 0)
-                      ? __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool ok = s0 + u < nsteps && sub < rows_per_iter && mm >= 0;
+          if (a.act_half)
+            h2[u] = ok ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.src_act) + mm * IC + ch)) : make_uint2(0u, 0u);
+          else
+            s4[u] = ok ? __ldg(reinterpret_cast<const float4*>(a.src_act + mm * IC + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int step = s0 + u;
-          const uint64_t b = (uint64_t)((s4[u].x > 0.f ? 1u : 0u) | (s4[u].y > 0.f ? 2u : 0u) | (s4[u].z > 0.f ? 4u : 0u) | (s4[u].w > 0.f ? 8u : 0u));
+          uint64_t b;
+          if (a.act_half)       // an fp16 is positive exactly when its bits are a positive int16
+            b = (uint64_t)(((short)(h2[u].x & 0xffffu) > 0 ? 1u : 0u) | ((int)h2[u].x >= 0x10000 ? 2u : 0u) |
+                           ((short)(h2[u].y & 0xffffu) > 0 ? 4u : 0u) | ((int)h2[u].y >= 0x10000 ? 8u : 0u));
+          else
+            b = (uint64_t)((s4[u].x > 0.f ? 1u : 0u) | (s4[u].y > 0.f ? 2u : 0u) | (s4[u].z > 0.f ? 4u : 0u) | (s4[u].w > 0.f ? 8u : 0u));
           if (step < 16) lrelu_bits[0] |= b << ((step & 15) * 4);
           else lrelu_bits[1] |= b << ((step & 15) * 4);
         }
@@ -961,14 +982,14 @@ static int launch_f2(const void* src, const void* w_eff_k, const float* bias, fl
 using namespace rcb;
 
 // w_eff_k: forward weights in K-major form [phase][oc][tap*ic] (rcb_fold_poly_k).
-extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const float* bias, float* out,
-                                 const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
+static int upconv_fwd_tc_impl(const float* src, const float* w_eff_k, const float* bias, float* out,
+                              const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream, int out_half) {
   PolyGeom g;
   if (int rc = make_geom_tc(geo, &g)) return rc;
   RCB_CHECK_ARG(src && w_eff_k && bias && out, "rcb_upconv_fwd_tc: null pointer");
   RCB_CHECK_ARG(g.ic % 32 == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
   if (items <= 0) return 0;
-  if (f2_eligible(g, false) && !getenv("RCB_NO_F2")) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, false);
+  if (f2_eligible(g, false) && !out_half && !getenv("RCB_NO_F2")) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, false);
   if (g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
     // 2-D grid with full 8 x 16 tiles: halo-tile kernel
     ConvHaloArgs h;
@@ -979,7 +1000,7 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
     if (ppc > g.phases()) ppc = g.phases();
     h.phases_per_cta = ppc;
     h.kblocks = g.ic / 32;
-    h.act = act; h.bias = bias; h.out = out;
+    h.act = act; h.out_half = out_half; h.bias = bias; h.out = out;
     h.b_bytes = (g.oc * 128 + 1023) / 1024 * 1024;
     h.nbs = 24576 / (4 * h.b_bytes);            // about 24 KB of weight ring, at least double-buffered
     if (h.nbs > HALO_NBS_MAX) h.nbs = HALO_NBS_MAX;
@@ -1009,7 +1030,7 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   a.phases_per_cta = ppc;
   a.kblocks = g.ic / 32;
   a.bk = 32;
-  a.act = act; a.bias = bias; a.src_act = nullptr; a.out = out;
+  a.act = act; a.out_half = out_half; a.act_half = 0; a.bias = bias; a.src_act = nullptr; a.out = out;
   int smem_total;
   smem_layout(&a, 128, g.oc, &smem_total, 3, 4 * 32 * (g.oc + 4) * 4);
   CUtensorMap tmA, tmB;
@@ -1021,6 +1042,16 @@ extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const f
   upconv_fwd_tc_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, a);
   RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc");
   return 0;
+}
+
+extern "C" int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const float* bias, float* out,
+                                 const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
+  return upconv_fwd_tc_impl(src, w_eff_k, bias, out, geo, items, act, stream, 0);
+}
+// same, writing the activations as fp16 for a following rcb_upconv_fwd_tc_h stage
+extern "C" int rcb_upconv_fwd_tc_oh(const float* src, const float* w_eff_k, const float* bias, void* out_h,
+                                    const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
+  return upconv_fwd_tc_impl(src, w_eff_k, bias, reinterpret_cast<float*>(out_h), geo, items, act, stream, 1);
 }
 
 // fp16 source activations and fp16 K-major weights (rcb_to_half of the rcb_fold_poly_k output); only the x2 / 16-channel
@@ -1036,8 +1067,8 @@ extern "C" int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, con
 }
 
 // w_eff: [phase][tap][ic][oc] as produced by rcb_fold_poly (already K-major for this GEMM).
-extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
-                                 const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+static int upconv_bwd_tc_impl(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
+                              const rcb_upconv_geom* geo, int items, rcb_stream_t stream, int act_half) {
   PolyGeom g;
   if (int rc = make_geom_tc(geo, &g)) return rc;
   RCB_CHECK_ARG(d_out && w_eff && d_src, "rcb_upconv_bwd_tc: null pointer");
@@ -1052,7 +1083,7 @@ extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const f
   const int bk = (g.oc == 16) ? 16 : 32;
   a.bk = bk;
   a.kblocks = g.oc / bk;
-  a.act = 0; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
+  a.act = 0; a.out_half = 0; a.act_half = act_half; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
   int smem_total;
   smem_layout(&a, bk * 4, g.ic, &smem_total);
   RCB_CHECK_ARG(4 * 32 * (g.ic + 4) * 4 <= a.bar_off, "rcb_upconv_bwd_tc: epilogue staging does not fit the pipeline stages");
@@ -1070,6 +1101,16 @@ extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const f
   }
   RCB_CHECK_LAUNCH("rcb_upconv_bwd_tc");
   return 0;
+}
+extern "C" int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
+                                 const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  return upconv_bwd_tc_impl(d_out, w_eff, src_act, d_src, geo, items, stream, 0);
+}
+// same, with the producing stage's activations stored as fp16 (rcb_upconv_fwd_tc_oh): only their signs are read
+extern "C" int rcb_upconv_bwd_tc_ah(const float* d_out, const float* w_eff, const void* src_act_h, float* d_src,
+                                    const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  RCB_CHECK_ARG(src_act_h != nullptr, "rcb_upconv_bwd_tc_ah: null activations");
+  return upconv_bwd_tc_impl(d_out, w_eff, reinterpret_cast<const float*>(src_act_h), d_src, geo, items, stream, 1);
 }
 
 // ===================================================================== weight gradient ====

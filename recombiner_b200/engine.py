@@ -176,6 +176,11 @@ class FitEngine:
         # the reparameterisation GEMMs (hw <-> wt) and the upsampler chain (lpe <-> pe) are independent
         # between the sampling kernel and the MLP: run them on two streams
         self.overlap = os.environ.get("RECOMBINER_OVERLAP", "1") != "0"
+        # conv2's activations are only ever read as MMA operands (conv3) and for their signs (LeakyReLU mask):
+        # where conv3 has the fp16-operand kernel they are stored as fp16 -- the 10 mantissa bits a TF32 MMA
+        # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
+        self.half_acts = self.tc_conv and os.environ.get("RECOMBINER_HALF_ACTS", "1") != "0"
+        self.f2_half = False
         self._side = None
         if not torch.cuda.is_available():
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -284,6 +289,12 @@ class FitEngine:
             if self.tc_conv:
                 self.w_eff_k[i] = torch.empty(n, device=dev)
                 check(self.lib.rcb_fold_poly_k(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff_k[i]), st), "rcb_fold_poly_k")
+        g3 = self.geoms[2]
+        self.f2_half = bool(self.tc_conv and self.data_dim == 2 and g3.d == 1 and g3.fy == 2 and g3.fx == 2 and g3.ky == 3
+                            and g3.kx == 3 and g3.ic == 64 and g3.oc == 16 and g3.h >= 16)
+        if self.f2_half:
+            self.w3_kh = torch.empty(self.w_eff_k[2].numel(), dtype=torch.float16, device=dev)
+            check(self.lib.rcb_to_half(ptr(self.w_eff_k[2]), ptr(self.w3_kh), self.w3_kh.numel(), st), "rcb_to_half")
 
     # -------------------------------------------------------------- workspaces --
     def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
@@ -437,10 +448,21 @@ class FitEngine:
                            citems, self.M1.shape[1], Lt, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
             else:
                 self._upconv_fwd(0, ws["lpe"], ws["a1"], citems, 1)
+        half = ws["a2_is_half"] = bool(self.half_acts and self.f2_half)
+        if half and "a2h" not in ws:
+            ws["a2h"] = torch.empty(ws["a2"].shape, dtype=torch.float16, device=self.device)
         with self.section("conv2_fwd"):
-            self._upconv_fwd(1, ws["a1"], ws["a2"], citems, 1)
+            if half:
+                check(self.lib.rcb_upconv_fwd_tc_oh(ptr(ws["a1"]), ptr(self.w_eff_k[1]), ptr(self.conv_b[1]), ptr(ws["a2h"]),
+                                                    C.byref(g2), citems, 1, stream()), "rcb_upconv_fwd_tc_oh[2]")
+            else:
+                self._upconv_fwd(1, ws["a1"], ws["a2"], citems, 1)
         with self.section("conv3_fwd"):
-            self._upconv_fwd(2, ws["a2"], ws["pe"], citems, 0)
+            if half:
+                check(self.lib.rcb_upconv_fwd_tc_h(ptr(ws["a2h"]), ptr(self.w3_kh), ptr(self.conv_b[2]), ptr(ws["pe"]),
+                                                   C.byref(g3), citems, 0, stream()), "rcb_upconv_fwd_tc_h[3]")
+            else:
+                self._upconv_fwd(2, ws["a2"], ws["pe"], citems, 0)
         join()
         return ws
 
@@ -504,7 +526,11 @@ class FitEngine:
                                ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])
         join = self._fork(reparam)
         with self.section("conv3_bwd"):
-            self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
+            if ws.get("a2_is_half"):
+                check(self.lib.rcb_upconv_bwd_tc_ah(ptr(ws["d_pe"]), ptr(self.w_eff[2]), ptr(ws["a2h"]), ptr(ws["d_a2"]),
+                                                    C.byref(g3), citems, stream()), "rcb_upconv_bwd_tc_ah[3]")
+            else:
+                self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
         with self.section("conv2_bwd"):
             self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
         with self.section("conv1_bwd"):
@@ -520,6 +546,8 @@ class FitEngine:
         """Gradients of the learned mappings (prior training): dA_l = hw_l^T d_wt_l, and the
         upsampler's conv weights/biases through the adjoints of the folds.  Call after
         backward_features (it consumes d_pe, d_a2, d_a1, d_wt)."""
+        if ws.get("a2_is_half"):
+            raise KernelError("the mapping gradients read the upsampler activations in fp32: set engine.half_acts = False")
         items = rows * S
         citems = ws["citems"]
         st = stream()

@@ -158,6 +158,7 @@ class PriorBNNmodel(nn.Module):
                                 layer_scales if layer_scales is not None else [4, 2, 2],
                                 paddings if paddings is not None else [2, 1, 1], w0, dev, precision=precision,
                                 patch_nums=patch_nums if patch else None)
+        self.engine.half_acts = False         # the weight gradients of the upsampler read its activations in fp32
         zero = torch.zeros(W + L)
         self._lv = LevelState(self._loc_all, self._log_scale_all, zero, zero, None, None, None, None, None, 0.0, dev)
         self._lv.p_scale_direct = True

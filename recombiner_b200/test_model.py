@@ -485,7 +485,7 @@ class TestBNNmodel(nn.Module):
         # everything a captured step holds by value or by pointer
         xt, x_stride = eng.prepare_x(x)
         key = (S, do_anneal, xt.data_ptr(), x_stride, y.data_ptr(), tuple(y.shape),
-               adam_cfg["b1"], adam_cfg["b2"], adam_cfg["eps"], self.row_offset, eng.map_generation,
+               adam_cfg["b1"], adam_cfg["b2"], adam_cfg["eps"], self.row_offset, eng.map_generation, eng.half_acts,
                self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer, float(self.bit_per_group)) + \
             tuple(v for lv in levels for v in (
                 lv.loc.data_ptr(), lv.log_scale.data_ptr(), lv.mask.data_ptr(), lv.sample.data_ptr(),
