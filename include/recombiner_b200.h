@@ -156,6 +156,12 @@ int rcb_upconv_fwd_tc_oh(const float* src, const float* w_eff_k, const float* bi
                          const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
 int rcb_upconv_bwd_tc_ah(const float* d_out, const float* w_eff, const void* src_act_h, float* d_src,
                          const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+/* Data gradient of the same x2 / 3-tap / 64 -> 16 channel stage with the 64 x 256 weight matrix resident in shared
+ * memory (w_bwd_k = rcb_fold_poly_bwd_f2 of the rcb_fold_poly output).  act_kind: 0 no LeakyReLU mask, 1 src_act is
+ * the producing stage's fp32 activations, 2 its fp16 activations. */
+int rcb_fold_poly_bwd_f2(const float* w_eff, const rcb_upconv_geom* g, float* w_bwd_k, rcb_stream_t stream);
+int rcb_upconv_bwd_f2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, float* d_src,
+                      const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 /* dst[i] = (fp16, round to nearest) src[i] */
 int rcb_to_half(const float* src, void* dst, int64_t n, rcb_stream_t stream);
 

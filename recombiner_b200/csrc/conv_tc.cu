@@ -844,6 +844,239 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// --------------------------------------- data gradient, factor 2, resident weights --
+// The adjoint of the stage above.  A source pixel s receives from the 4 x 4 output pixels 2s - 1 + (a, b):
+//   d_src[s][ic] = mask(s, ic) * sum_{a, b, oc} d_out[2s - 1 + (a, b)][oc] * W[a][b][oc][ic]
+// Seen as (item, y, line parity ry, x, (column parity rx, oc)) the output gradient has one dense 128-byte row per
+// source pixel and line parity, so the (8 + 2) x (16 + 2) neighbourhood of a tile travels as TWO halo boxes (ry = 0, 1)
+// and every (a, b) product reads a row-shifted window of one of them: a <-> (ry, dy) = (1,-1) (0,0) (1,0) (0,+1), and
+// likewise b <-> (rx, dx), where rx picks the 64-byte half of the row.  The 64 x 256 weight matrix (64 KB) stays in
+// shared memory; CTAs are persistent, accumulators double-buffered, the result leaves through TMA stores.
+constexpr int B2_STAGES = 4;
+struct ConvB2Args {
+  PolyGeom g;
+  int items, tiles_x, tiles_y, n_tiles;
+  int act_kind;                          // LeakyReLU mask of the producing stage: 0 none, 1 fp32, 2 fp16 activations
+  int a_off, epi_off, bar_off;
+  const void* src_act;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// w_bwd_k[ic][a * 64 + b * 16 + oc] = w_eff[phase (ry_a, rx_b)][tap (ty_a, tx_b)][ic][oc]
+__global__ void fold_bwd_f2_kernel(const float* __restrict__ w_eff, float* __restrict__ w_bwd_k, int ic, int oc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = 16 * oc;
+  if (e >= ic * K) return;
+  const int c = e / K, k = e - c * K;
+  const int a = k / (4 * oc), b = (k / oc) & 3, o = k % oc;
+  const int ry = (a == 0 || a == 2) ? 1 : 0, ty = (a < 2) ? 1 : 0;
+  const int rx = (b == 0 || b == 2) ? 1 : 0, tx = (b < 2) ? 1 : 0;
+  w_bwd_k[e] = w_eff[((size_t)((ry * 2 + rx) * 4 + ty * 2 + tx) * ic + c) * oc + o];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvB2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + a.bar_off);        // [B2_STAGES]
+  uint64_t* a_empty = a_full + B2_STAGES;
+  uint64_t* acc_full = a_empty + B2_STAGES;                 // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2], one arrival per epilogue warp
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+  constexpr int IC = 64, W_BLOCK = IC * 128;                // one 32-wide K block of the weights
+  constexpr uint32_t TMEM_COLS = 128;                       // two accumulator sets of 64 columns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PolyGeom& g = a.g;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int t, int& item, int& y0, int& x0) {
+    x0 = (t % a.tiles_x) * 8; t /= a.tiles_x;
+    y0 = (t % a.tiles_y) * 16; t /= a.tiles_y;
+    item = t;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights once, then the two halo boxes (line parity 0, 1) of every tile
+    if (elect_one()) {
+      mbar_expect_tx(w_full, 8u * W_BLOCK);
+      for (int kb = 0; kb < 8; ++kb) tma_load_2d(&tmB, w_full, smem + kb * W_BLOCK, kb * 32, 0);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t par = 1;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      for (int ry = 0; ry < 2; ++ry) {
+        mbar_wait(&a_empty[s], par);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[s], HALO_BYTES);
+          tma_load_5d(&tmA, &a_full[s], smem + a.a_off + s * HALO_BUF, 0, x0 - 1, ry, y0 - 1, item);
+        }
+        __syncwarp();
+        if (++s == B2_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint32_t idesc = idesc_tf32(IC);
+    const uint32_t w_addr = smem_u32(smem);
+    mbar_wait(w_full, 0);
+    int s = 0;
+    uint32_t par = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * IC);
+#pragma unroll
+      for (int ry = 0; ry < 2; ++ry) {
+        mbar_wait(&a_full[s], par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + a.a_off + s * HALO_BUF);
+#pragma unroll
+          for (int ai = 0; ai < 2; ++ai) {
+            // line parity 0 serves a = 1 (dy = 0) and a = 3 (dy = +1); parity 1 serves a = 2 (dy = 0) and a = 0 (dy = -1)
+            const int aa = ry == 0 ? (ai == 0 ? 1 : 3) : (ai == 0 ? 2 : 0);
+            const int dy = ry == 0 ? (ai == 0 ? 0 : 1) : (ai == 0 ? 0 : -1);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int rx = (b == 0 || b == 2) ? 1 : 0;
+              const int dx = b == 0 ? -1 : (b == 3 ? 1 : 0);
+              const uint32_t shift_rows = (uint32_t)((1 + dy) * HALO_PITCH + (1 + dx));
+              const uint64_t da = (da_hi | (uint64_t)(((a_addr + shift_rows * 128u) & 0x3FFFF) >> 4)) + (uint64_t)(rx * 4);
+              const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)((aa * 2 + (b >> 1)) * W_BLOCK)) + (uint64_t)((b & 1) * 4);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_tf32(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ry | ai | b | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[s]);
+          if (ry == 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == B2_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: row m = (line m / 8, pixel m % 8); mask bits fetched while the MMAs run; 32 rows x 32 channels
+    // staged as swizzled 128-byte rows per TMA store
+    const int q = warp & 3;
+    uint8_t* stage = smem + a.epi_off + q * 2 * 4096;
+    uint8_t* scratch = smem + a.epi_off + 4 * 2 * 4096 + q * 512;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      // LeakyReLU mask of this warp's 32 pixel rows (4 lines x 8 pixels): coalesced loads (consecutive lanes on
+      // consecutive 16-byte chunks), sign bits exchanged through a small shared-memory scratch so that each lane
+      // ends up with the 64 bits of its own row
+      uint64_t bits = ~0ull;
+      if (a.act_kind == 2) {
+        uint4 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                       // load i: half a line = 4 pixels x 8 chunks of 8 halves
+          const int yy = y0 + q * 4 + (i >> 1), xx = x0 + (i & 1) * 4 + (lane >> 3);
+          h[i] = (yy < g.h && xx < g.w)
+                     ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
+                                                            (((int64_t)item * g.h + yy) * g.w + xx) * IC) + (lane & 7))
+                     : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t w4[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
+          uint32_t b8 = 0u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)                       // an fp16 is positive exactly when its bits are a positive int16
+            b8 |= (((short)(w4[e] & 0xffffu) > 0 ? 1u : 0u) | ((int)w4[e] >= 0x10000 ? 2u : 0u)) << (e * 2);
+          scratch[i * 32 + lane] = (uint8_t)b8;             // = [pixel i * 4 + lane / 8][chunk lane % 8]
+        }
+        __syncwarp();
+        bits = *reinterpret_cast<const uint64_t*>(scratch + lane * 8);
+        __syncwarp();
+      } else if (a.act_kind == 1) {                         // fp32 activations: each lane walks its own 256-byte row
+        bits = 0ull;
+        const int m = q * 32 + lane;
+        const int y = y0 + (m >> 3), x = x0 + (m & 7);
+        if (y < g.h && x < g.w) {
+          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.src_act) + (((int64_t)item * g.h + y) * g.w + x) * IC);
+#pragma unroll
+          for (int c0 = 0; c0 < 16; c0 += 8) {
+            float4 f[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f[c] = __ldg(p + c0 + c);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint64_t b4 = (f[c].x > 0.f ? 1ull : 0ull) | (f[c].y > 0.f ? 2ull : 0ull) | (f[c].z > 0.f ? 4ull : 0ull) | (f[c].w > 0.f ? 8ull : 0ull);
+              bits |= b4 << ((c0 + c) * 4);
+            }
+          }
+        }
+      }
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * IC);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[2][16];
+        tmem_ld16_nowait(acc + (uint32_t)(hh * 32), v[0]);
+        tmem_ld16_nowait(acc + (uint32_t)(hh * 32 + 16), v[1]);
+        if (lane == 0) bulk_wait_read<1>();                // this buffer's previous store has left shared memory
+        __syncwarp();
+        tmem_wait_ld();
+        if (hh == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+        }
+        uint8_t* row = stage + hh * 4096 + lane * 128;
+        const uint32_t hb = (uint32_t)(bits >> (hh * 32));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((hb >> (c * 4 + e)) & 1u) ? 1.f : 0.01f);
+          *reinterpret_cast<float4*>(row + ((c ^ (lane & 7)) * 16)) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmO, stage + hh * 4096, hh * 32, x0, y0 + q * 4, item);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // ---------------------------------------------------------------------------------- host --
 static int make_geom_tc(const rcb_upconv_geom* g, PolyGeom* out) {
   RCB_CHECK_ARG(g != nullptr, "upconv_tc: null geometry");
@@ -977,6 +1210,56 @@ static int launch_f2(const void* src, const void* w_eff_k, const float* bias, fl
   return 0;
 }
 
+static bool b2_eligible(const PolyGeom& g) {
+  return g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16 && g.fy == 2 && g.fx == 2 && g.py == 1 && g.px == 1 &&
+         g.oc == 16 && g.ic == 64;
+}
+static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const char* what) {
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return -1; }
+  return 0;
+}
+static int launch_b2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, float* d_src,
+                     const PolyGeom& g, int items, rcb_stream_t stream) {
+  ConvB2Args f;
+  f.g = g; f.items = items;
+  f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
+  f.n_tiles = f.tiles_x * f.tiles_y * items;
+  f.act_kind = src_act ? act_kind : 0; f.src_act = src_act;
+  f.a_off = 8 * 64 * 128;
+  f.epi_off = f.a_off + B2_STAGES * HALO_BUF;
+  f.bar_off = f.epi_off + 4 * 2 * 4096 + 4 * 512;     // staging buffers + the mask scratch of the four epilogue warps
+  const int smem_total = f.bar_off + 512 + 1024;
+  CUtensorMap tmA, tmB, tmO;
+  {   // d_out as (item, y, line parity, x, (column parity, oc)): one 128-byte row per source pixel and line parity
+    const cuuint64_t line = (cuuint64_t)g.w * 128;
+    cuuint64_t dims[5] = {32, (cuuint64_t)g.w, 2, (cuuint64_t)g.h, (cuuint64_t)items};
+    cuuint64_t strides[4] = {128, line, 2 * line, (cuuint64_t)g.h * 2 * line};
+    cuuint32_t box[5] = {32, HALO_PITCH, 1, HALO_LINES, 1};
+    if (int rc = encode_map(&tmA, d_out, 5, dims, strides, box, "d_out")) return rc;
+  }
+  if (int rc = make_map_b(&tmB, w_bwd_k, 64, 256, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  {
+    cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
+    cuuint64_t strides[3] = {256, (cuuint64_t)g.w * 256, (cuuint64_t)g.h * g.w * 256};
+    cuuint32_t box[4] = {32, 8, 4, 1};
+    if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
+  }
+  if (int rc = opt_in_smem(upconv_bwd_f2_kernel, "rcb_upconv_bwd_f2")) return rc;
+  static int n_sm = 0;
+  if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
+  upconv_bwd_f2_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  RCB_CHECK_LAUNCH("rcb_upconv_bwd_f2");
+  return 0;
+}
+
 }  // namespace rcb
 
 using namespace rcb;
@@ -1064,6 +1347,29 @@ extern "C" int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, con
   RCB_CHECK_ARG(f2_eligible(g, true), "rcb_upconv_fwd_tc_h: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
   if (items <= 0) return 0;
   return launch_f2(src_h, w_eff_k_h, bias, out, g, items, act, stream, true);
+}
+
+// Data gradient of the x2 / 3-tap / 64 -> 16 channel stage with resident weights.  w_bwd_k: rcb_fold_poly_bwd_f2 of w_eff.
+// act_kind: 0 no mask, 1 src_act holds fp32 activations, 2 fp16 activations (rcb_upconv_fwd_tc_oh).
+extern "C" int rcb_fold_poly_bwd_f2(const float* w_eff, const rcb_upconv_geom* geo, float* w_bwd_k, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(w_eff && w_bwd_k, "rcb_fold_poly_bwd_f2: null pointer");
+  RCB_CHECK_ARG(b2_eligible(g), "rcb_fold_poly_bwd_f2: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
+  const int n = g.ic * 16 * g.oc;
+  fold_bwd_f2_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w_eff, w_bwd_k, g.ic, g.oc);
+  RCB_CHECK_LAUNCH("rcb_fold_poly_bwd_f2");
+  return 0;
+}
+extern "C" int rcb_upconv_bwd_f2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, float* d_src,
+                                 const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(d_out && w_bwd_k && d_src, "rcb_upconv_bwd_f2: null pointer");
+  RCB_CHECK_ARG(act_kind >= 0 && act_kind <= 2, "rcb_upconv_bwd_f2: act_kind must be 0, 1 or 2");
+  RCB_CHECK_ARG(b2_eligible(g), "rcb_upconv_bwd_f2: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
+  if (items <= 0) return 0;
+  return launch_b2(d_out, w_bwd_k, src_act, act_kind, d_src, g, items, stream);
 }
 
 // w_eff: [phase][tap][ic][oc] as produced by rcb_fold_poly (already K-major for this GEMM).

@@ -295,6 +295,8 @@ class FitEngine:
         if self.f2_half:
             self.w3_kh = torch.empty(self.w_eff_k[2].numel(), dtype=torch.float16, device=dev)
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[2]), ptr(self.w3_kh), self.w3_kh.numel(), st), "rcb_to_half")
+            self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
+            check(self.lib.rcb_fold_poly_bwd_f2(ptr(self.w_eff[2]), C.byref(g3), ptr(self.w3_bk), st), "rcb_fold_poly_bwd_f2")
 
     # -------------------------------------------------------------- workspaces --
     def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
@@ -526,9 +528,11 @@ class FitEngine:
                                ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])
         join = self._fork(reparam)
         with self.section("conv3_bwd"):
-            if ws.get("a2_is_half"):
-                check(self.lib.rcb_upconv_bwd_tc_ah(ptr(ws["d_pe"]), ptr(self.w_eff[2]), ptr(ws["a2h"]), ptr(ws["d_a2"]),
-                                                    C.byref(g3), citems, stream()), "rcb_upconv_bwd_tc_ah[3]")
+            if self.f2_half:
+                half = bool(ws.get("a2_is_half"))
+                check(self.lib.rcb_upconv_bwd_f2(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"] if half else ws["a2"]),
+                                                 2 if half else 1, ptr(ws["d_a2"]), C.byref(g3), citems, stream()),
+                      "rcb_upconv_bwd_f2[3]")
             else:
                 self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
         with self.section("conv2_bwd"):

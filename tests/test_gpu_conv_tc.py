@@ -130,3 +130,32 @@ def test_upconv_fwd_fp16_operands_match_simt_on_rounded_inputs(h, w, items):
     scale = float(src.norm(dim=-1).max()) * float(wt.flatten(1).norm(dim=1).max())
     err = float((got - ref).abs().max())
     assert err < 1e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("h,w,items", [(16, 16, 5), (40, 44, 20)])
+@pytest.mark.parametrize("act_kind", [0, 1, 2])
+def test_upconv_bwd_f2_matches_simt(h, w, items, act_kind):
+    """Resident-weight x2 data-gradient kernel against the fp32 SIMT engine; LeakyReLU mask absent, from fp32 and
+    from fp16 activations (the mask only reads signs, so both must agree with the SIMT kernel on the rounded ones)."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    ic, oc = 64, 16
+    geo = UpconvGeom(1, h, w, 1, 2, 2, 1, 3, 3, ic, oc)
+    gen = torch.Generator().manual_seed(h + w + act_kind)
+    wt = (torch.randn(oc, ic, 1, 3, 3, generator=gen) / np.sqrt(ic * 9)).cuda()
+    n = 4 * 4 * ic * oc
+    w_eff, w_eff_t, w_bk = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_bwd_f2(ptr(w_eff), C.byref(geo), ptr(w_bk), stream()))
+    d_out = torch.randn(items, 1, 2 * h, 2 * w, oc, generator=gen).cuda()
+    act = torch.randn(items, 1, h, w, ic, generator=gen).cuda().half().float()
+    act_arg = {0: None, 1: act, 2: act.half()}[act_kind]
+    ref = torch.zeros_like(act)
+    got = torch.full_like(act, 3.0)
+    check(lib.rcb_upconv_bwd(ptr(d_out), ptr(w_eff_t), ptr(act if act_kind else None), ptr(ref), C.byref(geo), items, stream()))
+    check(lib.rcb_upconv_bwd_f2(ptr(d_out), ptr(w_bk), ptr(act_arg), act_kind, ptr(got), C.byref(geo), items, stream()))
+    torch.cuda.synchronize()
+    scale = float(d_out.norm(dim=-1).max()) * float(wt.norm()) / np.sqrt(ic) * 4
+    err = float((got - ref).abs().max())
+    assert err < 2e-3 * scale, (err, scale)
