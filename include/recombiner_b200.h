@@ -103,6 +103,10 @@ int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, in
                 int M, int N, int K, const float* bias, int bias_mod, int act,
                 int accumulate, rcb_stream_t stream);
 
+/* rcb_gemm_tc with C written as fp16 (ldc in fp16 elements, N % 4 == 0, no accumulation into C). */
+int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt, void* C_h, int ldc,
+                   int M, int N, int K, const float* bias, int bias_mod, int act, rcb_stream_t stream);
+
 /* Geometry of one nearest-upsample + 'same' conv stage on a channel-last grid
  * (item, d, h, w, c).  2-D signals use d=1, fz=1, kz=1; 1-D also h=1, fy=1, ky=1.
  * prior_model.py:29-45. */
@@ -146,10 +150,14 @@ int rcb_upconv_fwd_tc(const float* src, const float* w_eff_k, const float* bias,
 int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_act, float* d_src,
                       const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 /* The x2 / 3-tap / 64 -> 16 channel stage (the last one of the 2-D upsamplers, prior_model.py:47-59) with fp16
- * source activations and fp16 weights (rcb_to_half of w_eff_k): fp16 keeps the same 10 mantissa bits the TF32
+ * source activations and fp16 weights (rcb_to_half of w_eff_k; other stages with ic % 64 == 0 run the general kernel
+ * with kind::f16 MMAs): fp16 keeps the same 10 mantissa bits the TF32
  * MMAs read of an fp32 operand, at half the bytes.  fp32 accumulation, bias, activation and output. */
 int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, const float* bias, float* out,
                         const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
+/* fp16 in and fp16 out (any stage with ic % 64 == 0; the general kernel with kind::f16 MMAs) */
+int rcb_upconv_fwd_tc_hh(const void* src_h, const void* w_eff_k_h, const float* bias, void* out_h,
+                         const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
 /* rcb_upconv_fwd_tc writing its activations as fp16 (for a following rcb_upconv_fwd_tc_h stage), and
  * rcb_upconv_bwd_tc reading the LeakyReLU mask from such fp16 activations (only the signs are used). */
 int rcb_upconv_fwd_tc_oh(const float* src, const float* w_eff_k, const float* bias, void* out_h,

@@ -75,6 +75,8 @@ SIGNATURES = {
     "rcb_fold_poly_k": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_upconv_fwd_tc": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_fwd_tc_h": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
+    "rcb_upconv_fwd_tc_hh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
+    "rcb_gemm_tc_oh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
     "rcb_upconv_fwd_tc_oh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd_tc_ah": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_fold_poly_bwd_f2": [P, C.POINTER(UpconvGeom), P, P],

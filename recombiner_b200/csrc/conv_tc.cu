@@ -21,6 +21,19 @@ __device__ __forceinline__ uint2 pack_h4(const float4& o) {
   return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
 }
 
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_f16_m128(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
 struct ConvTile {
   int tx, ty, tz, ni;            // box extent in source pixels / items (tx*ty*tz*ni <= 128)
   int ntx, nty, ntz;             // tiles per axis
@@ -35,6 +48,7 @@ struct ConvTcArgs {
   int bk;                        // 32 (128B swizzle) or 16 (64B swizzle)
   int act;
   int out_half;                  // forward: out is fp16 (the next stage reads it as an fp16 MMA operand)
+  int in_half;                   // forward: src and the weights are fp16 (64 channels per 128-byte row, kind::f16)
   int act_half;                  // backward: src_act is fp16
   int b_off, stage_bytes, bar_off;   // shared-memory layout (bytes): B tile offset in a stage, stage size, barriers
   int nstages, epi_off;              // forward: ring depth and the epilogue staging area (4 warps x 32 x (oc + 4) floats)
@@ -93,7 +107,8 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tile_origin(a, blockIdx.x, item0, z0, y0, x0);
   const int ph0 = blockIdx.y * a.phases_per_cta;
   const int nph = min(a.phases_per_cta, g.phases() - ph0);
-  const int kb_per_phase = g.taps() * a.kblocks;          // kblocks = ic / 32
+  const int kb_per_phase = g.taps() * a.kblocks;          // kblocks = ic / KC
+  const int KC = a.in_half ? 64 : 32;                     // channels per 128-byte operand row
   const uint32_t a_bytes = (uint32_t)(a.t.tx * a.t.ty * a.t.tz * a.t.ni) * 128u;
   const uint32_t b_bytes = (uint32_t)OC * 128u;
   uint32_t tmem_cols = 32;
@@ -127,15 +142,15 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               if (elect_one()) {
                 uint8_t* a_dst = smem + s * a.stage_bytes;
                 mbar_expect_tx(&full[s], a_bytes + b_bytes);
-                tma_load_5d(&tmA, &full[s], a_dst, cb * 32, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
-                tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * 32, (ph0 + p) * OC);
+                tma_load_5d(&tmA, &full[s], a_dst, cb * KC, x0 + bx + tx, y0 + by + ty, z0 + bz + tz, item0);
+                tma_load_2d(&tmB, &full[s], a_dst + a.b_off, kb * KC, (ph0 + p) * OC);
               }
               __syncwarp();
               if (++s == a.nstages) { s = 0; par ^= 1; }
             }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = idesc_tf32(OC);
+    const uint32_t idesc = a.in_half ? idesc_f16_m128(OC) : idesc_tf32(OC);
     int s = 0;
     uint32_t par = 0;
     for (int p = 0; p < nph; ++p) {
@@ -146,8 +161,10 @@ upconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint32_t a_addr = smem_u32(smem + s * a.stage_bytes);
           const uint64_t da = smem_desc_sw128(a_addr), db = smem_desc_sw128(a_addr + a.b_off);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            if (a.in_half) umma_f16_ss(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            else umma_tf32(tmem_base + (uint32_t)(p * OC), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
           umma_commit(&empty[s]);
           if (kb == kb_per_phase - 1) umma_commit(&acc_full[p]);
         }
@@ -486,19 +503,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128
-__device__ __forceinline__ uint32_t idesc_f16_m128(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 // HALF: the source activations and the weights are fp16 (the 10-bit mantissa TF32 keeps of an fp32 operand anyway):
@@ -1266,14 +1270,16 @@ using namespace rcb;
 
 // w_eff_k: forward weights in K-major form [phase][oc][tap*ic] (rcb_fold_poly_k).
 static int upconv_fwd_tc_impl(const float* src, const float* w_eff_k, const float* bias, float* out,
-                              const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream, int out_half) {
+                              const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream, int out_half,
+                              int in_half = 0) {
   PolyGeom g;
   if (int rc = make_geom_tc(geo, &g)) return rc;
   RCB_CHECK_ARG(src && w_eff_k && bias && out, "rcb_upconv_fwd_tc: null pointer");
-  RCB_CHECK_ARG(g.ic % 32 == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
+  RCB_CHECK_ARG(g.ic % (in_half ? 64 : 32) == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
   if (items <= 0) return 0;
+  if (in_half && f2_eligible(g, true) && !out_half) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, true);
   if (f2_eligible(g, false) && !out_half && !getenv("RCB_NO_F2")) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, false);
-  if (g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
+  if (!in_half && g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
     // 2-D grid with full 8 x 16 tiles: halo-tile kernel
     ConvHaloArgs h;
     h.g = g; h.items = items;
@@ -1311,15 +1317,16 @@ static int upconv_fwd_tc_impl(const float* src, const float* w_eff_k, const floa
   if (ppc > CT_MAX_PHASES) ppc = CT_MAX_PHASES;
   if (ppc > g.phases()) ppc = g.phases();
   a.phases_per_cta = ppc;
-  a.kblocks = g.ic / 32;
+  const int KC = in_half ? 64 : 32, es = in_half ? 2 : 4;
+  a.kblocks = g.ic / KC;
   a.bk = 32;
-  a.act = act; a.out_half = out_half; a.act_half = 0; a.bias = bias; a.src_act = nullptr; a.out = out;
+  a.act = act; a.out_half = out_half; a.in_half = in_half; a.act_half = 0; a.bias = bias; a.src_act = nullptr; a.out = out;
   int smem_total;
   smem_layout(&a, 128, g.oc, &smem_total, 3, 4 * 32 * (g.oc + 4) * 4);
   CUtensorMap tmA, tmB;
-  if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, a.t, 32, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-  if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, 32,
-                          CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_map_5d(&tmA, src, items, g.d, g.h, g.w, g.ic, a.t, KC, 1, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B, es)) return rc;
+  if (int rc = make_map_b(&tmB, w_eff_k, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, g.oc, KC,
+                          CU_TENSOR_MAP_SWIZZLE_128B, es)) return rc;
   if (int rc = opt_in_smem(upconv_fwd_tc_kernel, "rcb_upconv_fwd_tc")) return rc;
   dim3 grid(a.t.ntx * a.t.nty * a.t.ntz * ceil_div(items, a.t.ni), ceil_div(g.phases(), ppc));
   upconv_fwd_tc_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, a);
@@ -1337,16 +1344,18 @@ extern "C" int rcb_upconv_fwd_tc_oh(const float* src, const float* w_eff_k, cons
   return upconv_fwd_tc_impl(src, w_eff_k, bias, reinterpret_cast<float*>(out_h), geo, items, act, stream, 1);
 }
 
-// fp16 source activations and fp16 K-major weights (rcb_to_half of the rcb_fold_poly_k output); only the x2 / 16-channel
-// stage that launch_f2 covers.
+// fp16 source activations and fp16 K-major weights (rcb_to_half of the rcb_fold_poly_k output), ic % 64 == 0.  The
+// x2 / 16-channel stage runs the resident-weight kernel, everything else the general one with kind::f16 MMAs.
 extern "C" int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, const float* bias, float* out,
                                    const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
-  PolyGeom g;
-  if (int rc = make_geom_tc(geo, &g)) return rc;
-  RCB_CHECK_ARG(src_h && w_eff_k_h && bias && out, "rcb_upconv_fwd_tc_h: null pointer");
-  RCB_CHECK_ARG(f2_eligible(g, true), "rcb_upconv_fwd_tc_h: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
-  if (items <= 0) return 0;
-  return launch_f2(src_h, w_eff_k_h, bias, out, g, items, act, stream, true);
+  return upconv_fwd_tc_impl(reinterpret_cast<const float*>(src_h), reinterpret_cast<const float*>(w_eff_k_h), bias, out, geo,
+                            items, act, stream, 0, 1);
+}
+// fp16 in, fp16 out
+extern "C" int rcb_upconv_fwd_tc_hh(const void* src_h, const void* w_eff_k_h, const float* bias, void* out_h,
+                                    const rcb_upconv_geom* geo, int items, int act, rcb_stream_t stream) {
+  return upconv_fwd_tc_impl(reinterpret_cast<const float*>(src_h), reinterpret_cast<const float*>(w_eff_k_h), bias,
+                            reinterpret_cast<float*>(out_h), geo, items, act, stream, 1, 1);
 }
 
 // Data gradient of the x2 / 3-tap / 64 -> 16 channel stage with resident weights.  w_bwd_k: rcb_fold_poly_bwd_f2 of w_eff.
@@ -1389,7 +1398,7 @@ static int upconv_bwd_tc_impl(const float* d_out, const float* w_eff, const floa
   const int bk = (g.oc == 16) ? 16 : 32;
   a.bk = bk;
   a.kblocks = g.oc / bk;
-  a.act = 0; a.out_half = 0; a.act_half = act_half; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
+  a.act = 0; a.out_half = 0; a.in_half = 0; a.act_half = act_half; a.bias = nullptr; a.src_act = src_act; a.out = d_src;
   int smem_total;
   smem_layout(&a, bk * 4, g.ic, &smem_total);
   RCB_CHECK_ARG(4 * 32 * (g.ic + 4) * 4 <= a.bar_off, "rcb_upconv_bwd_tc: epilogue staging does not fit the pipeline stages");

@@ -10,6 +10,7 @@
 //              coalesced global stores); two CTAs per SM
 // Both operands are K-major (A row-major [M,K]; B passed transposed as [N,K]); ragged M/N/K
 // edges are handled by TMA out-of-bounds zero fill plus guarded stores.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace rcb {
@@ -33,7 +34,7 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     float* __restrict__ C, int ldc, int M, int N, int K,
-                    const float* __restrict__ bias, int bias_mod, int act, int accumulate) {
+                    const float* __restrict__ bias, int bias_mod, int act, int accumulate, int out_half) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -146,7 +147,11 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (act) o[t] = o[t] > 0.f ? o[t] : 0.01f * o[t];
           }
         }
-        if (n + 4 <= N) {
+        if (out_half) {                      // C is fp16 (N % 4 == 0, no accumulate: checked by the launcher)
+          const __half2 lo = __floats2half2_rn(o[0], o[1]), hi = __floats2half2_rn(o[2], o[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(C) + (int64_t)row * ldc + n) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        } else if (n + 4 <= N) {
           *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
           for (int t = 0; t < 4 && n + t < N; ++t) crow[n + t] = o[t];
@@ -192,7 +197,7 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
 
 template <int BN>
 static int launch_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, int ldc, int M, int N, int K,
-                     const float* bias, int bias_mod, int act, int accumulate, cudaStream_t st) {
+                     const float* bias, int bias_mod, int act, int accumulate, cudaStream_t st, int out_half = 0) {
   CUtensorMap tmA, tmB;
   if (int rc = make_map_2d(&tmA, A, M, K, lda, TC_BM)) return rc;
   if (int rc = make_map_2d(&tmB, Bt, N, K, ldbt, BN)) return rc;
@@ -204,7 +209,7 @@ static int launch_tc(const float* A, int lda, const float* Bt, int ldbt, float* 
     configured = true;
   }
   dim3 grid(ceil_div(M, TC_BM), ceil_div(N, BN));
-  gemm_tf32_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, C, ldc, M, N, K, bias, bias_mod, act, accumulate);
+  gemm_tf32_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, C, ldc, M, N, K, bias, bias_mod, act, accumulate, out_half);
   RCB_CHECK_LAUNCH("rcb_gemm_tc");
   return 0;
 }
@@ -224,4 +229,19 @@ extern "C" int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, f
   cudaStream_t st = (cudaStream_t)stream;
   if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st);
   return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st);
+}
+
+// Same GEMM, C written as fp16 (for a following fp16-operand stage).  N % 4 == 0, no accumulation into C.
+extern "C" int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt, void* C_h, int ldc, int M, int N, int K,
+                              const float* bias, int bias_mod, int act, rcb_stream_t stream) {
+  RCB_CHECK_ARG(A && Bt && C_h, "rcb_gemm_tc_oh: null operand");
+  RCB_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 4 == 0, "rcb_gemm_tc_oh: N must be a positive multiple of 4");
+  RCB_CHECK_ARG(lda % 4 == 0 && ldbt % 4 == 0 && ldc % 4 == 0, "rcb_gemm_tc_oh: leading dimensions must be multiples of 4");
+  RCB_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)Bt % 16 == 0) && ((uintptr_t)C_h % 8 == 0),
+                "rcb_gemm_tc_oh: operands must be 16-byte aligned (C: 8)");
+  RCB_CHECK_ARG(!bias || bias_mod > 0, "rcb_gemm_tc_oh: bias_mod must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* C = reinterpret_cast<float*>(C_h);
+  if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1);
+  return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1);
 }

@@ -290,11 +290,14 @@ class FitEngine:
                 self.w_eff_k[i] = torch.empty(n, device=dev)
                 check(self.lib.rcb_fold_poly_k(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff_k[i]), st), "rcb_fold_poly_k")
         g3 = self.geoms[2]
-        self.f2_half = bool(self.tc_conv and self.data_dim == 2 and g3.d == 1 and g3.fy == 2 and g3.fx == 2 and g3.ky == 3
-                            and g3.kx == 3 and g3.ic == 64 and g3.oc == 16 and g3.h >= 16)
+        self.f2_half = bool(self.tc_conv and self.tc and self.data_dim == 2 and g3.d == 1 and g3.fy == 2 and g3.fx == 2
+                            and g3.ky == 3 and g3.kx == 3 and g3.ic == 64 and g3.oc == 16 and g3.h >= 16
+                            and self.geoms[1].ic == 64)
         if self.f2_half:
             self.w3_kh = torch.empty(self.w_eff_k[2].numel(), dtype=torch.float16, device=dev)
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[2]), ptr(self.w3_kh), self.w3_kh.numel(), st), "rcb_to_half")
+            self.w2_kh = torch.empty(self.w_eff_k[1].numel(), dtype=torch.float16, device=dev)
+            check(self.lib.rcb_to_half(ptr(self.w_eff_k[1]), ptr(self.w2_kh), self.w2_kh.numel(), st), "rcb_to_half")
             self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
             check(self.lib.rcb_fold_poly_bwd_f2(ptr(self.w_eff[2]), C.byref(g3), ptr(self.w3_bk), st), "rcb_fold_poly_bwd_f2")
 
@@ -443,20 +446,29 @@ class FitEngine:
                                ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
         join = self._fork(reparam)
         g1, g2, g3 = self.geoms
+        half = ws["a2_is_half"] = bool(self.half_acts and self.f2_half)
+        if half and "a2h" not in ws:
+            ws["a1h"] = torch.empty(ws["a1"].shape, dtype=torch.float16, device=self.device)
+            ws["a2h"] = torch.empty(ws["a2"].shape, dtype=torch.float16, device=self.device)
         with self.section("conv1_fwd"):
             if self.dense1:
                 Lt = self.M1.shape[0]
-                self._gemm(ws["lpe"], 0, Lt, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
-                           citems, self.M1.shape[1], Lt, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
+                if half:
+                    check(self.lib.rcb_gemm_tc_oh(ptr(ws["lpe"]), Lt, ptr(self.M1T), self.M1T.shape[1], ptr(ws["a1h"]),
+                                                  ws["a1"].shape[1], citems, self.M1.shape[1], Lt, ptr(self.conv_b[0]), g1.oc, 1,
+                                                  stream()), "rcb_gemm_tc_oh")
+                else:
+                    self._gemm(ws["lpe"], 0, Lt, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
+                               citems, self.M1.shape[1], Lt, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)
+            elif half:
+                check(self.lib.rcb_upconv_fwd_tc_oh(ptr(ws["lpe"]), ptr(self.w_eff_k[0]), ptr(self.conv_b[0]), ptr(ws["a1h"]),
+                                                    C.byref(g1), citems, 1, stream()), "rcb_upconv_fwd_tc_oh[1]")
             else:
                 self._upconv_fwd(0, ws["lpe"], ws["a1"], citems, 1)
-        half = ws["a2_is_half"] = bool(self.half_acts and self.f2_half)
-        if half and "a2h" not in ws:
-            ws["a2h"] = torch.empty(ws["a2"].shape, dtype=torch.float16, device=self.device)
         with self.section("conv2_fwd"):
             if half:
-                check(self.lib.rcb_upconv_fwd_tc_oh(ptr(ws["a1"]), ptr(self.w_eff_k[1]), ptr(self.conv_b[1]), ptr(ws["a2h"]),
-                                                    C.byref(g2), citems, 1, stream()), "rcb_upconv_fwd_tc_oh[2]")
+                check(self.lib.rcb_upconv_fwd_tc_hh(ptr(ws["a1h"]), ptr(self.w2_kh), ptr(self.conv_b[1]), ptr(ws["a2h"]),
+                                                    C.byref(g2), citems, 1, stream()), "rcb_upconv_fwd_tc_hh[2]")
             else:
                 self._upconv_fwd(1, ws["a1"], ws["a2"], citems, 1)
         with self.section("conv3_fwd"):
@@ -536,7 +548,11 @@ class FitEngine:
             else:
                 self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
         with self.section("conv2_bwd"):
-            self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
+            if ws.get("a2_is_half"):
+                check(self.lib.rcb_upconv_bwd_tc_ah(ptr(ws["d_a2"]), ptr(self.w_eff[1]), ptr(ws["a1h"]), ptr(ws["d_a1"]),
+                                                    C.byref(g2), citems, stream()), "rcb_upconv_bwd_tc_ah[2]")
+            else:
+                self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
         with self.section("conv1_bwd"):
             if self.dense1:
                 Lt = self.M1.shape[0]

@@ -159,3 +159,50 @@ def test_upconv_bwd_f2_matches_simt(h, w, items, act_kind):
     scale = float(d_out.norm(dim=-1).max()) * float(wt.norm()) / np.sqrt(ic) * 4
     err = float((got - ref).abs().max())
     assert err < 2e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("name", ["cifar_conv2", "wide_2d_ragged", "video_conv2_3d", "protein_conv2"])
+def test_upconv_fwd_fp16_in_fp16_out_general_kernel(name):
+    """rcb_upconv_fwd_tc_hh (general kernel, kind::f16 MMAs, fp16 result) against the SIMT engine on the rounded inputs."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    d, h, w, fz, fy, fx, kz, ky, kx, ic, oc, items = GEOMS[name]
+    geo = UpconvGeom(d, h, w, fz, fy, fx, kz, ky, kx, ic, oc)
+    gen = torch.Generator().manual_seed(len(name) + 7)
+    wt = (torch.randn(oc, ic, kz, ky, kx, generator=gen) / np.sqrt(ic * kz * ky * kx)).cuda()
+    bias = torch.randn(oc, generator=gen).cuda()
+    src_h = torch.randn(items, d, h, w, ic, generator=gen).cuda().half()
+    taps = (1 if kz == 1 else 2) * (1 if ky == 1 else 2) * (1 if kx == 1 else 2)
+    n = fz * fy * fx * taps * ic * oc
+    w_eff, w_eff_t, w_eff_k = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_k(ptr(wt), C.byref(geo), ptr(w_eff_k), stream()))
+    w_h = w_eff_k.half()
+    out_shape = (items, d * fz, h * fy, w * fx, oc)
+    ref = torch.zeros(out_shape, device="cuda")
+    got = torch.full(out_shape, 3.0, device="cuda", dtype=torch.float16)
+    src_r = src_h.float().contiguous()
+    check(lib.rcb_upconv_fwd(ptr(src_r), ptr(w_eff), ptr(bias), ptr(ref), C.byref(geo), items, 1, stream()))
+    check(lib.rcb_upconv_fwd_tc_hh(ptr(src_h), ptr(w_h), ptr(bias), ptr(got), C.byref(geo), items, 1, stream()))
+    torch.cuda.synchronize()
+    scale = float(src_r.norm(dim=-1).max()) * float(wt.flatten(1).norm(dim=1).max())
+    err = float((got.float() - ref).abs().max())
+    assert err < 1e-3 * scale + 1e-3 * float(ref.abs().max()), (err, scale)      # + fp16 rounding of the result
+
+
+def test_gemm_tc_fp16_output_is_the_rounded_fp32_output():
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    M, N, K = 300, 4096, 2048
+    gen = torch.Generator().manual_seed(3)
+    A = torch.randn(M, K, generator=gen).cuda()
+    Bt = (torch.randn(N, K, generator=gen) / np.sqrt(K)).cuda()
+    bias = torch.randn(64, generator=gen).cuda()
+    c32 = torch.zeros(M, N, device="cuda")
+    c16 = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+    check(lib.rcb_gemm_tc(ptr(A), K, ptr(Bt), K, ptr(c32), N, M, N, K, ptr(bias), 64, 1, 0, stream()))
+    check(lib.rcb_gemm_tc_oh(ptr(A), K, ptr(Bt), K, ptr(c16), N, M, N, K, ptr(bias), 64, 1, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(c16, c32.half())
