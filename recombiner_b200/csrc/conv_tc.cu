@@ -848,6 +848,193 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------- forward, factor 2, 64 -> 64 channels, fp16 --
+// The middle upsampler stage (x2, 3-tap, 64 -> 64) in the same persistent form, with fp16 activations in and out and
+// fp16 weights: one 128-byte row per pixel is the whole K range, and the 16 (phase, tap) weight blocks (128 KB) stay
+// in shared memory.  Accumulators: 4 phases x 64 = 256 TMEM columns, two sets.  A tile is 16 eight-pixel row groups,
+// one halo row pitch (10 pixels) apart: 16 lines of one item (source grids with >= 16 lines), or 8 lines x 2 items
+// interleaved line by line (8 x 8 grids; the TMA box puts the item dimension between x and y), so that the same
+// shifted-descriptor trick serves both.  Output rows (pixel, column parity) are staged as swizzled 128-byte rows and
+// leave through one TMA store per warp and line parity.
+constexpr int F2W_STAGES = 2, F2W_STAGE_BYTES = 26 * 1024, F2W_W_BLOCK = 64 * 128;
+struct ConvF2WArgs {
+  PolyGeom g;
+  int items, tiles_x, tiles_y, n_tiles;
+  int ipt;                              // items per tile: 1 (8 px x 16 lines) or 2 (8 x 8 grids)
+  int act, halo_bytes;
+  int a_off, epi_off, bias_off, bar_off;
+  int grp_shift[F2_GROUPS], grp_col[F2_GROUPS], grp_n[F2_GROUPS], grp_row[F2_GROUPS];
+  int mem_phase[16], mem_tap[16];
+  int phase_col[4];
+  const float* bias;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvF2WArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + a.bar_off);        // [F2W_STAGES]
+  uint64_t* a_empty = a_full + F2W_STAGES;
+  uint64_t* acc_full = a_empty + F2W_STAGES;                // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2], one arrival per epilogue warp
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + a.bias_off);
+  constexpr int OC = 64, ACC_COLS = 4 * OC;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PolyGeom& g = a.g;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < F2W_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < OC) bias_s[threadIdx.x] = a.bias[threadIdx.x];
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> first item, first line, first pixel
+  auto tile_origin = [&](int t, int& item, int& y0, int& x0) {
+    if (a.ipt == 2) { item = 2 * t; y0 = 0; x0 = 0; return; }
+    x0 = (t % a.tiles_x) * 8; t /= a.tiles_x;
+    y0 = (t % a.tiles_y) * 16; t /= a.tiles_y;
+    item = t;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(w_full, 16u * F2W_W_BLOCK);
+      for (int b = 0; b < 16; ++b)
+        tma_load_2d(&tmB, w_full, smem + b * F2W_W_BLOCK, a.mem_tap[b] * g.ic, a.mem_phase[b] * OC);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t par = 1;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      mbar_wait(&a_empty[s], par);
+      if (elect_one()) {
+        mbar_expect_tx(&a_full[s], (uint32_t)a.halo_bytes);
+        if (a.ipt == 2) tma_load_4d(&tmA, &a_full[s], smem + a.a_off + s * F2W_STAGE_BYTES, 0, -1, item, -1);
+        else tma_load_4d(&tmA, &a_full[s], smem + a.a_off + s * F2W_STAGE_BYTES, 0, x0 - 1, y0 - 1, item);
+      }
+      __syncwarp();
+      if (++s == F2W_STAGES) { s = 0; par ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    uint32_t idesc[F2_GROUPS];
+#pragma unroll
+    for (int j = 0; j < F2_GROUPS; ++j) idesc[j] = idesc_f16_m128(a.grp_n[j]);
+    const uint32_t w_addr = smem_u32(smem);
+    mbar_wait(w_full, 0);
+    int s = 0;
+    uint32_t par = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * ACC_COLS);
+      mbar_wait(&a_full[s], par);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + a.a_off + s * F2W_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < F2_GROUPS; ++j) {
+          const uint64_t da = da_hi | (uint64_t)(((a_addr + (uint32_t)a.grp_shift[j] * 128u) & 0x3FFFF) >> 4);
+          const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)a.grp_row[j] * 128u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // group 0 covers every column, so it alone starts the accumulation
+            umma_f16_ss(acc + (uint32_t)a.grp_col[j], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc[j], (j | k) ? 1u : 0u);
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+      if (++s == F2W_STAGES) { s = 0; par ^= 1; }
+    }
+  } else {
+    // One (line parity, column parity) phase at a time: 32 pixel rows x 64 channels as fp16 = 32 swizzled 128-byte
+    // rows = one TMA store (two when the tile holds two items); two 4 KB buffers per warp alternate, and the next
+    // phase's accumulators are already on their way out of TMEM while this one is converted.
+    const int q = warp & 3;
+    uint8_t* stage = smem + a.epi_off + q * 8192;
+    const int gl = lane >> 3, px = lane & 7;
+    // staged row: [line][px] (one item) or [item][line][px] (two items: group = line * 2 + item)
+    const int row = (a.ipt == 2 ? ((gl & 1) * 2 + (gl >> 1)) : gl) * 8 + px;
+    const float slope = a.act ? 0.01f : 1.0f;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_COLS);
+      uint32_t v[2][4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(acc + (uint32_t)(a.phase_col[0] + c * 16), v[0][c]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) {                     // ph = ry * 2 + rx
+        const int ry = ph >> 1, rx = ph & 1;
+        if (ph < 3) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld16_nowait(acc + (uint32_t)(a.phase_col[ph + 1] + c * 16), v[(ph + 1) & 1][c]);
+        }
+        if (lane == 0) bulk_wait_read<1>();                // the store that last read this buffer has left it
+        __syncwarp();
+        uint8_t* dst = stage + (ph & 1) * 4096 + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                      // chunk c: channels 8c .. 8c+7 as fp16
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * 8), b1 = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float f = __uint_as_float(v[ph & 1][c >> 1][(c & 1) * 8 + e]) + bb[e];
+            o[e] = f > 0.f ? f : slope * f;
+          }
+          const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
+          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const uint8_t* sb = stage + (ph & 1) * 4096;
+          if (a.ipt == 2) {
+            tma_store_5d(&tmO, sb, 0, rx, 0, ry, item * g.h + 2 * q);
+            if (item + 1 < a.items) tma_store_5d(&tmO, sb + 2048, 0, rx, 0, ry, (item + 1) * g.h + 2 * q);
+          } else if (y0 + 4 * q < g.h) {                    // h % 4 == 0: a warp's four lines are all inside or all outside
+            tma_store_5d(&tmO, sb, 0, rx, x0, ry, item * g.h + y0 + 4 * q);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (ph < 3) {
+          tmem_wait_ld();
+        } else {                                           // accumulators drained: the next tile but one may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // --------------------------------------- data gradient, factor 2, resident weights --
 // The adjoint of the stage above.  A source pixel s receives from the 4 x 4 output pixels 2s - 1 + (a, b):
 //   d_src[s][ic] = mask(s, ic) * sum_{a, b, oc} d_out[2s - 1 + (a, b)][oc] * W[a][b][oc][ic]
@@ -1214,6 +1401,89 @@ static int launch_f2(const void* src, const void* w_eff_k, const float* bias, fl
   return 0;
 }
 
+static bool f2w_eligible(const PolyGeom& g) {
+  return g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.fy == 2 && g.fx == 2 && g.py == 1 && g.px == 1 &&
+         g.oc == 64 && g.ic == 64 && ((g.h == 8 && g.w == 8) || (g.h >= 16 && g.h % 4 == 0));
+}
+static int encode_map_t(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+                        const cuuint64_t* strides, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, dt, (cuuint32_t)rank, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return -1; }
+  return 0;
+}
+// fp16 in, fp16 out, fp16 K-major weights
+static int launch_f2w(const void* src_h, const void* w_eff_k_h, const float* bias, void* out_h, const PolyGeom& g, int items,
+                      int act, rcb_stream_t stream) {
+  ConvF2WArgs f;
+  f.g = g; f.items = items;
+  f.ipt = (g.h == 8 && g.w == 8) ? 2 : 1;
+  f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
+  f.n_tiles = f.ipt == 2 ? ceil_div(items, 2) : f.tiles_x * f.tiles_y * items;
+  f.act = act; f.bias = bias;
+  f.halo_bytes = (f.ipt == 2 ? 10 * 2 * HALO_PITCH : HALO_LINES * HALO_PITCH) * 128;
+  const int dy_rows = HALO_PITCH * f.ipt;
+  const int order[4] = {0, 1, 3, 2};
+  for (int i = 0; i < 4; ++i) f.phase_col[order[i]] = i * 64;
+  const int groups[F2_GROUPS][4] = {{0, 0, 0, 4}, {-1, 0, 0, 2}, {0, 1, 1, 2}, {1, 0, 2, 2}, {0, -1, 0, 1},
+                                    {0, -1, 3, 1}, {-1, -1, 0, 1}, {-1, 1, 1, 1}, {1, 1, 2, 1}, {1, -1, 3, 1}};
+  int nb = 0;
+  for (int j = 0; j < F2_GROUPS; ++j) {
+    const int dy = groups[j][0], dx = groups[j][1], slot = groups[j][2], mem = groups[j][3];
+    f.grp_shift[j] = (1 + dy) * dy_rows + (1 + dx);
+    f.grp_col[j] = slot * 64;
+    f.grp_n[j] = mem * 64;
+    f.grp_row[j] = nb * 64;
+    for (int i = 0; i < mem; ++i, ++nb) {
+      const int ph = order[slot + i], ry = ph >> 1, rx = ph & 1;
+      const int ty = dy - (ry == 0 ? -1 : 0), tx = dx - (rx == 0 ? -1 : 0);
+      RCB_CHECK_ARG(nb < 16 && ty >= 0 && ty < 2 && tx >= 0 && tx < 2, "rcb_upconv_fwd_tc_hh: bad shift table");
+      f.mem_phase[nb] = ph; f.mem_tap[nb] = ty * 2 + tx;
+    }
+  }
+  RCB_CHECK_ARG(nb == 16, "rcb_upconv_fwd_tc_hh: bad shift table");
+  f.a_off = 16 * F2W_W_BLOCK;
+  f.epi_off = f.a_off + F2W_STAGES * F2W_STAGE_BYTES;
+  f.bias_off = f.epi_off + 4 * 8192;
+  f.bar_off = f.bias_off + 1024;
+  const int smem_total = f.bar_off + 512 + 1024;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    const cuuint64_t px = 128, line = (cuuint64_t)g.w * px, img = (cuuint64_t)g.h * line;
+    if (f.ipt == 2) {     // (channels, x, item, y): the two items of a tile alternate line by line in shared memory
+      cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)items, (cuuint64_t)g.h};
+      cuuint64_t strides[3] = {px, img, line};
+      cuuint32_t box[4] = {64, HALO_PITCH, 2, 10};
+      if (int rc = encode_map_t(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, src_h, 4, dims, strides, box, "src")) return rc;
+    } else {
+      cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
+      cuuint64_t strides[3] = {px, line, img};
+      cuuint32_t box[4] = {64, HALO_PITCH, HALO_LINES, 1};
+      if (int rc = encode_map_t(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, src_h, 4, dims, strides, box, "src")) return rc;
+    }
+  }
+  if (int rc = make_map_b(&tmB, w_eff_k_h, (int64_t)g.phases() * g.oc, (int64_t)g.taps() * g.ic, 64, 64,
+                          CU_TENSOR_MAP_SWIZZLE_128B, 2)) return rc;
+  {   // out as ((item, y), line parity, px, column parity, 64 channels): a phase of 8 pixels x n lines is one box
+    const cuuint64_t px = 128, line = 2 * (cuuint64_t)g.w * px;
+    cuuint64_t dims[5] = {64, 2, (cuuint64_t)g.w, 2, (cuuint64_t)g.h * (cuuint64_t)items};
+    cuuint64_t strides[4] = {px, 2 * px, line, 2 * line};
+    cuuint32_t box[5] = {64, 1, 8, 1, (cuuint32_t)(f.ipt == 2 ? 2 : 4)};
+    if (int rc = encode_map_t(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, out_h, 5, dims, strides, box, "out")) return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(upconv_fwd_f2w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+  if (e != cudaSuccess) { set_error("rcb_upconv_fwd_tc_hh: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+  static int n_sm = 0;
+  if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
+  upconv_fwd_f2w_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc_hh");
+  return 0;
+}
+
 static bool b2_eligible(const PolyGeom& g) {
   return g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16 && g.fy == 2 && g.fx == 2 && g.py == 1 && g.px == 1 &&
          g.oc == 16 && g.ic == 64;
@@ -1278,6 +1548,7 @@ static int upconv_fwd_tc_impl(const float* src, const float* w_eff_k, const floa
   RCB_CHECK_ARG(g.ic % (in_half ? 64 : 32) == 0 && g.oc % 16 == 0 && g.oc <= 128, "rcb_upconv_fwd_tc: unsupported channels %d -> %d", g.ic, g.oc);
   if (items <= 0) return 0;
   if (in_half && f2_eligible(g, true) && !out_half) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, true);
+  if (in_half && out_half && f2w_eligible(g) && !getenv("RCB_NO_F2W")) return launch_f2w(src, w_eff_k, bias, out, g, items, act, stream);
   if (f2_eligible(g, false) && !out_half && !getenv("RCB_NO_F2")) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, false);
   if (!in_half && g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
     // 2-D grid with full 8 x 16 tiles: halo-tile kernel

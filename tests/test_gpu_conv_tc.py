@@ -23,6 +23,9 @@ GEOMS = {
     # persistent x2 kernel: ragged tiles, more than two tiles per CTA (both accumulator sets re-used)
     "f2_many_tiles": (1, 40, 44, 1, 2, 2, 1, 3, 3, 64, 16, 20),
     "f2_oc32": (1, 16, 24, 1, 2, 2, 1, 3, 3, 32, 32, 3),
+    # persistent 64 -> 64 fp16 kernel: one item per tile (ragged), two 8 x 8 items per tile (odd count, > 2 tiles per CTA)
+    "f2w_ragged": (1, 40, 44, 1, 2, 2, 1, 3, 3, 64, 64, 5),
+    "f2w_8x8_many": (1, 8, 8, 1, 2, 2, 1, 3, 3, 64, 64, 701),
 }
 
 
@@ -161,7 +164,7 @@ def test_upconv_bwd_f2_matches_simt(h, w, items, act_kind):
     assert err < 2e-3 * scale, (err, scale)
 
 
-@pytest.mark.parametrize("name", ["cifar_conv2", "wide_2d_ragged", "video_conv2_3d", "protein_conv2"])
+@pytest.mark.parametrize("name", ["cifar_conv2", "wide_2d_ragged", "video_conv2_3d", "protein_conv2", "f2w_ragged", "f2w_8x8_many"])
 def test_upconv_fwd_fp16_in_fp16_out_general_kernel(name):
     """rcb_upconv_fwd_tc_hh (general kernel, kind::f16 MMAs, fp16 result) against the SIMT engine on the rounded inputs."""
     from recombiner_b200 import _lib
