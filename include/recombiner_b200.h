@@ -82,6 +82,7 @@ typedef struct {
   int step, tensor_id, accumulate;
   int rows_per_datum, sp_total, lpe_c;   /* used with lpe_slot */
   const rcb_step_state* dyn;             /* optional: seed and step read from device memory */
+  void* lpe_h;                           /* optional: the latent grid is written here as fp16 INSTEAD of lpe (rcb_gemm_tc_hh) */
 } rcb_sample_args;
 int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
 
@@ -105,6 +106,10 @@ int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, in
 
 /* rcb_gemm_tc with C written as fp16 (ldc in fp16 elements, N % 4 == 0, no accumulation into C). */
 int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt, void* C_h, int ldc,
+                   int M, int N, int K, const float* bias, int bias_mod, int act, rcb_stream_t stream);
+
+/* fp16 A, fp16 Bt and fp16 C (K % 8 == 0; kind::f16 MMAs, twice the TF32 rate, fp32 accumulation) */
+int rcb_gemm_tc_hh(const void* A_h, int lda, const void* Bt_h, int ldbt, void* C_h, int ldc,
                    int M, int N, int K, const float* bias, int bias_mod, int act, rcb_stream_t stream);
 
 /* Geometry of one nearest-upsample + 'same' conv stage on a channel-last grid

@@ -41,13 +41,15 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
       float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
       *dst = a.accumulate ? *dst + v : v;
     }
-  } else if (a.lpe) {
+  } else if (a.lpe || a.lpe_h) {
     const int l = p - a.n_w;
     for (int s = 0; s < a.S; ++s) {
       float eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
                           : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
       if (a.eps_l_store) a.eps_l_store[((int64_t)s * a.rows + n) * a.n_l + l] = eps;
-      a.lpe[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)] = fmaf(sig, eps, mu);
+      const int64_t li = lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l);
+      if (a.lpe_h) reinterpret_cast<__half*>(a.lpe_h)[li] = __float2half_rn(fmaf(sig, eps, mu));
+      else a.lpe[li] = fmaf(sig, eps, mu);
     }
   }
 }
@@ -100,8 +102,9 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
         }
       }
     }
-    if (a.lpe) {
-      float* lpe = a.lpe + item * a.n_l;
+    if (a.lpe || a.lpe_h) {
+      float* lpe = a.lpe_h ? nullptr : a.lpe + item * a.n_l;
+      __half* lpe_h = a.lpe_h ? reinterpret_cast<__half*>(a.lpe_h) + item * a.n_l : nullptr;
       const float* lin = a.eps_l ? a.eps_l + ((int64_t)s * a.rows + n) * a.n_l : nullptr;
       float* lout = a.eps_l_store ? a.eps_l_store + ((int64_t)s * a.rows + n) * a.n_l : nullptr;
       for (int c0 = 0; c0 < a.n_l; c0 += 1024) {
@@ -113,7 +116,9 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
           if (l < a.n_l) {
             const float eps = lin ? lin[l] : z[k];
             if (lout) lout[l] = eps;
-            lpe[l] = fmaf(s_sig[a.n_w + l], eps, s_mu[a.n_w + l]);
+            const float val = fmaf(s_sig[a.n_w + l], eps, s_mu[a.n_w + l]);
+            if (lpe_h) lpe_h[l] = __float2half_rn(val);
+            else lpe[l] = val;
           }
         }
       }

@@ -34,7 +34,7 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     float* __restrict__ C, int ldc, int M, int N, int K,
-                    const float* __restrict__ bias, int bias_mod, int act, int accumulate, int out_half) {
+                    const float* __restrict__ bias, int bias_mod, int act, int accumulate, int out_half, int in_half) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -45,7 +45,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-  const int nkb = (K + TC_BK - 1) / TC_BK;
+  const int BKE = in_half ? 2 * TC_BK : TC_BK;          // elements per 128-byte operand row
+  const int nkb = (K + BKE - 1) / BKE;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -72,15 +73,15 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
         mbar_expect_tx(&full[s], S::STAGE_BYTES);
-        tma_load_2d(&tmA, &full[s], a_dst, kb * TC_BK, m0);
-        tma_load_2d(&tmB, &full[s], b_dst, kb * TC_BK, n0);
+        tma_load_2d(&tmA, &full[s], a_dst, kb * BKE, m0);
+        tma_load_2d(&tmB, &full[s], b_dst, kb * BKE, n0);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp converged, one elected lane issues) =====
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (in_half ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % GEMM_STAGES;
       const uint32_t ph = (kb / GEMM_STAGES) & 1;
@@ -93,7 +94,16 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           // advance 8 tf32 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-          umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          if (in_half) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                "}" ::"r"(tmem_base), "l"(da + (uint64_t)(k * 2)), "l"(db + (uint64_t)(k * 2)), "r"(idesc), "r"((kb | k) ? 1u : 0u) : "memory");
+          } else {
+            umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);          // frees the smem stage once these MMAs retire
         if (kb == nkb - 1) umma_commit(tmem_full);   // accumulator complete
@@ -181,14 +191,15 @@ EncodeTiledFn tc_get_encode() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row stride ld (elements), box = [box_rows, 32 cols], 128B swizzle
-static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int esize = 4) {
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -1; }
@@ -197,10 +208,11 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
 
 template <int BN>
 static int launch_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, int ldc, int M, int N, int K,
-                     const float* bias, int bias_mod, int act, int accumulate, cudaStream_t st, int out_half = 0) {
+                     const float* bias, int bias_mod, int act, int accumulate, cudaStream_t st, int out_half = 0, int in_half = 0) {
   CUtensorMap tmA, tmB;
-  if (int rc = make_map_2d(&tmA, A, M, K, lda, TC_BM)) return rc;
-  if (int rc = make_map_2d(&tmB, Bt, N, K, ldbt, BN)) return rc;
+  const int es = in_half ? 2 : 4;
+  if (int rc = make_map_2d(&tmA, A, M, K, lda, TC_BM, es)) return rc;
+  if (int rc = make_map_2d(&tmB, Bt, N, K, ldbt, BN, es)) return rc;
   const int smem = TcSmem<BN>::TOTAL;
   static bool configured = false;
   if (!configured) {
@@ -209,7 +221,7 @@ static int launch_tc(const float* A, int lda, const float* Bt, int ldbt, float* 
     configured = true;
   }
   dim3 grid(ceil_div(M, TC_BM), ceil_div(N, BN));
-  gemm_tf32_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, C, ldc, M, N, K, bias, bias_mod, act, accumulate, out_half);
+  gemm_tf32_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, C, ldc, M, N, K, bias, bias_mod, act, accumulate, out_half, in_half);
   RCB_CHECK_LAUNCH("rcb_gemm_tc");
   return 0;
 }
@@ -244,4 +256,21 @@ extern "C" int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt
   float* C = reinterpret_cast<float*>(C_h);
   if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1);
   return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1);
+}
+
+// fp16 A and Bt (K-major, 64 elements per 128-byte row, kind::f16), fp16 C.
+extern "C" int rcb_gemm_tc_hh(const void* A_h, int lda, const void* Bt_h, int ldbt, void* C_h, int ldc, int M, int N, int K,
+                              const float* bias, int bias_mod, int act, rcb_stream_t stream) {
+  RCB_CHECK_ARG(A_h && Bt_h && C_h, "rcb_gemm_tc_hh: null operand");
+  RCB_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 4 == 0 && K % 8 == 0, "rcb_gemm_tc_hh: N %% 4 == 0 and K %% 8 == 0 required");
+  RCB_CHECK_ARG(lda % 8 == 0 && ldbt % 8 == 0 && ldc % 4 == 0, "rcb_gemm_tc_hh: leading dimensions must keep rows 16-byte aligned");
+  RCB_CHECK_ARG(((uintptr_t)A_h % 16 == 0) && ((uintptr_t)Bt_h % 16 == 0) && ((uintptr_t)C_h % 8 == 0),
+                "rcb_gemm_tc_hh: operands must be 16-byte aligned (C: 8)");
+  RCB_CHECK_ARG(!bias || bias_mod > 0, "rcb_gemm_tc_hh: bias_mod must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* A = reinterpret_cast<const float*>(A_h);
+  const float* Bt = reinterpret_cast<const float*>(Bt_h);
+  float* C = reinterpret_cast<float*>(C_h);
+  if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1, 1);
+  return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1, 1);
 }

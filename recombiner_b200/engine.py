@@ -298,6 +298,9 @@ class FitEngine:
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[2]), ptr(self.w3_kh), self.w3_kh.numel(), st), "rcb_to_half")
             self.w2_kh = torch.empty(self.w_eff_k[1].numel(), dtype=torch.float16, device=dev)
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[1]), ptr(self.w2_kh), self.w2_kh.numel(), st), "rcb_to_half")
+            if self.dense1:
+                self.M1T_h = torch.empty(self.M1T.shape, dtype=torch.float16, device=dev)
+                check(self.lib.rcb_to_half(ptr(self.M1T), ptr(self.M1T_h), self.M1T_h.numel(), st), "rcb_to_half")
             self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
             check(self.lib.rcb_fold_poly_bwd_f2(ptr(self.w_eff[2]), C.byref(g3), ptr(self.w3_bk), st), "rcb_fold_poly_bwd_f2")
 
@@ -368,6 +371,11 @@ class FitEngine:
         a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
         a.hw = ptr(ws["hw"])
         a.lpe = ptr(ws["lpe"]) if lv.level == 0 else None
+        if lv.level == 0 and self.half_acts and self.f2_half and self.dense1:
+            # the dense first stage reads the latent grid as an fp16 MMA operand: write it that way
+            if "lpe_h" not in ws:
+                ws["lpe_h"] = torch.empty(ws["lpe"].shape, dtype=torch.float16, device=self.device)
+            a.lpe, a.lpe_h = None, ptr(ws["lpe_h"])
         a.lpe_slot = ptr(self.lpe_slot)
         a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
         # generated noise is kept for the gradient kernel: 4 B/element of HBM traffic is far
@@ -454,9 +462,9 @@ class FitEngine:
             if self.dense1:
                 Lt = self.M1.shape[0]
                 if half:
-                    check(self.lib.rcb_gemm_tc_oh(ptr(ws["lpe"]), Lt, ptr(self.M1T), self.M1T.shape[1], ptr(ws["a1h"]),
+                    check(self.lib.rcb_gemm_tc_hh(ptr(ws["lpe_h"]), Lt, ptr(self.M1T_h), self.M1T.shape[1], ptr(ws["a1h"]),
                                                   ws["a1"].shape[1], citems, self.M1.shape[1], Lt, ptr(self.conv_b[0]), g1.oc, 1,
-                                                  stream()), "rcb_gemm_tc_oh")
+                                                  stream()), "rcb_gemm_tc_hh")
                 else:
                     self._gemm(ws["lpe"], 0, Lt, self.M1, self.M1.shape[1], ws["a1"], 0, ws["a1"].shape[1],
                                citems, self.M1.shape[1], Lt, bias=self.conv_b[0], bias_mod=g1.oc, act=1, Bt=self.M1T)

@@ -209,3 +209,21 @@ def test_gemm_tc_fp16_output_is_the_rounded_fp32_output():
     check(lib.rcb_gemm_tc_oh(ptr(A), K, ptr(Bt), K, ptr(c16), N, M, N, K, ptr(bias), 64, 1, stream()))
     torch.cuda.synchronize()
     assert torch.equal(c16, c32.half())
+
+
+def test_gemm_tc_fp16_operands():
+    """rcb_gemm_tc_hh (kind::f16) against an fp32 matmul of the same fp16-rounded operands."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    M, N, K = 300, 4096, 2048
+    gen = torch.Generator().manual_seed(5)
+    A = torch.randn(M, K, generator=gen).cuda().half()
+    Bt = (torch.randn(N, K, generator=gen) / np.sqrt(K)).cuda().half()
+    bias = torch.randn(64, generator=gen).cuda()
+    c16 = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+    check(lib.rcb_gemm_tc_hh(ptr(A), K, ptr(Bt), K, ptr(c16), N, M, N, K, ptr(bias), 64, 1, stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.leaky_relu(A.float() @ Bt.float().t() + bias.repeat(N // 64), 0.01)
+    err = float((c16.float() - ref).abs().max())
+    assert err < 2e-3 * float(ref.abs().max()), err
