@@ -83,6 +83,8 @@ typedef struct {
   int rows_per_datum, sp_total, lpe_c;   /* used with lpe_slot */
   const rcb_step_state* dyn;             /* optional: seed and step read from device memory */
   void* lpe_h;                           /* optional: the latent grid is written here as fp16 INSTEAD of lpe (rcb_gemm_tc_hh) */
+  void* hw_h;                            /* optional: the weight samples are written here as fp16 INSTEAD of hw (row stride ld_hw
+                                            fp16 elements; not with accumulate) for rcb_gemm_tc_h */
 } rcb_sample_args;
 int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
 
@@ -108,6 +110,9 @@ int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, in
 int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt, void* C_h, int ldc,
                    int M, int N, int K, const float* bias, int bias_mod, int act, rcb_stream_t stream);
 
+/* fp16 A and fp16 Bt, fp32 C (K % 8 == 0, lda % 8 == 0, ldbt % 8 == 0): same epilogue as rcb_gemm_tc */
+int rcb_gemm_tc_h(const void* A_h, int lda, const void* Bt_h, int ldbt, float* C, int ldc,
+                  int M, int N, int K, const float* bias, int bias_mod, int act, int accumulate, rcb_stream_t stream);
 /* fp16 A, fp16 Bt and fp16 C (K % 8 == 0; kind::f16 MMAs, twice the TF32 rate, fp32 accumulation) */
 int rcb_gemm_tc_hh(const void* A_h, int lda, const void* Bt_h, int ldbt, void* C_h, int ldc,
                    int M, int N, int K, const float* bias, int bias_mod, int act, rcb_stream_t stream);

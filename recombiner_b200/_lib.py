@@ -23,7 +23,7 @@ class SampleArgs(C.Structure):
                                  "eps_w", "eps_l", "hw", "lpe", "lpe_slot", "eps_w_store", "eps_l_store")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate",
-                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P), ("lpe_h", P)]
+                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P), ("lpe_h", P), ("hw_h", P)]
 
 
 class UpconvGeom(C.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "rcb_upconv_fwd_tc_hh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_gemm_tc_oh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
     "rcb_gemm_tc_hh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
+    "rcb_gemm_tc_h": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],
     "rcb_upconv_fwd_tc_oh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd_tc_ah": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_fold_poly_bwd_f2": [P, C.POINTER(UpconvGeom), P, P],

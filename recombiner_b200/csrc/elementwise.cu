@@ -38,8 +38,12 @@ __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
                           : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
       if (a.eps_w_store) a.eps_w_store[((int64_t)n * a.S + s) * a.n_w + p] = eps;
       float v = fmaf(sig, eps, mu);
-      float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
-      *dst = a.accumulate ? *dst + v : v;
+      if (a.hw_h) {
+        reinterpret_cast<__half*>(a.hw_h)[((int64_t)n * a.S + s) * a.ld_hw + p] = __float2half_rn(v);
+      } else {
+        float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
+        *dst = a.accumulate ? *dst + v : v;
+      }
     }
   } else if (a.lpe || a.lpe_h) {
     const int l = p - a.n_w;
@@ -86,7 +90,8 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
   const int t = threadIdx.x;                     // blockDim.x == 256: slot of the Philox chunk
   for (int s = 0; s < a.S; ++s) {
     const int64_t item = (int64_t)n * a.S + s;
-    float* hw = a.hw + item * a.ld_hw;
+    float* hw = a.hw_h ? nullptr : a.hw + item * a.ld_hw;
+    __half* hw_h = a.hw_h ? reinterpret_cast<__half*>(a.hw_h) + item * a.ld_hw : nullptr;
     const float* ein = a.eps_w ? a.eps_w + item * a.n_w : nullptr;
     float* eout = a.eps_w_store ? a.eps_w_store + item * a.n_w : nullptr;
     for (int c0 = 0; c0 < a.n_w; c0 += 1024) {
@@ -98,7 +103,9 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
         if (p < a.n_w) {
           const float eps = ein ? ein[p] : z[k];
           if (eout) eout[p] = eps;
-          hw[p] = fmaf(s_sig[p], eps, s_mu[p]);
+          const float val = fmaf(s_sig[p], eps, s_mu[p]);
+          if (hw_h) hw_h[p] = __float2half_rn(val);
+          else hw[p] = val;
         }
       }
     }
@@ -529,7 +536,8 @@ extern "C" int rcb_set_step_state(rcb_step_state* dev, int64_t seed, int step, f
 
 extern "C" int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a != nullptr, "rcb_fit_sample: null args");
-  RCB_CHECK_ARG(a->loc && a->log_scale && a->hw, "rcb_fit_sample: null tensor");
+  RCB_CHECK_ARG(a->loc && a->log_scale && (a->hw || a->hw_h), "rcb_fit_sample: null tensor");
+  RCB_CHECK_ARG(!(a->hw_h && a->accumulate), "rcb_fit_sample: the fp16 weight samples cannot be accumulated into");
   RCB_CHECK_ARG(a->rows > 0 && a->S > 0 && a->P > 0, "rcb_fit_sample: empty problem");
   RCB_CHECK_ARG(a->n_w + a->n_l == a->P || (a->n_l == 0 && a->n_w == a->P), "rcb_fit_sample: n_w+n_l != P");
   RCB_CHECK_ARG(a->ld_hw >= a->n_w, "rcb_fit_sample: ld_hw too small");

@@ -274,3 +274,19 @@ extern "C" int rcb_gemm_tc_hh(const void* A_h, int lda, const void* Bt_h, int ld
   if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1, 1);
   return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, 0, st, 1, 1);
 }
+
+// fp16 A and Bt, fp32 C with the full epilogue of rcb_gemm_tc.
+extern "C" int rcb_gemm_tc_h(const void* A_h, int lda, const void* Bt_h, int ldbt, float* C, int ldc, int M, int N, int K,
+                             const float* bias, int bias_mod, int act, int accumulate, rcb_stream_t stream) {
+  RCB_CHECK_ARG(A_h && Bt_h && C, "rcb_gemm_tc_h: null operand");
+  RCB_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0, "rcb_gemm_tc_h: K %% 8 == 0 required");
+  RCB_CHECK_ARG(lda % 8 == 0 && ldbt % 8 == 0 && ldc % 4 == 0, "rcb_gemm_tc_h: leading dimensions must keep rows 16-byte aligned");
+  RCB_CHECK_ARG(((uintptr_t)A_h % 16 == 0) && ((uintptr_t)Bt_h % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                "rcb_gemm_tc_h: operands must be 16-byte aligned");
+  RCB_CHECK_ARG(!bias || bias_mod > 0, "rcb_gemm_tc_h: bias_mod must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* A = reinterpret_cast<const float*>(A_h);
+  const float* Bt = reinterpret_cast<const float*>(Bt_h);
+  if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st, 0, 1);
+  return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st, 0, 1);
+}

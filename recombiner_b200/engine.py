@@ -164,6 +164,12 @@ class FitEngine:
     def section(self, name):
         return _Section(self.timer, name)
 
+    @property
+    def half_hw(self):
+        """fp16 weight samples: tensor-core path, single-level posterior (nothing accumulates into hw), and no
+        prior training (its dA_l = hw^T d_wt reads hw in fp32)."""
+        return bool(self.tc and self.half_acts and self.patch_nums is None and all(o % 8 == 0 for o in self.offsets))
+
     def __init__(self, dims, data_dim, pixel_sizes, upsample_factors, latent_dim, layer_scales, paddings,
                  w0, device, precision=None, patch_nums=None, force_poly=False):
         import os
@@ -192,6 +198,7 @@ class FitEngine:
         self.offsets = [int(o) for o in self.offsets]
         self.W = int(sum(self.counts))
         self.ldw = _round_up(self.W, 4)
+        self.ldh = _round_up(self.W, 8)               # row stride of the fp16 weight samples
         if len(self.dims) != 5 or self.dims[1:4] != [32, 32, 32]:
             raise KernelError(f"unsupported INR {self.dims}: kernels are built for 3 hidden layers of 32")
         self.data_dim = data_dim
@@ -263,13 +270,16 @@ class FitEngine:
         self.map_generation += 1
         dev = self.device
         st = stream()
-        self.A, self.AT = [], []
+        self.A, self.AT, self.AT_h = [], [], []
         for a, c in zip(A_list, self.counts):
             a = a.detach().to(device=dev, dtype=torch.float32)
             ld = _round_up(c, 4)
             ap = torch.zeros(c, ld, device=dev); ap[:, :c] = a
             at = torch.zeros(c, ld, device=dev); at[:, :c] = a.t()
             self.A.append(ap); self.AT.append(at)
+            if self.tc:       # fp16 copy for the forward reparameterisation (K padded to whole 16-byte groups)
+                ah = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); ah[:, :c] = a.t().half()
+                self.AT_h.append(ah)
         self.conv_b = [up_state[f"conv{i}.bias"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
         conv_w = [up_state[f"conv{i}.weight"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
         self.w_eff, self.w_eff_t, self.w_eff_k = [None] * 3, [None] * 3, [None] * 3
@@ -370,6 +380,12 @@ class FitEngine:
         a.eps_w = ptr(noise.eps_for(lv.level))
         a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
         a.hw = ptr(ws["hw"])
+        if self.half_hw:
+            # single-level modalities: the weight samples are only read by the forward reparameterisation GEMM,
+            # as an MMA operand -- written as fp16 (rows padded to whole 16-byte groups, padding stays zero)
+            if "hw_h" not in ws:
+                ws["hw_h"] = torch.zeros(rows * S, self.ldh, dtype=torch.float16, device=self.device)
+            a.hw, a.hw_h = None, ptr(ws["hw_h"])
         a.lpe = ptr(ws["lpe"]) if lv.level == 0 else None
         if lv.level == 0 and self.half_acts and self.f2_half and self.dense1:
             # the dense first stage reads the latent grid as an fp16 MMA operand: write it that way
@@ -384,7 +400,7 @@ class FitEngine:
         a.eps_w_store = ptr(store[lv.level]) if a.eps_w is None else None
         a.eps_l_store = ptr(store[3]) if (lv.level == 0 and a.eps_l is None) else None
         a.seed, a.row_offset = noise.seed, noise.row_offset
-        a.rows, a.S, a.P, a.n_w, a.ld_hw = rows, S, lv.P, self.W, self.ldw
+        a.rows, a.S, a.P, a.n_w, a.ld_hw = rows, S, lv.P, self.W, (self.ldh if self.half_hw else self.ldw)
         a.n_l = self.L if lv.level == 0 else 0
         a.step, a.tensor_id, a.accumulate = noise.step, lv.level, int(lv.level > 0)
         a.dyn = ptr(self.step_state)
@@ -450,6 +466,11 @@ class FitEngine:
         def reparam():
             with self.section("reparam_fwd"):
                 for l, c in enumerate(self.counts):
+                    if self.half_hw:
+                        check(self.lib.rcb_gemm_tc_h(ws["hw_h"].data_ptr() + 2 * self.offsets[l], self.ldh, ptr(self.AT_h[l]),
+                                                     self.AT_h[l].shape[1], ws["wt"].data_ptr() + 4 * self.offsets[l], self.ldw,
+                                                     items, c, _round_up(c, 8), None, 1, 0, 0, stream()), "rcb_gemm_tc_h")
+                        continue
                     self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
                                ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
         join = self._fork(reparam)
