@@ -52,6 +52,20 @@ TRAFFIC = {"mlp_fwd_bwd": 775.5e6, "conv3_fwd": 625.6e6, "conv2_fwd": 365.5e6, "
            "conv2_bwd": 490.6e6, "update": 320.6e6, "sample": 158.1e6}   # profiles/r1_ncu_full_final.csv
 
 
+def conv_bytes(eng, items: int):
+    """Algorithmic HBM bytes per launch of the upsampler kernels (cifar shapes): every tensor read or written once."""
+    g1, g2, g3 = eng.geoms
+    n0 = g1.h * g1.w * g1.ic
+    n1 = g2.h * g2.w * g2.ic
+    n2 = g3.h * g3.w * g3.ic
+    n3 = g3.h * g3.fy * g3.w * g3.fx * g3.oc
+    h = 2 if (eng.half_acts and eng.f2_half) else 4          # bytes per stored activation element
+    per_item = {"conv2_fwd": n1 * h + n2 * h, "conv3_fwd": n2 * h + n3 * 4,
+                "conv3_bwd": n3 * 4 + n2 * h + n2 * 4, "conv2_bwd": n2 * 4 + n1 * h + n1 * 4,
+                "conv1_bwd": n1 * 4 + n0 * 4}
+    return {k: float(v) * items for k, v in per_item.items()}
+
+
 def schedule(G: int):
     return 30000 + G * max(30000 // G, 50)
 
@@ -431,7 +445,8 @@ def run_b200(args):
             "metric": "datapoints compressed/sec (CIFAR-10 32x32)", "value": value, "unit": "datapoints/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": t_fit, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": ("tf32 (tcgen05, fp32 accumulate) fit / f64 REC" if m.engine.tc else "f32 fit (SIMT FFMA) / f64 REC"),
+            "dtype": (("tf32 + fp16 upsampler activations / weight samples" if m.engine.half_hw else "tf32")
+                      + " (tcgen05, fp32 accumulate) fit / f64 REC" if m.engine.tc else "f32 fit (SIMT FFMA) / f64 REC"),
             "data": "synthetic",
             "config": {"workload": "cifar-shape 32x32, %d rows/GPU, S=5, G=%d blocks x 16 bit (0.52 bpp), "
                                    "random-init prior" % (ROWS_PER_GPU, G),
@@ -447,9 +462,14 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf"], "traffic": TRAFFIC.get(dom), "peak_source": pk["src"] + " bf16 sustained",
                          "frac_of_tf32_peak": achieved / (pk["tf"] / 2),
-                         "note": "operands are TF32 (half the bf16 rate): frac_of_tf32_peak uses peak/2; executed "
+                         "note": "MLP operands are TF32 (half the bf16 rate): frac_of_tf32_peak uses peak/2; executed "
                                  "(polyphase) FLOPs; per-launch ms: "
                                  + ", ".join(f"{k}={v:.3f}" for k, v in sorted(timed.items(), key=lambda kv: -kv[1]))},
+            # the upsampler kernels are HBM-bound: algorithmic bytes per launch (tensors read + written once, in the
+            # precision they are stored in) over the event-timed launch duration, against the measured copy bandwidth
+            "hbm_kernels": {k: {"ms": timed[k], "algorithmic_MB": b / 1e6, "achieved_GBps": b / (timed[k] * 1e-3) / 1e9,
+                                "frac": b / (timed[k] * 1e-3) / 1e9 / pk["hbm"]}
+                            for k, b in conv_bytes(m.engine, ROWS_PER_GPU * S).items() if k in timed},
             # REC round: every (row, block) pair streams its D x 65536 f32 candidate table once
             # (no reuse assumed) -> algorithmic bytes = rows * mean(D) * 65536 * 4
             "rec": {"candidates_per_s": cand_per_s, "ms_per_round": t_round, "pairs_per_round": ROWS_PER_GPU * world,

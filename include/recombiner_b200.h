@@ -110,6 +110,11 @@ int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, float* C, in
 int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt, void* C_h, int ldc,
                    int M, int N, int K, const float* bias, int bias_mod, int act, rcb_stream_t stream);
 
+/* nb <= 4 products C_i[M,N_i] = A_i[M,K_i] @ Bt_i[N_i,K_i]^T in ONE launch (the per-layer reparameterisation
+ * products h_w[seg_l] @ A_l, test_model.py:348-349, and their data gradients).  The arrays are host arrays of nb
+ * entries; A_i share lda, C_i share ldc; in_half: A_i and Bt_i are fp16.  No bias / activation / accumulation. */
+int rcb_gemm_tc_batch(int nb, const void* const* A, int lda, const void* const* Bt, const int* ldbt,
+                      float* const* C, int ldc, int M, const int* N, const int* K, int in_half, rcb_stream_t stream);
 /* fp16 A and fp16 Bt, fp32 C (K % 8 == 0, lda % 8 == 0, ldbt % 8 == 0): same epilogue as rcb_gemm_tc */
 int rcb_gemm_tc_h(const void* A_h, int lda, const void* Bt_h, int ldbt, float* C, int ldc,
                   int M, int N, int K, const float* bias, int bias_mod, int act, int accumulate, rcb_stream_t stream);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "rcb_upconv_fwd_tc_hh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_gemm_tc_oh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
     "rcb_gemm_tc_hh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
+    "rcb_gemm_tc_batch": [I32, P, I32, P, P, P, I32, I32, P, P, I32, P],
     "rcb_gemm_tc_h": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],
     "rcb_upconv_fwd_tc_oh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd_tc_ah": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],

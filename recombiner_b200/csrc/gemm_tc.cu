@@ -31,10 +31,10 @@ struct TcSmem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    float* __restrict__ C, int ldc, int M, int N, int K,
-                    const float* __restrict__ bias, int bias_mod, int act, int accumulate, int out_half, int in_half) {
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                             float* __restrict__ C, int ldc, int M, int N, int K,
+                                             const float* __restrict__ bias, int bias_mod, int act, int accumulate,
+                                             int out_half, int in_half) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -73,8 +73,8 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
         mbar_expect_tx(&full[s], S::STAGE_BYTES);
-        tma_load_2d(&tmA, &full[s], a_dst, kb * BKE, m0);
-        tma_load_2d(&tmB, &full[s], b_dst, kb * BKE, n0);
+        tma_load_2d(tmA, &full[s], a_dst, kb * BKE, m0);
+        tma_load_2d(tmB, &full[s], b_dst, kb * BKE, n0);
       }
       __syncwarp();
     }
@@ -174,6 +174,30 @@ gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
   }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tf32_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    float* __restrict__ C, int ldc, int M, int N, int K,
+                    const float* __restrict__ bias, int bias_mod, int act, int accumulate, int out_half, int in_half) {
+  gemm_tc_body<BN>(&tmA, &tmB, C, ldc, M, N, K, bias, bias_mod, act, accumulate, out_half, in_half);
+}
+
+// Several GEMMs that share M and the row strides in one launch (blockIdx.z picks the problem): the four per-layer
+// reparameterisation products are 360 CTAs each -- 1.2 waves of the 296 CTA slots -- but 3.7 waves together.
+constexpr int GEMM_MAX_BATCH = 4;
+struct GemmBatch {
+  CUtensorMap a[GEMM_MAX_BATCH], b[GEMM_MAX_BATCH];
+  float* C[GEMM_MAX_BATCH];
+  int N[GEMM_MAX_BATCH], K[GEMM_MAX_BATCH];
+};
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_batch_kernel(const __grid_constant__ GemmBatch g, int ldc, int M, int in_half) {
+  const int z = blockIdx.z;
+  if ((int)blockIdx.y * BN >= g.N[z]) return;
+  gemm_tc_body<BN>(&g.a[z], &g.b[z], g.C[z], ldc, M, g.N[z], g.K[z], nullptr, 1, 0, 0, 0, in_half);
 }
 
 // ---- host side: tensor maps through the driver entry point (no libcuda link) -------------
@@ -289,4 +313,38 @@ extern "C" int rcb_gemm_tc_h(const void* A_h, int lda, const void* Bt_h, int ldb
   const float* Bt = reinterpret_cast<const float*>(Bt_h);
   if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st, 0, 1);
   return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st, 0, 1);
+}
+
+// nb <= 4 products C_i[M, N_i] = A_i[M, K_i] @ Bt_i[N_i, K_i]^T in one launch; A_i share the row stride lda, C_i share ldc;
+// in_half: A_i and Bt_i are fp16 (K_i % 8 == 0), else fp32 / TF32.  No bias, activation or accumulation.
+extern "C" int rcb_gemm_tc_batch(int nb, const void* const* A, int lda, const void* const* Bt, const int* ldbt,
+                                 float* const* C, int ldc, int M, const int* N, const int* K, int in_half,
+                                 rcb_stream_t stream) {
+  RCB_CHECK_ARG(nb >= 1 && nb <= GEMM_MAX_BATCH && A && Bt && ldbt && C && N && K, "rcb_gemm_tc_batch: 1..4 problems");
+  const int al = in_half ? 8 : 4;
+  RCB_CHECK_ARG(M > 0 && lda % al == 0 && ldc % 4 == 0, "rcb_gemm_tc_batch: bad M or leading dimensions");
+  GemmBatch g;
+  int n_max = 0;
+  for (int i = 0; i < GEMM_MAX_BATCH; ++i) {
+    const int j = i < nb ? i : 0;             // unused slots repeat problem 0 (never launched: grid.z = nb)
+    RCB_CHECK_ARG(A[j] && Bt[j] && C[j] && N[j] > 0 && K[j] > 0 && ldbt[j] % al == 0, "rcb_gemm_tc_batch: bad problem");
+    RCB_CHECK_ARG(!in_half || K[j] % 8 == 0, "rcb_gemm_tc_batch: fp16 operands need K %% 8 == 0");
+    RCB_CHECK_ARG(((uintptr_t)A[j] % 16 == 0) && ((uintptr_t)Bt[j] % 16 == 0) && ((uintptr_t)C[j] % 16 == 0),
+                  "rcb_gemm_tc_batch: operands must be 16-byte aligned");
+    if (int rc = make_map_2d(&g.a[i], reinterpret_cast<const float*>(A[j]), M, K[j], lda, TC_BM, in_half ? 2 : 4)) return rc;
+    if (int rc = make_map_2d(&g.b[i], reinterpret_cast<const float*>(Bt[j]), N[j], K[j], ldbt[j], 128, in_half ? 2 : 4)) return rc;
+    g.C[i] = C[j]; g.N[i] = N[j]; g.K[i] = K[j];
+    if (i < nb && N[j] > n_max) n_max = N[j];
+  }
+  const int smem = TcSmem<128>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_batch_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("rcb_gemm_tc_batch: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+    configured = true;
+  }
+  dim3 grid(ceil_div(M, TC_BM), ceil_div(n_max, 128), nb);
+  gemm_tc_batch_kernel<128><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(g, ldc, M, in_half);
+  RCB_CHECK_LAUNCH("rcb_gemm_tc_batch");
+  return 0;
 }

@@ -182,6 +182,8 @@ class FitEngine:
         # the reparameterisation GEMMs (hw <-> wt) and the upsampler chain (lpe <-> pe) are independent
         # between the sampling kernel and the MLP: run them on two streams
         self.overlap = os.environ.get("RECOMBINER_OVERLAP", "1") != "0"
+        # the four per-layer reparameterisation GEMMs as one launch: "1" both directions, "fwd" forward only, "0" off
+        self.batch_gemm = os.environ.get("RECOMBINER_BATCH_GEMM", "fwd")
         # conv2's activations are only ever read as MMA operands (conv3) and for their signs (LeakyReLU mask):
         # where conv3 has the fp16-operand kernel they are stored as fp16 -- the 10 mantissa bits a TF32 MMA
         # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
@@ -420,6 +422,20 @@ class FitEngine:
         check(self.lib.rcb_gemm(pa, lda, pb, ldb, pc, ldc, M, N, K, ptr(bias), bias_mod, act, trans_a, acc, stream()),
               "rcb_gemm")
 
+    @staticmethod
+    def _batch_args(a_ptrs, lda, Bt, c_ptrs, ldc, M, Ns, Ks, in_half):
+        """Argument tuple of rcb_gemm_tc_batch (host arrays kept alive next to it)."""
+        nb = len(a_ptrs)
+        A = (C.c_void_p * nb)(*a_ptrs)
+        B = (C.c_void_p * nb)(*[t.data_ptr() for t in Bt])
+        ldb = (C.c_int * nb)(*[t.shape[1] for t in Bt])
+        Cp = (C.c_void_p * nb)(*c_ptrs)
+        N = (C.c_int * nb)(*Ns)
+        K = (C.c_int * nb)(*Ks)
+        args = (nb, C.addressof(A), lda, C.addressof(B), C.addressof(ldb), C.addressof(Cp), ldc, M, C.addressof(N),
+                C.addressof(K), in_half)
+        return args, (A, B, ldb, Cp, N, K, list(Bt))
+
     def _eps_store(self, ws, rows, S):
         st = ws.get("eps_store")
         if st is None:
@@ -465,6 +481,17 @@ class FitEngine:
 
         def reparam():
             with self.section("reparam_fwd"):
+                if self.tc and self.batch_gemm in ("1", "fwd"):
+                    half = self.half_hw
+                    key = ("rp_fwd", half, self.map_generation)
+                    if key not in ws:           # the four per-layer products in one launch
+                        src, es, ld = (ws["hw_h"], 2, self.ldh) if half else (ws["hw"], 4, self.ldw)
+                        Bt = self.AT_h if half else self.AT
+                        ws[key] = self._batch_args([src.data_ptr() + es * o for o in self.offsets], ld, Bt,
+                                                   [ws["wt"].data_ptr() + 4 * o for o in self.offsets], self.ldw, items,
+                                                   self.counts, [_round_up(c, 8) if half else c for c in self.counts], int(half))
+                    check(self.lib.rcb_gemm_tc_batch(*ws[key][0], stream()), "rcb_gemm_tc_batch")
+                    return
                 for l, c in enumerate(self.counts):
                     if self.half_hw:
                         check(self.lib.rcb_gemm_tc_h(ws["hw_h"].data_ptr() + 2 * self.offsets[l], self.ldh, ptr(self.AT_h[l]),
@@ -564,6 +591,14 @@ class FitEngine:
 
         def reparam():
             with self.section("reparam_bwd"):
+                if self.tc and self.batch_gemm == "1":
+                    key = ("rp_bwd", self.map_generation)
+                    if key not in ws:
+                        ws[key] = self._batch_args([ws["d_wt"].data_ptr() + 4 * o for o in self.offsets], self.ldw, self.A,
+                                                   [ws["d_hw"].data_ptr() + 4 * o for o in self.offsets], self.ldw, items,
+                                                   self.counts, self.counts, 0)
+                    check(self.lib.rcb_gemm_tc_batch(*ws[key][0], stream()), "rcb_gemm_tc_batch")
+                    return
                 for l, c in enumerate(self.counts):
                     self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
                                ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])

@@ -39,3 +39,38 @@ def test_gemm_tc_matches_fp64(M, N, K):
     check(lib.rcb_gemm_tc(ptr(Ad), lda, ptr(Bd), ldb, ptr(Cd), ldc, M, N, K, None, 1, 0, 1, stream()))
     got3 = Cd[:, :N].cpu().double().numpy()
     assert (np.abs(got3 - (ref.numpy() + 1.0)) / scale).max() < 2e-3
+
+
+def test_batched_launch_equals_separate_launches():
+    """rcb_gemm_tc_batch (one launch, blockIdx.z = problem) against one rcb_gemm_tc / rcb_gemm_tc_h per problem:
+    same kernel body, so the results must be bit-identical -- fp32 (TF32) and fp16 operands, ragged N and K."""
+    import ctypes as C
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import check, ptr, stream
+    from recombiner_b200.engine import FitEngine
+    lib = _lib.load()
+    M, ld = 300, 3272
+    Ns, Ks, offs = [1056, 1056, 1056, 99], [1056, 1056, 1056, 104], [0, 1056, 2112, 3168]
+    gen = torch.Generator().manual_seed(11)
+    for half in (0, 1):
+        dt = torch.float16 if half else torch.float32
+        es = 2 if half else 4
+        A = torch.randn(M, ld, generator=gen).cuda().to(dt)
+        A[:, 3267:] = 0
+        Bts = [(torch.randn(n, k, generator=gen) / np.sqrt(k)).cuda().to(dt) for n, k in zip(Ns, Ks)]
+        c_one = torch.zeros(M, 3268, device="cuda")
+        c_bat = torch.zeros(M, 3268, device="cuda")
+        for n, k, o, bt in zip(Ns, Ks, offs, Bts):
+            if half:
+                check(lib.rcb_gemm_tc_h(A.data_ptr() + es * o, ld, ptr(bt), k, c_one.data_ptr() + 4 * o, 3268, M, n, k,
+                                        None, 1, 0, 0, stream()))
+            else:
+                check(lib.rcb_gemm_tc(A.data_ptr() + es * o, ld, ptr(bt), k, c_one.data_ptr() + 4 * o, 3268, M, n, k,
+                                      None, 1, 0, 0, stream()))
+        args, keep = FitEngine._batch_args([A.data_ptr() + es * o for o in offs], ld, Bts,
+                                           [c_bat.data_ptr() + 4 * o for o in offs], 3268, M, Ns, Ks, half)
+        check(lib.rcb_gemm_tc_batch(*args, stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(c_one, c_bat)
+        ref = torch.cat([A[:, o:o + k].float() @ bt.float().t() for o, k, bt in zip(offs, Ks, Bts)], 1)
+        assert float((c_bat[:, :3267] - ref).abs().max()) < 5e-3 * float(ref.abs().max())
