@@ -279,3 +279,29 @@ def test_graph_replayed_steps_equal_eager_steps(name, dataset, n_data, S, precis
         assert torch.equal(le.beta, lg.beta)
         for k in ("m1_loc", "v_loc", "m1_ls", "v_ls"):
             assert torch.equal(le.adam[k], lg.adam[k])
+
+
+def test_full_size_kodak_tensor_core_path_against_fp32_path():
+    """kodak at its real shape on the tcgen05 path -- polyphase first stage with fp16 output, the persistent x2 kernels on
+    the stitched 64 x 96 / 128 x 192 grids (one item per tile, ragged tiles), fp16 activations, general sampling kernels --
+    against the fp32 SIMT path of the same model on the same noise: forward <= 5e-3 absolute, gradients <= 2 % relative L2
+    per tensor (the tolerance stated for the TF32 mode)."""
+    from tests.helpers import product_test_model
+    S = 1
+    case = cases.make_fit_case("kodak", 1, S, total_bits=800.0)
+    x, y = case["x"].cuda(), case["y"].cuda()
+    out = {}
+    for precision in ("fp32", "tf32"):
+        m = product_test_model(case, "kodak", precision=precision)
+        if precision == "tf32":
+            assert m.engine.f2_half and m.engine.half_acts and not m.engine.half_hw
+        y_pred = m.predict(x, None, S, eps=case["eps"])
+        yp = y_pred if S > 1 else y_pred[:, None]
+        loss = torch.mean((yp - y[:, None]) ** 2) * y.shape[0] + m.calculate_kl()
+        loss.backward()
+        out[precision] = (yp.detach().cpu().numpy(), loss.item(),
+                          [getattr(m, pre + k).grad.cpu().numpy() for pre in ("", "h_", "hh_") for k in ("loc", "log_scale")])
+    assert np.abs(out["tf32"][0] - out["fp32"][0]).max() < 5e-3
+    assert out["tf32"][1] == pytest.approx(out["fp32"][1], rel=1e-3)
+    for a, b in zip(out["tf32"][2], out["fp32"][2]):
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-2
