@@ -85,6 +85,8 @@ typedef struct {
   void* lpe_h;                           /* optional: the latent grid is written here as fp16 INSTEAD of lpe (rcb_gemm_tc_hh) */
   void* hw_h;                            /* optional: the weight samples are written here as fp16 INSTEAD of hw (row stride ld_hw
                                             fp16 elements; not with accumulate) for rcb_gemm_tc_h */
+  const int* p2g;                        /* optional: inverse of g2p (parameter index of a stored column), lets the row
+                                            kernel read the posterior coalesced */
 } rcb_sample_args;
 int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
 

@@ -23,7 +23,7 @@ class SampleArgs(C.Structure):
                                  "eps_w", "eps_l", "hw", "lpe", "lpe_slot", "eps_w_store", "eps_l_store")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate",
-                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P), ("lpe_h", P), ("hw_h", P)]
+                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P), ("lpe_h", P), ("hw_h", P), ("p2g", P)]
 
 
 class UpconvGeom(C.Structure):

@@ -68,22 +68,26 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
   extern __shared__ float sm[];
   float* s_mu = sm;                 // parameter order
   float* s_sig = sm + a.P;
-  float* g_mu = sm + 2 * a.P;       // group order (as stored)
-  float* g_sig = sm + 3 * a.P;
   const int n = blockIdx.x;
-  for (int q = threadIdx.x; q < a.P; q += blockDim.x) {
-    const int64_t e = (int64_t)n * a.P + q;
-    const float m = a.mask ? a.mask[e] : 0.f;
-    float mu = a.loc[e] * (1.f - m);
-    if (a.sample) mu += a.sample[e] * m;
-    g_mu[q] = mu;
-    g_sig[q] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
-  }
-  __syncthreads();
-  for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
-    const int q = a.g2p ? a.g2p[p] : p;
-    s_mu[p] = g_mu[q];
-    s_sig[p] = g_sig[q];
+  if (a.g2p && !a.p2g) {            // no inverse map given: gather the row through g2p
+    for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
+      const int64_t e = (int64_t)n * a.P + a.g2p[p];
+      const float m = a.mask ? a.mask[e] : 0.f;
+      float mu = a.loc[e] * (1.f - m);
+      if (a.sample) mu += a.sample[e] * m;
+      s_mu[p] = mu;
+      s_sig[p] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
+    }
+  } else {                          // coalesced read in stored (group) order, scattered into parameter order
+    for (int q = threadIdx.x; q < a.P; q += blockDim.x) {
+      const int64_t e = (int64_t)n * a.P + q;
+      const float m = a.mask ? a.mask[e] : 0.f;
+      float mu = a.loc[e] * (1.f - m);
+      if (a.sample) mu += a.sample[e] * m;
+      const int p = a.p2g ? a.p2g[q] : q;
+      s_mu[p] = mu;
+      s_sig[p] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
+    }
   }
   __syncthreads();
   const int64_t gn = a.row_offset + n;
@@ -144,6 +148,59 @@ __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) 
   float* s_dsig = sm + a.P;
   const int r = blockIdx.x;
   const int64_t gn = a.row_offset + r;
+  const bool stored_noise = a.eps_w && (a.n_l == 0 || a.eps_l);
+  if (stored_noise && a.S == 5) {
+    // the fit loop's case (five samples, noise kept by the sampling kernel): straight-line loads through
+    // per-sample base pointers, two parameters (twenty loads) in flight per thread; same summation order
+    constexpr int SS = 5;
+    const float* dh = a.d_hw + (int64_t)r * SS * a.ld_hw;
+    const float* ew = a.eps_w + (int64_t)r * SS * a.n_w;
+    for (int p0 = threadIdx.x; p0 < a.n_w; p0 += 2 * blockDim.x) {
+      const int p1 = p0 + blockDim.x;
+      const bool two = p1 < a.n_w;
+      float d0[SS], e0[SS], d1[SS], e1[SS];
+#pragma unroll
+      for (int k = 0; k < SS; ++k) {
+        d0[k] = dh[(int64_t)k * a.ld_hw + p0];
+        e0[k] = ew[(int64_t)k * a.n_w + p0];
+        d1[k] = two ? dh[(int64_t)k * a.ld_hw + p1] : 0.f;
+        e1[k] = two ? ew[(int64_t)k * a.n_w + p1] : 0.f;
+      }
+      float m0 = 0.f, s0 = 0.f, m1 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < SS; ++k) {
+        m0 += d0[k]; s0 = fmaf(d0[k], e0[k], s0);
+        m1 += d1[k]; s1 = fmaf(d1[k], e1[k], s1);
+      }
+      s_dmu[p0] = m0; s_dsig[p0] = s0;
+      if (two) { s_dmu[p1] = m1; s_dsig[p1] = s1; }
+    }
+    if (a.n_l > 0) {
+      const float* dl = a.d_lpe + (int64_t)r * SS * a.n_l;
+      const float* el = a.eps_l + (int64_t)r * a.n_l;
+      const int64_t es = (int64_t)a.rows * a.n_l;            // eps_l is (S, rows, n_l)
+      for (int l0 = threadIdx.x; l0 < a.n_l; l0 += 2 * blockDim.x) {
+        const int l1 = l0 + blockDim.x;
+        const bool two = l1 < a.n_l;
+        float d0[SS], e0[SS], d1[SS], e1[SS];
+#pragma unroll
+        for (int k = 0; k < SS; ++k) {
+          d0[k] = dl[(int64_t)k * a.n_l + l0];
+          e0[k] = el[k * es + l0];
+          d1[k] = two ? dl[(int64_t)k * a.n_l + l1] : 0.f;
+          e1[k] = two ? el[k * es + l1] : 0.f;
+        }
+        float m0 = 0.f, s0 = 0.f, m1 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < SS; ++k) {
+          m0 += d0[k]; s0 = fmaf(d0[k], e0[k], s0);
+          m1 += d1[k]; s1 = fmaf(d1[k], e1[k], s1);
+        }
+        s_dmu[a.n_w + l0] = m0; s_dsig[a.n_w + l0] = s0;
+        if (two) { s_dmu[a.n_w + l1] = m1; s_dsig[a.n_w + l1] = s1; }
+      }
+    }
+  } else
   // loads of 2 parameters x up to 4 samples are issued together (memory-level parallelism);
   // the sums still run over s in ascending order
   for (int p0 = threadIdx.x; p0 < a.P; p0 += 2 * blockDim.x) {
@@ -542,7 +599,7 @@ extern "C" int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->n_w + a->n_l == a->P || (a->n_l == 0 && a->n_w == a->P), "rcb_fit_sample: n_w+n_l != P");
   RCB_CHECK_ARG(a->ld_hw >= a->n_w, "rcb_fit_sample: ld_hw too small");
   RCB_CHECK_ARG(a->rows <= 65535, "rcb_fit_sample: at most 65535 rows per call");
-  const size_t row_smem = 4 * sizeof(float) * (size_t)a->P;
+  const size_t row_smem = 2 * sizeof(float) * (size_t)a->P;
   if (!a->perm && !a->row_map && !a->lpe_slot && !a->accumulate && row_smem <= 200 * 1024) {
     if (row_smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);

@@ -379,6 +379,7 @@ class FitEngine:
         a = SampleArgs()
         a.loc, a.log_scale, a.mask, a.sample = ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.mask), ptr(lv.sample)
         a.g2p, a.perm, a.row_map = ptr(lv.g2p), ptr(lv.perm), ptr(lv.row_map)
+        a.p2g = ptr(lv.p2g)
         a.eps_w = ptr(noise.eps_for(lv.level))
         a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
         a.hw = ptr(ws["hw"])
