@@ -141,25 +141,40 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* tmA, const CUten
     constexpr int LPR = BN / 4;
     constexpr int RPI = 32 / LPR;
     const int sub = lane / LPR, n = n0 + (lane % LPR) * 4;
-#pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += RPI) {
-      const int rr = r0 + sub;
-      const int row = m0 + q * 32 + rr;
-      if (row < M && n < N) {
-        const float4 f4 = *reinterpret_cast<const float4*>(wbuf + rr * S::EPI_LD + (lane % LPR) * 4);
-        float o[4] = {f4.x, f4.y, f4.z, f4.w};
-        float* crow = C + (int64_t)row * ldc;
+    // a lane keeps its four columns for every row it writes: bias fetched once
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (n + t < N) {
-            if (accumulate) o[t] += crow[n + t];
-            if (bias) o[t] += bias[(n + t) % bias_mod];
-            if (act) o[t] = o[t] > 0.f ? o[t] : 0.01f * o[t];
-          }
+      for (int t = 0; t < 4; ++t) if (n + t < N) bv[t] = bias[(n + t) % bias_mod];
+    }
+    const float slope = act ? 0.01f : 1.0f;
+    // four rows per trip: the shared-memory loads (and the C loads of an accumulating call) are issued together
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 4 * RPI) {
+      float4 f4[4], c4[4];
+      int rows[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r0 + u * RPI + sub;
+        rows[u] = (rr < 32 && n < N) ? m0 + q * 32 + rr : M;
+        f4[u] = *reinterpret_cast<const float4*>(wbuf + (rr & 31) * S::EPI_LD + (lane % LPR) * 4);
+        c4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (accumulate && rows[u] < M) {
+          const float* crow = C + (int64_t)rows[u] * ldc;
+          if (n + 4 <= N) c4[u] = *reinterpret_cast<const float4*>(crow + n);
+          else { c4[u].x = crow[n]; if (n + 1 < N) c4[u].y = crow[n + 1]; if (n + 2 < N) c4[u].z = crow[n + 2]; }
         }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rows[u] >= M) continue;
+        float o[4] = {f4[u].x + c4[u].x + bv[0], f4[u].y + c4[u].y + bv[1], f4[u].z + c4[u].z + bv[2], f4[u].w + c4[u].w + bv[3]};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[t] = o[t] > 0.f ? o[t] : slope * o[t];
+        float* crow = C + (int64_t)rows[u] * ldc;
         if (out_half) {                      // C is fp16 (N % 4 == 0, no accumulate: checked by the launcher)
           const __half2 lo = __floats2half2_rn(o[0], o[1]), hi = __floats2half2_rn(o[2], o[3]);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(C) + (int64_t)row * ldc + n) =
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(C) + (int64_t)rows[u] * ldc + n) =
               make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
         } else if (n + 4 <= N) {
           *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
