@@ -114,9 +114,11 @@ int rcb_gemm_tc_oh(const float* A, int lda, const float* Bt, int ldbt, void* C_h
 
 /* nb <= 4 products C_i[M,N_i] = A_i[M,K_i] @ Bt_i[N_i,K_i]^T in ONE launch (the per-layer reparameterisation
  * products h_w[seg_l] @ A_l, test_model.py:348-349, and their data gradients).  The arrays are host arrays of nb
- * entries; A_i share lda, C_i share ldc; in_half: A_i and Bt_i are fp16.  No bias / activation / accumulation. */
+ * entries; A_i share lda, C_i share ldc; in_half: A_i and Bt_i are fp16; C_i is multiplied by out_scale.  No bias /
+ * activation / accumulation. */
 int rcb_gemm_tc_batch(int nb, const void* const* A, int lda, const void* const* Bt, const int* ldbt,
-                      float* const* C, int ldc, int M, const int* N, const int* K, int in_half, rcb_stream_t stream);
+                      float* const* C, int ldc, int M, const int* N, const int* K, int in_half, float out_scale,
+                      rcb_stream_t stream);
 /* fp16 A and fp16 Bt, fp32 C (K % 8 == 0, lda % 8 == 0, ldbt % 8 == 0): same epilogue as rcb_gemm_tc */
 int rcb_gemm_tc_h(const void* A_h, int lda, const void* Bt_h, int ldbt, float* C, int ldc,
                   int M, int N, int K, const float* bias, int bias_mod, int act, int accumulate, rcb_stream_t stream);
@@ -223,6 +225,10 @@ typedef struct {
   int items, S, pix, n_f, out, ld_w, mode;
   int ph, pw;           /* patch extent along y and x (pixels); pix = pd*ph*pw (with pe_base) */
   float coef, w0;
+  float d_wt_h_scale;   /* with d_wt_h: power-of-two factor applied before the fp16 rounding (undone by the consumer) */
+  int ld_wh;            /* row stride of d_wt_h in fp16 elements */
+  void* d_wt_h;         /* optional (rcb_mlp_tc, mode 1): the weight gradients are written here as fp16 (clamped to the
+                           fp16 range) INSTEAD of d_wt, for an fp16-operand data-gradient GEMM (rcb_gemm_tc_batch) */
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
 /* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA (one 128-thread group

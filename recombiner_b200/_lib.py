@@ -34,7 +34,7 @@ class MlpArgs(C.Structure):
     _fields_ = [(n, P) for n in ("wt", "xt", "pe", "y", "dy", "y_pred", "d_pe", "d_wt", "sqerr", "pe_base")] + \
                [("x_row_stride", I64), ("pitch_z", I64), ("pitch_y", I64)] + \
                [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode", "ph", "pw")] + \
-               [("coef", F32), ("w0", F32)]
+               [("coef", F32), ("w0", F32), ("d_wt_h_scale", F32), ("ld_wh", I32), ("d_wt_h", P)]
 
 
 class UpdateArgs(C.Structure):
@@ -78,7 +78,7 @@ SIGNATURES = {
     "rcb_upconv_fwd_tc_hh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_gemm_tc_oh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
     "rcb_gemm_tc_hh": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, P],
-    "rcb_gemm_tc_batch": [I32, P, I32, P, P, P, I32, I32, P, P, I32, P],
+    "rcb_gemm_tc_batch": [I32, P, I32, P, P, P, I32, I32, P, P, I32, F32, P],
     "rcb_gemm_tc_h": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],
     "rcb_upconv_fwd_tc_oh": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],
     "rcb_upconv_bwd_tc_ah": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],

@@ -34,7 +34,7 @@ template <int BN>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* tmA, const CUtensorMap* tmB,
                                              float* __restrict__ C, int ldc, int M, int N, int K,
                                              const float* __restrict__ bias, int bias_mod, int act, int accumulate,
-                                             int out_half, int in_half) {
+                                             int out_half, int in_half, float out_scale = 1.0f) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -168,7 +168,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* tmA, const CUten
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (rows[u] >= M) continue;
-        float o[4] = {f4[u].x + c4[u].x + bv[0], f4[u].y + c4[u].y + bv[1], f4[u].z + c4[u].z + bv[2], f4[u].w + c4[u].w + bv[3]};
+        float o[4] = {f4[u].x * out_scale + c4[u].x + bv[0], f4[u].y * out_scale + c4[u].y + bv[1],
+                      f4[u].z * out_scale + c4[u].z + bv[2], f4[u].w * out_scale + c4[u].w + bv[3]};
 #pragma unroll
         for (int t = 0; t < 4; ++t) o[t] = o[t] > 0.f ? o[t] : slope * o[t];
         float* crow = C + (int64_t)rows[u] * ldc;
@@ -209,10 +210,10 @@ struct GemmBatch {
 };
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-gemm_tc_batch_kernel(const __grid_constant__ GemmBatch g, int ldc, int M, int in_half) {
+gemm_tc_batch_kernel(const __grid_constant__ GemmBatch g, int ldc, int M, int in_half, float out_scale) {
   const int z = blockIdx.z;
   if ((int)blockIdx.y * BN >= g.N[z]) return;
-  gemm_tc_body<BN>(&g.a[z], &g.b[z], g.C[z], ldc, M, g.N[z], g.K[z], nullptr, 1, 0, 0, 0, in_half);
+  gemm_tc_body<BN>(&g.a[z], &g.b[z], g.C[z], ldc, M, g.N[z], g.K[z], nullptr, 1, 0, 0, 0, in_half, out_scale);
 }
 
 // ---- host side: tensor maps through the driver entry point (no libcuda link) -------------
@@ -334,7 +335,7 @@ extern "C" int rcb_gemm_tc_h(const void* A_h, int lda, const void* Bt_h, int ldb
 // in_half: A_i and Bt_i are fp16 (K_i % 8 == 0), else fp32 / TF32.  No bias, activation or accumulation.
 extern "C" int rcb_gemm_tc_batch(int nb, const void* const* A, int lda, const void* const* Bt, const int* ldbt,
                                  float* const* C, int ldc, int M, const int* N, const int* K, int in_half,
-                                 rcb_stream_t stream) {
+                                 float out_scale, rcb_stream_t stream) {
   RCB_CHECK_ARG(nb >= 1 && nb <= GEMM_MAX_BATCH && A && Bt && ldbt && C && N && K, "rcb_gemm_tc_batch: 1..4 problems");
   const int al = in_half ? 8 : 4;
   RCB_CHECK_ARG(M > 0 && lda % al == 0 && ldc % 4 == 0, "rcb_gemm_tc_batch: bad M or leading dimensions");
@@ -359,7 +360,7 @@ extern "C" int rcb_gemm_tc_batch(int nb, const void* const* A, int lda, const vo
     configured = true;
   }
   dim3 grid(ceil_div(M, TC_BM), ceil_div(n_max, 128), nb);
-  gemm_tc_batch_kernel<128><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(g, ldc, M, in_half);
+  gemm_tc_batch_kernel<128><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(g, ldc, M, in_half, out_scale);
   RCB_CHECK_LAUNCH("rcb_gemm_tc_batch");
   return 0;
 }

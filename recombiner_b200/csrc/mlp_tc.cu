@@ -536,10 +536,13 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     // ---- weight gradients (M = 64 accumulators): input feature i < 16 in TMEM lane i, 16 <= i < 32 in lane
     //      32 + (i - 16), the ones row (bias) in lane 64; group 0's warps take columns 0-15, group 1's 16-31
     float* gw = a.d_wt + (int64_t)item * a.ld_w;
+    __half* gwh = a.d_wt_h ? reinterpret_cast<__half*>(a.d_wt_h) + (int64_t)item * a.ld_wh : nullptr;
+    auto to_h = [](float v) { return fminf(fmaxf(v, -65504.f), 65504.f); };      // clamp: an overflow must not turn into inf
     const int j0 = g * 16;
     if (q <= 2) {
       uint32_t acc[16];
-      const float sc = w0 * unscale;
+      const float sc = w0 * unscale * (gwh ? a.d_wt_h_scale : 1.f);
+      const float sc3 = unscale * (gwh ? a.d_wt_h_scale : 1.f);
       const bool wrow = q < 2 && lane < 16, brow = q == 2 && lane == 0;
       const int irow = q * 16 + lane;
 #pragma unroll
@@ -547,8 +550,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         tmem_ld16_issue(tm + TM_DW + (uint32_t)(l * 32 + j0), acc);
         tmem_ld_wait();
         const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
-        float* dst = wrow ? gw + off + HID + irow * HID + j0 : gw + off + j0;
-        if (wrow || brow) {
+        const int didx = wrow ? off + HID + irow * HID + j0 : off + j0;
+        float* dst = gw + didx;
+        if ((wrow || brow) && gwh) {
+          uint32_t hv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            hv[c] = pack_h2(to_h(sc * __uint_as_float(acc[2 * c])), to_h(sc * __uint_as_float(acc[2 * c + 1])));
+          *reinterpret_cast<uint4*>(gwh + didx) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<uint4*>(gwh + didx + 8) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+        } else if (wrow || brow) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *(float4*)(dst + c * 4) = make_float4(sc * __uint_as_float(acc[c * 4]), sc * __uint_as_float(acc[c * 4 + 1]),
@@ -560,10 +571,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         tmem_ld_wait();
         if (wrow) {
 #pragma unroll
-          for (int k = 0; k < OUT; ++k) gw[off3 + OUT + irow * OUT + k] = unscale * __uint_as_float(acc[k]);
+          for (int k = 0; k < OUT; ++k) {
+            if (gwh) gwh[off3 + OUT + irow * OUT + k] = __float2half_rn(to_h(sc3 * __uint_as_float(acc[k])));
+            else gw[off3 + OUT + irow * OUT + k] = unscale * __uint_as_float(acc[k]);
+          }
         } else if (brow) {
 #pragma unroll
-          for (int k = 0; k < OUT; ++k) gw[off3 + k] = unscale * __uint_as_float(acc[k]);
+          for (int k = 0; k < OUT; ++k) {
+            if (gwh) gwh[off3 + k] = __float2half_rn(to_h(sc3 * __uint_as_float(acc[k])));
+            else gw[off3 + k] = unscale * __uint_as_float(acc[k]);
+          }
         }
       }
     }

@@ -184,6 +184,7 @@ class FitEngine:
         self.overlap = os.environ.get("RECOMBINER_OVERLAP", "1") != "0"
         # the four per-layer reparameterisation GEMMs as one launch: "1" both directions, "fwd" forward only, "0" off
         self.batch_gemm = os.environ.get("RECOMBINER_BATCH_GEMM", "fwd")
+        self.half_dwt = os.environ.get("RECOMBINER_HALF_DWT", "1") != "0"
         # conv2's activations are only ever read as MMA operands (conv3) and for their signs (LeakyReLU mask):
         # where conv3 has the fp16-operand kernel they are stored as fp16 -- the 10 mantissa bits a TF32 MMA
         # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
@@ -272,7 +273,7 @@ class FitEngine:
         self.map_generation += 1
         dev = self.device
         st = stream()
-        self.A, self.AT, self.AT_h = [], [], []
+        self.A, self.AT, self.AT_h, self.A_h = [], [], [], []
         for a, c in zip(A_list, self.counts):
             a = a.detach().to(device=dev, dtype=torch.float32)
             ld = _round_up(c, 4)
@@ -282,6 +283,8 @@ class FitEngine:
             if self.tc:       # fp16 copy for the forward reparameterisation (K padded to whole 16-byte groups)
                 ah = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); ah[:, :c] = a.t().half()
                 self.AT_h.append(ah)
+                bh = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); bh[:, :c] = a.half()
+                self.A_h.append(bh)
         self.conv_b = [up_state[f"conv{i}.bias"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
         conv_w = [up_state[f"conv{i}.weight"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
         self.w_eff, self.w_eff_t, self.w_eff_k = [None] * 3, [None] * 3, [None] * 3
@@ -424,7 +427,7 @@ class FitEngine:
               "rcb_gemm")
 
     @staticmethod
-    def _batch_args(a_ptrs, lda, Bt, c_ptrs, ldc, M, Ns, Ks, in_half):
+    def _batch_args(a_ptrs, lda, Bt, c_ptrs, ldc, M, Ns, Ks, in_half, out_scale=1.0):
         """Argument tuple of rcb_gemm_tc_batch (host arrays kept alive next to it)."""
         nb = len(a_ptrs)
         A = (C.c_void_p * nb)(*a_ptrs)
@@ -434,7 +437,7 @@ class FitEngine:
         N = (C.c_int * nb)(*Ns)
         K = (C.c_int * nb)(*Ks)
         args = (nb, C.addressof(A), lda, C.addressof(B), C.addressof(ldb), C.addressof(Cp), ldc, M, C.addressof(N),
-                C.addressof(K), in_half)
+                C.addressof(K), in_half, out_scale)
         return args, (A, B, ldb, Cp, N, K, list(Bt))
 
     def _eps_store(self, ws, rows, S):
@@ -576,6 +579,14 @@ class FitEngine:
             amax = float(dy.abs().max())
             coef = 2.0 ** round(-math.log2(amax)) if amax > 0.0 and math.isfinite(amax) else 1.0
         a.coef, a.w0 = coef, self.w0
+        ws["d_wt_is_half"] = False
+        if use_tc and mode == 1 and self.half_hw and self.half_dwt:
+            # the weight gradients are only read by the data-gradient reparameterisation GEMM: written as fp16
+            # (scaled by 2^8, clamped), the GEMM divides the scale out again
+            if "d_wt_h" not in ws:
+                ws["d_wt_h"] = torch.zeros(rows * S, self.ldh, dtype=torch.float16, device=self.device)
+            a.d_wt_h, a.ld_wh, a.d_wt_h_scale = ptr(ws["d_wt_h"]), self.ldh, 256.0
+            ws["d_wt_is_half"] = True
         with self.section("mlp_fwd" if mode == 0 else "mlp_fwd_bwd"):
             if use_tc:
                 check(self.lib.rcb_mlp_tc(C.byref(a), stream()), "rcb_mlp_tc")
@@ -592,6 +603,14 @@ class FitEngine:
 
         def reparam():
             with self.section("reparam_bwd"):
+                if ws.get("d_wt_is_half"):
+                    key = ("rp_bwd_h", self.map_generation)
+                    if key not in ws:
+                        ws[key] = self._batch_args([ws["d_wt_h"].data_ptr() + 2 * o for o in self.offsets], self.ldh, self.A_h,
+                                                   [ws["d_hw"].data_ptr() + 4 * o for o in self.offsets], self.ldw, items,
+                                                   self.counts, [_round_up(c, 8) for c in self.counts], 1, 1.0 / 256.0)
+                    check(self.lib.rcb_gemm_tc_batch(*ws[key][0], stream()), "rcb_gemm_tc_batch")
+                    return
                 if self.tc and self.batch_gemm == "1":
                     key = ("rp_bwd", self.map_generation)
                     if key not in ws:

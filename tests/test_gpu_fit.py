@@ -305,3 +305,24 @@ def test_full_size_kodak_tensor_core_path_against_fp32_path():
     assert out["tf32"][1] == pytest.approx(out["fp32"][1], rel=1e-3)
     for a, b in zip(out["tf32"][2], out["fp32"][2]):
         assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-2
+
+
+def test_fp16_weight_gradients_of_the_fit_step_match_the_fp32_ones():
+    """Fit step on the tensor-core path with the MLP's weight gradients handed to the reparameterisation GEMM as
+    scaled fp16 (default) against the same step with fp32 / TF32 operands: d_hw within 2e-3 relative L2 and 1e-2 of
+    the largest entry elementwise (both are 10-bit-mantissa products; only the rounding points differ)."""
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case("cifar", 6, 3, coded_frac=0.0)
+    x, y = case["x"].cuda(), case["y"].cuda()
+    cfg = dict(lr=2e-4, b1=0.9, b2=0.999, eps=1e-8)
+    out = []
+    for half in (True, False):
+        m = product_test_model(case, "cifar", precision="tf32")
+        m.use_graph = False
+        m.engine.half_dwt = half
+        ws = m.fit_step(x, y, 3, cfg, sample_size=3)
+        assert ws["d_wt_is_half"] == half
+        out.append(ws["d_hw"][:, :m.engine.W].clone())
+    a, b = out
+    assert float((a - b).norm() / b.norm()) < 2e-3
+    assert float((a - b).abs().max()) < 1e-2 * float(b.abs().max())
