@@ -168,7 +168,8 @@ class FitEngine:
     def half_hw(self):
         """fp16 weight samples: tensor-core path, single-level posterior (nothing accumulates into hw), and no
         prior training (its dA_l = hw^T d_wt reads hw in fp32)."""
-        return bool(self.tc and self.half_acts and self.patch_nums is None and all(o % 8 == 0 for o in self.offsets))
+        return bool(self.tc and self.half_acts and self.patch_nums is None and all(o % 8 == 0 for o in self.offsets)
+                    and len(getattr(self, "AT_h", ())) == len(self.counts))      # fp16 copies staged by set_mappings
 
     def __init__(self, dims, data_dim, pixel_sizes, upsample_factors, latent_dim, layer_scales, paddings,
                  w0, device, precision=None, patch_nums=None, force_poly=False):
@@ -190,6 +191,7 @@ class FitEngine:
         # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
         self.half_acts = self.tc_conv and os.environ.get("RECOMBINER_HALF_ACTS", "1") != "0"
         self.f2_half = False
+        self._half_staged = False
         self._side = None
         if not torch.cuda.is_available():
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -280,7 +282,7 @@ class FitEngine:
             ap = torch.zeros(c, ld, device=dev); ap[:, :c] = a
             at = torch.zeros(c, ld, device=dev); at[:, :c] = a.t()
             self.A.append(ap); self.AT.append(at)
-            if self.tc:       # fp16 copy for the forward reparameterisation (K padded to whole 16-byte groups)
+            if self.tc and self.half_acts:   # fp16 copies for the reparameterisation GEMMs (K padded to whole 16-byte groups)
                 ah = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); ah[:, :c] = a.t().half()
                 self.AT_h.append(ah)
                 bh = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); bh[:, :c] = a.half()
@@ -308,7 +310,8 @@ class FitEngine:
         self.f2_half = bool(self.tc_conv and self.tc and self.data_dim == 2 and g3.d == 1 and g3.fy == 2 and g3.fx == 2
                             and g3.ky == 3 and g3.kx == 3 and g3.ic == 64 and g3.oc == 16 and g3.h >= 16
                             and self.geoms[1].ic == 64)
-        if self.f2_half:
+        self._half_staged = bool(self.f2_half and self.half_acts)      # fp16 weight copies exist (half_acts at staging time)
+        if self._half_staged:
             self.w3_kh = torch.empty(self.w_eff_k[2].numel(), dtype=torch.float16, device=dev)
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[2]), ptr(self.w3_kh), self.w3_kh.numel(), st), "rcb_to_half")
             self.w2_kh = torch.empty(self.w_eff_k[1].numel(), dtype=torch.float16, device=dev)
@@ -316,6 +319,7 @@ class FitEngine:
             if self.dense1:
                 self.M1T_h = torch.empty(self.M1T.shape, dtype=torch.float16, device=dev)
                 check(self.lib.rcb_to_half(ptr(self.M1T), ptr(self.M1T_h), self.M1T_h.numel(), st), "rcb_to_half")
+        if self.f2_half:
             self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
             check(self.lib.rcb_fold_poly_bwd_f2(ptr(self.w_eff[2]), C.byref(g3), ptr(self.w3_bk), st), "rcb_fold_poly_bwd_f2")
 
@@ -393,7 +397,7 @@ class FitEngine:
                 ws["hw_h"] = torch.zeros(rows * S, self.ldh, dtype=torch.float16, device=self.device)
             a.hw, a.hw_h = None, ptr(ws["hw_h"])
         a.lpe = ptr(ws["lpe"]) if lv.level == 0 else None
-        if lv.level == 0 and self.half_acts and self.f2_half and self.dense1:
+        if lv.level == 0 and self.half_acts and self.f2_half and self._half_staged and self.dense1:
             # the dense first stage reads the latent grid as an fp16 MMA operand: write it that way
             if "lpe_h" not in ws:
                 ws["lpe_h"] = torch.empty(ws["lpe"].shape, dtype=torch.float16, device=self.device)
@@ -506,7 +510,7 @@ class FitEngine:
                                ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
         join = self._fork(reparam)
         g1, g2, g3 = self.geoms
-        half = ws["a2_is_half"] = bool(self.half_acts and self.f2_half)
+        half = ws["a2_is_half"] = bool(self.half_acts and self.f2_half and self._half_staged)
         if half and "a2h" not in ws:
             ws["a1h"] = torch.empty(ws["a1"].shape, dtype=torch.float16, device=self.device)
             ws["a2h"] = torch.empty(ws["a2"].shape, dtype=torch.float16, device=self.device)
