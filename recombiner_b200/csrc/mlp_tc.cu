@@ -33,15 +33,17 @@ constexpr int MT_GROUP = 128;
 constexpr uint32_t TM_DW = 128, TM_COLS = 256;
 
 struct Sm {
-  static constexpr int XT_KB = 40 * 128;            // one 64-pixel K block (fp16): 32 feature rows, ones row, 7 zero rows
-  static constexpr int XT_BYTES = 2 * XT_KB;
+  // fp16 operands of the weight-gradient MMAs, pixel-major (MN-major for the MMA): one 64-byte row of 32 features per
+  // pixel, 64-byte swizzle, 8-pixel groups 512 B apart
+  static constexpr int XP = 128 * 64;
   // per tile slot
-  static constexpr int XT1 = 0, XT2 = XT_BYTES, XT3 = 2 * XT_BYTES;   // X_l^T [2 K blocks][40][64 px]; XT3 later holds X_0^T
-  static constexpr int DZT = 3 * XT_BYTES;          // dZ_l^T [2 K blocks][32][64 px]
-  static constexpr int DZ3 = DZT + 2 * 4096;        // dy^T   [2 K blocks][16][64 px] (rows >= OUT stay zero)
+  static constexpr int XT1 = 0, XT2 = XP, XT3 = 2 * XP;   // X_1, X_2, X_3 (XT3 later holds X_0)
+  static constexpr int DZT = 3 * XP;                // dZ_l
+  static constexpr int DZ3 = DZT + XP;              // dy^T   [2 K blocks][16][64 px], K-major (rows >= OUT stay zero)
   static constexpr int SLOT = DZ3 + 2 * 2048;
   // per CTA
-  static constexpr int WF = 2 * SLOT;               // 3 forward B tiles  [j][i] (tf32)
+  static constexpr int ONES = 2 * SLOT;             // second MN atom of every A operand: feature 32 = 1 (bias row), 33..63 = 0
+  static constexpr int WF = ONES + XP;              // 3 forward B tiles  [j][i] (tf32)
   static constexpr int WB = WF + 3 * 4096;          // 3 backward B tiles [i][j] (layer 0: the 16 pe inputs)
   static constexpr int W3 = WB + 3 * 4096;          // output B tile [16 (OUT used)][32]
   static constexpr int PLAIN = W3 + 2048;           // floats: [0,96) w0*b_l, [96,100) b3, [104,108) sq partials, [128,256) W3[j][4]
@@ -49,7 +51,6 @@ struct Sm {
   static constexpr int TOTAL = BAR + 64;
 };
 static_assert(Sm::SLOT % 1024 == 0 && Sm::WF % 1024 == 0 && Sm::W3 % 1024 == 0, "swizzled tiles need 1024-B alignment");
-static_assert(Sm::SLOT + Sm::XT3 + Sm::XT_KB + 64 * 128 <= Sm::BAR, "M=64 reads past the last A tile must stay in the allocation");
 
 // byte offset of element (row, col) in a tile of 128-byte rows with the 128-byte swizzle; 4- and 2-byte elements
 __device__ __forceinline__ uint32_t swz4(int row, int col) {
@@ -110,6 +111,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ uint32_t idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 }
+// MN-major operand (pixel rows of 64 B, 64-byte swizzle): leading-byte offset = distance to the next 32-feature atom,
+// stride-byte offset = 512 (eight pixel rows); one K = 16 step is 1024 B further
+__device__ __forceinline__ uint64_t smem_desc_pm(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;      // SWIZZLE_64B
+  return d;
+}
+constexpr uint32_t IDESC_A_MN = 1u << 15, IDESC_B_MN = 1u << 16;
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -258,10 +271,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     if (t < 4) plain[96 + t] = b3v;
     if (t < HID * 4) plain[128 + t] = w3p;
     if (MODE != 0) {
-      // rows 32..39 of every K block of every A tile: ones row + zeros (32-bit words = fp16 pairs)
-      for (int e = t; e < 2 * 3 * 2 * 8 * 32; e += MT_THREADS) {
-        const int s = e / 1536, b = (e / 512) % 3, kb = (e / 256) % 2, rr = 32 + (e / 32) % 8, c = e % 32;
-        sts32(sbase + s * Sm::SLOT + b * Sm::XT_BYTES + kb * Sm::XT_KB + rr * 128 + c * 4, rr == 32 ? 0x3c003c00u : 0u);
+      // the shared second atom of the A operands: per pixel row, feature 32 = 1.0 (chunk 0 of the swizzled row), rest 0
+      for (int e = t; e < 128 * 16; e += MT_THREADS) {
+        const int k = e >> 4, w = e & 15;
+        sts32(sbase + Sm::ONES + k * 64 + w * 4, w == (((k >> 1) & 3) << 2) ? 0x00003c00u : 0u);
       }
       for (int e = t; e < 2 * 1024; e += MT_THREADS) sts32(sbase + (e / 1024) * Sm::SLOT + Sm::DZ3 + (e % 1024) * 4, 0u);
     }
@@ -307,13 +320,23 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     for (int k = 0; k < 4; ++k)
       umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
   };
-  auto wgrad = [&](uint32_t d_col, int xt_off, int dz_off, int dz_kb, uint32_t idesc) {
+  // dW = X^T dZ over the tile's 128 pixels: both operands pixel-major (MN-major), eight K = 16 steps of 1024 B
+  auto wgrad = [&](uint32_t d_col, int x_off, int dz_off, uint32_t idesc) {
+    const uint32_t xa = sbase + x_off;
+    const uint64_t da = smem_desc_pm(xa, sbase + Sm::ONES - xa), db = smem_desc_pm(sbase + dz_off, 16);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16(tmem_base + d_col, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, 1u);
+  };
+  // dW3 = X3^T dy: A pixel-major, B = dy^T K-major [2 K blocks][16][64 px]
+  auto wgrad_dy = [&](uint32_t d_col, int x_off, int dy_off, uint32_t idesc) {
+    const uint32_t xa = sbase + x_off;
+    const uint64_t da = smem_desc_pm(xa, sbase + Sm::ONES - xa);
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb) {
-      const uint64_t da = smem_desc_sw128(sbase + xt_off + kb * Sm::XT_KB);
-      const uint64_t db = smem_desc_sw128(sbase + dz_off + kb * dz_kb);
+      const uint64_t db = smem_desc_sw128(sbase + dy_off + kb * 2048);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem_base + d_col, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem_base + d_col, da + (uint64_t)((kb * 4 + k) * 64), db + (uint64_t)(k * 2), idesc, 1u);
     }
   };
   // stages of one tile: 0-2 sine layers, 3 output layer, 4-6 backward
@@ -324,7 +347,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       tc_fence_after();
     }
     if (mine && elect_one()) {
-      const uint32_t t32 = idesc_tf32(32), t16 = idesc_tf32(16), h32 = idesc_f16(32), h16 = idesc_f16(16);
+      const uint32_t t32 = idesc_tf32(32), t16 = idesc_tf32(16);
+      const uint32_t h32 = idesc_f16(32) | IDESC_A_MN | IDESC_B_MN, h16 = idesc_f16(16) | IDESC_A_MN;
       switch (stage) {
         case 0: chain(R1, R0, Sm::WF, t32); break;                              // Z0 = X0 W0
         case 1: chain(R0, R1, Sm::WF + 4096, t32); break;                       // Z1 = X1 W1
@@ -336,20 +360,20 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         case 4:
           chain(R0, R1, Sm::WB + 8192, t32);                                    // dX2 = dZ2 W2^T
           while (wg_turn[0] != tile) {}
-          wgrad(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, 2048, h16);             // dW3 = X3^T dy
-          wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, 4096, h32);             // dW2 = X2^T dZ2
+          wgrad_dy(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, h16);                // dW3 = X3^T dy
+          wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, h32);                   // dW2 = X2^T dZ2
           wg_turn[0] = tile + 1;
           break;
         case 5:
           chain(R1, R0, Sm::WB + 4096, t32);                                    // dX1 = dZ1 W1^T
           while (wg_turn[1] != tile) {}
-          wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, 4096, h32);             // dW1 = X1^T dZ1
+          wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, h32);                   // dW1 = X1^T dZ1
           wg_turn[1] = tile + 1;
           break;
         default:
           chain(R0, R1, Sm::WB, t16);                                           // d pe = dZ0 W0[pe rows]^T
           while (wg_turn[2] != tile) {}
-          wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, 4096, h32);                  // dW0 = X0^T dZ0
+          wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, h32);                        // dW0 = X0^T dZ0
           wg_turn[2] = tile + 1;
           break;
       }
@@ -362,14 +386,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // feature-major fp16 element of this thread's pixel: K block r / 64, column r % 64
   const uint32_t t_kb = (uint32_t)(q >> 1);
   const int t_col = (q & 1) * 32 + lane;
-  // rows f0 .. f0+15 of a feature-major tile <- v[0..15] (fp16, round to nearest)
-  auto store_t16 = [&](uint32_t tile, int kb_bytes, int f0, const float* v) {
-    const uint32_t base = tile + t_kb * (uint32_t)kb_bytes;
+  // features f0 .. f0+15 of this thread's pixel row of a pixel-major buffer <- v[0..15] (fp16, round to nearest):
+  // two 16-byte chunks of the 64-byte row, chunk index XORed with bits 1-2 of the row (64-byte swizzle)
+  const uint32_t pm_row = (uint32_t)r * 64u, pm_x = ((uint32_t)r >> 1) & 3u;
+  auto store_t16 = [&](uint32_t buf, int f0, const float* v) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      const uint32_t h2 = pack_h2(v[j], v[j + 1]);
-      asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + swz2(f0 + j, t_col)), "h"((unsigned short)(h2 & 0xffffu)) : "memory");
-      asm volatile("st.shared.b16 [%0], %1;" ::"r"(base + swz2(f0 + j + 1, t_col)), "h"((unsigned short)(h2 >> 16)) : "memory");
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t addr = buf + pm_row + (((uint32_t)((f0 >> 3) + c) ^ pm_x) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_h2(v[8 * c], v[8 * c + 1])),
+                   "r"(pack_h2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_h2(v[8 * c + 4], v[8 * c + 5])),
+                   "r"(pack_h2(v[8 * c + 6], v[8 * c + 7])) : "memory");
     }
   };
   auto publish = [&](bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
@@ -420,7 +446,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           cs[l][(16 * h + j) >> 1] = pack_h2(__cosf(z0), __cosf(z1));
           acc[16 * h + j] = rnd_tf32(x[j]); acc[16 * h + j + 1] = rnd_tf32(x[j + 1]);
         }
-        if (MODE != 0) store_t16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), Sm::XT_KB, 16 * h, x);
+        if (MODE != 0) store_t16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), 16 * h, x);
       }
       tmem_st32(reg, acc);
       publish(MODE != 0);
@@ -472,7 +498,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           dz[j] = va * c2.x; dz[j + 1] = vb * c2.y;
           dzr[16 * h + j] = rnd_tf32(dz[j]); dzr[16 * h + j + 1] = rnd_tf32(dz[j + 1]);
         }
-        store_t16(sbase + so + Sm::DZT, 4096, 16 * h, dz);
+        store_t16(sbase + so + Sm::DZT, 16 * h, dz);
       }
       tmem_st32(tm + R1, dzr);                                           // A operand of dX2
     }
@@ -496,12 +522,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           dz[j] = __uint_as_float(acc[16 * h + j]) * c2.x; dz[j + 1] = __uint_as_float(acc[16 * h + j + 1]) * c2.y;
           acc[16 * h + j] = rnd_tf32(dz[j]); acc[16 * h + j + 1] = rnd_tf32(dz[j + 1]);
         }
-        store_t16(sbase + so + Sm::DZT, 4096, 16 * h, dz);
+        store_t16(sbase + so + Sm::DZT, 16 * h, dz);
         if (l == 0) {
           float xf[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) xf[j] = __uint_as_float(xin[16 * h + j]);
-          store_t16(sbase + so + Sm::XT3, Sm::XT_KB, 16 * h, xf);
+          store_t16(sbase + so + Sm::XT3, 16 * h, xf);
         }
       }
       tmem_st32(reg, acc);
