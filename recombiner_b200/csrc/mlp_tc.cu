@@ -43,10 +43,11 @@ struct Sm {
   static constexpr int SLOT = DZ3 + 2 * 2048;
   // per CTA
   static constexpr int ONES = 2 * SLOT;             // second MN atom of every A operand: feature 32 = 1 (bias row), 33..63 = 0
-  static constexpr int WF = ONES + XP;              // 3 forward B tiles  [j][i] (tf32)
-  static constexpr int WB = WF + 3 * 4096;          // 3 backward B tiles [i][j] (layer 0: the 16 pe inputs)
-  static constexpr int W3 = WB + 3 * 4096;          // output B tile [16 (OUT used)][32]
-  static constexpr int PLAIN = W3 + 2048;           // floats: [0,96) w0*b_l, [96,100) b3, [104,108) sq partials, [128,256) W3[j][4]
+  static constexpr int WT = 32 * 64;                // one fp16 weight tile: 32 rows of 32 K elements (64 B), 64-byte swizzle
+  static constexpr int WF = ONES + XP;              // 3 forward B tiles  [j][i]
+  static constexpr int WB = WF + 3 * WT;            // 3 backward B tiles [i][j] (layer 0: the 16 pe inputs)
+  static constexpr int W3 = WB + 3 * WT;            // output B tile [16 (OUT used)][32]
+  static constexpr int PLAIN = W3 + WT;           // floats: [0,96) w0*b_l, [96,100) b3, [104,108) sq partials, [128,256) W3[j][4]
   static constexpr int BAR = PLAIN + 1024;
   static constexpr int TOTAL = BAR + 64;
 };
@@ -58,6 +59,10 @@ __device__ __forceinline__ uint32_t swz4(int row, int col) {
 }
 __device__ __forceinline__ uint32_t swz2(int row, int col) {
   return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
+}
+// byte offset of fp16 element (row, col < 32) in a tile of 64-byte rows with the 64-byte swizzle
+__device__ __forceinline__ uint32_t swz64(int row, int col) {
+  return (uint32_t)(row * 64 + ((((col >> 3) ^ ((row >> 1) & 3)) << 4) | ((col & 7) << 1)));
 }
 __device__ __forceinline__ uint32_t rnd_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -96,6 +101,19 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem: lane = row, two fp16 K elements per 32-bit column] * B[smem descriptor], fp16 operands
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = f32, A = B = f16, both K-major, M = 128 (the chain products)
+__device__ __forceinline__ uint32_t idesc_f16_m128(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem], fp16 operands, fp32 accumulation
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -257,15 +275,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     for (int i = 0; i < 12; ++i) {
       const int e = t + i * MT_THREADS;
       const int l = e / (HID * HID), r = (e / HID) % HID, c = e % HID;
-      const uint32_t w = rnd_tf32(w0 * wv[i]);
-      sts32(sbase + Sm::WF + l * 4096 + swz4(c, r), w);                         // forward B: rows j, K = i
-      if (l > 0) sts32(sbase + Sm::WB + l * 4096 + swz4(r, c), w);              // backward B: rows i, K = j
-      else if (r >= F) sts32(sbase + Sm::WB + swz4(r - F, c), w);               // layer 0: pe inputs only
+      const __half w = __float2half_rn(w0 * wv[i]);
+      sts16(sbase + Sm::WF + l * Sm::WT + swz64(c, r), w);                      // forward B: rows j, K = i
+      if (l > 0) sts16(sbase + Sm::WB + l * Sm::WT + swz64(r, c), w);           // backward B: rows i, K = j
+      else if (r >= F) sts16(sbase + Sm::WB + swz64(r - F, c), w);              // layer 0: pe inputs only
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int e = t + i * MT_THREADS, k = e / HID, j = e % HID;
-      sts32(sbase + Sm::W3 + swz4(k, j), k < OUT ? rnd_tf32(w3v[i]) : 0u);
+      sts16(sbase + Sm::W3 + swz64(k, j), __float2half_rn(k < OUT ? w3v[i] : 0.f));
     }
     if (t < 3 * HID) plain[t] = w0 * bv;
     if (t < 4) plain[96 + t] = b3v;
@@ -314,11 +332,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // Consecutive stages of a tile are ordered by completion (commit -> wait -> publish); the groups
   // only share the weight-gradient accumulators, where the in-order pipe makes every D += A B atomic.
   uint32_t ph_ready = 0u;
+  // chain product over K = 32: two K = 16 steps; the A operand sits in the first 16 columns of its region as packed fp16
   auto chain = [&](uint32_t d_col, uint32_t a_col, int b_off, uint32_t idesc) {
-    const uint64_t db = smem_desc_sw128(sbase + b_off);
+    const uint64_t db = smem_desc_sw64(sbase + b_off);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+    for (int k = 0; k < 2; ++k)
+      umma_f16_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
   };
   // dW = X^T dZ over the tile's 128 pixels: both operands pixel-major (MN-major), eight K = 16 steps of 1024 B
   auto wgrad = [&](uint32_t d_col, int x_off, int dz_off, uint32_t idesc) {
@@ -347,25 +366,25 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       tc_fence_after();
     }
     if (mine && elect_one()) {
-      const uint32_t t32 = idesc_tf32(32), t16 = idesc_tf32(16);
+      const uint32_t t32 = idesc_f16_m128(32), t16 = idesc_f16_m128(16);
       const uint32_t h32 = idesc_f16(32) | IDESC_A_MN | IDESC_B_MN, h16 = idesc_f16(16) | IDESC_A_MN;
       switch (stage) {
         case 0: chain(R1, R0, Sm::WF, t32); break;                              // Z0 = X0 W0
-        case 1: chain(R0, R1, Sm::WF + 4096, t32); break;                       // Z1 = X1 W1
-        case 2: chain(R1, R0, Sm::WF + 8192, t32); break;                       // Z2 = X2 W2
+        case 1: chain(R0, R1, Sm::WF + Sm::WT, t32); break;                     // Z1 = X1 W1
+        case 2: chain(R1, R0, Sm::WF + 2 * Sm::WT, t32); break;                       // Z2 = X2 W2
         case 3: chain(R0, R1, Sm::W3, t16); break;                              // y  = X3 W3
         // The two groups add into the same weight-gradient accumulators.  The tensor pipe runs MMAs in the order
         // they are issued, so the tiles take turns (tile t after tile t - 1, per stage): the fp32 summation order,
         // and with it every bit of the gradients, does not depend on how the groups happen to interleave.
         case 4:
-          chain(R0, R1, Sm::WB + 8192, t32);                                    // dX2 = dZ2 W2^T
+          chain(R0, R1, Sm::WB + 2 * Sm::WT, t32);                                    // dX2 = dZ2 W2^T
           while (wg_turn[0] != tile) {}
           wgrad_dy(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, h16);                // dW3 = X3^T dy
           wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, h32);                   // dW2 = X2^T dZ2
           wg_turn[0] = tile + 1;
           break;
         case 5:
-          chain(R1, R0, Sm::WB + 4096, t32);                                    // dX1 = dZ1 W1^T
+          chain(R1, R0, Sm::WB + Sm::WT, t32);                                    // dX1 = dZ1 W1^T
           while (wg_turn[1] != tile) {}
           wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, h32);                   // dW1 = X1^T dZ1
           wg_turn[1] = tile + 1;
@@ -389,13 +408,13 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // features f0 .. f0+15 of this thread's pixel row of a pixel-major buffer <- v[0..15] (fp16, round to nearest):
   // two 16-byte chunks of the 64-byte row, chunk index XORed with bits 1-2 of the row (64-byte swizzle)
   const uint32_t pm_row = (uint32_t)r * 64u, pm_x = ((uint32_t)r >> 1) & 3u;
-  auto store_t16 = [&](uint32_t buf, int f0, const float* v) {
+  // hp[0..7] = the 16 features f0 .. f0+15 as packed fp16 pairs (the same words that go to TMEM as the chain operand)
+  auto store_p16 = [&](uint32_t buf, int f0, const uint32_t* hp) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t addr = buf + pm_row + (((uint32_t)((f0 >> 3) + c) ^ pm_x) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_h2(v[8 * c], v[8 * c + 1])),
-                   "r"(pack_h2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_h2(v[8 * c + 4], v[8 * c + 5])),
-                   "r"(pack_h2(v[8 * c + 6], v[8 * c + 7])) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[4 * c]), "r"(hp[4 * c + 1]),
+                   "r"(hp[4 * c + 2]), "r"(hp[4 * c + 3]) : "memory");
     }
   };
   auto publish = [&](bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
@@ -422,9 +441,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     const bool valid = gp < pix;
     uint32_t cs[3][16];                           // cos(.) of the three sine layers, packed half2
     // ---- X0 -> TMEM (R0)
+    {
+      uint32_t x0p[16];                                                  // the 32 inputs as packed fp16 pairs
 #pragma unroll
-    for (int i = 0; i < 32; ++i) xin[i] += 0x1000u;                      // TF32 round-to-nearest of the inputs
-    tmem_st32(tm + R0, xin);
+      for (int i = 0; i < 16; ++i) x0p[i] = pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
+      tmem_st16(tm + R0, x0p);
+    }
     publish(false);
     issue(0);
     // ---- three sine layers: X_{l+1} = sin(acc + b') back into the accumulator's columns, fp16 copy of X_{l+1}^T
@@ -435,20 +457,19 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       uint32_t acc[32];
       tmem_ld32_issue(reg, acc);
       tmem_ld_wait();
+      uint32_t xp[16];                                                   // X_{l+1} as packed fp16 pairs
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float x[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           const float z0 = __uint_as_float(acc[16 * h + j]) + plain[l * 32 + 16 * h + j];
           const float z1 = __uint_as_float(acc[16 * h + j + 1]) + plain[l * 32 + 16 * h + j + 1];
-          x[j] = __sinf(z0); x[j + 1] = __sinf(z1);
+          xp[(16 * h + j) >> 1] = pack_h2(__sinf(z0), __sinf(z1));
           cs[l][(16 * h + j) >> 1] = pack_h2(__cosf(z0), __cosf(z1));
-          acc[16 * h + j] = rnd_tf32(x[j]); acc[16 * h + j + 1] = rnd_tf32(x[j + 1]);
         }
-        if (MODE != 0) store_t16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), 16 * h, x);
+        if (MODE != 0) store_p16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), 16 * h, xp + 8 * h);
       }
-      tmem_st32(reg, acc);
+      tmem_st16(reg, xp);
       publish(MODE != 0);
       issue(l + 1);
     }
@@ -483,10 +504,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
     for (int k = 0; k < OUT; ++k) sts16(sbase + so + Sm::DZ3 + t_kb * 2048 + swz2(k, t_col), __float2half_rn(dy[k]));
     {
-      uint32_t dzr[32];
+      uint32_t dzp[16];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float dz[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           const float2 c2 = unpack_h2(cs[2][(16 * h + j) >> 1]);
@@ -495,12 +515,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           float va = dy[0] * wa.x, vb = dy[0] * wb.x;
           if (OUT > 1) { va = fmaf(dy[1], wa.y, va); vb = fmaf(dy[1], wb.y, vb); }
           if (OUT > 2) { va = fmaf(dy[2], wa.z, va); vb = fmaf(dy[2], wb.z, vb); }
-          dz[j] = va * c2.x; dz[j + 1] = vb * c2.y;
-          dzr[16 * h + j] = rnd_tf32(dz[j]); dzr[16 * h + j + 1] = rnd_tf32(dz[j + 1]);
+          dzp[(16 * h + j) >> 1] = pack_h2(va * c2.x, vb * c2.y);
         }
-        store_t16(sbase + so + Sm::DZT, 16 * h, dz);
+        store_p16(sbase + so + Sm::DZT, 16 * h, dzp + 8 * h);
       }
-      tmem_st32(tm + R1, dzr);                                           // A operand of dX2
+      tmem_st16(tm + R1, dzp);                                           // A operand of dX2
     }
     publish(true);
     issue(4, tile);
@@ -513,24 +532,23 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       uint32_t acc[32];
       tmem_ld32_issue(reg, acc);
       tmem_ld_wait();
+      uint32_t dzp[16];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float dz[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           const float2 c2 = unpack_h2(cs[l][(16 * h + j) >> 1]);
-          dz[j] = __uint_as_float(acc[16 * h + j]) * c2.x; dz[j + 1] = __uint_as_float(acc[16 * h + j + 1]) * c2.y;
-          acc[16 * h + j] = rnd_tf32(dz[j]); acc[16 * h + j + 1] = rnd_tf32(dz[j + 1]);
+          dzp[(16 * h + j) >> 1] = pack_h2(__uint_as_float(acc[16 * h + j]) * c2.x, __uint_as_float(acc[16 * h + j + 1]) * c2.y);
         }
-        store_t16(sbase + so + Sm::DZT, 16 * h, dz);
+        store_p16(sbase + so + Sm::DZT, 16 * h, dzp + 8 * h);
         if (l == 0) {
-          float xf[16];
+          uint32_t xf[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) xf[j] = __uint_as_float(xin[16 * h + j]);
-          store_t16(sbase + so + Sm::XT3, 16 * h, xf);
+          for (int j = 0; j < 8; ++j) xf[j] = pack_h2(__uint_as_float(xin[16 * h + 2 * j]), __uint_as_float(xin[16 * h + 2 * j + 1]));
+          store_p16(sbase + so + Sm::XT3, 16 * h, xf);
         }
       }
-      tmem_st32(reg, acc);
+      tmem_st16(reg, dzp);
       publish(true);
       issue(l == 1 ? 5 : 6, tile);
     }
