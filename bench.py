@@ -448,8 +448,9 @@ def run_b200(args):
             "metric": "datapoints compressed/sec (CIFAR-10 32x32)", "value": value, "unit": "datapoints/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": t_fit, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": (("tf32 + fp16 upsampler activations / weight samples" if m.engine.half_hw else "tf32")
-                      + " (tcgen05, fp32 accumulate) fit / f64 REC" if m.engine.tc else "f32 fit (SIMT FFMA) / f64 REC"),
+            "dtype": (("fp16 / tf32 operands" if m.engine.half_hw else "tf32 + fp16 operands")
+                      + " (tcgen05, fp32 accumulate in TMEM; fp32 state and gradients) fit / f64 REC"
+                      if m.engine.tc else "f32 fit (SIMT FFMA) / f64 REC"),
             "data": "synthetic",
             "config": {"workload": "cifar-shape 32x32, %d rows/GPU, S=5, G=%d blocks x 16 bit (0.52 bpp), "
                                    "random-init prior" % (ROWS_PER_GPU, G),
@@ -464,9 +465,9 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tf"], "traffic": TRAFFIC.get(dom), "peak_source": pk["src"] + " bf16 sustained",
-                         "frac_of_tf32_peak": achieved / (pk["tf"] / 2),
-                         "note": "MLP operands are TF32 (half the bf16 rate): frac_of_tf32_peak uses peak/2; executed "
-                                 "(polyphase) FLOPs; per-launch ms: "
+                         "note": "MLP operands are fp16 (kind::f16, fp32 accumulation in TMEM): the kernel is bound by its "
+                                 "CUDA-core epilogues (96 sin + 96 cos per pixel and tile, issue slots), not by the tensor "
+                                 "pipe; executed FLOPs; per-launch ms: "
                                  + ", ".join(f"{k}={v:.3f}" for k, v in sorted(timed.items(), key=lambda kv: -kv[1]))},
             # the upsampler kernels are HBM-bound: algorithmic bytes per launch (tensors read + written once, in the
             # precision they are stored in) over the event-timed launch duration, against the measured copy bandwidth
