@@ -60,7 +60,8 @@ def conv_bytes(eng, items: int):
     n2 = g3.h * g3.w * g3.ic
     n3 = g3.h * g3.fy * g3.w * g3.fx * g3.oc
     h = 2 if (eng.half_acts and eng.f2_half) else 4          # bytes per stored activation element
-    per_item = {"conv2_fwd": n1 * h + n2 * h, "conv3_fwd": n2 * h + n3 * 4,
+    hp = 2 if (h == 2 and eng.half_pe and eng.tc_mlp and eng.n_f == 16) else 4      # positional encodings
+    per_item = {"conv2_fwd": n1 * h + n2 * h, "conv3_fwd": n2 * h + n3 * hp,
                 "conv3_bwd": n3 * 4 + n2 * h + n2 * 4, "conv2_bwd": n2 * 4 + n1 * h + n1 * 4,
                 "conv1_bwd": n1 * 4 + n0 * 4}
     return {k: float(v) * items for k, v in per_item.items()}

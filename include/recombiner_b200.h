@@ -229,6 +229,7 @@ typedef struct {
   int ld_wh;            /* row stride of d_wt_h in fp16 elements */
   void* d_wt_h;         /* optional (rcb_mlp_tc, mode 1): the weight gradients are written here as fp16 (clamped to the
                            fp16 range) INSTEAD of d_wt, for an fp16-operand data-gradient GEMM (rcb_gemm_tc_batch) */
+  int pe_half;          /* rcb_mlp_tc only: pe holds fp16 values (written by rcb_upconv_fwd_tc_hh) */
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
 /* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA (one 128-thread group

@@ -34,7 +34,7 @@ class MlpArgs(C.Structure):
     _fields_ = [(n, P) for n in ("wt", "xt", "pe", "y", "dy", "y_pred", "d_pe", "d_wt", "sqerr", "pe_base")] + \
                [("x_row_stride", I64), ("pitch_z", I64), ("pitch_y", I64)] + \
                [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode", "ph", "pw")] + \
-               [("coef", F32), ("w0", F32), ("d_wt_h_scale", F32), ("ld_wh", I32), ("d_wt_h", P)]
+               [("coef", F32), ("w0", F32), ("d_wt_h_scale", F32), ("ld_wh", I32), ("d_wt_h", P), ("pe_half", I32)]
 
 
 class UpdateArgs(C.Structure):

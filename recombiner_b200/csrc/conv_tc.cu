@@ -473,7 +473,7 @@ constexpr int F2_GROUPS = 10, F2_STAGES = 4;
 struct ConvF2Args {
   PolyGeom g;
   int items, tiles_x, tiles_y, n_tiles;
-  int kblocks, act;
+  int kblocks, act, out_half;
   int w_bytes_kb;                       // bytes of resident weights per k-block: 16 blocks of oc rows x 128 B
   int a_off, epi_off, bar_off;          // shared-memory layout
   int grp_shift[F2_GROUPS];             // halo row shift of the group's A operand
@@ -643,6 +643,20 @@ upconv_fwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
         }
+        if (a.out_half) {                                  // fp16 output: 64-byte rows, no swizzle
+          uint8_t* row = stage + ry * 4096 + lane * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float f = __uint_as_float(v[c >> 1][(c & 1) * 8 + e]) + bias[(c & 1) * 8 + e];
+              o[e] = f > 0.f ? f : slope * f;
+            }
+            const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
+            *reinterpret_cast<uint4*>(row + c * 16) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+          }
+        } else {
         uint8_t* row = stage + ry * 4096 + lane * 128;
 #pragma unroll
         for (int rx = 0; rx < 2; ++rx)
@@ -657,6 +671,7 @@ upconv_fwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int chunk = (rx * 4 + (j >> 2)) ^ (lane & 7);
             *reinterpret_cast<float4*>(row + chunk * 16) = make_float4(o[0], o[1], o[2], o[3]);
           }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -1338,13 +1353,13 @@ static bool f2_eligible(const PolyGeom& g, bool half) {
          g.oc == 16 && g.ic <= 64 && g.ic % (half ? 64 : 32) == 0;
 }
 static int launch_f2(const void* src, const void* w_eff_k, const float* bias, float* out, const PolyGeom& g, int items,
-                     int act, rcb_stream_t stream, bool half) {
+                     int act, rcb_stream_t stream, bool half, bool out_half = false) {
   ConvF2Args f;
   f.g = g; f.items = items;
   f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
   f.n_tiles = f.tiles_x * f.tiles_y * items;
   const int KC = half ? 64 : 32, es = half ? 2 : 4;
-  f.kblocks = g.ic / KC; f.act = act; f.bias = bias; f.out = out;
+  f.kblocks = g.ic / KC; f.act = act; f.out_half = out_half ? 1 : 0; f.bias = bias; f.out = out;
   f.w_bytes_kb = 16 * g.oc * 128;
   // accumulator order (ry, rx) = (0,0) (0,1) (1,1) (1,0); a phase's tap for the shift (dy, dx) is
   // (dy - base_y(ry), dx - base_x(rx)) with base(0) = -1, base(1) = 0
@@ -1381,13 +1396,15 @@ static int launch_f2(const void* src, const void* w_eff_k, const float* bias, fl
   CUtensorMap tmO;                            // out as (item, y, line parity, x, 2 * oc): one 128-byte row per source pixel
   {
     EncodeTiledFn enc = tc_get_encode();
-    const cuuint64_t W2 = 2 * (cuuint64_t)g.oc, line = (cuuint64_t)g.w * W2 * 4;
+    const cuuint64_t oes = out_half ? 2 : 4;
+    const cuuint64_t W2 = 2 * (cuuint64_t)g.oc, line = (cuuint64_t)g.w * W2 * oes;
     cuuint64_t dims[5] = {W2, (cuuint64_t)g.w, 2, (cuuint64_t)g.h, (cuuint64_t)items};
-    cuuint64_t strides[4] = {W2 * 4, line, 2 * line, (cuuint64_t)g.h * 2 * line};
+    cuuint64_t strides[4] = {W2 * oes, line, 2 * line, (cuuint64_t)g.h * 2 * line};
     cuuint32_t obox[5] = {(cuuint32_t)W2, 8, 1, 4, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims, strides, obox, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+    CUresult r = enc(&tmO, out_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims,
+                     strides, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     out_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed with CUresult %d", (int)r); return -1; }
   }
@@ -1549,6 +1566,7 @@ static int upconv_fwd_tc_impl(const float* src, const float* w_eff_k, const floa
   if (items <= 0) return 0;
   if (in_half && f2_eligible(g, true) && !out_half) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, true);
   if (in_half && out_half && f2w_eligible(g) && !getenv("RCB_NO_F2W")) return launch_f2w(src, w_eff_k, bias, out, g, items, act, stream);
+  if (in_half && out_half && f2_eligible(g, true)) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, true, true);
   if (f2_eligible(g, false) && !out_half && !getenv("RCB_NO_F2")) return launch_f2(src, w_eff_k, bias, out, g, items, act, stream, false);
   if (!in_half && g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.h >= 16) {
     // 2-D grid with full 8 x 16 tiles: halo-tile kernel

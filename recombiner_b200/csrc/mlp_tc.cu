@@ -229,7 +229,19 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     const bool ok = gp < pix;
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
-    const uint4* p = reinterpret_cast<const uint4*>(a.pe + (pe_origin + (ok ? pe_off(gp) : 0)) * NPE);
+    const int64_t pidx = (pe_origin + (ok ? pe_off(gp) : 0)) * NPE;
+    if (a.pe_half) {      // fp16 positional encodings: v[16..23] are already the packed pairs the chain operand needs
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.pe) + pidx);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
+        v[16 + c * 4] = t4.x; v[17 + c * 4] = t4.y; v[18 + c * 4] = t4.z; v[19 + c * 4] = t4.w;
+      }
+#pragma unroll
+      for (int c = 24; c < 32; ++c) v[c] = 0u;
+      return;
+    }
+    const uint4* p = reinterpret_cast<const uint4*>(a.pe + pidx);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
@@ -444,7 +456,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     {
       uint32_t x0p[16];                                                  // the 32 inputs as packed fp16 pairs
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x0p[i] = pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
+      for (int i = 0; i < 16; ++i)
+        x0p[i] = (a.pe_half && i >= 8) ? xin[8 + i] : pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
       tmem_st16(tm + R0, x0p);
     }
     publish(false);
@@ -544,7 +557,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         if (l == 0) {
           uint32_t xf[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) xf[j] = pack_h2(__uint_as_float(xin[16 * h + 2 * j]), __uint_as_float(xin[16 * h + 2 * j + 1]));
+          for (int j = 0; j < 8; ++j)
+            xf[j] = (a.pe_half && h == 1) ? xin[16 + j] : pack_h2(__uint_as_float(xin[16 * h + 2 * j]), __uint_as_float(xin[16 * h + 2 * j + 1]));
           store_p16(sbase + so + Sm::XT3, 16 * h, xf);
         }
       }

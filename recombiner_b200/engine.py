@@ -186,6 +186,7 @@ class FitEngine:
         # the four per-layer reparameterisation GEMMs as one launch: "1" both directions, "fwd" forward only, "0" off
         self.batch_gemm = os.environ.get("RECOMBINER_BATCH_GEMM", "fwd")
         self.half_dwt = os.environ.get("RECOMBINER_HALF_DWT", "1") != "0"
+        self.half_pe = os.environ.get("RECOMBINER_HALF_PE", "1") != "0"
         # conv2's activations are only ever read as MMA operands (conv3) and for their signs (LeakyReLU mask):
         # where conv3 has the fp16-operand kernel they are stored as fp16 -- the 10 mantissa bits a TF32 MMA
         # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
@@ -535,8 +536,16 @@ class FitEngine:
                                                     C.byref(g2), citems, 1, stream()), "rcb_upconv_fwd_tc_hh[2]")
             else:
                 self._upconv_fwd(1, ws["a1"], ws["a2"], citems, 1)
+        # the MLP rounds the positional encodings to fp16 for its first MMA anyway: stored that way when both ends
+        # are the fp16 kernels
+        half_pe = ws["pe_is_half"] = bool(half and self.half_pe and self.tc_mlp and self.n_f == 16)
+        if half_pe and "pe_h" not in ws:
+            ws["pe_h"] = torch.empty(ws["pe"].shape, dtype=torch.float16, device=self.device)
         with self.section("conv3_fwd"):
-            if half:
+            if half_pe:
+                check(self.lib.rcb_upconv_fwd_tc_hh(ptr(ws["a2h"]), ptr(self.w3_kh), ptr(self.conv_b[2]), ptr(ws["pe_h"]),
+                                                    C.byref(g3), citems, 0, stream()), "rcb_upconv_fwd_tc_hh[3]")
+            elif half:
                 check(self.lib.rcb_upconv_fwd_tc_h(ptr(ws["a2h"]), ptr(self.w3_kh), ptr(self.conv_b[2]), ptr(ws["pe"]),
                                                    C.byref(g3), citems, 0, stream()), "rcb_upconv_fwd_tc_h[3]")
             else:
@@ -570,6 +579,8 @@ class FitEngine:
         xt, stride = self.prepare_x(x)
         a = MlpArgs()
         a.wt, a.xt, a.pe = ptr(ws["wt"]), ptr(xt), ptr(ws["pe"])
+        if ws.get("pe_is_half"):
+            a.pe, a.pe_half = ptr(ws["pe_h"]), 1
         a.y, a.dy, a.y_pred = ptr(y), ptr(dy), ptr(ws["y_pred"])
         a.d_pe, a.d_wt, a.sqerr = ptr(ws["d_pe"]), ptr(ws["d_wt"]), ptr(ws["sqerr"])
         a.x_row_stride = stride
