@@ -174,7 +174,9 @@ int rcb_upconv_bwd_tc(const float* d_out, const float* w_eff, const float* src_a
  * MMAs read of an fp32 operand, at half the bytes.  fp32 accumulation, bias, activation and output. */
 int rcb_upconv_fwd_tc_h(const void* src_h, const void* w_eff_k_h, const float* bias, float* out,
                         const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
-/* fp16 in and fp16 out (any stage with ic % 64 == 0; the general kernel with kind::f16 MMAs) */
+/* fp16 in and fp16 out (any stage with ic % 64 == 0): the persistent resident-weight kernels for the x2 / 3-tap stages
+ * with 64 -> 64 channels (source grid 8 x 8, or >= 16 lines with h % 4 == 0) and 64 -> 16 channels (>= 16 lines), the
+ * general kernel with kind::f16 MMAs otherwise */
 int rcb_upconv_fwd_tc_hh(const void* src_h, const void* w_eff_k_h, const float* bias, void* out_h,
                          const rcb_upconv_geom* g, int items, int act, rcb_stream_t stream);
 /* rcb_upconv_fwd_tc writing its activations as fp16 (for a following rcb_upconv_fwd_tc_h stage), and
