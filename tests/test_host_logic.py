@@ -140,3 +140,18 @@ def test_bitstream_pack_roundtrip():
         decode.pack_bitstream([np.array([[70000]])])
     with pytest.raises(ValueError):
         decode.unpack_bitstream(b"nope" + blob[4:])
+
+
+def test_batched_gemm_argument_block():
+    """FitEngine._batch_args lays out rcb_gemm_tc_batch's host arrays (pointers, row strides, N, K) in call order."""
+    import ctypes as C
+    from recombiner_b200.engine import FitEngine
+    Bt = [torch.zeros(3, 8), torch.zeros(5, 16)]
+    args, keep = FitEngine._batch_args([1024, 2048], 40, Bt, [4096, 8192], 48, 7, [3, 5], [8, 16], 1, 0.5)
+    nb, A, lda, B, ldb, Cp, ldc, M, N, K, in_half, out_scale = args
+    assert (nb, lda, ldc, M, in_half, out_scale) == (2, 40, 48, 7, 1, 0.5)
+    assert list((C.c_void_p * 2).from_address(A)) == [1024, 2048]
+    assert list((C.c_void_p * 2).from_address(B)) == [t.data_ptr() for t in Bt]
+    assert list((C.c_int * 2).from_address(ldb)) == [8, 16]
+    assert list((C.c_void_p * 2).from_address(Cp)) == [4096, 8192]
+    assert list((C.c_int * 2).from_address(N)) == [3, 5] and list((C.c_int * 2).from_address(K)) == [8, 16]
