@@ -341,8 +341,18 @@ typedef struct {
   double* logw_out;                             /* (n_pairs, n_cand) or NULL */
   float* sample; float* mask; float* beta; uint8_t* coded;   /* apply targets */
   int n_pairs, P, G, n_cand, max_D, apply;
+  /* Scratch of the staged scoring kernel (candidate table streamed through shared memory by bulk async copies,
+   * candidates split over several CTAs per run): >= n_pairs * 772 + 64 bytes, ZERO on the first call; the kernel
+   * leaves it zero again, so one buffer serves every later call on the same stream.  NULL (or n_cand % 4 != 0)
+   * selects the unstaged kernel; both produce bit-identical results. */
+  void* workspace; int64_t workspace_bytes;
 } rcb_rec_args;
 int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream);
+
+/* Measurement aid: `ctas` x 256 threads x 16 independent chains of `iters` double-precision FMAs; *flop_out (host)
+ * receives the FLOP count of the launch.  bench.py times it with CUDA events to get the FP64 peak the REC scoring
+ * kernel's roofline is stated against. */
+int rcb_ubench_dfma(double* scratch, int ctas, int iters, double* flop_out, rcb_stream_t stream);
 
 /* Receiver side: regenerate z for (row, block, idx) -> sample[row, start:end]. */
 int rcb_rec_decode(const int* pair_row, const int* pair_block, const int* idx,

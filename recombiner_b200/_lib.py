@@ -52,7 +52,8 @@ class RecArgs(C.Structure):
     _fields_ = [(n, P) for n in ("pair_row", "pair_block", "q_loc", "q_scale", "p_loc", "p_scale", "group_start",
                                  "group_end", "tables", "gumbel", "idx_out", "z_out", "logw_out", "sample", "mask",
                                  "beta", "coded")] + \
-               [(n, I32) for n in ("n_pairs", "P", "G", "n_cand", "max_D", "apply")]
+               [(n, I32) for n in ("n_pairs", "P", "G", "n_cand", "max_D", "apply")] + \
+               [("workspace", P), ("workspace_bytes", I64)]
 
 
 class StepState(C.Structure):
@@ -104,6 +105,7 @@ SIGNATURES = {
     "rcb_pick_block": [P, P, P, I32, I32, P],
     "rcb_rec_table": [P, P, P, I32, I32, P],
     "rcb_rec_encode": [C.POINTER(RecArgs), P],
+    "rcb_ubench_dfma": [P, I32, I32, C.POINTER(F64), P],
     "rcb_rec_decode": [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, P],
     "rcb_prior_suffstats": [P, P, P, I32, I32, P],
     "rcb_prior_from_stats": [P, P, P, I64, I32, P],
@@ -147,14 +149,27 @@ def check(rc: int, what: str = "") -> None:
 
 
 def ptr(t) -> int:
-    """Device pointer of a torch tensor (None -> NULL)."""
+    """Device pointer of a torch tensor (None -> NULL).  The kernels launch on the CURRENT device and stream, so a
+    tensor that lives on another GPU is refused instead of being dereferenced there."""
     if t is None:
         return None
     if not t.is_cuda:
         raise KernelError("librecombiner_b200 kernels take CUDA tensors only (no CPU fallback)")
     if not t.is_contiguous():
         raise KernelError("non-contiguous tensor passed to a kernel")
+    import torch
+    if t.device.index != torch.cuda.current_device():
+        raise KernelError(f"tensor on {t.device} passed to a kernel launching on cuda:{torch.cuda.current_device()} "
+                          "(models select their device with torch.cuda.set_device at construction)")
     return t.data_ptr()
+
+
+def use_device(device) -> None:
+    """Make `device` the current CUDA device: every C-ABI call launches on the current device and stream."""
+    import torch
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+        torch.cuda.set_device(dev)
 
 
 def stream() -> int:

@@ -80,7 +80,8 @@ __device__ __forceinline__ void philox_normal4(int64_t seed, int step, int tenso
     // u1 in (0,1], u2 in [0,1)
     const float u1 = ((float)(c[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);
     const float u2 = (float)(c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * __logf(u1));
+    // __logf has ~2^-22 absolute error near 1: a slightly positive result must not become sqrt(negative) = NaN
+    const float r = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
     float sn, cs;
     __sincosf(6.2831853071795865f * u2, &sn, &cs);
     z[2 * h] = r * cs;

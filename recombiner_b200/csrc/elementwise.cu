@@ -448,7 +448,8 @@ __global__ void pick_block_kernel(const double* __restrict__ kl, const uint8_t* 
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
-  if (lane == 0) block[r] = bi;
+  // a row whose KLs are all NaN (diverged fit) never wins a comparison: code block 0 instead of an out-of-range index
+  if (lane == 0) block[r] = bi < G ? bi : 0;
 }
 
 __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {

@@ -254,11 +254,13 @@ static int launch_tc(const float* A, int lda, const float* Bt, int ldbt, float* 
   if (int rc = make_map_2d(&tmA, A, M, K, lda, TC_BM, es)) return rc;
   if (int rc = make_map_2d(&tmB, Bt, N, K, ldbt, BN, es)) return rc;
   const int smem = TcSmem<BN>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;       // one bit per device: the opt-in is per device (and per template instance)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((configured >> (dev & 63)) & 1u)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("rcb_gemm_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
-    configured = true;
+    configured |= 1ull << (dev & 63);
   }
   dim3 grid(ceil_div(M, TC_BM), ceil_div(N, BN));
   gemm_tf32_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, C, ldc, M, N, K, bias, bias_mod, act, accumulate, out_half, in_half);
@@ -353,11 +355,13 @@ extern "C" int rcb_gemm_tc_batch(int nb, const void* const* A, int lda, const vo
     if (i < nb && N[j] > n_max) n_max = N[j];
   }
   const int smem = TcSmem<128>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;       // one bit per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((configured >> (dev & 63)) & 1u)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_batch_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("rcb_gemm_tc_batch: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
-    configured = true;
+    configured |= 1ull << (dev & 63);
   }
   dim3 grid(ceil_div(M, TC_BM), ceil_div(n_max, 128), nb);
   gemm_tc_batch_kernel<128><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(g, ldc, M, in_half, out_scale);

@@ -198,6 +198,9 @@ class FitEngine:
             raise KernelError("recombiner_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device)
+        _lib.use_device(self.device)          # 'cuda:1' as the reference accepts it: launches follow the model's device
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dims = list(dims)
         self.counts = layer_param_counts(self.dims)
         self.offsets = [0] + list(np.cumsum(self.counts))[:-1]

@@ -50,8 +50,10 @@ def _level_kwargs(prefix, grouping, prior, device):
 
 
 def compress(x, y, dataset, prior_objects, device, seed=42, fit_epochs=None, finetune_epochs=None, verbose=1,
-             row_offset=0):
-    """Library form of the driver body: returns (distortion, model)."""
+             row_offset=0, precision=None, code=True):
+    """Library form of the driver body: returns (distortion, model).  `precision` selects the kernel family
+    ('tf32' = tcgen05, the default; 'fp32' = SIMT parity path); `code=False` stops after optimize_posteriors
+    (returns (None, model))."""
     config = configs[dataset]
     g1, p1, g2, p2, g3, p3, linear_transform, upsample_net = prior_objects
     kw = {}
@@ -68,7 +70,8 @@ def compress(x, y, dataset, prior_objects, device, seed=42, fit_epochs=None, fin
                          linear_transform=linear_transform.to(device), upsample_net=upsample_net.to(device),
                          w0=30., c=6., random_seed=seed, device=device, kl_upper_buffer=0., kl_lower_buffer=0.4,
                          kl_adjust_gap=10, initial_beta=kl_beta, beta_step_size=0.05, row_offset=row_offset,
-                         layer_scales=config['layerwise_scale_factors'], paddings=config['paddings'], **kw).to(device)
+                         layer_scales=config['layerwise_scale_factors'], paddings=config['paddings'],
+                         precision=precision, **kw).to(device)
     n_groups = kw["n_groups"]
     h_n, hh_n = kw.get("h_n_groups"), kw.get("hh_n_groups")
     short = finetune_epochs            # an explicit fine-tune length also shortens the level-2/3 rounds
@@ -77,6 +80,8 @@ def compress(x, y, dataset, prior_objects, device, seed=42, fit_epochs=None, fin
         finetune_epochs = int(os.environ.get("RECOMBINER_FINETUNE_EPOCHS", max(30000 // n_groups, 50)))
     x, y = x.to(device), y.to(device)
     model.optimize_posteriors(x, y, n_epochs=fit_epochs, lr=2e-4, verbose=verbose)
+    if not code:
+        return None, model
     distortion = model.compress_posteriors(
         x, y, n_epochs_finetune=finetune_epochs,
         h_n_epochs_finetune=None if h_n is None else (max(15000 // h_n, 20) if short is None else short),
@@ -85,24 +90,57 @@ def compress(x, y, dataset, prior_objects, device, seed=42, fit_epochs=None, fin
     return distortion, model
 
 
-def main(argv=None):
-    args = parse_args(argv)
-    config = configs[args.dataset]
-    from data.load_data import load_test_set      # dataset loaders are outside the kernel path
-    x, y = load_test_set(args.test_dir, args.test_idx, args.dataset, config['fourier_dim'], config['patch'],
-                         config['pixel_sizes'])
-    distortion, model = compress(x, y, args.dataset, load_prior(args.prior_path), args.device, seed=args.seed)
+def _write_csvs(args, config, distortion, tables):
+    """The reference's output files (main_compression.py:163-178)."""
     if isinstance(distortion, float):
         distortion = np.array([[distortion]])
     np.savetxt(args.save_dir + "Distortion_test_id_%d" % args.test_idx + ".csv", distortion, delimiter=",")
     if int(args.save_bitstream):
-        np.savetxt(args.save_dir + "GroupIndex_test_id_%d" % args.test_idx + ".csv",
-                   model.compressed_idx_groupwise, delimiter=",")
-        if config['patch']:
-            np.savetxt(args.save_dir + "H_GroupIndex_test_id_%d" % args.test_idx + ".csv",
-                       model.h_compressed_idx_groupwise, delimiter=",")
-            np.savetxt(args.save_dir + "HH_GroupIndex_test_id_%d" % args.test_idx + ".csv",
-                       model.hh_compressed_idx_groupwise, delimiter=",")
+        names = ("GroupIndex", "H_GroupIndex", "HH_GroupIndex")
+        for name, t in zip(names, tables):
+            np.savetxt(args.save_dir + name + "_test_id_%d" % args.test_idx + ".csv", t, delimiter=",")
+
+
+def main(argv=None):
+    """Single process: the reference driver.  Under `torchrun` (one process per GPU) the rows of the test batch are
+    sharded by datapoint (by whole datum for the patch modalities) with no data-path collective; the per-row
+    distortions and index tables are gathered at the end and rank 0 writes the same CSVs
+    (main_compression.py:76-84 load, :163-178 write)."""
+    import torch.distributed as dist
+    from . import parallel
+    args = parse_args(argv)
+    config = configs[args.dataset]
+    from data.load_data import load_test_set      # input producer outside the kernel path (SURVEY C12)
+    x, y = load_test_set(args.test_dir, args.test_idx, args.dataset, config['fourier_dim'], config['patch'],
+                         config['pixel_sizes'])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = args.device
+    unit = int(np.prod(config['patch_nums'])) if config['patch'] else 1
+    sharded = world > 1 and x.shape[0] // unit >= world
+    if world > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        device = "cuda:%d" % local
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device(device))
+        if not sharded and dist.get_rank() != 0:      # fewer data than GPUs (one kodak image): rank 0 works alone
+            return
+    lo, hi = parallel.shard_rows(x.shape[0], world, dist.get_rank(), unit) if sharded else (0, x.shape[0])
+    distortion, model = compress(x[lo:hi], y[lo:hi], args.dataset, load_prior(args.prior_path), device, seed=args.seed,
+                                 row_offset=lo, verbose=1 if (not sharded or dist.get_rank() == 0) else 0)
+    tables = [model.compressed_idx_groupwise]
+    if config['patch']:
+        tables += [model.h_compressed_idx_groupwise, model.hh_compressed_idx_groupwise]
+    if sharded:
+        dev = torch.device(device)
+        d = np.atleast_1d(np.asarray(distortion, dtype=np.float64)).reshape(-1)
+        distortion = parallel.gather_rows(torch.from_numpy(d).to(dev)).cpu().numpy()
+        tables = [parallel.gather_rows(torch.from_numpy(t).to(dev)).cpu().numpy() for t in tables]
+        if not config['patch'] or distortion.size == 1:
+            distortion = distortion if distortion.size > 1 else float(distortion[0])
+        if dist.get_rank() != 0:
+            return
+    _write_csvs(args, config, distortion, tables)
 
 
 if __name__ == '__main__':

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from . import parallel
 from .config import configs
-from .prior_model import LinearTransform, PriorBNNmodel, Upsample, em_prior_update, get_grouping
+from .prior_model import LinearTransform, PriorBNNmodel, Upsample, em_prior_update, get_grouping, get_grouping_by_kl
 
 
 def parse_args(argv=None):
@@ -53,25 +53,48 @@ def step_beta(kl_beta, kl_bits, lo, hi):
     return min(max(kl_beta, 1e-20), 1)
 
 
+def _grouping_over_ranks(q_loc, q_scale, p_loc, p_scale, n_total):
+    """`get_grouping` (prior_model.py:264-271) with the per-parameter mean KL taken over the rows of ALL ranks:
+    local sums, one all-reduce, then the same seed-0 greedy binning on every rank."""
+    if parallel.world()[0] == 1:          # single process: the reference's own f32 arithmetic
+        return get_grouping(q_loc, q_scale, p_loc, p_scale)
+    ratio = (q_scale / p_scale) ** 2
+    kl_bits = (0.5 * (ratio + ((q_loc - p_loc) / p_scale) ** 2 - 1 - ratio.log()) / np.log(2.)).sum(0).double()
+    parallel.all_reduce_sum_(kl_bits)
+    return get_grouping_by_kl((kl_bits / n_total).float().cpu().numpy())
+
+
+def _mean_over_ranks(t, n_total):
+    if parallel.world()[0] == 1:
+        return t.detach().mean(0).cpu()
+    s = t.detach().sum(0).double()
+    parallel.all_reduce_sum_(s)
+    return (s / n_total).float().cpu()
+
+
 def checkpoint_objects(model, priors, kl_beta, linear_transform, upsample_net):
-    """The 8 pickled objects of a prior checkpoint (main_prior_training.py:284-335)."""
+    """The 8 pickled objects of a prior checkpoint (main_prior_training.py:284-335).  Under torch.distributed the
+    block grouping and the average training log-scale are statistics of the WHOLE training set (all-reduced sums
+    over the ranks' shards), so every rank builds the same objects a single process would."""
     prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale = priors[:4]
+    n1 = model.global_rows(0)
     with torch.no_grad():
         q_loc = torch.cat([model.loc.flatten(1), model.lpe_loc.flatten(1)], -1)
         q_scale = torch.cat([model.st(model.log_scale).flatten(1), model.st(model.lpe_log_scale).flatten(1)], -1)
         p_loc = torch.cat([prior_loc.flatten(), prior_lpe_loc.flatten()])
         p_scale = torch.cat([prior_scale.flatten(), prior_lpe_scale.flatten()])
-        grouping = get_grouping(q_loc, q_scale, p_loc, p_scale)
-        avg_ls = torch.cat([model.log_scale.detach().mean(0).cpu(), model.lpe_log_scale.detach().mean(0).flatten().cpu()])
+        grouping = _grouping_over_ranks(q_loc, q_scale, p_loc, p_scale, n1)
+        avg_ls = torch.cat([_mean_over_ranks(model.log_scale, n1), _mean_over_ranks(model.lpe_log_scale.flatten(1), n1)])
     none8 = (None,) * 8
     extra = [none8, (None, None, kl_beta, None), none8, (None, None, kl_beta, None)]
     if model.patch:
         extra = []
         for li, (q_l, q_ls) in enumerate(((model.h_loc, model.h_log_scale), (model.hh_loc, model.hh_log_scale))):
             pl, ps = priors[4 + 2 * li], priors[5 + 2 * li]
+            n = model.global_rows(li + 1)
             with torch.no_grad():
-                extra.append(get_grouping(q_l, model.st(q_ls), pl, ps))
-                extra.append((pl.cpu(), ps.cpu(), kl_beta, q_ls.detach().mean(0).flatten().cpu()))
+                extra.append(_grouping_over_ranks(q_l, model.st(q_ls), pl, ps, n))
+                extra.append((pl.cpu(), ps.cpu(), kl_beta, _mean_over_ranks(q_ls, n)))
     return [grouping, (p_loc.cpu(), p_scale.cpu(), kl_beta, avg_ls)] + extra + [linear_transform, upsample_net]
 
 
@@ -101,7 +124,6 @@ def train_prior(X, Y, dataset, max_bitrate, device="cuda", seed=42, n_em_iter=55
     linear_transform = LinearTransform(model.dims).to(device)     # same default init on every rank (same seed)
     upsample_net = Upsample(config['data_dim'], config['paddings'], config['layerwise_scale_factors']).to(device)
     world, rank = parallel.world()
-    n_total = train_size * world
     kl_beta = 1e-8
     lo, hi = budgets(dataset, config, max_bitrate)
     s0 = float(F.softplus(torch.tensor(-2.), beta=1, threshold=20) / 6)
@@ -131,22 +153,40 @@ def train_prior(X, Y, dataset, max_bitrate, device="cuda", seed=42, n_em_iter=55
 
 
 def main(argv=None):
+    """Single process: the reference driver.  Under `torchrun` every rank loads the training set and keeps a
+    contiguous shard of its rows (whole data for the patch modalities); rank 0 writes the checkpoints."""
+    import os
+    import torch.distributed as dist
     args = parse_args(argv)
     config = configs[args.dataset]
-    from data.load_data import load_training_set     # dataset loaders are outside the kernel path
+    from data.load_data import load_training_set     # input producer outside the kernel path (SURVEY C12)
     n_inst = args.train_size // np.prod(config['patch_nums']) if config['patch'] else args.train_size
     X, Y = load_training_set(args.train_dir, args.dataset, args.seed, n_inst, config['fourier_dim'], config['patch'],
                              config['pixel_sizes'])
     train_size = X.shape[0]
     print("Prior is trained on %d patches/images." % train_size, flush=True)
     name = "_train_size_%d" % train_size + "_max_bitrate=%.3f.pkl" % args.max_bitrate
+    device, lo, hi = args.device, 0, train_size
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        device = "cuda:%d" % local
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device(device))
+        unit = int(np.prod(config['hierarchical_patch_nums']['level3'])) if config['patch'] else 1
+        lo, hi = parallel.shard_rows(train_size, world, dist.get_rank(), unit)
 
     def write(objects, elbos):
         save_checkpoint(args.saving_dir + "PRIOR" + name, objects)
         with open(args.saving_dir + "LOSS" + name, "wb") as f:
             pickle.dump(elbos, f)
 
-    train_prior(X, Y, args.dataset, args.max_bitrate, device=args.device, seed=args.seed, on_checkpoint=write)
+    train_prior(X[lo:hi], Y[lo:hi], args.dataset, args.max_bitrate, device=device, seed=args.seed, on_checkpoint=write,
+                row_offset=lo, global_train_size=train_size,
+                n_em_iter=int(os.environ.get("RECOMBINER_EM_ITERS", 550)),
+                first_epochs=int(os.environ.get("RECOMBINER_FIRST_EPOCHS", 200)),
+                epochs=int(os.environ.get("RECOMBINER_EPOCHS", 100)))
 
 
 if __name__ == '__main__':

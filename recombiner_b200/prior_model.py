@@ -119,6 +119,8 @@ class PriorBNNmodel(nn.Module):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise KernelError("recombiner_b200.PriorBNNmodel runs on CUDA (sm_100a) only -- no CPU fallback")
+        _rcb_lib.use_device(dev)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
         self.random_seed, self.device = random_seed, dev
         self.n_layers = len(hidden_dims) + 1
         self.dims = [in_dim] + list(hidden_dims) + [out_dim]
@@ -183,6 +185,13 @@ class PriorBNNmodel(nn.Module):
                 lv.set_expansion(maps[li - 1])
                 self._levels.append(lv)
         self._call = 0
+
+    def global_rows(self, level: int = 0) -> int:
+        """Rows of a level over all ranks (cached: the sharding does not change during training)."""
+        cache = self.__dict__.setdefault("_global_rows", {})
+        if level not in cache:
+            cache[level] = global_count(self._levels[level].rows, self.device)
+        return cache[level]
 
     # views with the reference's attribute names
     @property
@@ -317,7 +326,7 @@ class PriorBNNmodel(nn.Module):
         opt = torch.optim.Adam(shared, lr) if training_mappings else None
         cfg = dict(lr=float(lr), b1=0.9, b2=0.999, eps=1e-8)
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        n_total = N * world
+        n_total = self.global_rows(0)            # true row count over all shards (they may be uneven)
         coef = 2.0 / (eng.pix * eng.out)
         stats = torch.zeros(n_epoch, 2, dtype=torch.float64, device=self.device)     # per step: (mse*N, beta*KL)
         kl_step = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -359,6 +368,17 @@ class PriorBNNmodel(nn.Module):
         return mse_last / n_total, float(kl_final.item()) / n_total, elbo
 
 
+def global_count(n_local: int, device) -> int:
+    """Sum of a per-rank row count over the process group (ranks may hold uneven shards:
+    parallel.shard_rows hands the remainder to the first ranks)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return int(n_local)
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
 def _level_prior(lib, loc, log_scale, n_rows, n_total):
     import torch.distributed as dist
     P, dev = loc.shape[1], loc.device
@@ -379,11 +399,10 @@ def em_prior_update(model: "PriorBNNmodel"):
     prior_hh_loc, prior_hh_scale])."""
     import torch.distributed as dist
     lib = _rcb_lib.load()
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     W = model._W
     out = []
     for li, lv in enumerate(model._levels):
-        p_loc, p_scale = _level_prior(lib, lv.loc.data, lv.log_scale.data, lv.rows, lv.rows * world)
+        p_loc, p_scale = _level_prior(lib, lv.loc.data, lv.log_scale.data, lv.rows, model.global_rows(li))
         if li == 0:
             out += [p_loc[:W], p_scale[:W], p_loc[W:].reshape(model._lpe_shape), p_scale[W:].reshape(model._lpe_shape)]
         else:

@@ -61,11 +61,25 @@ class CandidateTables:
         return torch.tensor([self.table(int(d)).data_ptr() for d in sizes], dtype=torch.int64, device=self.device)
 
 
+_WORKSPACES: Dict = {}
+
+
+def _workspace(device, n_pairs: int) -> torch.Tensor:
+    """Scratch of the staged scoring kernel, one per (device, stream): zero when allocated, left zero by every launch."""
+    need = n_pairs * 772 + 64
+    key = (str(device), stream())
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _WORKSPACES[key] = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+    return ws
+
+
 def encode(lv, tables_ptr: torch.Tensor, gumbel: torch.Tensor, q_scale: torch.Tensor, p_scale: torch.Tensor,
            pair_row: torch.Tensor, pair_block: torch.Tensor, n_cand: int, max_D: int, *, apply: bool,
-           want_logw: bool = False):
+           want_logw: bool = False, staged: bool = True):
     """Code `len(pair_row)` (row, block) pairs.  apply=True commits the result to the
-    level state (sample, mask, beta=0, coded, idx); otherwise returns (idx, z, log_w)."""
+    level state (sample, mask, beta=0, coded, idx); otherwise returns (idx, z, log_w).
+    staged=False forces the unstaged scoring kernel (same results bit for bit; kept for odd candidate counts)."""
     lib = _lib.load()
     n_pairs = int(pair_row.numel())
     dev = lv.device
@@ -86,6 +100,9 @@ def encode(lv, tables_ptr: torch.Tensor, gumbel: torch.Tensor, q_scale: torch.Te
         logw = torch.empty(n_pairs, n_cand, dtype=torch.float64, device=dev)
     a.logw_out = ptr(logw)
     a.n_pairs, a.P, a.G, a.n_cand, a.max_D, a.apply = n_pairs, lv.P, lv.G, n_cand, max_D, int(apply)
+    if staged:
+        ws = _workspace(dev, n_pairs)
+        a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
     check(lib.rcb_rec_encode(C.byref(a), stream()), "rcb_rec_encode")
     return idx, z, logw
 

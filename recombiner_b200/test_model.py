@@ -139,6 +139,9 @@ class TestBNNmodel(nn.Module):
         if dev.type != "cuda":
             raise KernelError("recombiner_b200.TestBNNmodel runs on CUDA (sm_100a) only -- there is no CPU "
                               "fallback; the CPU restatement used for parity lives in oracle/")
+        from ._lib import use_device
+        use_device(dev)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
         self.bit_per_group = 16
         self.n_layers = len(hidden_dims) + 1
         self.dims = [in_dim] + list(hidden_dims) + [out_dim]
@@ -398,9 +401,10 @@ class TestBNNmodel(nn.Module):
     def hh_compress_group(self, row_idx, group_idx):
         return self._compress_group(2, row_idx, group_idx)
 
-    def compress_round(self, blocks: Optional[torch.Tensor] = None, level: int = 0):
+    def compress_round(self, blocks: Optional[torch.Tensor] = None, level: int = 0, apply: bool = True):
         """Code one block of every row of a level in a single launch.  With blocks=None each
-        row codes its largest-KL not-yet-coded block (test_model.py:809-817)."""
+        row codes its largest-KL not-yet-coded block (test_model.py:809-817).  apply=False scores
+        and selects without committing anything (timing / what-if)."""
         from ._lib import check, ptr, stream
         n = int(np.ceil(2 ** self.bit_per_group))
         self._ensure_rec(n)
@@ -415,7 +419,7 @@ class TestBNNmodel(nn.Module):
         # pairs sorted by block: the kernel scores runs of equal blocks against one pass over the candidate table
         order = torch.argsort(blocks, stable=True)
         _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, rows[order].contiguous(),
-                    blocks[order].contiguous(), n, lv.max_D, apply=True)
+                    blocks[order].contiguous(), n, lv.max_D, apply=apply)
         return blocks
 
     def decode_posteriors(self, indices: np.ndarray, level: int = 0) -> torch.Tensor:
@@ -518,18 +522,71 @@ class TestBNNmodel(nn.Module):
             lv.adam["t"] = t + 1
         return ws
 
-    def train(self, x=True, y=None, n_epochs=0, optimizer=None, verbose=False, sample_size=5):
+    def _host_x_is_shared(self, x):
+        """Every row of a host x holds the same Fourier features (they depend on the pixel grid only): checked once
+        per tensor, then only one row is uploaded."""
+        key = (x.data_ptr(), tuple(x.shape), x._version)
+        c = self.__dict__.setdefault("_x_shared_cache", {})
+        if key not in c:
+            c.clear()
+            c[key] = bool(x.shape[0] == 1 or x.stride(0) == 0 or (x == x[:1]).all())
+        return c[key]
+
+    def _stage_inputs(self, x, y):
+        """Device-side inputs of a train() call.  CUDA tensors are used as they are.  Host tensors are uploaded on a
+        copy stream into one of two persistent staging sets (captured fit-step graphs hold their addresses), so the
+        upload of call k+1 travels under the kernels of call k when the host buffers are pinned.  Returns
+        (x, y, slot); `_release_inputs(slot)` marks the set reusable once the steps that read it are queued."""
+        if x.is_cuda and y.is_cuda:
+            return x, y.to(torch.float32).contiguous(), None
+        st = self.__dict__.get("_staging")
+        if st is None:
+            st = self._staging = dict(slot=0, bufs=[None, None], stream=torch.cuda.Stream(device=self.device),
+                                      up=[torch.cuda.Event(), torch.cuda.Event()],
+                                      done=[torch.cuda.Event(), torch.cuda.Event()])
+        b = st["slot"]
+        st["slot"] ^= 1
+        x, y = x.detach(), y.detach()
+        shared = (not x.is_cuda) and self._host_x_is_shared(x)
+        xs = x[:1] if shared else x
+        bufs = st["bufs"][b]
+        if bufs is None or bufs[0].shape != xs.shape or bufs[1].shape != y.shape:
+            bufs = st["bufs"][b] = (torch.empty(xs.shape, dtype=torch.float32, device=self.device),
+                                    torch.empty(y.shape, dtype=torch.float32, device=self.device))
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_event(st["done"][b])         # the steps that last read this set are over
+            bufs[0].copy_(xs, non_blocking=True)
+            bufs[1].copy_(y, non_blocking=True)
+            st["up"][b].record(st["stream"])
+        main.wait_event(st["up"][b])
+        xd = bufs[0].expand(x.shape[0], -1, -1) if shared else bufs[0]
+        return xd, bufs[1], b
+
+    def _release_inputs(self, slot):
+        if slot is not None:
+            self._staging["done"][slot].record(torch.cuda.current_stream())
+
+    def last_loss_terms(self, sample_size=5):
+        """Per-(row, sample) summed squared error of the most recent fit step (device tensor, rows * S)."""
+        return self.engine.workspace(self._levels[0].rows, sample_size)["sqerr"]
+
+    def train(self, x=True, y=None, n_epochs=0, optimizer=None, verbose=False, sample_size=5, start_epoch=0):
+        """Adam loop of test_model.py:621-635 (`predict(random_seed=epoch)` -> loss -> beta update every
+        kl_adjust_gap-th epoch -> step), every step one fused kernel sequence.  x, y may live on the host (pinned
+        memory makes the upload asynchronous).  `start_epoch` (extension) offsets the epoch counter, so a caller that
+        feeds the loop one step per call keeps the reference's noise keys and annealing cadence."""
         if isinstance(x, bool):          # nn.Module.train(mode) / .eval() compatibility
             return super().train(x)
         cfg = self._adam_config(optimizer)
-        x = x.to(self.device)
-        y = y.to(self.device, torch.float32).contiguous()
-        it = range(n_epochs)
+        x, y, slot = self._stage_inputs(x, y)
+        it = range(start_epoch, start_epoch + n_epochs)
         if verbose:
             from tqdm import tqdm
             it = tqdm(it)
         for epoch in it:
             self.fit_step(x, y, epoch, cfg, sample_size)
+        self._release_inputs(slot)
 
     def _distortion(self, x, y):
         with torch.no_grad():

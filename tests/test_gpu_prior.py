@@ -13,7 +13,7 @@ from oracle import recombiner_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _model(case):
+def _model(case, precision="fp32"):
     from recombiner_b200.prior_model import PriorBNNmodel
     from tests.helpers import product_mappings
     shape = case["shape"]
@@ -22,7 +22,7 @@ def _model(case):
                       train_size=case["rows"], data_dim=shape.data_dim, pixel_sizes=shape.pixel_sizes,
                       upsample_factors=shape.upsample_factors, latent_dim=shape.latent_dim, patch=shape.patch,
                       patch_nums=shape.patch_nums, hierarchical_patch_nums=shape.hier, device="cuda",
-                      layer_scales=shape.layer_scales, paddings=shape.paddings, precision="fp32")
+                      layer_scales=shape.layer_scales, paddings=shape.paddings, precision=precision)
     W = shape.n_weights
     with torch.no_grad():
         m._loc_all[:, :W] = case["loc"].cuda()
@@ -39,35 +39,58 @@ def _close(a, ref, rtol=2e-3):
     np.testing.assert_allclose(a, ref, rtol=rtol, atol=3e-6 * np.abs(ref).max() + 1e-9)
 
 
+# Stated tolerances per precision.  fp32 = SIMT parity path.  tf32 = the tcgen05 path the bench times (TF32 / fp16 MMA
+# operands, fp32 accumulation): every tensor within 3e-2 * max|reference| (precision policy), scalars and
+# gradient norms within 1e-2 relative.
+TOL = {"fp32": dict(y=(2e-4, 2e-5), scalar=1e-4, norm=1e-3, grad_max=None),
+       "tf32": dict(y=None, scalar=1e-2, norm=1e-2, grad_max=3e-2)}
+
+
+def _check(a, ref, tol, rtol=2e-3, sub_rtol=None):
+    a, ref = np.asarray(a), np.asarray(ref)
+    if tol["grad_max"] is not None:
+        assert np.abs(a - ref).max() <= tol["grad_max"] * np.abs(ref).max() + 1e-12
+    elif sub_rtol is not None:
+        np.testing.assert_allclose(a, ref, rtol=sub_rtol, atol=2e-5 * np.abs(ref).max())
+    else:
+        _close(a, ref, rtol)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
 @pytest.mark.parametrize("name,n_data", [("cifar", 3), ("protein", 4), ("patch2d", 1)])
-def test_prior_step_matches_reference(golden, name, n_data):
+def test_prior_step_matches_reference(golden, name, n_data, precision):
+    """One prior-training forward/backward (prior_model.py:129-200,237-250) against the goldens the unmodified reference
+    wrote: reconstruction, loss terms, posterior gradients, gradients of A_l and of the upsampler -- on the SIMT parity
+    path and on the tcgen05 path that `train` / bench.py run by default."""
     g = golden("prior_" + name)
+    tol = TOL[precision]
     case = cases.make_prior_case(name, n_data)
-    m, lt, up = _model(case)
+    m, lt, up = _model(case, precision)
     P = case["prior"]
     pri = (P["loc"], P["scale"], P["lpe_loc"], P["lpe_scale"])
     if case["shape"].patch:
         pri += (P["loc"], P["scale"], P["loc"], P["scale"])
-    y_hat = m.forward(case["x"].cuda(), lt, up, True, eps=case["eps"])
-    np.testing.assert_allclose(y_hat.cpu().numpy(), g["y_hat"], rtol=2e-4, atol=2e-5)
+    y_hat = m.forward(case["x"].cuda(), lt, up, True, eps=case["eps"]).cpu().numpy()
+    if tol["y"] is not None:
+        np.testing.assert_allclose(y_hat, g["y_hat"], rtol=tol["y"][0], atol=tol["y"][1])
+    else:
+        assert np.abs(y_hat - g["y_hat"]).max() <= 3e-2 * np.abs(g["y_hat"]).max()
     mse, kl, grads = m.loss_and_grads(case["x"], case["y"], pri, lt, up, case["kl_beta"], eps=case["eps"])
-    assert float(mse) == pytest.approx(float(g["mse"]), rel=1e-4)
+    assert float(mse) == pytest.approx(float(g["mse"]), rel=tol["scalar"])
     assert float(kl) == pytest.approx(float(g["kl"]), rel=1e-4)
     assert float(m.calculate_kl(*pri)) == pytest.approx(float(g["kl"]), rel=1e-4)
     for k in ("loc", "log_scale", "lpe_loc", "lpe_log_scale", "h_loc", "h_log_scale", "hh_loc", "hh_log_scale"):
         if k in grads:
-            _close(grads[k].cpu().numpy(), g["grad_" + k])
+            _check(grads[k].cpu().numpy(), g["grad_" + k], tol)
     for i in range(4):
         gf = grads[f"A{i}"].flatten().cpu()
-        assert float(gf.double().norm()) == pytest.approx(float(g[f"grad_A{i}_norm"]), rel=1e-3)
-        ref = g[f"grad_A{i}_sub"]
-        np.testing.assert_allclose(gf[::997].numpy(), ref, rtol=1e-2, atol=2e-5 * np.abs(ref).max())
+        assert float(gf.double().norm()) == pytest.approx(float(g[f"grad_A{i}_norm"]), rel=tol["norm"])
+        _check(gf[::997].numpy(), g[f"grad_A{i}_sub"], tol, sub_rtol=1e-2)
     for k in ("conv1", "conv2", "conv3"):
         for leaf in ("weight", "bias"):
             gf = grads[f"{k}.{leaf}"].flatten().cpu()
-            assert float(gf.double().norm()) == pytest.approx(float(g[f"grad_{k}.{leaf}_norm"]), rel=1e-3), (k, leaf)
-            ref = g[f"grad_{k}.{leaf}_sub"]
-            np.testing.assert_allclose(gf[::97].numpy(), ref, rtol=1e-2, atol=2e-5 * np.abs(ref).max())
+            assert float(gf.double().norm()) == pytest.approx(float(g[f"grad_{k}.{leaf}_norm"]), rel=tol["norm"]), (k, leaf)
+            _check(gf[::97].numpy(), g[f"grad_{k}.{leaf}_sub"], tol, sub_rtol=1e-2)
 
 
 @pytest.mark.parametrize("name,n_data", [("cifar", 3), ("protein", 4)])

@@ -103,3 +103,33 @@ def test_encode_all_blocks_then_decode_roundtrip():
     decoded = m.decode_posteriors(indices)
     assert torch.equal(decoded, m._lv.sample)          # bit-exact from (prior, seed, indices)
     assert torch.equal(m._lv.mask, torch.ones_like(m._lv.mask))
+
+
+@pytest.mark.parametrize("n_cand", [65536, 1000])
+def test_staged_scoring_equals_unstaged_bit_for_bit(n_cand):
+    """The staged kernel (table through shared memory by bulk async copies, rows of a run sharing the loads,
+    candidates split over CTAs, cross-CTA first-argmax) against the plain one: indices, samples and every
+    log-weight identical, for runs of 1..11 equal blocks and a candidate count with a ragged last chunk."""
+    from recombiner_b200 import rec
+    from tests.helpers import product_test_model
+    case = cases.make_fit_case("cifar", 37, 1, coded_frac=0.0)
+    m = product_test_model(case, "cifar")
+    m._ensure_rec(n_cand)
+    lv = m._lv
+    blocks = [0] * 11 + [1] * 8 + [2] * 5 + [3] * 3 + [4] * 2 + list(range(5, 13))
+    assert len(blocks) == 37
+    pr = torch.arange(37, dtype=torch.int32, device="cuda")
+    pb = torch.tensor(blocks, dtype=torch.int32, device="cuda")
+    q_scale, p_scale = m._scales()
+    out = {}
+    for staged in (True, False):
+        idx, z, logw = rec.encode(lv, lv.tables_ptr, m._g_dev, q_scale, p_scale, pr, pb, n_cand, lv.max_D, apply=False,
+                                  want_logw=True, staged=staged)
+        out[staged] = (idx.cpu(), z.cpu(), logw.cpu())
+    assert torch.equal(out[True][0], out[False][0])
+    assert torch.equal(out[True][1], out[False][1])
+    assert torch.equal(out[True][2], out[False][2])
+    assert (out[True][0] >= 0).all() and (out[True][0] < n_cand).all()
+    # a second launch reuses the workspace the first one left zeroed
+    idx2, _, _ = rec.encode(lv, lv.tables_ptr, m._g_dev, q_scale, p_scale, pr, pb, n_cand, lv.max_D, apply=False)
+    assert torch.equal(idx2.cpu(), out[True][0])

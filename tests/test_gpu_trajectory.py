@@ -1,0 +1,151 @@
+"""Trajectory-level parity of the BENCHMARKED precision (north_star: "final PSNR and bpp agree within a stated
+tolerance").
+
+The same short schedule -- `optimize_posteriors` (300 steps) + `compress_posteriors` (G rounds of REC + 5 fine-tune
+steps), i.e. main_compression.py:148-162 with shortened epochs -- is run three ways on the same rows, prior, mappings
+and block grouping:
+
+  1. precision="tf32": the tcgen05 path with every default fp16/TF32 operand switch (what bench.py times),
+  2. precision="fp32": the SIMT parity path the step-level goldens pin,
+  3. the UNMODIFIED reference `TestBNNmodel(device='cpu')` from oracle/_ref (CPU port of it if the copy is absent).
+
+The prior comes from a short run of this repo's prior training, so the mappings and INR weights are at trained scale,
+not at their init scale.  The three arms draw different noise (Philox on the GPU, torch's CPU generator in the
+reference), so the comparison is statistical; the stated tolerances are
+
+  * mean PSNR over the rows, after optimisation and after full coding: |delta| <= 0.3 dB between any two arms,
+  * KL of the optimised posterior (the bits REC has to code), mean over rows: within 5 %,
+  * bpp identical (same grouping), every coded block decodes bit-exactly from its index.
+"""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N_TRAIN, N_TEST = 32, 8
+N_FIT, N_FINETUNE = 300, 5
+TOTAL_BITS = 300.0          # synthetic grouping of the trained prior: G ~ 19 blocks of 16 bits
+PSNR_TOL_DB, KL_RTOL = 0.3, 0.05
+
+
+def _images(n, seed):
+    """Smooth synthetic 32x32 RGB images (low-frequency sinusoid mixtures): compressible, unlike white noise."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 32), torch.linspace(0, 1, 32), indexing="ij")
+    img = torch.zeros(n, 32, 32, 3)
+    for _ in range(4):
+        f = torch.rand(n, 1, 1, 3, 2, generator=g) * 3.0
+        ph = torch.rand(n, 1, 1, 3, generator=g) * 6.28
+        amp = torch.rand(n, 1, 1, 3, generator=g) * 0.2
+        img += amp * torch.sin(6.28 * (f[..., 0] * yy[None, :, :, None] + f[..., 1] * xx[None, :, :, None]) + ph)
+    img = (0.5 + img).clamp(0, 1)
+    return img.reshape(n, 1024, 3)
+
+
+def _x(n):
+    from recombiner_b200 import utils
+    from recombiner_b200.config import configs
+    cfg = configs["cifar"]
+    coords, _ = utils.to_grid_coordinates_and_features(torch.zeros(1, *cfg["pixel_sizes"]))
+    return utils.fourier_features(coords, cfg["fourier_dim"])[None].repeat(n, 1, 1)
+
+
+@pytest.fixture(scope="module")
+def trained_prior():
+    from recombiner_b200 import main_prior_training
+    from recombiner_b200.prior_model import get_grouping_by_kl
+    objects, elbos, _ = main_prior_training.train_prior(_x(N_TRAIN), _images(N_TRAIN, 3), "cifar", max_bitrate=0.3,
+                                                        n_em_iter=12, first_epochs=100, epochs=50, checkpoint_every=100,
+                                                        verbose=False)
+    assert np.isfinite(elbos).all() and np.mean(elbos[-20:]) > np.mean(elbos[:20])
+    # a fixed synthetic grouping keeps the number of blocks (and the CPU arm's run time) bounded whatever the
+    # short training reached; all arms share it
+    bits = np.random.RandomState(0).gamma(2.0, 1.0, objects[1][0].numel())
+    objects[0] = get_grouping_by_kl(bits * (TOTAL_BITS / bits.sum()))
+    return objects
+
+
+def _gpu_arm(objects, x, y, precision):
+    from recombiner_b200 import main_compression
+    # the driver's own loader and constructor; optimise and code in two calls so the statistics in between can be read
+    with contextlib.redirect_stdout(io.StringIO()):
+        d0, model = main_compression.compress(x, y, "cifar", objects, "cuda", fit_epochs=N_FIT, finetune_epochs=None,
+                                              verbose=0, precision=precision, code=False)
+        psnr_fit = float(np.mean(model._distortion(x, y)))
+        kl_bits = model.update_annealing_factors(False).sum(1) / np.log(2.)
+        d = model.compress_posteriors(x.cuda(), y.cuda(), n_epochs_finetune=N_FINETUNE, verbose=0, lr=2e-4, fine_tune_gap=1,
+                                      compress_from_group_with_largest_kl=True)
+    idx = model.compressed_idx_groupwise
+    assert torch.equal(model.decode_posteriors(idx), model._lv.sample), "decode is not bit-exact"
+    assert bool(model._lv.coded.all())
+    return dict(psnr_fit=psnr_fit, psnr=float(np.mean(d)), kl_bits=float(kl_bits.mean()), bpp=float(model.bpp))
+
+
+def _reference_arm(objects, x, y):
+    """Unmodified reference on the CPU (oracle/_ref); the class-level port if the copy did not travel."""
+    from recombiner_b200.config import configs
+    from recombiner_b200.utils import batch_PSNR
+    g1, p1 = objects[0], objects[1]
+    p2g = g1[4]
+    p_loc = p1[0].clone()[p2g]
+    p_log_scale = torch.log(torch.exp(p1[1] * 6) - 1)[p2g]
+    init_ls = p1[3][p2g].cpu().detach()
+    A = [a.detach().cpu() for a in objects[6].A]
+    up_state = {k: v.detach().cpu() for k, v in objects[7].state_dict().items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import build_ref
+    if build_ref.available():
+        from oracle import ref_arm
+        m = ref_arm.build_model(configs["cifar"], "cifar", x.shape[0], A, up_state, p_loc, p_log_scale, g1,
+                                init_log_scale=init_ls, initial_beta=p1[2])
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            m.optimize_posteriors(x, y, n_epochs=N_FIT, lr=2e-4, verbose=0)
+            with torch.no_grad():
+                psnr_fit = float(np.mean(batch_PSNR(y.numpy(), m.predict(x).numpy(), True)))
+            kl_bits = m.update_annealing_factors(False).sum(1) / np.log(2.)
+            d = m.compress_posteriors(x, y, n_epochs_finetune=N_FINETUNE, h_n_epochs_finetune=None,
+                                      hh_n_epochs_finetune=None, verbose=0, lr=2e-4, fine_tune_gap=1,
+                                      compress_from_group_with_largest_kl=True)
+        return dict(psnr_fit=psnr_fit, psnr=float(np.mean(d)), kl_bits=float(kl_bits.mean()), bpp=float(m.bpp),
+                    kind="reference")
+    from oracle import cases
+    from oracle import recombiner_oracle as orc
+    from oracle.ref_port import OracleCompressor
+    rows, P, G = x.shape[0], p_loc.numel(), g1[5]
+    lvl = dict(loc=p_loc[None].repeat(rows, 1), log_scale=init_ls[None].repeat(rows, 1).float(), p_loc=p_loc,
+               p_log_scale=p_log_scale, group_idx=g1[0], group_start=g1[1], group_end=g1[2], group_to_param=g1[3],
+               param_to_group=g1[4], n_groups=G, coded=np.zeros((rows, G), dtype=bool), mask=torch.zeros(rows, P),
+               sample=torch.zeros(rows, P), beta=torch.full((rows, G), float(p1[2])))
+    oc = OracleCompressor(dict(shape=cases.shape_of("cifar"), rows=rows, A=A, w_up=up_state, x=x, y=y, lvl1=lvl))
+    for ep in range(N_FIT):
+        oc.fit_step(ep, 5)
+    psnr_fit = float(np.mean(batch_PSNR(y.numpy(), oc.reconstruct().numpy()[:, 0], True)))
+    kl_bits = orc.group_kl_nats(oc.lv).sum(1) / np.log(2.)
+    for _ in range(G):
+        oc.compress_round()
+        oc.new_optimizer()
+        for ep in range(N_FINETUNE):
+            oc.fit_step(ep, 5)
+    psnr = float(np.mean(batch_PSNR(y.numpy(), oc.reconstruct().numpy()[:, 0], True)))
+    return dict(psnr_fit=psnr_fit, psnr=psnr, kl_bits=float(kl_bits.mean()), bpp=16.0 * G / 1024, kind="port")
+
+
+def test_short_schedule_tf32_fp32_reference_agree(trained_prior):
+    x, y = _x(N_TEST), _images(N_TEST, 17)
+    arms = {"tf32": _gpu_arm(trained_prior, x, y, "tf32"), "fp32": _gpu_arm(trained_prior, x, y, "fp32"),
+            "reference": _reference_arm(trained_prior, x, y)}
+    print("\ntrajectory arms:", arms)
+    names = list(arms)
+    assert arms["tf32"]["psnr_fit"] > 15.0, "the fit did not move"        # sanity: this schedule reaches > 20 dB
+    for i, a in enumerate(names):
+        for b in names[i + 1:]:
+            A, B = arms[a], arms[b]
+            assert abs(A["psnr_fit"] - B["psnr_fit"]) <= PSNR_TOL_DB, (a, b, A, B)
+            assert abs(A["psnr"] - B["psnr"]) <= PSNR_TOL_DB, (a, b, A, B)
+            assert abs(A["kl_bits"] - B["kl_bits"]) <= KL_RTOL * max(A["kl_bits"], B["kl_bits"]), (a, b, A, B)
+            assert A["bpp"] == pytest.approx(B["bpp"], rel=1e-12)
