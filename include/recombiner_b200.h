@@ -55,10 +55,22 @@ typedef struct {
   int step;
   float adam_step_size;    /* lr / (1 - b1^t) */
   float adam_bc2_sqrt;     /* sqrt(1 - b2^t) */
-  int reserved;
+  float beta_scalar;       /* >= 0: replaces rcb_update_args.beta_scalar (the global beta of prior training,
+                              prior_model.py:247); < 0: unused */
 } rcb_step_state;
 int rcb_set_step_state(rcb_step_state* dev, int64_t seed, int step, float adam_step_size, float adam_bc2_sqrt,
-                       rcb_stream_t stream);
+                       float beta_scalar, rcb_stream_t stream);
+
+/* Adam step on one flat fp32 vector with torch.optim.Adam's default arithmetic (prior_model.py:224-227,253: the
+ * optimiser of the shared mappings A_l / upsampler; the posteriors' Adam is fused into rcb_fit_update).
+ * step_size = lr / (1 - b1^t), bc2_sqrt = sqrt(1 - b2^t); with dyn != NULL both are read from device memory so
+ * that a captured step can be replayed.  All four buffers 16-byte aligned. */
+int rcb_adam_flat(float* theta, const float* grad, float* m, float* v, int64_t n, float step_size, float bc2_sqrt,
+                  float b1, float b2, float eps, const rcb_step_state* dyn, rcb_stream_t stream);
+
+/* out[0] = scale * sum(sqerr[0..n)), out[1] = kl[0] (kl may be NULL): the two loss terms of one prior-training
+ * step (prior_model.py:237-253) kept on the device in f64 instead of two .item() round trips per step. */
+int rcb_step_stats(const float* sqerr, int n, double scale, const double* kl, double* out, rcb_stream_t stream);
 
 typedef struct {
   const float* loc;        /* (src_rows, P) group order */
@@ -342,9 +354,11 @@ typedef struct {
   float* sample; float* mask; float* beta; uint8_t* coded;   /* apply targets */
   int n_pairs, P, G, n_cand, max_D, apply;
   /* Scratch of the staged scoring kernel (candidate table streamed through shared memory by bulk async copies,
-   * candidates split over several CTAs per run): >= n_pairs * 772 + 64 bytes, ZERO on the first call; the kernel
-   * leaves it zero again, so one buffer serves every later call on the same stream.  NULL (or n_cand % 4 != 0)
-   * selects the unstaged kernel; both produce bit-identical results. */
+   * candidates split over several CTAs per run): >= n_pairs * 772 + 128 bytes.  Its first
+   * (workspace_bytes - 64) / 772 * 4 bytes are per-pair arrival counters: ZERO before the first call; every launch
+   * leaves them zero again, so one buffer (always passed with the same workspace_bytes) serves every later call on
+   * the same stream.  NULL, a buffer that is too small, or n_cand % 4 != 0 select the unstaged kernel; both
+   * produce bit-identical results. */
   void* workspace; int64_t workspace_bytes;
 } rcb_rec_args;
 int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream);

@@ -57,7 +57,7 @@ class RecArgs(C.Structure):
 
 
 class StepState(C.Structure):
-    _fields_ = [("seed", I64), ("step", I32), ("adam_step_size", F32), ("adam_bc2_sqrt", F32), ("reserved", I32)]
+    _fields_ = [("seed", I64), ("step", I32), ("adam_step_size", F32), ("adam_bc2_sqrt", F32), ("beta_scalar", F32)]
 
 
 STRUCTS = {"rcb_step_state": StepState, "rcb_sample_args": SampleArgs, "rcb_upconv_geom": UpconvGeom, "rcb_mlp_args": MlpArgs,
@@ -67,7 +67,9 @@ STRUCTS = {"rcb_step_state": StepState, "rcb_sample_args": SampleArgs, "rcb_upco
 SIGNATURES = {
     "rcb_version": [],
     "rcb_last_error": [],
-    "rcb_set_step_state": [P, I64, I32, F32, F32, P],
+    "rcb_set_step_state": [P, I64, I32, F32, F32, F32, P],
+    "rcb_adam_flat": [P, P, P, P, I64, F32, F32, F32, F32, F32, P, P],
+    "rcb_step_stats": [P, I32, F64, P, P, P],
     "rcb_fit_sample": [C.POINTER(SampleArgs), P],
     "rcb_gemm": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, I32, P],
     "rcb_gemm_tc": [P, I32, P, I32, P, I32, I32, I32, I32, P, I32, I32, I32, P],

@@ -142,7 +142,10 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
 // order (coalesced on the stored state).  Same arithmetic order as update_kernel.
 // dynamic smem: 2 * P floats.
 __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) {
-  if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt; }
+  if (a.dyn) {
+    a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt;
+    if (a.dyn->beta_scalar >= 0.f) a.beta_scalar = a.dyn->beta_scalar;      // prior training: the global beta of a captured step
+  }
   extern __shared__ float sm[];
   float* s_dmu = sm;
   float* s_dsig = sm + a.P;
@@ -302,7 +305,10 @@ __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) 
 // ------------------------------------------- gradient reduction + KL + Adam --
 // grid: (ceil(P/256), src_rows).  One thread = one stored (row, group-order column).
 __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
-  if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt; }
+  if (a.dyn) {
+    a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt;
+    if (a.dyn->beta_scalar >= 0.f) a.beta_scalar = a.dyn->beta_scalar;      // prior training: the global beta of a captured step
+  }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
   float kl_term = 0.f;
@@ -459,8 +465,56 @@ __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ 
     if (i0 + e < n) dst[i0 + e] = __float2half_rn(src[i0 + e]);
 }
 
-__global__ void set_step_state_kernel(rcb_step_state* dev, long long seed, int step, float ss, float bc) {
-  dev->seed = seed; dev->step = step; dev->adam_step_size = ss; dev->adam_bc2_sqrt = bc; dev->reserved = 0;
+__global__ void set_step_state_kernel(rcb_step_state* dev, long long seed, int step, float ss, float bc, float beta) {
+  dev->seed = seed; dev->step = step; dev->adam_step_size = ss; dev->adam_bc2_sqrt = bc; dev->beta_scalar = beta;
+}
+
+// Adam on one flat fp32 parameter vector (the shared mappings of prior training): the update torch.optim.Adam makes
+// with default flags, theta -= step_size * m / (sqrt(v) / sqrt(1 - b2^t) + eps), step_size = lr / (1 - b1^t).
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ theta, const float* __restrict__ grad,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n, float step_size,
+                                                        float bc2s, float b1, float b2, float eps, const rcb_step_state* dyn) {
+  if (dyn) { step_size = dyn->adam_step_size; bc2s = dyn->adam_bc2_sqrt; }
+  const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  if (i0 + 4 <= n) {
+    const float4 g = *reinterpret_cast<const float4*>(grad + i0);
+    float4 mm = *reinterpret_cast<const float4*>(m + i0), vv = *reinterpret_cast<const float4*>(v + i0);
+    float4 t = *reinterpret_cast<const float4*>(theta + i0);
+#define RCB_ADAM1(c)                                                     \
+    mm.c = b1 * mm.c + (1.f - b1) * g.c;                                 \
+    vv.c = b2 * vv.c + (1.f - b2) * g.c * g.c;                           \
+    t.c = t.c - step_size * (mm.c / (sqrtf(vv.c) / bc2s + eps));
+    RCB_ADAM1(x) RCB_ADAM1(y) RCB_ADAM1(z) RCB_ADAM1(w)
+#undef RCB_ADAM1
+    *reinterpret_cast<float4*>(m + i0) = mm;
+    *reinterpret_cast<float4*>(v + i0) = vv;
+    *reinterpret_cast<float4*>(theta + i0) = t;
+  } else {
+    for (int64_t i = i0; i < n; ++i) {
+      const float g = grad[i];
+      const float mm = b1 * m[i] + (1.f - b1) * g, vv = b2 * v[i] + (1.f - b2) * g * g;
+      m[i] = mm; v[i] = vv;
+      theta[i] = theta[i] - step_size * (mm / (sqrtf(vv) / bc2s + eps));
+    }
+  }
+}
+
+// out[0] = scale * sum(sqerr[0..n)), out[1] = kl[0]  (per-step loss terms of prior training, f64; one CTA)
+__global__ void __launch_bounds__(256) step_stats_kernel(const float* __restrict__ sqerr, int n, double scale,
+                                                         const double* __restrict__ kl, double* __restrict__ out) {
+  __shared__ double red[8];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) t += (double)sqerr[i];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    out[0] = scale * s;
+    out[1] = kl ? kl[0] : 0.0;
+  }
 }
 
 // ------------------------------------------------------------------ transpose --
@@ -585,10 +639,29 @@ __global__ void prior_from_stats_kernel(const double* __restrict__ stats, float*
 using namespace rcb;
 
 extern "C" int rcb_set_step_state(rcb_step_state* dev, int64_t seed, int step, float adam_step_size,
-                                  float adam_bc2_sqrt, rcb_stream_t stream) {
+                                  float adam_bc2_sqrt, float beta_scalar, rcb_stream_t stream) {
   RCB_CHECK_ARG(dev != nullptr, "rcb_set_step_state: null pointer");
-  set_step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev, (long long)seed, step, adam_step_size, adam_bc2_sqrt);
+  set_step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev, (long long)seed, step, adam_step_size, adam_bc2_sqrt,
+                                                          beta_scalar);
   RCB_CHECK_LAUNCH("rcb_set_step_state");
+  return 0;
+}
+
+extern "C" int rcb_adam_flat(float* theta, const float* grad, float* m, float* v, int64_t n, float step_size,
+                             float bc2_sqrt, float b1, float b2, float eps, const rcb_step_state* dyn, rcb_stream_t stream) {
+  RCB_CHECK_ARG(theta && grad && m && v && n > 0, "rcb_adam_flat: bad arguments");
+  RCB_CHECK_ARG((((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "rcb_adam_flat: buffers must be 16-byte aligned");
+  const int64_t blocks = (n + 1023) / 1024;
+  RCB_CHECK_ARG(blocks < (1ll << 31), "rcb_adam_flat: vector too long");
+  adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, step_size, bc2_sqrt, b1, b2, eps, dyn);
+  RCB_CHECK_LAUNCH("rcb_adam_flat");
+  return 0;
+}
+
+extern "C" int rcb_step_stats(const float* sqerr, int n, double scale, const double* kl, double* out, rcb_stream_t stream) {
+  RCB_CHECK_ARG(sqerr && out && n > 0, "rcb_step_stats: bad arguments");
+  step_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sqerr, n, scale, kl, out);
+  RCB_CHECK_LAUNCH("rcb_step_stats");
   return 0;
 }
 

@@ -607,11 +607,14 @@ extern "C" int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream) {
       // enough CTAs for ~4 waves of 2 CTAs per SM, never more splits than chunks
       int splits = 1;
       while (splits < 64 && runs * splits < 148 * 8 && splits * 2 <= n_chunks) splits *= 2;
-      const size_t need = (size_t)a->n_pairs * ((size_t)splits * 12 + 4) + 64;
-      if (a->workspace_bytes >= (int64_t)need) {
+      // Workspace layout depends on its SIZE only, never on this call's n_pairs / splits: the arrival counters of
+      // `cap` pairs come first (they must be zero on entry and are left zero), the partial results after them.  A
+      // layout that moved with n_pairs would let one call's partial results land on the next call's counters.
+      const size_t cap = a->workspace_bytes > 64 ? ((size_t)a->workspace_bytes - 64) / (4 + 64 * 12) : 0;
+      if ((size_t)a->n_pairs <= cap) {
         uint8_t* w = reinterpret_cast<uint8_t*>(a->workspace);
-        unsigned* arrived = reinterpret_cast<unsigned*>(w);                      // zeroed by the caller once, kept zero
-        double* part_v = reinterpret_cast<double*>(w + (((size_t)a->n_pairs * 4 + 63) / 64) * 64);
+        unsigned* arrived = reinterpret_cast<unsigned*>(w);
+        double* part_v = reinterpret_cast<double*>(w + ((cap * 4 + 63) / 64) * 64);
         int* part_k = reinterpret_cast<int*>(part_v + (size_t)a->n_pairs * splits);
         cudaError_t e = cudaFuncSetAttribute(rec_encode_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("rcb_rec_encode: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }

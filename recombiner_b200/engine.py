@@ -274,57 +274,90 @@ class FitEngine:
 
     # ---------------------------------------------------------------- mappings --
     def set_mappings(self, A_list, up_state):
-        """Stage the frozen learned mappings on device: zero-padded A_l and A_l^T, and
-        the upsampler with its nearest-upsampling folded into the conv taps."""
+        """Stage the learned mappings on device: zero-padded A_l and A_l^T, and the upsampler with its
+        nearest-upsampling folded into the conv taps.  Buffers are allocated on the first call and refreshed in place
+        afterwards (prior training re-stages every step; captured steps keep the addresses)."""
+        conv_w = [up_state[f"conv{i}.weight"].detach().to(device=self.device, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
+        conv_b = [up_state[f"conv{i}.bias"].detach().to(device=self.device, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
+        first = self.A is None
+        if first:
+            self.A = [torch.zeros(c, _round_up(c, 4), device=self.device) for c in self.counts]
+            self.conv_w = [torch.empty_like(w) for w in conv_w]
+            self.conv_b = [torch.empty_like(b) for b in conv_b]
+        for l, (a, c) in enumerate(zip(A_list, self.counts)):
+            self.A[l][:, :c].copy_(a.detach())
+        for dst, src in zip(self.conv_w + self.conv_b, conv_w + conv_b):
+            dst.copy_(src)
+        self.restage_mappings()
+
+    def bind_mappings(self, A_padded, conv_w, conv_b):
+        """Use caller-owned tensors as the mapping parameters themselves (prior training: views of one flat parameter
+        vector that a fused Adam kernel updates in place): A_l as (c, round_up(c, 4)) with zero padding, conv weights
+        and biases in torch's layout.  `restage_mappings()` then derives everything else from them without a copy."""
+        self.A = list(A_padded)
+        self.conv_w, self.conv_b = list(conv_w), list(conv_b)
+        self._derived = False
+
+    def restage_mappings(self):
+        """Everything the kernels read besides A_l / conv biases, derived on the device from the current parameters:
+        A_l^T, fp16 copies, upsample-folded conv weights.  No allocation after the first call."""
         self.map_generation += 1
-        dev = self.device
-        st = stream()
-        self.A, self.AT, self.AT_h, self.A_h = [], [], [], []
-        for a, c in zip(A_list, self.counts):
-            a = a.detach().to(device=dev, dtype=torch.float32)
-            ld = _round_up(c, 4)
-            ap = torch.zeros(c, ld, device=dev); ap[:, :c] = a
-            at = torch.zeros(c, ld, device=dev); at[:, :c] = a.t()
-            self.A.append(ap); self.AT.append(at)
-            if self.tc and self.half_acts:   # fp16 copies for the reparameterisation GEMMs (K padded to whole 16-byte groups)
-                ah = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); ah[:, :c] = a.t().half()
-                self.AT_h.append(ah)
-                bh = torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev); bh[:, :c] = a.half()
-                self.A_h.append(bh)
-        self.conv_b = [up_state[f"conv{i}.bias"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
-        conv_w = [up_state[f"conv{i}.weight"].detach().to(device=dev, dtype=torch.float32).contiguous() for i in (1, 2, 3)]
-        self.w_eff, self.w_eff_t, self.w_eff_k = [None] * 3, [None] * 3, [None] * 3
+        dev, st = self.device, stream()
+        half = bool(self.tc and self.half_acts)
+        if not getattr(self, "_derived", False):
+            self.AT = [torch.zeros_like(a) for a in self.A]
+            self.AT_h, self.A_h = [], []
+            if half:   # fp16 copies for the reparameterisation GEMMs (K padded to whole 16-byte groups)
+                self.AT_h = [torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev) for c in self.counts]
+                self.A_h = [torch.zeros(c, _round_up(c, 8), dtype=torch.float16, device=dev) for c in self.counts]
+            self.w_eff, self.w_eff_t, self.w_eff_k = [None] * 3, [None] * 3, [None] * 3
+            for i, g in enumerate(self.geoms):
+                if i == 0 and self.dense1:
+                    rows = g.h * g.w * g.ic
+                    cols = g.h * g.fy * g.w * g.fx * g.oc          # dense fold: 1-D / 2-D grids only
+                    self.M1 = torch.empty(rows, cols, device=dev)
+                    self.M1T = torch.empty(cols, rows, device=dev)
+                    continue
+                taps = (1 if g.kz == 1 else 2) * (1 if g.ky == 1 else 2) * (1 if g.kx == 1 else 2)
+                n = g.fz * g.fy * g.fx * taps * g.ic * g.oc
+                self.w_eff[i] = torch.empty(n, device=dev)
+                self.w_eff_t[i] = torch.empty(n, device=dev)
+                if self.tc_conv:
+                    self.w_eff_k[i] = torch.empty(n, device=dev)
+            g3 = self.geoms[2]
+            self.f2_half = bool(self.tc_conv and self.tc and self.data_dim == 2 and g3.d == 1 and g3.fy == 2 and g3.fx == 2
+                                and g3.ky == 3 and g3.kx == 3 and g3.ic == 64 and g3.oc == 16 and g3.h >= 16
+                                and self.geoms[1].ic == 64)
+            self._half_staged = bool(self.f2_half and self.half_acts)      # fp16 weight copies exist (half_acts at staging time)
+            if self._half_staged:
+                self.w3_kh = torch.empty(self.w_eff_k[2].numel(), dtype=torch.float16, device=dev)
+                self.w2_kh = torch.empty(self.w_eff_k[1].numel(), dtype=torch.float16, device=dev)
+                if self.dense1:
+                    self.M1T_h = torch.empty(self.M1T.shape, dtype=torch.float16, device=dev)
+            if self.f2_half:
+                self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
+            self._derived = True
+        for l, c in enumerate(self.counts):
+            ld = self.A[l].shape[1]
+            check(self.lib.rcb_transpose(ptr(self.A[l]), ld, ptr(self.AT[l]), ld, c, c, st), "rcb_transpose")
+            if half and self.AT_h:
+                # (tiny, once per compression: torch copies of the two fp16 operand forms)
+                self.AT_h[l][:, :c].copy_(self.AT[l][:, :c])
+                self.A_h[l][:, :c].copy_(self.A[l][:, :c])
         for i, g in enumerate(self.geoms):
             if i == 0 and self.dense1:
-                rows = g.h * g.w * g.ic
-                cols = g.h * g.fy * g.w * g.fx * g.oc          # dense fold: 1-D / 2-D grids only
-                self.M1 = torch.empty(rows, cols, device=dev)
-                self.M1T = torch.empty(cols, rows, device=dev)
-                check(self.lib.rcb_fold_dense(ptr(conv_w[0]), C.byref(g), ptr(self.M1), ptr(self.M1T), st), "rcb_fold_dense")
+                check(self.lib.rcb_fold_dense(ptr(self.conv_w[0]), C.byref(g), ptr(self.M1), ptr(self.M1T), st), "rcb_fold_dense")
                 continue
-            taps = (1 if g.kz == 1 else 2) * (1 if g.ky == 1 else 2) * (1 if g.kx == 1 else 2)
-            n = g.fz * g.fy * g.fx * taps * g.ic * g.oc
-            self.w_eff[i] = torch.empty(n, device=dev)
-            self.w_eff_t[i] = torch.empty(n, device=dev)
-            check(self.lib.rcb_fold_poly(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff[i]), ptr(self.w_eff_t[i]), st), "rcb_fold_poly")
+            check(self.lib.rcb_fold_poly(ptr(self.conv_w[i]), C.byref(g), ptr(self.w_eff[i]), ptr(self.w_eff_t[i]), st), "rcb_fold_poly")
             if self.tc_conv:
-                self.w_eff_k[i] = torch.empty(n, device=dev)
-                check(self.lib.rcb_fold_poly_k(ptr(conv_w[i]), C.byref(g), ptr(self.w_eff_k[i]), st), "rcb_fold_poly_k")
+                check(self.lib.rcb_fold_poly_k(ptr(self.conv_w[i]), C.byref(g), ptr(self.w_eff_k[i]), st), "rcb_fold_poly_k")
         g3 = self.geoms[2]
-        self.f2_half = bool(self.tc_conv and self.tc and self.data_dim == 2 and g3.d == 1 and g3.fy == 2 and g3.fx == 2
-                            and g3.ky == 3 and g3.kx == 3 and g3.ic == 64 and g3.oc == 16 and g3.h >= 16
-                            and self.geoms[1].ic == 64)
-        self._half_staged = bool(self.f2_half and self.half_acts)      # fp16 weight copies exist (half_acts at staging time)
         if self._half_staged:
-            self.w3_kh = torch.empty(self.w_eff_k[2].numel(), dtype=torch.float16, device=dev)
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[2]), ptr(self.w3_kh), self.w3_kh.numel(), st), "rcb_to_half")
-            self.w2_kh = torch.empty(self.w_eff_k[1].numel(), dtype=torch.float16, device=dev)
             check(self.lib.rcb_to_half(ptr(self.w_eff_k[1]), ptr(self.w2_kh), self.w2_kh.numel(), st), "rcb_to_half")
             if self.dense1:
-                self.M1T_h = torch.empty(self.M1T.shape, dtype=torch.float16, device=dev)
                 check(self.lib.rcb_to_half(ptr(self.M1T), ptr(self.M1T_h), self.M1T_h.numel(), st), "rcb_to_half")
         if self.f2_half:
-            self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
             check(self.lib.rcb_fold_poly_bwd_f2(ptr(self.w_eff[2]), C.byref(g3), ptr(self.w3_bk), st), "rcb_fold_poly_bwd_f2")
 
     # -------------------------------------------------------------- workspaces --
@@ -556,10 +589,10 @@ class FitEngine:
         join()
         return ws
 
-    def set_step_state(self, buf: torch.Tensor, seed: int, step: int, adam: dict, t: int):
-        """Write the per-step scalars a captured fit step reads from device memory (rcb_step_state)."""
+    def set_step_state(self, buf: torch.Tensor, seed: int, step: int, adam: dict, t: int, beta_scalar: float = -1.0):
+        """Write the per-step scalars a captured step reads from device memory (rcb_step_state)."""
         check(self.lib.rcb_set_step_state(ptr(buf), seed, step, adam["lr"] / (1.0 - adam["b1"] ** t),
-                                          math.sqrt(1.0 - adam["b2"] ** t), stream()), "rcb_set_step_state")
+                                          math.sqrt(1.0 - adam["b2"] ** t), beta_scalar, stream()), "rcb_set_step_state")
 
     def _fork(self, fn):
         """Run fn on the side stream, ordered after everything queued so far on the current stream;
@@ -664,10 +697,11 @@ class FitEngine:
                 self._upconv_bwd(0, ws["d_a1"], None, ws["d_lpe"], citems)
         join()
 
-    def backward_mappings(self, ws, rows: int, S: int):
+    def backward_mappings(self, ws, rows: int, S: int, out=None):
         """Gradients of the learned mappings (prior training): dA_l = hw_l^T d_wt_l, and the
         upsampler's conv weights/biases through the adjoints of the folds.  Call after
-        backward_features (it consumes d_pe, d_a2, d_a1, d_wt)."""
+        backward_features (it consumes d_pe, d_a2, d_a1, d_wt).  `out` = {"A": [...], "conv1.weight": ..., ...}
+        gives the destination tensors (views of one flat gradient vector); otherwise they live in the workspace."""
         if ws.get("a2_is_half"):
             raise KernelError("the mapping gradients read the upsampler activations in fp32: set engine.half_acts = False")
         items = rows * S
@@ -675,15 +709,24 @@ class FitEngine:
         st = stream()
         dev = self.device
         g = ws.setdefault("map_grads", {})
-        if not g:
-            g["A"] = [torch.zeros(c, _round_up(c, 4), device=dev) for c in self.counts]
+        if not g or g.get("_out") is not out:
+            keep = {k: v for k, v in g.items() if k.startswith("eff") or k == "dM1"}
+            g.clear()
+            g.update(keep)
+            g["_out"] = out
+            if out is not None:
+                g.update({k: v for k, v in out.items()})
+            else:
+                g["A"] = [torch.zeros(c, _round_up(c, 4), device=dev) for c in self.counts]
             for i, geo in enumerate(self.geoms):
                 kshape = (geo.oc, geo.ic) + (geo.kz, geo.ky, geo.kx)[3 - self.data_dim:]
-                g[f"conv{i + 1}.weight"] = torch.zeros(*kshape, device=dev)
-                g[f"conv{i + 1}.bias"] = torch.zeros(geo.oc, device=dev)
+                if out is None:
+                    g[f"conv{i + 1}.weight"] = torch.zeros(*kshape, device=dev)
+                    g[f"conv{i + 1}.bias"] = torch.zeros(geo.oc, device=dev)
                 taps = (1 if geo.kz == 1 else 2) * (1 if geo.ky == 1 else 2) * (1 if geo.kx == 1 else 2)
-                g[f"eff{i}"] = torch.zeros(geo.fz * geo.fy * geo.fx * taps * geo.ic * geo.oc, device=dev)
-            if self.dense1:
+                if f"eff{i}" not in g:
+                    g[f"eff{i}"] = torch.zeros(geo.fz * geo.fy * geo.fx * taps * geo.ic * geo.oc, device=dev)
+            if self.dense1 and "dM1" not in g:
                 g["dM1"] = torch.zeros_like(self.M1)
         with self.section("reparam_wgrad"):
             if self.tc:

@@ -100,6 +100,58 @@ from ._lib import KernelError, check as _check, ptr as _ptr, stream as _stream
 from .utils import count_net_params
 
 
+class SharedMappings:
+    """The learned mappings of prior training (A_l of LinearTransform, conv weights / biases of Upsample) as ONE flat
+    fp32 parameter vector in the layout the kernels read, with a gradient vector and Adam moments of the same layout.
+
+    The weight-gradient kernels write straight into `grad` (no per-tensor copies), data-parallel ranks exchange it with
+    a single all-reduce, and `rcb_adam_flat` steps `theta` in place -- the reference's `Adam(list(A) + list(upsample))`
+    (prior_model.py:224-227) without per-step staging.  A_l is stored padded to (c, round_up(c, 4)) (16-byte rows for
+    the tensor-core GEMMs); the padding columns have zero gradient and stay zero."""
+
+    def __init__(self, engine, linear_transform, upsample_net):
+        dev = engine.device
+        self.lt, self.up = linear_transform, upsample_net
+        self.segments = []                     # (name, parameter, offset, stored shape, logical column count)
+        off = 0
+        for l, (p, c) in enumerate(zip(linear_transform.A, engine.counts)):
+            ld = (c + 3) // 4 * 4
+            self.segments.append((f"A{l}", p, off, (c, ld), c))
+            off += c * ld
+        for name, p in upsample_net.named_parameters():
+            off = (off + 3) // 4 * 4
+            self.segments.append((name, p, off, tuple(p.shape), None))
+            off += p.numel()
+        self.n = (off + 3) // 4 * 4
+        self.theta, self.grad, self.m, self.v = (torch.zeros(self.n, device=dev) for _ in range(4))
+        self.t = 0
+        view = lambda buf, o, shape: buf[o:o + int(np.prod(shape))].view(shape)
+        self.params = {nm: view(self.theta, o, shp) for nm, _, o, shp, _ in self.segments}
+        self.grads = {nm: view(self.grad, o, shp) for nm, _, o, shp, _ in self.segments}
+        n_a = len(engine.counts)
+        self.grad_out = {"A": [self.grads[f"A{l}"] for l in range(n_a)]}
+        self.grad_out.update({nm: self.grads[nm] for nm, _, _, _, c in self.segments if c is None})
+        engine.bind_mappings([self.params[f"A{l}"] for l in range(n_a)],
+                             [self.params[f"conv{i}.weight"] for i in (1, 2, 3)],
+                             [self.params[f"conv{i}.bias"] for i in (1, 2, 3)])
+
+    def load(self):
+        """modules -> theta; fresh Adam moments (the reference re-creates its optimiser on every train() call)."""
+        with torch.no_grad():
+            for nm, p, _, _, c in self.segments:
+                dst = self.params[nm]
+                (dst[:, :c] if c is not None else dst).copy_(p.detach())
+        self.m.zero_(); self.v.zero_()
+        self.t = 0
+
+    def store(self):
+        """theta -> modules (so checkpoints pickle the trained values)."""
+        with torch.no_grad():
+            for nm, p, _, _, c in self.segments:
+                src = self.params[nm]
+                p.copy_(src[:, :c] if c is not None else src)
+
+
 class PriorBNNmodel(nn.Module):
     """All training rows' factorised Gaussian posteriors, fitted jointly with the shared
     mappings (LinearTransform, Upsample) against the current prior.
@@ -231,13 +283,24 @@ class PriorBNNmodel(nn.Module):
 
     def _set_prior(self, prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc=None, prior_h_scale=None,
                    prior_hh_loc=None, prior_hh_scale=None):
-        f = lambda t: t.reshape(-1).to(self.device, torch.float32).contiguous()
-        lv = self._lv
-        lv.p_loc = torch.cat([f(prior_loc), f(prior_lpe_loc)]).contiguous()
-        lv.p_log_scale = torch.cat([f(prior_scale), f(prior_lpe_scale)]).contiguous()
+        """Copy the prior into the levels' persistent buffers (captured steps hold their addresses)."""
+        f = lambda t: t.reshape(-1).to(self.device, torch.float32)
+        W = self._W
+
+        def put(lv, loc_parts, scale_parts):
+            n = sum(p.numel() for p in loc_parts)
+            if lv.p_loc.numel() != n or not getattr(lv, "_prior_owned", False):
+                lv.p_loc, lv.p_log_scale = torch.empty(n, device=self.device), torch.empty(n, device=self.device)
+                lv._prior_owned = True
+            o = 0
+            for pl, ps in zip(loc_parts, scale_parts):
+                lv.p_loc[o:o + pl.numel()].copy_(f(pl))
+                lv.p_log_scale[o:o + ps.numel()].copy_(f(ps))
+                o += pl.numel()
+        put(self._lv, [prior_loc, prior_lpe_loc], [prior_scale, prior_lpe_scale])
         if self.patch:
-            self._levels[1].p_loc, self._levels[1].p_log_scale = f(prior_h_loc), f(prior_h_scale)
-            self._levels[2].p_loc, self._levels[2].p_log_scale = f(prior_hh_loc), f(prior_hh_scale)
+            put(self._levels[1], [prior_h_loc], [prior_h_scale])
+            put(self._levels[2], [prior_hh_loc], [prior_hh_scale])
 
     def forward(self, x, linear_transform, upsample_net, gradient_through_A=True, eps=None):
         """Single-sample reconstruction (rows, pixels, out) (prior_model.py:129-179).  Evaluation
@@ -303,16 +366,58 @@ class PriorBNNmodel(nn.Module):
         mse = ws["sqerr"].sum() / (eng.pix * eng.out)
         return mse, kl / max(float(kl_beta), 1e-300), grads
 
+    def _shared(self, linear_transform, upsample_net) -> SharedMappings:
+        sm = self.__dict__.get("_shared_mappings")
+        if sm is None or sm.lt is not linear_transform or sm.up is not upsample_net:
+            sm = self._shared_mappings = SharedMappings(self.engine, linear_transform, upsample_net)
+            self._step_graphs = {}
+        return sm
+
+    def _step_body(self, sm, x, y, noise, cfg, coef, training_mappings, kl_step, world):
+        """One full-batch step on the current stream: re-derive the staged mappings from theta, forward, loss,
+        backward, mapping gradients into sm.grad, [all-reduce], posterior KL-gradient + Adam, mapping Adam."""
+        import torch.distributed as dist
+        eng, N = self.engine, self.train_size
+        eng.restage_mappings()
+        ws = eng.forward_features(self._levels, 1, noise)
+        eng.mlp(ws, N, 1, x, mode=1, y=y, coef=coef)
+        eng.backward_features(ws, N, 1)
+        work = None
+        if training_mappings:
+            eng.backward_mappings(ws, N, 1, out=sm.grad_out)
+            if world > 1:        # ONE collective for all shared-mapping gradients, overlapped with the posterior update
+                work = dist.all_reduce(sm.grad, op=dist.ReduceOp.SUM, async_op=True)
+        kl_step.zero_()
+        for l in self._levels:
+            eng.update(l, ws, 1, noise, with_data_grads=True, adam=cfg, kl_out=kl_step, rows=N)
+        if training_mappings:
+            if work is not None:
+                work.wait()
+            t = max(self._levels[0].adam["t"], 1)
+            _check(eng.lib.rcb_adam_flat(_ptr(sm.theta), _ptr(sm.grad), _ptr(sm.m), _ptr(sm.v), sm.n,
+                                         cfg["lr"] / (1.0 - cfg["b1"] ** t), _math.sqrt(1.0 - cfg["b2"] ** t),
+                                         cfg["b1"], cfg["b2"], cfg["eps"], _ptr(eng.step_state), _stream()), "rcb_adam_flat")
+        return ws
+
     def train(self, n_epoch=True, lr=2e-4, x=None, y=None, prior_loc=None, prior_scale=None, prior_lpe_loc=None,
               prior_lpe_scale=None, prior_h_loc=None, prior_h_scale=None, prior_hh_loc=None, prior_hh_scale=None,
               linear_transform=None, upsample_net=None, kl_beta=1e-8, training_mappings=True, verbose=False):
         """n_epoch full-batch Adam steps on loss = N*mean((y_hat-y)^2) + kl_beta*sum KL over the
         posteriors and (optionally) the mappings (prior_model.py:202-262).  Returns
-        (last mse / N, KL / N, list of per-step ELBOs)."""
+        (last mse / N, KL / N, list of per-step ELBOs).
+
+        Device-resident: the mappings live in one flat parameter vector (SharedMappings), nothing is allocated per
+        step, the per-step loss terms stay on the device (one read-back per call), and on a single GPU the whole step
+        is replayed from a captured CUDA graph with the noise key, Adam bias corrections and kl_beta in device memory
+        (rcb_step_state).  With several ranks the step is launched kernel by kernel (no NCCL call inside a captured
+        graph) and the single all-reduce of the flat gradient vector runs beside the posterior update."""
         if isinstance(n_epoch, bool):           # nn.Module.train(mode) / .eval()
             return super().train(n_epoch)
+        import ctypes as C
+        import os
         import torch.distributed as dist
-        eng, lv, N = self.engine, self._lv, self.train_size
+        from ._lib import StepState
+        eng, N = self.engine, self.train_size
         x = x.to(self.device)
         y = y.to(self.device, torch.float32).contiguous()
         self._set_prior(prior_loc, prior_scale, prior_lpe_loc, prior_lpe_scale, prior_h_loc, prior_h_scale,
@@ -320,51 +425,62 @@ class PriorBNNmodel(nn.Module):
         for l in self._levels:
             l.beta_scalar = float(kl_beta)
             l.reset_adam()                       # the reference re-creates Adam on every call (:224-227)
-        shared = list(linear_transform.parameters()) + list(upsample_net.parameters())
-        for p in shared:
-            p.requires_grad_(True)
-        opt = torch.optim.Adam(shared, lr) if training_mappings else None
+        sm = self._shared(linear_transform, upsample_net)
+        sm.load()
         cfg = dict(lr=float(lr), b1=0.9, b2=0.999, eps=1e-8)
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         n_total = self.global_rows(0)            # true row count over all shards (they may be uneven)
         coef = 2.0 / (eng.pix * eng.out)
-        stats = torch.zeros(n_epoch, 2, dtype=torch.float64, device=self.device)     # per step: (mse*N, beta*KL)
-        kl_step = torch.zeros(1, dtype=torch.float64, device=self.device)
+        stats = torch.zeros(max(n_epoch, 1), 2, dtype=torch.float64, device=self.device)     # per step: (mse*N, beta*KL)
+        kl_step = self.__dict__.setdefault("_kl_step", torch.zeros(1, dtype=torch.float64, device=self.device))
         base_noise = self._noise()
+        Noise = type(base_noise)
+        use_graph = (os.environ.get("RECOMBINER_GRAPH", "1") != "0" and eng.timer is None
+                     and not torch.cuda.is_current_stream_capturing())
+        xt, x_stride = eng.prepare_x(x)
+        key = (xt.data_ptr(), x_stride, y.data_ptr(), tuple(y.shape), bool(training_mappings), world, cfg["b1"], cfg["b2"],
+               cfg["eps"], self.row_offset, id(sm)) + tuple(v for l in self._levels for v in (l.p_loc.data_ptr(), l.loc.data_ptr()))
+        graphs = self.__dict__.setdefault("_step_graphs", {})
+        state = self.__dict__.setdefault("_step_state", torch.zeros(C.sizeof(StepState), dtype=torch.uint8, device=self.device))
         it = range(n_epoch)
         if verbose:
             from tqdm import tqdm
             it = tqdm(it)
-        up_names = [k for k, _ in upsample_net.named_parameters()]
+        ws = None
         for i in it:
-            eng.set_mappings(list(linear_transform.A), upsample_net.state_dict())
-            noise = type(base_noise)(seed=base_noise.seed, step=i, row_offset=self.row_offset)
-            ws = eng.forward_features(self._levels, 1, noise)
-            eng.mlp(ws, N, 1, x, mode=1, y=y, coef=coef)
-            eng.backward_features(ws, N, 1)
-            if training_mappings:
-                g = eng.backward_mappings(ws, N, 1)
-                flat = [g["A"][l][:, :c].contiguous() for l, c in enumerate(eng.counts)] + [g[k] for k in up_names]
-                if world > 1:
-                    for t in flat:           # shared mappings: gradients are summed over all rows
-                        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-                for p, t in zip(shared, flat):
-                    p.grad = t.reshape(p.shape).clone()
-            kl_step.zero_()
-            for l in self._levels:
-                eng.update(l, ws, 1, noise, with_data_grads=True, adam=cfg, kl_out=kl_step, rows=N)
-            if opt is not None:
-                opt.step()
-            stats[i, 0] = ws["sqerr"].sum().double() / (eng.pix * eng.out)
-            stats[i, 1] = kl_step[0]
+            noise = Noise(seed=base_noise.seed, step=i, row_offset=self.row_offset)
+            entry = graphs.get(key) if use_graph else None
+            if use_graph and entry is None and key in graphs and world == 1:
+                # second sight of this configuration: capture the step (single GPU: all of it)
+                graph = torch.cuda.CUDAGraph()
+                eng.step_state = state
+                try:
+                    with torch.cuda.graph(graph):
+                        ws = self._step_body(sm, x, y, noise, cfg, coef, training_mappings, kl_step, world)
+                finally:
+                    eng.step_state = None
+                entry = graphs[key] = (graph, ws)
+            if entry is not None:
+                graph, ws = entry
+                eng.set_step_state(state, noise.seed, noise.step, cfg, i + 1, beta_scalar=float(kl_beta))
+                graph.replay()
+                for l in self._levels:
+                    l.adam["t"] = i + 1
+            else:
+                if use_graph and key not in graphs:
+                    graphs[key] = None           # first sight: run eagerly (sizes workspaces, TMA maps)
+                ws = self._step_body(sm, x, y, noise, cfg, coef, training_mappings, kl_step, world)
+            _check(eng.lib.rcb_step_stats(_ptr(ws["sqerr"]), N, 1.0 / (eng.pix * eng.out), _ptr(kl_step),
+                                          stats.data_ptr() + 16 * i, _stream()), "rcb_step_stats")
+        sm.store()
         if world > 1:
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         kl_final = self._kl(1.0)[0]
         if world > 1:
             dist.all_reduce(kl_final, op=dist.ReduceOp.SUM)
         stats = stats.cpu()
-        elbo = (-(stats[:, 0] + stats[:, 1])).tolist()
-        mse_last = float(stats[-1, 0]) if n_epoch > 0 else float("nan")
+        elbo = (-(stats[:n_epoch, 0] + stats[:n_epoch, 1])).tolist()
+        mse_last = float(stats[n_epoch - 1, 0]) if n_epoch > 0 else float("nan")
         return mse_last / n_total, float(kl_final.item()) / n_total, elbo
 
 

@@ -9,6 +9,7 @@ needs (D, seed) to rebuild the table of a block.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -66,11 +67,11 @@ _WORKSPACES: Dict = {}
 
 def _workspace(device, n_pairs: int) -> torch.Tensor:
     """Scratch of the staged scoring kernel, one per (device, stream): zero when allocated, left zero by every launch."""
-    need = n_pairs * 772 + 64
+    need = n_pairs * 772 + 128
     key = (str(device), stream())
     ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < need:
-        ws = _WORKSPACES[key] = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+    if ws is None or ws.numel() < need:      # a new (zeroed) buffer: the kernel's layout depends on the size only
+        ws = _WORKSPACES[key] = torch.zeros(max(2 * need, 1 << 20), dtype=torch.uint8, device=device)
     return ws
 
 
@@ -100,7 +101,7 @@ def encode(lv, tables_ptr: torch.Tensor, gumbel: torch.Tensor, q_scale: torch.Te
         logw = torch.empty(n_pairs, n_cand, dtype=torch.float64, device=dev)
     a.logw_out = ptr(logw)
     a.n_pairs, a.P, a.G, a.n_cand, a.max_D, a.apply = n_pairs, lv.P, lv.G, n_cand, max_D, int(apply)
-    if staged:
+    if staged and os.environ.get("RECOMBINER_REC_STAGED", "1") != "0":
         ws = _workspace(dev, n_pairs)
         a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
     check(lib.rcb_rec_encode(C.byref(a), stream()), "rcb_rec_encode")

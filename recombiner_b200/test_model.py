@@ -553,6 +553,10 @@ class TestBNNmodel(nn.Module):
         if bufs is None or bufs[0].shape != xs.shape or bufs[1].shape != y.shape:
             bufs = st["bufs"][b] = (torch.empty(xs.shape, dtype=torch.float32, device=self.device),
                                     torch.empty(y.shape, dtype=torch.float32, device=self.device))
+            # Fresh blocks from the caching allocator may be memory that kernels already queued on the compute stream
+            # still read (a tensor freed by Python is reusable in stream order on ITS stream only): the copy stream
+            # must not write into them before that work is over.
+            st["stream"].wait_stream(torch.cuda.current_stream())
         main = torch.cuda.current_stream()
         with torch.cuda.stream(st["stream"]):
             st["stream"].wait_event(st["done"][b])         # the steps that last read this set are over
