@@ -244,6 +244,14 @@ typedef struct {
   void* d_wt_h;         /* optional (rcb_mlp_tc, mode 1): the weight gradients are written here as fp16 (clamped to the
                            fp16 range) INSTEAD of d_wt, for an fp16-operand data-gradient GEMM (rcb_gemm_tc_batch) */
   int pe_half;          /* rcb_mlp_tc only: pe holds fp16 values (written by rcb_upconv_fwd_tc_hh) */
+  /* rcb_mlp_tc only, optional: generate the Fourier inputs from the pixel index instead of reading xt.  x_tab is the
+   * per-axis table rcb_fourier_table writes: for axis a and coordinate index i, 2*x_nfreq floats at
+   * x_tab[x_off[a] + i * 2 * x_nfreq] = cos(pi c_i w_j), j < x_nfreq, then sin(pi c_i w_j)  (data/image.py:24-27 on the
+   * pixel-centre grid of utils.py:265-284).  The pixel index is row-major over x_size[0 .. x_axes); n_f = 2 * x_axes *
+   * x_nfreq.  The (n_f, pix) tensor X -- identical for every datapoint -- is then never read. */
+  const float* x_tab;
+  int x_axes, x_nfreq;
+  int x_size[3], x_off[3];
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
 /* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA (one 128-thread group
@@ -255,6 +263,12 @@ int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
  * mode 1 needs coef > 0; in mode 2 `coef` (if > 0) is a scale applied to dy inside the kernel and
  * removed from the outputs (pick ~1/max|dy| so that fp16 keeps its 10-bit mantissa). */
 int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream);
+
+/* Per-axis Fourier feature table for rcb_mlp_args.x_tab, generated on the device from coordinate indices with the
+ * reference's fp32 arithmetic: c_i = -1 + 2 * ((0.5 + i) / size) (utils.py:265-284), t = (c_i * w_j) * pi_f32,
+ * tab[i * 2 * n_freq + j] = cos(t), tab[i * 2 * n_freq + n_freq + j] = sin(t).  freq: HOST array of n_freq <= 8
+ * frequencies w_j = exp(linspace(0, ln 1024, n_freq)) as the loaders compute them (data/image.py:25). */
+int rcb_fourier_table(float* tab, int size, const float* freq, int n_freq, rcb_stream_t stream);
 
 /* Polyphase conv weight gradient on tcgen05 (2-D grids, k > 1): d_w_eff[phase][tap][ic][oc] as produced by
  * rcb_upconv_wgrad, from channel-major copies srcT [3 x-shifts][ic][items*h*w] (rcb_transpose_xshift) and doutT

@@ -34,7 +34,8 @@ class MlpArgs(C.Structure):
     _fields_ = [(n, P) for n in ("wt", "xt", "pe", "y", "dy", "y_pred", "d_pe", "d_wt", "sqerr", "pe_base")] + \
                [("x_row_stride", I64), ("pitch_z", I64), ("pitch_y", I64)] + \
                [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode", "ph", "pw")] + \
-               [("coef", F32), ("w0", F32), ("d_wt_h_scale", F32), ("ld_wh", I32), ("d_wt_h", P), ("pe_half", I32)]
+               [("coef", F32), ("w0", F32), ("d_wt_h_scale", F32), ("ld_wh", I32), ("d_wt_h", P), ("pe_half", I32),
+                ("x_tab", P), ("x_axes", I32), ("x_nfreq", I32), ("x_size", I32 * 3), ("x_off", I32 * 3)]
 
 
 class UpdateArgs(C.Structure):
@@ -98,6 +99,7 @@ SIGNATURES = {
     "rcb_colsum": [P, I64, I32, I32, P, P],
     "rcb_mlp": [C.POINTER(MlpArgs), P],
     "rcb_mlp_tc": [C.POINTER(MlpArgs), P],
+    "rcb_fourier_table": [P, I32, C.POINTER(F32), I32, P],
     "rcb_transpose": [P, I64, P, I64, I32, I32, P],
     "rcb_transpose_phases": [P, P, I64, I32, I32, I32, I32, I32, P],
     "rcb_transpose_xshift": [P, P, I64, I32, I32, P],

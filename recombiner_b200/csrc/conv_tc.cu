@@ -1729,17 +1729,24 @@ extern "C" int rcb_upconv_bwd_tc_ah(const float* d_out, const float* w_eff, cons
 // are added atomically (like the SIMT kernel they replace).
 namespace rcb {
 
-constexpr int WG_MAX_SEG = 16, WG_MAX_SHIFT = 9;
+constexpr int WG_MAX_SEG = 16, WG_MAX_SHIFT = 9, WG_MAX_GROUPS = 16;
+
+// one group of phases handled by a CTA (blockIdx.y): its first phase and its set of distinct source shifts
+struct WgGroup {
+  int phase0, nshift;
+  int shift_dy[WG_MAX_SHIFT], shift_dx[WG_MAX_SHIFT];
+  int seg_shift[WG_MAX_SEG];          // per CTA-local segment: index of its shift
+};
 
 struct WgTcArgs {
   int h, w, fy, fx, ic, oc, items;
   int kb_per_item;                    // K block = 32 consecutive source pixels of the flattened (y, x) grid of one item
   int kb_total, kb_per_cta;
-  int phases_per_cta, nshift, phase0; // segments per CTA = 4 * phases_per_cta, first phase of this launch
-  int shift_dy[WG_MAX_SHIFT], shift_dx[WG_MAX_SHIFT];
-  int seg_shift[WG_MAX_SEG];          // per CTA-local segment: index of its shift
-  int a_bytes, b_bytes, stage_bytes, bar_off;
+  int phases_per_cta;                 // segments per CTA = 4 * phases_per_cta
+  int a_bytes, b_bytes, stage_bytes, bar_off;     // stage sized for the group with the most shifts
   float* d_w_eff;
+  WgGroup groups[WG_MAX_GROUPS];      // all phase groups run in ONE launch (grid.y): they share the SMs instead of
+                                      // queueing behind one another on the stream
 };
 
 __global__ void __launch_bounds__(TC_THREADS)
@@ -1753,7 +1760,8 @@ upconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nseg = 4 * a.phases_per_cta;
-  const int ph0 = a.phase0;
+  const WgGroup& gr = a.groups[blockIdx.y];
+  const int ph0 = gr.phase0;
   const int kb0 = blockIdx.x * a.kb_per_cta;
   const int nkb = min(a.kb_per_cta, a.kb_total - kb0);
   uint32_t tmem_cols = 32;
@@ -1783,14 +1791,14 @@ upconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(&empty[s], ((kb >> 1) & 1) ^ 1);
       if (elect_one()) {
         uint8_t* st = smem + s * a.stage_bytes;
-        mbar_expect_tx(&full[s], (uint32_t)(a.nshift * a.a_bytes + a.phases_per_cta * a.b_bytes));
+        mbar_expect_tx(&full[s], (uint32_t)(gr.nshift * a.a_bytes + a.phases_per_cta * a.b_bytes));
         const int p0 = kbi * 32;
         // a line shift is +-w pixels of the flattened grid; pixels before the first / after the last line of the item
         // are outside the tensor dimension and come back as zeros
-        for (int i = 0; i < a.nshift; ++i)
-          tma_load_3d(&tmA, &full[s], st + i * a.a_bytes, p0 + a.shift_dy[i] * a.w, item, (a.shift_dx[i] + 1) * a.ic);
+        for (int i = 0; i < gr.nshift; ++i)
+          tma_load_3d(&tmA, &full[s], st + i * a.a_bytes, p0 + gr.shift_dy[i] * a.w, item, (gr.shift_dx[i] + 1) * a.ic);
         for (int p = 0; p < a.phases_per_cta; ++p)
-          tma_load_3d(&tmB, &full[s], st + a.nshift * a.a_bytes + p * a.b_bytes, p0, item * (a.fy * a.fx) + ph0 + p, 0);
+          tma_load_3d(&tmB, &full[s], st + gr.nshift * a.a_bytes + p * a.b_bytes, p0, item * (a.fy * a.fx) + ph0 + p, 0);
       }
       __syncwarp();
       if (++kbi == a.kb_per_item) { kbi = 0; ++item; }
@@ -1805,8 +1813,8 @@ upconv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (elect_one()) {
         const uint32_t st = smem_u32(smem + s * a.stage_bytes);
         for (int sg = 0; sg < nseg; ++sg) {
-          const uint64_t da = smem_desc_sw128(st + a.seg_shift[sg] * a.a_bytes);
-          const uint64_t db = smem_desc_sw128(st + a.nshift * a.a_bytes + (sg >> 2) * a.b_bytes);
+          const uint64_t da = smem_desc_sw128(st + gr.seg_shift[sg] * a.a_bytes);
+          const uint64_t db = smem_desc_sw128(st + gr.nshift * a.a_bytes + (sg >> 2) * a.b_bytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_tf32(tmem_base + (uint32_t)(sg * a.oc), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
@@ -1892,8 +1900,10 @@ extern "C" int rcb_upconv_wgrad_tc(const float* srcT, const float* doutT, float*
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int ngroups = nphase / ppc;
-  for (int grp = 0; grp < ngroups; ++grp) {     // one launch per phase group: each has its own set of distinct shifts
-    WgTcArgs b = a;
+  RCB_CHECK_ARG(ngroups <= WG_MAX_GROUPS, "rcb_upconv_wgrad_tc: too many phase groups (%d)", ngroups);
+  int max_shift = 0;
+  for (int grp = 0; grp < ngroups; ++grp) {     // each phase group has its own set of distinct shifts
+    WgGroup& b = a.groups[grp];
     b.phase0 = grp * ppc;
     b.nshift = 0;
     for (int lp = 0; lp < ppc; ++lp)
@@ -1908,16 +1918,17 @@ extern "C" int rcb_upconv_wgrad_tc(const float* srcT, const float* doutT, float*
         }
         b.seg_shift[lp * 4 + t] = idx;
       }
-    b.stage_bytes = b.nshift * b.a_bytes + ppc * b.b_bytes;
-    b.bar_off = 2 * b.stage_bytes;
-    const int smem_total = b.bar_off + 256 + 1024;
-    RCB_CHECK_ARG(smem_total <= 200 * 1024, "rcb_upconv_wgrad_tc: stage does not fit shared memory");
-    int ksplit = (sms + ngroups - 1) / ngroups;  // the phase groups run concurrently: share the SMs
-    if (ksplit > b.kb_total) ksplit = b.kb_total;
-    b.kb_per_cta = (b.kb_total + ksplit - 1) / ksplit;
-    const int nct = (b.kb_total + b.kb_per_cta - 1) / b.kb_per_cta;
-    upconv_wgrad_tc_kernel<<<nct, TC_THREADS, smem_total, st>>>(tmA, tmB, b);
-    RCB_CHECK_LAUNCH("rcb_upconv_wgrad_tc");
+    if (b.nshift > max_shift) max_shift = b.nshift;
   }
+  a.stage_bytes = max_shift * a.a_bytes + ppc * a.b_bytes;
+  a.bar_off = 2 * a.stage_bytes;
+  const int smem_total = a.bar_off + 256 + 1024;
+  RCB_CHECK_ARG(smem_total <= 200 * 1024, "rcb_upconv_wgrad_tc: stage does not fit shared memory");
+  int ksplit = (sms + ngroups - 1) / ngroups;    // the phase groups run concurrently (grid.y): they share the SMs
+  if (ksplit > a.kb_total) ksplit = a.kb_total;
+  a.kb_per_cta = (a.kb_total + ksplit - 1) / ksplit;
+  const int nct = (a.kb_total + a.kb_per_cta - 1) / a.kb_per_cta;
+  upconv_wgrad_tc_kernel<<<dim3(nct, ngroups), TC_THREADS, smem_total, st>>>(tmA, tmB, a);
+  RCB_CHECK_LAUNCH("rcb_upconv_wgrad_tc");
   return 0;
 }

@@ -47,7 +47,8 @@ struct Sm {
   static constexpr int WF = ONES + XP;              // 3 forward B tiles  [j][i]
   static constexpr int WB = WF + 3 * WT;            // 3 backward B tiles [i][j] (layer 0: the 16 pe inputs)
   static constexpr int W3 = WB + 3 * WT;            // output B tile [16 (OUT used)][32]
-  static constexpr int PLAIN = W3 + WT;           // floats: [0,96) w0*b_l, [96,100) b3, [104,108) sq partials, [128,256) W3[j][4]
+  static constexpr int WF0B = W3 + WT;              // forward B tile of layer 0 for input features 32..47 (34-input INRs: video)
+  static constexpr int PLAIN = WF0B + WT;         // floats: [0,96) w0*b_l, [96,100) b3, [104,108) sq partials, [128,256) W3[j][4]
   static constexpr int BAR = PLAIN + 1024;
   static constexpr int TOTAL = BAR + 64;
 };
@@ -91,6 +92,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem: lane = row, one fp32 column per K element] * B[smem descriptor], TF32
@@ -184,14 +189,20 @@ __device__ long long rcb_prof_buf[4 * 1024];
 #define PROF(id) do {} while (0)
 #endif
 
-template <int OUT, int MODE>
+// F = Fourier features per pixel: 16 (32 INR inputs; cifar, kodak, audio, protein) or 18 (34 inputs; video).  With 34
+// inputs the first layer runs three K = 16 steps (features 32, 33 live in a third, zero-padded K block) and the second
+// 32-feature atom of dW0's A operand is a per-tile block [x32, x33, 1, 0, ...] instead of the shared bias-only block.
+// D = signal dimensionality (1, 2, 3): only used to generate the Fourier inputs from the pixel index (a.x_tab).
+template <int OUT, int MODE, int F, int D>
 __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #ifdef RCB_MLP_PROFILE
   int prof_n = 0;
   const int prof_slot = (blockIdx.x == 3000 && (threadIdx.x == 32 || threadIdx.x == 160)) ? (threadIdx.x == 32 ? 0 : 1) : -1;
 #endif
-  constexpr int F = 16, HID = 32, NPE = 16;
-  constexpr int off0 = 0, off1 = HID * (32 + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
+  constexpr int HID = 32, NPE = 16, IN = F + NPE;
+  constexpr bool WIDE = IN > 32;
+  static_assert(F == 16 || F == 18, "16 or 18 Fourier features");
+  constexpr int off0 = 0, off1 = HID * (IN + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   float* plain = (float*)(smem + Sm::PLAIN);
@@ -225,12 +236,48 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     return (int64_t)z * a.pitch_z + (int64_t)yy * a.pitch_y + xx;
   };
   // the 32 input features of pixel gp: 16 Fourier features, 16 positional encodings (raw fp32 patterns)
-  auto load_x0 = [&](int gp, uint32_t (&v)[32]) {
+  constexpr int NFQ = F / (2 * D);          // frequencies per axis
+  static_assert(2 * D * NFQ == F, "Fourier feature count does not match the dimensionality");
+  auto load_x0 = [&](int gp, uint32_t (&v)[IN]) {
     const bool ok = gp < pix;
+    if (a.x_tab) {
+      // generated inputs: per-axis rows [cos(pi c w_0..), sin(pi c w_0..)] looked up by the coordinate indices of the
+      // pixel; feature order [cos axis 0 .., cos axis 1 .., sin axis 0 .., sin axis 1 ..] (data/image.py:25-27)
+      int rem = ok ? gp : 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
+      for (int ax = D - 1; ax >= 0; --ax) {
+        const int sz = a.x_size[ax];
+        const int i = ax == 0 ? rem : rem % sz;
+        rem = ax == 0 ? 0 : rem / sz;
+        const float* row = a.x_tab + a.x_off[ax] + i * (2 * NFQ);
+        if (NFQ % 4 == 0) {
+#pragma unroll
+          for (int c = 0; c < NFQ / 4; ++c) {
+            const float4 cs4 = __ldg(reinterpret_cast<const float4*>(row) + c);
+            const float4 sn4 = __ldg(reinterpret_cast<const float4*>(row + NFQ) + c);
+            v[ax * NFQ + 4 * c] = __float_as_uint(cs4.x); v[ax * NFQ + 4 * c + 1] = __float_as_uint(cs4.y);
+            v[ax * NFQ + 4 * c + 2] = __float_as_uint(cs4.z); v[ax * NFQ + 4 * c + 3] = __float_as_uint(cs4.w);
+            v[D * NFQ + ax * NFQ + 4 * c] = __float_as_uint(sn4.x); v[D * NFQ + ax * NFQ + 4 * c + 1] = __float_as_uint(sn4.y);
+            v[D * NFQ + ax * NFQ + 4 * c + 2] = __float_as_uint(sn4.z); v[D * NFQ + ax * NFQ + 4 * c + 3] = __float_as_uint(sn4.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NFQ; ++j) {
+            v[ax * NFQ + j] = __float_as_uint(__ldg(row + j));
+            v[D * NFQ + ax * NFQ + j] = __float_as_uint(__ldg(row + NFQ + j));
+          }
+        }
+      }
+      if (!ok) {
+#pragma unroll
+        for (int i = 0; i < F; ++i) v[i] = 0u;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < F; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
+    }
     const int64_t pidx = (pe_origin + (ok ? pe_off(gp) : 0)) * NPE;
-    if (a.pe_half) {      // fp16 positional encodings: v[16..23] are already the packed pairs the chain operand needs
+    if (F == 16 && a.pe_half) {      // fp16 positional encodings: v[16..23] are already the packed pairs the chain operand needs
       const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.pe) + pidx);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -245,10 +292,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
-      v[16 + c * 4] = t4.x; v[17 + c * 4] = t4.y; v[18 + c * 4] = t4.z; v[19 + c * 4] = t4.w;
+      v[F + c * 4] = t4.x; v[F + 1 + c * 4] = t4.y; v[F + 2 + c * 4] = t4.z; v[F + 3 + c * 4] = t4.w;
     }
   };
-  uint32_t xin[32];
+  uint32_t xin[IN];
   if (g < ntiles) load_x0(g * 128 + r, xin);    // first tile's inputs travel under the weight staging
 
   PROF(1);
@@ -297,6 +344,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const int e = t + i * MT_THREADS, k = e / HID, j = e % HID;
       sts16(sbase + Sm::W3 + swz64(k, j), __float2half_rn(k < OUT ? w3v[i] : 0.f));
     }
+    if (WIDE) {
+      for (int e = t; e < Sm::WT / 4; e += MT_THREADS) sts32(sbase + Sm::WF0B + e * 4, 0u);      // K 2..15 of the third block stay zero
+    }
     if (t < 3 * HID) plain[t] = w0 * bv;
     if (t < 4) plain[96 + t] = b3v;
     if (t < HID * 4) plain[128 + t] = w3p;
@@ -310,6 +360,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     }
   }
   PROF(2);
+  if (WIDE) {
+    __syncthreads();                                  // the zero fill of the third K block is complete
+    const int t = threadIdx.x;
+    if (t < (IN - 32) * HID) {
+      const int r = 32 + t / HID, c = t % HID;
+      const __half w = __float2half_rn(w0 * wt_g[off0 + HID + r * HID + c]);
+      sts16(sbase + Sm::WF0B + swz64(c, r - 32), w);                            // forward B: rows j, K = i - 32
+      sts16(sbase + Sm::WB + swz64(r - F, c), w);                               // backward B (layer 0): pe input r - F
+    }
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -352,9 +412,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       umma_f16_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
   };
   // dW = X^T dZ over the tile's 128 pixels: both operands pixel-major (MN-major), eight K = 16 steps of 1024 B
-  auto wgrad = [&](uint32_t d_col, int x_off, int dz_off, uint32_t idesc) {
+  auto wgrad = [&](uint32_t d_col, int x_off, int dz_off, uint32_t idesc, int atom2_off = Sm::ONES) {
     const uint32_t xa = sbase + x_off;
-    const uint64_t da = smem_desc_pm(xa, sbase + Sm::ONES - xa), db = smem_desc_pm(sbase + dz_off, 16);
+    const uint64_t da = smem_desc_pm(xa, sbase + atom2_off - xa), db = smem_desc_pm(sbase + dz_off, 16);
 #pragma unroll
     for (int k = 0; k < 8; ++k) umma_f16(tmem_base + d_col, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, 1u);
   };
@@ -381,7 +441,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const uint32_t t32 = idesc_f16_m128(32), t16 = idesc_f16_m128(16);
       const uint32_t h32 = idesc_f16(32) | IDESC_A_MN | IDESC_B_MN, h16 = idesc_f16(16) | IDESC_A_MN;
       switch (stage) {
-        case 0: chain(R1, R0, Sm::WF, t32); break;                              // Z0 = X0 W0
+        case 0:                                                                 // Z0 = X0 W0
+          chain(R1, R0, Sm::WF, t32);
+          if (WIDE) umma_f16_ts(tmem_base + R1, tmem_base + R0 + 16u, smem_desc_sw64(sbase + Sm::WF0B), t32, 1u);
+          break;
         case 1: chain(R0, R1, Sm::WF + Sm::WT, t32); break;                     // Z1 = X1 W1
         case 2: chain(R1, R0, Sm::WF + 2 * Sm::WT, t32); break;                       // Z2 = X2 W2
         case 3: chain(R0, R1, Sm::W3, t16); break;                              // y  = X3 W3
@@ -404,7 +467,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         default:
           chain(R0, R1, Sm::WB, t16);                                           // d pe = dZ0 W0[pe rows]^T
           while (wg_turn[2] != tile) {}
-          wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, h32);                        // dW0 = X0^T dZ0
+          if (WIDE) wgrad(TM_DW, so + Sm::XT1, so + Sm::DZT, h32, so + Sm::XT2);  // dW0 = X0^T dZ0, 34 inputs + bias row
+          else wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, h32);                   // dW0 = X0^T dZ0
           wg_turn[2] = tile + 1;
           break;
       }
@@ -454,11 +518,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     uint32_t cs[3][16];                           // cos(.) of the three sine layers, packed half2
     // ---- X0 -> TMEM (R0)
     {
-      uint32_t x0p[16];                                                  // the 32 inputs as packed fp16 pairs
+      uint32_t x0p[WIDE ? 24 : 16];                                      // the inputs as packed fp16 pairs
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        x0p[i] = (a.pe_half && i >= 8) ? xin[8 + i] : pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
-      tmem_st16(tm + R0, x0p);
+        x0p[i] = (F == 16 && a.pe_half && i >= 8) ? xin[8 + i] : pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
+      tmem_st16(tm + R0, reinterpret_cast<const uint32_t(&)[16]>(x0p));
+      if (WIDE) {
+#pragma unroll
+        for (int i = 16; i < 24; ++i)
+          x0p[i] = 2 * i + 1 < IN ? pack_h2(__uint_as_float(xin[2 * i < IN ? 2 * i : 0]), __uint_as_float(xin[2 * i + 1 < IN ? 2 * i + 1 : 0])) : 0u;
+        tmem_st8(tm + R0 + 16u, x0p + 16);
+      }
     }
     publish(false);
     issue(0);
@@ -558,8 +628,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           uint32_t xf[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            xf[j] = (a.pe_half && h == 1) ? xin[16 + j] : pack_h2(__uint_as_float(xin[16 * h + 2 * j]), __uint_as_float(xin[16 * h + 2 * j + 1]));
-          store_p16(sbase + so + Sm::XT3, 16 * h, xf);
+            xf[j] = (F == 16 && a.pe_half && h == 1) ? xin[16 + j] : pack_h2(__uint_as_float(xin[16 * h + 2 * j]), __uint_as_float(xin[16 * h + 2 * j + 1]));
+          store_p16(sbase + so + (WIDE ? Sm::XT1 : Sm::XT3), 16 * h, xf);       // X1 / X2 are dead by now (34 inputs: both are reused)
+          if (WIDE && h == 1) {
+            // second atom of dW0's A operand: [x32, x33, 1, 0, ...] -- accumulator rows 32, 33 = the last two inputs, row 34 = bias
+            const uint32_t row = sbase + so + Sm::XT2 + pm_row;
+            const uint32_t w0p = pack_h2(__uint_as_float(xin[32]), __uint_as_float(xin[IN - 1]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)c ^ pm_x) << 4)),
+                           "r"(c == 0 ? w0p : 0u), "r"(c == 0 ? 0x00003c00u : 0u), "r"(0u), "r"(0u) : "memory");
+          }
         }
       }
       tmem_st16(reg, dzp);
@@ -601,13 +680,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       uint32_t acc[16];
       const float sc = w0 * unscale * (gwh ? a.d_wt_h_scale : 1.f);
       const float sc3 = unscale * (gwh ? a.d_wt_h_scale : 1.f);
-      const bool wrow = q < 2 && lane < 16, brow = q == 2 && lane == 0;
-      const int irow = q * 16 + lane;
+      const bool wrow_n = q < 2 && lane < 16, brow_n = q == 2 && lane == 0;
+      const int irow_n = q * 16 + lane;
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
         tmem_ld16_issue(tm + TM_DW + (uint32_t)(l * 32 + j0), acc);
         tmem_ld_wait();
         const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
+        // 34 inputs: layer 0 has two more weight rows (accumulator rows 32, 33 = lanes 64, 65) and its bias in row 34
+        const bool wide0 = WIDE && l == 0;
+        const bool wrow = wrow_n || (wide0 && q == 2 && lane < IN - 32);
+        const bool brow = wide0 ? (q == 2 && lane == IN - 32) : brow_n;
+        const int irow = (wide0 && q == 2) ? 32 + lane : irow_n;
         const int didx = wrow ? off + HID + irow * HID + j0 : off + j0;
         float* dst = gw + didx;
         if ((wrow || brow) && gwh) {
@@ -627,6 +711,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       if (g == 0) {
         tmem_ld16_issue(tm + TM_DW + 96, acc);
         tmem_ld_wait();
+        const bool wrow = wrow_n, brow = brow_n;
+        const int irow = irow_n;
         if (wrow) {
 #pragma unroll
           for (int k = 0; k < OUT; ++k) {
@@ -656,14 +742,14 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
 }
 
-template <int OUT>
+template <int OUT, int F, int D>
 static int launch(const rcb_mlp_args* a, cudaStream_t st) {
 #define RCB_MT_LAUNCH(MODE)                                                                                   \
   do {                                                                                                        \
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<OUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_kernel<OUT, MODE, F, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          Sm::TOTAL);                                                          \
     if (e != cudaSuccess) { set_error("rcb_mlp_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; } \
-    mlp_tc_kernel<OUT, MODE><<<a->items, MT_THREADS, Sm::TOTAL, st>>>(*a);                                   \
+    mlp_tc_kernel<OUT, MODE, F, D><<<a->items, MT_THREADS, Sm::TOTAL, st>>>(*a);                             \
   } while (0)
   if (a->mode == 0) RCB_MT_LAUNCH(0);
   else if (a->mode == 1) RCB_MT_LAUNCH(1);
@@ -684,12 +770,41 @@ extern "C" int rcb_mlp_prof_read(long long* host) {
 }
 #endif
 
+namespace rcb {
+// one thread per (coordinate index, frequency); fp32 arithmetic in the reference's order, accurate sincosf
+__global__ void fourier_table_kernel(float* __restrict__ tab, int size, int nf, float w0, float w1, float w2, float w3, float w4,
+                                     float w5, float w6, float w7) {
+  const float w[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= size * nf) return;
+  const int i = e / nf, j = e - i * nf;
+  const float c = __fadd_rn(-1.0f, __fmul_rn(2.0f, __fdiv_rn(0.5f + (float)i, (float)size)));   // utils.py:265-284
+  const float t = __fmul_rn(__fmul_rn(c, w[j]), 3.14159274101257324f);                         // (c * w) * float32(pi)
+  float sn, cs;
+  sincosf(t, &sn, &cs);
+  tab[i * 2 * nf + j] = cs;
+  tab[i * 2 * nf + nf + j] = sn;
+}
+}  // namespace rcb
+
+extern "C" int rcb_fourier_table(float* tab, int size, const float* freq, int n_freq, rcb_stream_t stream) {
+  RCB_CHECK_ARG(tab && freq && size > 0 && n_freq > 0 && n_freq <= 8, "rcb_fourier_table: bad arguments");
+  float w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < n_freq; ++j) w[j] = freq[j];
+  const int total = size * n_freq;
+  rcb::fourier_table_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(tab, size, n_freq, w[0], w[1], w[2], w[3], w[4],
+                                                                                  w[5], w[6], w[7]);
+  RCB_CHECK_LAUNCH("rcb_fourier_table");
+  return 0;
+}
+
 extern "C" int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a != nullptr, "rcb_mlp_tc: null args");
   RCB_CHECK_ARG(a->items > 0 && a->S > 0 && a->pix > 0, "rcb_mlp_tc: empty problem");
   RCB_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "rcb_mlp_tc: bad mode %d", a->mode);
-  RCB_CHECK_ARG(a->wt && a->xt && a->pe, "rcb_mlp_tc: null input");
-  RCB_CHECK_ARG(a->n_f == 16, "rcb_mlp_tc: built for 32 input features (16 Fourier + 16 pe); use rcb_mlp for other shapes");
+  RCB_CHECK_ARG(a->wt && (a->xt || a->x_tab) && a->pe, "rcb_mlp_tc: null input");
+  RCB_CHECK_ARG(a->n_f == 16 || a->n_f == 18, "rcb_mlp_tc: built for 16 or 18 Fourier features (+ 16 pe); use rcb_mlp for other shapes");
+  RCB_CHECK_ARG(!a->pe_half || a->n_f == 16, "rcb_mlp_tc: fp16 positional encodings need the 32-input form");
   RCB_CHECK_ARG(a->mode != 0 || a->y_pred, "rcb_mlp_tc: mode 0 needs y_pred");
   RCB_CHECK_ARG(a->mode != 1 || (a->y && a->sqerr && a->coef > 0.f), "rcb_mlp_tc: mode 1 needs y, sqerr and coef > 0");
   RCB_CHECK_ARG(a->mode != 2 || a->dy, "rcb_mlp_tc: mode 2 needs dy");
@@ -697,8 +812,23 @@ extern "C" int rcb_mlp_tc(const rcb_mlp_args* a, rcb_stream_t stream) {
   RCB_CHECK_ARG(a->ld_w % 4 == 0, "rcb_mlp_tc: ld_w must be a multiple of 4");
   RCB_CHECK_ARG(!a->pe_base || (a->ph > 0 && a->pw > 0), "rcb_mlp_tc: stitched addressing needs the patch extent");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->out == 3) return mlp::launch<3>(a, st);
-  if (a->out == 1) return mlp::launch<1>(a, st);
-  set_error("rcb_mlp_tc: unsupported output width %d", a->out);
+  // D only matters with generated inputs: the 16-feature forms exist for 1-D (8 frequencies) and 2-D (4 per axis)
+  // signals, the 18-feature one for 3-D (3 per axis); without x_tab any D serves
+  int D = a->n_f == 18 ? 3 : 2;
+  if (a->x_tab) {
+    RCB_CHECK_ARG(a->x_axes >= 1 && a->x_axes <= 3 && 2 * a->x_axes * a->x_nfreq == a->n_f, "rcb_mlp_tc: x_tab does not describe %d features", a->n_f);
+    RCB_CHECK_ARG((a->n_f == 18) == (a->x_axes == 3) && (((uintptr_t)a->x_tab) & 15) == 0, "rcb_mlp_tc: unsupported generated-input shape");
+    int64_t prod = 1;
+    for (int i = 0; i < a->x_axes; ++i) {
+      RCB_CHECK_ARG(a->x_size[i] > 0 && a->x_off[i] >= 0 && a->x_off[i] % 4 == 0, "rcb_mlp_tc: bad x_tab axis %d", i);
+      prod *= a->x_size[i];
+    }
+    RCB_CHECK_ARG(prod == a->pix, "rcb_mlp_tc: x_size does not multiply to pix");
+    D = a->x_axes;
+  }
+  if (a->out == 3 && a->n_f == 18) return mlp::launch<3, 18, 3>(a, st);
+  if (a->out == 3 && a->n_f == 16) return D == 1 ? mlp::launch<3, 16, 1>(a, st) : mlp::launch<3, 16, 2>(a, st);
+  if (a->out == 1 && a->n_f == 16) return D == 1 ? mlp::launch<1, 16, 1>(a, st) : mlp::launch<1, 16, 2>(a, st);
+  set_error("rcb_mlp_tc: unsupported shape (out %d, %d Fourier features)", a->out, a->n_f);
   return -2;
 }

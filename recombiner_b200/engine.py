@@ -187,6 +187,9 @@ class FitEngine:
         self.batch_gemm = os.environ.get("RECOMBINER_BATCH_GEMM", "fwd")
         self.half_dwt = os.environ.get("RECOMBINER_HALF_DWT", "1") != "0"
         self.half_pe = os.environ.get("RECOMBINER_HALF_PE", "1") != "0"
+        # Fourier inputs regenerated from the pixel index inside the tensor-core MLP when the caller's x is the canonical one
+        self.gen_x = os.environ.get("RECOMBINER_GEN_X", "1") != "0"
+        self.x_generated = False
         # conv2's activations are only ever read as MMA operands (conv3) and for their signs (LeakyReLU mask):
         # where conv3 has the fp16-operand kernel they are stored as fp16 -- the 10 mantissa bits a TF32 MMA
         # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
@@ -388,10 +391,64 @@ class FitEngine:
             self._ws[key] = ws
         return ws
 
-    def prepare_x(self, x: torch.Tensor):
-        """(rows, pix, F) Fourier inputs -> transposed (F, pix) [shared] or (rows, F, pix)."""
+    # ------------------------------------------------------ generated Fourier inputs --
+    def fourier_table(self):
+        """Per-axis Fourier feature table, generated on the device from coordinate indices (rcb_fourier_table), and the
+        canonical (pix, n_f) input built from it.  X is identical for every datapoint of a modality (the loaders compute
+        it from the pixel grid alone, data/image.py:24-27), so the tensor-core MLP regenerates it from the pixel index
+        instead of reading an input tensor whenever the caller's x IS that canonical input."""
+        if getattr(self, "_xtab", None) is None:
+            d = self.data_dim
+            nf = self.n_f // (2 * d)
+            if 2 * d * nf != self.n_f or nf > 8:
+                self._xtab = False
+                return None
+            freq = torch.exp(torch.linspace(0, float(np.log(1024)), nf))             # data/image.py:25, fp32 on the host
+            fa = (C.c_float * nf)(*[float(v) for v in freq])
+            offs, total = [], 0
+            for sz in self.pixel_sizes:
+                offs.append(total)
+                total += _round_up(sz * 2 * nf, 4)
+            tab = torch.zeros(total, device=self.device)
+            for sz, off in zip(self.pixel_sizes, offs):
+                check(self.lib.rcb_fourier_table(tab.data_ptr() + 4 * off, sz, fa, nf, stream()), "rcb_fourier_table")
+            idx = torch.arange(self.pix, device=self.device)
+            cos_parts, sin_parts = [], []
+            rem = idx
+            per_axis = []
+            for sz in reversed(self.pixel_sizes):
+                per_axis.append(rem % sz)
+                rem = rem // sz
+            per_axis.reverse()
+            for sz, off, ia in zip(self.pixel_sizes, offs, per_axis):
+                rows = tab[off:off + sz * 2 * nf].view(sz, 2 * nf)[ia]
+                cos_parts.append(rows[:, :nf])
+                sin_parts.append(rows[:, nf:])
+            canon = torch.cat(cos_parts + sin_parts, 1).contiguous()                  # (pix, n_f)
+            self._xtab = dict(tab=tab, offs=offs, nf=nf, canon=canon, canon_t=canon.t().contiguous())
+        return self._xtab or None
+
+    def x_is_canonical(self, x_row: torch.Tensor) -> bool:
+        """Does one row of a caller's x (pix, n_f) equal the canonical Fourier input of this modality's grid?  (Host and
+        device sin/cos differ in the last ulp: 2e-6 absolute on values in [-1, 1].)"""
+        ft = self.fourier_table()
+        if ft is None or tuple(x_row.shape) != (self.pix, self.n_f):
+            return False
+        return bool((x_row.to(self.device, torch.float32) - ft["canon"]).abs().max().item() <= 2e-6)
+
+    def prepare_x(self, x):
+        """(rows, pix, F) Fourier inputs -> transposed (F, pix) [shared] or (rows, F, pix).  x = None, or an x whose
+        rows all equal the canonical input of the grid, selects the generated form (`self.x_generated`): the tensor-core
+        MLP then takes the per-axis table and never reads X."""
+        if x is None:
+            ft = self.fourier_table()
+            if ft is None:
+                raise KernelError("this modality's inputs cannot be generated in-kernel: pass x")
+            self.x_generated = True
+            return ft["canon_t"], 0
         key = (x.data_ptr(), tuple(x.shape), x._version)
         if self._x_cache is not None and self._x_cache[0] == key:
+            self.x_generated = self._x_cache[3]
             return self._x_cache[1], self._x_cache[2]
         if x.shape[1] != self.pix or x.shape[2] != self.n_f:
             raise KernelError(f"x has shape {tuple(x.shape)}, expected (rows, {self.pix}, {self.n_f})")
@@ -400,6 +457,7 @@ class FitEngine:
             shared = True
         else:
             shared = bool((x == x[:1]).all().item())
+        generated = bool(shared and self.gen_x and self.x_is_canonical(x[0]))
         # the transposed copy lives in one buffer per layout, so that captured fit steps (which hold its
         # address) keep seeing the current x
         bkey = (shared, tuple(x.shape[1:]) if shared else tuple(x.shape))
@@ -413,7 +471,8 @@ class FitEngine:
         else:
             xt.copy_(x.transpose(1, 2))
             stride = self.n_f * self.pix
-        self._x_cache = (key, xt, stride)
+        self._x_cache = (key, xt, stride, generated)
+        self.x_generated = generated
         return xt, stride
 
     # ------------------------------------------------------------------ forward --
@@ -623,7 +682,12 @@ class FitEngine:
         a.pe_base = ptr(ws["pe_base"])
         a.pitch_z, a.pitch_y, a.ph, a.pw = self.pitch_z, self.pitch_y, self.ph, self.pw
         a.items, a.S, a.pix, a.n_f, a.out, a.ld_w, a.mode = rows * S, S, self.pix, self.n_f, self.out, self.ldw, mode
-        use_tc = self.tc_mlp and self.n_f == 16
+        use_tc = self.tc_mlp and self.n_f in (16, 18)
+        if use_tc and self.x_generated:
+            ft = self.fourier_table()
+            a.x_tab, a.x_axes, a.x_nfreq = ptr(ft["tab"]), self.data_dim, ft["nf"]
+            for i in range(self.data_dim):
+                a.x_size[i], a.x_off[i] = self.pixel_sizes[i], ft["offs"][i]
         if use_tc and mode == 2 and coef == 0.0:
             # the tensor-core kernel keeps its weight-gradient operands in fp16: hand it a power-of-two
             # scale that brings the caller's dy to O(1) (host sync; this is the autograd path, not the fit loop)

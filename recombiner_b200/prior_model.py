@@ -438,7 +438,7 @@ class PriorBNNmodel(nn.Module):
         use_graph = (os.environ.get("RECOMBINER_GRAPH", "1") != "0" and eng.timer is None
                      and not torch.cuda.is_current_stream_capturing())
         xt, x_stride = eng.prepare_x(x)
-        key = (xt.data_ptr(), x_stride, y.data_ptr(), tuple(y.shape), bool(training_mappings), world, cfg["b1"], cfg["b2"],
+        key = (xt.data_ptr(), x_stride, eng.x_generated, y.data_ptr(), tuple(y.shape), bool(training_mappings), world, cfg["b1"], cfg["b2"],
                cfg["eps"], self.row_offset, id(sm)) + tuple(v for l in self._levels for v in (l.p_loc.data_ptr(), l.loc.data_ptr()))
         graphs = self.__dict__.setdefault("_step_graphs", {})
         state = self.__dict__.setdefault("_step_state", torch.zeros(C.sizeof(StepState), dtype=torch.uint8, device=self.device))

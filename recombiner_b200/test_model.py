@@ -488,7 +488,7 @@ class TestBNNmodel(nn.Module):
             return None
         # everything a captured step holds by value or by pointer
         xt, x_stride = eng.prepare_x(x)
-        key = (S, do_anneal, xt.data_ptr(), x_stride, y.data_ptr(), tuple(y.shape),
+        key = (S, do_anneal, xt.data_ptr(), x_stride, eng.x_generated, y.data_ptr(), tuple(y.shape),
                adam_cfg["b1"], adam_cfg["b2"], adam_cfg["eps"], self.row_offset, eng.map_generation, eng.half_acts,
                self.beta_step_size, self.kl_upper_buffer, self.kl_lower_buffer, float(self.bit_per_group)) + \
             tuple(v for lv in levels for v in (
@@ -523,13 +523,17 @@ class TestBNNmodel(nn.Module):
         return ws
 
     def _host_x_is_shared(self, x):
-        """Every row of a host x holds the same Fourier features (they depend on the pixel grid only): checked once
-        per tensor, then only one row is uploaded."""
+        """(every row of a host x holds the same Fourier features, they are the canonical features of the grid): checked
+        once per tensor.  Shared -> one row is uploaded; canonical -> nothing is uploaded, the MLP kernel regenerates the
+        features from the pixel index (FitEngine.fourier_table)."""
         key = (x.data_ptr(), tuple(x.shape), x._version)
         c = self.__dict__.setdefault("_x_shared_cache", {})
         if key not in c:
             c.clear()
-            c[key] = bool(x.shape[0] == 1 or x.stride(0) == 0 or (x == x[:1]).all())
+            shared = bool(x.shape[0] == 1 or x.stride(0) == 0 or (x == x[:1]).all())
+            eng = self.engine
+            canonical = bool(shared and eng.gen_x and eng.tc_mlp and eng.n_f in (16, 18) and eng.x_is_canonical(x[0]))
+            c[key] = (shared, canonical)
         return c[key]
 
     def _stage_inputs(self, x, y):
@@ -547,8 +551,8 @@ class TestBNNmodel(nn.Module):
         b = st["slot"]
         st["slot"] ^= 1
         x, y = x.detach(), y.detach()
-        shared = (not x.is_cuda) and self._host_x_is_shared(x)
-        xs = x[:1] if shared else x
+        shared, canonical = self._host_x_is_shared(x) if not x.is_cuda else (False, False)
+        xs = x[:0] if canonical else (x[:1] if shared else x)          # canonical inputs are not uploaded at all
         bufs = st["bufs"][b]
         if bufs is None or bufs[0].shape != xs.shape or bufs[1].shape != y.shape:
             bufs = st["bufs"][b] = (torch.empty(xs.shape, dtype=torch.float32, device=self.device),
@@ -564,7 +568,7 @@ class TestBNNmodel(nn.Module):
             bufs[1].copy_(y, non_blocking=True)
             st["up"][b].record(st["stream"])
         main.wait_event(st["up"][b])
-        xd = bufs[0].expand(x.shape[0], -1, -1) if shared else bufs[0]
+        xd = None if canonical else (bufs[0].expand(x.shape[0], -1, -1) if shared else bufs[0])
         return xd, bufs[1], b
 
     def _release_inputs(self, slot):

@@ -45,7 +45,12 @@ def test_ctypes_structs_mirror_the_header():
             base = decl.replace("const", "").replace("*", " ").split()
             typ, names = base[0], "".join(base[1:]).split(",")
             for n in names:
-                fields.append((n.strip(), ctypes.c_void_p if is_ptr else ctype_of[typ]))
+                n = n.strip()
+                ct = ctypes.c_void_p if is_ptr else ctype_of[typ]
+                m_arr = re.fullmatch(r"(\w+)\[(\d+)\]", n)          # fixed-size array member
+                if m_arr:
+                    n, ct = m_arr.group(1), ct * int(m_arr.group(2))
+                fields.append((n, ct))
         struct = _lib.STRUCTS[name]
         assert [(n, t) for n, t in struct._fields_] == fields, name
 
