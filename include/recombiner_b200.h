@@ -159,7 +159,9 @@ int rcb_fold_poly(const float* w, const rcb_upconv_geom* g, float* w_eff, float*
 /* Forward weights in K-major form for the tensor-core path:
  * w_eff_k[phase][oc][tap*ic + c] (same values as w_eff). */
 int rcb_fold_poly_k(const float* w, const rcb_upconv_geom* g, float* w_eff_k, rcb_stream_t stream);
-/* Dense fold for tiny grids: m[(sy,sx,ic)][(oy,ox,oc)], and its transpose. */
+/* Dense fold for tiny grids (the 5-tap first stage, factor >= 4): m[(sy,sx,ic)][(oy,ox,oc)], and its transpose.
+ * Only the structurally non-zero entries are written (an output pixel's taps reach at most 2 x 2 source pixels): m and
+ * m_t must be ZERO before the first call; later calls with the same geometry overwrite the same entries. */
 int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m, float* m_t,
                    rcb_stream_t stream);
 
@@ -322,8 +324,29 @@ typedef struct {
    * host in f64 exactly as torch.optim.Adam does, then passed as f32. */
   float adam_step_size, adam_bc2_sqrt, b1, b2, adam_eps, beta_scalar, grad_scale;
   const rcb_step_state* dyn;             /* optional: seed, step and the Adam scalars read from device memory */
+  /* optional (general layout): per-patch-row sample sums written by rcb_fit_reduce -- red_mu / red_sig (rows, n_w) for
+   * the weights with THIS level's noise, red_mu_l / red_sig_l (rows, n_l) for the latent grid (level 1 only).  The data
+   * gradient is then read from them instead of d_hw / d_lpe / eps_*. */
+  const float* red_mu; const float* red_sig; const float* red_mu_l; const float* red_sig_l;
 } rcb_update_args;
 int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream);
+
+/* First half of the gradient reduction for the patch modalities (autograd backward of utils.py:142-198 with respect
+ * to every level's mean and scale): per patch row and parameter, the sums over the S samples of the data gradient and
+ * of gradient x noise for each of the n_levels levels (they share d_hw and differ in their noise).  eps_*: the noise
+ * the sampling kernel kept (or the caller injected). */
+typedef struct {
+  const float* d_hw;            /* (rows*S, ld_hw) */
+  const float* d_lpe;           /* stitched latent-grid gradient, or NULL if n_l == 0 */
+  const float* eps_w[3];        /* (rows, S, n_w) per level */
+  const float* eps_l;           /* (S, rows, n_l) */
+  const int* lpe_slot;          /* stitching table of rcb_sample_args, or NULL */
+  float* red_mu;                /* (rows, n_w) */
+  float* red_sig[3];            /* (rows, n_w) per level */
+  float* red_mu_l; float* red_sig_l;   /* (rows, n_l) */
+  int rows, S, n_w, n_l, ld_hw, n_levels, rows_per_datum, sp_total, lpe_c;
+} rcb_reduce_args;
+int rcb_fit_reduce(const rcb_reduce_args* a, rcb_stream_t stream);
 
 /* Per-(row, block) KL in nats, f64 accumulation (test_model.py:384-388). */
 int rcb_group_kl(const float* loc, const float* log_scale, const float* p_loc,

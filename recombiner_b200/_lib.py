@@ -46,7 +46,14 @@ class UpdateArgs(C.Structure):
                [(n, I32) for n in ("src_rows", "rows", "n_children", "S", "P", "n_w", "n_l", "ld_hw", "G",
                                    "step", "tensor_id", "adam", "p_scale_direct", "rows_per_datum", "sp_total", "lpe_c")] + \
                [(n, F32) for n in ("adam_step_size", "adam_bc2_sqrt", "b1", "b2", "adam_eps", "beta_scalar",
-                                   "grad_scale")] + [("dyn", P)]
+                                   "grad_scale")] + [("dyn", P)] + \
+               [(n, P) for n in ("red_mu", "red_sig", "red_mu_l", "red_sig_l")]
+
+
+class ReduceArgs(C.Structure):
+    _fields_ = [("d_hw", P), ("d_lpe", P), ("eps_w", P * 3), ("eps_l", P), ("lpe_slot", P), ("red_mu", P),
+                ("red_sig", P * 3), ("red_mu_l", P), ("red_sig_l", P)] + \
+               [(n, I32) for n in ("rows", "S", "n_w", "n_l", "ld_hw", "n_levels", "rows_per_datum", "sp_total", "lpe_c")]
 
 
 class RecArgs(C.Structure):
@@ -62,7 +69,7 @@ class StepState(C.Structure):
 
 
 STRUCTS = {"rcb_step_state": StepState, "rcb_sample_args": SampleArgs, "rcb_upconv_geom": UpconvGeom, "rcb_mlp_args": MlpArgs,
-           "rcb_update_args": UpdateArgs, "rcb_rec_args": RecArgs}
+           "rcb_update_args": UpdateArgs, "rcb_rec_args": RecArgs, "rcb_reduce_args": ReduceArgs}
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -104,6 +111,7 @@ SIGNATURES = {
     "rcb_transpose_phases": [P, P, I64, I32, I32, I32, I32, I32, P],
     "rcb_transpose_xshift": [P, P, I64, I32, I32, P],
     "rcb_fit_update": [C.POINTER(UpdateArgs), P],
+    "rcb_fit_reduce": [C.POINTER(ReduceArgs), P],
     "rcb_group_kl": [P, P, P, P, P, P, P, I32, I32, I32, P],
     "rcb_anneal_beta": [P, P, P, I32, I32, F64, F64, F64, F64, P],
     "rcb_pick_block": [P, P, P, I32, I32, P],

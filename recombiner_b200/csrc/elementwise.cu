@@ -17,43 +17,64 @@ __device__ __forceinline__ int64_t lpe_index(const int* slot, int rows_per_datum
 }
 
 // ----------------------------------------------------------------- sampling --
-// grid: (ceil(P/256), rows).  One thread = one (row, parameter); loops over S.
+// General form (patch modalities: per-column row permutation, level expansion, stitched latent grid, accumulation of
+// levels 2 / 3 into hw).  grid: (chunks of 1024 weight parameters + chunks of 1024 latent values, rows).  A thread owns
+// the four parameters {c0 + t, c0 + 256 + t, c0 + 512 + t, c0 + 768 + t} of its chunk -- the four normals of ONE
+// Philox block per sample (philox_normal4; a thread per parameter generated every block four times) -- and keeps their
+// four posterior gathers in flight together.
 __global__ void __launch_bounds__(256) sample_kernel(rcb_sample_args a) {
   if (a.dyn) { a.seed = a.dyn->seed; a.step = a.dyn->step; }
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = blockIdx.y;
-  if (p >= a.P) return;
-  const int q = a.g2p ? a.g2p[p] : p;
-  int r = a.row_map ? a.row_map[n] : n;
-  if (a.perm) r = a.perm[(int64_t)r * a.P + q];
-  const int64_t e = (int64_t)r * a.P + q;
-  const float m = a.mask ? a.mask[e] : 0.f;
-  float mu = a.loc[e] * (1.f - m);
-  if (a.sample) mu += a.sample[e] * m;
-  const float sig = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
-  const int64_t gn = a.row_offset + n;
-  if (p < a.n_w) {
-    for (int s = 0; s < a.S; ++s) {
-      float eps = a.eps_w ? a.eps_w[((int64_t)n * a.S + s) * a.n_w + p]
-                          : philox_normal(a.seed, a.step, a.tensor_id, gn * a.S + s, (uint32_t)p);
-      if (a.eps_w_store) a.eps_w_store[((int64_t)n * a.S + s) * a.n_w + p] = eps;
-      float v = fmaf(sig, eps, mu);
-      if (a.hw_h) {
-        reinterpret_cast<__half*>(a.hw_h)[((int64_t)n * a.S + s) * a.ld_hw + p] = __float2half_rn(v);
-      } else {
-        float* dst = a.hw + ((int64_t)n * a.S + s) * a.ld_hw + p;
-        *dst = a.accumulate ? *dst + v : v;
-      }
+  const int n = blockIdx.y, t = threadIdx.x;
+  const int w_chunks = (a.n_w + 1023) >> 10;
+  const bool is_w = (int)blockIdx.x < w_chunks;
+  const int c0 = (is_w ? blockIdx.x : blockIdx.x - w_chunks) << 10;
+  const int lim = is_w ? a.n_w : a.n_l;
+  if (!is_w && !(a.lpe || a.lpe_h)) return;
+  const int r0 = a.row_map ? a.row_map[n] : n;
+  float mu[4], sig[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = c0 + k * 256 + t;               // index inside the weight / latent part
+    mu[k] = 0.f; sig[k] = 0.f;
+    if (i < lim) {
+      const int p = is_w ? i : a.n_w + i;
+      const int q = a.g2p ? a.g2p[p] : p;
+      const int r = a.perm ? a.perm[(int64_t)r0 * a.P + q] : r0;
+      const int64_t e = (int64_t)r * a.P + q;
+      const float m = a.mask ? a.mask[e] : 0.f;
+      mu[k] = a.loc[e] * (1.f - m);
+      if (a.sample) mu[k] += a.sample[e] * m;
+      sig[k] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
     }
-  } else if (a.lpe || a.lpe_h) {
-    const int l = p - a.n_w;
-    for (int s = 0; s < a.S; ++s) {
-      float eps = a.eps_l ? a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l]
-                          : philox_normal(a.seed, a.step, a.tensor_id + 16, gn * a.S + s, (uint32_t)l);
-      if (a.eps_l_store) a.eps_l_store[((int64_t)s * a.rows + n) * a.n_l + l] = eps;
-      const int64_t li = lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l);
-      if (a.lpe_h) reinterpret_cast<__half*>(a.lpe_h)[li] = __float2half_rn(fmaf(sig, eps, mu));
-      else a.lpe[li] = fmaf(sig, eps, mu);
+  }
+  const int64_t gn = a.row_offset + n;
+  for (int s = 0; s < a.S; ++s) {
+    const int64_t item = (int64_t)n * a.S + s;
+    const float* ein = is_w ? (a.eps_w ? a.eps_w + item * a.n_w : nullptr)
+                            : (a.eps_l ? a.eps_l + ((int64_t)s * a.rows + n) * a.n_l : nullptr);
+    float* eout = is_w ? (a.eps_w_store ? a.eps_w_store + item * a.n_w : nullptr)
+                       : (a.eps_l_store ? a.eps_l_store + ((int64_t)s * a.rows + n) * a.n_l : nullptr);
+    float z[4];
+    if (!ein) philox_normal4(a.seed, a.step, is_w ? a.tensor_id : a.tensor_id + 16, gn * a.S + s, (uint32_t)((c0 >> 2) + t), z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = c0 + k * 256 + t;
+      if (i >= lim) continue;
+      const float eps = ein ? ein[i] : z[k];
+      if (eout) eout[i] = eps;
+      const float v = fmaf(sig[k], eps, mu[k]);
+      if (is_w) {
+        if (a.hw_h) {
+          reinterpret_cast<__half*>(a.hw_h)[item * a.ld_hw + i] = __float2half_rn(v);
+        } else {
+          float* dst = a.hw + item * a.ld_hw + i;
+          *dst = a.accumulate ? *dst + v : v;
+        }
+      } else {
+        const int64_t li = lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, i);
+        if (a.lpe_h) reinterpret_cast<__half*>(a.lpe_h)[li] = __float2half_rn(v);
+        else a.lpe[li] = v;
+      }
     }
   }
 }
@@ -137,25 +158,13 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
   }
 }
 
-// Row-per-CTA variant of update_kernel for the same case: the per-sample gradients are reduced
-// in parameter order (coalesced) into shared memory, then the KL gradient + Adam runs in group
-// order (coalesced on the stored state).  Same arithmetic order as update_kernel.
-// dynamic smem: 2 * P floats.
-__global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) {
-  if (a.dyn) {
-    a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt;
-    if (a.dyn->beta_scalar >= 0.f) a.beta_scalar = a.dyn->beta_scalar;      // prior training: the global beta of a captured step
-  }
-  extern __shared__ float sm[];
-  float* s_dmu = sm;
-  float* s_dsig = sm + a.P;
-  const int r = blockIdx.x;
-  const int64_t gn = a.row_offset + r;
-  const bool stored_noise = a.eps_w && (a.n_l == 0 || a.eps_l);
-  if (stored_noise && a.S == 5) {
+// Sample reduction of update_rows_kernel with the sample count as a compile-time constant (5: the fit loop, 1: prior
+// training) and the noise kept by the sampling kernel: straight-line loads through per-sample base pointers, two
+// parameters in flight per thread; sums over s in ascending order.
+template <int SS>
+__device__ __forceinline__ void reduce_row_samples(const rcb_update_args& a, int r, float* s_dmu, float* s_dsig) {
     // the fit loop's case (five samples, noise kept by the sampling kernel): straight-line loads through
     // per-sample base pointers, two parameters (twenty loads) in flight per thread; same summation order
-    constexpr int SS = 5;
     const float* dh = a.d_hw + (int64_t)r * SS * a.ld_hw;
     const float* ew = a.eps_w + (int64_t)r * SS * a.n_w;
     for (int p0 = threadIdx.x; p0 < a.n_w; p0 += 2 * blockDim.x) {
@@ -203,6 +212,27 @@ __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) 
         if (two) { s_dmu[a.n_w + l1] = m1; s_dsig[a.n_w + l1] = s1; }
       }
     }
+}
+
+// Row-per-CTA variant of update_kernel for the same case: the per-sample gradients are reduced
+// in parameter order (coalesced) into shared memory, then the KL gradient + Adam runs in group
+// order (coalesced on the stored state).  Same arithmetic order as update_kernel.
+// dynamic smem: 2 * P floats.
+__global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) {
+  if (a.dyn) {
+    a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt;
+    if (a.dyn->beta_scalar >= 0.f) a.beta_scalar = a.dyn->beta_scalar;      // prior training: the global beta of a captured step
+  }
+  extern __shared__ float sm[];
+  float* s_dmu = sm;
+  float* s_dsig = sm + a.P;
+  const int r = blockIdx.x;
+  const int64_t gn = a.row_offset + r;
+  const bool stored_noise = a.eps_w && (a.n_l == 0 || a.eps_l);
+  if (stored_noise && a.S == 5) {
+    reduce_row_samples<5>(a, r, s_dmu, s_dsig);
+  } else if (stored_noise && a.S == 1) {
+    reduce_row_samples<1>(a, r, s_dmu, s_dsig);
   } else
   // loads of 2 parameters x up to 4 samples are issued together (memory-level parallelism);
   // the sums still run over s in ascending order
@@ -302,6 +332,43 @@ __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) 
   }
 }
 
+// ------------------------------------------------ per-row sample reduction --
+// First half of the gradient reduction for the general (patch) layout: per patch row n and parameter p (parameter
+// order, coalesced), red_mu[n][p] = sum_s d[n,s,p] and, for every level l of the hierarchy, red_sig[l][n][p] =
+// sum_s d[n,s,p] * eps_l[n,s,p] (the levels share the data gradient and differ in their noise, utils.py:142-191);
+// the latent part likewise from the stitched d_lpe.  update_kernel then only sums these over the rows a stored
+// parameter feeds (one for level 1, 4 .. 96 children for levels 2 / 3) instead of over (children x samples) scattered
+// 4-byte loads.  grid: (ceil((n_w + n_l) / 256), rows).
+__global__ void __launch_bounds__(256) reduce_samples_kernel(rcb_reduce_args a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (p < a.n_w) {
+    float m = 0.f, sg[3] = {0.f, 0.f, 0.f};
+    for (int s = 0; s < a.S; ++s) {
+      const int64_t item = (int64_t)n * a.S + s;
+      const float d = a.d_hw[item * a.ld_hw + p];
+      m += d;
+#pragma unroll
+      for (int l = 0; l < 3; ++l)
+        if (l < a.n_levels) sg[l] = fmaf(d, a.eps_w[l][item * a.n_w + p], sg[l]);
+    }
+    a.red_mu[(int64_t)n * a.n_w + p] = m;
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+      if (l < a.n_levels) a.red_sig[l][(int64_t)n * a.n_w + p] = sg[l];
+  } else if (p < a.n_w + a.n_l) {
+    const int l = p - a.n_w;
+    float m = 0.f, sg = 0.f;
+    for (int s = 0; s < a.S; ++s) {
+      const float d = a.d_lpe[lpe_index(a.lpe_slot, a.rows_per_datum, a.sp_total, a.lpe_c, a.n_l, a.S, n, s, l)];
+      m += d;
+      sg = fmaf(d, a.eps_l[((int64_t)s * a.rows + n) * a.n_l + l], sg);
+    }
+    a.red_mu_l[(int64_t)n * a.n_l + l] = m;
+    a.red_sig_l[(int64_t)n * a.n_l + l] = sg;
+  }
+}
+
 // ------------------------------------------- gradient reduction + KL + Adam --
 // grid: (ceil(P/256), src_rows).  One thread = one stored (row, group-order column).
 __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
@@ -323,7 +390,30 @@ __global__ void __launch_bounds__(256) update_kernel(rcb_update_args a) {
     float d_mu = 0.f, d_sig = 0.f;
     const bool is_w = p < a.n_w;
     const float* src = is_w ? a.d_hw : a.d_lpe;
-    if (src && m != 1.f) {
+    if (a.red_mu && m != 1.f) {
+      // sample sums already reduced per patch row (rcb_fit_reduce): add the rows this parameter feeds
+      const int nch = a.row_children ? a.n_children : 1;
+      const float* rm = is_w ? a.red_mu : a.red_mu_l;
+      const float* rs = is_w ? a.red_sig : a.red_sig_l;
+      const int ld = is_w ? a.n_w : a.n_l, col = is_w ? p : p - a.n_w;
+      for (int c0 = 0; c0 < nch; c0 += 8) {
+        float dv[8], sv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + u;
+          dv[u] = 0.f; sv[u] = 0.f;
+          if (c < nch) {
+            const int n = a.row_children ? a.row_children[(int64_t)rr * a.n_children + c] : rr;
+            dv[u] = rm[(int64_t)n * ld + col];
+            sv[u] = rs[(int64_t)n * ld + col];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { d_mu += dv[u]; d_sig += sv[u]; }
+      }
+      d_mu *= a.grad_scale * (1.f - m);
+      d_sig *= a.grad_scale * (1.f - m);
+    } else if (src && m != 1.f) {
       const int nch = a.row_children ? a.n_children : 1;
       // (child row, sample) pairs in the reference's order; eight gradient / noise loads are issued together
       // (a level-3 row of a patch modality sums over every patch of the datum: hundreds of terms per thread)
@@ -602,6 +692,60 @@ __global__ void __launch_bounds__(256) transpose_phases_kernel(const float* __re
   }
 }
 
+// Wide-tile forms of the two kernels above for cols <= 64 (the upsampler's channel counts): one CTA moves 128
+// consecutive rows -- a contiguous 128 * cols block of the input, read as float4 -- through a padded shared-memory tile
+// and writes 32 consecutive rows of one channel per warp instruction.  Same outputs; 4 x fewer, 4 x larger CTAs and no
+// half-empty 32-column tiles for the 16-channel tensors.
+constexpr int TW_ROWS = 128;
+
+template <int MODE>        // 0: x-shifted copies (transpose_xshift), 1: phase planes (transpose_phases)
+__global__ void __launch_bounds__(256) transpose_wide_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
+                                                             int cols, int h, int w, int fy, int fx) {
+  extern __shared__ float tw_tile[];                  // [TW_ROWS + 2][cols + 1]; row 0 = the row before the block
+  const int ldt = cols + 1;
+  const int64_t r0 = (int64_t)blockIdx.x * TW_ROWS;
+  const int nrow = (int)min((int64_t)TW_ROWS, rows - r0);
+  // block rows r0 - 1 .. r0 + nrow (halo rows only matter for MODE 0)
+  const int64_t first = MODE == 0 ? r0 - 1 : r0;
+  const int nload = MODE == 0 ? nrow + 2 : nrow;
+  const int64_t base = first * cols;
+  const int total4 = nload * cols / 4;                // cols % 4 == 0
+  for (int i = threadIdx.x; i < total4; i += 256) {
+    const int64_t e = base + 4 * (int64_t)i;
+    const int lr = (4 * i) / cols, lc = (4 * i) - lr * cols;
+    const int64_t gr = first + lr;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr >= 0 && gr < rows) v = *reinterpret_cast<const float4*>(in + e);
+    float* t = tw_tile + (MODE == 0 ? lr : lr + 1) * ldt + lc;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rg = 0; rg < TW_ROWS / 32; ++rg) {
+    const int lr = rg * 32 + lane;
+    const int64_t r = r0 + lr;
+    if (lr >= nrow) continue;
+    if (MODE == 0) {
+      const int x = (int)(r % w);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int dx = k - 1;
+        const bool inside = x + dx >= 0 && x + dx < w;
+        for (int c = warp; c < cols; c += 8)
+          out[((int64_t)k * cols + c) * rows + r] = inside ? tw_tile[(lr + 1 + dx) * ldt + c] : 0.f;
+      }
+    } else {
+      const int Wo = w * fx, Ho = h * fy;
+      const int ox = (int)(r % Wo);
+      const int64_t t = r / Wo;
+      const int oy = (int)(t % Ho);
+      const int64_t item = t / Ho;
+      const int64_t ro = ((item * fy + oy % fy) * fx + ox % fx) * (int64_t)(h * w) + (int64_t)(oy / fy) * w + ox / fx;
+      for (int c = warp; c < cols; c += 8) out[(int64_t)c * rows + ro] = tw_tile[(lr + 1) * ldt + c];
+    }
+  }
+}
+
 // ------------------------------------------------------ EM prior statistics --
 // grid: (ceil(P/128), row chunks); f64 partial sums added with atomics.
 __global__ void __launch_bounds__(128) suffstats_kernel(const float* __restrict__ loc, const float* __restrict__ log_scale,
@@ -683,9 +827,22 @@ extern "C" int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream) {
     RCB_CHECK_LAUNCH("rcb_fit_sample");
     return 0;
   }
-  dim3 grid(ceil_div(a->P, 256), a->rows);
+  dim3 grid(ceil_div(a->n_w, 1024) + ceil_div(a->n_l, 1024), a->rows);
   sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
   RCB_CHECK_LAUNCH("rcb_fit_sample");
+  return 0;
+}
+
+extern "C" int rcb_fit_reduce(const rcb_reduce_args* a, rcb_stream_t stream) {
+  RCB_CHECK_ARG(a != nullptr, "rcb_fit_reduce: null args");
+  RCB_CHECK_ARG(a->d_hw && a->red_mu && a->n_levels >= 1 && a->n_levels <= 3, "rcb_fit_reduce: bad arguments");
+  for (int l = 0; l < a->n_levels; ++l)
+    RCB_CHECK_ARG(a->eps_w[l] && a->red_sig[l], "rcb_fit_reduce: level %d needs its noise and its output", l);
+  RCB_CHECK_ARG(a->n_l == 0 || (a->d_lpe && a->eps_l && a->red_mu_l && a->red_sig_l), "rcb_fit_reduce: latent part incomplete");
+  RCB_CHECK_ARG(a->rows > 0 && a->rows <= 65535 && a->S > 0 && a->n_w > 0 && a->ld_hw >= a->n_w, "rcb_fit_reduce: bad shape");
+  dim3 grid(ceil_div(a->n_w + a->n_l, 256), a->rows);
+  reduce_samples_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  RCB_CHECK_LAUNCH("rcb_fit_reduce");
   return 0;
 }
 
@@ -700,7 +857,8 @@ extern "C" int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream) {
     RCB_CHECK_ARG(a->g_loc && a->g_log_scale, "rcb_fit_update: gradient outputs missing");
   }
   const size_t row_smem = 2 * sizeof(float) * (size_t)a->P;
-  if (!a->perm_inv && !a->row_children && !a->lpe_slot && a->d_hw && (a->n_l == 0 || a->d_lpe) && a->n_w + a->n_l == a->P &&
+  RCB_CHECK_ARG(!a->red_mu || (a->red_sig && (a->n_l == 0 || (a->red_mu_l && a->red_sig_l))), "rcb_fit_update: reduced gradients incomplete");
+  if (!a->perm_inv && !a->row_children && !a->lpe_slot && !a->red_mu && a->d_hw && (a->n_l == 0 || a->d_lpe) && a->n_w + a->n_l == a->P &&
       row_smem <= 200 * 1024) {
     if (row_smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(update_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
@@ -767,6 +925,12 @@ extern "C" int rcb_transpose(const float* in, int64_t ld_in, float* out, int64_t
 extern "C" int rcb_transpose_xshift(const float* in, float* out, int64_t rows, int cols, int w, rcb_stream_t stream) {
   RCB_CHECK_ARG(in && out, "rcb_transpose_xshift: null tensor");
   RCB_CHECK_ARG(rows > 0 && cols > 0 && w > 0 && rows % w == 0, "rcb_transpose_xshift: rows must be whole lines of w pixels");
+  if (cols <= 64 && cols % 4 == 0 && (((uintptr_t)in) & 15) == 0) {
+    const size_t smem = sizeof(float) * (TW_ROWS + 2) * (size_t)(cols + 1);
+    transpose_wide_kernel<0><<<(unsigned)ceil_div(rows, (int64_t)TW_ROWS), 256, smem, (cudaStream_t)stream>>>(in, out, rows, cols, 1, w, 1, 1);
+    RCB_CHECK_LAUNCH("rcb_transpose_xshift");
+    return 0;
+  }
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
   RCB_CHECK_ARG(grid.y <= 65535 * 32, "rcb_transpose_xshift: too many rows");
   transpose_xshift_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, w);
@@ -779,6 +943,12 @@ extern "C" int rcb_transpose_phases(const float* in, float* out, int64_t rows, i
   RCB_CHECK_ARG(in && out, "rcb_transpose_phases: null tensor");
   RCB_CHECK_ARG(rows > 0 && cols > 0 && h > 0 && w > 0 && fy > 0 && fx > 0 && rows % ((int64_t)h * fy * w * fx) == 0,
                 "rcb_transpose_phases: rows must be whole (h*fy, w*fx) grids");
+  if (cols <= 64 && cols % 4 == 0 && (((uintptr_t)in) & 15) == 0) {
+    const size_t smem = sizeof(float) * (TW_ROWS + 2) * (size_t)(cols + 1);
+    transpose_wide_kernel<1><<<(unsigned)ceil_div(rows, (int64_t)TW_ROWS), 256, smem, (cudaStream_t)stream>>>(in, out, rows, cols, h, w, fy, fx);
+    RCB_CHECK_LAUNCH("rcb_transpose_phases");
+    return 0;
+  }
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
   RCB_CHECK_ARG(grid.y <= 65535 * 32, "rcb_transpose_phases: too many rows");
   transpose_phases_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, h, w, fy, fx);

@@ -120,30 +120,53 @@ __global__ void unfold_poly_kernel(const float* __restrict__ d_w_eff, PolyGeom g
 
 // d_w[o][c][a][b] = sum over output pixels whose tap (a,b) lands inside the grid of
 // d_m[(sy,sx,c)][(oy,ox,o)] with (sy,sx) the source pixel under that tap
-__global__ void unfold_dense_kernel(const float* __restrict__ d_m, PolyGeom g, int ky, int kx, float* __restrict__ d_w) {
+// One thread per (oc, ic) pair keeps the pair's KY x KX tap gradients in registers and walks the output pixels, reading
+// the (at most 2 x 2) entries of d_m that the pixel's taps fall on -- consecutive threads read consecutive oc, the
+// innermost index of d_m.  Per tap the terms are added in (oy, ox) order, as a thread per tap would.
+template <int KY, int KX>
+__global__ void __launch_bounds__(128) unfold_dense_kernel(const float* __restrict__ d_m, PolyGeom g, float* __restrict__ d_w) {
   const int H = g.h * g.fy, W = g.w * g.fx;
   const int64_t cols = (int64_t)H * W * g.oc;
-  int64_t total = (int64_t)g.oc * g.ic * ky * kx;
-  // thread order (a, b, c, o) with o fastest: d_m's innermost index is o, so a warp reads 128 contiguous bytes per
-  // output pixel (the (o, c, a, b) order of d_w made every one of the H*W loads a 2 KB-strided gather: 47 us per call)
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int o = e % g.oc; int64_t r = e / g.oc;
-    int c = r % g.ic; r /= g.ic;
-    int b = r % kx; int a = r / kx;
-    float s = 0.f;
-    for (int oy = 0; oy < H; ++oy) {
-      int uy = oy + a - g.py;
-      if (uy < 0 || uy >= H) continue;
-      int sy = uy / g.fy;
-      for (int ox = 0; ox < W; ++ox) {
-        int ux = ox + b - g.px;
-        if (ux < 0 || ux >= W) continue;
-        int sx = ux / g.fx;
-        s += d_m[(((int64_t)sy * g.w + sx) * g.ic + c) * cols + ((int64_t)oy * W + ox) * g.oc + o];
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= g.oc * g.ic) return;
+  const int o = pair % g.oc, c = pair / g.oc;
+  float acc[KY][KX];
+#pragma unroll
+  for (int a = 0; a < KY; ++a)
+#pragma unroll
+    for (int b = 0; b < KX; ++b) acc[a][b] = 0.f;
+  for (int oy = 0; oy < H; ++oy) {
+    const int sy0 = max(oy - g.py, 0) / g.fy;
+    for (int ox = 0; ox < W; ++ox) {
+      const int sx0 = max(ox - g.px, 0) / g.fx;
+      float v[2][2];
+#pragma unroll
+      for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+          const int sy = sy0 + iy, sx = sx0 + ix;
+          v[iy][ix] = (sy < g.h && sx < g.w)
+                          ? d_m[(((int64_t)sy * g.w + sx) * g.ic + c) * cols + ((int64_t)oy * W + ox) * g.oc + o] : 0.f;
+        }
+#pragma unroll
+      for (int a = 0; a < KY; ++a) {
+        const int uy = oy + a - g.py;
+        if (uy < 0 || uy >= H) continue;
+        const int iy = uy / g.fy - sy0;
+#pragma unroll
+        for (int b = 0; b < KX; ++b) {
+          const int ux = ox + b - g.px;
+          if (ux < 0 || ux >= W) continue;
+          const int ix = ux / g.fx - sx0;
+          acc[a][b] += (iy ? (ix ? v[1][1] : v[1][0]) : (ix ? v[0][1] : v[0][0]));
+        }
       }
     }
-    d_w[(((int64_t)o * g.ic + c) * ky + a) * kx + b] = s;
   }
+#pragma unroll
+  for (int a = 0; a < KY; ++a)
+#pragma unroll
+    for (int b = 0; b < KX; ++b) d_w[(((int64_t)o * g.ic + c) * KY + a) * KX + b] = acc[a][b];
 }
 
 // out[c % mod] += sum_r x[r][c]; grid (ceil(cols/256), row chunks)
@@ -224,8 +247,11 @@ extern "C" int rcb_unfold_dense(const float* d_m, const rcb_upconv_geom* g, floa
   if (int rc = geom_of(g, &pg)) return rc;
   RCB_CHECK_ARG(d_m && d_w, "rcb_unfold_dense: null pointer");
   RCB_CHECK_ARG(pg.d == 1 && pg.fz == 1 && g->kz == 1, "rcb_unfold_dense: 1-D / 2-D grids only");
-  int64_t total = (int64_t)pg.oc * pg.ic * g->ky * g->kx;
-  unfold_dense_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(d_m, pg, g->ky, g->kx, d_w);
+  RCB_CHECK_ARG((g->ky == 5 || g->ky == 1) && g->kx == 5 && g->ky - 1 <= pg.fy && g->kx - 1 <= pg.fx,
+                "rcb_unfold_dense: built for the 5-tap first stage (1 x 5 or 5 x 5) with factor >= 4");
+  const int pairs = pg.oc * pg.ic, blocks = (pairs + 127) / 128;
+  if (g->ky == 5) unfold_dense_kernel<5, 5><<<blocks, 128, 0, (cudaStream_t)stream>>>(d_m, pg, d_w);
+  else unfold_dense_kernel<1, 5><<<blocks, 128, 0, (cudaStream_t)stream>>>(d_m, pg, d_w);
   RCB_CHECK_LAUNCH("rcb_unfold_dense");
   return 0;
 }

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (KernelError, MlpArgs, SampleArgs, UpconvGeom, UpdateArgs, check, ptr, stream)
+from ._lib import (KernelError, MlpArgs, ReduceArgs, SampleArgs, UpconvGeom, UpdateArgs, check, ptr, stream)
 
 
 def _round_up(v: int, m: int) -> int:
@@ -318,8 +318,8 @@ class FitEngine:
                 if i == 0 and self.dense1:
                     rows = g.h * g.w * g.ic
                     cols = g.h * g.fy * g.w * g.fx * g.oc          # dense fold: 1-D / 2-D grids only
-                    self.M1 = torch.empty(rows, cols, device=dev)
-                    self.M1T = torch.empty(cols, rows, device=dev)
+                    self.M1 = torch.zeros(rows, cols, device=dev)        # rcb_fold_dense writes the structural non-zeros only
+                    self.M1T = torch.zeros(cols, rows, device=dev)
                     continue
                 taps = (1 if g.kz == 1 else 2) * (1 if g.ky == 1 else 2) * (1 if g.kx == 1 else 2)
                 n = g.fz * g.fy * g.fx * taps * g.ic * g.oc
@@ -576,6 +576,7 @@ class FitEngine:
         levels = lv if isinstance(lv, (list, tuple)) else [lv]
         rows = levels[0].rows
         ws = self.workspace(rows, S)
+        ws["red_ready"] = False                 # per-row sample sums of an earlier backward are stale now
         items = rows * S
         citems = ws["citems"]
         st = stream()
@@ -857,6 +858,35 @@ class FitEngine:
                       "rcb_unfold_poly")
         return g
 
+    def reduce_samples(self, levels, ws, S: int, noise: Noise, rows: int):
+        """Patch modalities: sum the data gradient (and gradient x noise of every level) over the S samples once per
+        patch row (rcb_fit_reduce); the per-level update kernels then read these sums.  No-op for the single-level
+        modalities, whose row kernel reduces in shared memory."""
+        if self.patch_nums is None:
+            return
+        red = ws.get("red")
+        if red is None:
+            e = lambda n: torch.empty(rows, n, device=self.device)
+            red = ws["red"] = dict(mu=e(self.W), sig=[e(self.W) for _ in levels], mu_l=e(self.L), sig_l=e(self.L))
+        store = ws.get("eps_store")
+        a = ReduceArgs()
+        a.d_hw, a.d_lpe, a.lpe_slot = ptr(ws["d_hw"]), ptr(ws["d_lpe"]), ptr(self.lpe_slot)
+        for l, lv in enumerate(levels):
+            eps = noise.eps_for(lv.level)
+            if eps is None:
+                if store is None:
+                    raise KernelError("reduce_samples needs the noise kept by the sampling kernel")
+                eps = store[lv.level]
+            a.eps_w[l] = ptr(eps)
+            a.red_sig[l] = ptr(red["sig"][l])
+        a.eps_l = ptr(noise.eps_l if noise.eps_l is not None else store[3])
+        a.red_mu, a.red_mu_l, a.red_sig_l = ptr(red["mu"]), ptr(red["mu_l"]), ptr(red["sig_l"])
+        a.rows, a.S, a.n_w, a.n_l, a.ld_hw, a.n_levels = rows, S, self.W, self.L, self.ldw, len(levels)
+        a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
+        with self.section("update"):
+            check(self.lib.rcb_fit_reduce(C.byref(a), stream()), "rcb_fit_reduce")
+        ws["red_ready"] = True
+
     def update(self, lv: LevelState, ws, S: int, noise: Noise, *, with_data_grads: bool, adam: Optional[dict],
                g_loc=None, g_log_scale=None, grad_scale: float = 1.0, kl_out: Optional[torch.Tensor] = None,
                rows: Optional[int] = None):
@@ -875,6 +905,11 @@ class FitEngine:
                 a.eps_l = ptr(ws["eps_store"][3])
         a.lpe_slot = ptr(self.lpe_slot)
         a.rows_per_datum, a.sp_total, a.lpe_c = self.R, self.sp_total, self.latent_dim
+        if with_data_grads and ws is not None and ws.get("red_ready"):
+            red = ws["red"]
+            a.red_mu, a.red_sig = ptr(red["mu"]), ptr(red["sig"][lv.level])
+            if lv.level == 0:
+                a.red_mu_l, a.red_sig_l = ptr(red["mu_l"]), ptr(red["sig_l"])
         a.g_loc, a.g_log_scale = ptr(g_loc), ptr(g_log_scale)
         a.kl_out = ptr(kl_out)
         a.seed, a.row_offset = noise.seed, noise.row_offset

@@ -351,6 +351,7 @@ class PriorBNNmodel(nn.Module):
                 grads[k + ".weight"], grads[k + ".bias"] = g[k + ".weight"].clone(), g[k + ".bias"].clone()
         kl = torch.zeros(1, dtype=torch.float64, device=self.device)
         per_level = []
+        eng.reduce_samples(self._levels, ws, 1, noise, N)
         for l in self._levels:
             g_loc, g_ls = torch.empty_like(l.loc.data), torch.empty_like(l.log_scale.data)
             l.beta_scalar = float(kl_beta)
@@ -388,6 +389,7 @@ class PriorBNNmodel(nn.Module):
             if world > 1:        # ONE collective for all shared-mapping gradients, overlapped with the posterior update
                 work = dist.all_reduce(sm.grad, op=dist.ReduceOp.SUM, async_op=True)
         kl_step.zero_()
+        eng.reduce_samples(self._levels, ws, 1, noise, N)
         for l in self._levels:
             eng.update(l, ws, 1, noise, with_data_grads=True, adam=cfg, kl_out=kl_step, rows=N)
         if training_mappings:

@@ -67,6 +67,7 @@ class _Predict(torch.autograd.Function):
         dy = dy.contiguous().view(rows * S, model.engine.pix, model.engine.out)
         model.engine.mlp(ws, rows, S, ctx.x, mode=2, dy=dy)
         model.engine.backward_features(ws, rows, S)
+        model.engine.reduce_samples(levels, ws, S, noise, rows)
         grads = []
         for lv in levels:
             g_loc, g_ls = torch.empty_like(lv.loc.data), torch.empty_like(lv.log_scale.data)
@@ -470,6 +471,7 @@ class TestBNNmodel(nn.Module):
         coef = 2.0 / (S * eng.pix * eng.out)
         eng.mlp(ws, rows, S, x, mode=1, y=y, coef=coef)
         eng.backward_features(ws, rows, S)
+        eng.reduce_samples(levels, ws, S, noise, rows)
         for lv in levels:
             if do_anneal:
                 eng.group_kl(lv)            # KL of the pre-step posterior ...
