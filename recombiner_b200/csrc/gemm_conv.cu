@@ -64,40 +64,50 @@ __global__ void fold_poly_kernel(const float* __restrict__ w, PolyGeom g, int kz
 
 // dense fold (2-D / 1-D grids only): m[(sy,sx,ic)][(oy,ox,oc)] = sum of the taps (a, b) of w[oc][ic][a][b] that carry
 // source pixel (sy, sx) to output pixel (oy, ox) through the nearest-upsampling; m_t is its transpose.
-// One thread per (oc, ic) pair keeps the pair's KY x KX taps in registers and walks the output pixels: the taps of a
-// pixel fall on at most 2 x 2 source pixels (KY - 1 <= fy, KX - 1 <= fx), whose sums are written; every other entry of
-// m / m_t is structurally zero and is never touched (the caller zeroes the buffers once).  TRANSPOSED selects which of
-// the two matrices is written and the thread order that makes its stores contiguous (oc fastest for m, ic for m_t).
-// (A thread per matrix element re-deriving its taps cost 60 us per matrix for the 512 x 4096 cifar fold.)
+// One thread per (output pixel, (oc, ic) pair): the taps of a pixel fall on at most 2 x 2 source pixels (KY - 1 <= fy,
+// KX - 1 <= fx), whose sums are written; every other entry of m / m_t is structurally zero and is never touched (the
+// caller zeroes the buffers once).  TRANSPOSED selects which of the two matrices is written and the thread order that
+// makes its stores contiguous (oc fastest for m, ic for m_t).  (A thread per matrix ELEMENT re-deriving its taps with
+// integer divisions cost 60 us per matrix for the 512 x 4096 cifar fold; a thread per pair walking all pixels, 170 us.)
 template <int KY, int KX, bool TRANSPOSED>
 __global__ void __launch_bounds__(128) fold_dense_kernel(const float* __restrict__ w, PolyGeom g, float* __restrict__ out) {
   const int H = g.h * g.fy, W = g.w * g.fx;
   const int64_t rows = (int64_t)g.h * g.w * g.ic, cols = (int64_t)H * W * g.oc;
-  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pair >= g.oc * g.ic) return;
+  const int npairs = g.oc * g.ic;
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)npairs * H * W) return;
+  const int pair = (int)(e % npairs), pixel = (int)(e / npairs);
   const int o = TRANSPOSED ? pair / g.ic : pair % g.oc, c = TRANSPOSED ? pair % g.ic : pair / g.oc;
   float wr[KY][KX];
 #pragma unroll
   for (int a = 0; a < KY; ++a)
 #pragma unroll
     for (int b = 0; b < KX; ++b) wr[a][b] = __ldg(w + (((int64_t)o * g.ic + c) * KY + a) * KX + b);
-  for (int oy = 0; oy < H; ++oy) {
+  {
+    const int oy = pixel / W, ox = pixel - oy * W;
     const int sy0 = max(oy - g.py, 0) / g.fy;
-    for (int ox = 0; ox < W; ++ox) {
+    {
       const int sx0 = max(ox - g.px, 0) / g.fx;
       float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+      int ixs[KX];                                 // per tap column: 0 / 1 = which source column, -1 = outside
+#pragma unroll
+      for (int b = 0; b < KX; ++b) {
+        const int ux = ox + b - g.px;
+        ixs[b] = (ux < 0 || ux >= W) ? -1 : ux / g.fx - sx0;
+      }
 #pragma unroll
       for (int a = 0; a < KY; ++a) {
         const int uy = oy + a - g.py;
         if (uy < 0 || uy >= H) continue;
-        const int iy = uy / g.fy - sy0;
+        const bool hi = uy / g.fy != sy0;
+        float r0 = 0.f, r1 = 0.f;                  // this tap row's sums for the two source columns, in b order
 #pragma unroll
         for (int b = 0; b < KX; ++b) {
-          const int ux = ox + b - g.px;
-          if (ux < 0 || ux >= W) continue;
-          const int ix = ux / g.fx - sx0;
-          acc[iy][ix] += wr[a][b];
+          if (ixs[b] == 0) r0 += wr[a][b];
+          else if (ixs[b] == 1) r1 += wr[a][b];
         }
+        if (hi) { acc[1][0] += r0; acc[1][1] += r1; }
+        else { acc[0][0] += r0; acc[0][1] += r1; }
       }
 #pragma unroll
       for (int iy = 0; iy < 2; ++iy)
@@ -166,7 +176,8 @@ extern "C" int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m
   RCB_CHECK_ARG(pg.d == 1 && pg.fz == 1 && g->kz == 1, "rcb_fold_dense: 1-D / 2-D grids only");
   RCB_CHECK_ARG((g->ky == 5 || g->ky == 1) && g->kx == 5 && g->ky - 1 <= pg.fy && g->kx - 1 <= pg.fx,
                 "rcb_fold_dense: built for the 5-tap first stage (1 x 5 or 5 x 5) with factor >= 4");
-  const int pairs = pg.oc * pg.ic, blocks = (pairs + 127) / 128;
+  const int64_t threads = (int64_t)pg.oc * pg.ic * pg.h * pg.fy * pg.w * pg.fx;
+  const int blocks = (int)((threads + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   if (g->ky == 5) {
     fold_dense_kernel<5, 5, false><<<blocks, 128, 0, st>>>(w, pg, m);

@@ -120,53 +120,40 @@ __global__ void unfold_poly_kernel(const float* __restrict__ d_w_eff, PolyGeom g
 
 // d_w[o][c][a][b] = sum over output pixels whose tap (a,b) lands inside the grid of
 // d_m[(sy,sx,c)][(oy,ox,o)] with (sy,sx) the source pixel under that tap
-// One thread per (oc, ic) pair keeps the pair's KY x KX tap gradients in registers and walks the output pixels, reading
-// the (at most 2 x 2) entries of d_m that the pixel's taps fall on -- consecutive threads read consecutive oc, the
-// innermost index of d_m.  Per tap the terms are added in (oy, ox) order, as a thread per tap would.
+// One thread per (tap row a, (oc, ic) pair), oc fastest: d_m's innermost index is oc, so a warp reads 128 contiguous
+// bytes per (output pixel, source pixel).  The thread walks the output pixels whose tap row a is inside the grid and
+// adds, for each of its KX taps, the entry of the source pixel the tap falls on (terms in (oy, ox) order).
 template <int KY, int KX>
 __global__ void __launch_bounds__(128) unfold_dense_kernel(const float* __restrict__ d_m, PolyGeom g, float* __restrict__ d_w) {
   const int H = g.h * g.fy, W = g.w * g.fx;
   const int64_t cols = (int64_t)H * W * g.oc;
-  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pair >= g.oc * g.ic) return;
+  const int npairs = g.oc * g.ic;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= npairs * KY) return;
+  const int pair = e % npairs, a = e / npairs;
   const int o = pair % g.oc, c = pair / g.oc;
-  float acc[KY][KX];
+  float acc[KX];
 #pragma unroll
-  for (int a = 0; a < KY; ++a)
-#pragma unroll
-    for (int b = 0; b < KX; ++b) acc[a][b] = 0.f;
+  for (int b = 0; b < KX; ++b) acc[b] = 0.f;
   for (int oy = 0; oy < H; ++oy) {
-    const int sy0 = max(oy - g.py, 0) / g.fy;
+    const int uy = oy + a - g.py;
+    if (uy < 0 || uy >= H) continue;
+    const int sy = uy / g.fy;
     for (int ox = 0; ox < W; ++ox) {
       const int sx0 = max(ox - g.px, 0) / g.fx;
-      float v[2][2];
+      const float* base = d_m + (((int64_t)sy * g.w) * g.ic + c) * cols + ((int64_t)oy * W + ox) * g.oc + o;
+      const float v0 = base[(int64_t)sx0 * g.ic * cols];
+      const float v1 = sx0 + 1 < g.w ? base[(int64_t)(sx0 + 1) * g.ic * cols] : 0.f;
 #pragma unroll
-      for (int iy = 0; iy < 2; ++iy)
-#pragma unroll
-        for (int ix = 0; ix < 2; ++ix) {
-          const int sy = sy0 + iy, sx = sx0 + ix;
-          v[iy][ix] = (sy < g.h && sx < g.w)
-                          ? d_m[(((int64_t)sy * g.w + sx) * g.ic + c) * cols + ((int64_t)oy * W + ox) * g.oc + o] : 0.f;
-        }
-#pragma unroll
-      for (int a = 0; a < KY; ++a) {
-        const int uy = oy + a - g.py;
-        if (uy < 0 || uy >= H) continue;
-        const int iy = uy / g.fy - sy0;
-#pragma unroll
-        for (int b = 0; b < KX; ++b) {
-          const int ux = ox + b - g.px;
-          if (ux < 0 || ux >= W) continue;
-          const int ix = ux / g.fx - sx0;
-          acc[a][b] += (iy ? (ix ? v[1][1] : v[1][0]) : (ix ? v[0][1] : v[0][0]));
-        }
+      for (int b = 0; b < KX; ++b) {
+        const int ux = ox + b - g.px;
+        if (ux < 0 || ux >= W) continue;
+        acc[b] += (ux / g.fx - sx0) ? v1 : v0;
       }
     }
   }
 #pragma unroll
-  for (int a = 0; a < KY; ++a)
-#pragma unroll
-    for (int b = 0; b < KX; ++b) d_w[(((int64_t)o * g.ic + c) * KY + a) * KX + b] = acc[a][b];
+  for (int b = 0; b < KX; ++b) d_w[(((int64_t)o * g.ic + c) * KY + a) * KX + b] = acc[b];
 }
 
 // out[c % mod] += sum_r x[r][c]; grid (ceil(cols/256), row chunks)
@@ -249,7 +236,7 @@ extern "C" int rcb_unfold_dense(const float* d_m, const rcb_upconv_geom* g, floa
   RCB_CHECK_ARG(pg.d == 1 && pg.fz == 1 && g->kz == 1, "rcb_unfold_dense: 1-D / 2-D grids only");
   RCB_CHECK_ARG((g->ky == 5 || g->ky == 1) && g->kx == 5 && g->ky - 1 <= pg.fy && g->kx - 1 <= pg.fx,
                 "rcb_unfold_dense: built for the 5-tap first stage (1 x 5 or 5 x 5) with factor >= 4");
-  const int pairs = pg.oc * pg.ic, blocks = (pairs + 127) / 128;
+  const int blocks = (pg.oc * pg.ic * g->ky + 127) / 128;
   if (g->ky == 5) unfold_dense_kernel<5, 5><<<blocks, 128, 0, (cudaStream_t)stream>>>(d_m, pg, d_w);
   else unfold_dense_kernel<1, 5><<<blocks, 128, 0, (cudaStream_t)stream>>>(d_m, pg, d_w);
   RCB_CHECK_LAUNCH("rcb_unfold_dense");
