@@ -281,7 +281,10 @@ extern "C" int rcb_gemm_tc(const float* A, int lda, const float* Bt, int ldbt, f
                 "rcb_gemm_tc: operands must be 16-byte aligned");
   RCB_CHECK_ARG(!bias || bias_mod > 0, "rcb_gemm_tc: bias_mod must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  if (N > 64) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st);
+  // 128-wide tiles unless they would leave most SMs idle (skinny problems of prior training: M = 1024 rows, N = 512):
+  // 64-wide tiles double the CTA count for the same K loop
+  const int64_t ctas128 = (int64_t)ceil_div(M, TC_BM) * ceil_div(N, 128);
+  if (N > 64 && ctas128 >= 96) return launch_tc<128>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st);
   return launch_tc<64>(A, lda, Bt, ldbt, C, ldc, M, N, K, bias, bias_mod, act, accumulate, st);
 }
 
