@@ -606,6 +606,12 @@ class FitEngine:
                     self._gemm(ws["hw"], self.offsets[l], self.ldw, self.A[l], self.A[l].shape[1],
                                ws["wt"], self.offsets[l], self.ldw, items, c, c, Bt=self.AT[l])
         join = self._fork(reparam)
+        self._upsample_chain(ws, citems)
+        join()
+        return ws
+
+    def _upsample_chain(self, ws, citems: int):
+        """lpe -> a1 -> a2 -> pe: the three folded nearest-up + conv stages (prior_model.py:47-59)."""
         g1, g2, g3 = self.geoms
         half = ws["a2_is_half"] = bool(self.half_acts and self.f2_half and self._half_staged)
         if half and "a2h" not in ws:
@@ -646,8 +652,40 @@ class FitEngine:
                                                    C.byref(g3), citems, 0, stream()), "rcb_upconv_fwd_tc_h[3]")
             else:
                 self._upconv_fwd(2, ws["a2"], ws["pe"], citems, 0)
-        join()
-        return ws
+
+    def upsample_latents(self, latent: torch.Tensor) -> torch.Tensor:
+        """(S, rows, L) latent grids (channel-last per row) -> (rows, S, pixels, 16) positional encodings: the kernel
+        form of utils.map_lpe_to_inr_inputs (utils.py:4-120), stitching the rows of a datum into one grid, running the
+        folded upsampler on it and cutting the result back into patches.  Evaluation only (no autograd graph)."""
+        if self.A is None and getattr(self, "conv_w", None) is None:
+            raise KernelError("the upsampler weights have not been staged (set_mappings / set_upsampler)")
+        S, rows = int(latent.shape[0]), int(latent.shape[1])
+        ws = self.workspace(rows, S)
+        D, C, sp = rows // self.R, self.latent_dim, self.sp
+        lat = latent.to(self.device, torch.float32).reshape(S, D, self.R, sp, C).permute(1, 0, 2, 3, 4)     # (D, S, R, sp, C)
+        dst = ws["lpe"].view(D, S, self.sp_total, C)
+        if self.lpe_slot is None:
+            dst.copy_(lat.reshape(D, S, self.sp_total, C))
+        else:
+            dst[:, :, self.lpe_slot.reshape(-1).long(), :] = lat.reshape(D, S, self.R * sp, C)
+        half = bool(self.half_acts and self.f2_half and self._half_staged)
+        if half and self.dense1:
+            if "lpe_h" not in ws:
+                ws["lpe_h"] = torch.empty(ws["lpe"].shape, dtype=torch.float16, device=self.device)
+            ws["lpe_h"].copy_(ws["lpe"])
+        self._upsample_chain(ws, ws["citems"])
+        pe = (ws["pe_h"] if ws.get("pe_is_half") else ws["pe"]).float().view(D, S, self.pix_total, 16)
+        if self.patch_nums is None:
+            return pe.view(rows, S, self.pix, 16).clone()
+        if getattr(self, "_patch_pixels", None) is None:          # stitched-grid offset of every pixel of every patch
+            pad = 3 - self.data_dim
+            fp = [1] * pad + list(self.full_pixels)
+            pp = [1] * pad + list(self.pixel_sizes)
+            z, y, x = np.meshgrid(np.arange(pp[0]), np.arange(pp[1]), np.arange(pp[2]), indexing="ij")
+            inner = (z * fp[1] * fp[2] + y * fp[2] + x).reshape(-1)
+            self._patch_pixels = torch.as_tensor((self._patch_origin[:, None] + inner[None, :]).reshape(-1), device=self.device)
+        out = pe[:, :, self._patch_pixels, :].view(D, S, self.R, self.pix, 16)
+        return out.permute(0, 2, 1, 3, 4).reshape(rows, S, self.pix, 16).contiguous()
 
     def set_step_state(self, buf: torch.Tensor, seed: int, step: int, adam: dict, t: int, beta_scalar: float = -1.0):
         """Write the per-step scalars a captured step reads from device memory (rcb_step_state)."""

@@ -41,8 +41,24 @@ class Upsample(nn.Module):
         self.kernel_dim = kernel_dim
 
     def forward(self, x):
-        raise RuntimeError("Upsample.forward is not part of the B200 fit path: the upsampler runs inside "
-                           "FitEngine as folded polyphase convolutions (rcb_upconv_fwd/bwd)")
+        """(B, 128, *grid) -> (B, 16, *pixels) as the reference module computes it (prior_model.py:47-59), on the folded
+        polyphase kernels.  Evaluation only: the fit path differentiates through FitEngine, not through this call."""
+        from . import utils as _utils
+        from ._lib import KernelError as _KE
+        if not x.is_cuda:
+            raise _KE("Upsample.forward runs on the sm_100a kernels: pass a CUDA tensor (no CPU fallback)")
+        d = self.kernel_dim
+        grid = list(x.shape[2:])
+        factors = [1] * d
+        for i in (1, 2, 3):
+            f = getattr(self, f"up{i}").scale_factor
+            f = [int(v) for v in f] if isinstance(f, (tuple, list)) else [int(f)] * d
+            factors = [a * b for a, b in zip(factors, f)]
+        pixels = [g * f for g, f in zip(grid, factors)]
+        eng = _utils._engine_for(self, int(x.shape[1]), pixels, factors, False, None, d, x.device)
+        lat = x.detach().movedim(1, -1).reshape(1, x.shape[0], -1)            # (S = 1, rows, L) channel-last
+        pe = eng.upsample_latents(lat)                                        # (rows, 1, pixels, 16)
+        return pe[:, 0].reshape(x.shape[0], *pixels, pe.shape[-1]).movedim(-1, 1).contiguous()
 
 
 # --------------------------------------------------------------------------- #

@@ -87,3 +87,85 @@ def fourier_features(coords, feature_size):
     w = torch.exp(torch.linspace(0, np.log(1024), feature_size // (2 * d), device=coords.device))
     arg = torch.matmul(coords.unsqueeze(-1), w.unsqueeze(0)).view(*coords.shape[:-1], -1)
     return torch.cat([torch.cos(np.pi * arg), torch.sin(np.pi * arg)], dim=-1)
+
+
+# --------------------------------------------------------------------------- #
+# functional glue of the reference, on the kernels (utils.py:4-198)
+# --------------------------------------------------------------------------- #
+_ENGINES = {}
+
+
+def _engine_for(upsample_net, latent_dim, pixel_sizes, upsample_factors, patch, patch_nums, data_dim, device):
+    """A FitEngine holding this upsampler's folded weights (cached per module object and weight version)."""
+    from .engine import FitEngine
+    scales = [getattr(upsample_net, f"up{i}").scale_factor for i in (1, 2, 3)]
+    scales = [tuple(int(v) for v in f) if isinstance(f, (tuple, list)) else int(f) for f in scales]
+    pads = [int(getattr(upsample_net, f"conv{i}").padding[0]) for i in (1, 2, 3)]
+    versions = tuple(p._version for p in upsample_net.parameters())
+    key = (id(upsample_net), tuple(pixel_sizes), tuple(upsample_factors), bool(patch), tuple(patch_nums) if patch else None, str(device))
+    ent = _ENGINES.get(key)
+    if ent is None or ent[1] != versions:
+        in_dim = 34 if data_dim == 3 else 32
+        eng = ent[0] if ent is not None else FitEngine([in_dim, 32, 32, 32, 3], data_dim, list(pixel_sizes), list(upsample_factors),
+                                                       latent_dim, scales, pads, 30.0, device,
+                                                       patch_nums=list(patch_nums) if patch else None)
+        eng.set_mappings([torch.zeros(c, c) for c in eng.counts], upsample_net.state_dict())
+        _ENGINES[key] = ent = (eng, versions)
+    return ent[0]
+
+
+def map_lpe_to_inr_inputs(upsample_net, latent_pe, latent_dim, pixel_sizes, upsample_factors, patch, patch_nums, data_dim):
+    """Latent positional encodings -> per-pixel encodings, (data_num, sample_size, pixels, 16) (utils.py:4-120): the
+    rows of a datum are stitched into one grid, upsampled as a whole by the folded polyphase kernels and cut back into
+    patches.  latent_pe: (sample_size, data_num, L) or (sample_size, data_num, *grid, latent_dim).  Evaluation only: the
+    result carries no autograd graph (the fit path differentiates through FitEngine, not through this function)."""
+    if not latent_pe.is_cuda:
+        from ._lib import KernelError
+        raise KernelError("map_lpe_to_inr_inputs runs on the sm_100a kernels: pass CUDA tensors (no CPU fallback)")
+    S, N = latent_pe.shape[:2]
+    eng = _engine_for(upsample_net, latent_dim, pixel_sizes, upsample_factors, patch, patch_nums, data_dim, latent_pe.device)
+    return eng.upsample_latents(latent_pe.detach().reshape(S, N, -1))
+
+
+def map_hierarchical_model_to_int_weights(use_hierarchical_model, loc, scale, h_loc, h_scale, hh_loc, hh_scale, sample_size,
+                                          hierarchical_patch_nums, patch_nums, data_dim):
+    """h_w (data_num, sample_size, W) = mu + sigma * eps, plus the level-2 and level-3 terms of the patch hierarchy,
+    each with its own per-patch noise (utils.py:122-198), drawn by rcb_fit_sample (Philox keyed from torch's global
+    generator, so `torch.manual_seed` controls it).  scale arguments are standard deviations, as in the reference.
+    Evaluation only (no autograd graph)."""
+    import ctypes as C
+    from . import _lib
+    from ._lib import KernelError, SampleArgs, check, ptr, stream
+    if not loc.is_cuda:
+        raise KernelError("map_hierarchical_model_to_int_weights runs on the sm_100a kernels: pass CUDA tensors")
+    lib = _lib.load()
+    dev = loc.device
+    N, W = loc.shape
+    ld = (W + 3) // 4 * 4
+    hw = torch.zeros(N * sample_size, ld, device=dev)
+    seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    levels = [(loc, scale, None)]
+    if use_hierarchical_model:
+        R = int(np.prod(patch_nums))
+        l2 = hierarchical_patch_nums['level2']
+        ng = [patch_nums[i] // l2[i] for i in range(data_dim)]
+        n = np.arange(N)
+        pc = np.unravel_index(n % R, patch_nums)
+        grp = np.ravel_multi_index([pc[i] // l2[i] for i in range(data_dim)], ng)
+        levels += [(h_loc, h_scale, (n // R) * int(np.prod(ng)) + grp), (hh_loc, hh_scale, n // R)]
+    keep = []
+    for li, (mu, sig, row_map) in enumerate(levels):
+        mu = mu.detach().to(dev, torch.float32).contiguous()
+        raw = torch.log(torch.expm1(6.0 * sig.detach().to(dev, torch.float32))).contiguous()      # inverse of softplus(.)/6
+        a = SampleArgs()
+        a.loc, a.log_scale, a.hw = ptr(mu), ptr(raw), ptr(hw)
+        if row_map is not None:
+            rm = torch.as_tensor(np.asarray(row_map).astype(np.int32), device=dev)
+            keep.append(rm)
+            a.row_map = ptr(rm)
+        a.seed, a.row_offset = (42 << 32) | seed, 0
+        a.rows, a.S, a.P, a.n_w, a.n_l, a.ld_hw = N, sample_size, W, W, 0, ld
+        a.step, a.tensor_id, a.accumulate = 0, li, int(li > 0)
+        keep += [mu, raw]
+        check(lib.rcb_fit_sample(C.byref(a), stream()), "rcb_fit_sample")
+    return hw[:, :W].reshape(N, sample_size, W).clone()
