@@ -696,11 +696,12 @@ __global__ void __launch_bounds__(256) transpose_phases_kernel(const float* __re
 // consecutive rows -- a contiguous 128 * cols block of the input, read as float4 -- through a padded shared-memory tile
 // and writes 32 consecutive rows of one channel per warp instruction.  Same outputs; 4 x fewer, 4 x larger CTAs and no
 // half-empty 32-column tiles for the 16-channel tensors.
-constexpr int TW_ROWS = 128;
+// rows per CTA: a tile of ~32 KB whatever the channel count (128 rows of 64 channels, 512 rows of 16)
+static inline int tw_rows(int cols) { return cols <= 16 ? 512 : (cols <= 32 ? 256 : 128); }
 
 template <int MODE>        // 0: x-shifted copies (transpose_xshift), 1: phase planes (transpose_phases)
 __global__ void __launch_bounds__(256) transpose_wide_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows,
-                                                             int cols, int h, int w, int fy, int fx) {
+                                                             int cols, int h, int w, int fy, int fx, int TW_ROWS) {
   extern __shared__ float tw_tile[];                  // [TW_ROWS + 2][cols + 1]; row 0 = the row before the block
   const int ldt = cols + 1;
   const int64_t r0 = (int64_t)blockIdx.x * TW_ROWS;
@@ -926,8 +927,9 @@ extern "C" int rcb_transpose_xshift(const float* in, float* out, int64_t rows, i
   RCB_CHECK_ARG(in && out, "rcb_transpose_xshift: null tensor");
   RCB_CHECK_ARG(rows > 0 && cols > 0 && w > 0 && rows % w == 0, "rcb_transpose_xshift: rows must be whole lines of w pixels");
   if (cols <= 64 && cols % 4 == 0 && (((uintptr_t)in) & 15) == 0) {
-    const size_t smem = sizeof(float) * (TW_ROWS + 2) * (size_t)(cols + 1);
-    transpose_wide_kernel<0><<<(unsigned)ceil_div(rows, (int64_t)TW_ROWS), 256, smem, (cudaStream_t)stream>>>(in, out, rows, cols, 1, w, 1, 1);
+    const int tr = tw_rows(cols);
+    const size_t smem = sizeof(float) * (tr + 2) * (size_t)(cols + 1);
+    transpose_wide_kernel<0><<<(unsigned)ceil_div(rows, (int64_t)tr), 256, smem, (cudaStream_t)stream>>>(in, out, rows, cols, 1, w, 1, 1, tr);
     RCB_CHECK_LAUNCH("rcb_transpose_xshift");
     return 0;
   }
@@ -944,8 +946,9 @@ extern "C" int rcb_transpose_phases(const float* in, float* out, int64_t rows, i
   RCB_CHECK_ARG(rows > 0 && cols > 0 && h > 0 && w > 0 && fy > 0 && fx > 0 && rows % ((int64_t)h * fy * w * fx) == 0,
                 "rcb_transpose_phases: rows must be whole (h*fy, w*fx) grids");
   if (cols <= 64 && cols % 4 == 0 && (((uintptr_t)in) & 15) == 0) {
-    const size_t smem = sizeof(float) * (TW_ROWS + 2) * (size_t)(cols + 1);
-    transpose_wide_kernel<1><<<(unsigned)ceil_div(rows, (int64_t)TW_ROWS), 256, smem, (cudaStream_t)stream>>>(in, out, rows, cols, h, w, fy, fx);
+    const int tr = tw_rows(cols);
+    const size_t smem = sizeof(float) * (tr + 2) * (size_t)(cols + 1);
+    transpose_wide_kernel<1><<<(unsigned)ceil_div(rows, (int64_t)tr), 256, smem, (cudaStream_t)stream>>>(in, out, rows, cols, h, w, fy, fx, tr);
     RCB_CHECK_LAUNCH("rcb_transpose_phases");
     return 0;
   }

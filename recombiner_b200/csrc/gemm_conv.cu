@@ -179,13 +179,17 @@ extern "C" int rcb_fold_dense(const float* w, const rcb_upconv_geom* g, float* m
   const int64_t threads = (int64_t)pg.oc * pg.ic * pg.h * pg.fy * pg.w * pg.fx;
   const int blocks = (int)((threads + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g->ky == 5) {
-    fold_dense_kernel<5, 5, false><<<blocks, 128, 0, st>>>(w, pg, m);
-    if (m_t) fold_dense_kernel<5, 5, true><<<blocks, 128, 0, st>>>(w, pg, m_t);
-  } else {
-    fold_dense_kernel<1, 5, false><<<blocks, 128, 0, st>>>(w, pg, m);
-    if (m_t) fold_dense_kernel<1, 5, true><<<blocks, 128, 0, st>>>(w, pg, m_t);
+  if (m_t) {
+    // the transposed matrix is the cheap one to fold (consecutive threads read neighbouring weights: 15 us against 51 us
+    // for the 512 x 4096 cifar fold); m is then an exact transposed copy of it
+    if (g->ky == 5) fold_dense_kernel<5, 5, true><<<blocks, 128, 0, st>>>(w, pg, m_t);
+    else fold_dense_kernel<1, 5, true><<<blocks, 128, 0, st>>>(w, pg, m_t);
+    RCB_CHECK_LAUNCH("rcb_fold_dense");
+    const int64_t rows = (int64_t)pg.h * pg.w * pg.ic, cols = (int64_t)pg.h * pg.fy * pg.w * pg.fx * pg.oc;
+    return rcb_transpose(m_t, rows, m, cols, (int)cols, (int)rows, stream);
   }
+  if (g->ky == 5) fold_dense_kernel<5, 5, false><<<blocks, 128, 0, st>>>(w, pg, m);
+  else fold_dense_kernel<1, 5, false><<<blocks, 128, 0, st>>>(w, pg, m);
   RCB_CHECK_LAUNCH("rcb_fold_dense");
   return 0;
 }
