@@ -348,6 +348,11 @@ typedef struct {
 } rcb_reduce_args;
 int rcb_fit_reduce(const rcb_reduce_args* a, rcb_stream_t stream);
 
+/* out[i] = softplus(in[i]) / 6 (threshold 20): the standard-deviation transform `st` of test_model.py:101 /
+ * prior_model.py:88 in the arithmetic every kernel here uses, for the q_scale / p_scale inputs of rcb_rec_encode and
+ * rcb_rec_decode (encoder and decoder then agree on every bit). */
+int rcb_std_transform(const float* in, float* out, int64_t n, rcb_stream_t stream);
+
 /* Per-(row, block) KL in nats, f64 accumulation (test_model.py:384-388). */
 int rcb_group_kl(const float* loc, const float* log_scale, const float* p_loc,
                  const float* p_log_scale, const int* group_start, const int* group_end,

@@ -112,6 +112,7 @@ SIGNATURES = {
     "rcb_transpose_xshift": [P, P, I64, I32, I32, P],
     "rcb_fit_update": [C.POINTER(UpdateArgs), P],
     "rcb_fit_reduce": [C.POINTER(ReduceArgs), P],
+    "rcb_std_transform": [P, P, I64, P],
     "rcb_group_kl": [P, P, P, P, P, P, P, I32, I32, I32, P],
     "rcb_anneal_beta": [P, P, P, I32, I32, F64, F64, F64, F64, P],
     "rcb_pick_block": [P, P, P, I32, I32, P],

@@ -555,6 +555,13 @@ __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ 
     if (i0 + e < n) dst[i0 + e] = __float2half_rn(src[i0 + e]);
 }
 
+// out = softplus(in) / 6 with the same device arithmetic the fit kernels use for the posterior / prior scales, so that the
+// encoder, the decoder and the fit agree on every bit of a standard deviation (test_model.py:101)
+__global__ void __launch_bounds__(256) std_transform_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = std_transform(in[i]);
+}
+
 __global__ void set_step_state_kernel(rcb_step_state* dev, long long seed, int step, float ss, float bc, float beta) {
   dev->seed = seed; dev->step = step; dev->adam_step_size = ss; dev->adam_bc2_sqrt = bc; dev->beta_scalar = beta;
 }
@@ -789,6 +796,15 @@ extern "C" int rcb_set_step_state(rcb_step_state* dev, int64_t seed, int step, f
   set_step_state_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev, (long long)seed, step, adam_step_size, adam_bc2_sqrt,
                                                           beta_scalar);
   RCB_CHECK_LAUNCH("rcb_set_step_state");
+  return 0;
+}
+
+extern "C" int rcb_std_transform(const float* in, float* out, int64_t n, rcb_stream_t stream) {
+  RCB_CHECK_ARG(in && out && n > 0, "rcb_std_transform: bad arguments");
+  const int64_t blocks = (n + 255) / 256;
+  RCB_CHECK_ARG(blocks < (1ll << 31), "rcb_std_transform: tensor too large");
+  std_transform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  RCB_CHECK_LAUNCH("rcb_std_transform");
   return 0;
 }
 

@@ -359,9 +359,22 @@ class TestBNNmodel(nn.Module):
         return (torch.as_tensor(rows, dtype=torch.int32, device=self.device).reshape(-1).contiguous(),
                 torch.as_tensor(blocks, dtype=torch.int32, device=self.device).reshape(-1).contiguous())
 
+    def _std(self, raw: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """softplus(raw) / 6 in the kernels' own arithmetic (rcb_std_transform): encoder, decoder and fit agree bit for bit."""
+        from ._lib import check, ptr, stream
+        raw = raw.contiguous()
+        out = torch.empty_like(raw) if out is None or out.shape != raw.shape else out
+        check(self.engine.lib.rcb_std_transform(ptr(raw), ptr(out), raw.numel(), stream()), "rcb_std_transform")
+        return out
+
     def _scales(self, li=0):
+        """(posterior, prior) standard deviations of a level as the REC kernels consume them; the buffers are reused
+        from round to round."""
         lv = self._levels[li]
-        return self.st(lv.log_scale.data).contiguous(), self.st(lv.p_log_scale).contiguous()
+        buf = self.__dict__.setdefault("_scale_bufs", {})
+        q = buf[(li, "q")] = self._std(lv.log_scale.data, buf.get((li, "q")))
+        p = buf[(li, "p")] = self._std(lv.p_log_scale, buf.get((li, "p")))
+        return q, p
 
     def _sample_group(self, li, row_idx, group_idx, n):
         self._ensure_rec(n)
@@ -433,7 +446,7 @@ class TestBNNmodel(nn.Module):
         blocks = torch.arange(lv.G, device=self.device, dtype=torch.int32).repeat(lv.rows).contiguous()
         idx = torch.as_tensor(np.asarray(indices).astype(np.int32), device=self.device).reshape(-1).contiguous()
         out = torch.zeros(lv.rows, lv.P, device=self.device)
-        _rec.decode(lv, lv.tables_ptr, self.st(lv.p_log_scale).contiguous(), rows, blocks, idx, n, out, None)
+        _rec.decode(lv, lv.tables_ptr, self._std(lv.p_log_scale), rows, blocks, idx, n, out, None)
         return out
 
     # ------------------------------------------------------------------- training --
