@@ -140,6 +140,11 @@ def test_short_schedule_tf32_fp32_reference_agree(trained_prior):
     arms = {"tf32": _gpu_arm(trained_prior, x, y, "tf32"), "fp32": _gpu_arm(trained_prior, x, y, "fp32"),
             "reference": _reference_arm(trained_prior, x, y)}
     print("\ntrajectory arms:", arms)
+    out = os.environ.get("RECOMBINER_TRAJECTORY_OUT")        # evidence for profiles/: the three arms' numbers as JSON
+    if out:
+        import json
+        with open(out, "w") as f:
+            json.dump(dict(arms=arms, n_fit=N_FIT, n_finetune=N_FINETUNE, rows=N_TEST, psnr_tol_db=PSNR_TOL_DB, kl_rtol=KL_RTOL), f, indent=1)
     names = list(arms)
     assert arms["tf32"]["psnr_fit"] > 15.0, "the fit did not move"        # sanity: this schedule reaches > 20 dB
     for i, a in enumerate(names):
