@@ -53,8 +53,9 @@ N_CAND = 65536
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/README.md); None where no capture exists yet
-TRAFFIC = {"mlp_fwd_bwd": 775.5e6, "conv3_fwd": 625.6e6, "conv2_fwd": 365.5e6, "conv3_bwd": 979.1e6,
-           "conv2_bwd": 490.6e6, "update": 320.6e6, "sample": 158.1e6}   # profiles/r1_ncu_full_final.csv
+TRAFFIC = {"mlp_fwd_bwd": 564.6e6, "update": 319.1e6, "sample": 120.3e6,    # profiles/r2_ncu_mlp_tc.csv, r2_ncu_update_sample.csv
+           "conv3_fwd": 448.0e6, "conv2_fwd": 151.0e6, "conv3_bwd": 804.0e6, "conv2_bwd": 449.0e6}   # profiles/r1_ncu_full_final.csv (kernels unchanged)
+REC_TRAFFIC = {"picked": 36.6e6, "spread": 1672.9e6}                       # profiles/r2_ncu_rec_encode_staged.csv
 
 
 def conv_bytes(eng, items: int):
@@ -618,9 +619,9 @@ def run_b200(args):
             # REC round: f64 quadratic form per (row, candidate, dimension); bound by the FP64 pipe once the tables
             # are staged through shared memory (they are shared by the rows of a run and mostly L2-resident)
             "rec": {"candidates_per_s": cand_per_s, "ms_per_round": t_round, "pairs_per_round": ROWS_PER_GPU * world,
-                    "roofline": rec_roof(t_round, None, "blocks picked by the rows themselves (largest KL): with the "
+                    "roofline": rec_roof(t_round, REC_TRAFFIC["picked"], "blocks picked by the rows themselves (largest KL): with the "
                                          "random-init workload they coincide, so the candidate tables are L2-resident"),
-                    "spread_over_all_blocks": dict(rec_roof(t_round_spread, None, "rows spread evenly over all G blocks: "
+                    "spread_over_all_blocks": dict(rec_roof(t_round_spread, REC_TRAFFIC["spread"], "rows spread evenly over all G blocks: "
                                                             "every table (0.99 GB in all) is streamed from HBM at least once"),
                                                    ms_per_round=t_round_spread,
                                                    candidates_per_s=ROWS_PER_GPU * world * N_CAND / (t_round_spread * 1e-3))},

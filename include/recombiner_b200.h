@@ -405,6 +405,11 @@ typedef struct {
 } rcb_rec_args;
 int rcb_rec_encode(const rcb_rec_args* a, rcb_stream_t stream);
 
+/* The (row, block) pairs of one round -- row i codes blocks[i] -- listed with equal blocks adjacent (rows_out,
+ * blocks_out: n entries each), the order rcb_rec_encode wants for its table sharing.  Replaces the host-side sort of
+ * round 1; the serial row loop it stands in for is test_model.py:807-818. */
+int rcb_rec_order(const int* blocks, int* rows_out, int* blocks_out, int n, int G, rcb_stream_t stream);
+
 /* Measurement aid: `ctas` x 256 threads x 16 independent chains of `iters` double-precision FMAs; *flop_out (host)
  * receives the FLOP count of the launch.  bench.py times it with CUDA events to get the FP64 peak the REC scoring
  * kernel's roofline is stated against. */

@@ -118,6 +118,7 @@ SIGNATURES = {
     "rcb_pick_block": [P, P, P, I32, I32, P],
     "rcb_rec_table": [P, P, P, I32, I32, P],
     "rcb_rec_encode": [C.POINTER(RecArgs), P],
+    "rcb_rec_order": [P, P, P, I32, I32, P],
     "rcb_ubench_dfma": [P, I32, I32, C.POINTER(F64), P],
     "rcb_rec_decode": [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, P],
     "rcb_prior_suffstats": [P, P, P, I32, I32, P],

@@ -546,6 +546,33 @@ __global__ void rec_decode_kernel(const int* __restrict__ pair_row, const int* _
   }
 }
 
+// Pairs of a round grouped by block (counting sort in one CTA): rows_out / blocks_out list the rows 0 .. n-1 so that
+// equal blocks are adjacent -- the scoring kernel shares every table value between the rows of such a run.  The order
+// inside a run is whatever the atomics give; each row's result is independent of the grouping (bit-identical).
+__global__ void __launch_bounds__(1024) rec_order_kernel(const int* __restrict__ blocks, int* __restrict__ rows_out,
+                                                         int* __restrict__ blocks_out, int n, int G) {
+  extern __shared__ int ro_cnt[];                   // [G] counts, then running offsets
+  for (int g = threadIdx.x; g < G; g += blockDim.x) ro_cnt[g] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = blocks[i];
+    if (b < 0 || b >= G) __trap();
+    atomicAdd(&ro_cnt[b], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int g = 0; g < G; ++g) { const int c = ro_cnt[g]; ro_cnt[g] = run; run += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = blocks[i];
+    const int pos = atomicAdd(&ro_cnt[b], 1);
+    rows_out[pos] = i;
+    blocks_out[pos] = b;
+  }
+}
+
 // FP64 FMA peak of the device, for the roofline of the REC scoring kernel (bench.py): 16 independent DFMA chains per
 // thread, nothing else in the loop.  2 * 16 * iters * threads FLOP per launch.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
@@ -566,6 +593,18 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
 }  // namespace rcb
 
 using namespace rcb;
+
+extern "C" int rcb_rec_order(const int* blocks, int* rows_out, int* blocks_out, int n, int G, rcb_stream_t stream) {
+  RCB_CHECK_ARG(blocks && rows_out && blocks_out && n > 0 && G > 0 && G <= 40000, "rcb_rec_order: bad arguments");
+  const size_t smem = sizeof(int) * (size_t)G;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rec_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rcb_rec_order: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+  }
+  rec_order_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(blocks, rows_out, blocks_out, n, G);
+  RCB_CHECK_LAUNCH("rcb_rec_order");
+  return 0;
+}
 
 extern "C" int rcb_ubench_dfma(double* scratch, int ctas, int iters, double* flop_out, rcb_stream_t stream) {
   RCB_CHECK_ARG(scratch && ctas > 0 && iters > 0, "rcb_ubench_dfma: bad arguments");

@@ -423,17 +423,23 @@ class TestBNNmodel(nn.Module):
         n = int(np.ceil(2 ** self.bit_per_group))
         self._ensure_rec(n)
         lv = self._levels[level]
-        rows = torch.arange(lv.rows, dtype=torch.int32, device=self.device)
+        bufs = self.__dict__.setdefault("_round_bufs", {})
+        if level not in bufs:
+            i32 = lambda: torch.empty(lv.rows, dtype=torch.int32, device=self.device)
+            bufs[level] = (i32(), i32(), i32())                  # picked blocks, pair rows, pair blocks
+        picked, pair_rows, pair_blocks = bufs[level]
         if blocks is None:
             kl = self.engine.group_kl(lv)
-            blocks = torch.empty(lv.rows, dtype=torch.int32, device=self.device)
+            blocks = picked
             check(self.engine.lib.rcb_pick_block(ptr(kl), ptr(lv.coded), ptr(blocks), lv.rows, lv.G, stream()),
                   "rcb_pick_block")
+        else:
+            blocks = blocks.to(device=self.device, dtype=torch.int32).contiguous()
         q_scale, p_scale = self._scales(level)
-        # pairs sorted by block: the kernel scores runs of equal blocks against one pass over the candidate table
-        order = torch.argsort(blocks, stable=True)
-        _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, rows[order].contiguous(),
-                    blocks[order].contiguous(), n, lv.max_D, apply=apply)
+        # pairs grouped by block: the kernel scores runs of equal blocks against one pass over the candidate table
+        check(self.engine.lib.rcb_rec_order(ptr(blocks), ptr(pair_rows), ptr(pair_blocks), lv.rows, lv.G, stream()),
+              "rcb_rec_order")
+        _rec.encode(lv, lv.tables_ptr, self._g_dev, q_scale, p_scale, pair_rows, pair_blocks, n, lv.max_D, apply=apply)
         return blocks
 
     def decode_posteriors(self, indices: np.ndarray, level: int = 0) -> torch.Tensor:
