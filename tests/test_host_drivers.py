@@ -56,18 +56,15 @@ def test_step_beta_controller():
 
 # ---------------------------------------------------------------- input producers (data/load_data.py) --
 def _ref_data_module(name):
-    """One of the reference's data/*.py, loaded by path with the reference's utils in scope."""
-    import importlib.util
-    base = os.path.join(ROOT, "oracle", "_ref")
+    """One of the reference's data/*.py, executed from the packed archive with the reference's utils in scope."""
+    import types
+    from oracle import build_ref
+    ref = build_ref.load()
     saved = sys.modules.get("utils")
-    spec = importlib.util.spec_from_file_location("_ref_utils", os.path.join(base, "utils.py"))
-    u = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(u)
-    sys.modules["utils"] = u
+    sys.modules["utils"] = ref.utils
     try:
-        spec = importlib.util.spec_from_file_location("_ref_data_" + name, os.path.join(base, "data", name + ".py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
+        mod = types.ModuleType("_ref_data_" + name)
+        exec(compile(build_ref.read_source("data/%s.py" % name), "oracle/_ref/data/%s.py" % name, "exec"), mod.__dict__)
     finally:
         if saved is not None:
             sys.modules["utils"] = saved
