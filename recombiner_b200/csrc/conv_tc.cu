@@ -643,8 +643,8 @@ upconv_fwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
         }
-        if (a.out_half) {                                  // fp16 output: 64-byte rows, no swizzle
-          uint8_t* row = stage + ry * 4096 + lane * 64;
+        if (a.out_half) {                                  // fp16 output: 64-byte rows, 64-byte swizzle (16-byte chunk ^ bits 1-2 of the row:
+          uint8_t* row = stage + ry * 4096 + lane * 64;    // unswizzled, 32 lanes x 16 B at a 64-byte stride were 16 wavefronts per store)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float o[8];
@@ -654,7 +654,7 @@ upconv_fwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               o[e] = f > 0.f ? f : slope * f;
             }
             const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
-            *reinterpret_cast<uint4*>(row + c * 16) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            *reinterpret_cast<uint4*>(row + ((c ^ ((lane >> 1) & 3)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
           }
         } else {
         uint8_t* row = stage + ry * 4096 + lane * 128;
@@ -1404,7 +1404,7 @@ static int launch_f2(const void* src, const void* w_eff_k, const float* bias, fl
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmO, out_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims,
                      strides, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     out_half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     out_half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed with CUresult %d", (int)r); return -1; }
   }
