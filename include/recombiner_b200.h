@@ -205,6 +205,19 @@ int rcb_upconv_bwd_tc_ah(const float* d_out, const float* w_eff, const void* src
 int rcb_fold_poly_bwd_f2(const float* w_eff, const rcb_upconv_geom* g, float* w_bwd_k, rcb_stream_t stream);
 int rcb_upconv_bwd_f2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, float* d_src,
                       const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+/* The same kernel leaving d_src as fp16 multiplied by out_scale (clamped to the fp16 range): the operand form of
+ * rcb_upconv_bwd_f2w below. */
+int rcb_upconv_bwd_f2_oh(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, void* d_src_h,
+                         float out_scale, const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+/* Data gradient of the x2 / 3-tap / 64 -> 64 channel stage (the middle one of the 2-D upsamplers) with fp16 operands
+ * and the 16 weight blocks (128 KB) resident in shared memory: d_out_h is the fp16 gradient of the stage's output
+ * (scaled, as rcb_upconv_bwd_f2_oh writes it), w_bwd_k_h = rcb_to_half of rcb_fold_poly_bwd_f2w(w_eff), src_act_h the
+ * producing stage's fp16 activations (LeakyReLU mask; null = none); d_src is fp32 and multiplied by out_scale_inv.
+ * Source grids of 8 x 8 (two items per tile) or >= 16 lines with h % 4 == 0; rcb_upconv_bwd_f2w_eligible says which. */
+int rcb_upconv_bwd_f2w_eligible(const rcb_upconv_geom* g);
+int rcb_fold_poly_bwd_f2w(const float* w_eff, const rcb_upconv_geom* g, float* w_bwd_k, rcb_stream_t stream);
+int rcb_upconv_bwd_f2w(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, float* d_src,
+                       float out_scale_inv, const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 /* dst[i] = (fp16, round to nearest) src[i] */
 int rcb_to_half(const float* src, void* dst, int64_t n, rcb_stream_t stream);
 

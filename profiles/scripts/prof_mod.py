@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # the repository root
 os.environ["RECOMBINER_GRAPH"] = "0"
 import numpy as np, torch, bench
 from recombiner_b200.config import configs

@@ -1,6 +1,6 @@
 """Short run for ncu: 3 fit steps (every kernel a launch of its own), REC rounds, 3 prior-training steps."""
 import sys, os, contextlib, io
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # the repository root
 os.environ.setdefault("RECOMBINER_GRAPH", "0")
 import torch, bench
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)

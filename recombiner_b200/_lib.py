@@ -95,6 +95,10 @@ SIGNATURES = {
     "rcb_upconv_bwd_tc_ah": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_fold_poly_bwd_f2": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_upconv_bwd_f2": [P, P, P, I32, P, C.POINTER(UpconvGeom), I32, P],
+    "rcb_upconv_bwd_f2_oh": [P, P, P, I32, P, F32, C.POINTER(UpconvGeom), I32, P],
+    "rcb_upconv_bwd_f2w_eligible": [C.POINTER(UpconvGeom)],
+    "rcb_fold_poly_bwd_f2w": [P, C.POINTER(UpconvGeom), P, P],
+    "rcb_upconv_bwd_f2w": [P, P, P, P, F32, C.POINTER(UpconvGeom), I32, P],
     "rcb_to_half": [P, P, I64, P],
     "rcb_upconv_bwd_tc": [P, P, P, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_fwd": [P, P, P, P, C.POINTER(UpconvGeom), I32, I32, P],

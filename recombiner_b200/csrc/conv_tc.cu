@@ -1064,6 +1064,8 @@ struct ConvB2Args {
   int items, tiles_x, tiles_y, n_tiles;
   int act_kind;                          // LeakyReLU mask of the producing stage: 0 none, 1 fp32, 2 fp16 activations
   int a_off, epi_off, bar_off;
+  int out_half;                          // d_src leaves as fp16, multiplied by out_scale (tmO then maps fp16 rows)
+  float out_scale;
   const void* src_act;
 };
 
@@ -1249,16 +1251,41 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t v[2][16];
         tmem_ld16_nowait(acc + (uint32_t)(hh * 32), v[0]);
         tmem_ld16_nowait(acc + (uint32_t)(hh * 32 + 16), v[1]);
-        if (lane == 0) bulk_wait_read<1>();                // this buffer's previous store has left shared memory
-        __syncwarp();
+        if (!a.out_half || hh == 0) {
+          if (lane == 0) bulk_wait_read<1>();              // this buffer's previous store has left shared memory
+          __syncwarp();
+        }
         tmem_wait_ld();
         if (hh == 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
         }
-        uint8_t* row = stage + hh * 4096 + lane * 128;
         const uint32_t hb = (uint32_t)(bits >> (hh * 32));
+        if (a.out_half) {
+          // all 64 channels of a pixel are one 128-byte fp16 row: both halves land in the same staged row, one store per tile
+          uint8_t* row = stage + buf * 4096 + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = fminf(fmaxf(__uint_as_float(v[c >> 1][(c & 1) * 8 + e]) * (((hb >> (c * 8 + e)) & 1u) ? a.out_scale : 0.01f * a.out_scale),
+                                 -65504.f), 65504.f);
+            const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
+            *reinterpret_cast<uint4*>(row + (((hh * 4 + c) ^ (lane & 7)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+          }
+          if (hh == 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmO, stage + buf * 4096, 0, x0, y0 + q * 4, item);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          continue;
+        }
+        uint8_t* row = stage + hh * 4096 + lane * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float o[4];
@@ -1271,6 +1298,214 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&tmO, stage + hh * 4096, hh * 32, x0, y0 + q * 4, item);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------- data gradient, factor 2, 64 -> 64 channels, fp16 operands, resident weights --
+// Same adjoint as above for the middle stage of the 2-D upsamplers.  With 64 output channels a (line parity, column
+// parity) phase of the output gradient has one dense 128-byte fp16 row per source pixel, so the neighbourhood of a tile
+// travels as FOUR halo boxes (TMA element strides of 2 along x and y pick a phase), each feeding the 2 x 2 products
+// (a, b) whose parities it matches through row-shifted descriptors.  The 16 weight blocks W[a][b] (64 ic rows x 64 oc,
+// 128 KB as fp16) stay resident.  A tile is 16 lines x 8 pixels of one item, or two whole 8 x 8 items interleaved line
+// by line (the box puts the item dimension between x and y, as in the forward kernel above).  The incoming gradient
+// is fp16 in units of 1 / out_scale_inv (written by the kernel above with out_half); the result is fp32, true units.
+constexpr int B2W_STAGES = 2;
+struct ConvB2WArgs {
+  PolyGeom g;
+  int items, tiles_x, tiles_y, n_tiles;
+  int ipt;                               // items per tile: 1 (8 px x 16 lines) or 2 (8 x 8 grids)
+  int halo_bytes;
+  int a_off, epi_off, bar_off;
+  float out_scale_inv;
+  const void* src_act;                   // fp16 activations of the producing stage (LeakyReLU mask) or null
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvB2WArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + a.bar_off);        // [B2W_STAGES]
+  uint64_t* a_empty = a_full + B2W_STAGES;
+  uint64_t* acc_full = a_empty + B2W_STAGES;                // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2], one arrival per epilogue warp
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+  constexpr int IC = 64;
+  constexpr uint32_t TMEM_COLS = 128;                       // two accumulator sets of 64 columns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PolyGeom& g = a.g;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B2W_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int t, int& item, int& y0, int& x0) {
+    if (a.ipt == 2) { item = 2 * t; y0 = 0; x0 = 0; return; }
+    x0 = (t % a.tiles_x) * 8; t /= a.tiles_x;
+    y0 = (t % a.tiles_y) * 16; t /= a.tiles_y;
+    item = t;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights once, then the four phase boxes (line parity, column parity) of every tile
+    if (elect_one()) {
+      mbar_expect_tx(w_full, 16u * F2W_W_BLOCK);
+      for (int b = 0; b < 16; ++b) tma_load_2d(&tmB, w_full, smem + b * F2W_W_BLOCK, b * 64, 0);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t par = 1;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      for (int ph = 0; ph < 4; ++ph) {
+        const int ry = ph >> 1, rx = ph & 1;
+        mbar_wait(&a_empty[s], par);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[s], (uint32_t)a.halo_bytes);
+          uint8_t* dst = smem + a.a_off + s * F2W_STAGE_BYTES;
+          if (a.ipt == 2) tma_load_4d(&tmA, &a_full[s], dst, 0, rx - 2, item, ry - 2);
+          else tma_load_4d(&tmA, &a_full[s], dst, 0, 2 * (x0 - 1) + rx, 2 * (y0 - 1) + ry, item);
+        }
+        __syncwarp();
+        if (++s == B2W_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint32_t idesc = idesc_f16_m128(IC);
+    const uint32_t w_addr = smem_u32(smem);
+    const int dy_rows = HALO_PITCH * a.ipt;
+    mbar_wait(w_full, 0);
+    int s = 0;
+    uint32_t par = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * IC);
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) {
+        const int ry = ph >> 1, rx = ph & 1;
+        mbar_wait(&a_full[s], par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + a.a_off + s * F2W_STAGE_BYTES);
+#pragma unroll
+          for (int ai = 0; ai < 2; ++ai) {
+            // parity 0 serves index 1 (shift 0) and 3 (shift +1); parity 1 serves 2 (shift 0) and 0 (shift -1)
+            const int aa = ry == 0 ? (ai == 0 ? 1 : 3) : (ai == 0 ? 2 : 0);
+            const int dy = ry == 0 ? (ai == 0 ? 0 : 1) : (ai == 0 ? 0 : -1);
+#pragma unroll
+            for (int bi = 0; bi < 2; ++bi) {
+              const int bb = rx == 0 ? (bi == 0 ? 1 : 3) : (bi == 0 ? 2 : 0);
+              const int dx = rx == 0 ? (bi == 0 ? 0 : 1) : (bi == 0 ? 0 : -1);
+              const uint32_t shift_rows = (uint32_t)((1 + dy) * dy_rows + (1 + dx));
+              const uint64_t da = da_hi | (uint64_t)(((a_addr + shift_rows * 128u) & 0x3FFFF) >> 4);
+              const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)((aa * 4 + bb) * F2W_W_BLOCK));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ss(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ph | ai | bi | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&a_empty[s]);
+          if (ph == 3) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == B2W_STAGES) { s = 0; par ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: accumulator row m = (line group m / 8, pixel m % 8); a warp owns four line groups: four lines
+    // of one item, or two lines of each of the tile's two items (group = line * 2 + item)
+    const int q = warp & 3;
+    uint8_t* stage = smem + a.epi_off + q * 2 * 4096;
+    uint8_t* scratch = smem + a.epi_off + 4 * 2 * 4096 + q * 512;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+      uint64_t bits = ~0ull;
+      if (a.src_act != nullptr) {
+        uint4 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                       // load i: half a line group = 4 pixels x 8 chunks of 8 halves
+          const int gi = i >> 1;
+          const int yy = a.ipt == 2 ? 2 * q + (gi >> 1) : y0 + q * 4 + gi;
+          const int ii = a.ipt == 2 ? item + (gi & 1) : item;
+          const int xx = x0 + (i & 1) * 4 + (lane >> 3);
+          h[i] = (yy < g.h && xx < g.w && ii < a.items)
+                     ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
+                                                            (((int64_t)ii * g.h + yy) * g.w + xx) * IC) + (lane & 7))
+                     : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t w4[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
+          uint32_t b8 = 0u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)                       // an fp16 is positive exactly when its bits are a positive int16
+            b8 |= (((short)(w4[e] & 0xffffu) > 0 ? 1u : 0u) | ((int)w4[e] >= 0x10000 ? 2u : 0u)) << (e * 2);
+          scratch[i * 32 + lane] = (uint8_t)b8;             // = [row i * 4 + lane / 8][chunk lane % 8]
+        }
+        __syncwarp();
+        bits = *reinterpret_cast<const uint64_t*>(scratch + lane * 8);
+        __syncwarp();
+      }
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * IC);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[2][16];
+        tmem_ld16_nowait(acc + (uint32_t)(hh * 32), v[0]);
+        tmem_ld16_nowait(acc + (uint32_t)(hh * 32 + 16), v[1]);
+        if (lane == 0) bulk_wait_read<1>();                // this buffer's previous store has left shared memory
+        __syncwarp();
+        tmem_wait_ld();
+        if (hh == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+        }
+        uint8_t* row = stage + hh * 4096 + lane * 128;
+        const uint32_t hb = (uint32_t)(bits >> (hh * 32));
+        const float s1 = a.out_scale_inv, s0 = 0.01f * a.out_scale_inv;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((hb >> (c * 4 + e)) & 1u) ? s1 : s0);
+          *reinterpret_cast<float4*>(row + ((c ^ (lane & 7)) * 16)) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (a.ipt == 2) tma_store_4d(&tmO, stage + hh * 4096, hh * 32, 0, item, 2 * q);
+          else if (y0 + 4 * q < g.h) tma_store_4d(&tmO, stage + hh * 4096, hh * 32, x0, y0 + q * 4, item);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -1516,10 +1751,11 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return -1; }
   return 0;
 }
-static int launch_b2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, float* d_src,
-                     const PolyGeom& g, int items, rcb_stream_t stream) {
+static int launch_b2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, void* d_src,
+                     const PolyGeom& g, int items, rcb_stream_t stream, int out_half = 0, float out_scale = 1.f) {
   ConvB2Args f;
   f.g = g; f.items = items;
+  f.out_half = out_half; f.out_scale = out_scale;
   f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
   f.n_tiles = f.tiles_x * f.tiles_y * items;
   f.act_kind = src_act ? act_kind : 0; f.src_act = src_act;
@@ -1537,10 +1773,13 @@ static int launch_b2(const float* d_out, const float* w_bwd_k, const void* src_a
   }
   if (int rc = make_map_b(&tmB, w_bwd_k, 64, 256, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   {
+    const cuuint64_t px = out_half ? 128 : 256;
     cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
-    cuuint64_t strides[3] = {256, (cuuint64_t)g.w * 256, (cuuint64_t)g.h * g.w * 256};
-    cuuint32_t box[4] = {32, 8, 4, 1};
-    if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
+    cuuint64_t strides[3] = {px, (cuuint64_t)g.w * px, (cuuint64_t)g.h * g.w * px};
+    cuuint32_t box[4] = {(cuuint32_t)(out_half ? 64 : 32), 8, 4, 1};
+    if (out_half) {
+      if (int rc = encode_map_t(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d_src, 4, dims, strides, box, "d_src")) return rc;
+    } else if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
   }
   if (int rc = opt_in_smem(upconv_bwd_f2_kernel, "rcb_upconv_bwd_f2")) return rc;
   static int n_sm = 0;
@@ -1548,6 +1787,73 @@ static int launch_b2(const float* d_out, const float* w_bwd_k, const void* src_a
   const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
   upconv_bwd_f2_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
   RCB_CHECK_LAUNCH("rcb_upconv_bwd_f2");
+  return 0;
+}
+
+static bool b2w_eligible(const PolyGeom& g) {
+  return g.d == 1 && g.Tz == 1 && g.Ty == 2 && g.Tx == 2 && g.fy == 2 && g.fx == 2 && g.py == 1 && g.px == 1 &&
+         g.oc == 64 && g.ic == 64 && ((g.h == 8 && g.w == 8) || (g.h >= 16 && g.h % 4 == 0));
+}
+// fp16 d_out (scaled), fp16 K-major weights [ic][(a, b, oc)], fp16 mask activations, fp32 d_src
+static int launch_b2w(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, float* d_src, const PolyGeom& g,
+                      int items, float out_scale_inv, rcb_stream_t stream) {
+  ConvB2WArgs f;
+  f.g = g; f.items = items;
+  f.ipt = (g.h == 8 && g.w == 8) ? 2 : 1;
+  f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
+  f.n_tiles = f.ipt == 2 ? ceil_div(items, 2) : f.tiles_x * f.tiles_y * items;
+  f.halo_bytes = (f.ipt == 2 ? 10 * 2 * HALO_PITCH : HALO_LINES * HALO_PITCH) * 128;
+  f.out_scale_inv = out_scale_inv; f.src_act = src_act_h;
+  f.a_off = 16 * F2W_W_BLOCK;
+  f.epi_off = f.a_off + B2W_STAGES * F2W_STAGE_BYTES;
+  f.bar_off = f.epi_off + 4 * 2 * 4096 + 4 * 512;
+  const int smem_total = f.bar_off + 512 + 1024;
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+  CUtensorMap tmA, tmB, tmO;
+  {   // d_out (item, 2h, 2w, 64 oc fp16), read with element strides 2 along x and y: one (line, column) parity per box
+    const cuuint64_t px = 128, line = 2 * (cuuint64_t)g.w * px, img = 2 * (cuuint64_t)g.h * line;
+    const cuuint32_t bx = 2 * HALO_PITCH - 1;
+    CUresult r;
+    if (f.ipt == 2) {
+      cuuint64_t dims[4] = {64, 2 * (cuuint64_t)g.w, (cuuint64_t)items, 2 * (cuuint64_t)g.h};
+      cuuint64_t strides[3] = {px, img, line};
+      cuuint32_t box[4] = {64, bx, 2, 2 * 10 - 1};
+      cuuint32_t estr[4] = {1, 2, 1, 2};
+      r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_out_h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[4] = {64, 2 * (cuuint64_t)g.w, 2 * (cuuint64_t)g.h, (cuuint64_t)items};
+      cuuint64_t strides[3] = {px, line, img};
+      cuuint32_t box[4] = {64, bx, 2 * HALO_LINES - 1, 1};
+      cuuint32_t estr[4] = {1, 2, 2, 1};
+      r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_out_h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(d_out, strided) failed with CUresult %d", (int)r); return -1; }
+  }
+  if (int rc = make_map_b(&tmB, w_bwd_k_h, 64, 1024, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return rc;
+  {
+    const cuuint64_t px = 256, line = (cuuint64_t)g.w * px, img = (cuuint64_t)g.h * line;
+    if (f.ipt == 2) {
+      cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)items, (cuuint64_t)g.h};
+      cuuint64_t strides[3] = {px, img, line};
+      cuuint32_t box[4] = {32, 8, 2, 2};
+      if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
+    } else {
+      cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
+      cuuint64_t strides[3] = {px, line, img};
+      cuuint32_t box[4] = {32, 8, 4, 1};
+      if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
+    }
+  }
+  cudaError_t e = cudaFuncSetAttribute(upconv_bwd_f2w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+  if (e != cudaSuccess) { set_error("rcb_upconv_bwd_f2w: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
+  static int n_sm = 0;
+  if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
+  upconv_bwd_f2w_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  RCB_CHECK_LAUNCH("rcb_upconv_bwd_f2w");
   return 0;
 }
 
@@ -1668,6 +1974,44 @@ extern "C" int rcb_upconv_bwd_f2(const float* d_out, const float* w_bwd_k, const
   RCB_CHECK_ARG(b2_eligible(g), "rcb_upconv_bwd_f2: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
   if (items <= 0) return 0;
   return launch_b2(d_out, w_bwd_k, src_act, act_kind, d_src, g, items, stream);
+}
+
+// same, leaving d_src as fp16 multiplied by out_scale (a power of two that brings the gradient to O(1))
+extern "C" int rcb_upconv_bwd_f2_oh(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, void* d_src_h,
+                                    float out_scale, const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(d_out && w_bwd_k && d_src_h, "rcb_upconv_bwd_f2_oh: null pointer");
+  RCB_CHECK_ARG(act_kind >= 0 && act_kind <= 2, "rcb_upconv_bwd_f2_oh: act_kind must be 0, 1 or 2");
+  RCB_CHECK_ARG(out_scale > 0.f, "rcb_upconv_bwd_f2_oh: out_scale must be positive");
+  RCB_CHECK_ARG(b2_eligible(g), "rcb_upconv_bwd_f2_oh: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
+  if (items <= 0) return 0;
+  return launch_b2(d_out, w_bwd_k, src_act, act_kind, d_src_h, g, items, stream, 1, out_scale);
+}
+extern "C" int rcb_upconv_bwd_f2w_eligible(const rcb_upconv_geom* geo) {
+  PolyGeom g;
+  if (make_geom_tc(geo, &g)) return 0;
+  return b2w_eligible(g) ? 1 : 0;
+}
+extern "C" int rcb_fold_poly_bwd_f2w(const float* w_eff, const rcb_upconv_geom* geo, float* w_bwd_k, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(w_eff && w_bwd_k, "rcb_fold_poly_bwd_f2w: null pointer");
+  RCB_CHECK_ARG(b2w_eligible(g), "rcb_fold_poly_bwd_f2w: only 2-D x2 stages with 64 -> 64 channels (8 x 8 grids or >= 16 lines)");
+  const int n = g.ic * 16 * g.oc;
+  fold_bwd_f2_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w_eff, w_bwd_k, g.ic, g.oc);
+  RCB_CHECK_LAUNCH("rcb_fold_poly_bwd_f2w");
+  return 0;
+}
+extern "C" int rcb_upconv_bwd_f2w(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, float* d_src,
+                                  float out_scale_inv, const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(d_out_h && w_bwd_k_h && d_src, "rcb_upconv_bwd_f2w: null pointer");
+  RCB_CHECK_ARG(out_scale_inv > 0.f, "rcb_upconv_bwd_f2w: out_scale_inv must be positive");
+  RCB_CHECK_ARG(b2w_eligible(g), "rcb_upconv_bwd_f2w: only 2-D x2 stages with 64 -> 64 channels (8 x 8 grids or >= 16 lines)");
+  if (items <= 0) return 0;
+  return launch_b2w(d_out_h, w_bwd_k_h, src_act_h, d_src, g, items, out_scale_inv, stream);
 }
 
 // w_eff: [phase][tap][ic][oc] as produced by rcb_fold_poly (already K-major for this GEMM).

@@ -195,6 +195,8 @@ class FitEngine:
         # reads anyway.  Prior training turns this off (its weight gradients read them in fp32).
         self.half_acts = self.tc_conv and os.environ.get("RECOMBINER_HALF_ACTS", "1") != "0"
         self.f2_half = False
+        self.b2w = False
+        self._b2w_enabled = os.environ.get("RECOMBINER_BWD_F2W", "1") != "0"
         self._half_staged = False
         self._side = None
         if not torch.cuda.is_available():
@@ -339,6 +341,12 @@ class FitEngine:
                     self.M1T_h = torch.empty(self.M1T.shape, dtype=torch.float16, device=dev)
             if self.f2_half:
                 self.w3_bk = torch.empty(self.w_eff[2].numel(), device=dev)        # resident-weight data gradient
+            # fp16 resident-weight data gradient of the middle stage (its incoming gradient then travels as scaled fp16)
+            self.b2w = bool(self._half_staged and self._b2w_enabled
+                            and self.lib.rcb_upconv_bwd_f2w_eligible(C.byref(self.geoms[1])) == 1)
+            if self.b2w:
+                self.w2_bk = torch.empty(self.w_eff[1].numel(), device=dev)
+                self.w2_bk_h = torch.empty(self.w_eff[1].numel(), dtype=torch.float16, device=dev)
             self._derived = True
         for l, c in enumerate(self.counts):
             ld = self.A[l].shape[1]
@@ -362,6 +370,10 @@ class FitEngine:
                 check(self.lib.rcb_to_half(ptr(self.M1T), ptr(self.M1T_h), self.M1T_h.numel(), st), "rcb_to_half")
         if self.f2_half:
             check(self.lib.rcb_fold_poly_bwd_f2(ptr(self.w_eff[2]), C.byref(g3), ptr(self.w3_bk), st), "rcb_fold_poly_bwd_f2")
+        if self.b2w:
+            check(self.lib.rcb_fold_poly_bwd_f2w(ptr(self.w_eff[1]), C.byref(self.geoms[1]), ptr(self.w2_bk), st),
+                  "rcb_fold_poly_bwd_f2w")
+            check(self.lib.rcb_to_half(ptr(self.w2_bk), ptr(self.w2_bk_h), self.w2_bk_h.numel(), st), "rcb_to_half")
 
     # -------------------------------------------------------------- workspaces --
     def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
@@ -733,6 +745,11 @@ class FitEngine:
             amax = float(dy.abs().max())
             coef = 2.0 ** round(-math.log2(amax)) if amax > 0.0 and math.isfinite(amax) else 1.0
         a.coef, a.w0 = coef, self.w0
+        # power of two that brings d_pe (and what the upsampler's adjoint makes of it) to O(1): mode 1 writes
+        # coef * (residual chain), mode 2 (chain of dy * coef) / coef
+        ws["bwd_scale"] = 0.0
+        if use_tc and coef > 0.0 and mode in (1, 2):
+            ws["bwd_scale"] = 2.0 ** round(-math.log2(coef)) if mode == 1 else coef
         ws["d_wt_is_half"] = False
         if use_tc and mode == 1 and self.half_hw and self.half_dwt:
             # the weight gradients are only read by the data-gradient reparameterisation GEMM: written as fp16
@@ -777,20 +794,33 @@ class FitEngine:
                     self._gemm(ws["d_wt"], self.offsets[l], self.ldw, self.AT[l], self.AT[l].shape[1],
                                ws["d_hw"], self.offsets[l], self.ldw, items, c, c, Bt=self.A[l])
         join = self._fork(reparam)
-        with self.section("conv3_bwd"):
-            if self.f2_half:
-                half = bool(ws.get("a2_is_half"))
-                check(self.lib.rcb_upconv_bwd_f2(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"] if half else ws["a2"]),
-                                                 2 if half else 1, ptr(ws["d_a2"]), C.byref(g3), citems, stream()),
-                      "rcb_upconv_bwd_f2[3]")
-            else:
-                self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
-        with self.section("conv2_bwd"):
-            if ws.get("a2_is_half"):
-                check(self.lib.rcb_upconv_bwd_tc_ah(ptr(ws["d_a2"]), ptr(self.w_eff[1]), ptr(ws["a1h"]), ptr(ws["d_a1"]),
-                                                    C.byref(g2), citems, stream()), "rcb_upconv_bwd_tc_ah[2]")
-            else:
-                self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
+        b2w = bool(self.b2w and ws.get("a2_is_half") and ws.get("bwd_scale", 0.0) > 0.0)
+        if b2w:
+            # fp16 gradient between the two x2 stages, in units of 1 / bwd_scale
+            if "d_a2_h" not in ws:
+                ws["d_a2_h"] = torch.empty(ws["d_a2"].shape, dtype=torch.float16, device=self.device)
+            sc = float(ws["bwd_scale"])
+            with self.section("conv3_bwd"):
+                check(self.lib.rcb_upconv_bwd_f2_oh(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"]), 2, ptr(ws["d_a2_h"]), sc,
+                                                    C.byref(g3), citems, stream()), "rcb_upconv_bwd_f2_oh[3]")
+            with self.section("conv2_bwd"):
+                check(self.lib.rcb_upconv_bwd_f2w(ptr(ws["d_a2_h"]), ptr(self.w2_bk_h), ptr(ws["a1h"]), ptr(ws["d_a1"]), 1.0 / sc,
+                                                  C.byref(g2), citems, stream()), "rcb_upconv_bwd_f2w[2]")
+        else:
+            with self.section("conv3_bwd"):
+                if self.f2_half:
+                    half = bool(ws.get("a2_is_half"))
+                    check(self.lib.rcb_upconv_bwd_f2(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"] if half else ws["a2"]),
+                                                     2 if half else 1, ptr(ws["d_a2"]), C.byref(g3), citems, stream()),
+                          "rcb_upconv_bwd_f2[3]")
+                else:
+                    self._upconv_bwd(2, ws["d_pe"], ws["a2"], ws["d_a2"], citems)
+            with self.section("conv2_bwd"):
+                if ws.get("a2_is_half"):
+                    check(self.lib.rcb_upconv_bwd_tc_ah(ptr(ws["d_a2"]), ptr(self.w_eff[1]), ptr(ws["a1h"]), ptr(ws["d_a1"]),
+                                                        C.byref(g2), citems, stream()), "rcb_upconv_bwd_tc_ah[2]")
+                else:
+                    self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
         with self.section("conv1_bwd"):
             if self.dense1:
                 Lt = self.M1.shape[0]

@@ -164,6 +164,72 @@ def test_upconv_bwd_f2_matches_simt(h, w, items, act_kind):
     assert err < 2e-3 * scale, (err, scale)
 
 
+@pytest.mark.parametrize("h,w,items", [(16, 16, 5), (40, 44, 20)])
+def test_upconv_bwd_f2_fp16_output_is_the_scaled_rounded_fp32_output(h, w, items):
+    """rcb_upconv_bwd_f2_oh = fp16(out_scale * rcb_upconv_bwd_f2), same accumulators: equal up to the last fp16 bit
+    (the scale is a power of two), and clamped instead of overflowing."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    ic, oc = 64, 16
+    geo = UpconvGeom(1, h, w, 1, 2, 2, 1, 3, 3, ic, oc)
+    gen = torch.Generator().manual_seed(h + w)
+    wt = (torch.randn(oc, ic, 1, 3, 3, generator=gen) / np.sqrt(ic * 9)).cuda()
+    n = 4 * 4 * ic * oc
+    w_eff, w_eff_t, w_bk = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_bwd_f2(ptr(w_eff), C.byref(geo), ptr(w_bk), stream()))
+    d_out = (torch.randn(items, 1, 2 * h, 2 * w, oc, generator=gen) * 1e-4).cuda()
+    act = torch.randn(items, 1, h, w, ic, generator=gen).cuda().half()
+    ref = torch.zeros(act.shape, device="cuda")
+    got = torch.full(act.shape, 3.0, dtype=torch.float16, device="cuda")
+    check(lib.rcb_upconv_bwd_f2(ptr(d_out), ptr(w_bk), ptr(act), 2, ptr(ref), C.byref(geo), items, stream()))
+    check(lib.rcb_upconv_bwd_f2_oh(ptr(d_out), ptr(w_bk), ptr(act), 2, ptr(got), 8192.0, C.byref(geo), items, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, (ref * 8192.0).half())
+    check(lib.rcb_upconv_bwd_f2_oh(ptr(d_out), ptr(w_bk), ptr(act), 2, ptr(got), 2.0 ** 40, C.byref(geo), items, stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all() and float(got.float().abs().max()) == 65504.0
+
+
+@pytest.mark.parametrize("h,w,items", [(8, 8, 7), (8, 8, 701), (16, 16, 3), (40, 44, 5)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_upconv_bwd_f2w_matches_simt_on_rounded_inputs(h, w, items, masked):
+    """Resident-weight fp16 data gradient of the 64 -> 64 x2 stage against the fp32 SIMT engine run on the same
+    fp16-rounded gradient: what is left is the fp16 rounding of the weights and the summation order.  Two 8 x 8
+    items per tile (odd count; more than two tiles per CTA) and one item per tile (ragged)."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    ic = oc = 64
+    geo = UpconvGeom(1, h, w, 1, 2, 2, 1, 3, 3, ic, oc)
+    assert lib.rcb_upconv_bwd_f2w_eligible(C.byref(geo)) == 1
+    gen = torch.Generator().manual_seed(h + w + items)
+    wt = (torch.randn(oc, ic, 1, 3, 3, generator=gen) / np.sqrt(ic * 9)).cuda()
+    n = 4 * 4 * ic * oc
+    w_eff, w_eff_t, w_bk = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_bwd_f2w(ptr(w_eff), C.byref(geo), ptr(w_bk), stream()))
+    w_bk_h = torch.empty(n, dtype=torch.float16, device="cuda")
+    check(lib.rcb_to_half(ptr(w_bk), ptr(w_bk_h), n, stream()))
+    scale = 256.0
+    d_true = torch.randn(items, 1, 2 * h, 2 * w, oc, generator=gen).cuda() / scale
+    d_h = (d_true * scale).half()
+    d_r = (d_h.float() / scale).contiguous()
+    act = torch.randn(items, 1, h, w, ic, generator=gen).cuda().half()
+    act_f = act.float().contiguous()
+    ref = torch.zeros(act.shape, device="cuda")
+    got = torch.full(act.shape, 3.0, device="cuda")
+    check(lib.rcb_upconv_bwd(ptr(d_r), ptr(w_eff_t), ptr(act_f if masked else None), ptr(ref), C.byref(geo), items, stream()))
+    check(lib.rcb_upconv_bwd_f2w(ptr(d_h), ptr(w_bk_h), ptr(act if masked else None), ptr(got), 1.0 / scale, C.byref(geo),
+                                 items, stream()))
+    torch.cuda.synchronize()
+    bound = float(d_r.norm(dim=-1).max()) * float(wt.norm()) / np.sqrt(ic) * 4
+    err = float((got - ref).abs().max())
+    print(f"[bwd_f2w {h}x{w} x{items}] err {err:.2e} bound {bound:.2e} max|ref| {float(ref.abs().max()):.2e}")
+    assert err < 2e-4 * bound, (err, bound)
+
+
 @pytest.mark.parametrize("name", ["cifar_conv2", "wide_2d_ragged", "video_conv2_3d", "protein_conv2", "f2w_ragged", "f2w_8x8_many"])
 def test_upconv_fwd_fp16_in_fp16_out_general_kernel(name):
     """rcb_upconv_fwd_tc_hh (general kernel, kind::f16 MMAs, fp16 result) against the SIMT engine on the rounded inputs."""
