@@ -209,6 +209,10 @@ int rcb_upconv_bwd_f2(const float* d_out, const float* w_bwd_k, const void* src_
  * rcb_upconv_bwd_f2w below. */
 int rcb_upconv_bwd_f2_oh(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, void* d_src_h,
                          float out_scale, const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+/* fp16 in as well: d_out_h (any fixed unit, e.g. rcb_mlp_args.d_pe_h) and w_bwd_k_h = rcb_to_half of w_bwd_k; one
+ * kind::f16 MMA per (a, b) product instead of two TF32 ones, half the gradient bytes. */
+int rcb_upconv_bwd_f2_hh(const void* d_out_h, const void* w_bwd_k_h, const void* src_act, int act_kind, void* d_src_h,
+                         float out_scale, const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 /* Data gradient of the x2 / 3-tap / 64 -> 64 channel stage (the middle one of the 2-D upsamplers) with fp16 operands
  * and the 16 weight blocks (128 KB) resident in shared memory: d_out_h is the fp16 gradient of the stage's output
  * (scaled, as rcb_upconv_bwd_f2_oh writes it), w_bwd_k_h = rcb_to_half of rcb_fold_poly_bwd_f2w(w_eff), src_act_h the
@@ -267,6 +271,9 @@ typedef struct {
   const float* x_tab;
   int x_axes, x_nfreq;
   int x_size[3], x_off[3];
+  void* d_pe_h;         /* optional (rcb_mlp_tc): d pe is written here as fp16 INSTEAD of d_pe, in the units the kernel carries
+                           its gradients in -- true d_pe / coef in mode 1, true d_pe * coef in mode 2 -- for the fp16 data
+                           gradient of the upsampler (rcb_upconv_bwd_f2_hh, rcb_upconv_bwd_f2w undoes the unit) */
 } rcb_mlp_args;
 int rcb_mlp(const rcb_mlp_args* a, rcb_stream_t stream);
 /* Same contract on tcgen05: two 128-pixel tiles of an item in flight per CTA (one 128-thread group

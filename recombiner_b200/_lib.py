@@ -35,7 +35,7 @@ class MlpArgs(C.Structure):
                [("x_row_stride", I64), ("pitch_z", I64), ("pitch_y", I64)] + \
                [(n, I32) for n in ("items", "S", "pix", "n_f", "out", "ld_w", "mode", "ph", "pw")] + \
                [("coef", F32), ("w0", F32), ("d_wt_h_scale", F32), ("ld_wh", I32), ("d_wt_h", P), ("pe_half", I32),
-                ("x_tab", P), ("x_axes", I32), ("x_nfreq", I32), ("x_size", I32 * 3), ("x_off", I32 * 3)]
+                ("x_tab", P), ("x_axes", I32), ("x_nfreq", I32), ("x_size", I32 * 3), ("x_off", I32 * 3), ("d_pe_h", P)]
 
 
 class UpdateArgs(C.Structure):
@@ -96,6 +96,7 @@ SIGNATURES = {
     "rcb_fold_poly_bwd_f2": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_upconv_bwd_f2": [P, P, P, I32, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_bwd_f2_oh": [P, P, P, I32, P, F32, C.POINTER(UpconvGeom), I32, P],
+    "rcb_upconv_bwd_f2_hh": [P, P, P, I32, P, F32, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_bwd_f2w_eligible": [C.POINTER(UpconvGeom)],
     "rcb_fold_poly_bwd_f2w": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_upconv_bwd_f2w": [P, P, P, P, F32, C.POINTER(UpconvGeom), I32, P],

@@ -10,6 +10,7 @@
 //             one CTA = 128 source pixels, K = phases*taps*oc
 // Warp roles as in gemm_tc.cu.  Reference semantics: prior_model.py:47-59.
 #include <cstdlib>
+#include <cstring>
 #include <cuda_fp16.h>
 #include "gemm_engine.cuh"
 #include "tc_common.cuh"
@@ -1059,11 +1060,14 @@ upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // likewise b <-> (rx, dx), where rx picks the 64-byte half of the row.  The 64 x 256 weight matrix (64 KB) stays in
 // shared memory; CTAs are persistent, accumulators double-buffered, the result leaves through TMA stores.
 constexpr int B2_STAGES = 4;
+constexpr int B2_MSTAGES = 2;                                   // mask tiles in flight (fp16 variant)
+constexpr int B2_THREADS = 320;                                 // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int HALO_BUF_H = 12 * 1024;                           // an fp16 halo box (18 x 10 rows of 64 bytes)
 struct ConvB2Args {
   PolyGeom g;
   int items, tiles_x, tiles_y, n_tiles;
   int act_kind;                          // LeakyReLU mask of the producing stage: 0 none, 1 fp32, 2 fp16 activations
-  int a_off, epi_off, bar_off;
+  int a_off, m_off, epi_off, bar_off;
   int out_half;                          // d_src leaves as fp16, multiplied by out_scale (tmO then maps fp16 rows)
   float out_scale;
   const void* src_act;
@@ -1086,9 +1090,12 @@ __global__ void fold_bwd_f2_kernel(const float* __restrict__ w_eff, float* __res
   w_bwd_k[e] = w_eff[((size_t)((ry * 2 + rx) * 4 + ty * 2 + tx) * ic + c) * oc + o];
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// HIN: d_out is fp16 (64-byte rows, 64-byte swizzle, one kind::f16 K step per product) and so are the weights
+template <bool HIN>
+__global__ void __launch_bounds__(B2_THREADS, 1)
 upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvB2Args a) {
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM,
+                     const __grid_constant__ ConvB2Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* a_full = (uint64_t*)(smem + a.bar_off);        // [B2_STAGES]
@@ -1096,8 +1103,14 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc_full = a_empty + B2_STAGES;                 // [2]
   uint64_t* acc_empty = acc_full + 2;                       // [2], one arrival per epilogue warp
   uint64_t* w_full = acc_empty + 2;
-  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
-  constexpr int IC = 64, W_BLOCK = IC * 128;                // one 32-wide K block of the weights
+  uint64_t* m_full = w_full + 1;                            // [B2_MSTAGES] mask tiles (HIN with fp16 activations)
+  uint64_t* m_empty = m_full + B2_MSTAGES;                  // one arrival per epilogue warp
+  uint32_t* tmem_slot = (uint32_t*)(m_empty + B2_MSTAGES);
+  const bool tma_mask = HIN && a.act_kind == 2;
+  constexpr int IC = 64, W_BLOCK = IC * 128;                // one 128-byte-wide K block of the weights
+  constexpr int W_BLOCKS = HIN ? 4 : 8;                     // K = 256: 64 halves or 32 floats per block row
+  constexpr int ROW_BYTES = HIN ? 64 : 128;                 // one source pixel and line parity of d_out
+  constexpr int A_BUF = HIN ? HALO_BUF_H : HALO_BUF;
   constexpr uint32_t TMEM_COLS = 128;                       // two accumulator sets of 64 columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1105,8 +1118,9 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(w_full, 1);
+    for (int i = 0; i < B2_MSTAGES; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -1124,20 +1138,31 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     // ===== TMA producer: the weights once, then the two halo boxes (line parity 0, 1) of every tile
     if (elect_one()) {
-      mbar_expect_tx(w_full, 8u * W_BLOCK);
-      for (int kb = 0; kb < 8; ++kb) tma_load_2d(&tmB, w_full, smem + kb * W_BLOCK, kb * 32, 0);
+      mbar_expect_tx(w_full, (uint32_t)(W_BLOCKS * W_BLOCK));
+      for (int kb = 0; kb < W_BLOCKS; ++kb) tma_load_2d(&tmB, w_full, smem + kb * W_BLOCK, kb * (HIN ? 64 : 32), 0);
     }
     __syncwarp();
-    int s = 0;
+    int s = 0, it = 0;
     uint32_t par = 1;
-    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
       int item, y0, x0;
       tile_origin(t, item, y0, x0);
+      if (tma_mask) {
+        // the tile's 128 rows of the producing stage's fp16 activations (only their signs are read): they ride the same
+        // pipeline as the operands, so no epilogue warp ever waits on a global load
+        const int ms = it % B2_MSTAGES;
+        mbar_wait(&m_empty[ms], ((it / B2_MSTAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&m_full[ms], 128u * 128u);
+          tma_load_4d(&tmM, &m_full[ms], smem + a.m_off + ms * 16384, 0, x0, y0, item);
+        }
+        __syncwarp();
+      }
       for (int ry = 0; ry < 2; ++ry) {
         mbar_wait(&a_empty[s], par);
         if (elect_one()) {
-          mbar_expect_tx(&a_full[s], HALO_BYTES);
-          tma_load_5d(&tmA, &a_full[s], smem + a.a_off + s * HALO_BUF, 0, x0 - 1, ry, y0 - 1, item);
+          mbar_expect_tx(&a_full[s], (uint32_t)(HALO_LINES * HALO_PITCH * ROW_BYTES));
+          tma_load_5d(&tmA, &a_full[s], smem + a.a_off + s * A_BUF, 0, x0 - 1, ry, y0 - 1, item);
         }
         __syncwarp();
         if (++s == B2_STAGES) { s = 0; par ^= 1; }
@@ -1145,8 +1170,9 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     // ===== MMA issuer
-    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    const uint32_t idesc = idesc_tf32(IC);
+    const uint64_t da_hi = ((uint64_t)1 << 16) | ((uint64_t)((HALO_PITCH * ROW_BYTES) >> 4) << 32) | ((uint64_t)1 << 46) |
+                           ((uint64_t)(HIN ? 4 : 2) << 61);
+    const uint32_t idesc = HIN ? idesc_f16_m128(IC) : idesc_tf32(IC);
     const uint32_t w_addr = smem_u32(smem);
     mbar_wait(w_full, 0);
     int s = 0;
@@ -1162,7 +1188,7 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&a_full[s], par);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + a.a_off + s * HALO_BUF);
+          const uint32_t a_addr = smem_u32(smem + a.a_off + s * A_BUF);
 #pragma unroll
           for (int ai = 0; ai < 2; ++ai) {
             // line parity 0 serves a = 1 (dy = 0) and a = 3 (dy = +1); parity 1 serves a = 2 (dy = 0) and a = 0 (dy = -1)
@@ -1173,11 +1199,17 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               const int rx = (b == 0 || b == 2) ? 1 : 0;
               const int dx = b == 0 ? -1 : (b == 3 ? 1 : 0);
               const uint32_t shift_rows = (uint32_t)((1 + dy) * HALO_PITCH + (1 + dx));
-              const uint64_t da = (da_hi | (uint64_t)(((a_addr + shift_rows * 128u) & 0x3FFFF) >> 4)) + (uint64_t)(rx * 4);
-              const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)((aa * 2 + (b >> 1)) * W_BLOCK)) + (uint64_t)((b & 1) * 4);
+              if (HIN) {      // 16 oc = 32 bytes = one K step; the weight block of `aa` holds all four b
+                const uint64_t da = (da_hi | (uint64_t)(((a_addr + shift_rows * 64u) & 0x3FFFF) >> 4)) + (uint64_t)(rx * 2);
+                const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)(aa * W_BLOCK)) + (uint64_t)(b * 2);
+                umma_f16_ss(acc, da, db, idesc, (ry | ai | b) ? 1u : 0u);
+              } else {
+                const uint64_t da = (da_hi | (uint64_t)(((a_addr + shift_rows * 128u) & 0x3FFFF) >> 4)) + (uint64_t)(rx * 4);
+                const uint64_t db = smem_desc_sw128(w_addr + (uint32_t)((aa * 2 + (b >> 1)) * W_BLOCK)) + (uint64_t)((b & 1) * 4);
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                umma_tf32(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ry | ai | b | k) ? 1u : 0u);
+                for (int k = 0; k < 2; ++k)
+                  umma_tf32(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ry | ai | b | k) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&a_empty[s]);
@@ -1188,118 +1220,106 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ===== epilogue: row m = (line m / 8, pixel m % 8); mask bits fetched while the MMAs run; 32 rows x 32 channels
-    // staged as swizzled 128-byte rows per TMA store
-    const int q = warp & 3;
-    uint8_t* stage = smem + a.epi_off + q * 2 * 4096;
-    uint8_t* scratch = smem + a.epi_off + 4 * 2 * 4096 + q * 512;
+    // ===== epilogue, EIGHT warps: accumulator row m = (line m / 8, pixel m % 8); warp (q, hh) owns the 32 rows of TMEM
+    // lane quarter q and the 32 channels of half hh.  (With four warps -- one per scheduler -- converting a whole
+    // 64-channel row each, the ~700 dependent instructions per tile of this chain, not HBM, bounded the kernel.)
+    const int q = warp & 3, hh = (warp - 2) >> 2, ew = warp - 2;
+    uint8_t* stage = smem + a.epi_off + ew * 2 * 4096;
     int it = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       int item, y0, x0;
       tile_origin(t, item, y0, x0);
-      // LeakyReLU mask of this warp's 32 pixel rows (4 lines x 8 pixels): coalesced loads (consecutive lanes on
-      // consecutive 16-byte chunks), sign bits exchanged through a small shared-memory scratch so that each lane
-      // ends up with the 64 bits of its own row
-      uint64_t bits = ~0ull;
-      if (a.act_kind == 2) {
-        uint4 h[8];
+      const int m = q * 32 + lane;
+      // LeakyReLU mask: the 32 sign bits of this lane's half row
+      uint32_t bits = ~0u;
+      if (tma_mask) {
+        const int ms = it % B2_MSTAGES;
+        mbar_wait(&m_full[ms], (it / B2_MSTAGES) & 1);
+        const uint8_t* row = smem + a.m_off + ms * 16384 + m * 128;
+        bits = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {                       // load i: half a line = 4 pixels x 8 chunks of 8 halves
-          const int yy = y0 + q * 4 + (i >> 1), xx = x0 + (i & 1) * 4 + (lane >> 3);
-          h[i] = (yy < g.h && xx < g.w)
-                     ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
-                                                            (((int64_t)item * g.h + yy) * g.w + xx) * IC) + (lane & 7))
-                     : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t w4[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
-          uint32_t b8 = 0u;
+        for (int c = 0; c < 4; ++c) {
+          const uint4 hv = *reinterpret_cast<const uint4*>(row + (((hh * 4 + c) ^ (m & 7)) * 16));
+          const uint32_t w4[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e)                       // an fp16 is positive exactly when its bits are a positive int16
-            b8 |= (((short)(w4[e] & 0xffffu) > 0 ? 1u : 0u) | ((int)w4[e] >= 0x10000 ? 2u : 0u)) << (e * 2);
-          scratch[i * 32 + lane] = (uint8_t)b8;             // = [pixel i * 4 + lane / 8][chunk lane % 8]
+            bits |= (((short)(w4[e] & 0xffffu) > 0 ? 1u : 0u) | ((int)w4[e] >= 0x10000 ? 2u : 0u)) << (c * 8 + e * 2);
         }
         __syncwarp();
-        bits = *reinterpret_cast<const uint64_t*>(scratch + lane * 8);
-        __syncwarp();
-      } else if (a.act_kind == 1) {                         // fp32 activations: each lane walks its own 256-byte row
-        bits = 0ull;
-        const int m = q * 32 + lane;
+        if (lane == 0) mbar_arrive_cta(&m_empty[ms]);
+      } else if (a.act_kind == 2) {                         // fp16 activations straight from global memory
+        const int y = y0 + (m >> 3), x = x0 + (m & 7);
+        bits = 0u;
+        if (y < g.h && x < g.w) {
+          const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
+                                                          (((int64_t)item * g.h + y) * g.w + x) * IC + hh * 32);
+          uint4 hv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hv[c] = __ldg(p + c);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t w4[4] = {hv[c].x, hv[c].y, hv[c].z, hv[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              bits |= (((short)(w4[e] & 0xffffu) > 0 ? 1u : 0u) | ((int)w4[e] >= 0x10000 ? 2u : 0u)) << (c * 8 + e * 2);
+          }
+        }
+      } else if (a.act_kind == 1) {                         // fp32 activations: each lane walks its own half row
+        bits = 0u;
         const int y = y0 + (m >> 3), x = x0 + (m & 7);
         if (y < g.h && x < g.w) {
-          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.src_act) + (((int64_t)item * g.h + y) * g.w + x) * IC);
+          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.src_act) +
+                                                            (((int64_t)item * g.h + y) * g.w + x) * IC + hh * 32);
+          float4 f[8];
 #pragma unroll
-          for (int c0 = 0; c0 < 16; c0 += 8) {
-            float4 f[8];
+          for (int c = 0; c < 8; ++c) f[c] = __ldg(p + c);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) f[c] = __ldg(p + c0 + c);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint64_t b4 = (f[c].x > 0.f ? 1ull : 0ull) | (f[c].y > 0.f ? 2ull : 0ull) | (f[c].z > 0.f ? 4ull : 0ull) | (f[c].w > 0.f ? 8ull : 0ull);
-              bits |= b4 << ((c0 + c) * 4);
-            }
-          }
+          for (int c = 0; c < 8; ++c)
+            bits |= ((f[c].x > 0.f ? 1u : 0u) | (f[c].y > 0.f ? 2u : 0u) | (f[c].z > 0.f ? 4u : 0u) | (f[c].w > 0.f ? 8u : 0u)) << (c * 4);
         }
       }
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * IC);
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * IC + hh * 32);
+      uint32_t v[2][16];
+      tmem_ld16_nowait(acc, v[0]);
+      tmem_ld16_nowait(acc + 16u, v[1]);
+      if (lane == 0) bulk_wait_read<1>();                  // the store that last read this buffer has left shared memory
+      __syncwarp();
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+      uint8_t* sbuf = stage + buf * 4096;
+      if (a.out_half) {                                     // 32 channels = one 64-byte fp16 row, 64-byte swizzle
+        uint8_t* row = sbuf + lane * 64;
+        const float s1 = a.out_scale, s0 = 0.01f * a.out_scale;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[2][16];
-        tmem_ld16_nowait(acc + (uint32_t)(hh * 32), v[0]);
-        tmem_ld16_nowait(acc + (uint32_t)(hh * 32 + 16), v[1]);
-        if (!a.out_half || hh == 0) {
-          if (lane == 0) bulk_wait_read<1>();              // this buffer's previous store has left shared memory
-          __syncwarp();
-        }
-        tmem_wait_ld();
-        if (hh == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
-        }
-        const uint32_t hb = (uint32_t)(bits >> (hh * 32));
-        if (a.out_half) {
-          // all 64 channels of a pixel are one 128-byte fp16 row: both halves land in the same staged row, one store per tile
-          uint8_t* row = stage + buf * 4096 + lane * 128;
+        for (int c = 0; c < 4; ++c) {
+          float o[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              o[e] = fminf(fmaxf(__uint_as_float(v[c >> 1][(c & 1) * 8 + e]) * (((hb >> (c * 8 + e)) & 1u) ? a.out_scale : 0.01f * a.out_scale),
-                                 -65504.f), 65504.f);
-            const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
-            *reinterpret_cast<uint4*>(row + (((hh * 4 + c) ^ (lane & 7)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-          }
-          if (hh == 1) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_4d(&tmO, stage + buf * 4096, 0, x0, y0 + q * 4, item);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-          continue;
+          for (int e = 0; e < 8; ++e)
+            o[e] = fminf(fmaxf(__uint_as_float(v[c >> 1][(c & 1) * 8 + e]) * (((bits >> (c * 8 + e)) & 1u) ? s1 : s0), -65504.f), 65504.f);
+          const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
+          *reinterpret_cast<uint4*>(row + ((c ^ ((lane >> 1) & 3)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
         }
-        uint8_t* row = stage + hh * 4096 + lane * 128;
+      } else {
+        uint8_t* row = sbuf + lane * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((hb >> (c * 4 + e)) & 1u) ? 1.f : 0.01f);
+            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((bits >> (c * 4 + e)) & 1u) ? 1.f : 0.01f);
           *reinterpret_cast<float4*>(row + ((c ^ (lane & 7)) * 16)) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&tmO, stage + hh * 4096, hh * 32, x0, y0 + q * 4, item);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&tmO, sbuf, hh * 32, x0, y0 + q * 4, item);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     if (lane == 0) bulk_wait_read<0>();
@@ -1442,6 +1462,23 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int q = warp & 3;
     uint8_t* stage = smem + a.epi_off + q * 2 * 4096;
     uint8_t* scratch = smem + a.epi_off + 4 * 2 * 4096 + q * 512;
+    uint4 h[8];                                             // mask loads run one tile ahead (see the kernel above)
+    auto load_mask = [&](int t) {
+      int item, y0, x0;
+      tile_origin(t, item, y0, x0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                         // load i: half a line group = 4 pixels x 8 chunks of 8 halves
+        const int gi = i >> 1;
+        const int yy = a.ipt == 2 ? 2 * q + (gi >> 1) : y0 + q * 4 + gi;
+        const int ii = a.ipt == 2 ? item + (gi & 1) : item;
+        const int xx = x0 + (i & 1) * 4 + (lane >> 3);
+        h[i] = (t < a.n_tiles && yy < g.h && xx < g.w && ii < a.items)
+                   ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
+                                                          (((int64_t)ii * g.h + yy) * g.w + xx) * IC) + (lane & 7))
+                   : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (a.src_act != nullptr) load_mask(blockIdx.x);
     int it = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -1449,18 +1486,6 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tile_origin(t, item, y0, x0);
       uint64_t bits = ~0ull;
       if (a.src_act != nullptr) {
-        uint4 h[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {                       // load i: half a line group = 4 pixels x 8 chunks of 8 halves
-          const int gi = i >> 1;
-          const int yy = a.ipt == 2 ? 2 * q + (gi >> 1) : y0 + q * 4 + gi;
-          const int ii = a.ipt == 2 ? item + (gi & 1) : item;
-          const int xx = x0 + (i & 1) * 4 + (lane >> 3);
-          h[i] = (yy < g.h && xx < g.w && ii < a.items)
-                     ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
-                                                            (((int64_t)ii * g.h + yy) * g.w + xx) * IC) + (lane & 7))
-                     : make_uint4(0u, 0u, 0u, 0u);
-        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t w4[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
@@ -1473,6 +1498,7 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         __syncwarp();
         bits = *reinterpret_cast<const uint64_t*>(scratch + lane * 8);
         __syncwarp();
+        load_mask(t + (int)gridDim.x);
       }
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -1576,8 +1602,8 @@ static int make_map_b(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 }
 
 template <class K>
-static int opt_in_smem(K kernel, const char* name) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+static int opt_in_smem(K kernel, const char* name, int bytes = 200 * 1024) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) { set_error("%s: smem opt-in failed: %s", name, cudaGetErrorString(e)); return -1; }
   return 0;
 }
@@ -1751,41 +1777,69 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return -1; }
   return 0;
 }
-static int launch_b2(const float* d_out, const float* w_bwd_k, const void* src_act, int act_kind, void* d_src,
-                     const PolyGeom& g, int items, rcb_stream_t stream, int out_half = 0, float out_scale = 1.f) {
+static int launch_b2(const void* d_out, const void* w_bwd_k, const void* src_act, int act_kind, void* d_src,
+                     const PolyGeom& g, int items, rcb_stream_t stream, int out_half = 0, float out_scale = 1.f, int in_half = 0) {
   ConvB2Args f;
   f.g = g; f.items = items;
   f.out_half = out_half; f.out_scale = out_scale;
   f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
   f.n_tiles = f.tiles_x * f.tiles_y * items;
   f.act_kind = src_act ? act_kind : 0; f.src_act = src_act;
-  f.a_off = 8 * 64 * 128;
-  f.epi_off = f.a_off + B2_STAGES * HALO_BUF;
-  f.bar_off = f.epi_off + 4 * 2 * 4096 + 4 * 512;     // staging buffers + the mask scratch of the four epilogue warps
+  f.a_off = (in_half ? 4 : 8) * 64 * 128;
+  f.m_off = f.a_off + B2_STAGES * (in_half ? HALO_BUF_H : HALO_BUF);
+  f.epi_off = f.m_off + (in_half ? B2_MSTAGES * 16384 : 0);
+  f.bar_off = f.epi_off + 8 * 2 * 4096;               // staging buffers of the eight epilogue warps
   const int smem_total = f.bar_off + 512 + 1024;
-  CUtensorMap tmA, tmB, tmO;
-  {   // d_out as (item, y, line parity, x, (column parity, oc)): one 128-byte row per source pixel and line parity
-    const cuuint64_t line = (cuuint64_t)g.w * 128;
-    cuuint64_t dims[5] = {32, (cuuint64_t)g.w, 2, (cuuint64_t)g.h, (cuuint64_t)items};
-    cuuint64_t strides[4] = {128, line, 2 * line, (cuuint64_t)g.h * 2 * line};
-    cuuint32_t box[5] = {32, HALO_PITCH, 1, HALO_LINES, 1};
-    if (int rc = encode_map(&tmA, d_out, 5, dims, strides, box, "d_out")) return rc;
+  CUtensorMap tmA, tmB, tmO, tmM;
+  memset(&tmM, 0, sizeof(tmM));
+  if (in_half && f.act_kind == 2) {   // the producing stage's fp16 activations, one 128-row tile per box
+    const cuuint64_t px = 128, line = (cuuint64_t)g.w * px;
+    cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
+    cuuint64_t strides[3] = {px, line, (cuuint64_t)g.h * line};
+    cuuint32_t box[4] = {64, 8, 16, 1};
+    if (int rc = encode_map_t(&tmM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, src_act, 4, dims, strides, box, "src_act")) return rc;
   }
-  if (int rc = make_map_b(&tmB, w_bwd_k, 64, 256, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  {   // d_out as (item, y, line parity, x, (column parity, oc)): one 128-byte (fp16: 64-byte) row per source pixel and line parity
+    const cuuint64_t row = in_half ? 64 : 128, line = (cuuint64_t)g.w * row;
+    cuuint64_t dims[5] = {32, (cuuint64_t)g.w, 2, (cuuint64_t)g.h, (cuuint64_t)items};
+    cuuint64_t strides[4] = {row, line, 2 * line, (cuuint64_t)g.h * 2 * line};
+    cuuint32_t box[5] = {32, HALO_PITCH, 1, HALO_LINES, 1};
+    if (in_half) {
+      EncodeTiledFn enc = tc_get_encode();
+      if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)d_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(d_out, fp16) failed with CUresult %d", (int)r); return -1; }
+    } else if (int rc = encode_map(&tmA, d_out, 5, dims, strides, box, "d_out")) return rc;
+  }
+  if (in_half) {
+    if (int rc = make_map_b(&tmB, w_bwd_k, 64, 256, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return rc;
+  } else if (int rc = make_map_b(&tmB, w_bwd_k, 64, 256, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   {
     const cuuint64_t px = out_half ? 128 : 256;
     cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
     cuuint64_t strides[3] = {px, (cuuint64_t)g.w * px, (cuuint64_t)g.h * g.w * px};
-    cuuint32_t box[4] = {(cuuint32_t)(out_half ? 64 : 32), 8, 4, 1};
+    cuuint32_t box[4] = {32, 8, 4, 1};                  // a warp's 32 rows x 32 channels
     if (out_half) {
-      if (int rc = encode_map_t(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, d_src, 4, dims, strides, box, "d_src")) return rc;
+      EncodeTiledFn enc = tc_get_encode();
+      if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(d_src, fp16) failed with CUresult %d", (int)r); return -1; }
     } else if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
   }
-  if (int rc = opt_in_smem(upconv_bwd_f2_kernel, "rcb_upconv_bwd_f2")) return rc;
   static int n_sm = 0;
   if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
-  upconv_bwd_f2_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  if (in_half) {
+    if (int rc = opt_in_smem(upconv_bwd_f2_kernel<true>, "rcb_upconv_bwd_f2", smem_total)) return rc;
+    upconv_bwd_f2_kernel<true><<<grid, B2_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, tmM, f);
+  } else {
+    if (int rc = opt_in_smem(upconv_bwd_f2_kernel<false>, "rcb_upconv_bwd_f2", smem_total)) return rc;
+    upconv_bwd_f2_kernel<false><<<grid, B2_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, tmM, f);
+  }
   RCB_CHECK_LAUNCH("rcb_upconv_bwd_f2");
   return 0;
 }
@@ -1987,6 +2041,18 @@ extern "C" int rcb_upconv_bwd_f2_oh(const float* d_out, const float* w_bwd_k, co
   RCB_CHECK_ARG(b2_eligible(g), "rcb_upconv_bwd_f2_oh: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
   if (items <= 0) return 0;
   return launch_b2(d_out, w_bwd_k, src_act, act_kind, d_src_h, g, items, stream, 1, out_scale);
+}
+// fp16 in (d_out_h in any fixed unit, w_bwd_k_h = rcb_to_half of the folded weights) and fp16 out, same unit x out_scale
+extern "C" int rcb_upconv_bwd_f2_hh(const void* d_out_h, const void* w_bwd_k_h, const void* src_act, int act_kind, void* d_src_h,
+                                    float out_scale, const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(d_out_h && w_bwd_k_h && d_src_h, "rcb_upconv_bwd_f2_hh: null pointer");
+  RCB_CHECK_ARG(act_kind >= 0 && act_kind <= 2, "rcb_upconv_bwd_f2_hh: act_kind must be 0, 1 or 2");
+  RCB_CHECK_ARG(out_scale > 0.f, "rcb_upconv_bwd_f2_hh: out_scale must be positive");
+  RCB_CHECK_ARG(b2_eligible(g), "rcb_upconv_bwd_f2_hh: only 2-D x2 stages with 64 -> 16 channels and h >= 16");
+  if (items <= 0) return 0;
+  return launch_b2(d_out_h, w_bwd_k_h, src_act, act_kind, d_src_h, g, items, stream, 1, out_scale, 1);
 }
 extern "C" int rcb_upconv_bwd_f2w_eligible(const rcb_upconv_geom* geo) {
   PolyGeom g;

@@ -197,6 +197,7 @@ class FitEngine:
         self.f2_half = False
         self.b2w = False
         self._b2w_enabled = os.environ.get("RECOMBINER_BWD_F2W", "1") != "0"
+        self._half_dpe = os.environ.get("RECOMBINER_HALF_DPE", "1") != "0"
         self._half_staged = False
         self._side = None
         if not torch.cuda.is_available():
@@ -347,6 +348,7 @@ class FitEngine:
             if self.b2w:
                 self.w2_bk = torch.empty(self.w_eff[1].numel(), device=dev)
                 self.w2_bk_h = torch.empty(self.w_eff[1].numel(), dtype=torch.float16, device=dev)
+                self.w3_bk_h = torch.empty(self.w_eff[2].numel(), dtype=torch.float16, device=dev)
             self._derived = True
         for l, c in enumerate(self.counts):
             ld = self.A[l].shape[1]
@@ -374,6 +376,7 @@ class FitEngine:
             check(self.lib.rcb_fold_poly_bwd_f2w(ptr(self.w_eff[1]), C.byref(self.geoms[1]), ptr(self.w2_bk), st),
                   "rcb_fold_poly_bwd_f2w")
             check(self.lib.rcb_to_half(ptr(self.w2_bk), ptr(self.w2_bk_h), self.w2_bk_h.numel(), st), "rcb_to_half")
+            check(self.lib.rcb_to_half(ptr(self.w3_bk), ptr(self.w3_bk_h), self.w3_bk_h.numel(), st), "rcb_to_half")
 
     # -------------------------------------------------------------- workspaces --
     def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
@@ -748,8 +751,17 @@ class FitEngine:
         # power of two that brings d_pe (and what the upsampler's adjoint makes of it) to O(1): mode 1 writes
         # coef * (residual chain), mode 2 (chain of dy * coef) / coef
         ws["bwd_scale"] = 0.0
+        ws["d_pe_is_half"] = False
         if use_tc and coef > 0.0 and mode in (1, 2):
             ws["bwd_scale"] = 2.0 ** round(-math.log2(coef)) if mode == 1 else coef
+            if self.b2w and self._half_dpe and ws.get("a2_is_half"):
+                # d pe leaves the kernel as fp16 in the chain's own units (true / coef resp. true * coef): the fp16
+                # data gradients of the two x2 stages carry that unit, the last one multiplies it out
+                if "d_pe_h" not in ws:
+                    ws["d_pe_h"] = torch.empty(ws["d_pe"].shape, dtype=torch.float16, device=self.device)
+                a.d_pe_h = ptr(ws["d_pe_h"])
+                ws["bwd_scale"] = 1.0 / coef if mode == 1 else coef
+                ws["d_pe_is_half"] = True
         ws["d_wt_is_half"] = False
         if use_tc and mode == 1 and self.half_hw and self.half_dwt:
             # the weight gradients are only read by the data-gradient reparameterisation GEMM: written as fp16
@@ -801,8 +813,12 @@ class FitEngine:
                 ws["d_a2_h"] = torch.empty(ws["d_a2"].shape, dtype=torch.float16, device=self.device)
             sc = float(ws["bwd_scale"])
             with self.section("conv3_bwd"):
-                check(self.lib.rcb_upconv_bwd_f2_oh(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"]), 2, ptr(ws["d_a2_h"]), sc,
-                                                    C.byref(g3), citems, stream()), "rcb_upconv_bwd_f2_oh[3]")
+                if ws.get("d_pe_is_half"):
+                    check(self.lib.rcb_upconv_bwd_f2_hh(ptr(ws["d_pe_h"]), ptr(self.w3_bk_h), ptr(ws["a2h"]), 2, ptr(ws["d_a2_h"]),
+                                                        1.0, C.byref(g3), citems, stream()), "rcb_upconv_bwd_f2_hh[3]")
+                else:
+                    check(self.lib.rcb_upconv_bwd_f2_oh(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"]), 2, ptr(ws["d_a2_h"]), sc,
+                                                        C.byref(g3), citems, stream()), "rcb_upconv_bwd_f2_oh[3]")
             with self.section("conv2_bwd"):
                 check(self.lib.rcb_upconv_bwd_f2w(ptr(ws["d_a2_h"]), ptr(self.w2_bk_h), ptr(ws["a1h"]), ptr(ws["d_a1"]), 1.0 / sc,
                                                   C.byref(g2), citems, stream()), "rcb_upconv_bwd_f2w[2]")

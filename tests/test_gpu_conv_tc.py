@@ -192,6 +192,38 @@ def test_upconv_bwd_f2_fp16_output_is_the_scaled_rounded_fp32_output(h, w, items
     assert torch.isfinite(got.float()).all() and float(got.float().abs().max()) == 65504.0
 
 
+@pytest.mark.parametrize("h,w,items", [(16, 16, 5), (40, 44, 20)])
+def test_upconv_bwd_f2_fp16_in_fp16_out_matches_simt_on_rounded_inputs(h, w, items):
+    """rcb_upconv_bwd_f2_hh (fp16 gradient in, fp16 weights, one kind::f16 MMA per product) against the fp32 SIMT
+    engine on the same fp16-rounded gradient: weight rounding, summation order and the fp16 rounding of the output."""
+    from recombiner_b200 import _lib
+    from recombiner_b200._lib import UpconvGeom, check, ptr, stream
+    lib = _lib.load()
+    ic, oc = 64, 16
+    geo = UpconvGeom(1, h, w, 1, 2, 2, 1, 3, 3, ic, oc)
+    gen = torch.Generator().manual_seed(h * w + 1)
+    wt = (torch.randn(oc, ic, 1, 3, 3, generator=gen) / np.sqrt(ic * 9)).cuda()
+    n = 4 * 4 * ic * oc
+    w_eff, w_eff_t, w_bk = (torch.empty(n, device="cuda") for _ in range(3))
+    check(lib.rcb_fold_poly(ptr(wt), C.byref(geo), ptr(w_eff), ptr(w_eff_t), stream()))
+    check(lib.rcb_fold_poly_bwd_f2(ptr(w_eff), C.byref(geo), ptr(w_bk), stream()))
+    w_bk_h = torch.empty(n, dtype=torch.float16, device="cuda")
+    check(lib.rcb_to_half(ptr(w_bk), ptr(w_bk_h), n, stream()))
+    d_h = torch.randn(items, 1, 2 * h, 2 * w, oc, generator=gen).cuda().half()
+    d_r = d_h.float().contiguous()
+    act = torch.randn(items, 1, h, w, ic, generator=gen).cuda().half()
+    act_f = act.float().contiguous()
+    ref = torch.zeros(act.shape, device="cuda")
+    got = torch.full(act.shape, 3.0, dtype=torch.float16, device="cuda")
+    check(lib.rcb_upconv_bwd(ptr(d_r), ptr(w_eff_t), ptr(act_f), ptr(ref), C.byref(geo), items, stream()))
+    check(lib.rcb_upconv_bwd_f2_hh(ptr(d_h), ptr(w_bk_h), ptr(act), 2, ptr(got), 4.0, C.byref(geo), items, stream()))
+    torch.cuda.synchronize()
+    bound = float(d_r.norm(dim=-1).max()) * float(wt.norm()) / np.sqrt(ic) * 4
+    err = float((got.float() / 4.0 - ref).abs().max())
+    print(f"[bwd_f2_hh {h}x{w} x{items}] err {err:.2e} bound {bound:.2e} max|ref| {float(ref.abs().max()):.2e}")
+    assert err < 1e-3 * bound, (err, bound)
+
+
 @pytest.mark.parametrize("h,w,items", [(8, 8, 7), (8, 8, 701), (16, 16, 3), (40, 44, 5)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_upconv_bwd_f2w_matches_simt_on_rounded_inputs(h, w, items, masked):
