@@ -22,6 +22,14 @@ __device__ __forceinline__ uint2 pack_h4(const float4& o) {
   return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
 }
 
+// same, saturating at +-65504 instead of producing inf (F2FP.SATFINITE)
+__device__ __forceinline__ uint2 pack_h4_sat(const float4& o) {
+  uint2 r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(o.y), "f"(o.x));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(o.w), "f"(o.z));
+  return r;
+}
+
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -872,6 +880,7 @@ upconv_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // interleaved line by line (8 x 8 grids; the TMA box puts the item dimension between x and y), so that the same
 // shifted-descriptor trick serves both.  Output rows (pixel, column parity) are staged as swizzled 128-byte rows and
 // leave through one TMA store per warp and line parity.
+constexpr int B2_THREADS = 320;                                 // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr int F2W_STAGES = 2, F2W_STAGE_BYTES = 26 * 1024, F2W_W_BLOCK = 64 * 128;
 struct ConvF2WArgs {
   PolyGeom g;
@@ -885,7 +894,7 @@ struct ConvF2WArgs {
   const float* bias;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(B2_THREADS, 1)
 upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvF2WArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -904,7 +913,7 @@ upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < F2W_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -978,15 +987,18 @@ upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (++s == F2W_STAGES) { s = 0; par ^= 1; }
     }
   } else {
-    // One (line parity, column parity) phase at a time: 32 pixel rows x 64 channels as fp16 = 32 swizzled 128-byte
-    // rows = one TMA store (two when the tile holds two items); two 4 KB buffers per warp alternate, and the next
-    // phase's accumulators are already on their way out of TMEM while this one is converted.
-    const int q = warp & 3;
-    uint8_t* stage = smem + a.epi_off + q * 8192;
+    // EIGHT epilogue warps: warp (q, hh) converts the 32 pixel rows of TMEM lane quarter q and the 32 channels of half hh,
+    // one (line parity, column parity) phase at a time: 32 rows x 32 channels as fp16 = 32 swizzled 64-byte rows = one TMA
+    // store (two when the tile holds two items); two 2 KB buffers per warp alternate, and the next phase's accumulators
+    // are already on their way out of TMEM while this one is converted.  (Four warps with 256 columns per lane each were
+    // the bottleneck of this kernel: the MMAs of a tile finished long before its conversion.)
+    const int q = warp & 3, hh = (warp - 2) >> 2, ew = warp - 2;
+    uint8_t* stage = smem + a.epi_off + ew * 4096;
     const int gl = lane >> 3, px = lane & 7;
     // staged row: [line][px] (one item) or [item][line][px] (two items: group = line * 2 + item)
     const int row = (a.ipt == 2 ? ((gl & 1) * 2 + (gl >> 1)) : gl) * 8 + px;
     const float slope = a.act ? 0.01f : 1.0f;
+    const float* bias_h = bias_s + hh * 32;
     int it = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -994,24 +1006,24 @@ upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tile_origin(t, item, y0, x0);
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      uint32_t v[2][4][16];
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_COLS + hh * 32);
+      uint32_t v[2][2][16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(acc + (uint32_t)(a.phase_col[0] + c * 16), v[0][c]);
+      for (int c = 0; c < 2; ++c) tmem_ld16_nowait(acc + (uint32_t)(a.phase_col[0] + c * 16), v[0][c]);
       tmem_wait_ld();
 #pragma unroll
       for (int ph = 0; ph < 4; ++ph) {                     // ph = ry * 2 + rx
         const int ry = ph >> 1, rx = ph & 1;
         if (ph < 3) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld16_nowait(acc + (uint32_t)(a.phase_col[ph + 1] + c * 16), v[(ph + 1) & 1][c]);
+          for (int c = 0; c < 2; ++c) tmem_ld16_nowait(acc + (uint32_t)(a.phase_col[ph + 1] + c * 16), v[(ph + 1) & 1][c]);
         }
         if (lane == 0) bulk_wait_read<1>();                // the store that last read this buffer has left it
         __syncwarp();
-        uint8_t* dst = stage + (ph & 1) * 4096 + row * 128;
+        uint8_t* dst = stage + (ph & 1) * 2048 + row * 64;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {                      // chunk c: channels 8c .. 8c+7 as fp16
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c * 8), b1 = *reinterpret_cast<const float4*>(bias_s + c * 8 + 4);
+        for (int c = 0; c < 4; ++c) {                      // chunk c: channels hh * 32 + 8c .. + 7 as fp16
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_h + c * 8), b1 = *reinterpret_cast<const float4*>(bias_h + c * 8 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float o[8];
 #pragma unroll
@@ -1020,17 +1032,17 @@ upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             o[e] = f > 0.f ? f : slope * f;
           }
           const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
-          *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+          *reinterpret_cast<uint4*>(dst + ((c ^ ((row >> 1) & 3)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          const uint8_t* sb = stage + (ph & 1) * 4096;
+          const uint8_t* sb = stage + (ph & 1) * 2048;
           if (a.ipt == 2) {
-            tma_store_5d(&tmO, sb, 0, rx, 0, ry, item * g.h + 2 * q);
-            if (item + 1 < a.items) tma_store_5d(&tmO, sb + 2048, 0, rx, 0, ry, (item + 1) * g.h + 2 * q);
+            tma_store_5d(&tmO, sb, hh * 32, rx, 0, ry, item * g.h + 2 * q);
+            if (item + 1 < a.items) tma_store_5d(&tmO, sb + 1024, hh * 32, rx, 0, ry, (item + 1) * g.h + 2 * q);
           } else if (y0 + 4 * q < g.h) {                    // h % 4 == 0: a warp's four lines are all inside or all outside
-            tma_store_5d(&tmO, sb, 0, rx, x0, ry, item * g.h + y0 + 4 * q);
+            tma_store_5d(&tmO, sb, hh * 32, rx, x0, ry, item * g.h + y0 + 4 * q);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -1061,7 +1073,6 @@ upconv_fwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // shared memory; CTAs are persistent, accumulators double-buffered, the result leaves through TMA stores.
 constexpr int B2_STAGES = 4;
 constexpr int B2_MSTAGES = 2;                                   // mask tiles in flight (fp16 variant)
-constexpr int B2_THREADS = 320;                                 // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr int HALO_BUF_H = 12 * 1024;                           // an fp16 halo box (18 x 10 rows of 64 bytes)
 struct ConvB2Args {
   PolyGeom g;
@@ -1300,8 +1311,8 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            o[e] = fminf(fmaxf(__uint_as_float(v[c >> 1][(c & 1) * 8 + e]) * (((bits >> (c * 8 + e)) & 1u) ? s1 : s0), -65504.f), 65504.f);
-          const uint2 lo = pack_h4(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4(make_float4(o[4], o[5], o[6], o[7]));
+            o[e] = __uint_as_float(v[c >> 1][(c & 1) * 8 + e]) * (((bits >> (c * 8 + e)) & 1u) ? s1 : s0);
+          const uint2 lo = pack_h4_sat(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4_sat(make_float4(o[4], o[5], o[6], o[7]));
           *reinterpret_cast<uint4*>(row + ((c ^ ((lane >> 1) & 3)) * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
         }
       } else {
@@ -1749,15 +1760,20 @@ static int launch_f2w(const void* src_h, const void* w_eff_k_h, const float* bia
     const cuuint64_t px = 128, line = 2 * (cuuint64_t)g.w * px;
     cuuint64_t dims[5] = {64, 2, (cuuint64_t)g.w, 2, (cuuint64_t)g.h * (cuuint64_t)items};
     cuuint64_t strides[4] = {px, 2 * px, line, 2 * line};
-    cuuint32_t box[5] = {64, 1, 8, 1, (cuuint32_t)(f.ipt == 2 ? 2 : 4)};
-    if (int rc = encode_map_t(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, out_h, 5, dims, strides, box, "out")) return rc;
+    cuuint32_t box[5] = {32, 1, 8, 1, (cuuint32_t)(f.ipt == 2 ? 2 : 4)};     // a warp's 32 rows x 32 channels of one phase
+    EncodeTiledFn enc = tc_get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)out_h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out, fp16) failed with CUresult %d", (int)r); return -1; }
   }
   cudaError_t e = cudaFuncSetAttribute(upconv_fwd_f2w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
   if (e != cudaSuccess) { set_error("rcb_upconv_fwd_tc_hh: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
   static int n_sm = 0;
   if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
-  upconv_fwd_f2w_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  upconv_fwd_f2w_kernel<<<grid, B2_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
   RCB_CHECK_LAUNCH("rcb_upconv_fwd_tc_hh");
   return 0;
 }

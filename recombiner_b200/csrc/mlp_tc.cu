@@ -48,7 +48,10 @@ struct Sm {
   static constexpr int WB = WF + 3 * WT;            // 3 backward B tiles [i][j] (layer 0: the 16 pe inputs)
   static constexpr int W3 = WB + 3 * WT;            // output B tile [16 (OUT used)][32]
   static constexpr int WF0B = W3 + WT;              // forward B tile of layer 0 for input features 32..47 (34-input INRs: video)
-  static constexpr int PLAIN = WF0B + WT;         // floats: [0,96) w0*b_l, [96,100) b3, [104,108) sq partials, [128,256) W3[j][4]
+  // the biases of the sine layers ride the chain MMAs: a third K = 16 block per layer whose rows hold (hi, lo) = the fp16
+  // split of w0 * b_l[j] in K elements 0, 1, against two constant 1.0 in the A operand (exact to 2^-22 relative)
+  static constexpr int WBI = WF0B + WT;             // 3 bias tiles [j][16 K], as 64-byte rows like the others (34 inputs: layer 0 uses WF0B)
+  static constexpr int PLAIN = WBI + 3 * WT;        // floats: [96,100) b3, [104,112) sq partials, [128,256) W3[j][4]
   static constexpr int BAR = PLAIN + 1024;
   static constexpr int TOTAL = BAR + 64;
 };
@@ -150,6 +153,12 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// same, saturating at +-65504 instead of producing inf (one F2FP.SATFINITE; NaN stays NaN)
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 // fp16 pair (lo * c.x, hi * c.y) for a packed fp16 pair c.  (One HMUL2 on the packed words instead of unpack + two
 // FMULs is 144 fewer instructions per pixel row and tile -- and measured SLOWER: 0.589 against 0.565 ms.)
@@ -241,6 +250,19 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     int yy = rem / a.pw, xx = rem - yy * a.pw;
     return (int64_t)z * a.pitch_z + (int64_t)yy * a.pitch_y + xx;
   };
+  // per-item bases, so that a pixel's pe / d pe address is one 32-bit multiply-add away (unstitched grids)
+  const char* pe_item = reinterpret_cast<const char*>(a.pe) + pe_origin * (NPE * (a.pe_half ? 2 : 4));
+  char* dpe_item = a.d_pe_h ? reinterpret_cast<char*>(a.d_pe_h) + pe_origin * (NPE * 2)
+                            : reinterpret_cast<char*>(a.d_pe) + pe_origin * (NPE * 4);
+  // coordinate decode of the generated inputs: shifts when the inner extents are powers of two (every shipped shape)
+  int x_sh[3] = {0, 0, 0};
+  bool x_pow2 = true;
+#pragma unroll
+  for (int ax = 1; ax < D; ++ax) {
+    const int sz = a.x_size[ax];
+    x_sh[ax] = 31 - __clz(sz);
+    x_pow2 = x_pow2 && (sz & (sz - 1)) == 0;
+  }
   // the 32 input features of pixel gp: 16 Fourier features, 16 positional encodings (raw fp32 patterns)
   constexpr int NFQ = F / (2 * D);          // frequencies per axis
   static_assert(2 * D * NFQ == F, "Fourier feature count does not match the dimensionality");
@@ -253,8 +275,10 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
       for (int ax = D - 1; ax >= 0; --ax) {
         const int sz = a.x_size[ax];
-        const int i = ax == 0 ? rem : rem % sz;
-        rem = ax == 0 ? 0 : rem / sz;
+        int i;
+        if (ax == 0) { i = rem; }
+        else if (x_pow2) { i = rem & (sz - 1); rem >>= x_sh[ax]; }
+        else { i = rem % sz; rem /= sz; }
         const float* row = a.x_tab + a.x_off[ax] + i * (2 * NFQ);
         if (NFQ % 4 == 0) {
 #pragma unroll
@@ -282,9 +306,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
       for (int i = 0; i < F; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
     }
-    const int64_t pidx = (pe_origin + (ok ? pe_off(gp) : 0)) * NPE;
     if (F == 16 && a.pe_half) {      // fp16 positional encodings: v[16..23] are already the packed pairs the chain operand needs
-      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.pe) + pidx);
+      const uint4* p = reinterpret_cast<const uint4*>(stitched ? pe_item + (ok ? pe_off(gp) : 0) * (NPE * 2)
+                                                               : pe_item + (uint32_t)(ok ? gp : 0) * (uint32_t)(NPE * 2));
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
@@ -294,7 +318,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       for (int c = 24; c < 32; ++c) v[c] = 0u;
       return;
     }
-    const uint4* p = reinterpret_cast<const uint4*>(a.pe + pidx);
+    const uint4* p = reinterpret_cast<const uint4*>(stitched ? pe_item + (ok ? pe_off(gp) : 0) * (NPE * 4)
+                                                             : pe_item + (uint32_t)(ok ? gp : 0) * (uint32_t)(NPE * 4));
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
@@ -321,7 +346,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     // all global loads first (they are independent), then the swizzled stores: the st.shared asm
     // statements are ordering points for the compiler, and a load-store-load-store chain would pay
     // the full memory latency twelve times per thread
-    float wv[12], w3v[2], bv = 0.f, b3v = 0.f, w3p = 0.f;
+    float wv[12], w3v[2], b3v = 0.f, w3p = 0.f;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const int e = t + i * MT_THREADS;                                         // W_l[i = r][j = c]
@@ -333,7 +358,6 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const int e = t + i * MT_THREADS, k = e / HID, j = e % HID;               // W_3[j][k] -> rows k, K = j
       w3v[i] = k < OUT ? wt_g[off3 + OUT + j * OUT + k] : 0.f;
     }
-    if (t < 3 * HID) bv = wt_g[(t / HID == 0 ? off0 : (t / HID == 1 ? off1 : off2)) + t % HID];
     if (t < OUT) b3v = wt_g[off3 + t];
     if (t < HID * 4 && t % 4 < OUT) w3p = wt_g[off3 + OUT + (t / 4) * OUT + t % 4];
 #pragma unroll
@@ -353,7 +377,23 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     if (WIDE) {
       for (int e = t; e < Sm::WT / 4; e += MT_THREADS) sts32(sbase + Sm::WF0B + e * 4, 0u);      // K 2..15 of the third block stay zero
     }
-    if (t < 3 * HID) plain[t] = w0 * bv;
+    // bias tiles: every 4-byte word written exactly once (row j = 64 bytes, the (hi, lo) pair is word 0 of the swizzled
+    // chunk 0); loads first, stores after, like the weights above
+    constexpr int BW = 3 * Sm::WT / 4 / MT_THREADS;
+    uint32_t bw[BW];
+#pragma unroll
+    for (int i = 0; i < BW; ++i) {
+      const int e = t + i * MT_THREADS;
+      const int l = e / (Sm::WT / 4), w = e % (Sm::WT / 4), j = w >> 4, ww = w & 15;
+      bw[i] = 0u;
+      if (ww == (((j >> 1) & 3) << 2) && !(WIDE && l == 0)) {
+        const float b = w0 * wt_g[(l == 0 ? off0 : (l == 1 ? off1 : off2)) + j];
+        const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+        bw[i] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BW; ++i) sts32(sbase + Sm::WBI + (t + i * MT_THREADS) * 4, bw[i]);
     if (t < 4) plain[96 + t] = b3v;
     if (t < HID * 4) plain[128 + t] = w3p;
     if (MODE != 0) {
@@ -374,6 +414,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const __half w = __float2half_rn(w0 * wt_g[off0 + HID + r * HID + c]);
       sts16(sbase + Sm::WF0B + swz64(c, r - 32), w);                            // forward B: rows j, K = i - 32
       sts16(sbase + Sm::WB + swz64(r - F, c), w);                               // backward B (layer 0): pe input r - F
+    }
+    if (t < HID) {                                                              // layer 0's bias: K elements 2, 3 of the same block
+      const float b = w0 * wt_g[off0 + t];
+      const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+      sts32(sbase + Sm::WF0B + swz64(t, 2), (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16));
     }
   }
   fence_async_smem();
@@ -447,32 +492,44 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const uint32_t t32 = idesc_f16_m128(32), t16 = idesc_f16_m128(16);
       const uint32_t h32 = idesc_f16(32) | IDESC_A_MN | IDESC_B_MN, h16 = idesc_f16(16) | IDESC_A_MN;
       switch (stage) {
-        case 0:                                                                 // Z0 = X0 W0
+        case 0:                                                                 // Z0 = X0 W0 + b0
           chain(R1, R0, Sm::WF, t32);
-          if (WIDE) umma_f16_ts(tmem_base + R1, tmem_base + R0 + 16u, smem_desc_sw64(sbase + Sm::WF0B), t32, 1u);
+          umma_f16_ts(tmem_base + R1, tmem_base + R0 + 16u, smem_desc_sw64(sbase + (WIDE ? Sm::WF0B : Sm::WBI)), t32, 1u);
           break;
-        case 1: chain(R0, R1, Sm::WF + Sm::WT, t32); break;                     // Z1 = X1 W1
-        case 2: chain(R1, R0, Sm::WF + 2 * Sm::WT, t32); break;                       // Z2 = X2 W2
+        case 1:                                                                 // Z1 = X1 W1 + b1
+          chain(R0, R1, Sm::WF + Sm::WT, t32);
+          umma_f16_ts(tmem_base + R0, tmem_base + R1 + 16u, smem_desc_sw64(sbase + Sm::WBI + Sm::WT), t32, 1u);
+          break;
+        case 2:                                                                 // Z2 = X2 W2 + b2
+          chain(R1, R0, Sm::WF + 2 * Sm::WT, t32);
+          umma_f16_ts(tmem_base + R1, tmem_base + R0 + 16u, smem_desc_sw64(sbase + Sm::WBI + 2 * Sm::WT), t32, 1u);
+          break;
         case 3: chain(R0, R1, Sm::W3, t16); break;                              // y  = X3 W3
         // The two groups add into the same weight-gradient accumulators.  The tensor pipe runs MMAs in the order
         // they are issued, so the tiles take turns (tile t after tile t - 1, per stage): the fp32 summation order,
         // and with it every bit of the gradients, does not depend on how the groups happen to interleave.
         case 4:
           chain(R0, R1, Sm::WB + 2 * Sm::WT, t32);                                    // dX2 = dZ2 W2^T
+#ifndef RCB_NO_TURN
           while (wg_turn[0] != tile) {}
+#endif
           wgrad_dy(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, h16);                // dW3 = X3^T dy
           wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, h32);                   // dW2 = X2^T dZ2
           wg_turn[0] = tile + 1;
           break;
         case 5:
           chain(R1, R0, Sm::WB + Sm::WT, t32);                                    // dX1 = dZ1 W1^T
+#ifndef RCB_NO_TURN
           while (wg_turn[1] != tile) {}
+#endif
           wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, h32);                   // dW1 = X1^T dZ1
           wg_turn[1] = tile + 1;
           break;
         default:
           chain(R0, R1, Sm::WB, t16);                                           // d pe = dZ0 W0[pe rows]^T
+#ifndef RCB_NO_TURN
           while (wg_turn[2] != tile) {}
+#endif
           if (WIDE) wgrad(TM_DW, so + Sm::XT1, so + Sm::DZT, h32, so + Sm::XT2);  // dW0 = X0^T dZ0, 34 inputs + bias row
           else wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, h32);                   // dW0 = X0^T dZ0
           wg_turn[2] = tile + 1;
@@ -517,6 +574,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   };
   PROF(4);
   float sq = 0.f;
+  constexpr uint32_t ONES2 = 0x3c003c00u;           // (1.0, 1.0) as packed fp16
+  const uint32_t ones8[8] = {ONES2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 
   for (int tile = g; tile < ntiles; tile += 2) {
     const int gp = tile * 128 + r;
@@ -529,11 +588,14 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       for (int i = 0; i < 16; ++i)
         x0p[i] = (F == 16 && a.pe_half && i >= 8) ? xin[8 + i] : pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
       tmem_st16(tm + R0, reinterpret_cast<const uint32_t(&)[16]>(x0p));
-      if (WIDE) {
+      if (WIDE) {          // third K block: inputs 32, 33, then the two ones that pick up the bias
 #pragma unroll
         for (int i = 16; i < 24; ++i)
-          x0p[i] = 2 * i + 1 < IN ? pack_h2(__uint_as_float(xin[2 * i < IN ? 2 * i : 0]), __uint_as_float(xin[2 * i + 1 < IN ? 2 * i + 1 : 0])) : 0u;
+          x0p[i] = 2 * i + 1 < IN ? pack_h2(__uint_as_float(xin[2 * i < IN ? 2 * i : 0]), __uint_as_float(xin[2 * i + 1 < IN ? 2 * i + 1 : 0]))
+                                  : (2 * i == IN ? ONES2 : 0u);
         tmem_st8(tm + R0 + 16u, x0p + 16);
+      } else {
+        tmem_st8(tm + R0 + 16u, ones8);
       }
     }
     publish(false);
@@ -551,14 +613,14 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float z0 = __uint_as_float(acc[16 * h + j]) + plain[l * 32 + 16 * h + j];
-          const float z1 = __uint_as_float(acc[16 * h + j + 1]) + plain[l * 32 + 16 * h + j + 1];
+          const float z0 = __uint_as_float(acc[16 * h + j]), z1 = __uint_as_float(acc[16 * h + j + 1]);     // bias included
           xp[(16 * h + j) >> 1] = pack_h2(__sinf(z0), __sinf(z1));
           cs[l][(16 * h + j) >> 1] = pack_h2(__cosf(z0), __cosf(z1));
         }
         if (MODE != 0) store_p16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), 16 * h, xp + 8 * h);
       }
       tmem_st16(reg, xp);
+      if (l < 2) tmem_st8(reg + 16u, ones8);                             // the next sine layer's bias block
       publish(MODE != 0);
       issue(l + 1);
     }
@@ -661,12 +723,12 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         uint32_t h[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          h[c] = pack_h2(fminf(fmaxf(__uint_as_float(acc[2 * c]), -65504.f), 65504.f), fminf(fmaxf(__uint_as_float(acc[2 * c + 1]), -65504.f), 65504.f));
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.d_pe_h) + (pe_origin + pe_off(gp)) * NPE);
+          h[c] = pack_h2_sat(__uint_as_float(acc[2 * c]), __uint_as_float(acc[2 * c + 1]));
+        uint4* dst = reinterpret_cast<uint4*>(stitched ? dpe_item + pe_off(gp) * (NPE * 2) : dpe_item + (uint32_t)gp * (uint32_t)(NPE * 2));
         dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
         dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
       } else if (valid) {
-        float4* dst = reinterpret_cast<float4*>(a.d_pe + (pe_origin + pe_off(gp)) * NPE);
+        float4* dst = reinterpret_cast<float4*>(stitched ? dpe_item + pe_off(gp) * (NPE * 4) : dpe_item + (uint32_t)gp * (uint32_t)(NPE * 4));
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           dst[c] = make_float4(unscale * __uint_as_float(acc[4 * c]), unscale * __uint_as_float(acc[4 * c + 1]),
@@ -710,7 +772,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           uint32_t hv[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            hv[c] = pack_h2(to_h(sc * __uint_as_float(acc[2 * c])), to_h(sc * __uint_as_float(acc[2 * c + 1])));
+            hv[c] = pack_h2_sat(sc * __uint_as_float(acc[2 * c]), sc * __uint_as_float(acc[2 * c + 1]));
           *reinterpret_cast<uint4*>(gwh + didx) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
           *reinterpret_cast<uint4*>(gwh + didx + 8) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
         } else if (wrow || brow) {
