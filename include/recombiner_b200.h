@@ -99,6 +99,8 @@ typedef struct {
                                             fp16 elements; not with accumulate) for rcb_gemm_tc_h */
   const int* p2g;                        /* optional: inverse of g2p (parameter index of a stored column), lets the row
                                             kernel read the posterior coalesced */
+  int fast_math;                         /* row-wise kernel only: softplus through the ex2 / lg2 approximations (as
+                                            rcb_update_args.fast_math); 0 in the fp32 parity configuration */
 } rcb_sample_args;
 int rcb_fit_sample(const rcb_sample_args* a, rcb_stream_t stream);
 
@@ -348,6 +350,10 @@ typedef struct {
    * the weights with THIS level's noise, red_mu_l / red_sig_l (rows, n_l) for the latent grid (level 1 only).  The data
    * gradient is then read from them instead of d_hw / d_lpe / eps_*. */
   const float* red_mu; const float* red_sig; const float* red_mu_l; const float* red_sig_l;
+  int fast_math;        /* row-wise kernel only: softplus / sigmoid / log, the divisions and square roots of the KL gradient
+                           and of Adam run on the special-function unit (ex2 / lg2 / rcp / rsqrt approximations, ~2 ulp;
+                           log1p by a series below 0.1) instead of the correctly rounded library sequences.  0 in the fp32
+                           parity configuration. */
 } rcb_update_args;
 int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream);
 

@@ -23,7 +23,7 @@ class SampleArgs(C.Structure):
                                  "eps_w", "eps_l", "hw", "lpe", "lpe_slot", "eps_w_store", "eps_l_store")] + \
                [("seed", I64), ("row_offset", I64)] + \
                [(n, I32) for n in ("rows", "S", "P", "n_w", "n_l", "ld_hw", "step", "tensor_id", "accumulate",
-                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P), ("lpe_h", P), ("hw_h", P), ("p2g", P)]
+                                   "rows_per_datum", "sp_total", "lpe_c")] + [("dyn", P), ("lpe_h", P), ("hw_h", P), ("p2g", P), ("fast_math", I32)]
 
 
 class UpconvGeom(C.Structure):
@@ -47,7 +47,7 @@ class UpdateArgs(C.Structure):
                                    "step", "tensor_id", "adam", "p_scale_direct", "rows_per_datum", "sp_total", "lpe_c")] + \
                [(n, F32) for n in ("adam_step_size", "adam_bc2_sqrt", "b1", "b2", "adam_eps", "beta_scalar",
                                    "grad_scale")] + [("dyn", P)] + \
-               [(n, P) for n in ("red_mu", "red_sig", "red_mu_l", "red_sig_l")]
+               [(n, P) for n in ("red_mu", "red_sig", "red_mu_l", "red_sig_l")] + [("fast_math", I32)]
 
 
 class ReduceArgs(C.Structure):

@@ -42,6 +42,25 @@ __device__ __forceinline__ float std_transform_grad(float x) {
   return sg / 6.f;
 }
 
+// The same two functions on the special-function unit (ex2 / lg2 / rcp approximations, ~2 ulp each).  log1p(t) keeps its
+// relative accuracy for small t = e^x through the alternating series below 0.1 (truncation < 2e-6 relative); above it
+// lg2(1 + t) is accurate to ~3e-6 relative.  Used by the update kernel when rcb_update_args.fast_math is set.
+__device__ __forceinline__ float std_transform_fast(float x) {
+  const float t = __expf(x);
+  const float series = t * (1.f - t * (0.5f - t * (0.33333334f - t * (0.25f - t * 0.2f))));
+  const float sp = x > 20.f ? x : (t < 0.1f ? series : __logf(1.f + t));
+  return sp * 0.16666667f;
+}
+__device__ __forceinline__ float std_transform_grad_fast(float x) {
+  const float sg = x > 20.f ? 1.f : __fdividef(1.f, 1.f + __expf(-x));
+  return sg * 0.16666667f;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // ---- counter-based Philox4x32-10 ------------------------------------------
 struct Philox {
   static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
@@ -81,7 +100,7 @@ __device__ __forceinline__ void philox_normal4(int64_t seed, int step, int tenso
     const float u1 = ((float)(c[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);
     const float u2 = (float)(c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
     // __logf has ~2^-22 absolute error near 1: a slightly positive result must not become sqrt(negative) = NaN
-    const float r = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
+    const float r = sqrt_fast(fmaxf(-2.0f * __logf(u1), 0.0f));     // MUFU: the radius does not need a correctly rounded root
     float sn, cs;
     __sincosf(6.2831853071795865f * u2, &sn, &cs);
     z[2 * h] = r * cs;

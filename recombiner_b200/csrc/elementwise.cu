@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
       float mu = a.loc[e] * (1.f - m);
       if (a.sample) mu += a.sample[e] * m;
       s_mu[p] = mu;
-      s_sig[p] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
+      s_sig[p] = (a.fast_math ? std_transform_fast(a.log_scale[e]) : std_transform(a.log_scale[e])) * (1.f - m) + 1e-15f * m;
     }
   } else {                          // coalesced read in stored (group) order, scattered into parameter order
     for (int q = threadIdx.x; q < a.P; q += blockDim.x) {
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, 4) sample_rows_kernel(rcb_sample_args a) 
       if (a.sample) mu += a.sample[e] * m;
       const int p = a.p2g ? a.p2g[q] : q;
       s_mu[p] = mu;
-      s_sig[p] = std_transform(a.log_scale[e]) * (1.f - m) + 1e-15f * m;
+      s_sig[p] = (a.fast_math ? std_transform_fast(a.log_scale[e]) : std_transform(a.log_scale[e])) * (1.f - m) + 1e-15f * m;
     }
   }
   __syncthreads();
@@ -218,6 +218,7 @@ __device__ __forceinline__ void reduce_row_samples(const rcb_update_args& a, int
 // in parameter order (coalesced) into shared memory, then the KL gradient + Adam runs in group
 // order (coalesced on the stored state).  Same arithmetic order as update_kernel.
 // dynamic smem: 2 * P floats.
+template <bool FAST>
 __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) {
   if (a.dyn) {
     a.seed = a.dyn->seed; a.step = a.dyn->step; a.adam_step_size = a.dyn->adam_step_size; a.adam_bc2_sqrt = a.dyn->adam_bc2_sqrt;
@@ -306,35 +307,52 @@ __global__ void __launch_bounds__(256, 4) update_rows_kernel(rcb_update_args a) 
       const int q = q0 + u * blockDim.x;
       const int64_t e = (int64_t)r * a.P + q;
       const float mu = mu_[u], rho = rho_[u], m = m_[u];
-      const float sig = std_transform(rho);
+      const float sig = FAST ? std_transform_fast(rho) : std_transform(rho);
       float d_mu = 0.f, d_sig = 0.f;
       if (m != 1.f) {
         d_mu = sdm_[u] * (a.grad_scale * (1.f - m));
         d_sig = sds_[u] * (a.grad_scale * (1.f - m));
       }
       const float beta = beta_[u];
-      const float mu_p = mup_[u], sig_p = a.p_scale_direct ? rawp_[u] : std_transform(rawp_[u]);
-      const float inv_vp = 1.f / (sig_p * sig_p);
+      const float mu_p = mup_[u];
+      const float sig_p = a.p_scale_direct ? rawp_[u] : (FAST ? std_transform_fast(rawp_[u]) : std_transform(rawp_[u]));
       const float dm = mu - mu_p;
-      const float ratio = sig / sig_p;
-      const float vr = ratio * ratio;
-      const float t1 = (dm / sig_p) * (dm / sig_p);
-      kl_term += beta * 0.5f * (vr + t1 - 1.f - logf(vr));
+      float inv_vp, vr, t1, inv_sig, lvr;
+      if (FAST) {      // the same expressions through one reciprocal of sigma_p and one of sigma
+        const float rp = __fdividef(1.f, sig_p);
+        inv_vp = rp * rp;
+        const float ratio = sig * rp;
+        vr = ratio * ratio;
+        t1 = (dm * rp) * (dm * rp);
+        inv_sig = __fdividef(1.f, sig);
+        lvr = __logf(vr);
+      } else {
+        inv_vp = 1.f / (sig_p * sig_p);
+        const float ratio = sig / sig_p;
+        vr = ratio * ratio;
+        t1 = (dm / sig_p) * (dm / sig_p);
+        inv_sig = 1.f / sig;
+        lvr = logf(vr);
+      }
+      kl_term += beta * 0.5f * (vr + t1 - 1.f - lvr);
       const float g_mu = d_mu + beta * dm * inv_vp;
-      const float g_sig = d_sig + beta * (sig * inv_vp - 1.f / sig);
-      const float g_rho = g_sig * std_transform_grad(rho);
+      const float g_sig = d_sig + beta * (sig * inv_vp - inv_sig);
+      const float g_rho = g_sig * (FAST ? std_transform_grad_fast(rho) : std_transform_grad(rho));
       if (a.adam) {
         const float step_size = a.adam_step_size, bc2s = a.adam_bc2_sqrt;
+        const float inv_bc2s = FAST ? __fdividef(1.f, bc2s) : 0.f;
         float m1 = m1a_[u], v = va_[u];
         m1 = m1 + (g_mu - m1) * (1.f - a.b1);
         v = v * a.b2 + (1.f - a.b2) * g_mu * g_mu;
         a.m1_loc[e] = m1; a.v_loc[e] = v;
-        a.loc[e] = mu - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
+        a.loc[e] = FAST ? mu - step_size * __fdividef(m1, fmaf(sqrt_fast(v), inv_bc2s, a.adam_eps))
+                        : mu - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
         m1 = m1b_[u]; v = vb_[u];
         m1 = m1 + (g_rho - m1) * (1.f - a.b1);
         v = v * a.b2 + (1.f - a.b2) * g_rho * g_rho;
         a.m1_ls[e] = m1; a.v_ls[e] = v;
-        a.log_scale[e] = rho - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
+        a.log_scale[e] = FAST ? rho - step_size * __fdividef(m1, fmaf(sqrt_fast(v), inv_bc2s, a.adam_eps))
+                              : rho - step_size * (m1 / (sqrtf(v) / bc2s + a.adam_eps));
       } else {
         a.g_loc[e] = g_mu;
         a.g_log_scale[e] = g_rho;
@@ -900,10 +918,12 @@ extern "C" int rcb_fit_update(const rcb_update_args* a, rcb_stream_t stream) {
   if (!a->perm_inv && !a->row_children && !a->lpe_slot && !a->red_mu && a->d_hw && (a->n_l == 0 || a->d_lpe) && a->n_w + a->n_l == a->P &&
       row_smem <= 200 * 1024) {
     if (row_smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(update_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
+      cudaError_t e = cudaFuncSetAttribute(update_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(update_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem);
       if (e != cudaSuccess) { set_error("rcb_fit_update: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
     }
-    update_rows_kernel<<<a->src_rows, 256, row_smem, (cudaStream_t)stream>>>(*a);
+    if (a->fast_math) update_rows_kernel<true><<<a->src_rows, 256, row_smem, (cudaStream_t)stream>>>(*a);
+    else update_rows_kernel<false><<<a->src_rows, 256, row_smem, (cudaStream_t)stream>>>(*a);
     RCB_CHECK_LAUNCH("rcb_fit_update");
     return 0;
   }

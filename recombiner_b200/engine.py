@@ -198,6 +198,7 @@ class FitEngine:
         self.b2w = False
         self._b2w_enabled = os.environ.get("RECOMBINER_BWD_F2W", "1") != "0"
         self._half_dpe = os.environ.get("RECOMBINER_HALF_DPE", "1") != "0"
+        self._fast_update = os.environ.get("RECOMBINER_FAST_UPDATE", "1") != "0"
         self._half_staged = False
         self._side = None
         if not torch.cuda.is_available():
@@ -498,6 +499,7 @@ class FitEngine:
         a.loc, a.log_scale, a.mask, a.sample = ptr(lv.loc.data), ptr(lv.log_scale.data), ptr(lv.mask), ptr(lv.sample)
         a.g2p, a.perm, a.row_map = ptr(lv.g2p), ptr(lv.perm), ptr(lv.row_map)
         a.p2g = ptr(lv.p2g)
+        a.fast_math = int(self.tc and self._fast_update)
         a.eps_w = ptr(noise.eps_for(lv.level))
         a.eps_l = ptr(noise.eps_l) if lv.level == 0 else None
         a.hw = ptr(ws["hw"])
@@ -1001,6 +1003,7 @@ class FitEngine:
         a.n_w, a.n_l, a.ld_hw, a.G = self.W, (self.L if lv.level == 0 else 0), self.ldw, lv.G
         a.step, a.tensor_id = noise.step, lv.level
         a.beta_scalar, a.grad_scale = float(lv.beta_scalar), grad_scale
+        a.fast_math = int(self.tc and self._fast_update)      # never in the fp32 parity configuration
         a.p_scale_direct = int(lv.p_scale_direct)
         a.dyn = ptr(self.step_state)
         if adam is not None:
