@@ -1349,7 +1349,7 @@ upconv_bwd_f2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // 128 KB as fp16) stay resident.  A tile is 16 lines x 8 pixels of one item, or two whole 8 x 8 items interleaved line
 // by line (the box puts the item dimension between x and y, as in the forward kernel above).  The incoming gradient
 // is fp16 in units of 1 / out_scale_inv (written by the kernel above with out_half); the result is fp32, true units.
-constexpr int B2W_STAGES = 2;
+constexpr int B2W_STAGES = 3;
 struct ConvB2WArgs {
   PolyGeom g;
   int items, tiles_x, tiles_y, n_tiles;
@@ -1358,9 +1358,10 @@ struct ConvB2WArgs {
   int a_off, epi_off, bar_off;
   float out_scale_inv;
   const void* src_act;                   // fp16 activations of the producing stage (LeakyReLU mask) or null
+  float* d_src;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(B2_THREADS, 1)
 upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvB2WArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -1379,7 +1380,7 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B2W_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1468,24 +1469,24 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // ===== epilogue: accumulator row m = (line group m / 8, pixel m % 8); a warp owns four line groups: four lines
-    // of one item, or two lines of each of the tile's two items (group = line * 2 + item)
-    const int q = warp & 3;
-    uint8_t* stage = smem + a.epi_off + q * 2 * 4096;
-    uint8_t* scratch = smem + a.epi_off + 4 * 2 * 4096 + q * 512;
-    uint4 h[8];                                             // mask loads run one tile ahead (see the kernel above)
+    // ===== epilogue, eight warps: accumulator row m = (line group m / 8, pixel m % 8); warp (q, hh) owns the 32 rows of
+    // TMEM lane quarter q -- four lines of one item, or two lines of each of the tile's two items (group = line * 2 +
+    // item) -- and the 32 channels of half hh.  Each lane holds 128 contiguous bytes of the fp32 result: they go straight
+    // from registers to global memory (eight 16-byte stores), which leaves the shared memory to a third operand stage.
+    const int q = warp & 3, hh = (warp - 2) >> 2, ew = warp - 2;
+    uint8_t* scratch = smem + a.epi_off + ew * 128;
+    uint4 h[4];                                             // mask loads run one tile ahead
     auto load_mask = [&](int t) {
       int item, y0, x0;
       tile_origin(t, item, y0, x0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {                         // load i: half a line group = 4 pixels x 8 chunks of 8 halves
-        const int gi = i >> 1;
-        const int yy = a.ipt == 2 ? 2 * q + (gi >> 1) : y0 + q * 4 + gi;
-        const int ii = a.ipt == 2 ? item + (gi & 1) : item;
-        const int xx = x0 + (i & 1) * 4 + (lane >> 3);
+      for (int i = 0; i < 4; ++i) {                         // load i: line group i of the warp's four, 8 pixels x 4 chunks of 8 halves
+        const int yy = a.ipt == 2 ? 2 * q + (i >> 1) : y0 + q * 4 + i;
+        const int ii = a.ipt == 2 ? item + (i & 1) : item;
+        const int xx = x0 + (lane >> 2);
         h[i] = (t < a.n_tiles && yy < g.h && xx < g.w && ii < a.items)
                    ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.src_act) +
-                                                          (((int64_t)ii * g.h + yy) * g.w + xx) * IC) + (lane & 7))
+                                                          (((int64_t)ii * g.h + yy) * g.w + xx) * IC) + hh * 4 + (lane & 3))
                    : make_uint4(0u, 0u, 0u, 0u);
       }
     };
@@ -1495,60 +1496,50 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int buf = it & 1;
       int item, y0, x0;
       tile_origin(t, item, y0, x0);
-      uint64_t bits = ~0ull;
+      uint32_t bits = ~0u;
       if (a.src_act != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const uint32_t w4[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
           uint32_t b8 = 0u;
 #pragma unroll
           for (int e = 0; e < 4; ++e)                       // an fp16 is positive exactly when its bits are a positive int16
             b8 |= (((short)(w4[e] & 0xffffu) > 0 ? 1u : 0u) | ((int)w4[e] >= 0x10000 ? 2u : 0u)) << (e * 2);
-          scratch[i * 32 + lane] = (uint8_t)b8;             // = [row i * 4 + lane / 8][chunk lane % 8]
+          scratch[i * 32 + lane] = (uint8_t)b8;             // = [row i * 8 + lane / 4][chunk lane % 4]
         }
         __syncwarp();
-        bits = *reinterpret_cast<const uint64_t*>(scratch + lane * 8);
+        bits = *reinterpret_cast<const uint32_t*>(scratch + lane * 4);
         __syncwarp();
-        load_mask(t + (int)gridDim.x);
       }
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * IC);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[2][16];
-        tmem_ld16_nowait(acc + (uint32_t)(hh * 32), v[0]);
-        tmem_ld16_nowait(acc + (uint32_t)(hh * 32 + 16), v[1]);
-        if (lane == 0) bulk_wait_read<1>();                // this buffer's previous store has left shared memory
-        __syncwarp();
-        tmem_wait_ld();
-        if (hh == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
-        }
-        uint8_t* row = stage + hh * 4096 + lane * 128;
-        const uint32_t hb = (uint32_t)(bits >> (hh * 32));
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * IC + hh * 32);
+      uint32_t v[2][16];
+      tmem_ld16_nowait(acc, v[0]);
+      tmem_ld16_nowait(acc + 16u, v[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&acc_empty[buf]);
+      if (a.src_act != nullptr) load_mask(t + (int)gridDim.x);
+      // this lane's pixel
+      const int gi = lane >> 3, px = lane & 7;
+      const int yy = a.ipt == 2 ? 2 * q + (gi >> 1) : y0 + q * 4 + gi;
+      const int ii = a.ipt == 2 ? item + (gi & 1) : item;
+      const int xx = x0 + px;
+      if (yy < g.h && xx < g.w && ii < a.items) {
+        float4* dst = reinterpret_cast<float4*>(a.d_src + (((int64_t)ii * g.h + yy) * g.w + xx) * IC + hh * 32);
         const float s1 = a.out_scale_inv, s0 = 0.01f * a.out_scale_inv;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((hb >> (c * 4 + e)) & 1u) ? s1 : s0);
-          *reinterpret_cast<float4*>(row + ((c ^ (lane & 7)) * 16)) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (a.ipt == 2) tma_store_4d(&tmO, stage + hh * 4096, hh * 32, 0, item, 2 * q);
-          else if (y0 + 4 * q < g.h) tma_store_4d(&tmO, stage + hh * 4096, hh * 32, x0, y0 + q * 4, item);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((bits >> (c * 4 + e)) & 1u) ? s1 : s0);
+          dst[c] = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
     }
-    if (lane == 0) bulk_wait_read<0>();
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -1873,10 +1864,10 @@ static int launch_b2w(const void* d_out_h, const void* w_bwd_k_h, const void* sr
   f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
   f.n_tiles = f.ipt == 2 ? ceil_div(items, 2) : f.tiles_x * f.tiles_y * items;
   f.halo_bytes = (f.ipt == 2 ? 10 * 2 * HALO_PITCH : HALO_LINES * HALO_PITCH) * 128;
-  f.out_scale_inv = out_scale_inv; f.src_act = src_act_h;
+  f.out_scale_inv = out_scale_inv; f.src_act = src_act_h; f.d_src = d_src;
   f.a_off = 16 * F2W_W_BLOCK;
   f.epi_off = f.a_off + B2W_STAGES * F2W_STAGE_BYTES;
-  f.bar_off = f.epi_off + 4 * 2 * 4096 + 4 * 512;
+  f.bar_off = f.epi_off + 8 * 128;                    // mask scratch of the eight epilogue warps
   const int smem_total = f.bar_off + 512 + 1024;
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
@@ -1922,7 +1913,7 @@ static int launch_b2w(const void* d_out_h, const void* w_bwd_k_h, const void* sr
   static int n_sm = 0;
   if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = f.n_tiles < n_sm ? f.n_tiles : n_sm;
-  upconv_bwd_f2w_kernel<<<grid, TC_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
+  upconv_bwd_f2w_kernel<<<grid, B2_THREADS, smem_total, (cudaStream_t)stream>>>(tmA, tmB, tmO, f);
   RCB_CHECK_LAUNCH("rcb_upconv_bwd_f2w");
   return 0;
 }

@@ -160,8 +160,9 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
-// fp16 pair (lo * c.x, hi * c.y) for a packed fp16 pair c.  (One HMUL2 on the packed words instead of unpack + two
-// FMULs is 144 fewer instructions per pixel row and tile -- and measured SLOWER: 0.589 against 0.565 ms.)
+// fp16 pair (lo * c.x, hi * c.y) for a packed fp16 pair c.  Two packed forms were measured and are SLOWER than the plain
+// unpack + two FMULs: one HMUL2 on the packed words (144 fewer instructions per pixel row and tile; 0.589 against
+// 0.565 ms) and one FMUL2 (mul.f32x2) per pair (48 fewer; 0.535 against 0.517 ms).
 __device__ __forceinline__ uint32_t mul_h2(float lo, float hi, uint32_t c) {
   const float2 c2 = unpack_h2(c);
   return pack_h2(lo * c2.x, hi * c2.y);
