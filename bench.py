@@ -53,8 +53,8 @@ N_CAND = 65536
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
 # captures (profiles/README.md); None where no capture exists yet
-TRAFFIC = {"mlp_fwd_bwd": 564.6e6, "update": 319.1e6, "sample": 120.3e6,    # profiles/r2_ncu_mlp_tc.csv, r2_ncu_update_sample.csv
-           "conv3_fwd": 448.0e6, "conv2_fwd": 151.0e6, "conv3_bwd": 804.0e6, "conv2_bwd": 449.0e6}   # profiles/r1_ncu_full_final.csv (kernels unchanged)
+TRAFFIC = {"mlp_fwd_bwd": 406.8e6, "update": 313.2e6, "sample": 116.4e6,     # profiles/r2_launches_final.csv (ncu, dram bytes per launch)
+           "conv3_fwd": 288.9e6, "conv2_fwd": 152.4e6, "conv3_bwd": 471.7e6, "conv2_bwd": 256.4e6}
 REC_TRAFFIC = {"picked": 36.6e6, "spread": 1672.9e6}                       # profiles/r2_ncu_rec_encode_staged.csv
 
 
@@ -67,8 +67,10 @@ def conv_bytes(eng, items: int):
     n3 = g3.h * g3.fy * g3.w * g3.fx * g3.oc
     h = 2 if (eng.half_acts and eng.f2_half) else 4          # bytes per stored activation element
     hp = 2 if (h == 2 and eng.half_pe and eng.tc_mlp and eng.n_f == 16) else 4      # positional encodings
+    hg = 2 if (h == 2 and getattr(eng, "b2w", False) and eng.tc_mlp) else 4          # gradients between the MLP and conv2
     per_item = {"conv2_fwd": n1 * h + n2 * h, "conv3_fwd": n2 * h + n3 * hp,
-                "conv3_bwd": n3 * 4 + n2 * h + n2 * 4, "conv2_bwd": n2 * 4 + n1 * h + n1 * 4,
+                # data gradients: with the fp16 exchange (engine.b2w) d_pe and d_a2 travel as fp16, d_a1 stays fp32
+                "conv3_bwd": n3 * hg + n2 * h + n2 * hg, "conv2_bwd": n2 * hg + n1 * h + n1 * 4,
                 "conv1_bwd": n1 * 4 + n0 * 4}
     return {k: float(v) * items for k, v in per_item.items()}
 

@@ -224,6 +224,10 @@ int rcb_upconv_bwd_f2w_eligible(const rcb_upconv_geom* g);
 int rcb_fold_poly_bwd_f2w(const float* w_eff, const rcb_upconv_geom* g, float* w_bwd_k, rcb_stream_t stream);
 int rcb_upconv_bwd_f2w(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, float* d_src,
                        float out_scale_inv, const rcb_upconv_geom* g, int items, rcb_stream_t stream);
+/* rcb_upconv_bwd_f2w leaving d_src as fp16 (saturating) multiplied by out_scale: the A operand of an fp16 GEMM for the
+ * stage below (rcb_gemm_tc_batch with in_half, whose out_scale undoes the unit). */
+int rcb_upconv_bwd_f2w_oh(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, void* d_src_h,
+                          float out_scale, const rcb_upconv_geom* g, int items, rcb_stream_t stream);
 /* dst[i] = (fp16, round to nearest) src[i] */
 int rcb_to_half(const float* src, void* dst, int64_t n, rcb_stream_t stream);
 

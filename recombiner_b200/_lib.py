@@ -97,6 +97,7 @@ SIGNATURES = {
     "rcb_upconv_bwd_f2": [P, P, P, I32, P, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_bwd_f2_oh": [P, P, P, I32, P, F32, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_bwd_f2_hh": [P, P, P, I32, P, F32, C.POINTER(UpconvGeom), I32, P],
+    "rcb_upconv_bwd_f2w_oh": [P, P, P, P, F32, C.POINTER(UpconvGeom), I32, P],
     "rcb_upconv_bwd_f2w_eligible": [C.POINTER(UpconvGeom)],
     "rcb_fold_poly_bwd_f2w": [P, C.POINTER(UpconvGeom), P, P],
     "rcb_upconv_bwd_f2w": [P, P, P, P, F32, C.POINTER(UpconvGeom), I32, P],

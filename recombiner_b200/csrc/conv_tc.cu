@@ -1357,8 +1357,9 @@ struct ConvB2WArgs {
   int halo_bytes;
   int a_off, epi_off, bar_off;
   float out_scale_inv;
+  int out_half;                          // d_src is fp16 (saturating), else fp32
   const void* src_act;                   // fp16 activations of the producing stage (LeakyReLU mask) or null
-  float* d_src;
+  void* d_src;
 };
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
@@ -1528,15 +1529,29 @@ upconv_bwd_f2w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int ii = a.ipt == 2 ? item + (gi & 1) : item;
       const int xx = x0 + px;
       if (yy < g.h && xx < g.w && ii < a.items) {
-        float4* dst = reinterpret_cast<float4*>(a.d_src + (((int64_t)ii * g.h + yy) * g.w + xx) * IC + hh * 32);
+        const int64_t off = (((int64_t)ii * g.h + yy) * g.w + xx) * IC + hh * 32;
         const float s1 = a.out_scale_inv, s0 = 0.01f * a.out_scale_inv;
+        if (a.out_half) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.d_src) + off);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float o[4];
+          for (int c = 0; c < 4; ++c) {
+            float o[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((bits >> (c * 4 + e)) & 1u) ? s1 : s0);
-          dst[c] = make_float4(o[0], o[1], o[2], o[3]);
+            for (int e = 0; e < 8; ++e)
+              o[e] = __uint_as_float(v[c >> 1][(c & 1) * 8 + e]) * (((bits >> (c * 8 + e)) & 1u) ? s1 : s0);
+            const uint2 lo = pack_h4_sat(make_float4(o[0], o[1], o[2], o[3])), hi = pack_h4_sat(make_float4(o[4], o[5], o[6], o[7]));
+            dst[c] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.d_src) + off);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = __uint_as_float(v[c >> 2][(c & 3) * 4 + e]) * (((bits >> (c * 4 + e)) & 1u) ? s1 : s0);
+            dst[c] = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
     }
@@ -1856,10 +1871,10 @@ static bool b2w_eligible(const PolyGeom& g) {
          g.oc == 64 && g.ic == 64 && ((g.h == 8 && g.w == 8) || (g.h >= 16 && g.h % 4 == 0));
 }
 // fp16 d_out (scaled), fp16 K-major weights [ic][(a, b, oc)], fp16 mask activations, fp32 d_src
-static int launch_b2w(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, float* d_src, const PolyGeom& g,
-                      int items, float out_scale_inv, rcb_stream_t stream) {
+static int launch_b2w(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, void* d_src, const PolyGeom& g,
+                      int items, float out_scale_inv, rcb_stream_t stream, int out_half = 0) {
   ConvB2WArgs f;
-  f.g = g; f.items = items;
+  f.g = g; f.items = items; f.out_half = out_half;
   f.ipt = (g.h == 8 && g.w == 8) ? 2 : 1;
   f.tiles_x = ceil_div(g.w, 8); f.tiles_y = ceil_div(g.h, 16);
   f.n_tiles = f.ipt == 2 ? ceil_div(items, 2) : f.tiles_x * f.tiles_y * items;
@@ -1894,20 +1909,7 @@ static int launch_b2w(const void* d_out_h, const void* w_bwd_k_h, const void* sr
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(d_out, strided) failed with CUresult %d", (int)r); return -1; }
   }
   if (int rc = make_map_b(&tmB, w_bwd_k_h, 64, 1024, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B, 2)) return rc;
-  {
-    const cuuint64_t px = 256, line = (cuuint64_t)g.w * px, img = (cuuint64_t)g.h * line;
-    if (f.ipt == 2) {
-      cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)items, (cuuint64_t)g.h};
-      cuuint64_t strides[3] = {px, img, line};
-      cuuint32_t box[4] = {32, 8, 2, 2};
-      if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
-    } else {
-      cuuint64_t dims[4] = {64, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)items};
-      cuuint64_t strides[3] = {px, line, img};
-      cuuint32_t box[4] = {32, 8, 4, 1};
-      if (int rc = encode_map(&tmO, d_src, 4, dims, strides, box, "d_src")) return rc;
-    }
-  }
+  memset(&tmO, 0, sizeof(tmO));            // the result leaves through plain stores (kernel parameter kept for ABI symmetry)
   cudaError_t e = cudaFuncSetAttribute(upconv_bwd_f2w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
   if (e != cudaSuccess) { set_error("rcb_upconv_bwd_f2w: smem opt-in failed: %s", cudaGetErrorString(e)); return -1; }
   static int n_sm = 0;
@@ -2085,6 +2087,17 @@ extern "C" int rcb_upconv_bwd_f2w(const void* d_out_h, const void* w_bwd_k_h, co
   RCB_CHECK_ARG(b2w_eligible(g), "rcb_upconv_bwd_f2w: only 2-D x2 stages with 64 -> 64 channels (8 x 8 grids or >= 16 lines)");
   if (items <= 0) return 0;
   return launch_b2w(d_out_h, w_bwd_k_h, src_act_h, d_src, g, items, out_scale_inv, stream);
+}
+// same with d_src left as fp16 (saturating), multiplied by out_scale: the operand of an fp16 GEMM for the stage below
+extern "C" int rcb_upconv_bwd_f2w_oh(const void* d_out_h, const void* w_bwd_k_h, const void* src_act_h, void* d_src_h,
+                                     float out_scale, const rcb_upconv_geom* geo, int items, rcb_stream_t stream) {
+  PolyGeom g;
+  if (int rc = make_geom_tc(geo, &g)) return rc;
+  RCB_CHECK_ARG(d_out_h && w_bwd_k_h && d_src_h, "rcb_upconv_bwd_f2w_oh: null pointer");
+  RCB_CHECK_ARG(out_scale > 0.f, "rcb_upconv_bwd_f2w_oh: out_scale must be positive");
+  RCB_CHECK_ARG(b2w_eligible(g), "rcb_upconv_bwd_f2w_oh: only 2-D x2 stages with 64 -> 64 channels (8 x 8 grids or >= 16 lines)");
+  if (items <= 0) return 0;
+  return launch_b2w(d_out_h, w_bwd_k_h, src_act_h, d_src_h, g, items, out_scale, stream, 1);
 }
 
 // w_eff: [phase][tap][ic][oc] as produced by rcb_fold_poly (already K-major for this GEMM).

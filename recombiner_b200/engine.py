@@ -199,6 +199,8 @@ class FitEngine:
         self._b2w_enabled = os.environ.get("RECOMBINER_BWD_F2W", "1") != "0"
         self._half_dpe = os.environ.get("RECOMBINER_HALF_DPE", "1") != "0"
         self._fast_update = os.environ.get("RECOMBINER_FAST_UPDATE", "1") != "0"
+        self._half_da1 = os.environ.get("RECOMBINER_HALF_DA1", "1") != "0"
+        self.M1_h = None
         self._half_staged = False
         self._side = None
         if not torch.cuda.is_available():
@@ -350,6 +352,8 @@ class FitEngine:
                 self.w2_bk = torch.empty(self.w_eff[1].numel(), device=dev)
                 self.w2_bk_h = torch.empty(self.w_eff[1].numel(), dtype=torch.float16, device=dev)
                 self.w3_bk_h = torch.empty(self.w_eff[2].numel(), dtype=torch.float16, device=dev)
+                if self.dense1 and self._half_da1:
+                    self.M1_h = torch.empty(self.M1.shape, dtype=torch.float16, device=dev)     # conv1 data gradient on fp16 operands
             self._derived = True
         for l, c in enumerate(self.counts):
             ld = self.A[l].shape[1]
@@ -378,6 +382,8 @@ class FitEngine:
                   "rcb_fold_poly_bwd_f2w")
             check(self.lib.rcb_to_half(ptr(self.w2_bk), ptr(self.w2_bk_h), self.w2_bk_h.numel(), st), "rcb_to_half")
             check(self.lib.rcb_to_half(ptr(self.w3_bk), ptr(self.w3_bk_h), self.w3_bk_h.numel(), st), "rcb_to_half")
+            if getattr(self, "M1_h", None) is not None:
+                check(self.lib.rcb_to_half(ptr(self.M1), ptr(self.M1_h), self.M1_h.numel(), st), "rcb_to_half")
 
     # -------------------------------------------------------------- workspaces --
     def workspace(self, rows: int, S: int) -> Dict[str, torch.Tensor]:
@@ -821,9 +827,17 @@ class FitEngine:
                 else:
                     check(self.lib.rcb_upconv_bwd_f2_oh(ptr(ws["d_pe"]), ptr(self.w3_bk), ptr(ws["a2h"]), 2, ptr(ws["d_a2_h"]), sc,
                                                         C.byref(g3), citems, stream()), "rcb_upconv_bwd_f2_oh[3]")
+            # d_a1 stays fp16 (same unit) when the stage below is the dense fp16 GEMM, which then multiplies the unit out
+            da1_half = bool(self.dense1 and self.M1_h is not None and ws.get("d_pe_is_half"))
             with self.section("conv2_bwd"):
-                check(self.lib.rcb_upconv_bwd_f2w(ptr(ws["d_a2_h"]), ptr(self.w2_bk_h), ptr(ws["a1h"]), ptr(ws["d_a1"]), 1.0 / sc,
-                                                  C.byref(g2), citems, stream()), "rcb_upconv_bwd_f2w[2]")
+                if da1_half:
+                    if "d_a1_h" not in ws:
+                        ws["d_a1_h"] = torch.empty(ws["d_a1"].shape, dtype=torch.float16, device=self.device)
+                    check(self.lib.rcb_upconv_bwd_f2w_oh(ptr(ws["d_a2_h"]), ptr(self.w2_bk_h), ptr(ws["a1h"]), ptr(ws["d_a1_h"]), 1.0,
+                                                         C.byref(g2), citems, stream()), "rcb_upconv_bwd_f2w_oh[2]")
+                else:
+                    check(self.lib.rcb_upconv_bwd_f2w(ptr(ws["d_a2_h"]), ptr(self.w2_bk_h), ptr(ws["a1h"]), ptr(ws["d_a1"]), 1.0 / sc,
+                                                      C.byref(g2), citems, stream()), "rcb_upconv_bwd_f2w[2]")
         else:
             with self.section("conv3_bwd"):
                 if self.f2_half:
@@ -840,7 +854,14 @@ class FitEngine:
                 else:
                     self._upconv_bwd(1, ws["d_a2"], ws["a1"], ws["d_a1"], citems)
         with self.section("conv1_bwd"):
-            if self.dense1:
+            if b2w and da1_half:
+                Lt, n1 = self.M1.shape
+                key = ("c1_bwd_h", self.map_generation, sc)
+                if key not in ws:
+                    ws[key] = self._batch_args([ws["d_a1_h"].data_ptr()], n1, [self.M1_h], [ws["d_lpe"].data_ptr()], Lt, citems,
+                                               [Lt], [n1], 1, 1.0 / sc)
+                check(self.lib.rcb_gemm_tc_batch(*ws[key][0], stream()), "rcb_gemm_tc_batch[conv1_bwd]")
+            elif self.dense1:
                 Lt = self.M1.shape[0]
                 self._gemm(ws["d_a1"], 0, ws["d_a1"].shape[1], self.M1T, self.M1T.shape[1], ws["d_lpe"], 0, Lt,
                            citems, Lt, self.M1T.shape[0], Bt=self.M1)

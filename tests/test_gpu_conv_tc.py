@@ -260,6 +260,12 @@ def test_upconv_bwd_f2w_matches_simt_on_rounded_inputs(h, w, items, masked):
     err = float((got - ref).abs().max())
     print(f"[bwd_f2w {h}x{w} x{items}] err {err:.2e} bound {bound:.2e} max|ref| {float(ref.abs().max()):.2e}")
     assert err < 2e-4 * bound, (err, bound)
+    # fp16 output = the fp32 output (same accumulators, same power-of-two factor) rounded once
+    got_h = torch.full(act.shape, 3.0, dtype=torch.float16, device="cuda")
+    check(lib.rcb_upconv_bwd_f2w_oh(ptr(d_h), ptr(w_bk_h), ptr(act if masked else None), ptr(got_h), 1.0 / scale, C.byref(geo),
+                                    items, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(got_h, got.half())
 
 
 @pytest.mark.parametrize("name", ["cifar_conv2", "wide_2d_ragged", "video_conv2_3d", "protein_conv2", "f2w_ragged", "f2w_8x8_many"])
