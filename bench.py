@@ -68,10 +68,11 @@ def conv_bytes(eng, items: int):
     h = 2 if (eng.half_acts and eng.f2_half) else 4          # bytes per stored activation element
     hp = 2 if (h == 2 and eng.half_pe and eng.tc_mlp and eng.n_f == 16) else 4      # positional encodings
     hg = 2 if (h == 2 and getattr(eng, "b2w", False) and eng.tc_mlp) else 4          # gradients between the MLP and conv2
+    hd = 2 if (hg == 2 and eng.dense1 and getattr(eng, "M1_h", None) is not None) else 4     # gradient into the dense first stage
     per_item = {"conv2_fwd": n1 * h + n2 * h, "conv3_fwd": n2 * h + n3 * hp,
                 # data gradients: with the fp16 exchange (engine.b2w) d_pe and d_a2 travel as fp16, d_a1 stays fp32
-                "conv3_bwd": n3 * hg + n2 * h + n2 * hg, "conv2_bwd": n2 * hg + n1 * h + n1 * 4,
-                "conv1_bwd": n1 * 4 + n0 * 4}
+                "conv3_bwd": n3 * hg + n2 * h + n2 * hg, "conv2_bwd": n2 * hg + n1 * h + n1 * hd,
+                "conv1_bwd": n1 * hd + n0 * 4}
     return {k: float(v) * items for k, v in per_item.items()}
 
 
