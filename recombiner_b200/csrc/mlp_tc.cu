@@ -16,6 +16,10 @@
 //    O(1)) or of the caller's scale (mode 2), which keeps them in fp16's normal range; the
 //    accumulators are fp32 and are unscaled when they leave TMEM;
 //  * the derivative factors cos(.) are held packed as half2.
+// A tile costs SIX MMA round trips: the first product of the group's NEXT tile (Z0 = X0 W0) is issued in the same batch
+// as the last one of the current tile (d pe = dZ0 W0^T), whose result is read back at the top of the next tile; the inputs
+// X0 are kept as an fp16 copy in shared memory for dW0 (no second load), and the constant (1, 1) block that picks up the
+// biases has TMEM columns of its own (written once).
 // As in the second design the A tiles carry a row of ones (accumulator row 32 = bias gradient),
 // w0 is folded into the staged weights, and TF32 rounding is +0x1000 on the fp32 pattern.
 // Reference semantics: test_model.py:347-355, 624-627; weight layout :269-280.
@@ -29,22 +33,26 @@ namespace mlp {
 constexpr int MT_THREADS = 256;        // 2 groups x 128 threads: one thread per pixel row of the group's tile
 constexpr int MT_GROUP = 128;
 
-// TMEM columns: tile slot s owns [64 s, 64 s + 64) = regions R0, R1; weight-gradient accumulators after
-constexpr uint32_t TM_DW = 128, TM_COLS = 256;
+// TMEM columns: tile slot s owns [64 s, 64 s + 64) = regions R0, R1; weight-gradient accumulators after (112 columns);
+// [240 + 8 s, 248 + 8 s): the slot's bias block of the chain's A operand (K elements (1, 1, 0 ..); 34 inputs: (x32, x33, 1, 1, 0 ..))
+constexpr uint32_t TM_DW = 128, TM_ONES = 240, TM_COLS = 256;
 
 struct Sm {
   // fp16 operands of the weight-gradient MMAs, pixel-major (MN-major for the MMA): one 64-byte row of 32 features per
   // pixel, 64-byte swizzle, 8-pixel groups 512 B apart
   static constexpr int XP = 128 * 64;
   // per tile slot
-  static constexpr int XT1 = 0, XT2 = XP, XT3 = 2 * XP;   // X_1, X_2, X_3 (XT3 later holds X_0)
-  static constexpr int DZT = 3 * XP;                // dZ_l
-  static constexpr int DZ3 = DZT + XP;              // dy^T   [2 K blocks][16][64 px], K-major (rows >= OUT stay zero)
+  // X_0 (the tile's inputs, for dW0) comes first: the second atom of its 34-input operand (over X_2) must lie above it
+  static constexpr int XT0 = 0, XT1 = XP, XT2 = 2 * XP, XT3 = 3 * XP;   // X_0 .. X_3
+  static constexpr int DZT = 4 * XP;                // dZ_l
+  static constexpr int DZ3 = 5 * XP;                // dy^T   [2 K blocks][16][64 px], K-major (rows >= OUT stay zero)
   static constexpr int SLOT = DZ3 + 2 * 2048;
   // per CTA
-  static constexpr int ONES = 2 * SLOT;             // second MN atom of every A operand: feature 32 = 1 (bias row), 33..63 = 0
+  // second MN atom of every A operand: feature 32 = 1 (bias row), 33..63 = 0.  Every pixel row is the same, so ONE K = 16
+  // step (16 pixel rows, 1 KB) serves all eight steps: the descriptor's leading-byte offset shrinks by 1 KB per step
+  static constexpr int ONES = 2 * SLOT;
   static constexpr int WT = 32 * 64;                // one fp16 weight tile: 32 rows of 32 K elements (64 B), 64-byte swizzle
-  static constexpr int WF = ONES + XP;              // 3 forward B tiles  [j][i]
+  static constexpr int WF = ONES + 1024;            // 3 forward B tiles  [j][i]
   static constexpr int WB = WF + 3 * WT;            // 3 backward B tiles [i][j] (layer 0: the 16 pe inputs)
   static constexpr int W3 = WB + 3 * WT;            // output B tile [16 (OUT used)][32]
   static constexpr int WF0B = W3 + WT;              // forward B tile of layer 0 for input features 32..47 (34-input INRs: video)
@@ -55,6 +63,7 @@ struct Sm {
   static constexpr int BAR = PLAIN + 1024;
   static constexpr int TOTAL = BAR + 64;
 };
+static_assert(2 * (Sm::TOTAL + 1024) <= 228 * 1024, "two CTAs per SM");
 static_assert(Sm::SLOT % 1024 == 0 && Sm::WF % 1024 == 0 && Sm::W3 % 1024 == 0, "swizzled tiles need 1024-B alignment");
 
 // byte offset of element (row, col) in a tile of 128-byte rows with the 128-byte swizzle; 4- and 2-byte elements
@@ -387,7 +396,9 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       const int e = t + i * MT_THREADS;
       const int l = e / (Sm::WT / 4), w = e % (Sm::WT / 4), j = w >> 4, ww = w & 15;
       bw[i] = 0u;
-      if (ww == (((j >> 1) & 3) << 2) && !(WIDE && l == 0)) {
+      // 34 inputs: the bias block of the A operand is (x32, x33, 1, 1, 0 ..) for all three layers, so the pair sits in K
+      // elements 2, 3 (word 1) and K elements 0, 1 stay zero
+      if (ww == ((((j >> 1) & 3) << 2) | (WIDE ? 1 : 0)) && !(WIDE && l == 0)) {
         const float b = w0 * wt_g[(l == 0 ? off0 : (l == 1 ? off1 : off2)) + j];
         const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
         bw[i] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
@@ -399,8 +410,8 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     if (t < HID * 4) plain[128 + t] = w3p;
     if (MODE != 0) {
       // the shared second atom of the A operands: per pixel row, feature 32 = 1.0 (chunk 0 of the swizzled row), rest 0
-      for (int e = t; e < 128 * 16; e += MT_THREADS) {
-        const int k = e >> 4, w = e & 15;
+      if (t < 16 * 16) {
+        const int k = t >> 4, w = t & 15;
         sts32(sbase + Sm::ONES + k * 64 + w * 4, w == (((k >> 1) & 3) << 2) ? 0x00003c00u : 0u);
       }
       for (int e = t; e < 2 * 1024; e += MT_THREADS) sts32(sbase + (e / 1024) * Sm::SLOT + Sm::DZ3 + (e % 1024) * 4, 0u);
@@ -430,7 +441,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16);
-  const uint32_t R0 = (uint32_t)(64 * g), R1 = R0 + 32;
+  const uint32_t R0 = (uint32_t)(64 * g), R1 = R0 + 32, RB = TM_ONES + (uint32_t)(8 * g);
   const int so = g * Sm::SLOT;
 
   if (MODE != 0) {
@@ -463,12 +474,21 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     for (int k = 0; k < 2; ++k)
       umma_f16_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)(k * 8), db + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
   };
-  // dW = X^T dZ over the tile's 128 pixels: both operands pixel-major (MN-major), eight K = 16 steps of 1024 B
-  auto wgrad = [&](uint32_t d_col, int x_off, int dz_off, uint32_t idesc, int atom2_off = Sm::ONES) {
+  // third K = 16 block of a sine layer's product: the group's bias block (RB) against the layer's bias tile
+  auto bias = [&](uint32_t d_col, int b_off, uint32_t idesc) {
+    umma_f16_ts(tmem_base + d_col, tmem_base + RB, smem_desc_sw64(sbase + b_off), idesc, 1u);
+  };
+  // dW = X^T dZ over the tile's 128 pixels: both operands pixel-major (MN-major), eight K = 16 steps of 1024 B.  The
+  // second 32-feature atom of A is the shared 1 KB ones block (its distance shrinks with every step) or, for the 34-input
+  // dW0, a per-tile block that advances with the first
+  auto wgrad = [&](uint32_t d_col, int x_off, int dz_off, uint32_t idesc, int atom2_off = Sm::ONES, bool atom2_fixed = true) {
     const uint32_t xa = sbase + x_off;
     const uint64_t da = smem_desc_pm(xa, sbase + atom2_off - xa), db = smem_desc_pm(sbase + dz_off, 16);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) umma_f16(tmem_base + d_col, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, 1u);
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t step = (uint64_t)(k * 64);
+      umma_f16(tmem_base + d_col, atom2_fixed ? da + step - (step << 16) : da + step, db + step, idesc, 1u);
+    }
   };
   // dW3 = X3^T dy: A pixel-major, B = dy^T K-major [2 K blocks][16][64 px]
   auto wgrad_dy = [&](uint32_t d_col, int x_off, int dy_off, uint32_t idesc) {
@@ -478,12 +498,16 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     for (int kb = 0; kb < 2; ++kb) {
       const uint64_t db = smem_desc_sw128(sbase + dy_off + kb * 2048);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(tmem_base + d_col, da + (uint64_t)((kb * 4 + k) * 64), db + (uint64_t)(k * 2), idesc, 1u);
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t step = (uint64_t)((kb * 4 + k) * 64);
+        umma_f16(tmem_base + d_col, da + step - (step << 16), db + (uint64_t)(k * 2), idesc, 1u);
+      }
     }
   };
-  // stages of one tile: 0-2 sine layers, 3 output layer, 4-6 backward
-  auto issue = [&](int stage, int tile = 0) {
+  // stages of one tile: 0-2 sine layers, 3 output layer, 4-6 backward.  Stage 6 also carries stage 0 of the group's NEXT
+  // tile (`next`): its inputs are already in R0[0, 16) and the bias block, and nothing it touches is read by stage 6
+  // except R1, which the in-order pipe has consumed (A of d pe) before the next tile's Z0 overwrites it.
+  auto issue = [&](int stage, int tile = 0, bool next = false) {
     const bool mine = q == (stage & 3);
     if (mine) {
       mbar_wait(&bar_ready[g], ph_ready);
@@ -495,15 +519,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       switch (stage) {
         case 0:                                                                 // Z0 = X0 W0 + b0
           chain(R1, R0, Sm::WF, t32);
-          umma_f16_ts(tmem_base + R1, tmem_base + R0 + 16u, smem_desc_sw64(sbase + (WIDE ? Sm::WF0B : Sm::WBI)), t32, 1u);
+          bias(R1, WIDE ? Sm::WF0B : Sm::WBI, t32);
           break;
         case 1:                                                                 // Z1 = X1 W1 + b1
           chain(R0, R1, Sm::WF + Sm::WT, t32);
-          umma_f16_ts(tmem_base + R0, tmem_base + R1 + 16u, smem_desc_sw64(sbase + Sm::WBI + Sm::WT), t32, 1u);
+          bias(R0, Sm::WBI + Sm::WT, t32);
           break;
         case 2:                                                                 // Z2 = X2 W2 + b2
           chain(R1, R0, Sm::WF + 2 * Sm::WT, t32);
-          umma_f16_ts(tmem_base + R1, tmem_base + R0 + 16u, smem_desc_sw64(sbase + Sm::WBI + 2 * Sm::WT), t32, 1u);
+          bias(R1, Sm::WBI + 2 * Sm::WT, t32);
           break;
         case 3: chain(R0, R1, Sm::W3, t16); break;                              // y  = X3 W3
         // The two groups add into the same weight-gradient accumulators.  The tensor pipe runs MMAs in the order
@@ -527,13 +551,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           wg_turn[1] = tile + 1;
           break;
         default:
-          chain(R0, R1, Sm::WB, t16);                                           // d pe = dZ0 W0[pe rows]^T
+          chain(R0 + 16u, R1, Sm::WB, t16);                                     // d pe = dZ0 W0[pe rows]^T  -> R0[16, 32)
 #ifndef RCB_NO_TURN
           while (wg_turn[2] != tile) {}
 #endif
-          if (WIDE) wgrad(TM_DW, so + Sm::XT1, so + Sm::DZT, h32, so + Sm::XT2);  // dW0 = X0^T dZ0, 34 inputs + bias row
-          else wgrad(TM_DW, so + Sm::XT3, so + Sm::DZT, h32);                   // dW0 = X0^T dZ0
+          if (WIDE) wgrad(TM_DW, so + Sm::XT0, so + Sm::DZT, h32, so + Sm::XT2, false);  // dW0 = X0^T dZ0, 34 inputs + bias row
+          else wgrad(TM_DW, so + Sm::XT0, so + Sm::DZT, h32);                   // dW0 = X0^T dZ0
           wg_turn[2] = tile + 1;
+          if (next) {                                                           // the next tile's Z0 = X0 W0 + b0
+            chain(R1, R0, Sm::WF, t32);
+            bias(R1, WIDE ? Sm::WF0B : Sm::WBI, t32);
+          }
           break;
       }
       umma_commit(&bar_mma[g]);
@@ -557,10 +585,13 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
                    "r"(hp[4 * c + 2]), "r"(hp[4 * c + 3]) : "memory");
     }
   };
-  auto publish = [&](bool smem_written) {   // hand this thread's share of the stage's operands to the MMAs
+  // hand this thread's share of the stage's operands to the MMAs.  `fence_smem`: the stage's MMAs read shared memory this
+  // thread wrote (through the async proxy); the proxy fence covers every earlier store of the thread, so the forward
+  // stages, whose fp16 copies are only read from stage 4 on, publish without it
+  auto publish = [&](bool fence_smem) {
     PROF(300);
     tmem_st_wait();
-    if (smem_written) fence_async_smem();
+    if (fence_smem) fence_async_smem();
     tc_fence_before();
     mbar_arrive(&bar_ready[g]);
     PROF(301);
@@ -576,36 +607,77 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   PROF(4);
   float sq = 0.f;
   constexpr uint32_t ONES2 = 0x3c003c00u;           // (1.0, 1.0) as packed fp16
-  const uint32_t ones8[8] = {ONES2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  uint32_t x0p[16];                                 // the tile's 32 first inputs as packed fp16 pairs
+  uint32_t wide_x = 0u;                             // 34 inputs: (x32, x33) of the tile whose inputs are in TMEM
+  uint32_t wide_n = 0u;                             // ... and of the tile whose inputs are in x0p
+  // the inputs in `xin` -> x0p (as soon as the loads have landed: 16 live registers instead of 32) ...
+  auto pack_x0 = [&]() {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      x0p[i] = (F == 16 && a.pe_half && i >= 8) ? xin[8 + i] : pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
+    if (WIDE) wide_n = pack_h2(__uint_as_float(xin[32]), __uint_as_float(xin[IN - 1]));
+  };
+  // ... -> the chain operand R0[0, 16) and (34 inputs) the per-tile bias block: inputs 32, 33, then the two ones
+  auto put_x0 = [&]() {
+    tmem_st16(tm + R0, x0p);
+    if (WIDE) {
+      wide_x = wide_n;
+      const uint32_t b8[8] = {wide_x, ONES2, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(tm + RB, b8);
+    }
+  };
+  // d pe of the tile whose pixel is gp: 16 columns R0[16, 32), back in true units
+  auto read_dpe = [&](int gp) {
+    uint32_t acc[16];
+    tmem_ld16_issue(tm + R0 + 16u, acc);
+    tmem_ld_wait();
+    if (gp >= pix) return;
+    if (a.d_pe_h != nullptr) {       // fp16, still in the chain's units
+      uint32_t h[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        h[c] = pack_h2_sat(__uint_as_float(acc[2 * c]), __uint_as_float(acc[2 * c + 1]));
+      uint4* dst = reinterpret_cast<uint4*>(stitched ? dpe_item + pe_off(gp) * (NPE * 2) : dpe_item + (uint32_t)gp * (uint32_t)(NPE * 2));
+      dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+      dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    } else {
+      float4* dst = reinterpret_cast<float4*>(stitched ? dpe_item + pe_off(gp) * (NPE * 4) : dpe_item + (uint32_t)gp * (uint32_t)(NPE * 4));
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        dst[c] = make_float4(unscale * __uint_as_float(acc[4 * c]), unscale * __uint_as_float(acc[4 * c + 1]),
+                             unscale * __uint_as_float(acc[4 * c + 2]), unscale * __uint_as_float(acc[4 * c + 3]));
+    }
+  };
 
+  if (g < ntiles) {
+    // the group's bias block (written once unless it carries inputs) and its first tile's inputs
+    if (!WIDE) {
+      const uint32_t ones8[8] = {ONES2, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(tm + RB, ones8);
+    }
+    pack_x0();
+    put_x0();
+    publish(false);
+    issue(0);
+  }
   for (int tile = g; tile < ntiles; tile += 2) {
     const int gp = tile * 128 + r;
     const bool valid = gp < pix;
+    const bool has_next = tile + 2 < ntiles;
     uint32_t cs[3][16];                           // cos(.) of the three sine layers, packed half2
-    // ---- X0 -> TMEM (R0)
-    {
-      uint32_t x0p[WIDE ? 24 : 16];                                      // the inputs as packed fp16 pairs
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        x0p[i] = (F == 16 && a.pe_half && i >= 8) ? xin[8 + i] : pack_h2(__uint_as_float(xin[2 * i]), __uint_as_float(xin[2 * i + 1]));
-      tmem_st16(tm + R0, reinterpret_cast<const uint32_t(&)[16]>(x0p));
-      if (WIDE) {          // third K block: inputs 32, 33, then the two ones that pick up the bias
-#pragma unroll
-        for (int i = 16; i < 24; ++i)
-          x0p[i] = 2 * i + 1 < IN ? pack_h2(__uint_as_float(xin[2 * i < IN ? 2 * i : 0]), __uint_as_float(xin[2 * i + 1 < IN ? 2 * i + 1 : 0]))
-                                  : (2 * i == IN ? ONES2 : 0u);
-        tmem_st8(tm + R0 + 16u, x0p + 16);
-      } else {
-        tmem_st8(tm + R0 + 16u, ones8);
-      }
+    // ---- Z0 of this tile is in flight (issued alone or with the previous tile's last stage, whose d pe comes back here)
+    wait_mma();
+    if (MODE != 0) {
+      if (tile > g) read_dpe(gp - 256);
+      // X0^T for dW0: its buffer was an operand of the previous tile's last stage until the wait above
+      store_p16(sbase + so + Sm::XT0, 0, x0p);
+      store_p16(sbase + so + Sm::XT0, 16, x0p + 8);
     }
-    publish(false);
-    issue(0);
     // ---- three sine layers: X_{l+1} = sin(acc + b') back into the accumulator's columns, fp16 copy of X_{l+1}^T
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
       const uint32_t reg = tm + ((l & 1) ? R0 : R1);                     // Z0 -> R1, Z1 -> R0, Z2 -> R1
-      wait_mma();
+      if (l > 0) wait_mma();
       uint32_t acc[32];
       tmem_ld32_issue(reg, acc);
       tmem_ld_wait();
@@ -621,8 +693,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         if (MODE != 0) store_p16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), 16 * h, xp + 8 * h);
       }
       tmem_st16(reg, xp);
-      if (l < 2) tmem_st8(reg + 16u, ones8);                             // the next sine layer's bias block
-      publish(MODE != 0);
+      publish(false);
       issue(l + 1);
     }
     // ---- output layer (on the tensor core), loss and dy; dZ2 = (dy W3^T) * cos in place of X3; dy^T, dZ2^T
@@ -650,7 +721,13 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       }
     }
     if (MODE == 0) {
-      if (tile + 2 < ntiles) load_x0(gp + 256, xin);
+      if (has_next) {
+        load_x0(gp + 256, xin);
+        pack_x0();
+        put_x0();
+        publish(false);
+        issue(0);
+      }
       continue;
     }
 #pragma unroll
@@ -672,14 +749,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       }
       tmem_st16(tm + R1, dzp);                                           // A operand of dX2
     }
-    publish(true);
+    publish(true);                                                       // covers X_0 .. X_3^T and dy^T as well
     issue(4, tile);
-    // ---- dZ1 (from R0, in place), dZ0 (from R1, in place) = data gradient * cos; X0^T reloaded for dW0
+    // ---- dZ1 (from R0, in place), dZ0 (from R1, in place) = data gradient * cos; the next tile's inputs join the last stage
 #pragma unroll
     for (int l = 1; l >= 0; --l) {
       const uint32_t reg = tm + (l == 1 ? R0 : R1);
-      if (l == 0) load_x0(gp, xin);                                      // in flight while the MMAs finish
+      // the next tile's inputs, in flight while the MMAs finish.  Unconditional (a pixel index past the end loads nothing)
+      // so that neither xin nor x0p is live across the rest of the loop body
+      if (l == 0) load_x0(has_next ? gp + 256 : pix, xin);
       wait_mma();
+      if (l == 0) pack_x0();
       uint32_t acc[32];
       tmem_ld32_issue(reg, acc);
       tmem_ld_wait();
@@ -691,51 +771,28 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           dzp[(16 * h + j) >> 1] = mul_h2(__uint_as_float(acc[16 * h + j]), __uint_as_float(acc[16 * h + j + 1]), cs[l][(16 * h + j) >> 1]);
         }
         store_p16(sbase + so + Sm::DZT, 16 * h, dzp + 8 * h);
-        if (l == 0) {
-          uint32_t xf[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            xf[j] = (F == 16 && a.pe_half && h == 1) ? xin[16 + j] : pack_h2(__uint_as_float(xin[16 * h + 2 * j]), __uint_as_float(xin[16 * h + 2 * j + 1]));
-          store_p16(sbase + so + (WIDE ? Sm::XT1 : Sm::XT3), 16 * h, xf);       // X1 / X2 are dead by now (34 inputs: both are reused)
-          if (WIDE && h == 1) {
-            // second atom of dW0's A operand: [x32, x33, 1, 0, ...] -- accumulator rows 32, 33 = the last two inputs, row 34 = bias
-            const uint32_t row = sbase + so + Sm::XT2 + pm_row;
-            const uint32_t w0p = pack_h2(__uint_as_float(xin[32]), __uint_as_float(xin[IN - 1]));
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)c ^ pm_x) << 4)),
-                           "r"(c == 0 ? w0p : 0u), "r"(c == 0 ? 0x00003c00u : 0u), "r"(0u), "r"(0u) : "memory");
-          }
-        }
       }
       tmem_st16(reg, dzp);
-      publish(true);
-      issue(l == 1 ? 5 : 6, tile);
-    }
-    // ---- the group's next tile's inputs travel while the last MMAs of this tile run
-    if (tile + 2 < ntiles) load_x0(gp + 256, xin);
-    // ---- d pe (16 columns of R0), back in true units
-    wait_mma();
-    {
-      uint32_t acc[16];
-      tmem_ld16_issue(tm + R0, acc);
-      tmem_ld_wait();
-      if (valid && a.d_pe_h != nullptr) {       // fp16, still in the chain's units
-        uint32_t h[8];
+      if (l == 0) {
+        if (WIDE) {
+          // second atom of dW0's A operand: [x32, x33, 1, 0, ...] -- accumulator rows 32, 33 = the last two inputs, row 34 = bias
+          // (over the dead X_2^T)
+          const uint32_t row = sbase + so + Sm::XT2 + pm_row;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          h[c] = pack_h2_sat(__uint_as_float(acc[2 * c]), __uint_as_float(acc[2 * c + 1]));
-        uint4* dst = reinterpret_cast<uint4*>(stitched ? dpe_item + pe_off(gp) * (NPE * 2) : dpe_item + (uint32_t)gp * (uint32_t)(NPE * 2));
-        dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
-        dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
-      } else if (valid) {
-        float4* dst = reinterpret_cast<float4*>(stitched ? dpe_item + pe_off(gp) * (NPE * 4) : dpe_item + (uint32_t)gp * (uint32_t)(NPE * 4));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[c] = make_float4(unscale * __uint_as_float(acc[4 * c]), unscale * __uint_as_float(acc[4 * c + 1]),
-                               unscale * __uint_as_float(acc[4 * c + 2]), unscale * __uint_as_float(acc[4 * c + 3]));
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)c ^ pm_x) << 4)),
+                         "r"(c == 0 ? wide_x : 0u), "r"(c == 0 ? 0x00003c00u : 0u), "r"(0u), "r"(0u) : "memory");
+        }
+        // R0[0, 16) (dZ1, consumed by stage 5) and the bias block (last read by stage 2) are free: the next tile's inputs
+        if (has_next) put_x0();
       }
+      publish(true);
+      issue(l == 1 ? 5 : 6, tile, has_next);
     }
+  }
+  if (MODE != 0 && g < ntiles) {                   // d pe of the group's last tile
+    wait_mma();
+    read_dpe((ntiles - 1 - ((ntiles - 1 - g) & 1)) * 128 + r);
   }
 
   PROF(5);
