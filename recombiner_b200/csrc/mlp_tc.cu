@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     const bool valid = gp < pix;
     const bool has_next = tile + 2 < ntiles;
     uint32_t cs[3][16];                           // cos(.) of the three sine layers, packed half2
+    float dy[OUT];                                // targets / output gradient first, then dy in the chain's units
     // ---- Z0 of this tile is in flight (issued alone or with the previous tile's last stage, whose d pe comes back here)
     wait_mma();
     if (MODE != 0) {
@@ -693,12 +694,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         if (MODE != 0) store_p16(sbase + so + (l == 0 ? Sm::XT1 : (l == 1 ? Sm::XT2 : Sm::XT3)), 16 * h, xp + 8 * h);
       }
       tmem_st16(reg, xp);
+      if (l == 2 && MODE != 0) {
+        // the pixel's targets (mode 1) or output gradient (mode 2): in flight under the output layer's round trip
+#pragma unroll
+        for (int k = 0; k < OUT; ++k)
+          dy[k] = !valid ? 0.f : (MODE == 1 ? __ldg(a.y + ((int64_t)row_item * pix + gp) * OUT + k)
+                                            : __ldg(a.dy + ((int64_t)item * pix + gp) * OUT + k));
+      }
       publish(false);
       issue(l + 1);
     }
     // ---- output layer (on the tensor core), loss and dy; dZ2 = (dy W3^T) * cos in place of X3; dy^T, dZ2^T
     wait_mma();
-    float dy[OUT];
     {
       uint32_t yv[16];
       tmem_ld16_issue(tm + R0, yv);
@@ -711,11 +718,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
         for (int k = 0; k < OUT; ++k) {
           if (MODE == 1) {
-            const float rr = valid ? __uint_as_float(yv[k]) + plain[96 + k] - __ldg(a.y + ((int64_t)row_item * pix + gp) * OUT + k) : 0.f;
+            const float rr = valid ? __uint_as_float(yv[k]) + plain[96 + k] - dy[k] : 0.f;
             sq = fmaf(rr, rr, sq);
             dy[k] = rr;
           } else {
-            dy[k] = valid ? gscale * __ldg(a.dy + ((int64_t)item * pix + gp) * OUT + k) : 0.f;
+            dy[k] *= gscale;
           }
         }
       }
@@ -759,21 +766,20 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       // so that neither xin nor x0p is live across the rest of the loop body
       if (l == 0) load_x0(has_next ? gp + 256 : pix, xin);
       wait_mma();
-      if (l == 0) pack_x0();
-      uint32_t acc[32];
-      tmem_ld32_issue(reg, acc);
-      tmem_ld_wait();
-      uint32_t dzp[16];
+      // two passes of 16 columns: 16 live accumulator registers while the next tile's 32 raw inputs are still in flight
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        uint32_t acc[16], dzp[8];
+        tmem_ld16_issue(reg + (uint32_t)(16 * h), acc);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          dzp[(16 * h + j) >> 1] = mul_h2(__uint_as_float(acc[16 * h + j]), __uint_as_float(acc[16 * h + j + 1]), cs[l][(16 * h + j) >> 1]);
-        }
-        store_p16(sbase + so + Sm::DZT, 16 * h, dzp + 8 * h);
+        for (int j = 0; j < 16; j += 2)
+          dzp[j >> 1] = mul_h2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), cs[l][(16 * h + j) >> 1]);
+        store_p16(sbase + so + Sm::DZT, 16 * h, dzp);
+        tmem_st8(reg + (uint32_t)(8 * h), dzp);
       }
-      tmem_st16(reg, dzp);
       if (l == 0) {
+        pack_x0();
         if (WIDE) {
           // second atom of dW0's A operand: [x32, x33, 1, 0, ...] -- accumulator rows 32, 33 = the last two inputs, row 34 = bias
           // (over the dead X_2^T)
@@ -809,15 +815,19 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     auto to_h = [](float v) { return fminf(fmaxf(v, -65504.f), 65504.f); };      // clamp: an overflow must not turn into inf
     const int j0 = g * 16;
     if (q <= 2) {
-      uint32_t acc[16];
+      // all four accumulator reads first, one wait: their latencies overlap instead of adding up
+      uint32_t acc_l[3][16], acc3[16];
+#pragma unroll
+      for (int l = 0; l < 3; ++l) tmem_ld16_issue(tm + TM_DW + (uint32_t)(l * 32 + j0), acc_l[l]);
+      if (g == 0) tmem_ld16_issue(tm + TM_DW + 96, acc3);
+      tmem_ld_wait();
       const float sc = w0 * unscale * (gwh ? a.d_wt_h_scale : 1.f);
       const float sc3 = unscale * (gwh ? a.d_wt_h_scale : 1.f);
       const bool wrow_n = q < 2 && lane < 16, brow_n = q == 2 && lane == 0;
       const int irow_n = q * 16 + lane;
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
-        tmem_ld16_issue(tm + TM_DW + (uint32_t)(l * 32 + j0), acc);
-        tmem_ld_wait();
+        const uint32_t (&acc)[16] = acc_l[l];
         const int off = l == 0 ? off0 : (l == 1 ? off1 : off2);
         // 34 inputs: layer 0 has two more weight rows (accumulator rows 32, 33 = lanes 64, 65) and its bias in row 34
         const bool wide0 = WIDE && l == 0;
@@ -841,8 +851,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         }
       }
       if (g == 0) {
-        tmem_ld16_issue(tm + TM_DW + 96, acc);
-        tmem_ld_wait();
+        const uint32_t (&acc)[16] = acc3;
         const bool wrow = wrow_n, brow = brow_n;
         const int irow = irow_n;
         if (wrow) {
