@@ -338,6 +338,18 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   };
   uint32_t xin[IN];
   if (g < ntiles) load_x0(g * 128 + r, xin);    // first tile's inputs travel under the weight staging
+#ifndef RCB_MLP_NO_L2_PREFETCH
+  {
+    // The weight samples were written a whole upsampler pass ago and have left L2 by now: every CTA starts on ~13 KB of
+    // DRAM misses.  Ask L2 for the rows of the CTA that will run about one CTA lifetime from now (two per SM are resident).
+    int sms;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(sms));
+    const int ahead = item + 2 * sms;
+    const int lines = (a.ld_w * 4 + 127) / 128;
+    if (ahead < a.items && (int)threadIdx.x < lines)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.wt + (int64_t)ahead * a.ld_w) + threadIdx.x * 128));
+  }
+#endif
 
   PROF(1);
   if ((sbase & 1023u) != 0u) __trap();                     // the swizzled tiles assume a 1024-B aligned window
