@@ -774,9 +774,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
     for (int l = 1; l >= 0; --l) {
       const uint32_t reg = tm + (l == 1 ? R0 : R1);
-      // the next tile's inputs, in flight while the MMAs finish.  Unconditional (a pixel index past the end loads nothing)
-      // so that neither xin nor x0p is live across the rest of the loop body
-      if (l == 0) load_x0(has_next ? gp + 256 : pix, xin);
+      // the next tile's inputs: requested a whole backward stage before they are packed (one stage later they still cost
+      // 4 % of the warp time in front of the first pack; yet another stage earlier the 32 extra live registers cost more
+      // than the latency).  Unconditional (a pixel index past the end loads nothing) so that neither xin nor x0p is live
+      // across the rest of the loop body
+      if (l == 1) load_x0(has_next ? gp + 256 : pix, xin);
       wait_mma();
       // two passes of 16 columns: 16 live accumulator registers while the next tile's 32 raw inputs are still in flight
 #pragma unroll
