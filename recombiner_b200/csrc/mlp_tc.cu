@@ -177,6 +177,29 @@ __device__ __forceinline__ uint32_t mul_h2(float lo, float hi, uint32_t c) {
   return pack_h2(lo * c2.x, hi * c2.y);
 }
 
+// Predicated read-only loads whose destination registers are zeroed BEFORE the load is issued.  The form
+// `v = ok ? __ldg(p) : 0` compiles to the load followed by a predicated zeroing of the same registers, and a write to the
+// destination of a load in flight waits for the load even when its predicate is off: the thread sat at the load site
+// for the whole memory latency (2.6 % of all stall samples of the kernel) instead of at the first use.
+__device__ __forceinline__ void ldg16_if(bool ok, const void* p, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+  x = y = z = w = 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%5];\n\t"
+      "}" : "+r"(x), "+r"(y), "+r"(z), "+r"(w) : "r"((uint32_t)ok), "l"(p));
+}
+__device__ __forceinline__ void ldg4_if(bool ok, const void* p, uint32_t& x) {
+  x = 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q ld.global.nc.u32 %0, [%2];\n\t"
+      "}" : "+r"(x) : "r"((uint32_t)ok), "l"(p));
+}
+
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -293,37 +316,27 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
         if (NFQ % 4 == 0) {
 #pragma unroll
           for (int c = 0; c < NFQ / 4; ++c) {
-            const float4 cs4 = __ldg(reinterpret_cast<const float4*>(row) + c);
-            const float4 sn4 = __ldg(reinterpret_cast<const float4*>(row + NFQ) + c);
-            v[ax * NFQ + 4 * c] = __float_as_uint(cs4.x); v[ax * NFQ + 4 * c + 1] = __float_as_uint(cs4.y);
-            v[ax * NFQ + 4 * c + 2] = __float_as_uint(cs4.z); v[ax * NFQ + 4 * c + 3] = __float_as_uint(cs4.w);
-            v[D * NFQ + ax * NFQ + 4 * c] = __float_as_uint(sn4.x); v[D * NFQ + ax * NFQ + 4 * c + 1] = __float_as_uint(sn4.y);
-            v[D * NFQ + ax * NFQ + 4 * c + 2] = __float_as_uint(sn4.z); v[D * NFQ + ax * NFQ + 4 * c + 3] = __float_as_uint(sn4.w);
+            const int ic = ax * NFQ + 4 * c, is = D * NFQ + ax * NFQ + 4 * c;
+            ldg16_if(ok, reinterpret_cast<const float4*>(row) + c, v[ic], v[ic + 1], v[ic + 2], v[ic + 3]);
+            ldg16_if(ok, reinterpret_cast<const float4*>(row + NFQ) + c, v[is], v[is + 1], v[is + 2], v[is + 3]);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < NFQ; ++j) {
-            v[ax * NFQ + j] = __float_as_uint(__ldg(row + j));
-            v[D * NFQ + ax * NFQ + j] = __float_as_uint(__ldg(row + NFQ + j));
+            ldg4_if(ok, row + j, v[ax * NFQ + j]);
+            ldg4_if(ok, row + NFQ + j, v[D * NFQ + ax * NFQ + j]);
           }
         }
       }
-      if (!ok) {
-#pragma unroll
-        for (int i = 0; i < F; ++i) v[i] = 0u;
-      }
     } else {
 #pragma unroll
-      for (int i = 0; i < F; ++i) v[i] = ok ? __float_as_uint(__ldg(xt + (int64_t)i * pix + gp)) : 0u;
+      for (int i = 0; i < F; ++i) ldg4_if(ok, xt + (int64_t)i * pix + (ok ? gp : 0), v[i]);
     }
     if (F == 16 && a.pe_half) {      // fp16 positional encodings: v[16..23] are already the packed pairs the chain operand needs
       const uint4* p = reinterpret_cast<const uint4*>(stitched ? pe_item + (ok ? pe_off(gp) : 0) * (NPE * 2)
                                                                : pe_item + (uint32_t)(ok ? gp : 0) * (uint32_t)(NPE * 2));
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
-        v[16 + c * 4] = t4.x; v[17 + c * 4] = t4.y; v[18 + c * 4] = t4.z; v[19 + c * 4] = t4.w;
-      }
+      for (int c = 0; c < 2; ++c) ldg16_if(ok, p + c, v[16 + c * 4], v[17 + c * 4], v[18 + c * 4], v[19 + c * 4]);
 #pragma unroll
       for (int c = 24; c < 32; ++c) v[c] = 0u;
       return;
@@ -331,10 +344,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     const uint4* p = reinterpret_cast<const uint4*>(stitched ? pe_item + (ok ? pe_off(gp) : 0) * (NPE * 4)
                                                              : pe_item + (uint32_t)(ok ? gp : 0) * (uint32_t)(NPE * 4));
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 t4 = ok ? __ldg(p + c) : make_uint4(0u, 0u, 0u, 0u);
-      v[F + c * 4] = t4.x; v[F + 1 + c * 4] = t4.y; v[F + 2 + c * 4] = t4.z; v[F + 3 + c * 4] = t4.w;
-    }
+    for (int c = 0; c < 4; ++c) ldg16_if(ok, p + c, v[F + c * 4], v[F + 1 + c * 4], v[F + 2 + c * 4], v[F + 3 + c * 4]);
   };
   uint32_t xin[IN];
   if (g < ntiles) load_x0(g * 128 + r, xin);    // first tile's inputs travel under the weight staging
