@@ -718,10 +718,14 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
       tmem_st16(reg, xp);
       if (l == 2 && MODE != 0) {
         // the pixel's targets (mode 1) or output gradient (mode 2): in flight under the output layer's round trip
+        const float* src = MODE == 1 ? a.y + ((int64_t)row_item * pix + (valid ? gp : 0)) * OUT
+                                     : a.dy + ((int64_t)item * pix + (valid ? gp : 0)) * OUT;
 #pragma unroll
-        for (int k = 0; k < OUT; ++k)
-          dy[k] = !valid ? 0.f : (MODE == 1 ? __ldg(a.y + ((int64_t)row_item * pix + gp) * OUT + k)
-                                            : __ldg(a.dy + ((int64_t)item * pix + gp) * OUT + k));
+        for (int k = 0; k < OUT; ++k) {
+          uint32_t t;
+          ldg4_if(valid, src + k, t);
+          dy[k] = __uint_as_float(t);
+        }
       }
       publish(false);
       issue(l + 1);
