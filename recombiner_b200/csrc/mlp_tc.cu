@@ -248,6 +248,15 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   const int prof_slot = (blockIdx.x == 3000 && (threadIdx.x == 32 || threadIdx.x == 160)) ? (threadIdx.x == 32 ? 0 : 1) : -1;
 #endif
   constexpr int HID = 32, NPE = 16, IN = F + NPE;
+  // Early commits.  Stage 5: the chain product dX1 is committed before the stage's weight-gradient MMAs are even issued,
+  // so its epilogue neither waits for them nor for the other group's turn.  That epilogue then must not write into dZ^T,
+  // which dW1 is still reading: dZ0^T goes over X3^T, whose last reader (dW3, stage 4) is complete by then.  Stage 6
+  // likewise commits after d pe and the next tile's first product; dW0 follows uncommitted (the group's next commit covers
+  // it) and the next tile's X0^T, which would overwrite its operand, is stored one stage later.  (Stage 4 has no free
+  // buffer for dZ1^T; with a barrier of their own for the weight-gradient MMAs and three more waits per tile the same idea
+  // measured slower.)
+  constexpr bool EARLY5 = true, EARLY6 = true;
+  constexpr int DZ0 = EARLY5 ? Sm::XT3 : Sm::DZT;
   constexpr bool WIDE = IN > 32;
   static_assert(F == 16 || F == 18, "16 or 18 Fourier features");
   constexpr int off0 = 0, off1 = HID * (IN + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
@@ -566,6 +575,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           break;
         case 5:
           chain(R1, R0, Sm::WB + Sm::WT, t32);                                    // dX1 = dZ1 W1^T
+          if (EARLY5) umma_commit(&bar_mma[g]);
 #ifndef RCB_NO_TURN
           while (wg_turn[1] != tile) {}
 #endif
@@ -574,19 +584,24 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           break;
         default:
           chain(R0 + 16u, R1, Sm::WB, t16);                                     // d pe = dZ0 W0[pe rows]^T  -> R0[16, 32)
+          if (EARLY6 && next) {
+            chain(R1, R0, Sm::WF, t32);
+            bias(R1, WIDE ? Sm::WF0B : Sm::WBI, t32);
+            umma_commit(&bar_mma[g]);
+          }
 #ifndef RCB_NO_TURN
           while (wg_turn[2] != tile) {}
 #endif
-          if (WIDE) wgrad(TM_DW, so + Sm::XT0, so + Sm::DZT, h32, so + Sm::XT2, false);  // dW0 = X0^T dZ0, 34 inputs + bias row
-          else wgrad(TM_DW, so + Sm::XT0, so + Sm::DZT, h32);                   // dW0 = X0^T dZ0
+          if (WIDE) wgrad(TM_DW, so + Sm::XT0, so + DZ0, h32, so + Sm::XT2, false);  // dW0 = X0^T dZ0, 34 inputs + bias row
+          else wgrad(TM_DW, so + Sm::XT0, so + DZ0, h32);                       // dW0 = X0^T dZ0
           wg_turn[2] = tile + 1;
-          if (next) {                                                           // the next tile's Z0 = X0 W0 + b0
+          if (next && !EARLY6) {                                                // the next tile's Z0 = X0 W0 + b0
             chain(R1, R0, Sm::WF, t32);
             bias(R1, WIDE ? Sm::WF0B : Sm::WBI, t32);
           }
           break;
       }
-      umma_commit(&bar_mma[g]);
+      if (!(EARLY5 && stage == 5) && !(EARLY6 && stage == 6 && next)) umma_commit(&bar_mma[g]);
     }
     ph_ready ^= 1;
     __syncwarp();
@@ -693,14 +708,20 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
     if (MODE != 0) {
       if (tile > g) read_dpe(gp - 256);
       // X0^T for dW0: its buffer was an operand of the previous tile's last stage until the wait above
-      store_p16(sbase + so + Sm::XT0, 0, x0p);
-      store_p16(sbase + so + Sm::XT0, 16, x0p + 8);
+      if (!EARLY6) {
+        store_p16(sbase + so + Sm::XT0, 0, x0p);
+        store_p16(sbase + so + Sm::XT0, 16, x0p + 8);
+      }
     }
     // ---- three sine layers: X_{l+1} = sin(acc + b') back into the accumulator's columns, fp16 copy of X_{l+1}^T
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
       const uint32_t reg = tm + ((l & 1) ? R0 : R1);                     // Z0 -> R1, Z1 -> R0, Z2 -> R1
       if (l > 0) wait_mma();
+      if (EARLY6 && l == 1 && MODE != 0) {        // the previous tile's dW0 has retired with this stage's commit
+        store_p16(sbase + so + Sm::XT0, 0, x0p);
+        store_p16(sbase + so + Sm::XT0, 16, x0p + 8);
+      }
       uint32_t acc[32];
       tmem_ld32_issue(reg, acc);
       tmem_ld_wait();
@@ -803,7 +824,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2)
           dzp[j >> 1] = mul_h2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), cs[l][(16 * h + j) >> 1]);
-        store_p16(sbase + so + Sm::DZT, 16 * h, dzp);
+        store_p16(sbase + so + (l == 0 ? DZ0 : Sm::DZT), 16 * h, dzp);
         tmem_st8(reg + (uint32_t)(8 * h), dzp);
       }
       if (l == 0) {
