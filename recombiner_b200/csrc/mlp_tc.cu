@@ -4,10 +4,10 @@
 // trip -- and two CTAs per SM, i.e. four tiles in flight per SM.
 //
 // What makes four tiles fit:
-//  * the chain  Z_l = X_l W_l,  y = X_3 W_3,  dX_l = dZ_l W_l^T  (tcgen05 kind::tf32, A operand in
-//    TMEM) ping-pongs between two 32-column TMEM regions per tile and updates them in place
-//    (tcgen05.ld -> sin / *cos -> tcgen05.st into the same lane and columns), so a tile owns 64
-//    TMEM columns instead of 128;
+//  * the chain  Z_l = X_l W_l,  y = X_3 W_3,  dX_l = dZ_l W_l^T  (tcgen05 kind::f16, the A operand as
+//    packed fp16 pairs in TMEM) ping-pongs between two 32-column TMEM regions per tile and updates
+//    them in place (tcgen05.ld -> sin / *cos -> tcgen05.st into the same lane and columns), so a
+//    tile owns 64 TMEM columns instead of 128;
 //  * the activations the weight gradients need later are kept as feature-major fp16 copies in
 //    shared memory (X in [-1,1]: fp16 keeps the same 10-bit mantissa TF32 does), written by the
 //    forward epilogue while the values are in registers; dW_l = X_l^T dZ_l is a kind::f16 MMA
@@ -20,8 +20,9 @@
 // as the last one of the current tile (d pe = dZ0 W0^T), whose result is read back at the top of the next tile; the inputs
 // X0 are kept as an fp16 copy in shared memory for dW0 (no second load), and the constant (1, 1) block that picks up the
 // biases has TMEM columns of its own (written once).
-// As in the second design the A tiles carry a row of ones (accumulator row 32 = bias gradient),
-// w0 is folded into the staged weights, and TF32 rounding is +0x1000 on the fp32 pattern.
+// The chain products of the last two backward stages are committed before their weight-gradient MMAs (early commits,
+// see EARLY5 / EARLY6 in the kernel).  The A tiles of the weight gradients carry a row of ones (accumulator row 32 =
+// bias gradient) and w0 is folded into the staged weights.
 // Reference semantics: test_model.py:347-355, 624-627; weight layout :269-280.
 #include <cuda_fp16.h>
 
