@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
   // buffer for dZ1^T; with a barrier of their own for the weight-gradient MMAs and three more waits per tile the same idea
   // measured slower.)
   constexpr bool EARLY5 = true, EARLY6 = true;
-  constexpr int DZ0 = EARLY5 ? Sm::XT3 : Sm::DZT;
+  // dW3 (eight N = 16 MMAs) leaves the batch of stage 4, the longest wait of a tile, for the uncommitted tail of stage 5;
+  // its operand X3^T must then survive the last epilogue, so dZ0^T goes over X2^T instead (32-input form only: the
+  // 34-input form keeps its second dW0 atom there)
+  constexpr bool DW3_LATE = IN <= 32;
+  constexpr int DZ0 = DW3_LATE ? Sm::XT2 : (EARLY5 ? Sm::XT3 : Sm::DZT);
   constexpr bool WIDE = IN > 32;
   static_assert(F == 16 || F == 18, "16 or 18 Fourier features");
   constexpr int off0 = 0, off1 = HID * (IN + 1), off2 = off1 + HID * (HID + 1), off3 = off2 + HID * (HID + 1);
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
 #ifndef RCB_NO_TURN
           while (wg_turn[0] != tile) {}
 #endif
-          wgrad_dy(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, h16);                // dW3 = X3^T dy
+          if (!DW3_LATE) wgrad_dy(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, h16);   // dW3 = X3^T dy
           wgrad(TM_DW + 64, so + Sm::XT2, so + Sm::DZT, h32);                   // dW2 = X2^T dZ2
           wg_turn[0] = tile + 1;
           break;
@@ -581,6 +585,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mlp_tc_kernel(rcb_mlp_args a) {
           while (wg_turn[1] != tile) {}
 #endif
           wgrad(TM_DW + 32, so + Sm::XT1, so + Sm::DZT, h32);                   // dW1 = X1^T dZ1
+          if (DW3_LATE) wgrad_dy(TM_DW + 96, so + Sm::XT3, so + Sm::DZ3, h16);    // dW3 = X3^T dy
           wg_turn[1] = tile + 1;
           break;
         default:
