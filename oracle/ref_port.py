@@ -18,7 +18,7 @@ from . import recombiner_oracle as orc
 
 
 class OracleCompressor:
-    def __init__(self, case: dict, seed: int = 42, lr: float = 2e-4, kl_adjust_gap: int = 10):
+    def __init__(self, case: dict, seed: int = 42, lr: float = 2e-4, kl_adjust_gap: int = 10, bits: float = 16.0):
         self.shape = case["shape"]
         if self.shape.patch:
             raise NotImplementedError("port covers the non-patch modalities used by the bench")
@@ -33,6 +33,8 @@ class OracleCompressor:
         self.A, self.w_up = case["A"], case["w_up"]
         self.x, self.y = case["x"], case["y"]
         self.seed, self.lr, self.gap = seed, lr, kl_adjust_gap
+        # bits per block (test_model.py:98): candidates per block = ceil(2 ** bits), also the annealing target
+        self.bits, self.n_cand = float(bits), int(np.ceil(2 ** bits))
         self.rows = self.lv.loc.shape[0]
         self.W, self.Ln = self.shape.n_weights, self.shape.n_latent
         self._tables = {}
@@ -53,7 +55,7 @@ class OracleCompressor:
         y_pred = orc.predict(self.x, self.lv, self.A, self.w_up, self.shape, eps, S)
         loss = orc.fit_loss(y_pred, self.y) + orc.weighted_kl(self.lv, self.beta)
         if epoch % self.gap == 0:
-            self.beta = orc.anneal_beta(self.beta, orc.group_kl_nats(self.lv), self.coded)
+            self.beta = orc.anneal_beta(self.beta, orc.group_kl_nats(self.lv), self.coded, bits=self.bits)
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()
@@ -63,12 +65,12 @@ class OracleCompressor:
     def table(self, block: int):
         D = int(self.lv.group_end[block] - self.lv.group_start[block])
         if block not in self._tables:                          # cached per block like test_model.py:459-471
-            self._tables[block] = orc.candidate_table(D, 65536, self.seed)
+            self._tables[block] = orc.candidate_table(D, self.n_cand, self.seed)
         return self._tables[block]
 
     def gumbel(self):
         if self._gumbel is None:
-            self._gumbel = orc.gumbel_sequence(self.seed)
+            self._gumbel = orc.gumbel_sequence(self.seed, self.n_cand)
         return self._gumbel
 
     def code_block(self, row: int, block: int):
