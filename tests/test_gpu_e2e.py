@@ -106,6 +106,68 @@ def test_short_schedule_matches_oracle_port_statistically():
     np.testing.assert_allclose(kl_gpu, kl_cpu, rtol=0.1)
 
 
+def test_coding_schedule_on_the_ports_noise_follows_the_port():
+    """The progressive-coding schedule WITHOUT the statistics: the fp32 path is fed the port's own noise (torch's
+    epoch-seeded CPU draws, uploaded per step), so fit, block choice, REC and the fine-tune steps between rounds can be
+    compared directly with the port -- which tests/test_oracle_trajectory.py shows to equal the unmodified reference bit
+    for bit through the same schedule.  fp32 rounding differs between the two (FFMA order, softplus), so the posterior is
+    compared at 1e-4 and the discrete decisions must agree for at least nine picks in ten (a near-tie between two
+    candidates may legitimately flip); the fully coded reconstructions within 0.05 dB."""
+    from oracle import cases
+    from oracle.ref_port import OracleCompressor
+    from recombiner_b200.utils import batch_PSNR
+    from tests.helpers import product_test_model
+    rows, n_fit, n_finetune, bits = 2, 30, 3, 12.0
+    case = cases.make_fit_case("cifar", rows, 5, coded_frac=0.0, total_bits=96.0)
+    L = case["lvl1"]
+    L["beta"] = torch.full_like(L["beta"], 1e-5)
+    L["loc"] = L["p_loc"][None].repeat(rows, 1)
+    L["log_scale"] = torch.full_like(L["log_scale"], -4.0)
+    G = int(L["n_groups"])
+    m = product_test_model(case, "cifar")
+    m.bit_per_group = bits
+    oc = OracleCompressor(case, bits=bits)
+    x, y = case["x"].cuda(), case["y"].cuda()
+    cfg = dict(lr=2e-4, b1=0.9, b2=0.999, eps=1e-8)
+    m._lv.reset_adam()
+
+    def both(ep):
+        eps = oc.draw_eps(ep, 5)
+        m.fit_step(x, y, ep, cfg, 5, eps=eps)
+        oc.fit_step(ep, 5, eps=eps)
+
+    def dloc():
+        return float((m._lv.loc.detach().cpu() - oc.lv.loc.detach()).abs().max())
+
+    for ep in range(n_fit):
+        both(ep)
+    d_fit = dloc()
+    same_block, same_idx, picks = 0, 0, 0
+    for rnd in range(G):
+        blocks = m.compress_round().cpu().numpy().tolist()
+        chosen = oc.compress_round()
+        oc.new_optimizer()
+        m._lv.reset_adam()
+        for ep in range(n_finetune):
+            both(ep)
+        idx_gpu = np.asarray(m.compressed_idx_groupwise)
+        for r in range(rows):
+            picks += 1
+            same_block += int(blocks[r] == chosen[r])
+            same_idx += int(blocks[r] == chosen[r] and idx_gpu[r, chosen[r]] == oc.idx[r, chosen[r]])
+    assert bool(m._lv.coded.all()) and bool(oc.coded.all())
+    with torch.no_grad():
+        yp = m.predict(x, random_seed=0).cpu().numpy()
+    yo = oc.reconstruct().numpy()[:, 0]
+    p_gpu = float(batch_PSNR(case["y"].numpy(), yp, True).mean())
+    p_cpu = float(batch_PSNR(case["y"].numpy(), yo, True).mean())
+    print(f"\n[coding schedule on shared noise] max|dloc| after fit {d_fit:.3e}, after coding {dloc():.3e}; "
+          f"same block {same_block}/{picks}, same index {same_idx}/{picks}; PSNR {p_gpu:.4f} vs {p_cpu:.4f} dB")
+    assert d_fit <= 1e-4
+    assert same_block >= 0.9 * picks and same_idx >= 0.9 * picks
+    assert abs(p_gpu - p_cpu) <= 0.05
+
+
 def test_patch_prior_training_and_compression_roundtrip(tmp_path):
     """Patch modality (audio shape, 2 clips = 120 rows) through prior training, the checkpoint
     stream with its level-2/3 groupings, and a short compression: plumbing + decode."""
